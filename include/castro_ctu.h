@@ -1,0 +1,214 @@
+/*
+ * castro_ctu.h -- C ABI of the B200-native CTU-PPM hydro hot path.
+ *
+ * This is the drop-in boundary for the ONE hot path of AMReX-Astro/Castro that this repository
+ * re-implements:   advance_status Castro::construct_ctu_hydro_source(Real time, Real dt)
+ *                  (decl  Source/hydro/Castro_hydro.H:34, body Source/hydro/Castro_ctu_hydro.cpp:17-1496,
+ *                   sole caller Castro::do_advance_ctu, Source/driver/Castro_advance_ctu.cpp:85)
+ * plus the CFL reduction  timestep::estdt<timestep::hydro>  (Source/driver/timestep.H:45-157,
+ * caller Castro::estTimeStep, Source/driver/Castro.cpp:1637) and the per-step state cleaning /
+ * ghost filling that the N-step parity contract depends on (clean_state, Castro.cpp:4537-4577;
+ * FillPatch + physical BCs, Castro_advance.cpp:167-170).
+ *
+ * Conventions
+ *   - plain C types only; every pointer inside a ctu_fab_t is a DEVICE pointer owned by the caller;
+ *   - ctu_fab_t is layout-identical to amrex::Array4<Real> (external/amrex/Src/Base/AMReX_Array4.H:922-975):
+ *         p[(i-lo[0]) + (j-lo[1])*nx + (k-lo[2])*nx*ny + n*nx*ny*nz],  nx = hi[0]-lo[0]+1, ...
+ *     i.e. Fortran order, i fastest, component slowest, all FP64;
+ *   - component order is Castro's (Source/driver/_variables): URHO UMX UMY UMZ UEDEN UEINT UTEMP
+ *     [UFA.. nadv] [UFS.. nspec] [UFX.. naux];
+ *   - functions return 0 on success, >0 = advance_status-like soft failure (bit mask CTU_STATUS_*),
+ *     <0 = fatal (bad arguments, CUDA error); nothing aborts;
+ *   - all work is enqueued on the cudaStream_t passed as `void* stream` (0 = legacy default stream);
+ *     functions that return scalars to the host synchronise that stream before returning.
+ *   - there is NO CPU fallback: if no CUDA device is present every compute entry point returns
+ *     CTU_ERR_NO_DEVICE.
+ */
+#ifndef CASTRO_CTU_H
+#define CASTRO_CTU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTU_MAX_SPEC 16   /* max (nspec), (naux), (nadv) each */
+#define CTU_NGROW 4       /* NUM_GROW, Source/driver/castro_limits.H:12 */
+#define CTU_NGROW_SRC 3   /* NUM_GROW_SRC, castro_limits.H:22 */
+
+/* error codes (<0) */
+#define CTU_ERR_BAD_ARG    (-1)
+#define CTU_ERR_NO_DEVICE  (-2)
+#define CTU_ERR_CUDA       (-3)
+#define CTU_ERR_NOMEM      (-4)
+#define CTU_ERR_UNSUPPORTED (-5)
+#define CTU_ERR_IO         (-6)
+
+/* soft status bits (>0), mirror advance_status.reason (Source/driver/Castro.H:113-118) */
+#define CTU_STATUS_INVALID_DENSITY  1   /* "invalid density"  Castro.cpp:3390-3393 */
+#define CTU_STATUS_INVALID_X        2   /* "invalid X"        Castro.cpp:3395-3398 */
+#define CTU_STATUS_NAN              4   /* check_for_nan      Castro.cpp:4510-4532 */
+#define CTU_STATUS_DT_PRE           8   /* "pre-advance timestep validity check failed"  Castro_advance.cpp:244 */
+#define CTU_STATUS_DT_POST         16   /* "post-advance timestep validity check failed" Castro_advance.cpp:302 */
+
+/* amrex::Array4<Real>-compatible view */
+typedef struct ctu_fab_t {
+    double* p;
+    int lo[3];
+    int hi[3];
+    int ncomp;
+} ctu_fab_t;
+
+/* subset of amrex::GeometryData + Castro's phys_bc (Castro.cpp:227-228) */
+typedef struct ctu_geom_t {
+    int domlo[3], domhi[3];
+    double dx[3];
+    double problo[3], probhi[3];
+    int coord;            /* 0 = Cartesian (only value supported in 3-D) */
+    int periodic[3];
+    int lo_bc[3], hi_bc[3];   /* 0 interior, 1 inflow, 2 outflow, 3 symmetry, 4 slipwall, 5 noslipwall */
+} ctu_geom_t;
+
+/* castro.* (Source/driver/_cpp_parameters), eos.* and network table values read by the hot path */
+typedef struct ctu_params_t {
+    /* hydrodynamics category, _cpp_parameters:36-297 */
+    int ppm_type;                  /* 1 (PPM) only */
+    int riemann_solver;            /* 0 = CGF (riemannus), 2 = HLLC */
+    int use_flattening;
+    int ppm_do_limiting;
+    int hybrid_riemann;            /* 0 only */
+    int transverse_use_eos;
+    int transverse_reset_density;
+    int transverse_reset_rhoe;
+    int limit_fluxes_on_small_dens; /* 0 only */
+    int first_order_hydro;
+    int ppm_temp_fix;              /* 0 only */
+    int use_pslope;                /* 0 only */
+    int ppm_well_balanced;         /* 0 only */
+    int source_term_predictor;
+    double difmag;
+    double small_dens, small_temp, small_pres, small_ener;
+    double dual_energy_eta1, dual_energy_eta2;
+    double abundance_failure_tolerance, abundance_failure_rho_cutoff;
+    double retry_small_density_cutoff;
+    double T_guess;
+    /* timestep control, _cpp_parameters:300-379 */
+    double cfl, init_shrink, change_max, max_dt, fixed_dt, initial_dt;
+    int check_dt_before_advance, check_dt_after_advance;
+    /* eos.* (external/Microphysics/EOS/gamma_law/_parameters) */
+    int eos_kind;                  /* 0 = gamma_law */
+    double eos_gamma;
+    int eos_assume_neutral;
+    /* network (general_null .net file -> network_properties.H) */
+    double small_x;                /* network.small_x */
+    int nspec, naux, nadv;
+    double aion[CTU_MAX_SPEC], zion[CTU_MAX_SPEC];
+} ctu_params_t;
+
+/* opaque scratch arena (replaces The_Async_Arena() temporaries of Castro_ctu_hydro.cpp:147-189) */
+typedef struct ctu_workspace ctu_workspace_t;
+
+/* ---- library / parameters ------------------------------------------------------------------ */
+const char* ctu_version(void);
+int  ctu_device_count(void);                               /* 0 if no usable CUDA device */
+void ctu_params_defaults(ctu_params_t* p);                 /* _cpp_parameters defaults, gammalaw.net */
+/* Castro::variableSetUp small_* / eos_init logic, Source/driver/Castro_setup.cpp:226-285 */
+int  ctu_params_finalize(ctu_params_t* p);
+int  ctu_num_state(const ctu_params_t* p);                 /* NUM_STATE = 7 + nadv + nspec + naux */
+
+/* ---- workspace ----------------------------------------------------------------------------- */
+/* max_bytes: upper bound on device scratch (0 = library default); the advance works through the box
+ * in z-slabs sized to fit (the role castro.hydro_memory_footprint_ratio plays, Castro_ctu_hydro.cpp:99-126). */
+int  ctu_workspace_create(ctu_workspace_t** ws, size_t max_bytes);
+void ctu_workspace_destroy(ctu_workspace_t* ws);
+size_t ctu_workspace_bytes(const ctu_workspace_t* ws);     /* bytes currently allocated */
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+/*
+ * Replaces the MFIter loop of Castro::construct_ctu_hydro_source (Castro_ctu_hydro.cpp:193-1407) for ONE
+ * box, followed (optionally) by the epilogue of that function and of the step:
+ *     check_for_negative_density (Castro_ctu_hydro.cpp:1436) -> n_bad[0] (rho), n_bad[1] (X)
+ *     clean_state(S_new)         (Castro_ctu_hydro.cpp:1444)           if do_clean != 0
+ *     estdt<hydro>(S_new)        (Castro_advance.cpp:298, Castro.cpp:1775) if dt_est != NULL
+ * Inputs  Sborder : NUM_STATE comps, must cover grow(valid, 4), already ghost-filled + clean_state'd
+ *         old_src, src_corr : NSRC=7 comps covering grow(valid,3), or NULL (== all zero, pure hydro)
+ * In/out  S_new   : NUM_STATE comps covering valid; on entry holds Sborder's valid data (+ dt*old_src),
+ *                   exactly like the reference (Castro_sources.cpp:627); may alias nothing else.
+ *                   If S_new == NULL ... not allowed.
+ * Outputs flux[d] : optional (NULL allowed) nodal-in-d, NUM_STATE comps, `+=` dt*A*F  (Castro_ctu_hydro.cpp:1297)
+ *         mass_flux[d] : optional, 1 comp, `=` dt*A*F(URHO)                        (Castro_ctu_hydro.cpp:1333)
+ *         dt_est  : HOST pointer; min over valid zones of dx_d/(c+|u_d|)  (NOT multiplied by cfl), dt_loc = (i,j,k)
+ *         n_bad   : HOST int[2]
+ * Returns status bits (0 ok).
+ */
+int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_geom_t* geom,
+                      const int valid_lo[3], const int valid_hi[3],
+                      const ctu_fab_t* Sborder, const ctu_fab_t* old_src, const ctu_fab_t* src_corr,
+                      ctu_fab_t* S_new, ctu_fab_t* const flux[3], ctu_fab_t* const mass_flux[3],
+                      double dt, int do_clean, double* dt_est, int dt_loc[3], int n_bad[2],
+                      void* stream);
+
+/* timestep::estdt<hydro> on one box (timestep.H:64-157): *dt_min = min_d dx_d/(c+|u_d|) over [lo,hi] */
+int ctu_estdt(const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3], const int hi[3],
+              const ctu_fab_t* S, double* dt_min, int ijk[3], void* stream);
+
+/* Castro::clean_state on [lo,hi] of S, applied `npass` times in sequence (Castro.cpp:4537-4577):
+ * enforce_min_density -> normalize_species -> reset_internal_energy -> EOS temperature. */
+int ctu_clean_state(const ctu_params_t* par, const int lo[3], const int hi[3], ctu_fab_t* S,
+                    int npass, void* stream);
+
+/* Fill the ghost zones of S (which covers grow(valid,ng)) that lie outside the PROBLEM DOMAIN or that wrap
+ * periodically onto this same box: periodic copy first, then physical BCs
+ * (foextrap / reflect_even / reflect_odd, Source/driver/Castro_setup.cpp:36-61,
+ *  external/amrex/Src/Base/AMReX_FilCC_3D_C.H:39-201).  Ghost zones owned by OTHER boxes are left alone
+ * (they are filled by ctu_halo_unpack). */
+int ctu_fill_boundary(const ctu_params_t* par, const ctu_geom_t* geom, const int valid_lo[3],
+                      const int valid_hi[3], ctu_fab_t* S, int ng, void* stream);
+
+/* Halo exchange building blocks (replace FillBoundary pack/unpack, AMReX_FBI.H:534-900): copy the region
+ * [lo,hi] (index space of S) x all comps to/from a contiguous device buffer (Fortran order, comp slowest). */
+int ctu_halo_pack(const ctu_fab_t* S, const int lo[3], const int hi[3], double* buf, void* stream);
+int ctu_halo_unpack(ctu_fab_t* S, const int lo[3], const int hi[3], const double* buf, void* stream);
+
+/* ---- problem hooks (Exec/hydro_tests/<problem>/problem_initialize*.H) ------------------------ */
+/* Fills [lo,hi] of the DEVICE fab S with the named problem's initial data, then computeTemp, exactly like
+ * Castro::initData (Castro.cpp:1149-1186).  prob_params: "key=value" pairs separated by blanks/newlines
+ * (the `problem.*` namelist of the inputs file).  Known problems: "Sedov", "Sod", "KH". */
+int ctu_problem_init(const char* problem, const char* prob_params, const ctu_params_t* par,
+                     const ctu_geom_t* geom, const int lo[3], const int hi[3], ctu_fab_t* S, void* stream);
+
+/* ---- inputs file --------------------------------------------------------------------------- */
+/* Parses an AMReX ParmParse inputs file (+ optional "k=v k=v" overrides) for castro.*, eos.*, network.*,
+ * geometry.*, amr.n_cell; unknown keys are ignored.  n_cell/max_step/stop_time outputs may be NULL.
+ * prob_params_out receives the problem.* namelist as "key=value\n" lines (buffer of prob_len bytes). */
+int ctu_parse_inputs(const char* path, const char* overrides, ctu_params_t* par, ctu_geom_t* geom,
+                     int n_cell[3], int* max_step, double* stop_time,
+                     char* prob_params_out, size_t prob_len);
+
+/* ---- single-box host driver (mirrors Amr::coarseTimeStep for max_level = 0) ------------------ */
+typedef struct ctu_sim ctu_sim_t;
+/* box [lo,hi] is this rank's share of the domain described by geom; the state lives in two ghosted device
+ * buffers owned by the sim. */
+int  ctu_sim_create(ctu_sim_t** sim, const ctu_params_t* par, const ctu_geom_t* geom,
+                    const int lo[3], const int hi[3], size_t workspace_bytes, void* stream);
+void ctu_sim_destroy(ctu_sim_t* sim);
+int  ctu_sim_state(ctu_sim_t* sim, ctu_fab_t* out);        /* view of the current (ghosted) state */
+/* step phases, split so that a multi-rank caller can interleave its halo exchange / allreduce:
+ *   pre  : clean_state(S_old) [Castro_advance.cpp:487] + local estdt of S_old (pre-advance check)
+ *   fill : local periodic wrap + physical BCs, then clean_state(Sborder, ng=4) [Castro_advance.cpp:169-170]
+ *          (the caller exchanges inter-box halos between pre and fill)
+ *   hydro: S_new <- Sborder; construct_ctu_hydro_source; clean_state(S_new); local estdt(S_new)   */
+int  ctu_sim_step_pre(ctu_sim_t* sim, double* dt_old_est);
+int  ctu_sim_step_fill(ctu_sim_t* sim);
+int  ctu_sim_step_hydro(ctu_sim_t* sim, double dt, double* dt_new_est, int n_bad[2]);
+/* convenience for a single box covering the whole domain: runs pre+fill+hydro and the dt control of
+ * Castro::computeNewDt / computeInitialDt (Castro.cpp:1559-1573,1751-1992).  Returns status bits. */
+int  ctu_sim_init_problem(ctu_sim_t* sim, const char* problem, const char* prob_params);
+int  ctu_sim_advance(ctu_sim_t* sim, int nsteps, double stop_time, double* time_inout, double* dt_inout,
+                     double* dt_history /* nsteps entries or NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASTRO_CTU_H */

@@ -1,0 +1,43 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY -- builds the UNMODIFIED reference (AMReX-Astro/Castro, read-only at
+# /root/reference) into oracle/_ref/ so that the oracle restatement (oracle/ctu_oracle.cpp) and the
+# CUDA path can be checked against the reference's own CPU executable, and so that
+# `bench.py --impl reference` can time the reference's CPU implementation on the GPU box's cores.
+#
+# The reference hot path cannot be compiled "from a few source files": every hydro header pulls
+# in headers that the reference *generates* at build time (state_indices.H, castro_params.H,
+# prob_parameters.H, network_properties.H, extern_parameters.H, AMReX_Config.H).  The recipe
+# therefore drives the reference's own GNU-make files from a scratch copy of the problem
+# directory under /tmp (the reference tree itself is never written).  This is stated in DESIGN.md.
+#
+# Outputs (git-ignored, but shipped to the GPU box by gpurun):
+#   oracle/_ref/Castro3d_sedov.ex        serial, -O3, no FMA  (parity oracle, golden generator)
+#   oracle/_ref/Castro3d_sedov_omp.ex    OpenMP build         (CPU baseline for bench.py)
+#   oracle/_ref/fcompare.ex              AMReX plotfile comparator (DIM=3)
+set -euo pipefail
+REF=${REF:-/root/reference}
+HERE="$(cd "$(dirname "$0")" && pwd)"
+OUT="$HERE/_ref"
+W=${W:-/tmp/castro_ref_build}
+J=${J:-$(nproc)}
+mkdir -p "$OUT" "$W"
+[ -d "$REF" ] || { echo "no reference at $REF; keeping prebuilt oracle/_ref" ; exit 0; }
+
+build() {  # $1 = problem dir name, $2 = output name, rest = make args
+  local prob=$1 out=$2; shift 2
+  local d="$W/${out}"
+  if [ ! -d "$d" ]; then cp -r "$REF/Exec/hydro_tests/$prob" "$d"; fi
+  ( cd "$d" && make CASTRO_HOME="$REF" USE_MPI=FALSE "$@" -j"$J" >build.log 2>&1 ) || { tail -30 "$d/build.log"; exit 1; }
+  local exe; exe=$(ls -t "$d"/Castro*.ex | head -1)
+  cp "$exe" "$OUT/$out.ex"
+  echo "built $OUT/$out.ex"
+}
+
+what=${1:-all}
+if [ "$what" = all ] || [ "$what" = serial ]; then build Sedov Castro3d_sedov DIM=3; fi
+if [ "$what" = all ] || [ "$what" = omp ];    then build Sedov Castro3d_sedov_omp DIM=3 USE_OMP=TRUE; fi
+if [ "$what" = all ] || [ "$what" = fcompare ]; then
+  d="$W/fcompare"; mkdir -p "$d"; cp -r "$REF/external/amrex/Tools/Plotfile/"* "$d"/
+  ( cd "$d" && make AMREX_HOME="$REF/external/amrex" programs=fcompare DIM=3 USE_MPI=FALSE -j"$J" >build.log 2>&1 ) || { tail -30 "$d/build.log"; exit 1; }
+  cp "$d"/fcompare.gnu.ex "$OUT/fcompare.ex"; echo "built $OUT/fcompare.ex"
+fi

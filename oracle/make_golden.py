@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE: generate tests/golden/*.npz from the UNMODIFIED reference executable
+(oracle/_ref/Castro3d_sedov.ex, built by oracle/build_ref.sh from /root/reference).
+
+Each fixture holds the reference's conserved state (density xmom ymom zmom rho_E rho_e Temp rho_X, exactly the
+plotfile's raw FP64 bytes) at selected steps of a small uniform-grid 3-D Sedov run, plus the simulation time at
+every step (the plotfile Header prints it with 17 significant digits, which pins the dt history).
+
+Run from the repo root IN THE BUILD CONTAINER (needs oracle/_ref):   python oracle/make_golden.py
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from plotfile import read_plotfile, read_header  # noqa: E402
+
+EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_sedov.ex")
+INPUTS = "/root/reference/Exec/hydro_tests/Sedov/inputs.3d.sph"
+
+# name -> (n_cell, max_step, snapshot steps, extra overrides)
+CASES = {
+    "sedov16_hllc": (16, 20, [0, 1, 2, 5, 20], ["castro.riemann_solver=2"]),
+    "sedov16_cgf": (16, 20, [0, 1, 2, 5, 20], ["castro.riemann_solver=0"]),
+    "sedov32_hllc": (32, 10, [10], ["castro.riemann_solver=2"]),
+    # long enough that dt becomes CFL-limited (pins estdt) and the blast reaches the outflow boundary
+    "sedov16_hllc_long": (16, 80, [80], ["castro.riemann_solver=2"]),
+    "sedov16_cgf_long": (16, 80, [80], ["castro.riemann_solver=0"]),
+    # periodic variant with the mini-Castro (cgs) parameter set, Exec/hydro_tests/Sedov/inputs.mini-Castro
+    "sedov16_periodic_hllc": (16, 10, [0, 10], ["castro.riemann_solver=2", "geometry.is_periodic=1 1 1",
+                                                "castro.lo_bc=0 0 0", "castro.hi_bc=0 0 0", "geometry.prob_hi=1.e9 1.e9 1.e9",
+                                                "problem.r_init=1.25e8", "problem.p_ambient=1.e21",
+                                                "problem.exp_energy=1.e52", "problem.dens_ambient=1.e4",
+                                                "castro.init_shrink=0.1", "castro.change_max=1.1", "stop_time=1.e9"]),
+    # non-cubic box + anisotropic dx, CGF
+    "sedov_24x16x8_cgf": ((24, 16, 8), 6, [6], ["castro.riemann_solver=0", "geometry.prob_hi=1.5 1.0 0.5"]),
+}
+
+
+def run_case(name, n_cell, max_step, snaps, extra):
+    if isinstance(n_cell, int):
+        n_cell = (n_cell,) * 3
+    wd = tempfile.mkdtemp(prefix="golden_")
+    try:
+        args = [EXE, INPUTS, "amr.max_level=0", "amr.n_cell=%d %d %d" % n_cell, "amr.max_grid_size=64",
+                "amr.blocking_factor=8", "max_step=%d" % max_step, "stop_time=1.e9", "amr.plot_int=1",
+                "amr.check_int=-1", "amr.derive_plot_vars=NONE", "castro.sum_interval=-1", "amr.plot_file=plt",
+                "castro.v=0", "amr.v=0"] + extra
+        # later key=value on the command line override earlier ones in ParmParse
+        out = subprocess.run(args, cwd=wd, capture_output=True, text=True)
+        if out.returncode != 0:
+            print(out.stdout[-3000:], out.stderr[-3000:])
+            raise RuntimeError(name)
+        times = []
+        states = {}
+        for s in range(max_step + 1):
+            pf = os.path.join(wd, "plt%05d" % s)
+            h = read_header(pf)
+            times.append(h["time"])
+            if s in snaps:
+                h, U = read_plotfile(pf)
+                states["U%d" % s] = U
+        meta = dict(n_cell=np.array(n_cell), times=np.array(times), names=np.array(h["names"]),
+                    problo=np.array(h["problo"]), probhi=np.array(h["probhi"]), overrides=np.array(extra))
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **meta, **states)
+        print(name, "ok: steps", max_step, "t_end", times[-1])
+    finally:
+        shutil.rmtree(wd)
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    for name, (n, ms, snaps, extra) in CASES.items():
+        if only and name not in only:
+            continue
+        run_case(name, n, ms, snaps, extra)
