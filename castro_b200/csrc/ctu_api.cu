@@ -1,0 +1,412 @@
+// ctu_api.cu -- C ABI entry points of the hot path (include/castro_ctu.h) and the host-side orchestration of
+// the kernels in ctu_kernels.cuh.  No CPU fallback exists: without a CUDA device every compute entry point
+// returns CTU_ERR_NO_DEVICE.
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+
+#include "ctu_kernels.cuh"
+#include "ctu_internal.h"
+
+using namespace ctu;
+
+#define CUDA_TRY(x)                                                                                       \
+    do {                                                                                                  \
+        cudaError_t e_ = (x);                                                                             \
+        if (e_ != cudaSuccess) {                                                                          \
+            std::fprintf(stderr, "[castro_ctu] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return CTU_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+struct ctu_workspace {
+    double* arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t max_bytes = 0;
+    unsigned long long* d_dtmin = nullptr;   // 2 entries + 1 for location
+    int* d_counters = nullptr;               // 4 entries
+    unsigned long long* h_dtmin = nullptr;   // pinned
+    int* h_counters = nullptr;               // pinned
+    int last_slab_planes = 0;
+    int last_num_slabs = 0;
+    int kernel_launches = 0;
+};
+
+namespace ctu {
+
+int device_ok() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n > 0;
+}
+
+DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
+    DevPar P;
+    std::memset(&P, 0, sizeof(P));
+    P.riemann_solver = par->riemann_solver;
+    P.use_flattening = par->use_flattening;
+    P.ppm_do_limiting = par->ppm_do_limiting;
+    P.first_order_hydro = par->first_order_hydro;
+    P.transverse_use_eos = par->transverse_use_eos;
+    P.transverse_reset_density = par->transverse_reset_density;
+    P.transverse_reset_rhoe = par->transverse_reset_rhoe;
+    P.eos_assume_neutral = par->eos_assume_neutral;
+    P.nspec = par->nspec; P.naux = par->naux; P.nadv = par->nadv;
+    P.npassive = par->nspec + par->naux + par->nadv;
+    P.nstate = 7 + P.npassive;
+    P.UFS = UFA + par->nadv;
+    P.QFS_off = par->nadv;
+    P.gamc_const = (par->eos_kind == 0);
+    P.difmag = par->difmag;
+    P.small_dens = par->small_dens; P.small_temp = par->small_temp;
+    P.small_pres = par->small_pres; P.small_ener = par->small_ener;
+    P.dual_energy_eta1 = par->dual_energy_eta1; P.dual_energy_eta2 = par->dual_energy_eta2;
+    P.abundance_failure_tolerance = par->abundance_failure_tolerance;
+    P.abundance_failure_rho_cutoff = par->abundance_failure_rho_cutoff;
+    P.retry_small_density_cutoff = par->retry_small_density_cutoff;
+    P.T_guess = par->T_guess;
+    P.small_x = par->small_x;
+    P.gamma = par->eos_gamma;
+    P.gm1 = par->eos_gamma - 1.0;
+    // eos_init (Microphysics interfaces/eos.H:17-50)
+    P.mintemp = std::max(1.e-200, par->small_temp); P.maxtemp = 1.e200;
+    P.mindens = std::max(1.e-200, par->small_dens); P.maxdens = 1.e200;
+    P.mine = 1.e-200; P.maxe = 1.e200;
+    for (int n = 0; n < CTU_MAX_SPEC; ++n) {
+        P.aion_inv[n] = (n < par->nspec) ? 1.0 / par->aion[n] : 0.0;
+        P.zion[n] = (n < par->nspec) ? par->zion[n] : 0.0;
+    }
+    if (geom) {
+        for (int d = 0; d < 3; ++d) {
+            P.dx[d] = geom->dx[d];
+            P.domlo[d] = geom->domlo[d]; P.domhi[d] = geom->domhi[d];
+            P.lo_bc[d] = geom->lo_bc[d]; P.hi_bc[d] = geom->hi_bc[d];
+            P.periodic[d] = geom->periodic[d];
+        }
+    }
+    return P;
+}
+
+int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
+    if (!p) return CTU_ERR_BAD_ARG;
+    if (p->nspec < 1 || p->nspec > CTU_MAX_SPEC || p->naux < 0 || p->nadv < 0 || p->nspec + p->naux + p->nadv > 3 * CTU_MAX_SPEC)
+        return CTU_ERR_BAD_ARG;
+    if (p->ppm_type != 1) return CTU_ERR_UNSUPPORTED;                           // PLM: SURVEY §8(f) rank 4
+    if (p->riemann_solver != 0 && p->riemann_solver != 2) return CTU_ERR_UNSUPPORTED;   // CG solver: not in the parity contract
+    if (p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->ppm_temp_fix || p->use_pslope || p->ppm_well_balanced)
+        return CTU_ERR_UNSUPPORTED;
+    if (p->transverse_use_eos || p->transverse_reset_rhoe) return CTU_ERR_UNSUPPORTED;
+    if (p->eos_kind != 0) return CTU_ERR_UNSUPPORTED;                           // helmholtz: SURVEY §8(f) rank 2
+    if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
+    return 0;
+}
+
+static inline unsigned nblocks(unsigned n) { return (n + TPB - 1) / TPB; }
+
+bool fab_covers(const ctu_fab_t* f, const Box3& b) {
+    for (int d = 0; d < 3; ++d) if (f->lo[d] > b.lo[d] || f->hi[d] < b.hi[d]) return false;
+    return true;
+}
+
+}  // namespace ctu
+
+// ================================================================================================
+extern "C" {
+
+const char* ctu_version(void) { return "castro_ctu_b200 0.1 (sm_100a, fp64, fmad=false)"; }
+
+int ctu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ctu_num_state(const ctu_params_t* p) { return 7 + p->nadv + p->nspec + p->naux; }
+
+int ctu_workspace_create(ctu_workspace_t** ws, size_t max_bytes) {
+    if (!ws) return CTU_ERR_BAD_ARG;
+    if (!device_ok()) return CTU_ERR_NO_DEVICE;
+    ctu_workspace* w = new ctu_workspace();
+    w->max_bytes = max_bytes ? max_bytes : ((size_t)32 << 30);
+    CUDA_TRY(cudaMalloc(&w->d_dtmin, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&w->d_counters, 4 * sizeof(int)));
+    CUDA_TRY(cudaMallocHost(&w->h_dtmin, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMallocHost(&w->h_counters, 4 * sizeof(int)));
+    *ws = w;
+    return 0;
+}
+
+void ctu_workspace_destroy(ctu_workspace_t* w) {
+    if (!w) return;
+    if (w->arena) cudaFree(w->arena);
+    if (w->d_dtmin) cudaFree(w->d_dtmin);
+    if (w->d_counters) cudaFree(w->d_counters);
+    if (w->h_dtmin) cudaFreeHost(w->h_dtmin);
+    if (w->h_counters) cudaFreeHost(w->h_counters);
+    delete w;
+}
+
+size_t ctu_workspace_bytes(const ctu_workspace_t* w) { return w ? w->arena_bytes : 0; }
+int ctu_workspace_last_slabs(const ctu_workspace_t* w) { return w ? w->last_num_slabs : 0; }
+int ctu_workspace_launches(const ctu_workspace_t* w) { return w ? w->kernel_launches : 0; }
+
+static int ws_reserve(ctu_workspace* w, size_t bytes, cudaStream_t st) {
+    if (bytes <= w->arena_bytes) return 0;
+    if (w->arena) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(w->arena)); w->arena = nullptr; w->arena_bytes = 0; }
+    cudaError_t e = cudaMalloc(&w->arena, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return CTU_ERR_NOMEM; }
+    w->arena_bytes = bytes;
+    return 0;
+}
+
+int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_geom_t* geom,
+                      const int valid_lo[3], const int valid_hi[3],
+                      const ctu_fab_t* Sborder, const ctu_fab_t* old_src, const ctu_fab_t* src_corr,
+                      ctu_fab_t* S_new, ctu_fab_t* const flux[3], ctu_fab_t* const mass_flux[3],
+                      double dt, int flags, double dt_est[2], int dt_loc[3], int n_bad[2], void* stream) {
+    if (!ws || !par || !geom || !Sborder || !S_new || !valid_lo || !valid_hi) return CTU_ERR_BAD_ARG;
+    if (!device_ok()) return CTU_ERR_NO_DEVICE;
+    int rc = check_supported(par, geom);
+    if (rc) return rc;
+    if (old_src || src_corr) return CTU_ERR_UNSUPPORTED;   // source-term tracing: SURVEY §8(f) rank 1
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevPar P = make_devpar(par, geom);
+    const int np = P.npassive;
+    const Box3 vbx = make_box(valid_lo, valid_hi);
+    if (!vbx.ok()) return CTU_ERR_BAD_ARG;
+    if (Sborder->ncomp < P.nstate || S_new->ncomp < P.nstate) return CTU_ERR_BAD_ARG;
+    if (!fab_covers(Sborder, grow(vbx, CTU_NGROW)) || !fab_covers(S_new, vbx)) return CTU_ERR_BAD_ARG;
+    const int n_clean = flags & CTU_ADV_NCLEAN_MASK;
+    const bool from_sb = (flags & CTU_ADV_SNEW_FROM_SBORDER) != 0;
+
+    const int NQS = QS_X + np, NIS = IS_X + np, NFX = FX_X + np;
+    const long nxg = (vbx.hi[0] - vbx.lo[0] + 1), nyg = (vbx.hi[1] - vbx.lo[1] + 1), nzv = (vbx.hi[2] - vbx.lo[2] + 1);
+    // per z-plane scratch: qs on grow(tile,4); everything else on ibx = [lo-1, hi+2]
+    const size_t plane_q = (size_t)(nxg + 8) * (nyg + 8) * NQS * sizeof(double);
+    const size_t plane_i = (size_t)(nxg + 4) * (nyg + 4) * (size_t)(2 + 6 * NIS + 9 * NFX) * sizeof(double);
+    // bytes(KS) = plane_q*(KS+8) + plane_i*(KS+4)
+    long KS = (long)((double)(ws->max_bytes - std::min(ws->max_bytes, 8 * plane_q + 4 * plane_i)) / (double)(plane_q + plane_i));
+    if (KS < 1) return CTU_ERR_NOMEM;
+    if (KS > nzv) KS = nzv;
+    // balance the slabs
+    const int nslab = (int)((nzv + KS - 1) / KS);
+    KS = (nzv + nslab - 1) / nslab;
+    const size_t need = plane_q * (KS + 8) + plane_i * (KS + 4);
+    rc = ws_reserve(ws, need, st);
+    if (rc) return rc;
+    ws->last_slab_planes = (int)KS;
+    ws->last_num_slabs = nslab;
+
+    const A4 Sb = make_a4(*Sborder), Sn = make_a4(*S_new);
+    unsigned long long init[4] = {0x7fefffffffffffffull, 0x7fefffffffffffffull, 0xffffffffffffffffull, 0};
+    CUDA_TRY(cudaMemcpyAsync(ws->d_dtmin, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(ws->d_counters, 0, 4 * sizeof(int), st));
+    int launches = 0;
+
+    const double* dx = geom->dx;
+    const double hdtd[3] = {0.5 * dt / dx[0], 0.5 * dt / dx[1], 0.5 * dt / dx[2]};
+    const double cdtd[3] = {dt / dx[0] / 3.0, dt / dx[1] / 3.0, dt / dx[2] / 3.0};
+
+    for (int s = 0; s < nslab; ++s) {
+        Box3 tb = vbx;
+        tb.lo[2] = vbx.lo[2] + (int)(s * KS);
+        tb.hi[2] = std::min(vbx.hi[2], tb.lo[2] + (int)KS - 1);
+        const Box3 qbx = grow(tb, 4);
+        const Box3 obx = grow(tb, 1);
+        Box3 ibx = obx; ibx.hi[0] += 1; ibx.hi[1] += 1; ibx.hi[2] += 1;
+        // carve the arena
+        double* p = ws->arena;
+        const A4 qs = make_a4(p, qbx); p += qbx.npts() * NQS;
+        const size_t ni = ibx.npts();
+        const A4 fd = make_a4(p, ibx); p += ni * 2;
+        TraceArgs ta;
+        for (int d = 0; d < 3; ++d) {
+            ta.qm[d] = make_a4(p, ibx); p += ni * NIS;
+            ta.qp[d] = make_a4(p, ibx); p += ni * NIS;
+            ta.vlo[d] = tb.lo[d]; ta.vhi[d] = tb.hi[d];
+        }
+        A4 F1[3], F2[3][3];
+        for (int d = 0; d < 3; ++d) { F1[d] = make_a4(p, ibx); p += ni * NFX; }
+        for (int n = 0; n < 3; ++n) for (int t = 0; t < 3; ++t) if (n != t) { F2[n][t] = make_a4(p, ibx); p += ni * NFX; }
+
+        {   LaunchBox lb = make_lb(qbx);
+            k_ctoprim<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, qs, lb); ++launches; }
+        {   LaunchBox lb = make_lb(obx);
+            k_flat_div<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb); ++launches;
+            k_trace<0><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt);
+            k_trace<1><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt);
+            k_trace<2><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt); launches += 3; }
+        const Box3 nb[3] = {[&] { Box3 b = tb; b.hi[0] += 1; return b; }(), [&] { Box3 b = tb; b.hi[1] += 1; return b; }(),
+                            [&] { Box3 b = tb; b.hi[2] += 1; return b; }()};
+        // first-pass fluxes: cxbx = grow(xbx,(0,1,1)), cybx = grow(ybx,(1,0,1)), czbx = grow(zbx,(1,1,0))
+        {   LaunchBox lb = make_lb(grow(nb[0], 0, 1, 1));
+            k_riemann1<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb);
+            lb = make_lb(grow(nb[1], 1, 0, 1));
+            k_riemann1<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb);
+            lb = make_lb(grow(nb[2], 1, 1, 0));
+            k_riemann1<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb); launches += 3; }
+        // F^{N|T}: box = nodal(N) grown by one in the third direction
+        {   LaunchBox lb;
+            lb = make_lb(grow(nb[0], 0, 0, 1));   // F^{x|y}
+            k_trans_riemann<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], F2[0][1], lb, cdtd[1]);
+            lb = make_lb(grow(nb[0], 0, 1, 0));   // F^{x|z}
+            k_trans_riemann<0, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[2], F2[0][2], lb, cdtd[2]);
+            lb = make_lb(grow(nb[1], 0, 0, 1));   // F^{y|x}
+            k_trans_riemann<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], F2[1][0], lb, cdtd[0]);
+            lb = make_lb(grow(nb[1], 1, 0, 0));   // F^{y|z}
+            k_trans_riemann<1, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[2], F2[1][2], lb, cdtd[2]);
+            lb = make_lb(grow(nb[2], 0, 1, 0));   // F^{z|x}
+            k_trans_riemann<2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[0], F2[2][0], lb, cdtd[0]);
+            lb = make_lb(grow(nb[2], 1, 0, 0));   // F^{z|y}
+            k_trans_riemann<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1]); launches += 6; }
+        // final fluxes overwrite the (now dead) first-pass flux storage
+        {   LaunchBox lb;
+            lb = make_lb(nb[0]);
+            k_final<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F2[1][2], F2[2][1], fd, Sb, F1[0], lb, hdtd[1], hdtd[2]);
+            lb = make_lb(nb[1]);
+            k_final<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F2[0][2], F2[2][0], fd, Sb, F1[1], lb, hdtd[0], hdtd[2]);
+            lb = make_lb(nb[2]);
+            k_final<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F2[0][1], F2[1][0], fd, Sb, F1[2], lb, hdtd[0], hdtd[1]); launches += 3; }
+        {   UpdateArgs ua;
+            for (int d = 0; d < 3; ++d) ua.F[d] = F1[d];
+            ua.dtmin = ws->d_dtmin; ua.counters = ws->d_counters;
+            ua.n_clean = n_clean; ua.want_dt = (dt_est != nullptr);
+            LaunchBox lb = make_lb(tb);
+            k_update<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, from_sb ? Sb : Sn, Sn, ua, lb, dt); ++launches; }
+        for (int d = 0; d < 3; ++d) {
+            const bool want_f = flux && flux[d], want_m = mass_flux && mass_flux[d];
+            if (!want_f && !want_m) continue;
+            Box3 fb = tb;
+            if (d != 2 || s == nslab - 1) fb.hi[d] += 1;     // nodaltilebox: no face is visited twice
+            A4 fo, mo;
+            std::memset(&fo, 0, sizeof(fo)); std::memset(&mo, 0, sizeof(mo));
+            if (want_f) { if (!fab_covers(flux[d], fb) || flux[d]->ncomp < P.nstate) return CTU_ERR_BAD_ARG; fo = make_a4(*flux[d]); }
+            if (want_m) { if (!fab_covers(mass_flux[d], fb)) return CTU_ERR_BAD_ARG; mo = make_a4(*mass_flux[d]); }
+            LaunchBox lb = make_lb(fb);
+            if (d == 0) k_store_flux<0><<<nblocks(lb.n), TPB, 0, st>>>(P, F1[0], fo, mo, lb, dt);
+            if (d == 1) k_store_flux<1><<<nblocks(lb.n), TPB, 0, st>>>(P, F1[1], fo, mo, lb, dt);
+            if (d == 2) k_store_flux<2><<<nblocks(lb.n), TPB, 0, st>>>(P, F1[2], fo, mo, lb, dt);
+            ++launches;
+        }
+    }
+    if (dt_est && dt_loc) {
+        LaunchBox lb = make_lb(vbx);
+        k_estdt_loc<<<nblocks(lb.n), TPB, 0, st>>>(P, Sn, lb, ws->d_dtmin + 1, ws->d_dtmin + 2); ++launches;
+    }
+    ws->kernel_launches += launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(ws->h_dtmin, ws->d_dtmin, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->h_counters, ws->d_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int status = 0;
+    if (ws->h_counters[0]) status |= CTU_STATUS_INVALID_DENSITY;
+    if (ws->h_counters[1]) status |= CTU_STATUS_INVALID_X;
+    if (ws->h_counters[3]) status |= CTU_STATUS_NAN;
+    if (n_bad) { n_bad[0] = ws->h_counters[0]; n_bad[1] = ws->h_counters[1]; }
+    if (dt_est) {
+        std::memcpy(&dt_est[0], &ws->h_dtmin[0], sizeof(double));
+        std::memcpy(&dt_est[1], &ws->h_dtmin[1], sizeof(double));
+        if (dt_loc) {
+            const unsigned long long t = ws->h_dtmin[2];
+            const unsigned long long nx = nxg, ny = nyg;
+            dt_loc[2] = vbx.lo[2] + (int)(t / (nx * ny));
+            dt_loc[1] = vbx.lo[1] + (int)((t % (nx * ny)) / nx);
+            dt_loc[0] = vbx.lo[0] + (int)(t % nx);
+        }
+    }
+    return status;
+}
+
+int ctu_estdt(const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3], const int hi[3],
+              const ctu_fab_t* S, double* dt_min, int ijk[3], void* stream) {
+    if (!par || !geom || !S || !dt_min) return CTU_ERR_BAD_ARG;
+    if (!device_ok()) return CTU_ERR_NO_DEVICE;
+    int rc = check_supported(par, geom);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevPar P = make_devpar(par, geom);
+    const Box3 bx = make_box(lo, hi);
+    if (!bx.ok() || !fab_covers(S, bx)) return CTU_ERR_BAD_ARG;
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    unsigned long long init[2] = {0x7fefffffffffffffull, 0xffffffffffffffffull};
+    CUDA_TRY(cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const A4 a = make_a4(*S);
+    LaunchBox lb = make_lb(bx);
+    k_estdt<<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, d);
+    if (ijk) k_estdt_loc<<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, d, d + 1);
+    unsigned long long h[2];
+    CUDA_TRY(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaFree(d));
+    std::memcpy(dt_min, &h[0], sizeof(double));
+    if (ijk) {
+        const unsigned long long nx = lb.nx, ny = lb.ny, t = h[1];
+        ijk[2] = bx.lo[2] + (int)(t / (nx * ny));
+        ijk[1] = bx.lo[1] + (int)((t % (nx * ny)) / nx);
+        ijk[0] = bx.lo[0] + (int)(t % nx);
+    }
+    return 0;
+}
+
+int ctu_clean_state(const ctu_params_t* par, const int lo[3], const int hi[3], ctu_fab_t* S, int npass, void* stream) {
+    if (!par || !S) return CTU_ERR_BAD_ARG;
+    if (!device_ok()) return CTU_ERR_NO_DEVICE;
+    int rc = check_supported(par, nullptr);
+    if (rc) return rc;
+    const DevPar P = make_devpar(par, nullptr);
+    const Box3 bx = make_box(lo, hi);
+    if (!bx.ok() || !fab_covers(S, bx)) return CTU_ERR_BAD_ARG;
+    LaunchBox lb = make_lb(bx);
+    k_clean<<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(P, make_a4(*S), lb, npass, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ctu_fill_boundary(const ctu_params_t* par, const ctu_geom_t* geom, const int valid_lo[3], const int valid_hi[3],
+                      ctu_fab_t* S, int ng, void* stream) {
+    if (!par || !geom || !S) return CTU_ERR_BAD_ARG;
+    if (!device_ok()) return CTU_ERR_NO_DEVICE;
+    for (int d = 0; d < 3; ++d) {
+        if (geom->periodic[d]) continue;
+        const int bcs[2] = {geom->lo_bc[d], geom->hi_bc[d]};
+        for (int b : bcs) if (b == 1) return CTU_ERR_UNSUPPORTED;   // inflow (ext_dir) needs a problem-specific fill
+    }
+    const DevPar P = make_devpar(par, geom);
+    const Box3 vbx = make_box(valid_lo, valid_hi);
+    const Box3 gbx = grow(vbx, ng);
+    if (!fab_covers(S, gbx)) return CTU_ERR_BAD_ARG;
+    const A4 a = make_a4(*S);
+    LaunchBox lb = make_lb(gbx);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_fill<0><<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, vbx);
+    k_fill<1><<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, vbx);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ctu_halo_pack(const ctu_fab_t* S, const int lo[3], const int hi[3], double* buf, void* stream) {
+    if (!S || !buf) return CTU_ERR_BAD_ARG;
+    if (!device_ok()) return CTU_ERR_NO_DEVICE;
+    const Box3 bx = make_box(lo, hi);
+    if (!bx.ok() || !fab_covers(S, bx)) return CTU_ERR_BAD_ARG;
+    LaunchBox lb = make_lb(bx);
+    k_pack<0><<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(make_a4(*S), lb, buf, S->ncomp);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ctu_halo_unpack(ctu_fab_t* S, const int lo[3], const int hi[3], const double* buf, void* stream) {
+    if (!S || !buf) return CTU_ERR_BAD_ARG;
+    if (!device_ok()) return CTU_ERR_NO_DEVICE;
+    const Box3 bx = make_box(lo, hi);
+    if (!bx.ok() || !fab_covers(S, bx)) return CTU_ERR_BAD_ARG;
+    LaunchBox lb = make_lb(bx);
+    k_pack<1><<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(make_a4(*S), lb, const_cast<double*>(buf), S->ncomp);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

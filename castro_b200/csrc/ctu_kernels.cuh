@@ -1,0 +1,854 @@
+// ctu_kernels.cuh -- the sm_100a kernels of the fused CTU-PPM advance.
+//
+// Pipeline for one z-slab ("tile" in the sense of the reference's MFIter(S_new, hydro_tile_size) loop,
+// Castro_ctu_hydro.cpp:193).  The reference issues ~75 ParallelFor launches per tile and round-trips 239
+// doubles/zone of temporaries; here the same arithmetic is grouped into 16 launches:
+//
+//   k_ctoprim          U -> qs = (rho u v w p rhoe c gamc X..)                     [a2,a3,a4 of SURVEY §8]
+//   k_flat_div         flattening coefficient (once per zone, not 3x) + nodal div(u) [a7, a18]
+//   k_trace            PPM reconstruction + characteristic tracing, 3 directions     [a8-a11]
+//   k_riemann1<d>      first-pass Riemann fluxes F^x F^y F^z                          [a12-a14]
+//   k_trans_riemann    trans_single (both states) fused with the Riemann solve that consumes it: the 12
+//                      singly-corrected interface arrays of the reference never exist   [a15 + a12]
+//   k_final<d>         trans_final (both states) + final Riemann + zero T flux + artificial viscosity +
+//                      species-flux normalisation                                      [a16 + a12 + a18]
+//   k_update           consup_hydro + check_for_negative_density + clean_state + estdt [a19, a22, a20]
+//
+// Threads map 1:1 to zones/faces with i fastest, so every global access is coalesced along x.
+#pragma once
+#include "ctu_physics.cuh"
+
+namespace ctu {
+
+constexpr int TPB = 128;
+
+struct LaunchBox {
+    int lo0, lo1, lo2;
+    unsigned nx, ny, nz;
+    unsigned n;
+};
+inline LaunchBox make_lb(const Box3& b) {
+    LaunchBox l;
+    l.lo0 = b.lo[0]; l.lo1 = b.lo[1]; l.lo2 = b.lo[2];
+    l.nx = b.hi[0] - b.lo[0] + 1; l.ny = b.hi[1] - b.lo[1] + 1; l.nz = b.hi[2] - b.lo[2] + 1;
+    l.n = l.nx * l.ny * l.nz;
+    return l;
+}
+__device__ __forceinline__ bool thread_zone(const LaunchBox& lb, int& i, int& j, int& k) {
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= lb.n) return false;
+    unsigned nxy = lb.nx * lb.ny;
+    unsigned kk = t / nxy;
+    unsigned r = t - kk * nxy;
+    unsigned jj = r / lb.nx;
+    i = lb.lo0 + (int)(r - jj * lb.nx);
+    j = lb.lo1 + (int)jj;
+    k = lb.lo2 + (int)kk;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ctoprim: hydro::conservative_to_primitive (advection_util.H:98-235) + rho_inv passives
+// (Castro_ctu_hydro.cpp:226-230, reconstruction.H:50-83)
+// ------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(TPB) k_ctoprim(const DevPar P, const A4 U, const A4 qs, const LaunchBox lb) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long ou = U.idx(i, j, k), oq = qs.idx(i, j, k);
+    const double rho = U.at(ou, URHO);
+    const double rhoinv = 1.0 / rho;
+    const double u = U.at(ou, UMX) * rhoinv, v = U.at(ou, UMY) * rhoinv, w = U.at(ou, UMZ) * rhoinv;
+    const double kineng = 0.5 * rho * (u * u + v * v + w * w);
+    const double E = U.at(ou, UEDEN);
+    double e;
+    if ((E - kineng) > P.dual_energy_eta1 * E) e = (E - kineng) * rhoinv;
+    else e = U.at(ou, UEINT) * rhoinv;
+    Eos s;
+    s.T = U.at(ou, UTEMP); s.rho = rho; s.e = e;
+    s.mu = eos_mu(P, [&](int n) { return U.at(ou, P.UFS + n) * rhoinv; });
+    eos_re<false>(P, s);
+    qs.at(oq, QS_RHO) = rho;
+    qs.at(oq, QS_U) = u; qs.at(oq, QS_V) = v; qs.at(oq, QS_W) = w;
+    qs.at(oq, QS_P) = s.p;
+    qs.at(oq, QS_RE) = s.e * rho;
+    qs.at(oq, QS_C) = s.cs;
+    qs.at(oq, QS_GAMC) = P.gamma;
+    for (int ip = 0; ip < P.npassive; ++ip) qs.at(oq, QS_X + ip) = U.at(ou, UFA + ip) * rhoinv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// flattening (flatten.H:6-155; zones of obx) and node-centred div(u) (advection_util.cpp:330-347; nodes of obx)
+// ------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(TPB) k_flat_div(const DevPar P, const A4 qs, const A4 fd, const LaunchBox lb) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long oq = qs.idx(i, j, k), of = fd.idx(i, j, k);
+    const double* __restrict__ pp = qs.p + oq + QS_P * qs.sn;
+    double flatn = 1.0;
+    if (P.first_order_hydro) flatn = 0.0;
+    else if (P.use_flattening) {
+        {
+            const double* __restrict__ uu = qs.p + oq + QS_U * qs.sn;
+            flatn = flatten_dir([&](int s) { return pp[s]; }, [&](int s) { return uu[s]; });
+        }
+        {
+            const double* __restrict__ uu = qs.p + oq + QS_V * qs.sn;
+            const long st = qs.sj;
+            flatn = smin(flatn, flatten_dir([&](int s) { return pp[s * st]; }, [&](int s) { return uu[s * st]; }));
+        }
+        {
+            const double* __restrict__ uu = qs.p + oq + QS_W * qs.sn;
+            const long st = qs.sk;
+            flatn = smin(flatn, flatten_dir([&](int s) { return pp[s * st]; }, [&](int s) { return uu[s * st]; }));
+        }
+    }
+    fd.at(of, 0) = flatn;
+    // divu
+    const double dxinv = 1.0 / P.dx[0], dyinv = 1.0 / P.dx[1], dzinv = 1.0 / P.dx[2];
+    const long sj = qs.sj, sk = qs.sk;
+    const double* __restrict__ qu = qs.p + oq + QS_U * qs.sn;
+    const double* __restrict__ qv = qs.p + oq + QS_V * qs.sn;
+    const double* __restrict__ qw = qs.p + oq + QS_W * qs.sn;
+    double ux = 0.25 * (qu[0] - qu[-1] + qu[-sk] - qu[-1 - sk] + qu[-sj] - qu[-1 - sj] + qu[-sj - sk] - qu[-1 - sj - sk]) * dxinv;
+    double vy = 0.25 * (qv[0] - qv[-sj] + qv[-sk] - qv[-sj - sk] + qv[-1] - qv[-1 - sj] + qv[-1 - sk] - qv[-1 - sj - sk]) * dyinv;
+    double wz = 0.25 * (qw[0] - qw[-sk] + qw[-sj] - qw[-sj - sk] + qw[-1] - qw[-1 - sk] + qw[-1 - sj] - qw[-1 - sj - sk]) * dzinv;
+    fd.at(of, 1) = ux + vy + wz;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Castro::trace_ppm (trace_ppm.cpp:17-678) for one direction of one zone, zero source terms.
+// ------------------------------------------------------------------------------------------------
+template <int DIR>
+__device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq, long st, double flat, double dtdL,
+                                          const A4& qm, const A4& qp, long op, long om, bool do_p, bool do_m,
+                                          bool refl_lo, bool refl_hi) {
+    constexpr int QUN = QS_U + DIR;
+    constexpr int QUT = QS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
+    constexpr int QUTT = QS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
+    constexpr int IUN = IS_U + DIR;
+    constexpr int IUT = IS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
+    constexpr int IUTT = IS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
+    const double* __restrict__ base = qs.p + oq;
+    const long sn = qs.sn;
+    const double cc = base[QS_C * sn];
+    const double un = base[QUN * sn];
+    double sm, sp, dum;
+    Parabola pb;
+
+#define CTU_RECON(comp)                                                                          \
+    {                                                                                            \
+        const double* __restrict__ a = base + (comp) * sn;                                       \
+        const double s0 = a[0];                                                                  \
+        ppm_reconstruct(P, a[-2 * st], a[-st], s0, a[st], a[2 * st], flat, sm, sp);              \
+        pb.set(sm, sp, s0);                                                                      \
+    }
+
+    double Ip_rho1, Im_rho1, Ip_rho2, Im_rho0;
+    CTU_RECON(QS_RHO);
+    pb.integ(un - cc, dtdL, dum, Im_rho0);
+    pb.integ(un, dtdL, Ip_rho1, Im_rho1);
+    pb.integ(un + cc, dtdL, Ip_rho2, dum);
+
+    double Ip_un0, Im_un0, Ip_un2, Im_un2;
+    CTU_RECON(QUN);
+    pb.integ(un - cc, dtdL, Ip_un0, Im_un0);
+    pb.integ(un + cc, dtdL, Ip_un2, Im_un2);
+
+    double Ip_p0, Im_p0, Ip_p1, Im_p1, Ip_p2, Im_p2;
+    CTU_RECON(QS_P);
+    pb.integ(un - cc, dtdL, Ip_p0, Im_p0);
+    pb.integ(un, dtdL, Ip_p1, Im_p1);
+    pb.integ(un + cc, dtdL, Ip_p2, Im_p2);
+
+    double Ip_re1, Im_re1, Ip_re2, Im_re0;
+    CTU_RECON(QS_RE);
+    pb.integ(un - cc, dtdL, dum, Im_re0);
+    pb.integ(un, dtdL, Ip_re1, Im_re1);
+    pb.integ(un + cc, dtdL, Ip_re2, dum);
+
+    double Ip_ut, Im_ut, Ip_utt, Im_utt;
+    CTU_RECON(QUT);
+    pb.integ(un, dtdL, Ip_ut, Im_ut);
+    CTU_RECON(QUTT);
+    pb.integ(un, dtdL, Ip_utt, Im_utt);
+
+    double Ip_gc2, Im_gc0;
+    if (P.gamc_const) {
+        // PPM of a spatially constant field returns the constant exactly (all limited slopes vanish, the
+        // flattened edges collapse onto s0 in the monotonisation branch, s6 == 0): skip the arithmetic.
+        Ip_gc2 = P.gamma; Im_gc0 = P.gamma;
+    } else {
+        CTU_RECON(QS_GAMC);
+        pb.integ(un - cc, dtdL, dum, Im_gc0);
+        pb.integ(un + cc, dtdL, Ip_gc2, dum);
+    }
+
+    // passives (trace_ppm.cpp:443-485)
+    for (int ip = 0; ip < P.npassive; ++ip) {
+        double Ipp, Imp;
+        CTU_RECON(QS_X + ip);
+        pb.integ(un, dtdL, Ipp, Imp);
+        if (do_p) { qp.at(op, IS_X + ip) = Imp; if (refl_lo) qm.at(op, IS_X + ip) = Imp; }
+        if (do_m) { qm.at(om, IS_X + ip) = Ipp; if (refl_hi) qp.at(om, IS_X + ip) = Ipp; }
+    }
+#undef CTU_RECON
+
+    const double small_re = P.small_dens * P.small_ener;
+    // "x + 0.0" below stands for the reference's "+ hdt * Im_src_*" with identically zero sources: it is kept
+    // because it turns -0.0 into +0.0 exactly like the reference does.
+    if (do_p) {   // plus state on face i (trace_ppm.cpp:494-581)
+        double rho_ref = Im_rho0 + 0.0;
+        double un_ref = Im_un0 + 0.0;
+        double p_ref = Im_p0 + 0.0;
+        double rhoe_g_ref = Im_re0 + 0.0;
+        double gam_g_ref = Im_gc0;
+        rho_ref = smax(rho_ref, P.small_dens);
+        double rho_ref_inv = 1.0 / rho_ref;
+        p_ref = smax(p_ref, P.small_pres);
+        double csq_ref = gam_g_ref * (0.0 + p_ref) * rho_ref_inv;
+        double cc_ref = sqrt(csq_ref);
+        double cc_ref_inv = 1.0 / cc_ref;
+        double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
+        double d_um = un_ref - Im_un0 - 0.0;
+        double dptotm = p_ref - Im_p0 - 0.0;
+        double drho = rho_ref - Im_rho1 - 0.0;
+        double dptot = p_ref - Im_p1 - 0.0;
+        double drhoe_g = rhoe_g_ref - Im_re1 - 0.0;
+        double d_up = un_ref - Im_un2 - 0.0;
+        double dptotp = p_ref - Im_p2 - 0.0;
+        double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
+        double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
+        double alpha0r = drho - dptot / csq_ref;
+        double alpha0e_g = drhoe_g - dptot * h_g_ref / csq_ref;
+        alpham = un - cc > 0.0 ? 0.0 : -alpham;
+        alphap = un + cc > 0.0 ? 0.0 : -alphap;
+        alpha0r = un > 0.0 ? 0.0 : -alpha0r;
+        alpha0e_g = un > 0.0 ? 0.0 : -alpha0e_g;
+        const double o_rho = smax(P.small_dens, rho_ref + alphap + alpham + alpha0r);
+        const double o_un = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
+        const double o_re = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
+        const double o_p = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
+        const double o_ut = Im_ut + 0.0;
+        const double o_utt = Im_utt + 0.0;
+        qp.at(op, IS_RHO) = o_rho; qp.at(op, IUN) = o_un; qp.at(op, IS_RE) = o_re; qp.at(op, IS_P) = o_p;
+        qp.at(op, IUT) = o_ut; qp.at(op, IUTT) = o_utt;
+        if (refl_lo) {   // enforce_reflect_states (advection_util.cpp:766-785): left state mirrors the right one
+            qm.at(op, IS_RHO) = o_rho; qm.at(op, IUN) = -o_un; qm.at(op, IS_RE) = o_re; qm.at(op, IS_P) = o_p;
+            qm.at(op, IUT) = o_ut; qm.at(op, IUTT) = o_utt;
+        }
+    }
+    if (do_m) {   // minus state on face i+1 (trace_ppm.cpp:583-675)
+        double rho_ref = Ip_rho2 + 0.0;
+        double un_ref = Ip_un2 + 0.0;
+        double p_ref = Ip_p2 + 0.0;
+        double rhoe_g_ref = Ip_re2 + 0.0;
+        double gam_g_ref = Ip_gc2;
+        rho_ref = smax(rho_ref, P.small_dens);
+        double rho_ref_inv = 1.0 / rho_ref;
+        p_ref = smax(p_ref, P.small_pres);
+        double csq_ref = gam_g_ref * (0.0 + p_ref) * rho_ref_inv;
+        double cc_ref = sqrt(csq_ref);
+        double cc_ref_inv = 1.0 / cc_ref;
+        double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
+        double d_um = un_ref - Ip_un0 - 0.0;
+        double dptotm = p_ref - Ip_p0 - 0.0;
+        double drho = rho_ref - Ip_rho1 - 0.0;
+        double dptot = p_ref - Ip_p1 - 0.0;
+        double drhoe_g = rhoe_g_ref - Ip_re1 - 0.0;
+        double d_up = un_ref - Ip_un2 - 0.0;
+        double dptotp = p_ref - Ip_p2 - 0.0;
+        double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
+        double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
+        double alpha0r = drho - dptot / csq_ref;
+        double alpha0e_g = drhoe_g - dptot * h_g_ref / csq_ref;
+        alpham = un - cc > 0.0 ? -alpham : 0.0;
+        alphap = un + cc > 0.0 ? -alphap : 0.0;
+        alpha0r = un > 0.0 ? -alpha0r : 0.0;
+        alpha0e_g = un > 0.0 ? -alpha0e_g : 0.0;
+        const double o_rho = smax(P.small_dens, rho_ref + alphap + alpham + alpha0r);
+        const double o_un = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
+        const double o_re = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
+        const double o_p = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
+        const double o_ut = Ip_ut + 0.0;
+        const double o_utt = Ip_utt + 0.0;
+        qm.at(om, IS_RHO) = o_rho; qm.at(om, IUN) = o_un; qm.at(om, IS_RE) = o_re; qm.at(om, IS_P) = o_p;
+        qm.at(om, IUT) = o_ut; qm.at(om, IUTT) = o_utt;
+        if (refl_hi) {   // advection_util.cpp:787-805: right state mirrors the left one
+            qp.at(om, IS_RHO) = o_rho; qp.at(om, IUN) = -o_un; qp.at(om, IS_RE) = o_re; qp.at(om, IS_P) = o_p;
+            qp.at(om, IUT) = o_ut; qp.at(om, IUTT) = o_utt;
+        }
+    }
+}
+
+struct TraceArgs {
+    A4 qm[3], qp[3];
+    int vlo[3], vhi[3];
+};
+
+// one thread = one zone of obx, one direction per launch (blockIdx.y)
+template <int DIR>
+static __global__ void __launch_bounds__(TPB) k_trace(const DevPar P, const A4 qs, const A4 fd, const TraceArgs ta, const LaunchBox lb,
+                                               const double dt) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long oq = qs.idx(i, j, k);
+    const double flat = fd(i, j, k, 0);
+    const int idx = (DIR == 0) ? i : (DIR == 1) ? j : k;
+    const long st = (DIR == 0) ? 1 : (DIR == 1) ? qs.sj : qs.sk;
+    const A4& qm = ta.qm[DIR];
+    const A4& qp = ta.qp[DIR];
+    const long op = qp.idx(i, j, k);
+    const long om = op + ((DIR == 0) ? 1 : (DIR == 1) ? qp.sj : qp.sk);
+    const bool sym_lo = P.lo_bc[DIR] == 3, sym_hi = P.hi_bc[DIR] == 3;
+    bool do_p = idx >= ta.vlo[DIR];
+    bool do_m = idx <= ta.vhi[DIR];
+    const bool refl_lo = do_p && sym_lo && idx == P.domlo[DIR];         // this zone owns face domlo: also writes qm there
+    const bool refl_hi = do_m && sym_hi && idx + 1 == P.domhi[DIR] + 1;  // owns face domhi+1: also writes qp there
+    if (sym_lo && idx + 1 == P.domlo[DIR]) do_m = false;                 // qm(domlo) is the mirrored state instead
+    if (sym_hi && idx == P.domhi[DIR] + 1) do_p = false;                 // qp(domhi+1) is the mirrored state instead
+    trace_dir<DIR>(P, qs, oq, st, flat, dt / P.dx[DIR], qm, qp, op, om, do_p, do_m, refl_lo, refl_hi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Riemann driver shared by the three flux kernels: Castro::cmpflx_plus_godunov (riemann.cpp:15-200)
+//   XM(ip)/XP(ip): passive ip (mass fraction etc.) of the minus/plus state
+// ------------------------------------------------------------------------------------------------
+template <int DIR, class XM, class XP>
+__device__ __forceinline__ void solve_face(const DevPar& P, const double* qm, const double* qp, const A4& qs, int i, int j, int k,
+                                           XM xm, XP xp, double* F, double& ugd, double& pgd, PassiveUpwind& pu) {
+    const long oq = qs.idx(i, j, k);
+    const long om = oq - ((DIR == 0) ? 1 : (DIR == 1) ? qs.sj : qs.sk);
+    const double cr = qs.at(oq, QS_C), cl = qs.at(om, QS_C);
+    const double gamcr = P.gamc_const ? P.gamma : qs.at(oq, QS_GAMC);
+    const double gamcl = P.gamc_const ? P.gamma : qs.at(om, QS_GAMC);
+    const int idx = (DIR == 0) ? i : (DIR == 1) ? j : k;
+    const bool sp_lo = P.lo_bc[DIR] >= 3 && P.lo_bc[DIR] <= 5, sp_hi = P.hi_bc[DIR] >= 3 && P.hi_bc[DIR] <= 5;
+    double bnd_fac = 1.0;
+    if ((idx == P.domlo[DIR] && sp_lo) || (idx == P.domhi[DIR] + 1 && sp_hi)) bnd_fac = 0.0;
+    if (P.riemann_solver == 0) {
+        riemann_cgf<DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac,
+                         [&](int n) { return xm(P.QFS_off + n); }, [&](int n) { return xp(P.QFS_off + n); }, F, ugd, pgd, pu);
+    } else {
+        riemann_hllc<DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, F, ugd, pgd, pu);
+    }
+}
+
+__device__ __forceinline__ double passive_flux(const DevPar& P, const PassiveUpwind& pu, double Xm, double Xp) {
+    return (P.riemann_solver == 0) ? passive_flux_cgf(pu, Xm, Xp) : passive_flux_hllc(pu, Xm, Xp);
+}
+
+__device__ __forceinline__ void load6(const A4& a, long off, double* q) {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) q[n] = a.at(off, n);
+}
+
+// first-pass fluxes (Castro_ctu_hydro.cpp:674,745,817)
+template <int DIR>
+static __global__ void __launch_bounds__(TPB) k_riemann1(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Fo, const LaunchBox lb) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long o = qm.idx(i, j, k);
+    double ql[6], qr[6], F[6], ugd, pgd;
+    PassiveUpwind pu;
+    load6(qm, o, ql);
+    load6(qp, o, qr);
+    solve_face<DIR>(P, ql, qr, qs, i, j, k, [&](int ip) { return qm.at(o, IS_X + ip); }, [&](int ip) { return qp.at(o, IS_X + ip); },
+                    F, ugd, pgd, pu);
+    const long of = Fo.idx(i, j, k);
+#pragma unroll
+    for (int n = 0; n < 6; ++n) Fo.at(of, n) = F[n];
+    Fo.at(of, FX_UG) = ugd;
+    Fo.at(of, FX_PG) = pgd;
+    for (int ip = 0; ip < P.npassive; ++ip) Fo.at(of, FX_X + ip) = passive_flux(P, pu, qm.at(o, IS_X + ip), qp.at(o, IS_X + ip));
+}
+
+// species verdict of trans_single / trans_final (trans.cpp:360-402, 838-881): returns true if the corrected state
+// must be reset to the uncorrected one.  corr(ip) = sum over transverse directions of cdtdx*(F_r - F_l) of passive ip.
+template <class XF, class CF>
+__device__ __forceinline__ bool trans_reset(const DevPar& P, double rho, double rrnew, XF x, CF corr) {
+    bool reset = (P.transverse_reset_density && rrnew < 0.0);
+    if (!reset) {
+        for (int n = 0; n < P.nspec; ++n) {
+            const int ip = P.QFS_off + n;
+            const double Xo = corr(ip, rho * x(ip)) / rrnew;
+            if (Xo > 1.0 + P.abundance_failure_tolerance || Xo < -P.abundance_failure_tolerance) { reset = true; break; }
+        }
+    }
+    return reset;
+}
+
+// trans_single (both states) fused with the Riemann solve on the corrected states.
+//   N = face direction, T = transverse direction whose first-pass flux Ft corrects the states.
+//   reference: trans_single(...) + cmpflx_plus_godunov(...), Castro_ctu_hydro.cpp:699-880 and :895-1080
+template <int N, int T>
+static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Ft, const A4 Fo,
+                                                       const LaunchBox lb, const double cdtdx) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long o = qm.idx(i, j, k);
+    const long sN_f = (N == 0) ? 1 : (N == 1) ? Ft.sj : Ft.sk;
+    const long sT_f = (T == 0) ? 1 : (T == 1) ? Ft.sj : Ft.sk;
+    const long sN_q = (N == 0) ? 1 : (N == 1) ? qs.sj : qs.sk;
+    const long ofp = Ft.idx(i, j, k);           // low transverse face of the zone on the plus side
+    const long ofm = ofp - sN_f;                // ... of the zone on the minus side
+    const long oqp = qs.idx(i, j, k);
+    const long oqm = oqp - sN_q;
+    double qlo[6], qro[6];
+    bool reset_m, reset_p;
+    double rrnew_m, rrnew_p;
+    {   // minus state: zone (face - e_N)
+        double q[6], fl[6], fr[6];
+        load6(qm, o, q);
+        load6(Ft, ofm, fl);
+        load6(Ft, ofm + sT_f, fr);
+        rrnew_m = q[IS_RHO] - cdtdx * (fr[0] - fl[0]);
+        reset_m = trans_reset(P, q[IS_RHO], rrnew_m, [&](int ip) { return qm.at(o, IS_X + ip); },
+                              [&](int ip, double c0) { return c0 - cdtdx * (Ft.at(ofm + sT_f, FX_X + ip) - Ft.at(ofm, FX_X + ip)); });
+        const double gamc = P.gamc_const ? P.gamma : qs.at(oqm, QS_GAMC);
+        trans_single_hydro(P, q, qlo, fl, fr, Ft.at(ofm, FX_UG), Ft.at(ofm + sT_f, FX_UG), Ft.at(ofm, FX_PG), Ft.at(ofm + sT_f, FX_PG),
+                           gamc, cdtdx, rrnew_m, reset_m);
+    }
+    {   // plus state: zone (face)
+        double q[6], fl[6], fr[6];
+        load6(qp, o, q);
+        load6(Ft, ofp, fl);
+        load6(Ft, ofp + sT_f, fr);
+        rrnew_p = q[IS_RHO] - cdtdx * (fr[0] - fl[0]);
+        reset_p = trans_reset(P, q[IS_RHO], rrnew_p, [&](int ip) { return qp.at(o, IS_X + ip); },
+                              [&](int ip, double c0) { return c0 - cdtdx * (Ft.at(ofp + sT_f, FX_X + ip) - Ft.at(ofp, FX_X + ip)); });
+        const double gamc = P.gamc_const ? P.gamma : qs.at(oqp, QS_GAMC);
+        trans_single_hydro(P, q, qro, fl, fr, Ft.at(ofp, FX_UG), Ft.at(ofp + sT_f, FX_UG), Ft.at(ofp, FX_PG), Ft.at(ofp + sT_f, FX_PG),
+                           gamc, cdtdx, rrnew_p, reset_p);
+    }
+    // corrected passives, recomputed on demand (they are never stored)
+    const double rho_m = qm.at(o, IS_RHO), rho_p = qp.at(o, IS_RHO);
+    auto xm = [&](int ip) {
+        const double X = qm.at(o, IS_X + ip);
+        if (reset_m) return X;
+        return (rho_m * X - cdtdx * (Ft.at(ofm + sT_f, FX_X + ip) - Ft.at(ofm, FX_X + ip))) / rrnew_m;
+    };
+    auto xp = [&](int ip) {
+        const double X = qp.at(o, IS_X + ip);
+        if (reset_p) return X;
+        return (rho_p * X - cdtdx * (Ft.at(ofp + sT_f, FX_X + ip) - Ft.at(ofp, FX_X + ip))) / rrnew_p;
+    };
+    double F[6], ugd, pgd;
+    PassiveUpwind pu;
+    solve_face<N>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu);
+    const long of = Fo.idx(i, j, k);
+#pragma unroll
+    for (int n = 0; n < 6; ++n) Fo.at(of, n) = F[n];
+    Fo.at(of, FX_UG) = ugd;
+    Fo.at(of, FX_PG) = pgd;
+    for (int ip = 0; ip < P.npassive; ++ip) Fo.at(of, FX_X + ip) = passive_flux(P, pu, xm(ip), xp(ip));
+}
+
+// trans_final (both states) + final Riemann solve + flux cleaning:
+//   Castro_ctu_hydro.cpp:925-961 / 1004-1042 / 1085-1123, then :1131-1172 (zero T flux, apply_av, normalize_species_fluxes)
+//   F1 = F^{T1|T2}, F2 = F^{T2|T1};  c1 = dt/(2 dx_T1), c2 = dt/(2 dx_T2)
+template <int N>
+static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 F1, const A4 F2,
+                                               const A4 fd, const A4 U, const A4 Fo, const LaunchBox lb, const double c1, const double c2) {
+    constexpr int T1 = (N == 0) ? 1 : 0;
+    constexpr int T2 = (N == 2) ? 1 : 2;
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long o = qm.idx(i, j, k);
+    const long sN_f = (N == 0) ? 1 : (N == 1) ? F1.sj : F1.sk;     // all flux scratch arrays share one box
+    const long s1_f = (T1 == 0) ? 1 : F1.sj;
+    const long s2_f = (T2 == 1) ? F1.sj : F1.sk;
+    const long sN_q = (N == 0) ? 1 : (N == 1) ? qs.sj : qs.sk;
+    const long ofp = F1.idx(i, j, k), ofm = ofp - sN_f;
+    const long oqp = qs.idx(i, j, k), oqm = oqp - sN_q;
+    double qlo[6], qro[6];
+    bool reset_m, reset_p;
+    double rrnew_m, rrnew_p;
+    {
+        double q[6], f1l[6], f1r[6], f2l[6], f2r[6];
+        load6(qm, o, q);
+        load6(F1, ofm, f1l); load6(F1, ofm + s1_f, f1r);
+        load6(F2, ofm, f2l); load6(F2, ofm + s2_f, f2r);
+        rrnew_m = q[IS_RHO] - c1 * (f1r[0] - f1l[0]) - c2 * (f2r[0] - f2l[0]);
+        reset_m = trans_reset(P, q[IS_RHO], rrnew_m, [&](int ip) { return qm.at(o, IS_X + ip); },
+                              [&](int ip, double c0) {
+                                  return c0 - c1 * (F1.at(ofm + s1_f, FX_X + ip) - F1.at(ofm, FX_X + ip)) -
+                                         c2 * (F2.at(ofm + s2_f, FX_X + ip) - F2.at(ofm, FX_X + ip));
+                              });
+        const double gamc = P.gamc_const ? P.gamma : qs.at(oqm, QS_GAMC);
+        trans_final_hydro(P, q, qlo, f1l, f1r, f2l, f2r, F1.at(ofm, FX_UG), F1.at(ofm + s1_f, FX_UG), F1.at(ofm, FX_PG),
+                          F1.at(ofm + s1_f, FX_PG), F2.at(ofm, FX_UG), F2.at(ofm + s2_f, FX_UG), F2.at(ofm, FX_PG),
+                          F2.at(ofm + s2_f, FX_PG), gamc, c1, c2, rrnew_m, reset_m);
+    }
+    {
+        double q[6], f1l[6], f1r[6], f2l[6], f2r[6];
+        load6(qp, o, q);
+        load6(F1, ofp, f1l); load6(F1, ofp + s1_f, f1r);
+        load6(F2, ofp, f2l); load6(F2, ofp + s2_f, f2r);
+        rrnew_p = q[IS_RHO] - c1 * (f1r[0] - f1l[0]) - c2 * (f2r[0] - f2l[0]);
+        reset_p = trans_reset(P, q[IS_RHO], rrnew_p, [&](int ip) { return qp.at(o, IS_X + ip); },
+                              [&](int ip, double c0) {
+                                  return c0 - c1 * (F1.at(ofp + s1_f, FX_X + ip) - F1.at(ofp, FX_X + ip)) -
+                                         c2 * (F2.at(ofp + s2_f, FX_X + ip) - F2.at(ofp, FX_X + ip));
+                              });
+        const double gamc = P.gamc_const ? P.gamma : qs.at(oqp, QS_GAMC);
+        trans_final_hydro(P, q, qro, f1l, f1r, f2l, f2r, F1.at(ofp, FX_UG), F1.at(ofp + s1_f, FX_UG), F1.at(ofp, FX_PG),
+                          F1.at(ofp + s1_f, FX_PG), F2.at(ofp, FX_UG), F2.at(ofp + s2_f, FX_UG), F2.at(ofp, FX_PG),
+                          F2.at(ofp + s2_f, FX_PG), gamc, c1, c2, rrnew_p, reset_p);
+    }
+    const double rho_m = qm.at(o, IS_RHO), rho_p = qp.at(o, IS_RHO);
+    auto xm = [&](int ip) {
+        const double X = qm.at(o, IS_X + ip);
+        if (reset_m) return X;
+        const double compn = rho_m * X;
+        return (compn - c1 * (F1.at(ofm + s1_f, FX_X + ip) - F1.at(ofm, FX_X + ip)) -
+                c2 * (F2.at(ofm + s2_f, FX_X + ip) - F2.at(ofm, FX_X + ip))) / rrnew_m;
+    };
+    auto xp = [&](int ip) {
+        const double X = qp.at(o, IS_X + ip);
+        if (reset_p) return X;
+        const double compn = rho_p * X;
+        return (compn - c1 * (F1.at(ofp + s1_f, FX_X + ip) - F1.at(ofp, FX_X + ip)) -
+                c2 * (F2.at(ofp + s2_f, FX_X + ip) - F2.at(ofp, FX_X + ip))) / rrnew_p;
+    };
+    double F[6], ugd, pgd;
+    PassiveUpwind pu;
+    solve_face<N>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu);
+
+    // apply_av (advection_util.cpp:354-419): div1 = difmag * min(0, <div u> over the 4 nodes of the face)
+    const long od = fd.idx(i, j, k);
+    const double* __restrict__ dv = fd.p + od + fd.sn;
+    double div1;
+    if (N == 0) div1 = 0.25 * (dv[0] + dv[fd.sj] + dv[fd.sk] + dv[fd.sj + fd.sk]);
+    else if (N == 1) div1 = 0.25 * (dv[0] + dv[1] + dv[fd.sk] + dv[1 + fd.sk]);
+    else div1 = 0.25 * (dv[0] + dv[1] + dv[fd.sj] + dv[1 + fd.sj]);
+    div1 = P.difmag * smin(0.0, div1);
+    const double dL = P.dx[N];
+    const long ou = U.idx(i, j, k);
+    const long oum = ou - ((N == 0) ? 1 : (N == 1) ? U.sj : U.sk);
+    const long of = Fo.idx(i, j, k);
+    // fixed components: URHO UMX UMY UMZ UEDEN UEINT map 1:1 onto F[0..5]; UTEMP flux is zero
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+        const double div_var = div1 * (U.at(ou, n) - U.at(oum, n));
+        F[n] += dL * div_var;
+        Fo.at(of, n) = F[n];
+    }
+    Fo.at(of, FX_UG) = ugd;
+    Fo.at(of, FX_PG) = pgd;
+    // passives + normalize_species_fluxes (advection_util.cpp:473-509)
+    double sum = 0.0;
+    for (int ip = 0; ip < P.npassive; ++ip) {
+        double f = passive_flux(P, pu, xm(ip), xp(ip));
+        const double div_var = div1 * (U.at(ou, UFA + ip) - U.at(oum, UFA + ip));
+        f += dL * div_var;
+        Fo.at(of, FX_X + ip) = f;
+        if (ip >= P.QFS_off && ip < P.QFS_off + P.nspec) sum += f;
+    }
+    double fac = 1.0;
+    if (fabs(sum) > 2.220446049250313e-16 * fabs(F[0])) fac = F[0] / sum;
+    for (int n = 0; n < P.nspec; ++n) {
+        const int ip = P.QFS_off + n;
+        Fo.at(of, FX_X + ip) = Fo.at(of, FX_X + ip) * fac;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// clean_state on one zone held in registers + passives in global memory: Castro::clean_state (Castro.cpp:4537-4577)
+//   = enforce_min_density (advection_util.cpp:649-743) -> normalize_species (Castro.cpp:3140-3212)
+//     -> reset_internal_energy (:3742-3808) -> EOS temperature (:4044-4070)
+// u[0..6] = URHO..UTEMP ; passives live in S at offset o.  Returns number of invalid mass fractions (normalize_species).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clean_zone(const DevPar& P, double* __restrict__ u, const A4& S, long o) {
+    int nfail = 0;
+    if (u[URHO] < P.small_dens) {
+        for (int ip = 0; ip < P.npassive; ++ip) S.at(o, UFA + ip) *= (P.small_dens / u[URHO]);
+        Eos s; s.rho = P.small_dens; s.T = P.small_temp;
+        s.mu = eos_mu(P, [&](int n) { return S.at(o, P.UFS + n) / P.small_dens; });
+        eos_rt<false>(P, s);
+        u[URHO] = s.rho;
+        u[UTEMP] = s.T;
+        u[UMX] = 0.0; u[UMY] = 0.0; u[UMZ] = 0.0;
+        u[UEINT] = s.rho * s.e;
+        u[UEDEN] = u[UEINT];
+    }
+    const double rho = u[URHO];
+    const double rhoInv = 1.0 / rho;
+    {   // normalize_species
+        double rhoX_sum = 0.0;
+        for (int n = 0; n < P.nspec; ++n) {
+            double rX = S.at(o, P.UFS + n);
+            const double X = rX * rhoInv;
+            if (rho >= P.abundance_failure_rho_cutoff) {
+                if (X < -P.abundance_failure_tolerance || X > 1.0 + P.abundance_failure_tolerance) nfail++;
+            }
+            rX = clampd(rX, P.small_x * rho, rho);
+            S.at(o, P.UFS + n) = rX;
+            rhoX_sum += rX;
+        }
+        const double fac = rho / rhoX_sum;
+        for (int n = 0; n < P.nspec; ++n) S.at(o, P.UFS + n) *= fac;
+    }
+    const double mu = eos_mu(P, [&](int n) { return S.at(o, P.UFS + n) * rhoInv; });
+    {   // reset_internal_energy
+        const double Up = u[UMX] * rhoInv, Vp = u[UMY] * rhoInv, Wp = u[UMZ] * rhoInv;
+        const double ke = 0.5 * (Up * Up + Vp * Vp + Wp * Wp);
+        Eos s; s.rho = rho; s.T = P.small_temp; s.mu = mu;
+        eos_rt<false>(P, s);
+        const double small_e = s.e;
+        u[UEINT] = amax(u[UEINT], rho * small_e);
+        u[UEDEN] = amax(u[UEDEN], rho * (small_e + ke) + 0.0);
+        const double rho_eint = u[UEDEN] - rho * ke - 0.0;
+        if (rho_eint > P.dual_energy_eta2 * u[UEDEN]) u[UEINT] = rho_eint;
+    }
+    {   // computeTemp
+        Eos s; s.rho = rho; s.T = u[UTEMP]; s.e = u[UEINT] * rhoInv; s.mu = mu;
+        eos_re<false>(P, s);
+        u[UTEMP] = s.T;
+    }
+    return nfail;
+}
+
+// estdt<hydro> for one zone (timestep.H:84-139)
+__device__ __forceinline__ double estdt_zone(const DevPar& P, const double* __restrict__ u, const A4& S, long o) {
+    const double rhoInv = 1.0 / u[URHO];
+    Eos s; s.rho = u[URHO]; s.T = u[UTEMP]; s.e = u[UEINT] * rhoInv;
+    s.mu = eos_mu(P, [&](int n) { return S.at(o, P.UFS + n) * rhoInv; });
+    eos_re<false>(P, s);
+    const double ux = u[UMX] * rhoInv, uy = u[UMY] * rhoInv, uz = u[UMZ] * rhoInv;
+    const double c = s.cs;
+    const double dt1 = P.dx[0] / (c + fabs(ux));
+    const double dt2 = P.dx[1] / (c + fabs(uy));
+    const double dt3 = P.dx[2] / (c + fabs(uz));
+    return amin(amin(dt1, dt2), dt3);
+}
+
+// warp-shuffle + shared-memory block min, one atomicMin per block (positive doubles order like their bit patterns)
+__device__ __forceinline__ void block_min_atomic(double v, unsigned long long* dst) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, b, s);
+        b = (o < b) ? o : b;
+    }
+    __shared__ unsigned long long sm[TPB / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = b;
+    __syncthreads();
+    if (wid == 0) {
+        b = (lane < TPB / 32) ? sm[lane] : 0xffffffffffffffffull;
+#pragma unroll
+        for (int s = (TPB / 64); s > 0; s >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, b, s);
+            b = (o < b) ? o : b;
+        }
+        if (lane == 0) atomicMin(dst, b);
+    }
+    __syncthreads();
+}
+
+constexpr double DT_HUGE = 1.0e300;
+
+struct UpdateArgs {
+    A4 F[3];            // final fluxes (scratch layout)
+    A4 flux_out[3];     // optional user flux registers (Castro layout), p == nullptr if absent
+    A4 mass_out[3];     // optional mass fluxes
+    unsigned long long* dtmin;   // [0] after the first clean, [1] after the last clean
+    int* counters;      // [0] bad rho, [1] bad X, [2] invalid X seen by normalize_species, [3] NaN
+    int n_clean;
+    int want_dt;
+};
+
+// consup_hydro (Castro_ctu.cpp:10-83) + check_for_negative_density (Castro.cpp:3311-3402) + n_clean x clean_state + estdt
+//   Sin: where the pre-update state is read from -- S_new itself (reference semantics: S_new was pre-loaded with
+//   Sborder, Castro_sources.cpp:627) or Sborder directly (saves the copy pass for pure hydro)
+static __global__ void __launch_bounds__(TPB) k_update(const DevPar P, const A4 Sb, const A4 Sin, const A4 Sn, const UpdateArgs a, const LaunchBox lb,
+                                                const double dt) {
+    int i, j, k;
+    const bool active = thread_zone(lb, i, j, k);
+    double dt0 = DT_HUGE, dt1 = DT_HUGE;
+    if (active) {
+        const double a0 = P.dx[1] * P.dx[2], a1 = P.dx[0] * P.dx[2], a2 = P.dx[0] * P.dx[1];
+        const double vol = P.dx[0] * P.dx[1] * P.dx[2];
+        const double volinv = 1.0 / vol;
+        const long ob = Sb.idx(i, j, k), on = Sn.idx(i, j, k), oi = Sin.idx(i, j, k);
+        const A4& F0 = a.F[0]; const A4& F1 = a.F[1]; const A4& F2 = a.F[2];
+        const long f0 = F0.idx(i, j, k), f1 = F1.idx(i, j, k), f2 = F2.idx(i, j, k);
+        const long f0p = f0 + 1, f1p = f1 + F1.sj, f2p = f2 + F2.sk;
+        double u[7];
+        const double rho_old = Sb.at(ob, URHO);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) {
+            u[n] = Sin.at(oi, n) + dt * (F0.at(f0, n) * a0 - F0.at(f0p, n) * a0 + F1.at(f1, n) * a1 - F1.at(f1p, n) * a1 +
+                                        F2.at(f2, n) * a2 - F2.at(f2p, n) * a2) * volinv;
+        }
+        u[UTEMP] = Sin.at(oi, UTEMP);   // the T flux is identically zero (Castro_ctu_hydro.cpp:1141)
+        {
+            double pdu = (F0.at(f0p, FX_PG) + F0.at(f0, FX_PG)) * (F0.at(f0p, FX_UG) * a0 - F0.at(f0, FX_UG) * a0);
+            pdu += (F1.at(f1p, FX_PG) + F1.at(f1, FX_PG)) * (F1.at(f1p, FX_UG) * a1 - F1.at(f1, FX_UG) * a1);
+            pdu += (F2.at(f2p, FX_PG) + F2.at(f2, FX_PG)) * (F2.at(f2p, FX_UG) * a2 - F2.at(f2, FX_UG) * a2);
+            pdu = 0.5 * pdu * volinv;
+            u[UEINT] = u[UEINT] - dt * pdu;
+        }
+        for (int ip = 0; ip < P.npassive; ++ip) {
+            const int n = FX_X + ip;
+            Sn.at(on, UFA + ip) = Sin.at(oi, UFA + ip) + dt * (F0.at(f0, n) * a0 - F0.at(f0p, n) * a0 + F1.at(f1, n) * a1 - F1.at(f1p, n) * a1 +
+                                                              F2.at(f2, n) * a2 - F2.at(f2p, n) * a2) * volinv;
+        }
+        // check_for_negative_density
+        {
+            const double rho = u[URHO];
+            const double rhoInv = 1.0 / rho;
+            if (rho_old >= P.retry_small_density_cutoff && rho < P.small_dens) atomicAdd(&a.counters[0], 1);
+            if (rho >= P.abundance_failure_rho_cutoff) {
+                for (int n = 0; n < P.nspec; ++n) {
+                    const double X = Sn.at(on, P.UFS + n) * rhoInv;
+                    if (X < -P.abundance_failure_tolerance || X > 1.0 + P.abundance_failure_tolerance) atomicAdd(&a.counters[1], 1);
+                }
+            }
+        }
+        for (int c = 0; c < a.n_clean; ++c) {
+            const int nf = clean_zone(P, u, Sn, on);
+            if (nf) atomicAdd(&a.counters[2], nf);
+            if (c == 0 && a.want_dt) dt0 = estdt_zone(P, u, Sn, on);
+        }
+        if (a.want_dt) dt1 = (a.n_clean <= 1) ? ((a.n_clean == 1) ? dt0 : estdt_zone(P, u, Sn, on)) : estdt_zone(P, u, Sn, on);
+        if (a.n_clean == 0) dt0 = dt1;
+        bool nan = false;
+#pragma unroll
+        for (int n = 0; n < 7; ++n) { Sn.at(on, n) = u[n]; nan |= (u[n] != u[n]); }
+        if (nan) atomicAdd(&a.counters[3], 1);
+    }
+    if (a.want_dt) {
+        block_min_atomic(dt0, a.dtmin + 0);
+        block_min_atomic(dt1, a.dtmin + 1);
+    }
+}
+
+// scale_flux + flux register accumulation + mass fluxes (Castro_ctu_hydro.cpp:1255-1343); DIR-face kernel
+template <int DIR>
+static __global__ void __launch_bounds__(TPB) k_store_flux(const DevPar P, const A4 F, const A4 fo, const A4 mo, const LaunchBox lb, const double dt) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const double area = (DIR == 0) ? P.dx[1] * P.dx[2] : (DIR == 1) ? P.dx[0] * P.dx[2] : P.dx[0] * P.dx[1];
+    const long of = F.idx(i, j, k);
+    if (fo.p) {
+        const long oo = fo.idx(i, j, k);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) fo.at(oo, n) += dt * F.at(of, n) * area;
+        fo.at(oo, UTEMP) += dt * 0.0 * area;
+        for (int ip = 0; ip < P.npassive; ++ip) fo.at(oo, UFA + ip) += dt * F.at(of, FX_X + ip) * area;
+    }
+    if (mo.p) mo(i, j, k, 0) = dt * F.at(of, FX_RHO) * area;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone state kernels
+// ------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(TPB) k_clean(const DevPar P, const A4 S, const LaunchBox lb, const int npass, int* counters) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long o = S.idx(i, j, k);
+    double u[7];
+#pragma unroll
+    for (int n = 0; n < 7; ++n) u[n] = S.at(o, n);
+    int nf = 0;
+    for (int c = 0; c < npass; ++c) nf += clean_zone(P, u, S, o);
+#pragma unroll
+    for (int n = 0; n < 7; ++n) S.at(o, n) = u[n];
+    if (nf && counters) atomicAdd(&counters[2], nf);
+}
+
+static __global__ void __launch_bounds__(TPB) k_estdt(const DevPar P, const A4 S, const LaunchBox lb, unsigned long long* dtmin) {
+    int i, j, k;
+    const bool active = thread_zone(lb, i, j, k);
+    double d = DT_HUGE;
+    if (active) {
+        const long o = S.idx(i, j, k);
+        double u[7];
+#pragma unroll
+        for (int n = 0; n < 7; ++n) u[n] = S.at(o, n);
+        d = estdt_zone(P, u, S, o);
+    }
+    block_min_atomic(d, dtmin);
+}
+
+// first zone (smallest linear index) whose dt equals the reduced minimum -> location (diagnostic, Castro.cpp:1652-1662)
+static __global__ void __launch_bounds__(TPB) k_estdt_loc(const DevPar P, const A4 S, const LaunchBox lb, const unsigned long long* dtmin,
+                                                   unsigned long long* loc) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long o = S.idx(i, j, k);
+    double u[7];
+#pragma unroll
+    for (int n = 0; n < 7; ++n) u[n] = S.at(o, n);
+    const double d = estdt_zone(P, u, S, o);
+    if ((unsigned long long)__double_as_longlong(d) == *dtmin) atomicMin(loc, (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x));
+}
+
+// Ghost fill.  PASS 0: periodic self-wrap (ghost zones whose periodic image is one of this box's valid zones).
+//              PASS 1: physical boundaries (foextrap / reflect_even / reflect_odd; Castro_setup.cpp:36-61,
+//                      AMReX_FilCC_3D_C.H:39-201) as a composition of per-dimension index maps; reads only
+//                      in-domain zones (valid or already-exchanged ghosts), writes only out-of-domain zones.
+template <int PASS>
+static __global__ void __launch_bounds__(TPB) k_fill(const DevPar P, const A4 S, const LaunchBox lb, const Box3 vbx) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    if (vbx.contains(i, j, k)) return;
+    const int idx[3] = {i, j, k};
+    int src[3];
+    bool flip[3] = {false, false, false};
+    bool any = false;
+    for (int d = 0; d < 3; ++d) {
+        int g = idx[d];
+        src[d] = g;
+        const bool outside = (g < P.domlo[d] || g > P.domhi[d]);
+        if (PASS == 0) {
+            if (outside) {
+                if (!P.periodic[d]) return;   // handled by pass 1
+                const int n = P.domhi[d] - P.domlo[d] + 1;
+                src[d] = P.domlo[d] + (((g - P.domlo[d]) % n) + n) % n;
+                any = true;
+            }
+            if (src[d] < vbx.lo[d] || src[d] > vbx.hi[d]) return;   // image owned by another box: halo exchange
+        } else {
+            if (outside && !P.periodic[d]) {
+                const bool lo_side = g < P.domlo[d];
+                const int bc = lo_side ? P.lo_bc[d] : P.hi_bc[d];
+                if (bc == 2) src[d] = lo_side ? P.domlo[d] : P.domhi[d];
+                else if (bc >= 3 && bc <= 5) { src[d] = lo_side ? 2 * P.domlo[d] - g - 1 : 2 * P.domhi[d] - g + 1; flip[d] = true; }
+                else return;
+                any = true;
+            }
+        }
+    }
+    if (!any) return;
+    const long o = S.idx(i, j, k), os = S.idx(src[0], src[1], src[2]);
+    for (int n = 0; n < P.nstate; ++n) {
+        double v = S.at(os, n);
+        if ((n == UMX && flip[0]) || (n == UMY && flip[1]) || (n == UMZ && flip[2])) v = -v;
+        S.at(o, n) = v;
+    }
+}
+
+// contiguous pack / unpack of a sub-box (all components): FillBoundary's pack/unpack kernels (AMReX_FBI.H:534-900)
+template <int UNPACK>
+static __global__ void __launch_bounds__(TPB) k_pack(const A4 S, const LaunchBox lb, double* __restrict__ buf, const int ncomp) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const long o = S.idx(i, j, k);
+    for (int n = 0; n < ncomp; ++n) {
+        if (UNPACK) S.at(o, n) = buf[(size_t)n * lb.n + t];
+        else buf[(size_t)n * lb.n + t] = S.at(o, n);
+    }
+}
+
+// S_new <- Sborder on the valid box (Castro_sources.cpp:627)
+static __global__ void __launch_bounds__(TPB) k_copy(const A4 src, const A4 dst, const LaunchBox lb, const int ncomp) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long os = src.idx(i, j, k), od = dst.idx(i, j, k);
+    for (int n = 0; n < ncomp; ++n) dst.at(od, n) = src.at(os, n);
+}
+
+}  // namespace ctu

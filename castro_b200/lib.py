@@ -1,0 +1,273 @@
+"""Loader + thin Python mirror of the C ABI (include/castro_ctu.h) of libcastro_ctu.so.
+
+PyTorch is used only as plumbing (device memory, streams, torch.distributed); every number is computed by the
+hand-written sm_100a kernels behind the C ABI.  There is no CPU or PyTorch fallback: if the shared library is
+missing or no CUDA device is usable, the calls raise."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcastro_ctu.so")
+_LIB = None
+
+
+class CtuError(RuntimeError):
+    pass
+
+
+_ERR = {-1: "bad argument", -2: "no CUDA device (there is no CPU fallback)", -3: "CUDA error", -4: "out of memory",
+        -5: "unsupported parameter combination", -6: "I/O error"}
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise CtuError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` or "
+                           "`make -C castro_b200/csrc` (no fallback path exists)" % SO_PATH)
+        L = C.CDLL(SO_PATH)
+        L.ctu_version.restype = C.c_char_p
+        L.ctu_workspace_bytes.restype = C.c_size_t
+        L.ctu_sim_workspace.restype = C.c_void_p
+        L.ctu_workspace_create.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.ctu_workspace_destroy.argtypes = [C.c_void_p]
+        L.ctu_workspace_bytes.argtypes = [C.c_void_p]
+        L.ctu_workspace_last_slabs.argtypes = [C.c_void_p]
+        L.ctu_workspace_launches.argtypes = [C.c_void_p]
+        L.ctu_sim_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3,
+                                     C.c_size_t, C.c_void_p]
+        for fn in ("ctu_sim_destroy", "ctu_sim_step_pre", "ctu_sim_step_fill"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+        L.ctu_sim_workspace.argtypes = [C.c_void_p]
+        L.ctu_sim_state.argtypes = [C.c_void_p, C.POINTER(abi.Fab)]
+        L.ctu_sim_download.argtypes = [C.c_void_p, C.c_void_p]
+        L.ctu_sim_upload.argtypes = [C.c_void_p, C.c_void_p]
+        L.ctu_sim_init_problem.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.ctu_sim_step_hydro.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ctu_sim_advance.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ctu_hydro_advance.argtypes = [C.c_void_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3,
+                                        C.POINTER(abi.Fab), C.POINTER(abi.Fab), C.POINTER(abi.Fab), C.POINTER(abi.Fab),
+                                        C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int), C.c_void_p]
+        L.ctu_estdt.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3, C.POINTER(abi.Fab),
+                                C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p]
+        L.ctu_clean_state.argtypes = [C.POINTER(abi.Params), abi.Int3, abi.Int3, C.POINTER(abi.Fab), C.c_int, C.c_void_p]
+        L.ctu_fill_boundary.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3, C.POINTER(abi.Fab),
+                                        C.c_int, C.c_void_p]
+        L.ctu_halo_pack.argtypes = [C.POINTER(abi.Fab), abi.Int3, abi.Int3, C.c_void_p, C.c_void_p]
+        L.ctu_halo_unpack.argtypes = [C.POINTER(abi.Fab), abi.Int3, abi.Int3, C.c_void_p, C.c_void_p]
+        L.ctu_problem_init.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3,
+                                       C.POINTER(abi.Fab), C.c_void_p]
+        L.ctu_parse_inputs.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_char_p, C.c_size_t]
+        _LIB = L
+    return _LIB
+
+
+def check(rc, what=""):
+    if rc < 0:
+        raise CtuError("%s failed: %s (%d)" % (what or "ctu call", _ERR.get(rc, "?"), rc))
+    return rc
+
+
+def default_params():
+    p = abi.Params()
+    lib().ctu_params_defaults(C.byref(p))
+    return p
+
+
+def params_finalize(p):
+    check(lib().ctu_params_finalize(C.byref(p)), "ctu_params_finalize")
+    return p
+
+
+def parse_inputs(path, overrides=""):
+    p = default_params()
+    g = abi.Geom()
+    nc = (C.c_int * 3)()
+    ms = C.c_int(-1)
+    stop = C.c_double(-1.0)
+    buf = C.create_string_buffer(4096)
+    check(lib().ctu_parse_inputs(path.encode() if path else None, overrides.encode(), C.byref(p), C.byref(g), nc, C.byref(ms),
+                                 C.byref(stop), buf, 4096), "ctu_parse_inputs")
+    return p, g, tuple(nc), ms.value, stop.value, buf.value.decode()
+
+
+def tensor_fab(t, lo):
+    """torch CUDA float64 tensor [ncomp, nz, ny, nx] -> Fab view (Array4 layout)."""
+    assert t.is_cuda and t.is_contiguous() and str(t.dtype) == "torch.float64"
+    nc, nz, ny, nx = t.shape
+    return abi.Fab.make(t.data_ptr(), lo, (lo[0] + nx - 1, lo[1] + ny - 1, lo[2] + nz - 1), nc)
+
+
+def prob_string(d):
+    return " ".join("%s=%r" % (k, v) for k, v in d.items())
+
+
+class Workspace:
+    def __init__(self, max_bytes=0):
+        self.h = C.c_void_p()
+        check(lib().ctu_workspace_create(C.byref(self.h), max_bytes), "ctu_workspace_create")
+
+    def close(self):
+        if self.h:
+            lib().ctu_workspace_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def bytes(self):
+        return lib().ctu_workspace_bytes(self.h)
+
+    @property
+    def last_slabs(self):
+        return lib().ctu_workspace_last_slabs(self.h)
+
+    @property
+    def launches(self):
+        return lib().ctu_workspace_launches(self.h)
+
+
+def hydro_advance(ws, par, geom, vlo, vhi, Sborder, sb_lo, S_new, sn_lo, dt, n_clean=1, from_sborder=False, fluxes=None,
+                  flux_los=None, mass_fluxes=None, mass_los=None, want_loc=False, stream=0):
+    """Sborder, S_new, fluxes: torch CUDA tensors [ncomp, nz, ny, nx].  Returns (status, dt_est[2], loc, n_bad)."""
+    fb = tensor_fab(Sborder, sb_lo)
+    fn = tensor_fab(S_new, sn_lo)
+    est = (C.c_double * 2)()
+    loc = (C.c_int * 3)()
+    nbad = (C.c_int * 2)()
+    FabP3 = C.POINTER(abi.Fab) * 3
+    keep = []
+
+    def mk(ts, los):
+        if ts is None:
+            return None
+        arr = FabP3()
+        for d in range(3):
+            f = tensor_fab(ts[d], los[d])
+            keep.append(f)
+            arr[d] = C.pointer(f)
+        return C.cast(arr, C.c_void_p)
+
+    flags = (n_clean & 3) | (4 if from_sborder else 0)
+    rc = lib().ctu_hydro_advance(ws.h, C.byref(par), C.byref(geom), abi.Int3(*vlo), abi.Int3(*vhi), C.byref(fb), None, None,
+                                 C.byref(fn), mk(fluxes, flux_los), mk(mass_fluxes, mass_los), dt, flags, est,
+                                 loc if want_loc else None, nbad, stream)
+    check(rc, "ctu_hydro_advance")
+    return rc, (est[0], est[1]), tuple(loc), tuple(nbad)
+
+
+def estdt(par, geom, lo, hi, S, s_lo, stream=0):
+    f = tensor_fab(S, s_lo)
+    dt = C.c_double(0)
+    loc = (C.c_int * 3)()
+    check(lib().ctu_estdt(C.byref(par), C.byref(geom), abi.Int3(*lo), abi.Int3(*hi), C.byref(f), C.byref(dt), loc, stream), "ctu_estdt")
+    return dt.value, tuple(loc)
+
+
+def clean_state(par, lo, hi, S, s_lo, npass=1, stream=0):
+    f = tensor_fab(S, s_lo)
+    check(lib().ctu_clean_state(C.byref(par), abi.Int3(*lo), abi.Int3(*hi), C.byref(f), npass, stream), "ctu_clean_state")
+
+
+def fill_boundary(par, geom, vlo, vhi, S, ng=abi.CTU_NGROW, stream=0):
+    f = tensor_fab(S, tuple(l - ng for l in vlo))
+    check(lib().ctu_fill_boundary(C.byref(par), C.byref(geom), abi.Int3(*vlo), abi.Int3(*vhi), C.byref(f), ng, stream),
+          "ctu_fill_boundary")
+
+
+def halo_pack(S, s_lo, lo, hi, buf, stream=0):
+    f = tensor_fab(S, s_lo)
+    check(lib().ctu_halo_pack(C.byref(f), abi.Int3(*lo), abi.Int3(*hi), buf.data_ptr(), stream), "ctu_halo_pack")
+
+
+def halo_unpack(S, s_lo, lo, hi, buf, stream=0):
+    f = tensor_fab(S, s_lo)
+    check(lib().ctu_halo_unpack(C.byref(f), abi.Int3(*lo), abi.Int3(*hi), buf.data_ptr(), stream), "ctu_halo_unpack")
+
+
+def problem_init(problem, prob, par, geom, lo, hi, S, s_lo, stream=0):
+    f = tensor_fab(S, s_lo)
+    check(lib().ctu_problem_init(problem.encode(), prob_string(prob).encode(), C.byref(par), C.byref(geom), abi.Int3(*lo),
+                                 abi.Int3(*hi), C.byref(f), stream), "ctu_problem_init")
+
+
+class Sim:
+    """Single-box driver (one per rank): owns the ghosted ping-pong state buffers on the device."""
+
+    def __init__(self, par, geom, lo, hi, workspace_bytes=0, stream=0):
+        self.par, self.geom = par, geom
+        self.lo, self.hi = tuple(lo), tuple(hi)
+        self.h = C.c_void_p()
+        check(lib().ctu_sim_create(C.byref(self.h), C.byref(par), C.byref(geom), abi.Int3(*lo), abi.Int3(*hi), workspace_bytes,
+                                   stream), "ctu_sim_create")
+        self.shape = (par.num_state,) + tuple(hi[d] - lo[d] + 1 for d in (2, 1, 0))
+
+    def close(self):
+        if self.h:
+            lib().ctu_sim_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init_problem(self, problem, prob):
+        check(lib().ctu_sim_init_problem(self.h, problem.encode(), prob_string(prob).encode()), "ctu_sim_init_problem")
+
+    def state_fab(self):
+        f = abi.Fab()
+        check(lib().ctu_sim_state(self.h, C.byref(f)), "ctu_sim_state")
+        return f
+
+    def download(self, out=None):
+        """valid zones -> host ndarray [ncomp, nz, ny, nx]"""
+        if out is None:
+            out = np.empty(self.shape)
+        check(lib().ctu_sim_download(self.h, out.ctypes.data), "ctu_sim_download")
+        return out
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        assert arr.shape == self.shape
+        check(lib().ctu_sim_upload(self.h, arr.ctypes.data), "ctu_sim_upload")
+
+    def step_pre(self):
+        check(lib().ctu_sim_step_pre(self.h), "ctu_sim_step_pre")
+
+    def step_fill(self):
+        check(lib().ctu_sim_step_fill(self.h), "ctu_sim_step_fill")
+
+    def step_hydro(self, dt):
+        est = (C.c_double * 2)()
+        nbad = (C.c_int * 2)()
+        rc = check(lib().ctu_sim_step_hydro(self.h, dt, est, nbad), "ctu_sim_step_hydro")
+        return rc, (est[0], est[1]), tuple(nbad)
+
+    def advance(self, nsteps, stop_time=-1.0, time=0.0, dt=-1.0):
+        t = C.c_double(time)
+        d = C.c_double(dt)
+        hist = (C.c_double * max(nsteps, 1))()
+        done = C.c_int(0)
+        rc = check(lib().ctu_sim_advance(self.h, nsteps, stop_time, C.byref(t), C.byref(d), hist, C.byref(done)), "ctu_sim_advance")
+        return rc, t.value, d.value, np.array(hist[:done.value])
+
+    @property
+    def launches(self):
+        return lib().ctu_workspace_launches(lib().ctu_sim_workspace(self.h))
+
+    @property
+    def last_slabs(self):
+        return lib().ctu_workspace_last_slabs(lib().ctu_sim_workspace(self.h))

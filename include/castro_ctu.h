@@ -125,29 +125,38 @@ void ctu_workspace_destroy(ctu_workspace_t* ws);
 size_t ctu_workspace_bytes(const ctu_workspace_t* ws);     /* bytes currently allocated */
 
 /* ---- the hot path -------------------------------------------------------------------------- */
+/* flags of ctu_hydro_advance */
+#define CTU_ADV_NCLEAN_MASK        3   /* low 2 bits: how many clean_state passes follow the update (0, 1 or 2) */
+#define CTU_ADV_SNEW_FROM_SBORDER  4   /* ignore S_new's input content and start from Sborder's valid zones
+                                          (== the reference's S_new <- Sborder copy, Castro_sources.cpp:627) */
 /*
  * Replaces the MFIter loop of Castro::construct_ctu_hydro_source (Castro_ctu_hydro.cpp:193-1407) for ONE
- * box, followed (optionally) by the epilogue of that function and of the step:
- *     check_for_negative_density (Castro_ctu_hydro.cpp:1436) -> n_bad[0] (rho), n_bad[1] (X)
- *     clean_state(S_new)         (Castro_ctu_hydro.cpp:1444)           if do_clean != 0
- *     estdt<hydro>(S_new)        (Castro_advance.cpp:298, Castro.cpp:1775) if dt_est != NULL
+ * box, followed by the epilogue of that function and (optionally) of the step, fused into the update kernel:
+ *     check_for_negative_density (Castro_ctu_hydro.cpp:1436)  -> n_bad[0] (rho), n_bad[1] (X)
+ *     clean_state(S_new)         (Castro_ctu_hydro.cpp:1444)   if (flags & 3) >= 1
+ *     clean_state(S_new) again   (Castro::post_timestep, Castro.cpp:2043-2050) if (flags & 3) == 2
+ *     estdt<hydro>(S_new)        after the first and after the last clean (Castro_advance.cpp:298, Castro.cpp:1775)
  * Inputs  Sborder : NUM_STATE comps, must cover grow(valid, 4), already ghost-filled + clean_state'd
- *         old_src, src_corr : NSRC=7 comps covering grow(valid,3), or NULL (== all zero, pure hydro)
+ *         old_src, src_corr : NSRC=7 comps covering grow(valid,3), or NULL (== all zero, pure hydro);
+ *                   non-NULL is not implemented yet (returns CTU_ERR_UNSUPPORTED)
  * In/out  S_new   : NUM_STATE comps covering valid; on entry holds Sborder's valid data (+ dt*old_src),
- *                   exactly like the reference (Castro_sources.cpp:627); may alias nothing else.
- *                   If S_new == NULL ... not allowed.
+ *                   exactly like the reference, unless CTU_ADV_SNEW_FROM_SBORDER is set.  Must not alias Sborder.
  * Outputs flux[d] : optional (NULL allowed) nodal-in-d, NUM_STATE comps, `+=` dt*A*F  (Castro_ctu_hydro.cpp:1297)
  *         mass_flux[d] : optional, 1 comp, `=` dt*A*F(URHO)                        (Castro_ctu_hydro.cpp:1333)
- *         dt_est  : HOST pointer; min over valid zones of dx_d/(c+|u_d|)  (NOT multiplied by cfl), dt_loc = (i,j,k)
- *         n_bad   : HOST int[2]
- * Returns status bits (0 ok).
+ *         dt_est  : HOST double[2] or NULL; min over valid zones of dx_d/(c+|u_d|) (NOT multiplied by cfl):
+ *                   [0] after the first clean pass, [1] after the last;  dt_loc = (i,j,k) of [1] or NULL
+ *         n_bad   : HOST int[2] or NULL
+ * Returns status bits (0 ok), or a negative error.
  */
 int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_geom_t* geom,
                       const int valid_lo[3], const int valid_hi[3],
                       const ctu_fab_t* Sborder, const ctu_fab_t* old_src, const ctu_fab_t* src_corr,
                       ctu_fab_t* S_new, ctu_fab_t* const flux[3], ctu_fab_t* const mass_flux[3],
-                      double dt, int do_clean, double* dt_est, int dt_loc[3], int n_bad[2],
+                      double dt, int flags, double dt_est[2], int dt_loc[3], int n_bad[2],
                       void* stream);
+/* diagnostics of the last advance: number of z-slabs used, kernels launched since creation */
+int ctu_workspace_last_slabs(const ctu_workspace_t* ws);
+int ctu_workspace_launches(const ctu_workspace_t* ws);
 
 /* timestep::estdt<hydro> on one box (timestep.H:64-157): *dt_min = min_d dx_d/(c+|u_d|) over [lo,hi] */
 int ctu_estdt(const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3], const int hi[3],
@@ -186,27 +195,34 @@ int ctu_parse_inputs(const char* path, const char* overrides, ctu_params_t* par,
                      int n_cell[3], int* max_step, double* stop_time,
                      char* prob_params_out, size_t prob_len);
 
-/* ---- single-box host driver (mirrors Amr::coarseTimeStep for max_level = 0) ------------------ */
+/* ---- single-box host driver (mirrors Amr::coarseTimeStep / Castro::advance for amr.max_level = 0) -------- */
 typedef struct ctu_sim ctu_sim_t;
-/* box [lo,hi] is this rank's share of the domain described by geom; the state lives in two ghosted device
- * buffers owned by the sim. */
+/* box [lo,hi] is this rank's share of the domain described by geom; the state lives in two ghosted (NUM_GROW)
+ * device buffers owned by the sim (Sborder and S_new ping-pong, so no S_new <- Sborder copy is ever made). */
 int  ctu_sim_create(ctu_sim_t** sim, const ctu_params_t* par, const ctu_geom_t* geom,
                     const int lo[3], const int hi[3], size_t workspace_bytes, void* stream);
 void ctu_sim_destroy(ctu_sim_t* sim);
 int  ctu_sim_state(ctu_sim_t* sim, ctu_fab_t* out);        /* view of the current (ghosted) state */
-/* step phases, split so that a multi-rank caller can interleave its halo exchange / allreduce:
- *   pre  : clean_state(S_old) [Castro_advance.cpp:487] + local estdt of S_old (pre-advance check)
- *   fill : local periodic wrap + physical BCs, then clean_state(Sborder, ng=4) [Castro_advance.cpp:169-170]
- *          (the caller exchanges inter-box halos between pre and fill)
- *   hydro: S_new <- Sborder; construct_ctu_hydro_source; clean_state(S_new); local estdt(S_new)   */
-int  ctu_sim_step_pre(ctu_sim_t* sim, double* dt_old_est);
-int  ctu_sim_step_fill(ctu_sim_t* sim);
-int  ctu_sim_step_hydro(ctu_sim_t* sim, double dt, double* dt_new_est, int n_bad[2]);
-/* convenience for a single box covering the whole domain: runs pre+fill+hydro and the dt control of
- * Castro::computeNewDt / computeInitialDt (Castro.cpp:1559-1573,1751-1992).  Returns status bits. */
+ctu_workspace_t* ctu_sim_workspace(ctu_sim_t* sim);
+/* valid zones <-> contiguous HOST array [ncomp][nz][ny][nx] (i fastest); synchronous */
+int  ctu_sim_download(ctu_sim_t* sim, double* host);
+int  ctu_sim_upload(ctu_sim_t* sim, const double* host);
 int  ctu_sim_init_problem(ctu_sim_t* sim, const char* problem, const char* prob_params);
+/* One step in three phases, so that a multi-rank caller can put its halo exchange and allreduce between them:
+ *   pre  : clean_state(S_old)                                   [Castro::initialize_advance, Castro_advance.cpp:487]
+ *   (caller: exchange the 4-zone halos with the other boxes -- ctu_halo_pack / ctu_halo_unpack)
+ *   fill : periodic self-wrap + physical BCs, clean_state(Sborder, 4) [initialize_do_advance, Castro_advance.cpp:167-170]
+ *   hydro: construct_ctu_hydro_source + clean_state (Castro_ctu_hydro.cpp:1444) + post_timestep's clean_state
+ *          (Castro.cpp:2043-2050); dt_est[0] / dt_est[1] = local min of dx/(c+|u|) after the first / second clean
+ *          (caller: min-allreduce dt_est, max-allreduce the returned status)                                      */
+int  ctu_sim_step_pre(ctu_sim_t* sim);
+int  ctu_sim_step_fill(ctu_sim_t* sim);
+int  ctu_sim_step_hydro(ctu_sim_t* sim, double dt, double dt_est[2], int n_bad[2]);
+/* Single box covering the whole domain: runs nsteps of pre+fill+hydro with the dt control of
+ * Castro::computeInitialDt / computeNewDt / subcycle_advance_ctu (Castro.cpp:1559-1573,1751-1992;
+ * Castro_advance_ctu.cpp:301-303).  Pass *dt_inout <= 0 on the first call.  Returns status bits. */
 int  ctu_sim_advance(ctu_sim_t* sim, int nsteps, double stop_time, double* time_inout, double* dt_inout,
-                     double* dt_history /* nsteps entries or NULL */);
+                     double* dt_history /* nsteps entries or NULL */, int* steps_done /* or NULL */);
 
 #ifdef __cplusplus
 }
