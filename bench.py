@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- zone-updates/s of the FP64 CTU-PPM hydro step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 512] [--solver 2]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+A "step" is one full coarse time step of the single-level 3-D Sedov problem (512^3 zones per GPU,
+gamma = 1.4, HLLC, outflow, cfl 0.5): clean_state(S_old) -> halo exchange (N > 1) -> physical-BC fill +
+clean_state(Sborder) -> construct_ctu_hydro_source (+ fused check_for_negative_density, clean_state x2, estdt x2)
+-> dt/status min-all-reduce -> host dt control; exactly what the parity tests check against the reference.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline     : the whole fused hydro pipeline of one box against the HBM roofline, algorithmic bytes =
+                 16*NUM_STATE B per zone-update (read U once, write U once), timed live with CUDA events
+                 on the launching stream (the C ABI's per-stage event timers, summed); "kernels" gives each kernel
+                 family's share so that the ncu launch list under profiles/ can be cross-checked
+  cpu_baseline : the UNMODIFIED reference executable (oracle/_ref, OpenMP build) on this box's host cores, bounded sample
+  e2e          : the same step driven through the C ABI with HOST buffers: pinned-host -> device upload of the state,
+                 the step, device -> pinned-host download of the new state, all inside the timed region
+`--impl reference` times the reference's own CPU implementation instead (rank 0 only).
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "zone-updates/sec (FP64 CTU-PPM, 3D Sedov 512^3 per GPU)"
+UNIT = "zone-updates/s"
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_sedov_omp.ex")
+REF_INPUTS = os.path.join(ROOT, "bench_inputs", "inputs.sedov3d")
+HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            if "hbm_gbs" in d:
+                return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---- reference CPU arm ------------------------------------------------------------------------------------------
+def run_reference_cpu(n_sample, steps, warmup, solver, threads=None):
+    """Runs the unmodified reference executable on a bounded sample (n_sample^3 zones) for warmup+steps coarse steps and
+    returns (zones/s over the timed steps, mean s/step, threads, description).  Falls back to the CPU port (liboracle,
+    1 thread) when the reference executable is not present."""
+    threads = threads or (os.cpu_count() or 1)
+    if os.path.exists(REF_EXE):
+        wd = tempfile.mkdtemp(prefix="refbench_")
+        mgs = 32 if n_sample >= 64 else 16
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        args = [REF_EXE, REF_INPUTS, "amr.n_cell=%d %d %d" % ((n_sample,) * 3), "amr.max_grid_size=%d" % mgs,
+                "max_step=%d" % (warmup + steps), "castro.riemann_solver=%d" % solver]
+        out = subprocess.run(args, cwd=wd, env=env, capture_output=True, text=True)
+        if out.returncode != 0:
+            raise RuntimeError("reference executable failed: " + out.stdout[-2000:] + out.stderr[-2000:])
+        ts = [float(x) for x in re.findall(r"\[STEP \d+\] Coarse TimeStep time: ([0-9.eE+-]+)", out.stdout)]
+        ts = ts[warmup:warmup + steps]
+        assert len(ts) == steps, "could not parse per-step times of the reference run"
+        tot = sum(ts)
+        desc = "%d^3 Sedov (max_grid_size %d), %d timed coarse steps after %d warm-up, OMP_NUM_THREADS=%d" % (
+            n_sample, mgs, steps, warmup, threads)
+        return n_sample ** 3 * steps / tot, tot / steps, threads, "reference", desc
+    # CPU port (single thread)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from cases import sedov_params
+    from castro_b200 import abi
+    n = min(n_sample, 32)
+    par = sedov_params(solver)
+    O.params_finalize(par)
+    geom = abi.make_geom((n, n, n))
+    U = O.sedov_init(par, geom, (n, n, n))
+    st, t, dt, _ = O.run(par, geom, U, warmup)
+    t0 = time.perf_counter()
+    st, t, dt, _ = O.run(par, geom, U, steps, time=t, dt=dt)
+    el = time.perf_counter() - t0
+    return n ** 3 * steps / el, el / steps, 1, "port", "%d^3 Sedov, %d steps, oracle/liboracle.so single thread" % (n, steps)
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    val, s_per_step, threads, kind, desc = run_reference_cpu(args.cpu_n, args.steps, args.warmup, args.solver)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    from castro_b200.dist import proc_grid
+    dims = proc_grid(world)
+    return {"workload": "Exec/hydro_tests/Sedov 3-D, %d^3 zones per GPU (global %s), gamma-law EOS gamma=1.4, CTU-PPM + %s, "
+                        "single level, outflow BCs, cfl 0.5" % (args.n, "x".join(str(args.n * d) for d in dims),
+                                                                "HLLC" if args.solver == 2 else "CGF"),
+            "zones_per_gpu": args.n ** 3, "num_state": 8, "proc_grid": list(dims),
+            "l2": "inputs larger than L2 (state %.1f GB per GPU); no explicit flush" % (8 * 8 * (args.n + 8) ** 3 / 1e9)}
+
+
+# ---- clocks -------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---- GPU arm ------------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, "--gpus %d but WORLD_SIZE %d" % (args.gpus, world)
+
+    from castro_b200 import lib, abi
+    from castro_b200.dist import DistSim, CudaBoxEngine, proc_grid
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+    dims = proc_grid(world)
+    n = args.n
+    n_cell = tuple(n * d for d in dims)
+    par = lib.default_params()
+    par.riemann_solver = args.solver
+    par.cfl, par.init_shrink, par.change_max = 0.5, 0.01, 1.1
+    par.eos_gamma, par.eos_assume_neutral = 1.4, 1
+    lib.params_finalize(par)
+    geom = abi.make_geom(n_cell, probhi=tuple(float(d) for d in dims))     # dx = 1/n whatever the process grid
+    prob = dict(r_init=0.01, p_ambient=1.e-5, exp_energy=1.0, dens_ambient=1.0, nsub=10)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sim = DistSim(par, geom, n_cell, lambda p, g, lo, hi: CudaBoxEngine(p, g, lo, hi, workspace_bytes=args.workspace_gb << 30),
+                  comm=dist, rank=rank, world=world, dims=dims)
+    sim.init_problem("Sedov", prob)
+    eng = sim.engine
+    ws = eng.sim.ws_handle
+    zones_local = n ** 3
+    zones_total = zones_local * world
+
+    # ---- warm-up -------------------------------------------------------------------------------------------------
+    st, _ = sim.advance(args.warmup)
+    assert st == 0, "warm-up step failed with status %d" % st
+    barrier()
+
+    # ---- timed region: K steps, device-resident state --------------------------------------------------------------
+    lib.workspace_set_profiling(ws, True)
+    lib.workspace_stage_times(ws, reset=True)
+    l0 = eng.launches + sim.exchange_launches
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    st, hist = sim.advance(args.steps)
+    e1.record()
+    barrier()
+    clk = clocks.stop() if clocks else None
+    assert st == 0 and len(hist) == args.steps, "timed steps failed with status %d" % st
+    ms = e0.elapsed_time(e1)
+    launches = eng.launches + sim.exchange_launches - l0
+    stages = lib.workspace_stage_times(ws, reset=True)
+    lib.workspace_set_profiling(ws, False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = zones_total * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, H2D + step + D2H per step ------------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    nbytes = 8 * par.num_state * zones_local
+    host = torch.empty((par.num_state, n, n, n), dtype=torch.float64, pin_memory=True)
+    hnp = host.numpy()
+    eng.sim.download(out=hnp)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        eng.sim.upload(hnp)                 # pinned host -> device (valid zones of this rank's box)
+        st, _ = sim.advance(1)
+        assert st == 0
+        eng.sim.download(out=hnp)           # device -> pinned host
+    f1.record()
+    barrier()
+    t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = zones_total * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        hydro_ms = sum(v[0] for v in stages.values())
+        hydro_launches = sum(v[1] for v in stages.values())
+        alg_bytes = 16 * par.num_state          # B per zone-update: read U once + write U once
+        achieved = zones_local * args.steps * alg_bytes / (hydro_ms * 1e-3) / 1e9 if hydro_ms > 0 else 0.0
+        top = max(stages, key=lambda k: stages[k][0])
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src,
+            "kernel": "ctu_hydro_advance pipeline (all kernels of construct_ctu_hydro_source for one box)",
+            "algorithmic_bytes_per_zone": alg_bytes,
+            "pipeline_ms_per_step": hydro_ms / args.steps, "pipeline_launches_per_step": hydro_launches / args.steps,
+            "top_kernel": top,
+            "kernels": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+                            "share": (v[0] / hydro_ms if hydro_ms else 0.0)} for k, v in stages.items() if v[1]},
+            "note": "FP64-pipe bound, not HBM bound, once fused (SURVEY §8d); see DESIGN.md and profiles/",
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                roofline["traffic"] = json.load(open(traffic_file)).get("pipeline_dram_bytes_per_zone")
+            except Exception:
+                pass
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, spp, threads, kind, desc = run_reference_cpu(args.cpu_n, args.cpu_steps, 1, args.solver)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, world),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": launches, "clocks": clk,
+            "halo_bytes_per_step_per_gpu": sim.halo_bytes_per_step,
+        }
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="zones per GPU per dimension")
+    ap.add_argument("--solver", type=int, default=2, help="castro.riemann_solver: 2 = HLLC, 0 = CGF")
+    ap.add_argument("--workspace-gb", type=int, default=48, help="device scratch bound for the z-slab pipeline")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-n", type=int, default=128, help="edge of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true", help="allow warmup < 3 (ncu runs only; never a bench value)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200" and not args.profile_mode:
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args, int(os.environ.get("RANK", "0")))
+        return
+    gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,40 @@ struct ctu_workspace {
     int last_slab_planes = 0;
     int last_num_slabs = 0;
     int kernel_launches = 0;
+    // optional per-stage device timing (CUDA events on the launching stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    double stage_ms[CTU_NSTAGE] = {0};
+    int stage_launches[CTU_NSTAGE] = {0};
+};
+
+static const char* const k_stage_names[CTU_NSTAGE] = {"k_ctoprim", "k_flat_div", "k_trace", "k_riemann1", "k_trans_riemann",
+                                                      "k_final", "k_update", "k_store_flux"};
+
+// records stage boundaries of one advance; elapsed times are folded into the workspace after the final sync
+struct StageTimer {
+    ctu_workspace* w;
+    cudaStream_t st;
+    struct Mark { int stage; int launches; size_t e0, e1; };
+    std::vector<Mark> marks;
+    size_t used = 0;
+    StageTimer(ctu_workspace* w_, cudaStream_t s) : w(w_), st(s) {}
+    size_t ev() {
+        if (used == w->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); w->ev_pool.push_back(e); }
+        cudaEventRecord(w->ev_pool[used], st);
+        return used++;
+    }
+    void begin(int stage) { if (w->profiling) marks.push_back({stage, 0, ev(), 0}); }
+    void end(int launches) { if (w->profiling) { marks.back().e1 = ev(); marks.back().launches = launches; } }
+    void fold() {
+        if (!w->profiling) return;
+        for (auto& m : marks) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, w->ev_pool[m.e0], w->ev_pool[m.e1]);
+            w->stage_ms[m.stage] += ms;
+            w->stage_launches[m.stage] += m.launches;
+        }
+    }
 };
 
 namespace ctu {
@@ -140,6 +174,7 @@ int ctu_workspace_create(ctu_workspace_t** ws, size_t max_bytes) {
 
 void ctu_workspace_destroy(ctu_workspace_t* w) {
     if (!w) return;
+    for (cudaEvent_t e : w->ev_pool) cudaEventDestroy(e);
     if (w->arena) cudaFree(w->arena);
     if (w->d_dtmin) cudaFree(w->d_dtmin);
     if (w->d_counters) cudaFree(w->d_counters);
@@ -151,6 +186,22 @@ void ctu_workspace_destroy(ctu_workspace_t* w) {
 size_t ctu_workspace_bytes(const ctu_workspace_t* w) { return w ? w->arena_bytes : 0; }
 int ctu_workspace_last_slabs(const ctu_workspace_t* w) { return w ? w->last_num_slabs : 0; }
 int ctu_workspace_launches(const ctu_workspace_t* w) { return w ? w->kernel_launches : 0; }
+
+int ctu_workspace_set_profiling(ctu_workspace_t* w, int on) {
+    if (!w) return CTU_ERR_BAD_ARG;
+    w->profiling = (on != 0);
+    return 0;
+}
+const char* ctu_stage_name(int i) { return (i >= 0 && i < CTU_NSTAGE) ? k_stage_names[i] : nullptr; }
+int ctu_workspace_stage_times(ctu_workspace_t* w, double ms[CTU_NSTAGE], int launches[CTU_NSTAGE], int reset) {
+    if (!w) return CTU_ERR_BAD_ARG;
+    for (int i = 0; i < CTU_NSTAGE; ++i) {
+        if (ms) ms[i] = w->stage_ms[i];
+        if (launches) launches[i] = w->stage_launches[i];
+        if (reset) { w->stage_ms[i] = 0.0; w->stage_launches[i] = 0; }
+    }
+    return 0;
+}
 
 static int ws_reserve(ctu_workspace* w, size_t bytes, cudaStream_t st) {
     if (bytes <= w->arena_bytes) return 0;
@@ -204,6 +255,7 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     CUDA_TRY(cudaMemcpyAsync(ws->d_dtmin, init, sizeof(init), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(ws->d_counters, 0, 4 * sizeof(int), st));
     int launches = 0;
+    StageTimer tm(ws, st);
 
     const double* dx = geom->dx;
     const double hdtd[3] = {0.5 * dt / dx[0], 0.5 * dt / dx[1], 0.5 * dt / dx[2]};
@@ -232,23 +284,28 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
         for (int n = 0; n < 3; ++n) for (int t = 0; t < 3; ++t) if (n != t) { F2[n][t] = make_a4(p, ibx); p += ni * NFX; }
 
         {   LaunchBox lb = make_lb(qbx);
-            k_ctoprim<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, qs, lb); ++launches; }
+            tm.begin(0);
+            k_ctoprim<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, qs, lb); ++launches; tm.end(1); }
         {   LaunchBox lb = make_lb(obx);
-            k_flat_div<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb); ++launches;
+            tm.begin(1);
+            k_flat_div<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb); ++launches; tm.end(1);
+            tm.begin(2);
             k_trace<0><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt);
             k_trace<1><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt);
-            k_trace<2><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt); launches += 3; }
+            k_trace<2><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt); launches += 3; tm.end(3); }
         const Box3 nb[3] = {[&] { Box3 b = tb; b.hi[0] += 1; return b; }(), [&] { Box3 b = tb; b.hi[1] += 1; return b; }(),
                             [&] { Box3 b = tb; b.hi[2] += 1; return b; }()};
         // first-pass fluxes: cxbx = grow(xbx,(0,1,1)), cybx = grow(ybx,(1,0,1)), czbx = grow(zbx,(1,1,0))
         {   LaunchBox lb = make_lb(grow(nb[0], 0, 1, 1));
+            tm.begin(3);
             k_riemann1<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb);
             lb = make_lb(grow(nb[1], 1, 0, 1));
             k_riemann1<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb);
             lb = make_lb(grow(nb[2], 1, 1, 0));
-            k_riemann1<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb); launches += 3; }
+            k_riemann1<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb); launches += 3; tm.end(3); }
         // F^{N|T}: box = nodal(N) grown by one in the third direction
         {   LaunchBox lb;
+            tm.begin(4);
             lb = make_lb(grow(nb[0], 0, 0, 1));   // F^{x|y}
             k_trans_riemann<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], F2[0][1], lb, cdtd[1]);
             lb = make_lb(grow(nb[0], 0, 1, 0));   // F^{x|z}
@@ -260,21 +317,23 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
             lb = make_lb(grow(nb[2], 0, 1, 0));   // F^{z|x}
             k_trans_riemann<2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[0], F2[2][0], lb, cdtd[0]);
             lb = make_lb(grow(nb[2], 1, 0, 0));   // F^{z|y}
-            k_trans_riemann<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1]); launches += 6; }
+            k_trans_riemann<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1]); launches += 6; tm.end(6); }
         // final fluxes overwrite the (now dead) first-pass flux storage
         {   LaunchBox lb;
+            tm.begin(5);
             lb = make_lb(nb[0]);
             k_final<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F2[1][2], F2[2][1], fd, Sb, F1[0], lb, hdtd[1], hdtd[2]);
             lb = make_lb(nb[1]);
             k_final<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F2[0][2], F2[2][0], fd, Sb, F1[1], lb, hdtd[0], hdtd[2]);
             lb = make_lb(nb[2]);
-            k_final<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F2[0][1], F2[1][0], fd, Sb, F1[2], lb, hdtd[0], hdtd[1]); launches += 3; }
+            k_final<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F2[0][1], F2[1][0], fd, Sb, F1[2], lb, hdtd[0], hdtd[1]); launches += 3; tm.end(3); }
         {   UpdateArgs ua;
             for (int d = 0; d < 3; ++d) ua.F[d] = F1[d];
             ua.dtmin = ws->d_dtmin; ua.counters = ws->d_counters;
             ua.n_clean = n_clean; ua.want_dt = (dt_est != nullptr);
             LaunchBox lb = make_lb(tb);
-            k_update<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, from_sb ? Sb : Sn, Sn, ua, lb, dt); ++launches; }
+            tm.begin(6);
+            k_update<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, from_sb ? Sb : Sn, Sn, ua, lb, dt); ++launches; tm.end(1); }
         for (int d = 0; d < 3; ++d) {
             const bool want_f = flux && flux[d], want_m = mass_flux && mass_flux[d];
             if (!want_f && !want_m) continue;
@@ -285,10 +344,11 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
             if (want_f) { if (!fab_covers(flux[d], fb) || flux[d]->ncomp < P.nstate) return CTU_ERR_BAD_ARG; fo = make_a4(*flux[d]); }
             if (want_m) { if (!fab_covers(mass_flux[d], fb)) return CTU_ERR_BAD_ARG; mo = make_a4(*mass_flux[d]); }
             LaunchBox lb = make_lb(fb);
+            tm.begin(7);
             if (d == 0) k_store_flux<0><<<nblocks(lb.n), TPB, 0, st>>>(P, F1[0], fo, mo, lb, dt);
             if (d == 1) k_store_flux<1><<<nblocks(lb.n), TPB, 0, st>>>(P, F1[1], fo, mo, lb, dt);
             if (d == 2) k_store_flux<2><<<nblocks(lb.n), TPB, 0, st>>>(P, F1[2], fo, mo, lb, dt);
-            ++launches;
+            ++launches; tm.end(1);
         }
     }
     if (dt_est && dt_loc) {
@@ -300,6 +360,7 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     CUDA_TRY(cudaMemcpyAsync(ws->h_dtmin, ws->d_dtmin, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(ws->h_counters, ws->d_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    tm.fold();
     int status = 0;
     if (ws->h_counters[0]) status |= CTU_STATUS_INVALID_DENSITY;
     if (ws->h_counters[1]) status |= CTU_STATUS_INVALID_X;

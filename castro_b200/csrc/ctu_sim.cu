@@ -391,6 +391,7 @@ struct ctu_sim {
     ctu_workspace_t* ws = nullptr;
     cudaStream_t st = 0;
     int step = 0;
+    int launches = 0;     // kernels launched by the sim itself (clean / fill / init), on top of the workspace's count
     ctu_fab_t fab(int which) const {
         ctu_fab_t f;
         f.p = buf[which];
@@ -603,6 +604,7 @@ int ctu_sim_state(ctu_sim_t* s, ctu_fab_t* out) {
 }
 
 ctu_workspace_t* ctu_sim_workspace(ctu_sim_t* s) { return s ? s->ws : nullptr; }
+int ctu_sim_launches(const ctu_sim_t* s) { return s ? s->launches + ctu_workspace_launches(s->ws) : 0; }
 
 // valid zones <-> contiguous HOST array [ncomp][nz][ny][nx] (pinned or pageable)
 static int sim_xfer(ctu_sim_t* s, double* host, bool download) {
@@ -636,6 +638,7 @@ int ctu_sim_init_problem(ctu_sim_t* s, const char* problem, const char* prob_par
 int ctu_sim_step_pre(ctu_sim_t* s) {
     if (!s) return CTU_ERR_BAD_ARG;
     ctu_fab_t f = s->fab(s->cur);
+    s->launches += 1;
     return ctu_clean_state(&s->par, s->vbx.lo, s->vbx.hi, &f, 1, s->st);
 }
 
@@ -645,6 +648,7 @@ int ctu_sim_step_fill(ctu_sim_t* s) {
     ctu_fab_t f = s->fab(s->cur);
     int rc = ctu_fill_boundary(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &f, CTU_NGROW, s->st);
     if (rc) return rc;
+    s->launches += 3;
     return ctu_clean_state(&s->par, s->gbx.lo, s->gbx.hi, &f, 1, s->st);
 }
 

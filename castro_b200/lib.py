@@ -38,11 +38,16 @@ def lib():
         L.ctu_workspace_bytes.argtypes = [C.c_void_p]
         L.ctu_workspace_last_slabs.argtypes = [C.c_void_p]
         L.ctu_workspace_launches.argtypes = [C.c_void_p]
+        L.ctu_workspace_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.ctu_stage_name.restype = C.c_char_p
+        L.ctu_stage_name.argtypes = [C.c_int]
+        L.ctu_workspace_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
         L.ctu_sim_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3,
                                      C.c_size_t, C.c_void_p]
         for fn in ("ctu_sim_destroy", "ctu_sim_step_pre", "ctu_sim_step_fill"):
             getattr(L, fn).argtypes = [C.c_void_p]
         L.ctu_sim_workspace.argtypes = [C.c_void_p]
+        L.ctu_sim_launches.argtypes = [C.c_void_p]
         L.ctu_sim_state.argtypes = [C.c_void_p, C.POINTER(abi.Fab)]
         L.ctu_sim_download.argtypes = [C.c_void_p, C.c_void_p]
         L.ctu_sim_upload.argtypes = [C.c_void_p, C.c_void_p]
@@ -73,6 +78,25 @@ def check(rc, what=""):
     if rc < 0:
         raise CtuError("%s failed: %s (%d)" % (what or "ctu call", _ERR.get(rc, "?"), rc))
     return rc
+
+
+NSTAGE = 8
+
+
+def stage_names():
+    return [lib().ctu_stage_name(i).decode() for i in range(NSTAGE)]
+
+
+def workspace_set_profiling(ws_handle, on):
+    check(lib().ctu_workspace_set_profiling(ws_handle, 1 if on else 0), "ctu_workspace_set_profiling")
+
+
+def workspace_stage_times(ws_handle, reset=False):
+    """-> {kernel family: (total ms, launches)} accumulated since the last reset"""
+    ms = (C.c_double * NSTAGE)()
+    nl = (C.c_int * NSTAGE)()
+    check(lib().ctu_workspace_stage_times(ws_handle, ms, nl, 1 if reset else 0), "ctu_workspace_stage_times")
+    return {n: (ms[i], nl[i]) for i, n in enumerate(stage_names())}
 
 
 def default_params():
@@ -244,6 +268,22 @@ class Sim:
         assert arr.shape == self.shape
         check(lib().ctu_sim_upload(self.h, arr.ctypes.data), "ctu_sim_upload")
 
+    def pack(self, lo, hi, buf, stream=0):
+        """region [lo,hi] x all comps of the current state -> contiguous torch CUDA buffer"""
+        f = self.state_fab()
+        check(lib().ctu_halo_pack(C.byref(f), abi.Int3(*lo), abi.Int3(*hi), buf.data_ptr(), stream), "ctu_halo_pack")
+
+    def unpack(self, lo, hi, buf, stream=0):
+        f = self.state_fab()
+        check(lib().ctu_halo_unpack(C.byref(f), abi.Int3(*lo), abi.Int3(*hi), buf.data_ptr(), stream), "ctu_halo_unpack")
+
+    def estdt(self, stream=0):
+        f = self.state_fab()
+        dt = C.c_double(0)
+        check(lib().ctu_estdt(C.byref(self.par), C.byref(self.geom), abi.Int3(*self.lo), abi.Int3(*self.hi), C.byref(f),
+                              C.byref(dt), None, stream), "ctu_estdt")
+        return dt.value
+
     def step_pre(self):
         check(lib().ctu_sim_step_pre(self.h), "ctu_sim_step_pre")
 
@@ -265,8 +305,12 @@ class Sim:
         return rc, t.value, d.value, np.array(hist[:done.value])
 
     @property
+    def ws_handle(self):
+        return C.c_void_p(lib().ctu_sim_workspace(self.h))
+
+    @property
     def launches(self):
-        return lib().ctu_workspace_launches(lib().ctu_sim_workspace(self.h))
+        return lib().ctu_sim_launches(self.h)
 
     @property
     def last_slabs(self):

@@ -157,6 +157,12 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
 /* diagnostics of the last advance: number of z-slabs used, kernels launched since creation */
 int ctu_workspace_last_slabs(const ctu_workspace_t* ws);
 int ctu_workspace_launches(const ctu_workspace_t* ws);
+/* optional per-stage device timing (CUDA events on the launching stream; used by bench.py for the roofline line):
+ * stage i covers every launch of the kernel family ctu_stage_name(i) inside ctu_hydro_advance. */
+#define CTU_NSTAGE 8
+int ctu_workspace_set_profiling(ctu_workspace_t* ws, int on);
+const char* ctu_stage_name(int i);
+int ctu_workspace_stage_times(ctu_workspace_t* ws, double ms[CTU_NSTAGE], int launches[CTU_NSTAGE], int reset);
 
 /* timestep::estdt<hydro> on one box (timestep.H:64-157): *dt_min = min_d dx_d/(c+|u_d|) over [lo,hi] */
 int ctu_estdt(const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3], const int hi[3],
@@ -204,6 +210,7 @@ int  ctu_sim_create(ctu_sim_t** sim, const ctu_params_t* par, const ctu_geom_t* 
 void ctu_sim_destroy(ctu_sim_t* sim);
 int  ctu_sim_state(ctu_sim_t* sim, ctu_fab_t* out);        /* view of the current (ghosted) state */
 ctu_workspace_t* ctu_sim_workspace(ctu_sim_t* sim);
+int  ctu_sim_launches(const ctu_sim_t* sim);               /* kernels launched so far by this sim (all phases) */
 /* valid zones <-> contiguous HOST array [ncomp][nz][ny][nx] (i fastest); synchronous */
 int  ctu_sim_download(ctu_sim_t* sim, double* host);
 int  ctu_sim_upload(ctu_sim_t* sim, const double* host);

@@ -60,7 +60,7 @@ def test_sim_matches_reference_golden(name):
     sim.close()
 
 
-@pytest.mark.parametrize("solver,n_cell,nslab_bytes", [(2, (16, 16, 16), 0), (0, (16, 16, 16), 0), (2, (24, 16, 20), 3 << 20)])
+@pytest.mark.parametrize("solver,n_cell,nslab_bytes", [(2, (16, 16, 16), 0), (0, (16, 16, 16), 0), (2, (24, 16, 20), 6 << 20)])
 def test_hydro_advance_vs_oracle(solver, n_cell, nslab_bytes):
     """one call of ctu_hydro_advance on an evolved state: S_new, flux registers, mass fluxes, dt estimate, status"""
     torch = _torch()
