@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <vector>
 
+#include <cstdlib>
 #include "ctu_kernels.cuh"
+#include "ctu_kernels_tma.cuh"
 #include "ctu_internal.h"
 
 using namespace ctu;
@@ -146,6 +148,126 @@ bool fab_covers(const ctu_fab_t* f, const Box3& b) {
 
 }  // namespace ctu
 
+
+// ---- launchers of the TMA-staged kernels (ctu_kernels_tma.cuh) ---------------------------------------------------
+namespace {
+
+// The tile-staged kernels cover the gamma-law EOS (Gamma_1 constant) with 1 or 2 passive scalars (Sod/Sedov: 1 species;
+// KH as shipped: 1 advected + 1 species); other set-ups run the register-staged kernels of ctu_kernels.cuh.
+// CTU_NO_TMA=1 forces the register-staged kernels (A/B measurements).
+bool tma_ok(const DevPar& P) {
+    static const bool disabled = (std::getenv("CTU_NO_TMA") != nullptr);
+    if (disabled || !P.gamc_const) return false;
+    if (P.npassive != 1 && P.npassive != 2) return false;
+    return tma::encode_fn() != nullptr;
+}
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { std::fprintf(stderr, "[castro_ctu] cudaFuncSetAttribute: %s\n", cudaGetErrorString(e)); return CTU_ERR_CUDA; }
+    return 0;
+}
+
+#define CTU_MAP(var, arr, abx, ncomp, Tile, nc)                                                              \
+    CUtensorMap var;                                                                                         \
+    if (!tma::make_map(&var, arr, abx, ncomp, Tile::EX, Tile::EY, Tile::EZ, nc)) return CTU_ERR_CUDA;
+
+template <int N, int NP>
+int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
+                  const Box3* nb, const double* cdtd, cudaStream_t st) {
+    using L = Trans2Smem<N, NP>;
+    constexpr int T1 = L::T1, T2 = L::T2;
+    static bool attr = false;
+    if (!attr) { int rc = set_smem(k_trans2_tma<N, NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    CTU_MAP(m_qm, ta.qm[N], ibx, L::NIS, FaceTile, L::NIS)
+    CTU_MAP(m_qp, ta.qp[N], ibx, L::NIS, FaceTile, L::NIS)
+    CTU_MAP(m_f1, F1[T1], ibx, L::NFX, L::F1T, L::NFX)
+    CTU_MAP(m_f2, F1[T2], ibx, L::NFX, L::F2T, L::NFX)
+    CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
+    Trans2Args a;
+    a.Fo1 = F2[N][T1]; a.Fo2 = F2[N][T2];
+    int g1[3] = {0, 0, 0}, g2[3] = {0, 0, 0}, gu[3] = {0, 0, 0};
+    g1[T2] = 1; g2[T1] = 1; gu[T1] = 1; gu[T2] = 1;
+    a.b1 = grow(nb[N], g1[0], g1[1], g1[2]);       // F^{N|T1} lives on nodal(N) grown by one in T2
+    a.b2 = grow(nb[N], g2[0], g2[1], g2[2]);
+    for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
+    a.cdt1 = cdtd[T1]; a.cdt2 = cdtd[T2];
+    const TileGrid tg = make_tg(grow(nb[N], gu[0], gu[1], gu[2]));
+    k_trans2_tma<N, NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg);
+    return 0;
+}
+
+template <int NP>
+int launch_trans2_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
+                     const Box3* nb, const double* cdtd, cudaStream_t st) {
+    int rc = launch_trans2<0, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    if (!rc) rc = launch_trans2<1, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    if (!rc) rc = launch_trans2<2, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    return rc;
+}
+int launch_trans2_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1,
+                      A4 (*F2)[3], const Box3* nb, const double* cdtd, cudaStream_t st) {
+    if (np == 1) return launch_trans2_np<1>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    return launch_trans2_np<2>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+}
+
+template <int N, int NP>
+int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
+                 const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
+    using L = FinalSmem<N, NP>;
+    constexpr int T1 = L::T1, T2 = L::T2;
+    static bool attr = false;
+    if (!attr) { int rc = set_smem(k_final_tma<N, NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    CTU_MAP(m_qm, ta.qm[N], ibx, L::NIS, FaceTile, L::NIS)
+    CTU_MAP(m_qp, ta.qp[N], ibx, L::NIS, FaceTile, L::NIS)
+    CTU_MAP(m_f1, F2[T1][T2], ibx, L::NFX, L::F1T, L::NFX)
+    CTU_MAP(m_f2, F2[T2][T1], ibx, L::NFX, L::F2T, L::NFX)
+    CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
+    CTU_MAP(m_d, fd, ibx, 2, L::DT, 1)
+    FinalArgs a;
+    a.U = Sb; a.Fo = F1[N];
+    for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
+    a.c1 = hdtd[T1]; a.c2 = hdtd[T2];
+    const TileGrid tg = make_tg(nb[N]);
+    k_final_tma<N, NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, m_d, a, tg);
+    return 0;
+}
+template <int NP>
+int launch_final_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
+                    const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
+    int rc = launch_final<0, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    if (!rc) rc = launch_final<1, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    if (!rc) rc = launch_final<2, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    return rc;
+}
+int launch_final_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd,
+                     const A4& Sb, const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
+    if (np == 1) return launch_final_np<1>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    return launch_final_np<2>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+}
+
+template <int NP>
+int launch_update_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,
+                     const Box3& tb, double dt, cudaStream_t st) {
+    using L = UpdateSmem<NP>;
+    static bool attr = false;
+    if (!attr) { int rc = set_smem(k_update_tma<NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    CTU_MAP(m_f0, F[0], ibx, L::NFX, L::F0T, L::NFX)
+    CTU_MAP(m_f1, F[1], ibx, L::NFX, L::F1T, L::NFX)
+    CTU_MAP(m_f2, F[2], ibx, L::NFX, L::F2T, L::NFX)
+    const TileGrid tg = make_tg(tb);
+    k_update_tma<NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_f0, m_f1, m_f2, Sb, Sin, Sn, ua, ibx.lo[0], ibx.lo[1], ibx.lo[2], tg, dt);
+    return 0;
+}
+int launch_update(const DevPar& P, int np, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,
+                  const Box3& tb, double dt, cudaStream_t st) {
+    if (np == 1) return launch_update_np<1>(P, F, ibx, Sb, Sin, Sn, ua, tb, dt, st);
+    return launch_update_np<2>(P, F, ibx, Sb, Sin, Sn, ua, tb, dt, st);
+}
+
+}  // namespace
+
 // ================================================================================================
 extern "C" {
 
@@ -234,9 +356,13 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
 
     const int NQS = QS_X + np, NIS = IS_X + np, NFX = FX_X + np;
     const long nxg = (vbx.hi[0] - vbx.lo[0] + 1), nyg = (vbx.hi[1] - vbx.lo[1] + 1), nzv = (vbx.hi[2] - vbx.lo[2] + 1);
+    // scratch rows are padded to an even number of doubles: every row / plane / component stride is then a multiple of
+    // 16 bytes, which is what the TMA tensor maps of the tile-staged kernels require
+    const long qpad = (nxg + 8) & 1, ipad = (nxg + 3) & 1;
     // per z-plane scratch: qs on grow(tile,4); everything else on ibx = [lo-1, hi+2]
-    const size_t plane_q = (size_t)(nxg + 8) * (nyg + 8) * NQS * sizeof(double);
-    const size_t plane_i = (size_t)(nxg + 4) * (nyg + 4) * (size_t)(2 + 6 * NIS + 9 * NFX) * sizeof(double);
+    const size_t plane_q = (size_t)(nxg + 8 + qpad) * (nyg + 8) * NQS * sizeof(double);
+    const size_t plane_i = (size_t)(nxg + 3 + ipad) * (nyg + 4) * (size_t)(2 + 6 * NIS + 9 * NFX) * sizeof(double);
+    const bool use_tma = tma_ok(P);
     // bytes(KS) = plane_q*(KS+8) + plane_i*(KS+4)
     long KS = (long)((double)(ws->max_bytes - std::min(ws->max_bytes, 8 * plane_q + 4 * plane_i)) / (double)(plane_q + plane_i));
     if (KS < 1) return CTU_ERR_NOMEM;
@@ -268,9 +394,11 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
         const Box3 qbx = grow(tb, 4);
         const Box3 obx = grow(tb, 1);
         Box3 ibx = obx; ibx.hi[0] += 1; ibx.hi[1] += 1; ibx.hi[2] += 1;
+        Box3 qbx_a = qbx; qbx_a.hi[0] += (int)qpad;      // allocation boxes (padded rows)
+        ibx.hi[0] += (int)ipad;
         // carve the arena
         double* p = ws->arena;
-        const A4 qs = make_a4(p, qbx); p += qbx.npts() * NQS;
+        const A4 qs = make_a4(p, qbx_a); p += qbx_a.npts() * NQS;
         const size_t ni = ibx.npts();
         const A4 fd = make_a4(p, ibx); p += ni * 2;
         TraceArgs ta;
@@ -304,6 +432,12 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
             lb = make_lb(grow(nb[2], 1, 1, 0));
             k_riemann1<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb); launches += 3; tm.end(3); }
         // F^{N|T}: box = nodal(N) grown by one in the third direction
+        if (use_tma) {
+            tm.begin(4);
+            rc = launch_trans2_all(P, np, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+            if (rc) return rc;
+            launches += 3; tm.end(3);
+        } else
         {   LaunchBox lb;
             tm.begin(4);
             lb = make_lb(grow(nb[0], 0, 0, 1));   // F^{x|y}
@@ -319,6 +453,12 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
             lb = make_lb(grow(nb[2], 1, 0, 0));   // F^{z|y}
             k_trans_riemann<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1]); launches += 6; tm.end(6); }
         // final fluxes overwrite the (now dead) first-pass flux storage
+        if (use_tma) {
+            tm.begin(5);
+            rc = launch_final_all(P, np, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+            if (rc) return rc;
+            launches += 3; tm.end(3);
+        } else
         {   LaunchBox lb;
             tm.begin(5);
             lb = make_lb(nb[0]);
@@ -333,7 +473,13 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
             ua.n_clean = n_clean; ua.want_dt = (dt_est != nullptr);
             LaunchBox lb = make_lb(tb);
             tm.begin(6);
-            k_update<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, from_sb ? Sb : Sn, Sn, ua, lb, dt); ++launches; tm.end(1); }
+            if (use_tma) {
+                rc = launch_update(P, np, F1, ibx, Sb, from_sb ? Sb : Sn, Sn, ua, tb, dt, st);
+                if (rc) return rc;
+            } else {
+                k_update<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, from_sb ? Sb : Sn, Sn, ua, lb, dt);
+            }
+            ++launches; tm.end(1); }
         for (int d = 0; d < 3; ++d) {
             const bool want_f = flux && flux[d], want_m = mass_flux && mass_flux[d];
             if (!want_f && !want_m) continue;

@@ -1,0 +1,482 @@
+// ctu_kernels_tma.cuh -- TMA-staged versions of the flux-stage kernels (the 70 % of the step that was latency-bound).
+//
+// One CTA = one 32x4x2 tile of faces (or zones).  Thread 0 issues one cp.async.bulk.tensor per input array (tile + the
+// one-zone halo the stage needs); everybody waits once on the mbarrier; all operands are then read from shared memory
+// with compile-time strides.  NP (number of passively advected scalars) is a template parameter, so the passive loops
+// unroll into registers.  The arithmetic is exactly that of ctu_kernels.cuh (same helper functions, same operation
+// order): results are bit-identical, which the parity tests check.
+//
+//   k_trans2_tma<N>   trans_single with BOTH transverse directions of normal N, each fused with its Riemann solve:
+//                     F^{N|T1} and F^{N|T2} from one staging of the q_N^-/q_N^+ tile        [SURVEY §8 a15 + a12]
+//   k_final_tma<N>    trans_final + final Riemann + zero T flux + artificial viscosity + species-flux
+//                     normalisation                                                          [a16 + a12 + a18]
+//   k_update_tma      consup_hydro + check_for_negative_density + clean_state + estdt        [a19, a22, a20]
+#pragma once
+#include "ctu_kernels.cuh"
+#include "ctu_tma.cuh"
+
+namespace ctu {
+
+constexpr int TX = 32, TY = 4, TZ = 2, TTHR = TX * TY * TZ;
+constexpr int ceven(int n) { return (n + 1) & ~1; }
+constexpr size_t al128(size_t b) { return (b + 127) & ~(size_t)127; }
+
+struct TileGrid {
+    int lo0, lo1, lo2, hi0, hi1, hi2;   // launch box
+    int ntx, nty, ntz;
+};
+inline TileGrid make_tg(const Box3& b) {
+    TileGrid t;
+    t.lo0 = b.lo[0]; t.lo1 = b.lo[1]; t.lo2 = b.lo[2]; t.hi0 = b.hi[0]; t.hi1 = b.hi[1]; t.hi2 = b.hi[2];
+    t.ntx = (b.hi[0] - b.lo[0] + TX) / TX; t.nty = (b.hi[1] - b.lo[1] + TY) / TY; t.ntz = (b.hi[2] - b.lo[2] + TZ) / TZ;
+    return t;
+}
+inline unsigned tg_blocks(const TileGrid& t) { return (unsigned)t.ntx * (unsigned)t.nty * (unsigned)t.ntz; }
+
+struct TileCtx { int i0, j0, k0, tx, ty, tz, i, j, k; };
+__device__ __forceinline__ TileCtx tile_ctx(const TileGrid& tg) {
+    TileCtx c;
+    const int bt = blockIdx.x;
+    const int bx = bt % tg.ntx, r = bt / tg.ntx, by = r % tg.nty, bz = r / tg.nty;
+    c.i0 = tg.lo0 + bx * TX; c.j0 = tg.lo1 + by * TY; c.k0 = tg.lo2 + bz * TZ;
+    c.tx = threadIdx.x & (TX - 1); c.ty = (threadIdx.x / TX) % TY; c.tz = threadIdx.x / (TX * TY);
+    c.i = c.i0 + c.tx; c.j = c.j0 + c.ty; c.k = c.k0 + c.tz;
+    return c;
+}
+
+// shared-memory tile [comp][z][y][x], dense
+template <int EX_, int EY_, int EZ_>
+struct STile {
+    static constexpr int EX = EX_, EY = EY_, EZ = EZ_, ZONES = EX_ * EY_ * EZ_;
+    const double* __restrict__ s;
+    __device__ __forceinline__ double operator()(int off, int n) const { return s[n * ZONES + off]; }
+    static __device__ __forceinline__ int off(int x, int y, int z) { return (z * EY + y) * EX + x; }
+    static __host__ __device__ constexpr int stride(int d) { return d == 0 ? 1 : d == 1 ? EX_ : EX_ * EY_; }
+};
+// A TMA box must start on a 16-byte boundary, i.e. at an EVEN x coordinate for FP64.  Every tile is therefore fetched from
+// the even coordinate at or below its true origin (shift px = origin & 1, uniform over the launch) and is EXT = TX + 2
+// doubles wide in x: room for the widest stencil (TX + 1) plus the parity shift.  In-tile x offsets are tx + px.
+constexpr int EXT = TX + 2;
+using FaceTile = STile<EXT, TY, TZ>;
+// T-face fluxes of the two zones adjacent to the N-faces of the tile: origin = tile origin - e_N, +1 on the high side in T
+template <int N, int T>
+using FluxTile = STile<EXT, TY + (N == 1) + (T == 1), TZ + (N == 2) + (T == 2)>;
+// zone-centred scalars of the two zones adjacent to the N-faces: origin = tile origin - e_N
+template <int N>
+using ZoneTile = STile<EXT, TY + (N == 1), TZ + (N == 2)>;
+// nodal div(u) at the four nodes of an N-face: origin = tile origin, +1 on the high side in both transverse directions
+template <int N>
+using NodeTile = STile<EXT, TY + (N != 1), TZ + (N != 2)>;
+// N-face fluxes of the zones of the tile: origin = tile origin, +1 on the high side in N
+template <int N>
+using OwnFluxTile = STile<EXT, TY + (N == 1), TZ + (N == 2)>;
+
+template <int NP>
+__device__ __forceinline__ bool is_species(const DevPar& P, int ip) { return ip >= P.QFS_off && ip < P.QFS_off + P.nspec; }
+
+// Riemann solve on register states with register passives (Castro::cmpflx_plus_godunov, riemann.cpp:15-200)
+template <int DIR, int NP>
+__device__ __forceinline__ void solve_face_r(const DevPar& P, const double* ql, const double* qr, const double* xl, const double* xr,
+                                             double cl, double cr, int idx, double* F, double& ugd, double& pgd, double* FX) {
+    const bool sp_lo = P.lo_bc[DIR] >= 3 && P.lo_bc[DIR] <= 5, sp_hi = P.hi_bc[DIR] >= 3 && P.hi_bc[DIR] <= 5;
+    double bnd_fac = 1.0;
+    if ((idx == P.domlo[DIR] && sp_lo) || (idx == P.domhi[DIR] + 1 && sp_hi)) bnd_fac = 0.0;
+    PassiveUpwind pu;
+    if (P.riemann_solver == 0) {
+        auto sel = [&](const double* x, int n) {
+            double r = 0.0;
+#pragma unroll
+            for (int ip = 0; ip < NP; ++ip) if (ip == P.QFS_off + n) r = x[ip];
+            return r;
+        };
+        riemann_cgf<DIR>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, [&](int n) { return sel(xl, n); }, [&](int n) { return sel(xr, n); },
+                         F, ugd, pgd, pu);
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) FX[ip] = passive_flux_cgf(pu, xl[ip], xr[ip]);
+    } else {
+        riemann_hllc<DIR>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, F, ugd, pgd, pu);
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) FX[ip] = passive_flux_hllc(pu, xl[ip], xr[ip]);
+    }
+}
+
+// actual_trans_single for one state (trans.cpp:67-498): zone at tile offset oz of the T-flux tile sF
+template <int NP, class FT, int ST>
+__device__ __forceinline__ void trans_single_side(const DevPar& P, const FT& sF, int oz, const double* q, const double* x, double cdt,
+                                                  double* qo, double* xo) {
+    double fl[6], fr[6], dX[NP];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) { fl[n] = sF(oz, n); fr[n] = sF(oz + ST, n); }
+    const double ugm = sF(oz, FX_UG), ugp = sF(oz + ST, FX_UG), pgm = sF(oz, FX_PG), pgp = sF(oz + ST, FX_PG);
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) dX[ip] = cdt * (sF(oz + ST, FX_X + ip) - sF(oz, FX_X + ip));
+    const double rho = q[IS_RHO];
+    const double rrnew = rho - cdt * (fr[0] - fl[0]);
+    bool reset = (P.transverse_reset_density && rrnew < 0.0);
+    double xn[NP];
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) {
+        xn[ip] = (rho * x[ip] - dX[ip]) / rrnew;
+        if (is_species<NP>(P, ip) && (xn[ip] > 1.0 + P.abundance_failure_tolerance || xn[ip] < -P.abundance_failure_tolerance)) reset = true;
+    }
+    trans_single_hydro(P, q, qo, fl, fr, ugm, ugp, pgm, pgp, P.gamma, cdt, rrnew, reset);
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) xo[ip] = reset ? x[ip] : xn[ip];
+}
+
+// actual_trans_final for one state (trans.cpp:559-968)
+template <int NP, class F1T, int S1, class F2T, int S2>
+__device__ __forceinline__ void trans_final_side(const DevPar& P, const F1T& sF1, int o1, const F2T& sF2, int o2, const double* q,
+                                                 const double* x, double c1, double c2, double* qo, double* xo) {
+    double f1l[6], f1r[6], f2l[6], f2r[6];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) { f1l[n] = sF1(o1, n); f1r[n] = sF1(o1 + S1, n); f2l[n] = sF2(o2, n); f2r[n] = sF2(o2 + S2, n); }
+    const double rho = q[IS_RHO];
+    const double rrnew = rho - c1 * (f1r[0] - f1l[0]) - c2 * (f2r[0] - f2l[0]);
+    bool reset = (P.transverse_reset_density && rrnew < 0.0);
+    double xn[NP];
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) {
+        xn[ip] = (rho * x[ip] - c1 * (sF1(o1 + S1, FX_X + ip) - sF1(o1, FX_X + ip)) - c2 * (sF2(o2 + S2, FX_X + ip) - sF2(o2, FX_X + ip))) / rrnew;
+        if (is_species<NP>(P, ip) && (xn[ip] > 1.0 + P.abundance_failure_tolerance || xn[ip] < -P.abundance_failure_tolerance)) reset = true;
+    }
+    trans_final_hydro(P, q, qo, f1l, f1r, f2l, f2r, sF1(o1, FX_UG), sF1(o1 + S1, FX_UG), sF1(o1, FX_PG), sF1(o1 + S1, FX_PG),
+                      sF2(o2, FX_UG), sF2(o2 + S2, FX_UG), sF2(o2, FX_PG), sF2(o2 + S2, FX_PG), P.gamma, c1, c2, rrnew, reset);
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) xo[ip] = reset ? x[ip] : xn[ip];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_trans2_tma
+// ------------------------------------------------------------------------------------------------
+template <int N, int NP>
+struct Trans2Smem {
+    static constexpr int T1 = (N == 0) ? 1 : 0, T2 = (N == 2) ? 1 : 2;
+    static constexpr int NIS = IS_X + NP, NFX = FX_X + NP;
+    using F1T = FluxTile<N, T1>;
+    using F2T = FluxTile<N, T2>;
+    using CT = ZoneTile<N>;
+    static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = (size_t)NFX * F1T::ZONES * 8, B_F2 = (size_t)NFX * F2T::ZONES * 8,
+                            B_C = (size_t)CT::ZONES * 8;
+    static constexpr size_t O_QM = 0, O_QP = al128(O_QM + B_Q), O_F1 = al128(O_QP + B_Q), O_F2 = al128(O_F1 + B_F1),
+                            O_C = al128(O_F2 + B_F2), O_BAR = al128(O_C + B_C), TOTAL = O_BAR + 128;
+    static constexpr unsigned TX_BYTES = (unsigned)(2 * B_Q + B_F1 + B_F2 + B_C);
+};
+
+struct Trans2Args {
+    A4 Fo1, Fo2;          // outputs F^{N|T1}, F^{N|T2}
+    Box3 b1, b2;          // their boxes
+    int ilo[3], qlo[3];   // low corners of the interface-array box and of the qs box (TMA coordinates are relative to them)
+    double cdt1, cdt2;
+};
+
+template <int N, int NP>
+static __global__ void __launch_bounds__(TTHR, 2)
+k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
+             const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
+             const Trans2Args a, const TileGrid tg) {
+    using L = Trans2Smem<N, NP>;
+    constexpr int T1 = L::T1, T2 = L::T2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    const TileCtx c = tile_ctx(tg);
+    // x coordinates of the tile origins in their arrays and their parity shifts (see EXT)
+    const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
+    const int gi = fi - (N == 0), pg = gi & 1;
+    const int qi = c.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
+        tma::load_4d(smem + L::O_QM, &m_qm, bar, fi - pf, fj, fk, 0);
+        tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
+        tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
+    }
+    tma::mbar_wait(bar, 0);
+    const bool in1 = a.b1.contains(c.i, c.j, c.k), in2 = a.b2.contains(c.i, c.j, c.k);
+    if (!in1 && !in2) return;
+    const FaceTile sQM{reinterpret_cast<const double*>(smem + L::O_QM)}, sQP{reinterpret_cast<const double*>(smem + L::O_QP)};
+    const typename L::F1T sF1{reinterpret_cast<const double*>(smem + L::O_F1)};
+    const typename L::F2T sF2{reinterpret_cast<const double*>(smem + L::O_F2)};
+    const typename L::CT sC{reinterpret_cast<const double*>(smem + L::O_C)};
+    const int of = FaceTile::off(c.tx + pf, c.ty, c.tz);
+    double ql[6], qr[6], xl[NP], xr[NP];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) { ql[n] = sQM(of, n); qr[n] = sQP(of, n); }
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) { xl[ip] = sQM(of, IS_X + ip); xr[ip] = sQP(of, IS_X + ip); }
+    const int oc = L::CT::off(c.tx + pq, c.ty, c.tz);
+    const double cl = sC(oc, 0), cr = sC(oc + L::CT::stride(N), 0);
+    const int idx = (N == 0) ? c.i : (N == 1) ? c.j : c.k;
+    if (in1) {
+        constexpr int sN = L::F1T::stride(N), sT = L::F1T::stride(T1);
+        const int oz = L::F1T::off(c.tx + pg, c.ty, c.tz);
+        double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
+        trans_single_side<NP, typename L::F1T, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
+        trans_single_side<NP, typename L::F1T, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
+        solve_face_r<N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+        const long o = a.Fo1.idx(c.i, c.j, c.k);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) a.Fo1.at(o, n) = F[n];
+        a.Fo1.at(o, FX_UG) = ugd;
+        a.Fo1.at(o, FX_PG) = pgd;
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) a.Fo1.at(o, FX_X + ip) = FX[ip];
+    }
+    if (in2) {
+        constexpr int sN = L::F2T::stride(N), sT = L::F2T::stride(T2);
+        const int oz = L::F2T::off(c.tx + pg, c.ty, c.tz);
+        double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
+        trans_single_side<NP, typename L::F2T, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
+        trans_single_side<NP, typename L::F2T, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
+        solve_face_r<N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+        const long o = a.Fo2.idx(c.i, c.j, c.k);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) a.Fo2.at(o, n) = F[n];
+        a.Fo2.at(o, FX_UG) = ugd;
+        a.Fo2.at(o, FX_PG) = pgd;
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) a.Fo2.at(o, FX_X + ip) = FX[ip];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_final_tma
+// ------------------------------------------------------------------------------------------------
+template <int N, int NP>
+struct FinalSmem {
+    static constexpr int T1 = (N == 0) ? 1 : 0, T2 = (N == 2) ? 1 : 2;
+    static constexpr int NIS = IS_X + NP, NFX = FX_X + NP;
+    using F1T = FluxTile<N, T1>;
+    using F2T = FluxTile<N, T2>;
+    using CT = ZoneTile<N>;
+    using DT = NodeTile<N>;
+    static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = (size_t)NFX * F1T::ZONES * 8, B_F2 = (size_t)NFX * F2T::ZONES * 8,
+                            B_C = (size_t)CT::ZONES * 8, B_D = (size_t)DT::ZONES * 8;
+    static constexpr size_t O_QM = 0, O_QP = al128(O_QM + B_Q), O_F1 = al128(O_QP + B_Q), O_F2 = al128(O_F1 + B_F1),
+                            O_C = al128(O_F2 + B_F2), O_D = al128(O_C + B_C), O_BAR = al128(O_D + B_D), TOTAL = O_BAR + 128;
+    static constexpr unsigned TX_BYTES = (unsigned)(2 * B_Q + B_F1 + B_F2 + B_C + B_D);
+};
+
+struct FinalArgs {
+    A4 U;                 // Sborder (artificial viscosity needs U_i - U_{i-1})
+    A4 Fo;                // output: final flux on N-faces
+    int ilo[3], qlo[3];
+    double c1, c2;        // dt/(2 dx_T1), dt/(2 dx_T2)
+};
+
+template <int N, int NP>
+static __global__ void __launch_bounds__(TTHR, 2)
+k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
+            const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
+            const __grid_constant__ CUtensorMap m_d, const FinalArgs a, const TileGrid tg) {
+    using L = FinalSmem<N, NP>;
+    constexpr int T1 = L::T1, T2 = L::T2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    const TileCtx c = tile_ctx(tg);
+    const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
+    const int gi = fi - (N == 0), pg = gi & 1;
+    const int qi = c.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
+        tma::load_4d(smem + L::O_QM, &m_qm, bar, fi - pf, fj, fk, 0);
+        tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
+        tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
+        tma::load_4d(smem + L::O_D, &m_d, bar, fi - pf, fj, fk, 1);
+    }
+    const bool active = c.i <= tg.hi0 && c.j <= tg.hi1 && c.k <= tg.hi2;
+    // conserved-state differences for the artificial viscosity: plain global loads, in flight while the tile lands
+    double dU[6], dUX[NP];
+    if (active) {
+        const long ou = a.U.idx(c.i, c.j, c.k);
+        const long oum = ou - ((N == 0) ? 1 : (N == 1) ? a.U.sj : a.U.sk);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) dU[n] = a.U.at(ou, n) - a.U.at(oum, n);
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) dUX[ip] = a.U.at(ou, UFA + ip) - a.U.at(oum, UFA + ip);
+    }
+    tma::mbar_wait(bar, 0);
+    if (!active) return;
+    const FaceTile sQM{reinterpret_cast<const double*>(smem + L::O_QM)}, sQP{reinterpret_cast<const double*>(smem + L::O_QP)};
+    const typename L::F1T sF1{reinterpret_cast<const double*>(smem + L::O_F1)};
+    const typename L::F2T sF2{reinterpret_cast<const double*>(smem + L::O_F2)};
+    const typename L::CT sC{reinterpret_cast<const double*>(smem + L::O_C)};
+    const typename L::DT sD{reinterpret_cast<const double*>(smem + L::O_D)};
+    const int of = FaceTile::off(c.tx + pf, c.ty, c.tz);
+    double ql[6], qr[6], xl[NP], xr[NP];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) { ql[n] = sQM(of, n); qr[n] = sQP(of, n); }
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) { xl[ip] = sQM(of, IS_X + ip); xr[ip] = sQP(of, IS_X + ip); }
+    const int oc = L::CT::off(c.tx + pq, c.ty, c.tz);
+    const double cl = sC(oc, 0), cr = sC(oc + L::CT::stride(N), 0);
+    const int idx = (N == 0) ? c.i : (N == 1) ? c.j : c.k;
+    constexpr int s1N = L::F1T::stride(N), s1T = L::F1T::stride(T1), s2N = L::F2T::stride(N), s2T = L::F2T::stride(T2);
+    const int o1 = L::F1T::off(c.tx + pg, c.ty, c.tz), o2 = L::F2T::off(c.tx + pg, c.ty, c.tz);
+    double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
+    trans_final_side<NP, typename L::F1T, s1T, typename L::F2T, s2T>(P, sF1, o1, sF2, o2, ql, xl, a.c1, a.c2, qlo, xlo);
+    trans_final_side<NP, typename L::F1T, s1T, typename L::F2T, s2T>(P, sF1, o1 + s1N, sF2, o2 + s2N, qr, xr, a.c1, a.c2, qro, xro);
+    solve_face_r<N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+
+    // apply_av (advection_util.cpp:354-419): div1 = difmag * min(0, <div u> over the 4 nodes of the face)
+    const int od = L::DT::off(c.tx + pf, c.ty, c.tz);
+    constexpr int d1 = L::DT::stride(T1), d2 = L::DT::stride(T2);
+    double div1 = 0.25 * (sD(od, 0) + sD(od + d1, 0) + sD(od + d2, 0) + sD(od + d1 + d2, 0));
+    div1 = P.difmag * smin(0.0, div1);
+    const double dL = P.dx[N];
+    const long o = a.Fo.idx(c.i, c.j, c.k);
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+        const double div_var = div1 * dU[n];
+        F[n] += dL * div_var;
+        a.Fo.at(o, n) = F[n];
+    }
+    a.Fo.at(o, FX_UG) = ugd;
+    a.Fo.at(o, FX_PG) = pgd;
+    // passives + normalize_species_fluxes (advection_util.cpp:473-509)
+    double sum = 0.0;
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) {
+        const double div_var = div1 * dUX[ip];
+        FX[ip] += dL * div_var;
+        if (is_species<NP>(P, ip)) sum += FX[ip];
+    }
+    double fac = 1.0;
+    if (fabs(sum) > 2.220446049250313e-16 * fabs(F[0])) fac = F[0] / sum;
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) a.Fo.at(o, FX_X + ip) = is_species<NP>(P, ip) ? FX[ip] * fac : FX[ip];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_update_tma
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void block_min_atomic_n(double v, unsigned long long* dst, unsigned long long* sm) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, b, s);
+        b = (o < b) ? o : b;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = b;
+    __syncthreads();
+    if (wid == 0) {
+        b = (lane < NT / 32) ? sm[lane] : 0xffffffffffffffffull;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, b, s);
+            b = (o < b) ? o : b;
+        }
+        if (lane == 0) atomicMin(dst, b);
+    }
+    __syncthreads();
+}
+
+template <int NP>
+struct UpdateSmem {
+    static constexpr int NFX = FX_X + NP;
+    using F0T = OwnFluxTile<0>;
+    using F1T = OwnFluxTile<1>;
+    using F2T = OwnFluxTile<2>;
+    static constexpr size_t B_0 = (size_t)NFX * F0T::ZONES * 8, B_1 = (size_t)NFX * F1T::ZONES * 8, B_2 = (size_t)NFX * F2T::ZONES * 8;
+    static constexpr size_t O_0 = 0, O_1 = al128(O_0 + B_0), O_2 = al128(O_1 + B_1), O_BAR = al128(O_2 + B_2), O_RED = O_BAR + 128,
+                            TOTAL = O_RED + 128;
+    static constexpr unsigned TX_BYTES = (unsigned)(B_0 + B_1 + B_2);
+};
+
+template <int NP>
+static __global__ void __launch_bounds__(TTHR, 2)
+k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __grid_constant__ CUtensorMap m_f1,
+             const __grid_constant__ CUtensorMap m_f2, const A4 Sb, const A4 Sin, const A4 Sn, const UpdateArgs a, const int ilo0,
+             const int ilo1, const int ilo2, const TileGrid tg, const double dt) {
+    using L = UpdateSmem<NP>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(smem + L::O_RED);
+    const TileCtx c = tile_ctx(tg);
+    const int fi = c.i0 - ilo0, fj = c.j0 - ilo1, fk = c.k0 - ilo2, pf = fi & 1;
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
+        tma::load_4d(smem + L::O_0, &m_f0, bar, fi - pf, fj, fk, 0);
+        tma::load_4d(smem + L::O_1, &m_f1, bar, fi - pf, fj, fk, 0);
+        tma::load_4d(smem + L::O_2, &m_f2, bar, fi - pf, fj, fk, 0);
+    }
+    const bool active = c.i <= tg.hi0 && c.j <= tg.hi1 && c.k <= tg.hi2;
+    double dt0 = DT_HUGE, dt1 = DT_HUGE;
+    double u[7], ux[NP], rho_old = 0.0;
+    long on = 0;
+    if (active) {   // old state: plain global loads, in flight while the flux tiles land
+        const long ob = Sb.idx(c.i, c.j, c.k), oi = Sin.idx(c.i, c.j, c.k);
+        on = Sn.idx(c.i, c.j, c.k);
+        rho_old = Sb.at(ob, URHO);
+#pragma unroll
+        for (int n = 0; n < 7; ++n) u[n] = Sin.at(oi, n);
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) ux[ip] = Sin.at(oi, UFA + ip);
+    }
+    tma::mbar_wait(bar, 0);
+    if (active) {
+        const typename L::F0T F0{reinterpret_cast<const double*>(smem + L::O_0)};
+        const typename L::F1T F1{reinterpret_cast<const double*>(smem + L::O_1)};
+        const typename L::F2T F2{reinterpret_cast<const double*>(smem + L::O_2)};
+        const double a0 = P.dx[1] * P.dx[2], a1 = P.dx[0] * P.dx[2], a2 = P.dx[0] * P.dx[1];
+        const double vol = P.dx[0] * P.dx[1] * P.dx[2];
+        const double volinv = 1.0 / vol;
+        const int f0 = L::F0T::off(c.tx + pf, c.ty, c.tz), f1 = L::F1T::off(c.tx + pf, c.ty, c.tz), f2 = L::F2T::off(c.tx + pf, c.ty, c.tz);
+        const int f0p = f0 + L::F0T::stride(0), f1p = f1 + L::F1T::stride(1), f2p = f2 + L::F2T::stride(2);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) {
+            u[n] = u[n] + dt * (F0(f0, n) * a0 - F0(f0p, n) * a0 + F1(f1, n) * a1 - F1(f1p, n) * a1 + F2(f2, n) * a2 - F2(f2p, n) * a2) * volinv;
+        }
+        {
+            double pdu = (F0(f0p, FX_PG) + F0(f0, FX_PG)) * (F0(f0p, FX_UG) * a0 - F0(f0, FX_UG) * a0);
+            pdu += (F1(f1p, FX_PG) + F1(f1, FX_PG)) * (F1(f1p, FX_UG) * a1 - F1(f1, FX_UG) * a1);
+            pdu += (F2(f2p, FX_PG) + F2(f2, FX_PG)) * (F2(f2p, FX_UG) * a2 - F2(f2, FX_UG) * a2);
+            pdu = 0.5 * pdu * volinv;
+            u[UEINT] = u[UEINT] - dt * pdu;
+        }
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) {
+            const int n = FX_X + ip;
+            Sn.at(on, UFA + ip) = ux[ip] + dt * (F0(f0, n) * a0 - F0(f0p, n) * a0 + F1(f1, n) * a1 - F1(f1p, n) * a1 + F2(f2, n) * a2 - F2(f2p, n) * a2) * volinv;
+        }
+        {   // check_for_negative_density
+            const double rho = u[URHO];
+            const double rhoInv = 1.0 / rho;
+            if (rho_old >= P.retry_small_density_cutoff && rho < P.small_dens) atomicAdd(&a.counters[0], 1);
+            if (rho >= P.abundance_failure_rho_cutoff) {
+                for (int n = 0; n < P.nspec; ++n) {
+                    const double X = Sn.at(on, P.UFS + n) * rhoInv;
+                    if (X < -P.abundance_failure_tolerance || X > 1.0 + P.abundance_failure_tolerance) atomicAdd(&a.counters[1], 1);
+                }
+            }
+        }
+        for (int cc = 0; cc < a.n_clean; ++cc) {
+            const int nf = clean_zone(P, u, Sn, on);
+            if (nf) atomicAdd(&a.counters[2], nf);
+            if (cc == 0 && a.want_dt) dt0 = estdt_zone(P, u, Sn, on);
+        }
+        if (a.want_dt) dt1 = (a.n_clean == 1) ? dt0 : estdt_zone(P, u, Sn, on);
+        if (a.n_clean == 0) dt0 = dt1;
+        bool nan = false;
+#pragma unroll
+        for (int n = 0; n < 7; ++n) { Sn.at(on, n) = u[n]; nan |= (u[n] != u[n]); }
+        if (nan) atomicAdd(&a.counters[3], 1);
+    }
+    if (a.want_dt) {
+        block_min_atomic_n<TTHR>(dt0, a.dtmin + 0, red);
+        block_min_atomic_n<TTHR>(dt1, a.dtmin + 1, red);
+    }
+}
+
+}  // namespace ctu

@@ -176,3 +176,30 @@ def test_slab_count_does_not_change_results():
     assert outs[0][1] == 1 and outs[1][1] > 1
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     assert_bitwise(outs[1][0], g["U10"], "sedov32 multi-slab")
+
+
+def test_register_staged_kernels_match_golden():
+    """CTU_NO_TMA=1 selects the register-staged kernels (the path other passive counts / EOSs take); it must agree bit for
+    bit with the golden states as well.  Run in a subprocess because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    _torch()
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from cases import load_case\n"
+        "from castro_b200 import lib\n"
+        "for name in ('sedov16_hllc', 'sedov_24x16x8_cgf'):\n"
+        "    par, geom, prob, g, snaps = load_case(name)\n"
+        "    lib.params_finalize(par)\n"
+        "    n = tuple(int(x) for x in g['n_cell'])\n"
+        "    sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in n))\n"
+        "    sim.init_problem('Sedov', prob)\n"
+        "    rc, t, dt, hist = sim.advance(snaps[-1])\n"
+        "    assert rc == 0\n"
+        "    assert np.array_equal(sim.download(), g['U%%d' %% snaps[-1]]), name\n"
+        "print('ok')\n") % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, CTU_NO_TMA="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
