@@ -17,6 +17,9 @@
 
 namespace ctu {
 
+#ifndef CTU_TMA_MINB
+#define CTU_TMA_MINB 2
+#endif
 constexpr int TX = 32, TY = 4, TZ = 2, TTHR = TX * TY * TZ;
 constexpr int ceven(int n) { return (n + 1) & ~1; }
 constexpr size_t al128(size_t b) { return (b + 127) & ~(size_t)127; }
@@ -171,7 +174,7 @@ struct Trans2Args {
 };
 
 template <int N, int NP>
-static __global__ void __launch_bounds__(TTHR, 2)
+static __global__ void __launch_bounds__(TTHR, CTU_TMA_MINB)
 k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
              const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
              const Trans2Args a, const TileGrid tg) {
@@ -268,7 +271,7 @@ struct FinalArgs {
 };
 
 template <int N, int NP>
-static __global__ void __launch_bounds__(TTHR, 2)
+static __global__ void __launch_bounds__(TTHR, CTU_TMA_MINB)
 k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
             const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
             const __grid_constant__ CUtensorMap m_d, const FinalArgs a, const TileGrid tg) {
@@ -393,7 +396,7 @@ struct UpdateSmem {
 };
 
 template <int NP>
-static __global__ void __launch_bounds__(TTHR, 2)
+static __global__ void __launch_bounds__(TTHR, 3)
 k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __grid_constant__ CUtensorMap m_f1,
              const __grid_constant__ CUtensorMap m_f2, const A4 Sb, const A4 Sin, const A4 Sn, const UpdateArgs a, const int ilo0,
              const int ilo1, const int ilo2, const TileGrid tg, const double dt) {
