@@ -212,6 +212,42 @@ int launch_trans2_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs
     return launch_trans2_np<2>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
 }
 
+template <int D, int NP>
+int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1, const Box3& tb,
+                         double dt, cudaStream_t st) {
+    using L = TraceSmem<D, NP>;
+    using TT = TrTile<D>;
+    static bool attr = false;
+    if (!attr) { int rc = set_smem(k_trace_riemann_tma<D, NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    CTU_MAP(m_q, qs, qbx_a, L::NQC, L::QT, L::NQC)
+    TraceRiemannArgs a;
+    a.fd = fd; a.qm = ta.qm[D]; a.qp = ta.qp[D]; a.Fo = F1[D];
+    a.obx = grow(tb, 1);
+    a.vlo = tb.lo[D]; a.vhi = tb.hi[D];
+    for (int d = 0; d < 3; ++d) a.qlo[d] = qbx_a.lo[d];
+    const int n[3] = {a.obx.hi[0] - a.obx.lo[0] + 1, a.obx.hi[1] - a.obx.lo[1] + 1, a.obx.hi[2] - a.obx.lo[2] + 1};
+    // along D the tiles overlap by one zone (N zones -> N-1 faces): the zones must reach index n[D]-1
+    a.ntx = (D == 0) ? (n[0] - 1 + TT::SX - 1) / TT::SX : (n[0] + TT::SX - 1) / TT::SX;
+    a.nty = (D == 1) ? (n[1] - 1 + TT::SY - 1) / TT::SY : (n[1] + TT::SY - 1) / TT::SY;
+    a.ntz = (D == 2) ? (n[2] - 1 + TT::SZ - 1) / TT::SZ : (n[2] + TT::SZ - 1) / TT::SZ;
+    a.dtdL = dt / P.dx[D];
+    k_trace_riemann_tma<D, NP><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
+    return 0;
+}
+template <int NP>
+int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
+                            const Box3& tb, double dt, cudaStream_t st) {
+    int rc = launch_trace_riemann<0, NP>(P, ta, qs, qbx_a, fd, F1, tb, dt, st);
+    if (!rc) rc = launch_trace_riemann<1, NP>(P, ta, qs, qbx_a, fd, F1, tb, dt, st);
+    if (!rc) rc = launch_trace_riemann<2, NP>(P, ta, qs, qbx_a, fd, F1, tb, dt, st);
+    return rc;
+}
+int launch_trace_riemann_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
+                             const Box3& tb, double dt, cudaStream_t st) {
+    if (np == 1) return launch_trace_riemann_np<1>(P, ta, qs, qbx_a, fd, F1, tb, dt, st);
+    return launch_trace_riemann_np<2>(P, ta, qs, qbx_a, fd, F1, tb, dt, st);
+}
+
 template <int N, int NP>
 int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
                  const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
@@ -417,14 +453,21 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
         {   LaunchBox lb = make_lb(obx);
             tm.begin(1);
             k_flat_div<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb); ++launches; tm.end(1);
+            if (use_tma) {
+                tm.begin(2);
+                rc = launch_trace_riemann_all(P, np, ta, qs, qbx_a, fd, F1, tb, dt, st);
+                if (rc) return rc;
+                launches += 3; tm.end(3);
+            } else {
             tm.begin(2);
             k_trace<0><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt);
             k_trace<1><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt);
-            k_trace<2><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt); launches += 3; tm.end(3); }
+            k_trace<2><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt); launches += 3; tm.end(3); } }
         const Box3 nb[3] = {[&] { Box3 b = tb; b.hi[0] += 1; return b; }(), [&] { Box3 b = tb; b.hi[1] += 1; return b; }(),
                             [&] { Box3 b = tb; b.hi[2] += 1; return b; }()};
         // first-pass fluxes: cxbx = grow(xbx,(0,1,1)), cybx = grow(ybx,(1,0,1)), czbx = grow(zbx,(1,1,0))
-        {   LaunchBox lb = make_lb(grow(nb[0], 0, 1, 1));
+        if (!use_tma) {
+            LaunchBox lb = make_lb(grow(nb[0], 0, 1, 1));
             tm.begin(3);
             k_riemann1<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb);
             lb = make_lb(grow(nb[1], 1, 0, 1));

@@ -483,3 +483,300 @@ k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __g
 }
 
 }  // namespace ctu
+
+// ================================================================================================
+// k_trace_riemann_tma<D>: PPM reconstruction + characteristic tracing in direction D fused with the first-pass
+// Riemann solve on the D-faces (reference: trace_ppm + cmpflx_plus_godunov, Castro_ctu_hydro.cpp:378 and :674/745/817).
+//
+// A CTA traces a tile of zones that is one zone longer than its tile of faces along D; the minus state a zone produces
+// for its high face goes to the neighbouring thread through shared memory, so the interface states are written to HBM
+// once (later stages need them) but never read back for the first-pass fluxes.  The primitive tile (+2 zones each side
+// along D) is staged by TMA.
+//   D = 0: zones 32x4x2, 31 faces per row (tiles overlap by one zone in x);  D = 1: zones 32x9x1 (8 face rows);
+//   D = 2: zones 32x1x9.
+// ================================================================================================
+namespace ctu {
+
+template <int D> struct TrTile;
+template <> struct TrTile<0> { static constexpr int NX = 32, NY = 4, NZ = 2, SX = 31, SY = 4, SZ = 2; };
+template <> struct TrTile<1> { static constexpr int NX = 32, NY = 9, NZ = 1, SX = 32, SY = 8, SZ = 1; };
+template <> struct TrTile<2> { static constexpr int NX = 32, NY = 1, NZ = 9, SX = 32, SY = 1, SZ = 8; };
+
+template <int D, int NP>
+struct TraceSmem {
+    using TT = TrTile<D>;
+    static constexpr int NTHR = TT::NX * TT::NY * TT::NZ;
+    static constexpr int NQC = QS_X + NP;                  // rho u v w p rhoe c gamc + passives (the qs layout)
+    using QT = STile<TT::NX + 2 + (D == 0 ? 4 : 0), TT::NY + (D == 1 ? 4 : 0), TT::NZ + (D == 2 ? 4 : 0)>;
+    static constexpr int NEX = 6 + NP;                     // exchanged minus state
+    static constexpr size_t B_Q = (size_t)NQC * QT::ZONES * 8, B_EX = (size_t)NEX * NTHR * 8;
+    static constexpr size_t O_Q = 0, O_EX = al128(B_Q), O_BAR = al128(O_EX + B_EX), TOTAL = O_BAR + 128;
+    static constexpr unsigned TX_BYTES = (unsigned)B_Q;
+};
+
+struct TraceRiemannArgs {
+    A4 fd;                // flattening coefficient (comp 0)
+    A4 qm, qp;            // interface states of direction D (outputs)
+    A4 Fo;                // first-pass flux of direction D (output)
+    Box3 obx;             // zones to trace: grow(slab, 1)
+    int vlo, vhi;         // valid range of the slab along D
+    int qlo[3];           // low corner of the qs allocation box
+    int ntx, nty, ntz;
+    double dtdL;          // dt / dx_D
+};
+
+// Castro::trace_ppm for one zone and direction, zero source terms (trace_ppm.cpp:17-678): the arithmetic of trace_dir in
+// ctu_kernels.cuh with the primitive stencil in shared memory and the results left in registers.
+//   base: &tile(zone, comp 0);  sn: component stride;  st: stride along DIR.   op/om: plus state on the low face, minus
+//   state on the high face (rho u v w p rhoe), xp/xm the passives.
+template <int DIR, int NP>
+__device__ __forceinline__ void trace_core(const DevPar& P, const double* __restrict__ base, const int sn, const int st, const double flat,
+                                           const double dtdL, double* __restrict__ op, double* __restrict__ om, double* __restrict__ xp,
+                                           double* __restrict__ xm) {
+    constexpr int QUN = QS_U + DIR;
+    constexpr int QUT = QS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
+    constexpr int QUTT = QS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
+    constexpr int IUN = IS_U + DIR;
+    constexpr int IUT = IS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
+    constexpr int IUTT = IS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
+    const double cc = base[QS_C * sn];
+    const double un = base[QUN * sn];
+    double sm, sp, dum;
+    Parabola pb;
+#define CTU_RECON(comp)                                                                          \
+    {                                                                                            \
+        const double* __restrict__ a = base + (comp) * sn;                                       \
+        const double s0 = a[0];                                                                  \
+        ppm_reconstruct(P, a[-2 * st], a[-st], s0, a[st], a[2 * st], flat, sm, sp);              \
+        pb.set(sm, sp, s0);                                                                      \
+    }
+    double Ip_rho1, Im_rho1, Ip_rho2, Im_rho0;
+    CTU_RECON(QS_RHO);
+    pb.integ(un - cc, dtdL, dum, Im_rho0);
+    pb.integ(un, dtdL, Ip_rho1, Im_rho1);
+    pb.integ(un + cc, dtdL, Ip_rho2, dum);
+    double Ip_un0, Im_un0, Ip_un2, Im_un2;
+    CTU_RECON(QUN);
+    pb.integ(un - cc, dtdL, Ip_un0, Im_un0);
+    pb.integ(un + cc, dtdL, Ip_un2, Im_un2);
+    double Ip_p0, Im_p0, Ip_p1, Im_p1, Ip_p2, Im_p2;
+    CTU_RECON(QS_P);
+    pb.integ(un - cc, dtdL, Ip_p0, Im_p0);
+    pb.integ(un, dtdL, Ip_p1, Im_p1);
+    pb.integ(un + cc, dtdL, Ip_p2, Im_p2);
+    double Ip_re1, Im_re1, Ip_re2, Im_re0;
+    CTU_RECON(QS_RE);
+    pb.integ(un - cc, dtdL, dum, Im_re0);
+    pb.integ(un, dtdL, Ip_re1, Im_re1);
+    pb.integ(un + cc, dtdL, Ip_re2, dum);
+    double Ip_ut, Im_ut, Ip_utt, Im_utt;
+    CTU_RECON(QUT);
+    pb.integ(un, dtdL, Ip_ut, Im_ut);
+    CTU_RECON(QUTT);
+    pb.integ(un, dtdL, Ip_utt, Im_utt);
+    // gamma-law EOS: PPM of a spatially constant Gamma_1 returns the constant exactly (see trace_dir)
+    const double Ip_gc2 = P.gamma, Im_gc0 = P.gamma;
+    // passives (trace_ppm.cpp:443-485)
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) {
+        double Ipp, Imp;
+        CTU_RECON(QS_X + ip);
+        pb.integ(un, dtdL, Ipp, Imp);
+        xp[ip] = Imp;
+        xm[ip] = Ipp;
+    }
+#undef CTU_RECON
+    const double small_re = P.small_dens * P.small_ener;
+    {   // plus state on the low face (trace_ppm.cpp:494-581)
+        double rho_ref = Im_rho0 + 0.0;
+        double un_ref = Im_un0 + 0.0;
+        double p_ref = Im_p0 + 0.0;
+        double rhoe_g_ref = Im_re0 + 0.0;
+        double gam_g_ref = Im_gc0;
+        rho_ref = smax(rho_ref, P.small_dens);
+        double rho_ref_inv = 1.0 / rho_ref;
+        p_ref = smax(p_ref, P.small_pres);
+        double csq_ref = gam_g_ref * (0.0 + p_ref) * rho_ref_inv;
+        double cc_ref = sqrt(csq_ref);
+        double cc_ref_inv = 1.0 / cc_ref;
+        double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
+        double d_um = un_ref - Im_un0 - 0.0;
+        double dptotm = p_ref - Im_p0 - 0.0;
+        double drho = rho_ref - Im_rho1 - 0.0;
+        double dptot = p_ref - Im_p1 - 0.0;
+        double drhoe_g = rhoe_g_ref - Im_re1 - 0.0;
+        double d_up = un_ref - Im_un2 - 0.0;
+        double dptotp = p_ref - Im_p2 - 0.0;
+        double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
+        double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
+        double alpha0r = drho - dptot / csq_ref;
+        double alpha0e_g = drhoe_g - dptot * h_g_ref / csq_ref;
+        alpham = un - cc > 0.0 ? 0.0 : -alpham;
+        alphap = un + cc > 0.0 ? 0.0 : -alphap;
+        alpha0r = un > 0.0 ? 0.0 : -alpha0r;
+        alpha0e_g = un > 0.0 ? 0.0 : -alpha0e_g;
+        op[IS_RHO] = smax(P.small_dens, rho_ref + alphap + alpham + alpha0r);
+        op[IUN] = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
+        op[IS_RE] = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
+        op[IS_P] = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
+        op[IUT] = Im_ut + 0.0;
+        op[IUTT] = Im_utt + 0.0;
+    }
+    {   // minus state on the high face (trace_ppm.cpp:583-675)
+        double rho_ref = Ip_rho2 + 0.0;
+        double un_ref = Ip_un2 + 0.0;
+        double p_ref = Ip_p2 + 0.0;
+        double rhoe_g_ref = Ip_re2 + 0.0;
+        double gam_g_ref = Ip_gc2;
+        rho_ref = smax(rho_ref, P.small_dens);
+        double rho_ref_inv = 1.0 / rho_ref;
+        p_ref = smax(p_ref, P.small_pres);
+        double csq_ref = gam_g_ref * (0.0 + p_ref) * rho_ref_inv;
+        double cc_ref = sqrt(csq_ref);
+        double cc_ref_inv = 1.0 / cc_ref;
+        double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
+        double d_um = un_ref - Ip_un0 - 0.0;
+        double dptotm = p_ref - Ip_p0 - 0.0;
+        double drho = rho_ref - Ip_rho1 - 0.0;
+        double dptot = p_ref - Ip_p1 - 0.0;
+        double drhoe_g = rhoe_g_ref - Ip_re1 - 0.0;
+        double d_up = un_ref - Ip_un2 - 0.0;
+        double dptotp = p_ref - Ip_p2 - 0.0;
+        double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
+        double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
+        double alpha0r = drho - dptot / csq_ref;
+        double alpha0e_g = drhoe_g - dptot * h_g_ref / csq_ref;
+        alpham = un - cc > 0.0 ? -alpham : 0.0;
+        alphap = un + cc > 0.0 ? -alphap : 0.0;
+        alpha0r = un > 0.0 ? -alpha0r : 0.0;
+        alpha0e_g = un > 0.0 ? -alpha0e_g : 0.0;
+        om[IS_RHO] = smax(P.small_dens, rho_ref + alphap + alpham + alpha0r);
+        om[IUN] = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
+        om[IS_RE] = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
+        om[IS_P] = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
+        om[IUT] = Ip_ut + 0.0;
+        om[IUTT] = Ip_utt + 0.0;
+    }
+}
+
+template <int D, int NP>
+static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, 2)
+k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, const TraceRiemannArgs a) {
+    using L = TraceSmem<D, NP>;
+    using TT = TrTile<D>;
+    using QT = typename L::QT;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    double* sEx = reinterpret_cast<double*>(smem + L::O_EX);
+    // tile and thread coordinates
+    const int bt = blockIdx.x;
+    const int bx = bt % a.ntx, r = bt / a.ntx, by = r % a.nty, bz = r / a.nty;
+    const int i0 = a.obx.lo[0] + bx * TT::SX, j0 = a.obx.lo[1] + by * TT::SY, k0 = a.obx.lo[2] + bz * TT::SZ;
+    const int tx = threadIdx.x % TT::NX, ty = (threadIdx.x / TT::NX) % TT::NY, tz = threadIdx.x / (TT::NX * TT::NY);
+    const int i = i0 + tx, j = j0 + ty, k = k0 + tz;
+    const int dloc = (D == 0) ? tx : (D == 1) ? ty : tz;            // position of the zone along D inside the tile
+    const int btile = (D == 0) ? bx : (D == 1) ? by : bz;
+    // primitive tile: origin = zone-tile origin - 2 e_D, fetched from the even x coordinate at or below it
+    const int qi = i0 - (D == 0 ? 2 : 0) - a.qlo[0], pq = qi & 1;
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
+        const int qj = j0 - (D == 1 ? 2 : 0) - a.qlo[1], qk = k0 - (D == 2 ? 2 : 0) - a.qlo[2];
+        tma::load_4d(smem + L::O_Q, &m_q, bar, qi - pq, qj, qk, 0);
+    }
+    const bool active = a.obx.contains(i, j, k);
+    double flat = 0.0;
+    if (active) flat = a.fd(i, j, k, 0);
+    tma::mbar_wait(bar, 0);
+    double qp_own[6], qm_nxt[6], xp_own[NP], xm_nxt[NP];
+    const int idx = (D == 0) ? i : (D == 1) ? j : k;
+    const bool sym_lo = P.lo_bc[D] == 3, sym_hi = P.hi_bc[D] == 3;
+    constexpr int IUN = IS_U + D;
+    if (active) {
+        const int oq = QT::off(tx + pq + (D == 0 ? 2 : 0), ty + (D == 1 ? 2 : 0), tz + (D == 2 ? 2 : 0));
+        trace_core<D, NP>(P, reinterpret_cast<const double*>(smem + L::O_Q) + oq, QT::ZONES, QT::stride(D), flat, a.dtdL, qp_own, qm_nxt,
+                          xp_own, xm_nxt);
+        // hand the minus state to the thread that owns the high face
+#pragma unroll
+        for (int n = 0; n < 6; ++n) sEx[n * L::NTHR + threadIdx.x] = qm_nxt[n];
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) sEx[(6 + ip) * L::NTHR + threadIdx.x] = xm_nxt[ip];
+        // interface states to HBM for the transverse stages; a zone shared by two overlapping tiles is written by the tile
+        // in which it is not the first zone (same masks as k_trace: trace_ppm.cpp:461-484 + enforce_reflect_states)
+        if (dloc >= 1 || btile == 0) {
+            bool do_p = idx >= a.vlo;
+            bool do_m = idx <= a.vhi;
+            const bool refl_lo = do_p && sym_lo && idx == P.domlo[D];
+            const bool refl_hi = do_m && sym_hi && idx + 1 == P.domhi[D] + 1;
+            if (sym_lo && idx + 1 == P.domlo[D]) do_m = false;
+            if (sym_hi && idx == P.domhi[D] + 1) do_p = false;
+            const long op = a.qp.idx(i, j, k);
+            const long om = op + ((D == 0) ? 1 : (D == 1) ? a.qp.sj : a.qp.sk);
+            if (do_p) {
+#pragma unroll
+                for (int n = 0; n < 6; ++n) a.qp.at(op, n) = qp_own[n];
+#pragma unroll
+                for (int ip = 0; ip < NP; ++ip) a.qp.at(op, IS_X + ip) = xp_own[ip];
+                if (refl_lo) {
+#pragma unroll
+                    for (int n = 0; n < 6; ++n) a.qm.at(op, n) = (n == IUN) ? -qp_own[n] : qp_own[n];
+#pragma unroll
+                    for (int ip = 0; ip < NP; ++ip) a.qm.at(op, IS_X + ip) = xp_own[ip];
+                }
+            }
+            if (do_m) {
+#pragma unroll
+                for (int n = 0; n < 6; ++n) a.qm.at(om, n) = qm_nxt[n];
+#pragma unroll
+                for (int ip = 0; ip < NP; ++ip) a.qm.at(om, IS_X + ip) = xm_nxt[ip];
+                if (refl_hi) {
+#pragma unroll
+                    for (int n = 0; n < 6; ++n) a.qp.at(om, n) = (n == IUN) ? -qm_nxt[n] : qm_nxt[n];
+#pragma unroll
+                    for (int ip = 0; ip < NP; ++ip) a.qp.at(om, IS_X + ip) = xm_nxt[ip];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // first-pass Riemann problem on the low face of every zone that has its left neighbour in the tile
+    if (!active || dloc < 1) return;
+    constexpr int sEx_D = (D == 0) ? 1 : (D == 1) ? TT::NX : TT::NX * TT::NY;
+    double ql[6], xl[NP];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) ql[n] = sEx[n * L::NTHR + threadIdx.x - sEx_D];
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) xl[ip] = sEx[(6 + ip) * L::NTHR + threadIdx.x - sEx_D];
+    double qr[6], xr[NP];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) qr[n] = qp_own[n];
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) xr[ip] = xp_own[ip];
+    if (sym_lo && idx == P.domlo[D]) {          // enforce_reflect_states: left state mirrors the right one
+#pragma unroll
+        for (int n = 0; n < 6; ++n) ql[n] = (n == IUN) ? -qp_own[n] : qp_own[n];
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) xl[ip] = xp_own[ip];
+    }
+    if (sym_hi && idx == P.domhi[D] + 1) {      // right state mirrors the left one
+#pragma unroll
+        for (int n = 0; n < 6; ++n) qr[n] = (n == IUN) ? -ql[n] : ql[n];
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) xr[ip] = xl[ip];
+    }
+    const double* sq = reinterpret_cast<const double*>(smem + L::O_Q);
+    const int oq = QT::off(tx + pq + (D == 0 ? 2 : 0), ty + (D == 1 ? 2 : 0), tz + (D == 2 ? 2 : 0));
+    const double cr = sq[QS_C * QT::ZONES + oq], cl = sq[QS_C * QT::ZONES + oq - QT::stride(D)];
+    double F[6], FX[NP], ugd, pgd;
+    solve_face_r<D, NP>(P, ql, qr, xl, xr, cl, cr, idx, F, ugd, pgd, FX);
+    const long of = a.Fo.idx(i, j, k);
+#pragma unroll
+    for (int n = 0; n < 6; ++n) a.Fo.at(of, n) = F[n];
+    a.Fo.at(of, FX_UG) = ugd;
+    a.Fo.at(of, FX_PG) = pgd;
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) a.Fo.at(of, FX_X + ip) = FX[ip];
+}
+
+}  // namespace ctu
