@@ -370,63 +370,102 @@ static int ws_reserve(ctu_workspace* w, size_t bytes, cudaStream_t st) {
     return 0;
 }
 
-int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_geom_t* geom,
-                      const int valid_lo[3], const int valid_hi[3],
-                      const ctu_fab_t* Sborder, const ctu_fab_t* old_src, const ctu_fab_t* src_corr,
-                      ctu_fab_t* S_new, ctu_fab_t* const flux[3], ctu_fab_t* const mass_flux[3],
-                      double dt, int flags, double dt_est[2], int dt_loc[3], int n_bad[2], void* stream) {
-    if (!ws || !par || !geom || !Sborder || !S_new || !valid_lo || !valid_hi) return CTU_ERR_BAD_ARG;
-    if (!device_ok()) return CTU_ERR_NO_DEVICE;
-    int rc = check_supported(par, geom);
-    if (rc) return rc;
-    if (old_src || src_corr) return CTU_ERR_UNSUPPORTED;   // source-term tracing: SURVEY §8(f) rank 1
-    cudaStream_t st = (cudaStream_t)stream;
-    const DevPar P = make_devpar(par, geom);
-    const int np = P.npassive;
-    const Box3 vbx = make_box(valid_lo, valid_hi);
-    if (!vbx.ok()) return CTU_ERR_BAD_ARG;
-    if (Sborder->ncomp < P.nstate || S_new->ncomp < P.nstate) return CTU_ERR_BAD_ARG;
-    if (!fab_covers(Sborder, grow(vbx, CTU_NGROW)) || !fab_covers(S_new, vbx)) return CTU_ERR_BAD_ARG;
-    const int n_clean = flags & CTU_ADV_NCLEAN_MASK;
-    const bool from_sb = (flags & CTU_ADV_SNEW_FROM_SBORDER) != 0;
+}  // extern "C"
 
-    const int NQS = QS_X + np, NIS = IS_X + np, NFX = FX_X + np;
-    const long nxg = (vbx.hi[0] - vbx.lo[0] + 1), nyg = (vbx.hi[1] - vbx.lo[1] + 1), nzv = (vbx.hi[2] - vbx.lo[2] + 1);
+// ---- one advance of one box, enqueued slab by slab (shared by ctu_hydro_advance and the host-streaming driver) ------
+namespace ctu {
+
+struct HydroRun {
+    ctu_workspace* ws;
+    DevPar P;
+    int np, NQS, NIS, NFX;
+    Box3 vbx;
+    A4 Sb, Sn;
+    bool from_sb, want_dt, use_tma;
+    int n_clean;
+    double dt;
+    double hdtd[3], cdtd[3];
+    long qpad, ipad;
+    size_t plane_q, plane_i;
+    ctu_fab_t* const* flux;
+    ctu_fab_t* const* mass_flux;
+    cudaStream_t st;
+    int launches;
+    StageTimer tm;
+    HydroRun(ctu_workspace* w, cudaStream_t s) : ws(w), st(s), launches(0), tm(w, s) {}
+};
+
+HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_geom_t* geom, const int valid_lo[3], const int valid_hi[3],
+                      const ctu_fab_t* Sborder, ctu_fab_t* S_new, ctu_fab_t* const flux[3], ctu_fab_t* const mass_flux[3], double dt,
+                      int flags, bool want_dt, cudaStream_t st, int* rc_out) {
+    *rc_out = 0;
+    if (!ws || !par || !geom || !Sborder || !S_new || !valid_lo || !valid_hi) { *rc_out = CTU_ERR_BAD_ARG; return nullptr; }
+    if (!device_ok()) { *rc_out = CTU_ERR_NO_DEVICE; return nullptr; }
+    int rc = check_supported(par, geom);
+    if (rc) { *rc_out = rc; return nullptr; }
+    HydroRun* r = new HydroRun(ws, st);
+    r->P = make_devpar(par, geom);
+    const DevPar& P = r->P;
+    r->np = P.npassive;
+    r->vbx = make_box(valid_lo, valid_hi);
+    if (!r->vbx.ok() || Sborder->ncomp < P.nstate || S_new->ncomp < P.nstate || !fab_covers(Sborder, grow(r->vbx, CTU_NGROW)) ||
+        !fab_covers(S_new, r->vbx)) {
+        delete r; *rc_out = CTU_ERR_BAD_ARG; return nullptr;
+    }
+    r->n_clean = flags & CTU_ADV_NCLEAN_MASK;
+    r->from_sb = (flags & CTU_ADV_SNEW_FROM_SBORDER) != 0;
+    r->want_dt = want_dt;
+    r->dt = dt;
+    r->flux = flux; r->mass_flux = mass_flux;
+    r->NQS = QS_X + r->np; r->NIS = IS_X + r->np; r->NFX = FX_X + r->np;
+    const long nxg = (r->vbx.hi[0] - r->vbx.lo[0] + 1), nyg = (r->vbx.hi[1] - r->vbx.lo[1] + 1);
     // scratch rows are padded to an even number of doubles: every row / plane / component stride is then a multiple of
     // 16 bytes, which is what the TMA tensor maps of the tile-staged kernels require
-    const long qpad = (nxg + 8) & 1, ipad = (nxg + 3) & 1;
+    r->qpad = (nxg + 8) & 1; r->ipad = (nxg + 3) & 1;
     // per z-plane scratch: qs on grow(tile,4); everything else on ibx = [lo-1, hi+2]
-    const size_t plane_q = (size_t)(nxg + 8 + qpad) * (nyg + 8) * NQS * sizeof(double);
-    const size_t plane_i = (size_t)(nxg + 3 + ipad) * (nyg + 4) * (size_t)(2 + 6 * NIS + 9 * NFX) * sizeof(double);
-    const bool use_tma = tma_ok(P);
-    // bytes(KS) = plane_q*(KS+8) + plane_i*(KS+4)
-    long KS = (long)((double)(ws->max_bytes - std::min(ws->max_bytes, 8 * plane_q + 4 * plane_i)) / (double)(plane_q + plane_i));
-    if (KS < 1) return CTU_ERR_NOMEM;
-    if (KS > nzv) KS = nzv;
-    // balance the slabs
-    const int nslab = (int)((nzv + KS - 1) / KS);
-    KS = (nzv + nslab - 1) / nslab;
-    const size_t need = plane_q * (KS + 8) + plane_i * (KS + 4);
-    rc = ws_reserve(ws, need, st);
-    if (rc) return rc;
-    ws->last_slab_planes = (int)KS;
-    ws->last_num_slabs = nslab;
-
-    const A4 Sb = make_a4(*Sborder), Sn = make_a4(*S_new);
-    unsigned long long init[4] = {0x7fefffffffffffffull, 0x7fefffffffffffffull, 0xffffffffffffffffull, 0};
-    CUDA_TRY(cudaMemcpyAsync(ws->d_dtmin, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(ws->d_counters, 0, 4 * sizeof(int), st));
-    int launches = 0;
-    StageTimer tm(ws, st);
-
+    r->plane_q = (size_t)(nxg + 8 + r->qpad) * (nyg + 8) * r->NQS * sizeof(double);
+    r->plane_i = (size_t)(nxg + 3 + r->ipad) * (nyg + 4) * (size_t)(2 + 6 * r->NIS + 9 * r->NFX) * sizeof(double);
+    r->use_tma = tma_ok(P);
     const double* dx = geom->dx;
-    const double hdtd[3] = {0.5 * dt / dx[0], 0.5 * dt / dx[1], 0.5 * dt / dx[2]};
-    const double cdtd[3] = {dt / dx[0] / 3.0, dt / dx[1] / 3.0, dt / dx[2] / 3.0};
+    for (int d = 0; d < 3; ++d) { r->hdtd[d] = 0.5 * dt / dx[d]; r->cdtd[d] = dt / dx[d] / 3.0; }
+    r->Sb = make_a4(*Sborder); r->Sn = make_a4(*S_new);
+    unsigned long long init[4] = {0x7fefffffffffffffull, 0x7fefffffffffffffull, 0xffffffffffffffffull, 0};
+    if (cudaMemcpyAsync(ws->d_dtmin, init, sizeof(init), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemsetAsync(ws->d_counters, 0, 4 * sizeof(int), st) != cudaSuccess) {
+        delete r; *rc_out = CTU_ERR_CUDA; return nullptr;
+    }
+    return r;
+}
 
-    for (int s = 0; s < nslab; ++s) {
-        Box3 tb = vbx;
-        tb.lo[2] = vbx.lo[2] + (int)(s * KS);
-        tb.hi[2] = std::min(vbx.hi[2], tb.lo[2] + (int)KS - 1);
+// largest number of valid planes per slab that fits the workspace bound (0 if not even one plane fits)
+long hydro_max_slab_planes(const HydroRun* r) {
+    const size_t mb = r->ws->max_bytes;
+    // bytes(KS) = plane_q*(KS+8) + plane_i*(KS+4)
+    return (long)((double)(mb - std::min(mb, 8 * r->plane_q + 4 * r->plane_i)) / (double)(r->plane_q + r->plane_i));
+}
+
+int hydro_reserve(HydroRun* r, long KS) {
+    return ws_reserve(r->ws, r->plane_q * (KS + 8) + r->plane_i * (KS + 4), r->st);
+}
+
+// enqueue every kernel of the slab of valid planes [klo, khi]
+int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
+    ctu_workspace* ws = r->ws;
+    const DevPar& P = r->P;
+    const int np = r->np, NQS = r->NQS, NIS = r->NIS, NFX = r->NFX;
+    const A4& Sb = r->Sb; const A4& Sn = r->Sn;
+    const bool use_tma = r->use_tma, from_sb = r->from_sb;
+    const double dt = r->dt;
+    const double* hdtd = r->hdtd; const double* cdtd = r->cdtd;
+    const long qpad = r->qpad, ipad = r->ipad;
+    ctu_fab_t* const* flux = r->flux; ctu_fab_t* const* mass_flux = r->mass_flux;
+    cudaStream_t st = r->st;
+    StageTimer& tm = r->tm;
+    int& launches = r->launches;
+    int rc = 0;
+    Box3 tb = r->vbx;
+    tb.lo[2] = klo; tb.hi[2] = khi;
+    if ((size_t)(r->plane_q * (khi - klo + 9) + r->plane_i * (khi - klo + 5)) > ws->arena_bytes) return CTU_ERR_NOMEM;
         const Box3 qbx = grow(tb, 4);
         const Box3 obx = grow(tb, 1);
         Box3 ibx = obx; ibx.hi[0] += 1; ibx.hi[1] += 1; ibx.hi[2] += 1;
@@ -513,7 +552,7 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
         {   UpdateArgs ua;
             for (int d = 0; d < 3; ++d) ua.F[d] = F1[d];
             ua.dtmin = ws->d_dtmin; ua.counters = ws->d_counters;
-            ua.n_clean = n_clean; ua.want_dt = (dt_est != nullptr);
+            ua.n_clean = r->n_clean; ua.want_dt = r->want_dt;
             LaunchBox lb = make_lb(tb);
             tm.begin(6);
             if (use_tma) {
@@ -527,7 +566,7 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
             const bool want_f = flux && flux[d], want_m = mass_flux && mass_flux[d];
             if (!want_f && !want_m) continue;
             Box3 fb = tb;
-            if (d != 2 || s == nslab - 1) fb.hi[d] += 1;     // nodaltilebox: no face is visited twice
+            if (d != 2 || last_slab) fb.hi[d] += 1;     // nodaltilebox: no face is visited twice
             A4 fo, mo;
             std::memset(&fo, 0, sizeof(fo)); std::memset(&mo, 0, sizeof(mo));
             if (want_f) { if (!fab_covers(flux[d], fb) || flux[d]->ncomp < P.nstate) return CTU_ERR_BAD_ARG; fo = make_a4(*flux[d]); }
@@ -539,17 +578,25 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
             if (d == 2) k_store_flux<2><<<nblocks(lb.n), TPB, 0, st>>>(P, F1[2], fo, mo, lb, dt);
             ++launches; tm.end(1);
         }
-    }
+    return 0;
+}
+
+// read the reductions back (synchronises the stream), fold the stage timers, free the run
+int hydro_end(HydroRun* r, double dt_est[2], int dt_loc[3], int n_bad[2]) {
+    ctu_workspace* ws = r->ws;
+    cudaStream_t st = r->st;
+    const Box3 vbx = r->vbx;
+    struct Guard { HydroRun* r; ~Guard() { delete r; } } guard{r};
     if (dt_est && dt_loc) {
         LaunchBox lb = make_lb(vbx);
-        k_estdt_loc<<<nblocks(lb.n), TPB, 0, st>>>(P, Sn, lb, ws->d_dtmin + 1, ws->d_dtmin + 2); ++launches;
+        k_estdt_loc<<<nblocks(lb.n), TPB, 0, st>>>(r->P, r->Sn, lb, ws->d_dtmin + 1, ws->d_dtmin + 2); ++r->launches;
     }
-    ws->kernel_launches += launches;
+    ws->kernel_launches += r->launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(ws->h_dtmin, ws->d_dtmin, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(ws->h_counters, ws->d_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    tm.fold();
+    r->tm.fold();
     int status = 0;
     if (ws->h_counters[0]) status |= CTU_STATUS_INVALID_DENSITY;
     if (ws->h_counters[1]) status |= CTU_STATUS_INVALID_X;
@@ -560,13 +607,71 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
         std::memcpy(&dt_est[1], &ws->h_dtmin[1], sizeof(double));
         if (dt_loc) {
             const unsigned long long t = ws->h_dtmin[2];
-            const unsigned long long nx = nxg, ny = nyg;
+            const unsigned long long nx = vbx.hi[0] - vbx.lo[0] + 1, ny = vbx.hi[1] - vbx.lo[1] + 1;
             dt_loc[2] = vbx.lo[2] + (int)(t / (nx * ny));
             dt_loc[1] = vbx.lo[1] + (int)((t % (nx * ny)) / nx);
             dt_loc[0] = vbx.lo[0] + (int)(t % nx);
         }
     }
     return status;
+}
+
+void hydro_abort(HydroRun* r) { delete r; }
+void hydro_set_slab_info(HydroRun* r, int planes, int nslab) { r->ws->last_slab_planes = planes; r->ws->last_num_slabs = nslab; }
+
+int fill_boundary_planes(const ctu_params_t* par, const ctu_geom_t* geom, const int valid_lo[3], const int valid_hi[3], ctu_fab_t* S,
+                         int ng, int zlo, int zhi, cudaStream_t st) {
+    if (!par || !geom || !S) return CTU_ERR_BAD_ARG;
+    if (!device_ok()) return CTU_ERR_NO_DEVICE;
+    for (int d = 0; d < 3; ++d) {
+        if (geom->periodic[d]) continue;
+        const int bcs[2] = {geom->lo_bc[d], geom->hi_bc[d]};
+        for (int b : bcs) if (b == 1) return CTU_ERR_UNSUPPORTED;   // inflow (ext_dir) needs a problem-specific fill
+    }
+    const DevPar P = make_devpar(par, geom);
+    const Box3 vbx = make_box(valid_lo, valid_hi);
+    Box3 gbx = grow(vbx, ng);
+    if (!fab_covers(S, gbx)) return CTU_ERR_BAD_ARG;
+    gbx.lo[2] = std::max(gbx.lo[2], zlo); gbx.hi[2] = std::min(gbx.hi[2], zhi);
+    if (!gbx.ok()) return 0;
+    const A4 a = make_a4(*S);
+    LaunchBox lb = make_lb(gbx);
+    k_fill<0><<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, vbx);
+    k_fill<1><<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, vbx);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ctu
+
+extern "C" {
+
+int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_geom_t* geom,
+                      const int valid_lo[3], const int valid_hi[3],
+                      const ctu_fab_t* Sborder, const ctu_fab_t* old_src, const ctu_fab_t* src_corr,
+                      ctu_fab_t* S_new, ctu_fab_t* const flux[3], ctu_fab_t* const mass_flux[3],
+                      double dt, int flags, double dt_est[2], int dt_loc[3], int n_bad[2], void* stream) {
+    if (old_src || src_corr) return CTU_ERR_UNSUPPORTED;   // source-term tracing: SURVEY §8(f) rank 1
+    int rc = 0;
+    HydroRun* r = hydro_begin(ws, par, geom, valid_lo, valid_hi, Sborder, S_new, flux, mass_flux, dt, flags, dt_est != nullptr,
+                              (cudaStream_t)stream, &rc);
+    if (!r) return rc;
+    const long nzv = valid_hi[2] - valid_lo[2] + 1;
+    long KS = hydro_max_slab_planes(r);
+    if (KS < 1) { delete r; return CTU_ERR_NOMEM; }
+    if (KS > nzv) KS = nzv;
+    const int nslab = (int)((nzv + KS - 1) / KS);     // balance the slabs
+    KS = (nzv + nslab - 1) / nslab;
+    rc = hydro_reserve(r, KS);
+    if (rc) { delete r; return rc; }
+    hydro_set_slab_info(r, (int)KS, nslab);
+    for (int s = 0; s < nslab; ++s) {
+        const int klo = valid_lo[2] + (int)(s * KS);
+        const int khi = std::min(valid_hi[2], klo + (int)KS - 1);
+        rc = hydro_slab(r, klo, khi, s == nslab - 1);
+        if (rc) { delete r; return rc; }
+    }
+    return hydro_end(r, dt_est, dt_loc, n_bad);
 }
 
 int ctu_estdt(const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3], const int hi[3],
@@ -617,24 +722,8 @@ int ctu_clean_state(const ctu_params_t* par, const int lo[3], const int hi[3], c
 
 int ctu_fill_boundary(const ctu_params_t* par, const ctu_geom_t* geom, const int valid_lo[3], const int valid_hi[3],
                       ctu_fab_t* S, int ng, void* stream) {
-    if (!par || !geom || !S) return CTU_ERR_BAD_ARG;
-    if (!device_ok()) return CTU_ERR_NO_DEVICE;
-    for (int d = 0; d < 3; ++d) {
-        if (geom->periodic[d]) continue;
-        const int bcs[2] = {geom->lo_bc[d], geom->hi_bc[d]};
-        for (int b : bcs) if (b == 1) return CTU_ERR_UNSUPPORTED;   // inflow (ext_dir) needs a problem-specific fill
-    }
-    const DevPar P = make_devpar(par, geom);
-    const Box3 vbx = make_box(valid_lo, valid_hi);
-    const Box3 gbx = grow(vbx, ng);
-    if (!fab_covers(S, gbx)) return CTU_ERR_BAD_ARG;
-    const A4 a = make_a4(*S);
-    LaunchBox lb = make_lb(gbx);
-    cudaStream_t st = (cudaStream_t)stream;
-    k_fill<0><<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, vbx);
-    k_fill<1><<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, vbx);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    if (!valid_lo || !valid_hi) return CTU_ERR_BAD_ARG;
+    return fill_boundary_planes(par, geom, valid_lo, valid_hi, S, ng, valid_lo[2] - ng, valid_hi[2] + ng, (cudaStream_t)stream);
 }
 
 int ctu_halo_pack(const ctu_fab_t* S, const int lo[3], const int hi[3], double* buf, void* stream) {

@@ -392,6 +392,13 @@ struct ctu_sim {
     cudaStream_t st = 0;
     int step = 0;
     int launches = 0;     // kernels launched by the sim itself (clean / fill / init), on top of the workspace's count
+    // host-streaming step (ctu_sim_step_host): copy streams, double-buffered staging, hand-over events
+    cudaStream_t s_up = nullptr, s_dn = nullptr;
+    double* stage_up[2] = {nullptr, nullptr};
+    double* stage_dn[2] = {nullptr, nullptr};
+    size_t stage_doubles = 0;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_upfree[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr}, ev_dnfree[2] = {nullptr, nullptr};
+    bool upfree_rec[2] = {false, false}, dnfree_rec[2] = {false, false};
     ctu_fab_t fab(int which) const {
         ctu_fab_t f;
         f.p = buf[which];
@@ -592,6 +599,16 @@ int ctu_sim_create(ctu_sim_t** out, const ctu_params_t* par, const ctu_geom_t* g
 
 void ctu_sim_destroy(ctu_sim_t* s) {
     if (!s) return;
+    for (int b = 0; b < 2; ++b) {
+        if (s->stage_up[b]) cudaFree(s->stage_up[b]);
+        if (s->stage_dn[b]) cudaFree(s->stage_dn[b]);
+        if (s->ev_up[b]) cudaEventDestroy(s->ev_up[b]);
+        if (s->ev_upfree[b]) cudaEventDestroy(s->ev_upfree[b]);
+        if (s->ev_dn[b]) cudaEventDestroy(s->ev_dn[b]);
+        if (s->ev_dnfree[b]) cudaEventDestroy(s->ev_dnfree[b]);
+    }
+    if (s->s_up) cudaStreamDestroy(s->s_up);
+    if (s->s_dn) cudaStreamDestroy(s->s_dn);
     for (int b = 0; b < 2; ++b) if (s->buf[b]) cudaFree(s->buf[b]);
     if (s->ws) ctu_workspace_destroy(s->ws);
     delete s;
@@ -658,6 +675,147 @@ int ctu_sim_step_hydro(ctu_sim_t* s, double dt, double dt_est[2], int n_bad[2]) 
     ctu_fab_t sb = s->fab(s->cur), sn = s->fab(1 - s->cur);
     int rc = ctu_hydro_advance(s->ws, &s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, nullptr, nullptr, &sn, nullptr, nullptr, dt,
                                2 | CTU_ADV_SNEW_FROM_SBORDER, dt_est, nullptr, n_bad, s->st);
+    if (rc < 0) return rc;
+    if (rc == 0) { s->cur = 1 - s->cur; s->step++; }
+    return rc;
+}
+
+
+// ---- one step with the state in HOST memory, streamed through the device in z-chunks ----------------------------
+// Same arithmetic as ctu_sim_upload + step_pre + step_fill + step_hydro + ctu_sim_download (and bit-identical to it),
+// but the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap on three streams:
+//   copy-in stream : host planes -> contiguous staging buffer (one plain copy per component)
+//   compute stream : unpack into the ghosted state, clean_state, x/y boundary fill, clean_state(ghosted planes),
+//                    then every kernel of the hydro slab that became complete, pack S_new's planes into staging
+//   copy-out stream: staging -> host planes
+// The z-ghost planes need the first / last four valid planes (outflow, reflecting or periodic images), so these are
+// sent ahead in a small prologue.  Single-box only (box == domain); multi-box runs exchange halos between the phases
+// of ctu_sim_step_pre / _fill / _hydro instead.
+static int host_step_setup(ctu_sim_t* s, int kc) {
+    const size_t plane = (size_t)(s->vbx.hi[0] - s->vbx.lo[0] + 1) * (s->vbx.hi[1] - s->vbx.lo[1] + 1);
+    const size_t need = plane * (size_t)kc * s->nstate;
+    if (!s->s_up) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->s_up, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->s_dn, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_up[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_upfree[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_dn[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_dnfree[b], cudaEventDisableTiming));
+        }
+    }
+    if (need > s->stage_doubles) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; ++b) {
+            if (s->stage_up[b]) cudaFree(s->stage_up[b]);
+            if (s->stage_dn[b]) cudaFree(s->stage_dn[b]);
+            s->stage_up[b] = s->stage_dn[b] = nullptr;
+        }
+        s->stage_doubles = 0;
+        for (int b = 0; b < 2; ++b) {
+            if (cudaMalloc(&s->stage_up[b], need * sizeof(double)) != cudaSuccess || cudaMalloc(&s->stage_dn[b], need * sizeof(double)) != cudaSuccess) {
+                cudaGetLastError();
+                return CTU_ERR_NOMEM;
+            }
+        }
+        s->stage_doubles = need;
+        s->upfree_rec[0] = s->upfree_rec[1] = s->dnfree_rec[0] = s->dnfree_rec[1] = false;
+    }
+    return 0;
+}
+
+// host planes [k0,k1] (all components) -> staging buffer b -> ghosted state `f`
+static int host_upload_planes(ctu_sim_t* s, const double* host, int b, int k0, int k1, ctu_fab_t* f) {
+    const int nx = s->vbx.hi[0] - s->vbx.lo[0] + 1, ny = s->vbx.hi[1] - s->vbx.lo[1] + 1, nz = s->vbx.hi[2] - s->vbx.lo[2] + 1;
+    const size_t plane = (size_t)nx * ny;
+    const int nk = k1 - k0 + 1;
+    if (s->upfree_rec[b]) CUDA_TRY(cudaStreamWaitEvent(s->s_up, s->ev_upfree[b], 0));
+    for (int n = 0; n < s->nstate; ++n)
+        CUDA_TRY(cudaMemcpyAsync(s->stage_up[b] + (size_t)n * nk * plane, host + ((size_t)n * nz + (k0 - s->vbx.lo[2])) * plane,
+                                 (size_t)nk * plane * sizeof(double), cudaMemcpyHostToDevice, s->s_up));
+    CUDA_TRY(cudaEventRecord(s->ev_up[b], s->s_up));
+    CUDA_TRY(cudaStreamWaitEvent(s->st, s->ev_up[b], 0));
+    const int lo[3] = {s->vbx.lo[0], s->vbx.lo[1], k0}, hi[3] = {s->vbx.hi[0], s->vbx.hi[1], k1};
+    int rc = ctu_halo_unpack(f, lo, hi, s->stage_up[b], s->st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s->ev_upfree[b], s->st));
+    s->upfree_rec[b] = true;
+    s->launches += 1;
+    return ctu_clean_state(&s->par, lo, hi, f, 1, s->st);          // Castro::initialize_advance: clean_state(S_old)
+}
+
+int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, double dt, double dt_est[2], int n_bad[2]) {
+    if (!s || !host_in || !host_out) return CTU_ERR_BAD_ARG;
+    for (int d = 0; d < 3; ++d)
+        if (s->vbx.lo[d] != s->geom.domlo[d] || s->vbx.hi[d] != s->geom.domhi[d]) return CTU_ERR_UNSUPPORTED;
+    const int nz = s->vbx.hi[2] - s->vbx.lo[2] + 1;
+    const int zlo = s->vbx.lo[2], zhi = s->vbx.hi[2];
+    ctu_fab_t sb = s->fab(s->cur), sn = s->fab(1 - s->cur);
+    int rc = 0;
+    HydroRun* run = hydro_begin(s->ws, &s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, &sn, nullptr, nullptr, dt,
+                                2 | CTU_ADV_SNEW_FROM_SBORDER, true, s->st, &rc);
+    if (!run) return rc;
+    // chunk size: CTU_HOST_CHUNK planes (default 32), at least the 4 planes a neighbouring slab reads, at most what the
+    // workspace bound allows
+    long kc = 32;
+    if (const char* e = std::getenv("CTU_HOST_CHUNK")) kc = std::max(1L, std::strtol(e, nullptr, 10));
+    kc = std::min(kc, hydro_max_slab_planes(run));
+    if (kc < 1) { hydro_abort(run); return CTU_ERR_NOMEM; }
+    if (kc < CTU_NGROW || kc > nz) kc = nz;
+    const int nchunk = (int)((nz + kc - 1) / kc);
+    rc = hydro_reserve(run, kc);
+    if (!rc) rc = host_step_setup(s, (int)kc);
+    if (rc) { hydro_abort(run); return rc; }
+    hydro_set_slab_info(run, (int)kc, nchunk);
+    const int np4 = std::min(CTU_NGROW, nz);
+    const int glo[3] = {s->gbx.lo[0], s->gbx.lo[1], 0}, ghi[3] = {s->gbx.hi[0], s->gbx.hi[1], 0};
+    auto clean_planes = [&](int k0, int k1) {      // clean_state over the full ghosted x-y extent of planes [k0,k1]
+        int lo[3] = {glo[0], glo[1], k0}, hi[3] = {ghi[0], ghi[1], k1};
+        s->launches += 1;
+        return ctu_clean_state(&s->par, lo, hi, &sb, 1, s->st);
+    };
+    // prologue: z-ghost planes
+    rc = host_upload_planes(s, host_in, 0, zlo, zlo + np4 - 1, &sb);
+    if (!rc) rc = host_upload_planes(s, host_in, 1, zhi - np4 + 1, zhi, &sb);
+    if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, zlo - CTU_NGROW, zlo - 1, s->st);
+    if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, zhi + 1, zhi + CTU_NGROW, s->st);
+    if (!rc) rc = clean_planes(zlo - CTU_NGROW, zlo - 1);
+    if (!rc) rc = clean_planes(zhi + 1, zhi + CTU_NGROW);
+    s->launches += 4;
+    auto slab = [&](int c) {
+        const int k0 = zlo + (int)(c * kc), k1 = std::min(zhi, k0 + (int)kc - 1), b = c & 1;
+        int r = hydro_slab(run, k0, k1, c == nchunk - 1);
+        if (r) return r;
+        if (s->dnfree_rec[b]) CUDA_TRY(cudaStreamWaitEvent(s->st, s->ev_dnfree[b], 0));
+        const int lo[3] = {s->vbx.lo[0], s->vbx.lo[1], k0}, hi[3] = {s->vbx.hi[0], s->vbx.hi[1], k1};
+        r = ctu_halo_pack(&sn, lo, hi, s->stage_dn[b], s->st);
+        if (r) return r;
+        s->launches += 1;
+        CUDA_TRY(cudaEventRecord(s->ev_dn[b], s->st));
+        CUDA_TRY(cudaStreamWaitEvent(s->s_dn, s->ev_dn[b], 0));
+        const int nx = s->vbx.hi[0] - s->vbx.lo[0] + 1, ny = s->vbx.hi[1] - s->vbx.lo[1] + 1;
+        const size_t plane = (size_t)nx * ny;
+        const int nk = k1 - k0 + 1;
+        for (int n = 0; n < s->nstate; ++n)
+            CUDA_TRY(cudaMemcpyAsync(host_out + ((size_t)n * nz + (k0 - zlo)) * plane, s->stage_dn[b] + (size_t)n * nk * plane,
+                                     (size_t)nk * plane * sizeof(double), cudaMemcpyDeviceToHost, s->s_dn));
+        CUDA_TRY(cudaEventRecord(s->ev_dnfree[b], s->s_dn));
+        s->dnfree_rec[b] = true;
+        return 0;
+    };
+    for (int c = 0; c < nchunk && !rc; ++c) {
+        const int k0 = zlo + (int)(c * kc), k1 = std::min(zhi, k0 + (int)kc - 1);
+        rc = host_upload_planes(s, host_in, c & 1, k0, k1, &sb);
+        // Castro::initialize_do_advance: boundary fill + clean_state(Sborder, NUM_GROW) on these planes
+        if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, k0, k1, s->st);
+        if (!rc) rc = clean_planes(k0, k1);
+        s->launches += 2;
+        if (!rc && c >= 1) rc = slab(c - 1);
+    }
+    if (!rc) rc = slab(nchunk - 1);
+    if (rc) { hydro_abort(run); cudaDeviceSynchronize(); return rc; }
+    rc = hydro_end(run, dt_est, nullptr, n_bad);
+    CUDA_TRY(cudaStreamSynchronize(s->s_dn));
     if (rc < 0) return rc;
     if (rc == 0) { s->cur = 1 - s->cur; s->step++; }
     return rc;

@@ -53,6 +53,7 @@ def lib():
         L.ctu_sim_upload.argtypes = [C.c_void_p, C.c_void_p]
         L.ctu_sim_init_problem.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.ctu_sim_step_hydro.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ctu_sim_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ctu_sim_advance.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ctu_hydro_advance.argtypes = [C.c_void_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3,
@@ -294,6 +295,15 @@ class Sim:
         est = (C.c_double * 2)()
         nbad = (C.c_int * 2)()
         rc = check(lib().ctu_sim_step_hydro(self.h, dt, est, nbad), "ctu_sim_step_hydro")
+        return rc, (est[0], est[1]), tuple(nbad)
+
+    def step_host(self, host_in, host_out, dt):
+        """one step with the state in host memory (numpy [ncomp, nz, ny, nx], ideally pinned), streamed in z-chunks"""
+        assert host_in.shape == self.shape and host_out.shape == self.shape
+        assert host_in.flags["C_CONTIGUOUS"] and host_out.flags["C_CONTIGUOUS"]
+        est = (C.c_double * 2)()
+        nbad = (C.c_int * 2)()
+        rc = check(lib().ctu_sim_step_host(self.h, host_in.ctypes.data, host_out.ctypes.data, dt, est, nbad), "ctu_sim_step_host")
         return rc, (est[0], est[1]), tuple(nbad)
 
     def advance(self, nsteps, stop_time=-1.0, time=0.0, dt=-1.0):

@@ -225,6 +225,11 @@ int  ctu_sim_init_problem(ctu_sim_t* sim, const char* problem, const char* prob_
 int  ctu_sim_step_pre(ctu_sim_t* sim);
 int  ctu_sim_step_fill(ctu_sim_t* sim);
 int  ctu_sim_step_hydro(ctu_sim_t* sim, double dt, double dt_est[2], int n_bad[2]);
+/* One step with the state in HOST memory (what a CPU-resident caller of the path does every step), single box == domain:
+ * host_in / host_out: valid zones [ncomp][nz][ny][nx] (i fastest; pinned memory recommended; may alias).  Same result as
+ * ctu_sim_upload + pre + fill + hydro + ctu_sim_download, but streamed in z-chunks (CTU_HOST_CHUNK planes, default 32) so
+ * that the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap. */
+int  ctu_sim_step_host(ctu_sim_t* sim, const double* host_in, double* host_out, double dt, double dt_est[2], int n_bad[2]);
 /* Single box covering the whole domain: runs nsteps of pre+fill+hydro with the dt control of
  * Castro::computeInitialDt / computeNewDt / subcycle_advance_ctu (Castro.cpp:1559-1573,1751-1992;
  * Castro_advance_ctu.cpp:301-303).  Pass *dt_inout <= 0 on the first call.  Returns status bits. */

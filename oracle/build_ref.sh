@@ -13,6 +13,7 @@
 # Outputs (git-ignored, but shipped to the GPU box by gpurun):
 #   oracle/_ref/Castro3d_sedov.ex        serial, -O3, no FMA  (parity oracle, golden generator)
 #   oracle/_ref/Castro3d_sedov_omp.ex    OpenMP build         (CPU baseline for bench.py)
+#   oracle/_ref/Castro3d_kh.ex           Kelvin-Helmholtz problem, serial (golden generator for the 2-passive path)
 #   oracle/_ref/fcompare.ex              AMReX plotfile comparator (DIM=3)
 set -euo pipefail
 REF=${REF:-/root/reference}
@@ -36,6 +37,8 @@ build() {  # $1 = problem dir name, $2 = output name, rest = make args
 what=${1:-all}
 if [ "$what" = all ] || [ "$what" = serial ]; then build Sedov Castro3d_sedov DIM=3; fi
 if [ "$what" = all ] || [ "$what" = omp ];    then build Sedov Castro3d_sedov_omp DIM=3 USE_OMP=TRUE; fi
+# KH as shipped: NUMADV := 1 in its GNUmakefile -> NUM_STATE = 9 (one advected scalar + one species): pins the 2-passive path
+if [ "$what" = all ] || [ "$what" = kh ];     then build KH Castro3d_kh DIM=3; fi
 if [ "$what" = all ] || [ "$what" = fcompare ]; then
   d="$W/fcompare"; mkdir -p "$d"; cp -r "$REF/external/amrex/Tools/Plotfile/"* "$d"/
   ( cd "$d" && make AMREX_HOME="$REF/external/amrex" programs=fcompare DIM=3 USE_MPI=FALSE -j"$J" >build.log 2>&1 ) || { tail -30 "$d/build.log"; exit 1; }
