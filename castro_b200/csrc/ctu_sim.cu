@@ -281,9 +281,9 @@ int kh_init(const ctu_params_t* par, const ctu_geom_t* g, const std::map<std::st
     else if (problem == 3) { sine_n = 4; w0 = 0.01; delta_y = 0.025; }
     else if (problem == 4) { sine_n = 2; w0 = 0.01; delta_y = 0.025; }
     else { sine_n = 2; w0 = 0.01; delta_y = 0.05; sigma = 0.2; vel1 = 1.0; vel2 = 1.0; }
-    // problem::center defaults to the domain centre (Source/problems: problem.center is set in Castro::variableSetUp
-    // from geometry: center = 0.5*(problo+probhi) for Cartesian)
-    const double center1 = 0.5 * (g->problo[1] + g->probhi[1]);
+    // problem::center: the KH problem_initialize() never sets it, so it keeps the default of the `problem.center` runtime
+    // parameter (0 0 0) -- the interfaces sit at y = -+ L_y/4 about y = 0, not about the domain centre.
+    const double center1 = kv_d(kv, "center_y", 0.0);
     const double y1 = center1 - (g->probhi[1] - g->problo[1]) * 0.25e0;
     const double y2 = center1 + (g->probhi[1] - g->problo[1]) * 0.25e0;
     const int ni = lb.nx, nj = lb.ny;

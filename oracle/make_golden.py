@@ -22,6 +22,9 @@ from plotfile import read_plotfile, read_header  # noqa: E402
 
 EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_sedov.ex")
 INPUTS = "/root/reference/Exec/hydro_tests/Sedov/inputs.3d.sph"
+# Kelvin-Helmholtz as shipped (NUMADV = 1 -> 9 state components: pins the two-passive path and the periodic time loop)
+KH_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_kh.ex")
+KH_INPUTS = os.path.join(ROOT, "bench_inputs", "inputs.kh3d")
 
 # name -> (n_cell, max_step, snapshot steps, extra overrides)
 CASES = {
@@ -42,12 +45,18 @@ CASES = {
 }
 
 
-def run_case(name, n_cell, max_step, snaps, extra):
+KH_CASES = {
+    "kh16_cgf": ((16, 16, 8), 10, [0, 10], ["castro.riemann_solver=0"]),
+    "kh16_hllc": ((16, 16, 8), 10, [0, 10], ["castro.riemann_solver=2", "problem.bulk_velocity=0.3"]),
+}
+
+
+def run_case(name, n_cell, max_step, snaps, extra, exe=EXE, inputs=INPUTS):
     if isinstance(n_cell, int):
         n_cell = (n_cell,) * 3
     wd = tempfile.mkdtemp(prefix="golden_")
     try:
-        args = [EXE, INPUTS, "amr.max_level=0", "amr.n_cell=%d %d %d" % n_cell, "amr.max_grid_size=64",
+        args = [exe, inputs, "amr.max_level=0", "amr.n_cell=%d %d %d" % n_cell, "amr.max_grid_size=64",
                 "amr.blocking_factor=8", "max_step=%d" % max_step, "stop_time=1.e9", "amr.plot_int=1",
                 "amr.check_int=-1", "amr.derive_plot_vars=NONE", "castro.sum_interval=-1", "amr.plot_file=plt",
                 "castro.v=0", "amr.v=0"] + extra
@@ -79,3 +88,7 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case(name, n, ms, snaps, extra)
+    for name, (n, ms, snaps, extra) in KH_CASES.items():
+        if only and name not in only:
+            continue
+        run_case(name, n, ms, snaps, extra, exe=KH_EXE, inputs=KH_INPUTS)

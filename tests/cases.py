@@ -47,3 +47,25 @@ def load_case(name):
     prob.update(c.get("prob", {}))
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
     return par, geom, prob, g, snaps
+
+
+KH_CASES = {
+    "kh16_cgf": dict(solver=0, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0)),
+    "kh16_hllc": dict(solver=2, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.3)),
+}
+
+
+def load_kh_case(name):
+    """Kelvin-Helmholtz as shipped (NUMADV = 1: one advected scalar + one species -> 9 state components), parameters of
+    bench_inputs/inputs.kh3d; goldens from the reference's KH executable (oracle/make_golden.py KH_CASES)."""
+    c = KH_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    par = abi.default_params()
+    par.riemann_solver = c["solver"]
+    par.cfl, par.init_shrink, par.change_max = 0.5, 0.1, 1.1
+    par.small_dens, par.small_temp = 1.e-10, 1.e-10
+    par.nadv, par.nspec = 1, 1
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), periodic=(1, 1, 1), lo_bc=(0, 0, 0), hi_bc=(0, 0, 0))
+    snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
+    return par, geom, c["prob"], g, snaps
