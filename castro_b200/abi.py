@@ -47,6 +47,7 @@ class Params(C.Structure):
         ("small_x", C.c_double),
         ("nspec", C.c_int), ("naux", C.c_int), ("nadv", C.c_int),
         ("aion", DblS), ("zion", DblS),
+        ("do_grav", C.c_int), ("grav_source_type", C.c_int), ("const_grav", C.c_double),
     ]
 
     @property
@@ -86,6 +87,7 @@ def default_params():
     p.nspec, p.naux, p.nadv = 1, 0, 0
     p.aion[0] = 1.0
     p.zion[0] = 1.0
+    p.do_grav, p.grav_source_type, p.const_grav = 0, 4, 0.0
     return p
 
 

@@ -186,6 +186,7 @@ int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3
     CTU_MAP(m_f2, F1[T2], ibx, L::NFX, L::F2T, L::NFX)
     CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
     Trans2Args a;
+    a.qm = ta.qm[N]; a.qp = ta.qp[N];
     a.Fo1 = F2[N][T1]; a.Fo2 = F2[N][T2];
     int g1[3] = {0, 0, 0}, g2[3] = {0, 0, 0}, gu[3] = {0, 0, 0};
     g1[T2] = 1; g2[T1] = 1; gu[T1] = 1; gu[T2] = 1;
@@ -262,6 +263,7 @@ int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3&
     CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
     CTU_MAP(m_d, fd, ibx, 2, L::DT, 1)
     FinalArgs a;
+    a.qm = ta.qm[N]; a.qp = ta.qp[N];
     a.U = Sb; a.Fo = F1[N];
     for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
     a.c1 = hdtd[T1]; a.c2 = hdtd[T2];

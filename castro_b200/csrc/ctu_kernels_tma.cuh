@@ -17,10 +17,27 @@
 
 namespace ctu {
 
+#ifndef CTU_TRACE_MINB
+#define CTU_TRACE_MINB 2
+#endif
 #ifndef CTU_TMA_MINB
 #define CTU_TMA_MINB 2
 #endif
-constexpr int TX = 32, TY = 4, TZ = 2, TTHR = TX * TY * TZ;
+// CTU_Q_LDG = 1: the interface-state tiles (each element is consumed by exactly one thread) are read with plain coalesced
+// global loads that are in flight while the TMA flux tiles land, instead of being staged through shared memory: the CTA's
+// shared-memory footprint drops by ~30 KB, which is what lets a third CTA fit on the SM.
+#ifndef CTU_Q_LDG
+#define CTU_Q_LDG 0
+#endif
+#ifndef CTU_TY
+#define CTU_TY 4
+#endif
+#ifndef CTU_TZ
+#define CTU_TZ 2
+#endif
+constexpr int TX = 32, TY = CTU_TY, TZ = CTU_TZ, TTHR = TX * TY * TZ;
+// resident CTAs per SM the flux-stage kernels are compiled for: the second passive scalar makes the flux tiles too large for a third CTA
+template <int NP> struct TmaMinB { static constexpr int value = (NP == 1) ? CTU_TMA_MINB : 2; };
 constexpr int ceven(int n) { return (n + 1) & ~1; }
 constexpr size_t al128(size_t b) { return (b + 127) & ~(size_t)127; }
 
@@ -161,12 +178,14 @@ struct Trans2Smem {
     using CT = ZoneTile<N>;
     static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = (size_t)NFX * F1T::ZONES * 8, B_F2 = (size_t)NFX * F2T::ZONES * 8,
                             B_C = (size_t)CT::ZONES * 8;
-    static constexpr size_t O_QM = 0, O_QP = al128(O_QM + B_Q), O_F1 = al128(O_QP + B_Q), O_F2 = al128(O_F1 + B_F1),
+    static constexpr size_t B_QS = CTU_Q_LDG ? 0 : B_Q;    // shared-memory bytes of one interface-state tile
+    static constexpr size_t O_QM = 0, O_QP = al128(O_QM + B_QS), O_F1 = al128(O_QP + B_QS), O_F2 = al128(O_F1 + B_F1),
                             O_C = al128(O_F2 + B_F2), O_BAR = al128(O_C + B_C), TOTAL = O_BAR + 128;
-    static constexpr unsigned TX_BYTES = (unsigned)(2 * B_Q + B_F1 + B_F2 + B_C);
+    static constexpr unsigned TX_BYTES = (unsigned)(2 * B_QS + B_F1 + B_F2 + B_C);
 };
 
 struct Trans2Args {
+    A4 qm, qp;            // interface states of direction N (read directly when CTU_Q_LDG)
     A4 Fo1, Fo2;          // outputs F^{N|T1}, F^{N|T2}
     Box3 b1, b2;          // their boxes
     int ilo[3], qlo[3];   // low corners of the interface-array box and of the qs box (TMA coordinates are relative to them)
@@ -174,7 +193,7 @@ struct Trans2Args {
 };
 
 template <int N, int NP>
-static __global__ void __launch_bounds__(TTHR, CTU_TMA_MINB)
+static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
 k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
              const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
              const Trans2Args a, const TileGrid tg) {
@@ -191,25 +210,38 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
     __syncthreads();
     if (threadIdx.x == 0) {
         tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
+#if !CTU_Q_LDG
         tma::load_4d(smem + L::O_QM, &m_qm, bar, fi - pf, fj, fk, 0);
         tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
+#endif
         tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
         tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
         tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
     }
-    tma::mbar_wait(bar, 0);
     const bool in1 = a.b1.contains(c.i, c.j, c.k), in2 = a.b2.contains(c.i, c.j, c.k);
+    double ql[6], qr[6], xl[NP], xr[NP];
+#if CTU_Q_LDG
+    if (in1 || in2) {   // own face's states: plain global loads, in flight while the flux tiles land
+        const long oq = a.qm.idx(c.i, c.j, c.k);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) { ql[n] = a.qm.at(oq, n); qr[n] = a.qp.at(oq, n); }
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) { xl[ip] = a.qm.at(oq, IS_X + ip); xr[ip] = a.qp.at(oq, IS_X + ip); }
+    }
+#endif
+    tma::mbar_wait(bar, 0);
     if (!in1 && !in2) return;
-    const FaceTile sQM{reinterpret_cast<const double*>(smem + L::O_QM)}, sQP{reinterpret_cast<const double*>(smem + L::O_QP)};
     const typename L::F1T sF1{reinterpret_cast<const double*>(smem + L::O_F1)};
     const typename L::F2T sF2{reinterpret_cast<const double*>(smem + L::O_F2)};
     const typename L::CT sC{reinterpret_cast<const double*>(smem + L::O_C)};
+#if !CTU_Q_LDG
+    const FaceTile sQM{reinterpret_cast<const double*>(smem + L::O_QM)}, sQP{reinterpret_cast<const double*>(smem + L::O_QP)};
     const int of = FaceTile::off(c.tx + pf, c.ty, c.tz);
-    double ql[6], qr[6], xl[NP], xr[NP];
 #pragma unroll
     for (int n = 0; n < 6; ++n) { ql[n] = sQM(of, n); qr[n] = sQP(of, n); }
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) { xl[ip] = sQM(of, IS_X + ip); xr[ip] = sQP(of, IS_X + ip); }
+#endif
     const int oc = L::CT::off(c.tx + pq, c.ty, c.tz);
     const double cl = sC(oc, 0), cr = sC(oc + L::CT::stride(N), 0);
     const int idx = (N == 0) ? c.i : (N == 1) ? c.j : c.k;
@@ -258,12 +290,14 @@ struct FinalSmem {
     using DT = NodeTile<N>;
     static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = (size_t)NFX * F1T::ZONES * 8, B_F2 = (size_t)NFX * F2T::ZONES * 8,
                             B_C = (size_t)CT::ZONES * 8, B_D = (size_t)DT::ZONES * 8;
-    static constexpr size_t O_QM = 0, O_QP = al128(O_QM + B_Q), O_F1 = al128(O_QP + B_Q), O_F2 = al128(O_F1 + B_F1),
+    static constexpr size_t B_QS = CTU_Q_LDG ? 0 : B_Q;
+    static constexpr size_t O_QM = 0, O_QP = al128(O_QM + B_QS), O_F1 = al128(O_QP + B_QS), O_F2 = al128(O_F1 + B_F1),
                             O_C = al128(O_F2 + B_F2), O_D = al128(O_C + B_C), O_BAR = al128(O_D + B_D), TOTAL = O_BAR + 128;
-    static constexpr unsigned TX_BYTES = (unsigned)(2 * B_Q + B_F1 + B_F2 + B_C + B_D);
+    static constexpr unsigned TX_BYTES = (unsigned)(2 * B_QS + B_F1 + B_F2 + B_C + B_D);
 };
 
 struct FinalArgs {
+    A4 qm, qp;            // interface states of direction N (read directly when CTU_Q_LDG)
     A4 U;                 // Sborder (artificial viscosity needs U_i - U_{i-1})
     A4 Fo;                // output: final flux on N-faces
     int ilo[3], qlo[3];
@@ -271,7 +305,7 @@ struct FinalArgs {
 };
 
 template <int N, int NP>
-static __global__ void __launch_bounds__(TTHR, CTU_TMA_MINB)
+static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
 k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
             const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
             const __grid_constant__ CUtensorMap m_d, const FinalArgs a, const TileGrid tg) {
@@ -287,8 +321,10 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
     __syncthreads();
     if (threadIdx.x == 0) {
         tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
+#if !CTU_Q_LDG
         tma::load_4d(smem + L::O_QM, &m_qm, bar, fi - pf, fj, fk, 0);
         tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
+#endif
         tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
         tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
         tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
@@ -297,7 +333,15 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
     const bool active = c.i <= tg.hi0 && c.j <= tg.hi1 && c.k <= tg.hi2;
     // conserved-state differences for the artificial viscosity: plain global loads, in flight while the tile lands
     double dU[6], dUX[NP];
+    double ql[6], qr[6], xl[NP], xr[NP];
     if (active) {
+#if CTU_Q_LDG
+        const long oq = a.qm.idx(c.i, c.j, c.k);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) { ql[n] = a.qm.at(oq, n); qr[n] = a.qp.at(oq, n); }
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) { xl[ip] = a.qm.at(oq, IS_X + ip); xr[ip] = a.qp.at(oq, IS_X + ip); }
+#endif
         const long ou = a.U.idx(c.i, c.j, c.k);
         const long oum = ou - ((N == 0) ? 1 : (N == 1) ? a.U.sj : a.U.sk);
 #pragma unroll
@@ -307,17 +351,18 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
     }
     tma::mbar_wait(bar, 0);
     if (!active) return;
-    const FaceTile sQM{reinterpret_cast<const double*>(smem + L::O_QM)}, sQP{reinterpret_cast<const double*>(smem + L::O_QP)};
     const typename L::F1T sF1{reinterpret_cast<const double*>(smem + L::O_F1)};
     const typename L::F2T sF2{reinterpret_cast<const double*>(smem + L::O_F2)};
     const typename L::CT sC{reinterpret_cast<const double*>(smem + L::O_C)};
     const typename L::DT sD{reinterpret_cast<const double*>(smem + L::O_D)};
+#if !CTU_Q_LDG
+    const FaceTile sQM{reinterpret_cast<const double*>(smem + L::O_QM)}, sQP{reinterpret_cast<const double*>(smem + L::O_QP)};
     const int of = FaceTile::off(c.tx + pf, c.ty, c.tz);
-    double ql[6], qr[6], xl[NP], xr[NP];
 #pragma unroll
     for (int n = 0; n < 6; ++n) { ql[n] = sQM(of, n); qr[n] = sQP(of, n); }
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) { xl[ip] = sQM(of, IS_X + ip); xr[ip] = sQP(of, IS_X + ip); }
+#endif
     const int oc = L::CT::off(c.tx + pq, c.ty, c.tz);
     const double cl = sC(oc, 0), cr = sC(oc + L::CT::stride(N), 0);
     const int idx = (N == 0) ? c.i : (N == 1) ? c.j : c.k;
@@ -660,7 +705,7 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
 }
 
 template <int D, int NP>
-static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, 2)
+static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, CTU_TRACE_MINB)
 k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, const TraceRiemannArgs a) {
     using L = TraceSmem<D, NP>;
     using TT = TrTile<D>;

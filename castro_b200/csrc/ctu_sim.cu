@@ -440,6 +440,7 @@ void ctu_params_defaults(ctu_params_t* p) {
     p->small_x = 1.e-30;
     p->nspec = 1; p->naux = 0; p->nadv = 0;
     p->aion[0] = 1.0; p->zion[0] = 1.0;
+    p->do_grav = 0; p->grav_source_type = 4; p->const_grav = 0.0;
 }
 
 // Castro::variableSetUp, Source/driver/Castro_setup.cpp:226-285 (+ eos_init, Microphysics interfaces/eos.H:17-50)

@@ -11,7 +11,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcastro_ctu.so")
+# CTU_LIB: developer A/B switch (tools/build_variant.sh); the product library is libcastro_ctu.so
+SO_PATH = os.environ.get("CTU_LIB") or os.path.join(_HERE, "libcastro_ctu.so")
 _LIB = None
 
 

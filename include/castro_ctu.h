@@ -104,6 +104,12 @@ typedef struct ctu_params_t {
     double small_x;                /* network.small_x */
     int nspec, naux, nadv;
     double aion[CTU_MAX_SPEC], zion[CTU_MAX_SPEC];
+    /* gravity category (Source/driver/_cpp_parameters: do_grav, grav_source_type; gravity.gravity_type = ConstantGrav,
+     * gravity.const_grav, Source/gravity/Gravity.cpp).  Only used by the host drivers (ctu_sim_*), which build the old-/new-time
+     * gravitational source terms around ctu_hydro_advance exactly like Castro::do_old_sources / do_new_sources. */
+    int do_grav;                   /* 0 = pure hydro */
+    int grav_source_type;          /* 1..4 (default 4), Castro_gravity.cpp:316-690 */
+    double const_grav;             /* ConstantGrav: acceleration along the LAST dimension (z in 3-D) */
 } ctu_params_t;
 
 /* opaque scratch arena (replaces The_Async_Arena() temporaries of Castro_ctu_hydro.cpp:147-189) */

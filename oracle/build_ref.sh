@@ -14,6 +14,10 @@
 #   oracle/_ref/Castro3d_sedov.ex        serial, -O3, no FMA  (parity oracle, golden generator)
 #   oracle/_ref/Castro3d_sedov_omp.ex    OpenMP build         (CPU baseline for bench.py)
 #   oracle/_ref/Castro3d_kh.ex           Kelvin-Helmholtz problem, serial (golden generator for the 2-passive path)
+#   oracle/_ref/Castro3d_rt.ex           Rayleigh-Taylor problem with constant gravity, serial (golden generator for the source-term path).
+#                                        The reference's RT initial-data header does not compile with DIM=3 (an unqualified `L_x`,
+#                                        problem_initialize_state_data.H:50); the recipe qualifies that one identifier in the SCRATCH COPY of
+#                                        the problem directory.  No file of the hot path (Source/hydro, Source/driver, Source/gravity) is touched.
 #   oracle/_ref/fcompare.ex              AMReX plotfile comparator (DIM=3)
 set -euo pipefail
 REF=${REF:-/root/reference}
@@ -39,6 +43,11 @@ if [ "$what" = all ] || [ "$what" = serial ]; then build Sedov Castro3d_sedov DI
 if [ "$what" = all ] || [ "$what" = omp ];    then build Sedov Castro3d_sedov_omp DIM=3 USE_OMP=TRUE; fi
 # KH as shipped: NUMADV := 1 in its GNUmakefile -> NUM_STATE = 9 (one advected scalar + one species): pins the 2-passive path
 if [ "$what" = all ] || [ "$what" = kh ];     then build KH Castro3d_kh DIM=3; fi
+if [ "$what" = all ] || [ "$what" = rt ]; then
+  if [ ! -d "$W/Castro3d_rt" ]; then cp -r "$REF/Exec/hydro_tests/RT" "$W/Castro3d_rt"; fi
+  sed -i 's/0.5e0_rt \* L_x/0.5e0_rt * problem::L_x/' "$W/Castro3d_rt/problem_initialize_state_data.H"
+  build RT Castro3d_rt DIM=3
+fi
 if [ "$what" = all ] || [ "$what" = fcompare ]; then
   d="$W/fcompare"; mkdir -p "$d"; cp -r "$REF/external/amrex/Tools/Plotfile/"* "$d"/
   ( cd "$d" && make AMREX_HOME="$REF/external/amrex" programs=fcompare DIM=3 USE_MPI=FALSE -j"$J" >build.log 2>&1 ) || { tail -30 "$d/build.log"; exit 1; }

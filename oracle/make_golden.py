@@ -51,7 +51,16 @@ KH_CASES = {
 }
 
 
-def run_case(name, n_cell, max_step, snaps, extra, exe=EXE, inputs=INPUTS):
+# Rayleigh-Taylor with constant gravity (pins the source-term path: old/new gravity sources, src_to_prim, traced sources)
+RT_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_rt.ex")
+RT_INPUTS = os.path.join(ROOT, "bench_inputs", "inputs.rt3d")
+RT_CASES = {
+    "rt16_cgf": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=0"]),                                # grav_source_type = 4 (default)
+    "rt16_hllc_gst2": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=2", "castro.grav_source_type=2"]),
+}
+
+
+def run_case(name, n_cell, max_step, snaps, extra, exe=EXE, inputs=INPUTS, ncomp=None):
     if isinstance(n_cell, int):
         n_cell = (n_cell,) * 3
     wd = tempfile.mkdtemp(prefix="golden_")
@@ -73,7 +82,7 @@ def run_case(name, n_cell, max_step, snaps, extra, exe=EXE, inputs=INPUTS):
             times.append(h["time"])
             if s in snaps:
                 h, U = read_plotfile(pf)
-                states["U%d" % s] = U
+                states["U%d" % s] = U if ncomp is None else np.ascontiguousarray(U[:ncomp])   # gravity builds append phiGrav, grav_*
         meta = dict(n_cell=np.array(n_cell), times=np.array(times), names=np.array(h["names"]),
                     problo=np.array(h["problo"]), probhi=np.array(h["probhi"]), overrides=np.array(extra))
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **meta, **states)
@@ -92,3 +101,7 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case(name, n, ms, snaps, extra, exe=KH_EXE, inputs=KH_INPUTS)
+    for name, (n, ms, snaps, extra) in RT_CASES.items():
+        if only and name not in only:
+            continue
+        run_case(name, n, ms, snaps, extra, exe=RT_EXE, inputs=RT_INPUTS, ncomp=8)

@@ -69,3 +69,24 @@ def load_kh_case(name):
     geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), periodic=(1, 1, 1), lo_bc=(0, 0, 0), hi_bc=(0, 0, 0))
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
     return par, geom, c["prob"], g, snaps
+
+
+RT_CASES = {
+    "rt16_cgf": dict(solver=0, grav_source_type=4),
+    "rt16_hllc_gst2": dict(solver=2, grav_source_type=2),
+}
+
+
+def load_rt_case(name):
+    """Rayleigh-Taylor with constant gravity (bench_inputs/inputs.rt3d; goldens from the reference's RT executable,
+    oracle/make_golden.py RT_CASES): periodic x,y, slip walls in z, const_grav = -1, gamma = 5/3."""
+    c = RT_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    par = abi.default_params()
+    par.riemann_solver = c["solver"]
+    par.cfl, par.init_shrink, par.change_max = 0.8, 0.3, 1.1
+    par.do_grav, par.grav_source_type, par.const_grav = 1, c["grav_source_type"], -1.0
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), periodic=(1, 1, 0), lo_bc=(0, 0, 4), hi_bc=(0, 0, 4))
+    snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
+    return par, geom, g, snaps

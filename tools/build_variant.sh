@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+# Developer A/B tool: build castro_b200/libcastro_ctu_<name>.so with extra -D flags (same sources, same arithmetic);
+# select it at run time with CTU_LIB=<path> (castro_b200/lib.py).   usage: tools/build_variant.sh <name> [-DFLAG=..]...
+set -euo pipefail
+name=$1; shift
+here="$(cd "$(dirname "$0")/.." && pwd)"
+src="$here/castro_b200/csrc"
+obj="/tmp/ctu_variant_$name"; mkdir -p "$obj"
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+for f in ctu_api ctu_sim; do
+  nvcc $ARCH -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC "$@" -c "$src/$f.cu" -o "$obj/$f.o" &
+done
+wait
+nvcc $ARCH -shared -o "$here/castro_b200/libcastro_ctu_$name.so" "$obj/ctu_api.o" "$obj/ctu_sim.o" -lcudart
+echo "built castro_b200/libcastro_ctu_$name.so ($*)"
