@@ -213,13 +213,13 @@ int launch_trans2_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs
     return launch_trans2_np<2>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
 }
 
-template <int D, int NP>
+template <int D, int NP, bool SRC>
 int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1, const Box3& tb,
-                         double dt, cudaStream_t st) {
+                         double dt, const A4& srcq, cudaStream_t st) {
     using L = TraceSmem<D, NP>;
     using TT = TrTile<D>;
     static bool attr = false;
-    if (!attr) { int rc = set_smem(k_trace_riemann_tma<D, NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    if (!attr) { int rc = set_smem(k_trace_riemann_tma<D, NP, SRC>, L::TOTAL); if (rc) return rc; attr = true; }
     CTU_MAP(m_q, qs, qbx_a, L::NQC, L::QT, L::NQC)
     TraceRiemannArgs a;
     a.fd = fd; a.qm = ta.qm[D]; a.qp = ta.qp[D]; a.Fo = F1[D];
@@ -232,21 +232,28 @@ int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, con
     a.nty = (D == 1) ? (n[1] - 1 + TT::SY - 1) / TT::SY : (n[1] + TT::SY - 1) / TT::SY;
     a.ntz = (D == 2) ? (n[2] - 1 + TT::SZ - 1) / TT::SZ : (n[2] + TT::SZ - 1) / TT::SZ;
     a.dtdL = dt / P.dx[D];
-    k_trace_riemann_tma<D, NP><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
+    a.srcq = srcq; a.hdt = 0.5 * dt;
+    k_trace_riemann_tma<D, NP, SRC><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
     return 0;
 }
-template <int NP>
+template <int NP, bool SRC>
 int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
-                            const Box3& tb, double dt, cudaStream_t st) {
-    int rc = launch_trace_riemann<0, NP>(P, ta, qs, qbx_a, fd, F1, tb, dt, st);
-    if (!rc) rc = launch_trace_riemann<1, NP>(P, ta, qs, qbx_a, fd, F1, tb, dt, st);
-    if (!rc) rc = launch_trace_riemann<2, NP>(P, ta, qs, qbx_a, fd, F1, tb, dt, st);
+                            const Box3& tb, double dt, const A4& srcq, cudaStream_t st) {
+    int rc = launch_trace_riemann<0, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, st);
+    if (!rc) rc = launch_trace_riemann<1, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, st);
+    if (!rc) rc = launch_trace_riemann<2, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, st);
     return rc;
 }
 int launch_trace_riemann_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
-                             const Box3& tb, double dt, cudaStream_t st) {
-    if (np == 1) return launch_trace_riemann_np<1>(P, ta, qs, qbx_a, fd, F1, tb, dt, st);
-    return launch_trace_riemann_np<2>(P, ta, qs, qbx_a, fd, F1, tb, dt, st);
+                             const Box3& tb, double dt, const A4* srcq, cudaStream_t st) {
+    if (srcq) {
+        if (np == 1) return launch_trace_riemann_np<1, true>(P, ta, qs, qbx_a, fd, F1, tb, dt, *srcq, st);
+        return launch_trace_riemann_np<2, true>(P, ta, qs, qbx_a, fd, F1, tb, dt, *srcq, st);
+    }
+    A4 none;
+    std::memset(&none, 0, sizeof(none));
+    if (np == 1) return launch_trace_riemann_np<1, false>(P, ta, qs, qbx_a, fd, F1, tb, dt, none, st);
+    return launch_trace_riemann_np<2, false>(P, ta, qs, qbx_a, fd, F1, tb, dt, none, st);
 }
 
 template <int N, int NP>
@@ -381,8 +388,11 @@ struct HydroRun {
     ctu_workspace* ws;
     DevPar P;
     int np, NQS, NIS, NFX;
+    int P_predictor;         // castro.source_term_predictor
     Box3 vbx;
     A4 Sb, Sn;
+    A4 osrc, scorr;          // conserved old-time source / source corrector (p == nullptr if absent)
+    bool have_src;
     bool from_sb, want_dt, use_tma;
     int n_clean;
     double dt;
@@ -399,7 +409,7 @@ struct HydroRun {
 
 HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_geom_t* geom, const int valid_lo[3], const int valid_hi[3],
                       const ctu_fab_t* Sborder, ctu_fab_t* S_new, ctu_fab_t* const flux[3], ctu_fab_t* const mass_flux[3], double dt,
-                      int flags, bool want_dt, cudaStream_t st, int* rc_out) {
+                      int flags, bool want_dt, cudaStream_t st, int* rc_out, const ctu_fab_t* old_src, const ctu_fab_t* src_corr) {
     *rc_out = 0;
     if (!ws || !par || !geom || !Sborder || !S_new || !valid_lo || !valid_hi) { *rc_out = CTU_ERR_BAD_ARG; return nullptr; }
     if (!device_ok()) { *rc_out = CTU_ERR_NO_DEVICE; return nullptr; }
@@ -408,12 +418,22 @@ HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     HydroRun* r = new HydroRun(ws, st);
     r->P = make_devpar(par, geom);
     const DevPar& P = r->P;
+    r->P_predictor = par->source_term_predictor;
     r->np = P.npassive;
     r->vbx = make_box(valid_lo, valid_hi);
     if (!r->vbx.ok() || Sborder->ncomp < P.nstate || S_new->ncomp < P.nstate || !fab_covers(Sborder, grow(r->vbx, CTU_NGROW)) ||
         !fab_covers(S_new, r->vbx)) {
         delete r; *rc_out = CTU_ERR_BAD_ARG; return nullptr;
     }
+    // source terms: NSRC = 7 components on grow(valid, NUM_GROW_SRC); src_corr only together with old_src
+    std::memset(&r->osrc, 0, sizeof(A4)); std::memset(&r->scorr, 0, sizeof(A4));
+    r->have_src = old_src != nullptr;
+    if ((src_corr && !old_src) || (old_src && (old_src->ncomp < 7 || !fab_covers(old_src, grow(r->vbx, CTU_NGROW_SRC)))) ||
+        (src_corr && (src_corr->ncomp < 7 || !fab_covers(src_corr, grow(r->vbx, CTU_NGROW_SRC))))) {
+        delete r; *rc_out = CTU_ERR_BAD_ARG; return nullptr;
+    }
+    if (old_src) r->osrc = make_a4(*old_src);
+    if (src_corr) r->scorr = make_a4(*src_corr);
     r->n_clean = flags & CTU_ADV_NCLEAN_MASK;
     r->from_sb = (flags & CTU_ADV_SNEW_FROM_SBORDER) != 0;
     r->want_dt = want_dt;
@@ -425,7 +445,7 @@ HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     // 16 bytes, which is what the TMA tensor maps of the tile-staged kernels require
     r->qpad = (nxg + 8) & 1; r->ipad = (nxg + 3) & 1;
     // per z-plane scratch: qs on grow(tile,4); everything else on ibx = [lo-1, hi+2]
-    r->plane_q = (size_t)(nxg + 8 + r->qpad) * (nyg + 8) * r->NQS * sizeof(double);
+    r->plane_q = (size_t)(nxg + 8 + r->qpad) * (nyg + 8) * (r->NQS + (r->have_src ? NSRCQ : 0)) * sizeof(double);
     r->plane_i = (size_t)(nxg + 3 + r->ipad) * (nyg + 4) * (size_t)(2 + 6 * r->NIS + 9 * r->NFX) * sizeof(double);
     r->use_tma = tma_ok(P);
     const double* dx = geom->dx;
@@ -476,6 +496,10 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
         // carve the arena
         double* p = ws->arena;
         const A4 qs = make_a4(p, qbx_a); p += qbx_a.npts() * NQS;
+        const Box3 sbx = grow(tb, CTU_NGROW_SRC);
+        A4 srcq;
+        std::memset(&srcq, 0, sizeof(srcq));
+        if (r->have_src) { srcq = make_a4(p, sbx); p += sbx.npts() * NSRCQ; }
         const size_t ni = ibx.npts();
         const A4 fd = make_a4(p, ibx); p += ni * 2;
         TraceArgs ta;
@@ -490,20 +514,32 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
 
         {   LaunchBox lb = make_lb(qbx);
             tm.begin(0);
-            k_ctoprim<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, qs, lb); ++launches; tm.end(1); }
+            k_ctoprim<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, qs, lb); ++launches;
+            if (r->have_src) {   // src_to_prim on grow(slab, 3) (Castro_ctu_hydro.cpp:282); timed with ctoprim
+                const LaunchBox ls = make_lb(sbx);
+                k_src_to_prim<<<nblocks(ls.n), TPB, 0, st>>>(P, Sb, qs, r->osrc, r->scorr, r->P_predictor, srcq, ls, dt); ++launches;
+            }
+            tm.end(r->have_src ? 2 : 1); }
         {   LaunchBox lb = make_lb(obx);
             tm.begin(1);
             k_flat_div<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb); ++launches; tm.end(1);
             if (use_tma) {
                 tm.begin(2);
-                rc = launch_trace_riemann_all(P, np, ta, qs, qbx_a, fd, F1, tb, dt, st);
+                rc = launch_trace_riemann_all(P, np, ta, qs, qbx_a, fd, F1, tb, dt, r->have_src ? &srcq : nullptr, st);
                 if (rc) return rc;
                 launches += 3; tm.end(3);
             } else {
             tm.begin(2);
-            k_trace<0><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt);
-            k_trace<1><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt);
-            k_trace<2><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt); launches += 3; tm.end(3); } }
+            if (r->have_src) {
+                k_trace<0, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                k_trace<1, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                k_trace<2, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+            } else {
+                k_trace<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                k_trace<1, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                k_trace<2, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+            }
+            launches += 3; tm.end(3); } }
         const Box3 nb[3] = {[&] { Box3 b = tb; b.hi[0] += 1; return b; }(), [&] { Box3 b = tb; b.hi[1] += 1; return b; }(),
                             [&] { Box3 b = tb; b.hi[2] += 1; return b; }()};
         // first-pass fluxes: cxbx = grow(xbx,(0,1,1)), cybx = grow(ybx,(1,0,1)), czbx = grow(zbx,(1,1,0))
@@ -653,10 +689,9 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
                       const ctu_fab_t* Sborder, const ctu_fab_t* old_src, const ctu_fab_t* src_corr,
                       ctu_fab_t* S_new, ctu_fab_t* const flux[3], ctu_fab_t* const mass_flux[3],
                       double dt, int flags, double dt_est[2], int dt_loc[3], int n_bad[2], void* stream) {
-    if (old_src || src_corr) return CTU_ERR_UNSUPPORTED;   // source-term tracing: SURVEY §8(f) rank 1
     int rc = 0;
     HydroRun* r = hydro_begin(ws, par, geom, valid_lo, valid_hi, Sborder, S_new, flux, mass_flux, dt, flags, dt_est != nullptr,
-                              (cudaStream_t)stream, &rc);
+                              (cudaStream_t)stream, &rc, old_src, src_corr);
     if (!r) return rc;
     const long nzv = valid_hi[2] - valid_lo[2] + 1;
     long KS = hydro_max_slab_planes(r);

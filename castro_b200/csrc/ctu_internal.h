@@ -12,7 +12,8 @@ bool fab_covers(const ctu_fab_t* f, const Box3& b);
 struct HydroRun;
 HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_geom_t* geom, const int valid_lo[3], const int valid_hi[3],
                       const ctu_fab_t* Sborder, ctu_fab_t* S_new, ctu_fab_t* const flux[3], ctu_fab_t* const mass_flux[3], double dt,
-                      int flags, bool want_dt, cudaStream_t st, int* rc_out);
+                      int flags, bool want_dt, cudaStream_t st, int* rc_out, const ctu_fab_t* old_src = nullptr,
+                      const ctu_fab_t* src_corr = nullptr);
 long hydro_max_slab_planes(const HydroRun* r);
 int hydro_reserve(HydroRun* r, long planes_per_slab);
 int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab);

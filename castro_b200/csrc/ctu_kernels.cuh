@@ -116,12 +116,98 @@ static __global__ void __launch_bounds__(TPB) k_flat_div(const DevPar P, const A
 }
 
 // ------------------------------------------------------------------------------------------------
-// Castro::trace_ppm (trace_ppm.cpp:17-678) for one direction of one zone, zero source terms.
+// Source terms in the tracing: hydro::src_to_prim (advection_util.H:16-79) and the traced primitive sources of
+// trace_ppm (trace_ppm.cpp:309-440).  srcq scratch layout: rho u v w p (rho e)  (reference src_q minus the unused QTEMP slot).
 // ------------------------------------------------------------------------------------------------
+constexpr int NSRCQ = 6;
+
+// one thread = one zone of grow(slab, 3)
+static __global__ void __launch_bounds__(TPB) k_src_to_prim(const DevPar P, const A4 U, const A4 qs, const A4 osrc, const A4 scorr,
+                                                     const int predictor, const A4 srcq, const LaunchBox lb, const double dt) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long ou = U.idx(i, j, k), oq = qs.idx(i, j, k), oo = osrc.idx(i, j, k), os = srcq.idx(i, j, k);
+    double srcU[7];
+#pragma unroll
+    for (int n = 0; n < 7; ++n) {
+        double v = 0.0;
+        if (predictor == 1 && scorr.p && (n == UMX || n == UMY || n == UMZ)) v += 0.5 * dt * scorr.at(scorr.idx(i, j, k), n);
+        v += osrc.at(oo, n);
+        srcU[n] = v;
+    }
+    const double rho = qs.at(oq, QS_RHO);
+    const double rhoinv = 1.0 / rho;
+    const double qre = qs.at(oq, QS_RE);
+    Eos s;
+    s.T = U.at(ou, UTEMP); s.rho = rho; s.e = qre * rhoinv;
+    s.mu = eos_mu(P, [&](int n) { return U.at(ou, P.UFS + n) * rhoinv; });
+    eos_re<true>(P, s);
+    const double s_rho = srcU[URHO];
+    srcq.at(os, QS_RHO) = s_rho;
+    srcq.at(os, QS_U) = (srcU[UMX] - qs.at(oq, QS_U) * s_rho) * rhoinv;
+    srcq.at(os, QS_V) = (srcU[UMY] - qs.at(oq, QS_V) * s_rho) * rhoinv;
+    srcq.at(os, QS_W) = (srcU[UMZ] - qs.at(oq, QS_W) * s_rho) * rhoinv;
+    const double s_re = srcU[UEINT];
+    srcq.at(os, QS_RE) = s_re;
+    srcq.at(os, QS_P) = s.dpde * (s_re - qre * s_rho * rhoinv) * rhoinv + s.dpdr_e * s_rho;
+}
+
+// hdt * (Im_src_*, Ip_src_*) of trace_ppm.cpp:494-675; all +0.0 when a source component is not traced, which is exactly
+// what the reference adds in that case
+struct SrcAdd {
+    double m_rho0 = 0.0, m_rho1 = 0.0, m_un0 = 0.0, m_un2 = 0.0, m_p0 = 0.0, m_p1 = 0.0, m_p2 = 0.0, m_re0 = 0.0, m_re1 = 0.0,
+           m_ut = 0.0, m_utt = 0.0;   // plus state on the low face
+    double p_rho2 = 0.0, p_rho1 = 0.0, p_un0 = 0.0, p_un2 = 0.0, p_p0 = 0.0, p_p1 = 0.0, p_p2 = 0.0, p_re2 = 0.0, p_re1 = 0.0,
+           p_ut = 0.0, p_utt = 0.0;   // minus state on the high face
+};
+
+// sb: &srcq(zone, comp 0); sn component stride; st stride along DIR.  Per-zone check_trace_source (ppm.H:13-43).
 template <int DIR>
+__device__ __forceinline__ void trace_sources(const DevPar& P, const double* __restrict__ sb, const long sn, const long st, const double flat,
+                                              const double un, const double cc, const double dtdL, const double hdt, SrcAdd& sa) {
+    constexpr int QUN = QS_U + DIR;
+    constexpr int QUT = QS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
+    constexpr int QUTT = QS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
+    double sm, sp, Ip, Im;
+    Parabola pb;
+#define CTU_SRC_RECON(comp, BODY)                                                                \
+    {                                                                                            \
+        const double* __restrict__ a = sb + (comp) * sn;                                         \
+        const double s2m = a[-2 * st], s1m = a[-st], s0 = a[0], s1p = a[st], s2p = a[2 * st];    \
+        if (fabs(s2m) > 0.0 || fabs(s1m) > 0.0 || fabs(s0) > 0.0 || fabs(s1p) > 0.0 || fabs(s2p) > 0.0) { \
+            ppm_reconstruct(P, s2m, s1m, s0, s1p, s2p, flat, sm, sp);                            \
+            pb.set(sm, sp, s0);                                                                  \
+            BODY                                                                                 \
+        }                                                                                        \
+    }
+    CTU_SRC_RECON(QS_RHO, {
+        pb.integ(un - cc, dtdL, Ip, Im); sa.m_rho0 = hdt * Im;
+        pb.integ(un, dtdL, Ip, Im); sa.m_rho1 = hdt * Im; sa.p_rho1 = hdt * Ip;
+        pb.integ(un + cc, dtdL, Ip, Im); sa.p_rho2 = hdt * Ip; })
+    CTU_SRC_RECON(QUN, {
+        pb.integ(un - cc, dtdL, Ip, Im); sa.m_un0 = hdt * Im; sa.p_un0 = hdt * Ip;
+        pb.integ(un + cc, dtdL, Ip, Im); sa.m_un2 = hdt * Im; sa.p_un2 = hdt * Ip; })
+    CTU_SRC_RECON(QS_P, {
+        pb.integ(un - cc, dtdL, Ip, Im); sa.m_p0 = hdt * Im; sa.p_p0 = hdt * Ip;
+        pb.integ(un, dtdL, Ip, Im); sa.m_p1 = hdt * Im; sa.p_p1 = hdt * Ip;
+        pb.integ(un + cc, dtdL, Ip, Im); sa.m_p2 = hdt * Im; sa.p_p2 = hdt * Ip; })
+    CTU_SRC_RECON(QS_RE, {
+        pb.integ(un - cc, dtdL, Ip, Im); sa.m_re0 = hdt * Im;
+        pb.integ(un, dtdL, Ip, Im); sa.m_re1 = hdt * Im; sa.p_re1 = hdt * Ip;
+        pb.integ(un + cc, dtdL, Ip, Im); sa.p_re2 = hdt * Ip; })
+    CTU_SRC_RECON(QUT, { pb.integ(un, dtdL, Ip, Im); sa.m_ut = hdt * Im; sa.p_ut = hdt * Ip; })
+    CTU_SRC_RECON(QUTT, { pb.integ(un, dtdL, Ip, Im); sa.m_utt = hdt * Im; sa.p_utt = hdt * Ip; })
+#undef CTU_SRC_RECON
+}
+
+// ------------------------------------------------------------------------------------------------
+// Castro::trace_ppm (trace_ppm.cpp:17-678) for one direction of one zone; SRC: with traced source terms (sa), else zero sources.
+// ------------------------------------------------------------------------------------------------
+template <int DIR, bool SRC>
 __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq, long st, double flat, double dtdL,
                                           const A4& qm, const A4& qp, long op, long om, bool do_p, bool do_m,
-                                          bool refl_lo, bool refl_hi) {
+                                          bool refl_lo, bool refl_hi, const SrcAdd& sa) {
+#define SA(x) (SRC ? sa.x : 0.0)
     constexpr int QUN = QS_U + DIR;
     constexpr int QUT = QS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
     constexpr int QUTT = QS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
@@ -197,10 +283,10 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
     // "x + 0.0" below stands for the reference's "+ hdt * Im_src_*" with identically zero sources: it is kept
     // because it turns -0.0 into +0.0 exactly like the reference does.
     if (do_p) {   // plus state on face i (trace_ppm.cpp:494-581)
-        double rho_ref = Im_rho0 + 0.0;
-        double un_ref = Im_un0 + 0.0;
-        double p_ref = Im_p0 + 0.0;
-        double rhoe_g_ref = Im_re0 + 0.0;
+        double rho_ref = Im_rho0 + SA(m_rho0);
+        double un_ref = Im_un0 + SA(m_un0);
+        double p_ref = Im_p0 + SA(m_p0);
+        double rhoe_g_ref = Im_re0 + SA(m_re0);
         double gam_g_ref = Im_gc0;
         rho_ref = smax(rho_ref, P.small_dens);
         double rho_ref_inv = 1.0 / rho_ref;
@@ -209,13 +295,13 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
         double cc_ref = sqrt(csq_ref);
         double cc_ref_inv = 1.0 / cc_ref;
         double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
-        double d_um = un_ref - Im_un0 - 0.0;
-        double dptotm = p_ref - Im_p0 - 0.0;
-        double drho = rho_ref - Im_rho1 - 0.0;
-        double dptot = p_ref - Im_p1 - 0.0;
-        double drhoe_g = rhoe_g_ref - Im_re1 - 0.0;
-        double d_up = un_ref - Im_un2 - 0.0;
-        double dptotp = p_ref - Im_p2 - 0.0;
+        double d_um = un_ref - Im_un0 - SA(m_un0);
+        double dptotm = p_ref - Im_p0 - SA(m_p0);
+        double drho = rho_ref - Im_rho1 - SA(m_rho1);
+        double dptot = p_ref - Im_p1 - SA(m_p1);
+        double drhoe_g = rhoe_g_ref - Im_re1 - SA(m_re1);
+        double d_up = un_ref - Im_un2 - SA(m_un2);
+        double dptotp = p_ref - Im_p2 - SA(m_p2);
         double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
         double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
         double alpha0r = drho - dptot / csq_ref;
@@ -228,8 +314,8 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
         const double o_un = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
         const double o_re = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
         const double o_p = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
-        const double o_ut = Im_ut + 0.0;
-        const double o_utt = Im_utt + 0.0;
+        const double o_ut = Im_ut + SA(m_ut);
+        const double o_utt = Im_utt + SA(m_utt);
         qp.at(op, IS_RHO) = o_rho; qp.at(op, IUN) = o_un; qp.at(op, IS_RE) = o_re; qp.at(op, IS_P) = o_p;
         qp.at(op, IUT) = o_ut; qp.at(op, IUTT) = o_utt;
         if (refl_lo) {   // enforce_reflect_states (advection_util.cpp:766-785): left state mirrors the right one
@@ -238,10 +324,10 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
         }
     }
     if (do_m) {   // minus state on face i+1 (trace_ppm.cpp:583-675)
-        double rho_ref = Ip_rho2 + 0.0;
-        double un_ref = Ip_un2 + 0.0;
-        double p_ref = Ip_p2 + 0.0;
-        double rhoe_g_ref = Ip_re2 + 0.0;
+        double rho_ref = Ip_rho2 + SA(p_rho2);
+        double un_ref = Ip_un2 + SA(p_un2);
+        double p_ref = Ip_p2 + SA(p_p2);
+        double rhoe_g_ref = Ip_re2 + SA(p_re2);
         double gam_g_ref = Ip_gc2;
         rho_ref = smax(rho_ref, P.small_dens);
         double rho_ref_inv = 1.0 / rho_ref;
@@ -250,13 +336,13 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
         double cc_ref = sqrt(csq_ref);
         double cc_ref_inv = 1.0 / cc_ref;
         double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
-        double d_um = un_ref - Ip_un0 - 0.0;
-        double dptotm = p_ref - Ip_p0 - 0.0;
-        double drho = rho_ref - Ip_rho1 - 0.0;
-        double dptot = p_ref - Ip_p1 - 0.0;
-        double drhoe_g = rhoe_g_ref - Ip_re1 - 0.0;
-        double d_up = un_ref - Ip_un2 - 0.0;
-        double dptotp = p_ref - Ip_p2 - 0.0;
+        double d_um = un_ref - Ip_un0 - SA(p_un0);
+        double dptotm = p_ref - Ip_p0 - SA(p_p0);
+        double drho = rho_ref - Ip_rho1 - SA(p_rho1);
+        double dptot = p_ref - Ip_p1 - SA(p_p1);
+        double drhoe_g = rhoe_g_ref - Ip_re1 - SA(p_re1);
+        double d_up = un_ref - Ip_un2 - SA(p_un2);
+        double dptotp = p_ref - Ip_p2 - SA(p_p2);
         double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
         double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
         double alpha0r = drho - dptot / csq_ref;
@@ -269,8 +355,8 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
         const double o_un = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
         const double o_re = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
         const double o_p = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
-        const double o_ut = Ip_ut + 0.0;
-        const double o_utt = Ip_utt + 0.0;
+        const double o_ut = Ip_ut + SA(p_ut);
+        const double o_utt = Ip_utt + SA(p_utt);
         qm.at(om, IS_RHO) = o_rho; qm.at(om, IUN) = o_un; qm.at(om, IS_RE) = o_re; qm.at(om, IS_P) = o_p;
         qm.at(om, IUT) = o_ut; qm.at(om, IUTT) = o_utt;
         if (refl_hi) {   // advection_util.cpp:787-805: right state mirrors the left one
@@ -278,6 +364,7 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
             qp.at(om, IUT) = o_ut; qp.at(om, IUTT) = o_utt;
         }
     }
+#undef SA
 }
 
 struct TraceArgs {
@@ -286,9 +373,9 @@ struct TraceArgs {
 };
 
 // one thread = one zone of obx, one direction per launch (blockIdx.y)
-template <int DIR>
+template <int DIR, bool SRC>
 static __global__ void __launch_bounds__(TPB) k_trace(const DevPar P, const A4 qs, const A4 fd, const TraceArgs ta, const LaunchBox lb,
-                                               const double dt) {
+                                               const double dt, const A4 srcq) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
     const long oq = qs.idx(i, j, k);
@@ -306,7 +393,13 @@ static __global__ void __launch_bounds__(TPB) k_trace(const DevPar P, const A4 q
     const bool refl_hi = do_m && sym_hi && idx + 1 == P.domhi[DIR] + 1;  // owns face domhi+1: also writes qp there
     if (sym_lo && idx + 1 == P.domlo[DIR]) do_m = false;                 // qm(domlo) is the mirrored state instead
     if (sym_hi && idx == P.domhi[DIR] + 1) do_p = false;                 // qp(domhi+1) is the mirrored state instead
-    trace_dir<DIR>(P, qs, oq, st, flat, dt / P.dx[DIR], qm, qp, op, om, do_p, do_m, refl_lo, refl_hi);
+    SrcAdd sa;
+    if (SRC) {
+        const long sst = (DIR == 0) ? 1 : (DIR == 1) ? srcq.sj : srcq.sk;
+        trace_sources<DIR>(P, srcq.p + srcq.idx(i, j, k), srcq.sn, sst, flat, qs.at(oq, QS_U + DIR), qs.at(oq, QS_C), dt / P.dx[DIR],
+                           0.5 * dt, sa);
+    }
+    trace_dir<DIR, SRC>(P, qs, oq, st, flat, dt / P.dx[DIR], qm, qp, op, om, do_p, do_m, refl_lo, refl_hi, sa);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -568,16 +568,19 @@ struct TraceRiemannArgs {
     int qlo[3];           // low corner of the qs allocation box
     int ntx, nty, ntz;
     double dtdL;          // dt / dx_D
+    A4 srcq;              // primitive source terms on grow(slab, 3) (SRC instances only)
+    double hdt;           // dt / 2
 };
 
 // Castro::trace_ppm for one zone and direction, zero source terms (trace_ppm.cpp:17-678): the arithmetic of trace_dir in
 // ctu_kernels.cuh with the primitive stencil in shared memory and the results left in registers.
 //   base: &tile(zone, comp 0);  sn: component stride;  st: stride along DIR.   op/om: plus state on the low face, minus
 //   state on the high face (rho u v w p rhoe), xp/xm the passives.
-template <int DIR, int NP>
+template <int DIR, int NP, bool SRC>
 __device__ __forceinline__ void trace_core(const DevPar& P, const double* __restrict__ base, const int sn, const int st, const double flat,
                                            const double dtdL, double* __restrict__ op, double* __restrict__ om, double* __restrict__ xp,
-                                           double* __restrict__ xm) {
+                                           double* __restrict__ xm, const SrcAdd& sa) {
+#define SA(x) (SRC ? sa.x : 0.0)
     constexpr int QUN = QS_U + DIR;
     constexpr int QUT = QS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
     constexpr int QUTT = QS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
@@ -633,10 +636,10 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
 #undef CTU_RECON
     const double small_re = P.small_dens * P.small_ener;
     {   // plus state on the low face (trace_ppm.cpp:494-581)
-        double rho_ref = Im_rho0 + 0.0;
-        double un_ref = Im_un0 + 0.0;
-        double p_ref = Im_p0 + 0.0;
-        double rhoe_g_ref = Im_re0 + 0.0;
+        double rho_ref = Im_rho0 + SA(m_rho0);
+        double un_ref = Im_un0 + SA(m_un0);
+        double p_ref = Im_p0 + SA(m_p0);
+        double rhoe_g_ref = Im_re0 + SA(m_re0);
         double gam_g_ref = Im_gc0;
         rho_ref = smax(rho_ref, P.small_dens);
         double rho_ref_inv = 1.0 / rho_ref;
@@ -645,13 +648,13 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
         double cc_ref = sqrt(csq_ref);
         double cc_ref_inv = 1.0 / cc_ref;
         double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
-        double d_um = un_ref - Im_un0 - 0.0;
-        double dptotm = p_ref - Im_p0 - 0.0;
-        double drho = rho_ref - Im_rho1 - 0.0;
-        double dptot = p_ref - Im_p1 - 0.0;
-        double drhoe_g = rhoe_g_ref - Im_re1 - 0.0;
-        double d_up = un_ref - Im_un2 - 0.0;
-        double dptotp = p_ref - Im_p2 - 0.0;
+        double d_um = un_ref - Im_un0 - SA(m_un0);
+        double dptotm = p_ref - Im_p0 - SA(m_p0);
+        double drho = rho_ref - Im_rho1 - SA(m_rho1);
+        double dptot = p_ref - Im_p1 - SA(m_p1);
+        double drhoe_g = rhoe_g_ref - Im_re1 - SA(m_re1);
+        double d_up = un_ref - Im_un2 - SA(m_un2);
+        double dptotp = p_ref - Im_p2 - SA(m_p2);
         double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
         double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
         double alpha0r = drho - dptot / csq_ref;
@@ -664,14 +667,14 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
         op[IUN] = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
         op[IS_RE] = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
         op[IS_P] = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
-        op[IUT] = Im_ut + 0.0;
-        op[IUTT] = Im_utt + 0.0;
+        op[IUT] = Im_ut + SA(m_ut);
+        op[IUTT] = Im_utt + SA(m_utt);
     }
     {   // minus state on the high face (trace_ppm.cpp:583-675)
-        double rho_ref = Ip_rho2 + 0.0;
-        double un_ref = Ip_un2 + 0.0;
-        double p_ref = Ip_p2 + 0.0;
-        double rhoe_g_ref = Ip_re2 + 0.0;
+        double rho_ref = Ip_rho2 + SA(p_rho2);
+        double un_ref = Ip_un2 + SA(p_un2);
+        double p_ref = Ip_p2 + SA(p_p2);
+        double rhoe_g_ref = Ip_re2 + SA(p_re2);
         double gam_g_ref = Ip_gc2;
         rho_ref = smax(rho_ref, P.small_dens);
         double rho_ref_inv = 1.0 / rho_ref;
@@ -680,13 +683,13 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
         double cc_ref = sqrt(csq_ref);
         double cc_ref_inv = 1.0 / cc_ref;
         double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
-        double d_um = un_ref - Ip_un0 - 0.0;
-        double dptotm = p_ref - Ip_p0 - 0.0;
-        double drho = rho_ref - Ip_rho1 - 0.0;
-        double dptot = p_ref - Ip_p1 - 0.0;
-        double drhoe_g = rhoe_g_ref - Ip_re1 - 0.0;
-        double d_up = un_ref - Ip_un2 - 0.0;
-        double dptotp = p_ref - Ip_p2 - 0.0;
+        double d_um = un_ref - Ip_un0 - SA(p_un0);
+        double dptotm = p_ref - Ip_p0 - SA(p_p0);
+        double drho = rho_ref - Ip_rho1 - SA(p_rho1);
+        double dptot = p_ref - Ip_p1 - SA(p_p1);
+        double drhoe_g = rhoe_g_ref - Ip_re1 - SA(p_re1);
+        double d_up = un_ref - Ip_un2 - SA(p_un2);
+        double dptotp = p_ref - Ip_p2 - SA(p_p2);
         double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
         double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
         double alpha0r = drho - dptot / csq_ref;
@@ -699,12 +702,13 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
         om[IUN] = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
         om[IS_RE] = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
         om[IS_P] = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
-        om[IUT] = Ip_ut + 0.0;
-        om[IUTT] = Ip_utt + 0.0;
+        om[IUT] = Ip_ut + SA(p_ut);
+        om[IUTT] = Ip_utt + SA(p_utt);
     }
+#undef SA
 }
 
-template <int D, int NP>
+template <int D, int NP, bool SRC>
 static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, CTU_TRACE_MINB)
 k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, const TraceRiemannArgs a) {
     using L = TraceSmem<D, NP>;
@@ -740,8 +744,14 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     constexpr int IUN = IS_U + D;
     if (active) {
         const int oq = QT::off(tx + pq + (D == 0 ? 2 : 0), ty + (D == 1 ? 2 : 0), tz + (D == 2 ? 2 : 0));
-        trace_core<D, NP>(P, reinterpret_cast<const double*>(smem + L::O_Q) + oq, QT::ZONES, QT::stride(D), flat, a.dtdL, qp_own, qm_nxt,
-                          xp_own, xm_nxt);
+        const double* sq0 = reinterpret_cast<const double*>(smem + L::O_Q) + oq;
+        SrcAdd sa;
+        if (SRC) {   // traced source terms (trace_ppm.cpp:309-440): the primitive sources come straight from HBM / L2
+            const long sst = (D == 0) ? 1 : (D == 1) ? a.srcq.sj : a.srcq.sk;
+            trace_sources<D>(P, a.srcq.p + a.srcq.idx(i, j, k), a.srcq.sn, sst, flat, sq0[(QS_U + D) * QT::ZONES], sq0[QS_C * QT::ZONES],
+                             a.dtdL, a.hdt, sa);
+        }
+        trace_core<D, NP, SRC>(P, sq0, QT::ZONES, QT::stride(D), flat, a.dtdL, qp_own, qm_nxt, xp_own, xm_nxt, sa);
         // hand the minus state to the thread that owns the high face
 #pragma unroll
         for (int n = 0; n < 6; ++n) sEx[n * L::NTHR + threadIdx.x] = qm_nxt[n];

@@ -378,6 +378,142 @@ __global__ void __launch_bounds__(TPB) k_init_tail(const DevPar P, const A4 S, c
     for (int n = 0; n < 7; ++n) S.at(o, n) = u[n];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Constant gravity (gravity.gravity_type = "ConstantGrav": g = const_grav along z in 3-D), SURVEY §8(f) rank 1.
+//   k_grav_old: Castro::construct_old_gravity_source (Source/gravity/Castro_gravity.cpp:300-428) on every zone of
+//               grow(valid, NUM_GROW_SRC) that lies inside the domain or is a periodic image (Sborder already holds the right
+//               state there, so no separate FillPatch of the source is needed for those zones; physical boundaries are filled
+//               afterwards by k_fill<1> exactly like the reference's FillPatch of Source_Type), fused with
+//               S_new <- Sborder + dt*source and clean_state(S_new) of Castro::do_old_sources (Castro_sources.cpp:111-175).
+//   k_grav_new: Castro::construct_new_gravity_source (Castro_gravity.cpp:430-690) + S_new += dt*source + clean_state
+//               (do_new_sources, Castro_sources.cpp:204-260) + post_timestep's clean_state, with both dt estimates.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_grav_old(const DevPar P, const A4 Sb, const A4 Sn, const A4 osrc, const LaunchBox lb, const Box3 vbx,
+                                                  const double const_grav, const int gst, const double dt) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const int idx[3] = {i, j, k};
+    for (int d = 0; d < 3; ++d)
+        if (!P.periodic[d] && (idx[d] < P.domlo[d] || idx[d] > P.domhi[d])) return;
+    const long ob = Sb.idx(i, j, k);
+    const double grav[3] = {0.0, 0.0, const_grav};
+    double src[7] = {0, 0, 0, 0, 0, 0, 0};
+    double snew[3];
+    const double rho = Sb.at(ob, URHO);
+    const double rhoInv = 1.0 / rho;
+    const double mom[3] = {Sb.at(ob, UMX), Sb.at(ob, UMY), Sb.at(ob, UMZ)};
+#pragma unroll
+    for (int n = 0; n < 3; ++n) snew[n] = mom[n];
+    const double old_ke = 0.5 * (snew[0] * snew[0] + snew[1] * snew[1] + snew[2] * snew[2]) * rhoInv;
+    double Sr[3];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+        Sr[n] = rho * grav[n];
+        src[UMX + n] = Sr[n];
+        snew[n] += dt * src[UMX + n];
+    }
+    double SrE = 0.0;
+    if (gst == 1 || gst == 2 || gst == 4) {
+        SrE = (mom[0] * Sr[0] + mom[1] * Sr[1] + mom[2] * Sr[2]) * rhoInv;
+    } else if (gst == 3) {
+        const double new_ke = 0.5 * (snew[0] * snew[0] + snew[1] * snew[1] + snew[2] * snew[2]) * rhoInv;
+        SrE = new_ke - old_ke;
+    }
+    src[UEDEN] = SrE;
+    const long oo = osrc.idx(i, j, k);
+#pragma unroll
+    for (int n = 0; n < 7; ++n) { src[n] = 0.0 + src[n]; osrc.at(oo, n) = src[n]; }
+    if (!vbx.contains(i, j, k)) return;
+    const long on = Sn.idx(i, j, k);
+    double u[7];
+#pragma unroll
+    for (int n = 0; n < 7; ++n) u[n] = Sb.at(ob, n) + dt * src[n];
+    for (int ip = 0; ip < P.npassive; ++ip) Sn.at(on, UFA + ip) = Sb.at(ob, UFA + ip);
+    clean_zone(P, u, Sn, on);
+#pragma unroll
+    for (int n = 0; n < 7; ++n) Sn.at(on, n) = u[n];
+}
+
+struct GravNewArgs {
+    A4 mflux[3];                 // dt*A*F(rho) on the faces (grav_source_type 4 only)
+    unsigned long long* dtmin;   // [0] after the clean_state of do_new_sources, [1] after post_timestep's
+    double const_grav;
+    int gst;
+};
+
+__global__ void __launch_bounds__(TPB) k_grav_new(const DevPar P, const A4 Sb, const A4 Sn, const GravNewArgs a, const LaunchBox lb, const double dt) {
+    int i, j, k;
+    const bool active = thread_zone(lb, i, j, k);
+    double dt0 = DT_HUGE, dt1 = DT_HUGE;
+    if (active) {
+        const long ob = Sb.idx(i, j, k), on = Sn.idx(i, j, k);
+        const double vol = P.dx[0] * P.dx[1] * P.dx[2];
+        const double gold[3] = {0.0, 0.0, a.const_grav}, gnew[3] = {0.0, 0.0, a.const_grav};
+        double src[7] = {0, 0, 0, 0, 0, 0, 0};
+        double u[7];
+#pragma unroll
+        for (int n = 0; n < 7; ++n) u[n] = Sn.at(on, n);
+        const double hdtInv = 0.5 / dt;
+        const double rhoo = Sb.at(ob, URHO);
+        const double rhooinv = 1.0 / rhoo;
+        const double rhon = u[URHO];
+        const double rhoninv = 1.0 / rhon;
+        double snew[3] = {u[UMX], u[UMY], u[UMZ]};
+        const double old_ke = 0.5 * (snew[0] * snew[0] + snew[1] * snew[1] + snew[2] * snew[2]) * rhoninv;
+        double vold[3], Sr_old[3], vnew[3], Sr_new[3], Srcorr[3];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) vold[n] = Sb.at(ob, UMX + n) * rhooinv;
+#pragma unroll
+        for (int n = 0; n < 3; ++n) Sr_old[n] = rhoo * gold[n];
+        const double SrE_old = vold[0] * Sr_old[0] + vold[1] * Sr_old[1] + vold[2] * Sr_old[2];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) vnew[n] = snew[n] * rhoninv;
+#pragma unroll
+        for (int n = 0; n < 3; ++n) Sr_new[n] = rhon * gnew[n];
+        double SrE_new = vnew[0] * Sr_new[0] + vnew[1] * Sr_new[1] + vnew[2] * Sr_new[2];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) Srcorr[n] = 0.5 * (Sr_new[n] - Sr_old[n]);
+#pragma unroll
+        for (int n = 0; n < 3; ++n) { src[UMX + n] = Srcorr[n]; snew[n] += dt * src[UMX + n]; }
+        double SrEcorr = 0.0;
+        if (a.gst == 1) {
+            SrEcorr = 0.5 * (SrE_new - SrE_old);
+        } else if (a.gst == 2) {
+#pragma unroll
+            for (int n = 0; n < 3; ++n) vnew[n] = snew[n] * rhoninv;
+            SrE_new = vnew[0] * Sr_new[0] + vnew[1] * Sr_new[1] + vnew[2] * Sr_new[2];
+            SrEcorr = 0.5 * (SrE_new - SrE_old);
+        } else if (a.gst == 3) {
+            const double new_ke = 0.5 * (snew[0] * snew[0] + snew[1] * snew[1] + snew[2] * snew[2]) * rhoninv;
+            SrEcorr = new_ke - old_ke;
+        } else if (a.gst == 4) {
+            SrEcorr = -SrE_old;
+            double g[3];
+#pragma unroll
+            for (int n = 0; n < 3; ++n) g[n] = 0.5 * (gnew[n] + gold[n]);
+            // the gravity of the neighbouring zones is the same constant vector
+            const double gxl = 0.5 * (g[0] + 0.5 * (gnew[0] + gold[0])), gxr = 0.5 * (g[0] + 0.5 * (gnew[0] + gold[0]));
+            const double gyl = 0.5 * (g[1] + 0.5 * (gnew[1] + gold[1])), gyr = 0.5 * (g[1] + 0.5 * (gnew[1] + gold[1]));
+            const double gzl = 0.5 * (g[2] + 0.5 * (gnew[2] + gold[2])), gzr = 0.5 * (g[2] + 0.5 * (gnew[2] + gold[2]));
+            const A4& m0 = a.mflux[0]; const A4& m1 = a.mflux[1]; const A4& m2 = a.mflux[2];
+            SrEcorr += hdtInv * (m0(i, j, k, 0) * gxl * P.dx[0] + m0(i + 1, j, k, 0) * gxr * P.dx[0] +
+                                 m1(i, j, k, 0) * gyl * P.dx[1] + m1(i, j + 1, k, 0) * gyr * P.dx[1] +
+                                 m2(i, j, k, 0) * gzl * P.dx[2] + m2(i, j, k + 1, 0) * gzr * P.dx[2]) / vol;
+        }
+        src[UEDEN] = SrEcorr;
+#pragma unroll
+        for (int n = 0; n < 7; ++n) u[n] += dt * (0.0 + src[n]);
+        clean_zone(P, u, Sn, on);
+        dt0 = estdt_zone(P, u, Sn, on);
+        clean_zone(P, u, Sn, on);
+        dt1 = estdt_zone(P, u, Sn, on);
+#pragma unroll
+        for (int n = 0; n < 7; ++n) Sn.at(on, n) = u[n];
+    }
+    block_min_atomic(dt0, a.dtmin + 0);
+    block_min_atomic(dt1, a.dtmin + 1);
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -392,6 +528,10 @@ struct ctu_sim {
     cudaStream_t st = 0;
     int step = 0;
     int launches = 0;     // kernels launched by the sim itself (clean / fill / init), on top of the workspace's count
+    // constant gravity (par.do_grav): old-time source on grow(valid, NUM_GROW_SRC), mass fluxes for grav_source_type 4, dt reduction
+    double* osrc = nullptr;
+    double* mflux[3] = {nullptr, nullptr, nullptr};
+    unsigned long long* d_dt2 = nullptr;
     // host-streaming step (ctu_sim_step_host): copy streams, double-buffered staging, hand-over events
     cudaStream_t s_up = nullptr, s_dn = nullptr;
     double* stage_up[2] = {nullptr, nullptr};
@@ -546,6 +686,7 @@ int ctu_parse_inputs(const char* path, const char* overrides, ctu_params_t* par,
     gi("castro.check_dt_before_advance", par->check_dt_before_advance); gi("castro.check_dt_after_advance", par->check_dt_after_advance);
     gd("eos.eos_gamma", par->eos_gamma); gi("eos.eos_assume_neutral", par->eos_assume_neutral);
     gd("network.small_x", par->small_x);
+    gi("castro.do_grav", par->do_grav); gi("castro.grav_source_type", par->grav_source_type); gd("gravity.const_grav", par->const_grav);
     int nc[3] = {32, 32, 32};
     gi3("amr.n_cell", nc);
     double plo[3] = {0, 0, 0}, phi[3] = {1, 1, 1};
@@ -594,6 +735,18 @@ int ctu_sim_create(ctu_sim_t** out, const ctu_params_t* par, const ctu_geom_t* g
     }
     rc = ctu_workspace_create(&s->ws, workspace_bytes);
     if (rc) { ctu_sim_destroy(s); return rc; }
+    if (par->do_grav) {
+        if (par->grav_source_type < 1 || par->grav_source_type > 4) { ctu_sim_destroy(s); return CTU_ERR_UNSUPPORTED; }
+        const Box3 sbx = grow(s->vbx, CTU_NGROW_SRC);
+        bool ok = cudaMalloc(&s->osrc, (size_t)sbx.npts() * 7 * sizeof(double)) == cudaSuccess &&
+                  cudaMalloc(&s->d_dt2, 2 * sizeof(unsigned long long)) == cudaSuccess;
+        for (int d = 0; d < 3 && ok; ++d) {
+            Box3 nb = s->vbx; nb.hi[d] += 1;
+            ok = cudaMalloc(&s->mflux[d], (size_t)nb.npts() * sizeof(double)) == cudaSuccess;
+        }
+        if (!ok) { cudaGetLastError(); ctu_sim_destroy(s); return CTU_ERR_NOMEM; }
+        cudaMemsetAsync(s->osrc, 0, (size_t)sbx.npts() * 7 * sizeof(double), s->st);
+    }
     *out = s;
     return 0;
 }
@@ -611,6 +764,9 @@ void ctu_sim_destroy(ctu_sim_t* s) {
     if (s->s_up) cudaStreamDestroy(s->s_up);
     if (s->s_dn) cudaStreamDestroy(s->s_dn);
     for (int b = 0; b < 2; ++b) if (s->buf[b]) cudaFree(s->buf[b]);
+    if (s->osrc) cudaFree(s->osrc);
+    if (s->d_dt2) cudaFree(s->d_dt2);
+    for (int d = 0; d < 3; ++d) if (s->mflux[d]) cudaFree(s->mflux[d]);
     if (s->ws) ctu_workspace_destroy(s->ws);
     delete s;
 }
@@ -670,9 +826,59 @@ int ctu_sim_step_fill(ctu_sim_t* s) {
     return ctu_clean_state(&s->par, s->gbx.lo, s->gbx.hi, &f, 1, s->st);
 }
 
+// the same step with gravitational source terms around the hydro (Castro::do_advance_ctu, Castro_advance_ctu.cpp:60-130):
+// do_old_sources -> construct_ctu_hydro_source (sources traced) + clean_state -> do_new_sources + clean_state -> post_timestep
+static int sim_step_hydro_grav(ctu_sim_t* s, double dt, double dt_est[2], int n_bad[2]) {
+    const ctu_params_t& par = s->par;
+    const DevPar P = make_devpar(&s->par, &s->geom);
+    ctu_fab_t sb = s->fab(s->cur), sn = s->fab(1 - s->cur);
+    const A4 Sb = make_a4(sb), Sn = make_a4(sn);
+    const Box3 sbx = grow(s->vbx, CTU_NGROW_SRC);
+    ctu_fab_t fo;
+    fo.p = s->osrc; fo.ncomp = 7;
+    for (int d = 0; d < 3; ++d) { fo.lo[d] = sbx.lo[d]; fo.hi[d] = sbx.hi[d]; }
+    const A4 osrc = make_a4(fo);
+    {   LaunchBox lb = make_lb(sbx);
+        k_grav_old<<<nblk(lb.n), TPB, 0, s->st>>>(P, Sb, Sn, osrc, lb, s->vbx, par.const_grav, par.grav_source_type, dt);
+        DevPar P7 = P;
+        P7.nstate = 7;          // the source has NSRC components and the state's boundary types (Castro_setup.cpp: Source_Type)
+        k_fill<1><<<nblk(lb.n), TPB, 0, s->st>>>(P7, osrc, lb, s->vbx);
+        s->launches += 2;
+        CUDA_TRY(cudaGetLastError()); }
+    ctu_fab_t mf[3];
+    ctu_fab_t* mfp[3] = {nullptr, nullptr, nullptr};
+    GravNewArgs ga;
+    std::memset(&ga, 0, sizeof(ga));
+    if (par.grav_source_type == 4) {
+        for (int d = 0; d < 3; ++d) {
+            mf[d].p = s->mflux[d]; mf[d].ncomp = 1;
+            for (int e = 0; e < 3; ++e) { mf[d].lo[e] = s->vbx.lo[e]; mf[d].hi[e] = s->vbx.hi[e] + (e == d ? 1 : 0); }
+            mfp[d] = &mf[d];
+            ga.mflux[d] = make_a4(mf[d]);
+        }
+    }
+    int rc = ctu_hydro_advance(s->ws, &s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, &fo, nullptr, &sn, nullptr,
+                               par.grav_source_type == 4 ? mfp : nullptr, dt, 1, nullptr, nullptr, n_bad, s->st);
+    if (rc != 0) return rc;
+    const unsigned long long init[2] = {0x7fefffffffffffffull, 0x7fefffffffffffffull};
+    CUDA_TRY(cudaMemcpyAsync(s->d_dt2, init, sizeof(init), cudaMemcpyHostToDevice, s->st));
+    ga.dtmin = s->d_dt2; ga.const_grav = par.const_grav; ga.gst = par.grav_source_type;
+    {   LaunchBox lb = make_lb(s->vbx);
+        k_grav_new<<<nblk(lb.n), TPB, 0, s->st>>>(P, Sb, Sn, ga, lb, dt);
+        s->launches += 1;
+        CUDA_TRY(cudaGetLastError()); }
+    unsigned long long h[2];
+    CUDA_TRY(cudaMemcpyAsync(h, s->d_dt2, sizeof(h), cudaMemcpyDeviceToHost, s->st));
+    CUDA_TRY(cudaStreamSynchronize(s->st));
+    if (dt_est) { std::memcpy(&dt_est[0], &h[0], sizeof(double)); std::memcpy(&dt_est[1], &h[1], sizeof(double)); }
+    s->cur = 1 - s->cur; s->step++;
+    return 0;
+}
+
 // construct_ctu_hydro_source + its clean_state + post_timestep's clean_state, with both dt estimates
 int ctu_sim_step_hydro(ctu_sim_t* s, double dt, double dt_est[2], int n_bad[2]) {
     if (!s) return CTU_ERR_BAD_ARG;
+    if (s->par.do_grav) return sim_step_hydro_grav(s, dt, dt_est, n_bad);
     ctu_fab_t sb = s->fab(s->cur), sn = s->fab(1 - s->cur);
     int rc = ctu_hydro_advance(s->ws, &s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, nullptr, nullptr, &sn, nullptr, nullptr, dt,
                                2 | CTU_ADV_SNEW_FROM_SBORDER, dt_est, nullptr, n_bad, s->st);
@@ -749,6 +955,7 @@ int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, dou
     if (!s || !host_in || !host_out) return CTU_ERR_BAD_ARG;
     for (int d = 0; d < 3; ++d)
         if (s->vbx.lo[d] != s->geom.domlo[d] || s->vbx.hi[d] != s->geom.domhi[d]) return CTU_ERR_UNSUPPORTED;
+    if (s->par.do_grav) return CTU_ERR_UNSUPPORTED;     // the streamed step covers pure hydro only
     const int nz = s->vbx.hi[2] - s->vbx.lo[2] + 1;
     const int zlo = s->vbx.lo[2], zhi = s->vbx.hi[2];
     ctu_fab_t sb = s->fab(s->cur), sn = s->fab(1 - s->cur);

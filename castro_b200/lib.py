@@ -165,8 +165,11 @@ class Workspace:
 
 
 def hydro_advance(ws, par, geom, vlo, vhi, Sborder, sb_lo, S_new, sn_lo, dt, n_clean=1, from_sborder=False, fluxes=None,
-                  flux_los=None, mass_fluxes=None, mass_los=None, want_loc=False, stream=0):
-    """Sborder, S_new, fluxes: torch CUDA tensors [ncomp, nz, ny, nx].  Returns (status, dt_est[2], loc, n_bad)."""
+                  flux_los=None, mass_fluxes=None, mass_los=None, want_loc=False, stream=0, old_src=None, src_corr=None, src_lo=None):
+    """Sborder, S_new, fluxes: torch CUDA tensors [ncomp, nz, ny, nx].  old_src / src_corr: optional NSRC = 7 component
+    tensors on grow(valid, 3) with low corner src_lo.  Returns (status, dt_est[2], loc, n_bad)."""
+    fos = tensor_fab(old_src, src_lo) if old_src is not None else None
+    fsc = tensor_fab(src_corr, src_lo) if src_corr is not None else None
     fb = tensor_fab(Sborder, sb_lo)
     fn = tensor_fab(S_new, sn_lo)
     est = (C.c_double * 2)()
@@ -186,7 +189,8 @@ def hydro_advance(ws, par, geom, vlo, vhi, Sborder, sb_lo, S_new, sn_lo, dt, n_c
         return C.cast(arr, C.c_void_p)
 
     flags = (n_clean & 3) | (4 if from_sborder else 0)
-    rc = lib().ctu_hydro_advance(ws.h, C.byref(par), C.byref(geom), abi.Int3(*vlo), abi.Int3(*vhi), C.byref(fb), None, None,
+    rc = lib().ctu_hydro_advance(ws.h, C.byref(par), C.byref(geom), abi.Int3(*vlo), abi.Int3(*vhi), C.byref(fb),
+                                 C.byref(fos) if fos is not None else None, C.byref(fsc) if fsc is not None else None,
                                  C.byref(fn), mk(fluxes, flux_los), mk(mass_fluxes, mass_los), dt, flags, est,
                                  loc if want_loc else None, nbad, stream)
     check(rc, "ctu_hydro_advance")

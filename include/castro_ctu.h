@@ -143,8 +143,10 @@ size_t ctu_workspace_bytes(const ctu_workspace_t* ws);     /* bytes currently al
  *     clean_state(S_new) again   (Castro::post_timestep, Castro.cpp:2043-2050) if (flags & 3) == 2
  *     estdt<hydro>(S_new)        after the first and after the last clean (Castro_advance.cpp:298, Castro.cpp:1775)
  * Inputs  Sborder : NUM_STATE comps, must cover grow(valid, 4), already ghost-filled + clean_state'd
- *         old_src, src_corr : NSRC=7 comps covering grow(valid,3), or NULL (== all zero, pure hydro);
- *                   non-NULL is not implemented yet (returns CTU_ERR_UNSUPPORTED)
+ *         old_src, src_corr : NSRC=7 comps covering grow(valid,3), or NULL (== all zero, pure hydro).  old_src is the
+ *                   old-time conserved source (get_old_data(Source_Type)), converted by hydro::src_to_prim
+ *                   (advection_util.H:16-79) and traced with the states (trace_ppm.cpp:309-440); src_corr is the
+ *                   source corrector used when castro.source_term_predictor = 1 (requires old_src)
  * In/out  S_new   : NUM_STATE comps covering valid; on entry holds Sborder's valid data (+ dt*old_src),
  *                   exactly like the reference, unless CTU_ADV_SNEW_FROM_SBORDER is set.  Must not alias Sborder.
  * Outputs flux[d] : optional (NULL allowed) nodal-in-d, NUM_STATE comps, `+=` dt*A*F  (Castro_ctu_hydro.cpp:1297)

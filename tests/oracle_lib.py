@@ -60,7 +60,10 @@ def run(par, geom, U, nsteps, stop_time=-1.0, time=0.0, dt=-1.0, ng=abi.CTU_NGRO
     return st, t.value, d.value, np.array(hist[:done.value])
 
 
-def hydro_advance(par, geom, vlo, vhi, Sborder, sb_lo, S_new, sn_lo, dt, do_clean=1, fluxes=None, flux_los=None):
+def hydro_advance(par, geom, vlo, vhi, Sborder, sb_lo, S_new, sn_lo, dt, do_clean=1, fluxes=None, flux_los=None, old_src=None,
+                  src_corr=None, src_lo=None, mass_fluxes=None, mass_los=None):
+    fos = fab(old_src, src_lo) if old_src is not None else None
+    fsc = fab(src_corr, src_lo) if src_corr is not None else None
     fb = fab(Sborder, sb_lo)
     fn = fab(S_new, sn_lo)
     dt_est = C.c_double(0)
@@ -75,8 +78,16 @@ def hydro_advance(par, geom, vlo, vhi, Sborder, sb_lo, S_new, sn_lo, dt, do_clea
             ff = fab(fluxes[d], flux_los[d])
             keep.append(ff)
             fl[d] = C.pointer(ff)
-    st = lib().orc_hydro_advance(C.byref(par), C.byref(geom), abi.Int3(*vlo), abi.Int3(*vhi), C.byref(fb), None, None,
-                                 C.byref(fn), fl, None, C.c_double(dt), C.c_int(do_clean), C.byref(dt_est), loc, nbad)
+    ml = None
+    if mass_fluxes is not None:
+        ml = FabP3()
+        for d in range(3):
+            ff = fab(mass_fluxes[d], mass_los[d])
+            keep.append(ff)
+            ml[d] = C.pointer(ff)
+    st = lib().orc_hydro_advance(C.byref(par), C.byref(geom), abi.Int3(*vlo), abi.Int3(*vhi), C.byref(fb),
+                                 C.byref(fos) if fos is not None else None, C.byref(fsc) if fsc is not None else None,
+                                 C.byref(fn), fl, ml, C.c_double(dt), C.c_int(do_clean), C.byref(dt_est), loc, nbad)
     return st, dt_est.value, tuple(loc), tuple(nbad)
 
 
