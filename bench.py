@@ -212,6 +212,7 @@ def gpu_arm(args):
     lib.workspace_set_profiling(ws, True)
     lib.workspace_stage_times(ws, reset=True)
     l0 = eng.launches + sim.exchange_launches
+    r0 = lib.workspace_replays(ws)
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -223,6 +224,7 @@ def gpu_arm(args):
     assert st == 0 and len(hist) == args.steps, "timed steps failed with status %d" % st
     ms = e0.elapsed_time(e1)
     launches = eng.launches + sim.exchange_launches - l0
+    replays = lib.workspace_replays(ws) - r0
     stages = lib.workspace_stage_times(ws, reset=True)
     lib.workspace_set_profiling(ws, False)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -308,6 +310,7 @@ def gpu_arm(args):
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "mode": e2e_mode},
             "gpu_launches": launches, "clocks": clk,
             "halo_bytes_per_step_per_gpu": sim.halo_bytes_per_step,
+            "exact_replay_tiles_per_step": replays / args.steps,
         }
         print(json.dumps(line), flush=True)
     sim.close()

@@ -27,10 +27,11 @@ struct ctu_workspace {
     size_t arena_bytes = 0;
     size_t max_bytes = 0;
     unsigned long long* d_dtmin = nullptr;   // 2 entries + 1 for location
-    int* d_counters = nullptr;               // 4 entries
+    int* d_counters = nullptr;               // 8 entries: bad rho, bad X, invalid X, NaN, tiles replayed with exact division, -
     unsigned long long* h_dtmin = nullptr;   // pinned
     int* h_counters = nullptr;               // pinned
     int last_slab_planes = 0;
+    long replays_total = 0;                  // tiles replayed with the exact operators since creation (diagnostic)
     int last_num_slabs = 0;
     int kernel_launches = 0;
     // optional per-stage device timing (CUDA events on the launching stream)
@@ -332,9 +333,9 @@ int ctu_workspace_create(ctu_workspace_t** ws, size_t max_bytes) {
     ctu_workspace* w = new ctu_workspace();
     w->max_bytes = max_bytes ? max_bytes : ((size_t)32 << 30);
     CUDA_TRY(cudaMalloc(&w->d_dtmin, 4 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMalloc(&w->d_counters, 4 * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&w->d_counters, 8 * sizeof(int)));
     CUDA_TRY(cudaMallocHost(&w->h_dtmin, 4 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMallocHost(&w->h_counters, 4 * sizeof(int)));
+    CUDA_TRY(cudaMallocHost(&w->h_counters, 8 * sizeof(int)));
     *ws = w;
     return 0;
 }
@@ -352,6 +353,7 @@ void ctu_workspace_destroy(ctu_workspace_t* w) {
 
 size_t ctu_workspace_bytes(const ctu_workspace_t* w) { return w ? w->arena_bytes : 0; }
 int ctu_workspace_last_slabs(const ctu_workspace_t* w) { return w ? w->last_num_slabs : 0; }
+long ctu_workspace_replays(const ctu_workspace_t* w) { return w ? w->replays_total : 0; }
 int ctu_workspace_launches(const ctu_workspace_t* w) { return w ? w->kernel_launches : 0; }
 
 int ctu_workspace_set_profiling(ctu_workspace_t* w, int on) {
@@ -417,6 +419,7 @@ HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     if (rc) { *rc_out = rc; return nullptr; }
     HydroRun* r = new HydroRun(ws, st);
     r->P = make_devpar(par, geom);
+    r->P.replays = ws->d_counters + 4;
     const DevPar& P = r->P;
     r->P_predictor = par->source_term_predictor;
     r->np = P.npassive;
@@ -453,7 +456,7 @@ HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     r->Sb = make_a4(*Sborder); r->Sn = make_a4(*S_new);
     unsigned long long init[4] = {0x7fefffffffffffffull, 0x7fefffffffffffffull, 0xffffffffffffffffull, 0};
     if (cudaMemcpyAsync(ws->d_dtmin, init, sizeof(init), cudaMemcpyHostToDevice, st) != cudaSuccess ||
-        cudaMemsetAsync(ws->d_counters, 0, 4 * sizeof(int), st) != cudaSuccess) {
+        cudaMemsetAsync(ws->d_counters, 0, 8 * sizeof(int), st) != cudaSuccess) {
         delete r; *rc_out = CTU_ERR_CUDA; return nullptr;
     }
     return r;
@@ -632,13 +635,14 @@ int hydro_end(HydroRun* r, double dt_est[2], int dt_loc[3], int n_bad[2]) {
     ws->kernel_launches += r->launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(ws->h_dtmin, ws->d_dtmin, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(ws->h_counters, ws->d_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->h_counters, ws->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     r->tm.fold();
     int status = 0;
     if (ws->h_counters[0]) status |= CTU_STATUS_INVALID_DENSITY;
     if (ws->h_counters[1]) status |= CTU_STATUS_INVALID_X;
     if (ws->h_counters[3]) status |= CTU_STATUS_NAN;
+    ws->replays_total += ws->h_counters[4];
     if (n_bad) { n_bad[0] = ws->h_counters[0]; n_bad[1] = ws->h_counters[1]; }
     if (dt_est) {
         std::memcpy(&dt_est[0], &ws->h_dtmin[0], sizeof(double));

@@ -419,10 +419,10 @@ __device__ __forceinline__ void solve_face(const DevPar& P, const double* qm, co
     double bnd_fac = 1.0;
     if ((idx == P.domlo[DIR] && sp_lo) || (idx == P.domhi[DIR] + 1 && sp_hi)) bnd_fac = 0.0;
     if (P.riemann_solver == 0) {
-        riemann_cgf<DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac,
+        riemann_cgf<MathExact, DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac,
                          [&](int n) { return xm(P.QFS_off + n); }, [&](int n) { return xp(P.QFS_off + n); }, F, ugd, pgd, pu);
     } else {
-        riemann_hllc<DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, F, ugd, pgd, pu);
+        riemann_hllc<MathExact, DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, F, ugd, pgd, pu);
     }
 }
 
@@ -498,7 +498,7 @@ static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, co
         reset_m = trans_reset(P, q[IS_RHO], rrnew_m, [&](int ip) { return qm.at(o, IS_X + ip); },
                               [&](int ip, double c0) { return c0 - cdtdx * (Ft.at(ofm + sT_f, FX_X + ip) - Ft.at(ofm, FX_X + ip)); });
         const double gamc = P.gamc_const ? P.gamma : qs.at(oqm, QS_GAMC);
-        trans_single_hydro(P, q, qlo, fl, fr, Ft.at(ofm, FX_UG), Ft.at(ofm + sT_f, FX_UG), Ft.at(ofm, FX_PG), Ft.at(ofm + sT_f, FX_PG),
+        trans_single_hydro<MathExact>(P, q, qlo, fl, fr, Ft.at(ofm, FX_UG), Ft.at(ofm + sT_f, FX_UG), Ft.at(ofm, FX_PG), Ft.at(ofm + sT_f, FX_PG),
                            gamc, cdtdx, rrnew_m, reset_m);
     }
     {   // plus state: zone (face)
@@ -510,7 +510,7 @@ static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, co
         reset_p = trans_reset(P, q[IS_RHO], rrnew_p, [&](int ip) { return qp.at(o, IS_X + ip); },
                               [&](int ip, double c0) { return c0 - cdtdx * (Ft.at(ofp + sT_f, FX_X + ip) - Ft.at(ofp, FX_X + ip)); });
         const double gamc = P.gamc_const ? P.gamma : qs.at(oqp, QS_GAMC);
-        trans_single_hydro(P, q, qro, fl, fr, Ft.at(ofp, FX_UG), Ft.at(ofp + sT_f, FX_UG), Ft.at(ofp, FX_PG), Ft.at(ofp + sT_f, FX_PG),
+        trans_single_hydro<MathExact>(P, q, qro, fl, fr, Ft.at(ofp, FX_UG), Ft.at(ofp + sT_f, FX_UG), Ft.at(ofp, FX_PG), Ft.at(ofp + sT_f, FX_PG),
                            gamc, cdtdx, rrnew_p, reset_p);
     }
     // corrected passives, recomputed on demand (they are never stored)
@@ -568,7 +568,7 @@ static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 q
                                          c2 * (F2.at(ofm + s2_f, FX_X + ip) - F2.at(ofm, FX_X + ip));
                               });
         const double gamc = P.gamc_const ? P.gamma : qs.at(oqm, QS_GAMC);
-        trans_final_hydro(P, q, qlo, f1l, f1r, f2l, f2r, F1.at(ofm, FX_UG), F1.at(ofm + s1_f, FX_UG), F1.at(ofm, FX_PG),
+        trans_final_hydro<MathExact>(P, q, qlo, f1l, f1r, f2l, f2r, F1.at(ofm, FX_UG), F1.at(ofm + s1_f, FX_UG), F1.at(ofm, FX_PG),
                           F1.at(ofm + s1_f, FX_PG), F2.at(ofm, FX_UG), F2.at(ofm + s2_f, FX_UG), F2.at(ofm, FX_PG),
                           F2.at(ofm + s2_f, FX_PG), gamc, c1, c2, rrnew_m, reset_m);
     }
@@ -584,7 +584,7 @@ static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 q
                                          c2 * (F2.at(ofp + s2_f, FX_X + ip) - F2.at(ofp, FX_X + ip));
                               });
         const double gamc = P.gamc_const ? P.gamma : qs.at(oqp, QS_GAMC);
-        trans_final_hydro(P, q, qro, f1l, f1r, f2l, f2r, F1.at(ofp, FX_UG), F1.at(ofp + s1_f, FX_UG), F1.at(ofp, FX_PG),
+        trans_final_hydro<MathExact>(P, q, qro, f1l, f1r, f2l, f2r, F1.at(ofp, FX_UG), F1.at(ofp + s1_f, FX_UG), F1.at(ofp, FX_PG),
                           F1.at(ofp + s1_f, FX_PG), F2.at(ofp, FX_UG), F2.at(ofp + s2_f, FX_UG), F2.at(ofp, FX_PG),
                           F2.at(ofp + s2_f, FX_PG), gamc, c1, c2, rrnew_p, reset_p);
     }

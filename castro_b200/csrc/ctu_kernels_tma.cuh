@@ -18,7 +18,7 @@
 namespace ctu {
 
 #ifndef CTU_TRACE_MINB
-#define CTU_TRACE_MINB 2
+#define CTU_TRACE_MINB 3
 #endif
 #ifndef CTU_TMA_MINB
 #define CTU_TMA_MINB 2
@@ -95,7 +95,7 @@ template <int NP>
 __device__ __forceinline__ bool is_species(const DevPar& P, int ip) { return ip >= P.QFS_off && ip < P.QFS_off + P.nspec; }
 
 // Riemann solve on register states with register passives (Castro::cmpflx_plus_godunov, riemann.cpp:15-200)
-template <int DIR, int NP>
+template <class M, int DIR, int NP>
 __device__ __forceinline__ void solve_face_r(const DevPar& P, const double* ql, const double* qr, const double* xl, const double* xr,
                                              double cl, double cr, int idx, double* F, double& ugd, double& pgd, double* FX) {
     const bool sp_lo = P.lo_bc[DIR] >= 3 && P.lo_bc[DIR] <= 5, sp_hi = P.hi_bc[DIR] >= 3 && P.hi_bc[DIR] <= 5;
@@ -109,19 +109,19 @@ __device__ __forceinline__ void solve_face_r(const DevPar& P, const double* ql, 
             for (int ip = 0; ip < NP; ++ip) if (ip == P.QFS_off + n) r = x[ip];
             return r;
         };
-        riemann_cgf<DIR>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, [&](int n) { return sel(xl, n); }, [&](int n) { return sel(xr, n); },
+        riemann_cgf<M, DIR>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, [&](int n) { return sel(xl, n); }, [&](int n) { return sel(xr, n); },
                          F, ugd, pgd, pu);
 #pragma unroll
         for (int ip = 0; ip < NP; ++ip) FX[ip] = passive_flux_cgf(pu, xl[ip], xr[ip]);
     } else {
-        riemann_hllc<DIR>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, F, ugd, pgd, pu);
+        riemann_hllc<M, DIR>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, F, ugd, pgd, pu);
 #pragma unroll
         for (int ip = 0; ip < NP; ++ip) FX[ip] = passive_flux_hllc(pu, xl[ip], xr[ip]);
     }
 }
 
 // actual_trans_single for one state (trans.cpp:67-498): zone at tile offset oz of the T-flux tile sF
-template <int NP, class FT, int ST>
+template <class M, int NP, class FT, int ST>
 __device__ __forceinline__ void trans_single_side(const DevPar& P, const FT& sF, int oz, const double* q, const double* x, double cdt,
                                                   double* qo, double* xo) {
     double fl[6], fr[6], dX[NP];
@@ -136,16 +136,16 @@ __device__ __forceinline__ void trans_single_side(const DevPar& P, const FT& sF,
     double xn[NP];
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) {
-        xn[ip] = (rho * x[ip] - dX[ip]) / rrnew;
+        xn[ip] = M::div(rho * x[ip] - dX[ip], rrnew);
         if (is_species<NP>(P, ip) && (xn[ip] > 1.0 + P.abundance_failure_tolerance || xn[ip] < -P.abundance_failure_tolerance)) reset = true;
     }
-    trans_single_hydro(P, q, qo, fl, fr, ugm, ugp, pgm, pgp, P.gamma, cdt, rrnew, reset);
+    trans_single_hydro<M>(P, q, qo, fl, fr, ugm, ugp, pgm, pgp, P.gamma, cdt, rrnew, reset);
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) xo[ip] = reset ? x[ip] : xn[ip];
 }
 
 // actual_trans_final for one state (trans.cpp:559-968)
-template <int NP, class F1T, int S1, class F2T, int S2>
+template <class M, int NP, class F1T, int S1, class F2T, int S2>
 __device__ __forceinline__ void trans_final_side(const DevPar& P, const F1T& sF1, int o1, const F2T& sF2, int o2, const double* q,
                                                  const double* x, double c1, double c2, double* qo, double* xo) {
     double f1l[6], f1r[6], f2l[6], f2r[6];
@@ -157,10 +157,10 @@ __device__ __forceinline__ void trans_final_side(const DevPar& P, const F1T& sF1
     double xn[NP];
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) {
-        xn[ip] = (rho * x[ip] - c1 * (sF1(o1 + S1, FX_X + ip) - sF1(o1, FX_X + ip)) - c2 * (sF2(o2 + S2, FX_X + ip) - sF2(o2, FX_X + ip))) / rrnew;
+        xn[ip] = M::div(rho * x[ip] - c1 * (sF1(o1 + S1, FX_X + ip) - sF1(o1, FX_X + ip)) - c2 * (sF2(o2 + S2, FX_X + ip) - sF2(o2, FX_X + ip)), rrnew);
         if (is_species<NP>(P, ip) && (xn[ip] > 1.0 + P.abundance_failure_tolerance || xn[ip] < -P.abundance_failure_tolerance)) reset = true;
     }
-    trans_final_hydro(P, q, qo, f1l, f1r, f2l, f2r, sF1(o1, FX_UG), sF1(o1 + S1, FX_UG), sF1(o1, FX_PG), sF1(o1 + S1, FX_PG),
+    trans_final_hydro<M>(P, q, qo, f1l, f1r, f2l, f2r, sF1(o1, FX_UG), sF1(o1 + S1, FX_UG), sF1(o1, FX_PG), sF1(o1 + S1, FX_PG),
                       sF2(o2, FX_UG), sF2(o2 + S2, FX_UG), sF2(o2, FX_PG), sF2(o2 + S2, FX_PG), P.gamma, c1, c2, rrnew, reset);
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) xo[ip] = reset ? x[ip] : xn[ip];
@@ -192,48 +192,18 @@ struct Trans2Args {
     double cdt1, cdt2;
 };
 
-template <int N, int NP>
-static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
-k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
-             const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
-             const Trans2Args a, const TileGrid tg) {
+// the arithmetic of one face of the tile, on the staged operands (M = MathFast: speculative pass, MathExact: replay)
+template <class M, int N, int NP>
+__device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a, const unsigned char* smem, const TileCtx& c, const bool in1,
+                                            const bool in2, const int pf, const int pg, const int pq, const double* gql, const double* gqr,
+                                            const double* gxl, const double* gxr) {
     using L = Trans2Smem<N, NP>;
     constexpr int T1 = L::T1, T2 = L::T2;
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
-    const TileCtx c = tile_ctx(tg);
-    // x coordinates of the tile origins in their arrays and their parity shifts (see EXT)
-    const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
-    const int gi = fi - (N == 0), pg = gi & 1;
-    const int qi = c.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
-    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
-#if !CTU_Q_LDG
-        tma::load_4d(smem + L::O_QM, &m_qm, bar, fi - pf, fj, fk, 0);
-        tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
-#endif
-        tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
-        tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
-        tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
-    }
-    const bool in1 = a.b1.contains(c.i, c.j, c.k), in2 = a.b2.contains(c.i, c.j, c.k);
-    double ql[6], qr[6], xl[NP], xr[NP];
-#if CTU_Q_LDG
-    if (in1 || in2) {   // own face's states: plain global loads, in flight while the flux tiles land
-        const long oq = a.qm.idx(c.i, c.j, c.k);
-#pragma unroll
-        for (int n = 0; n < 6; ++n) { ql[n] = a.qm.at(oq, n); qr[n] = a.qp.at(oq, n); }
-#pragma unroll
-        for (int ip = 0; ip < NP; ++ip) { xl[ip] = a.qm.at(oq, IS_X + ip); xr[ip] = a.qp.at(oq, IS_X + ip); }
-    }
-#endif
-    tma::mbar_wait(bar, 0);
     if (!in1 && !in2) return;
     const typename L::F1T sF1{reinterpret_cast<const double*>(smem + L::O_F1)};
     const typename L::F2T sF2{reinterpret_cast<const double*>(smem + L::O_F2)};
     const typename L::CT sC{reinterpret_cast<const double*>(smem + L::O_C)};
+    double ql[6], qr[6], xl[NP], xr[NP];
 #if !CTU_Q_LDG
     const FaceTile sQM{reinterpret_cast<const double*>(smem + L::O_QM)}, sQP{reinterpret_cast<const double*>(smem + L::O_QP)};
     const int of = FaceTile::off(c.tx + pf, c.ty, c.tz);
@@ -241,6 +211,11 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
     for (int n = 0; n < 6; ++n) { ql[n] = sQM(of, n); qr[n] = sQP(of, n); }
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) { xl[ip] = sQM(of, IS_X + ip); xr[ip] = sQP(of, IS_X + ip); }
+#else
+#pragma unroll
+    for (int n = 0; n < 6; ++n) { ql[n] = gql[n]; qr[n] = gqr[n]; }
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) { xl[ip] = gxl[ip]; xr[ip] = gxr[ip]; }
 #endif
     const int oc = L::CT::off(c.tx + pq, c.ty, c.tz);
     const double cl = sC(oc, 0), cr = sC(oc + L::CT::stride(N), 0);
@@ -249,9 +224,9 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
         constexpr int sN = L::F1T::stride(N), sT = L::F1T::stride(T1);
         const int oz = L::F1T::off(c.tx + pg, c.ty, c.tz);
         double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
-        trans_single_side<NP, typename L::F1T, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
-        trans_single_side<NP, typename L::F1T, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
-        solve_face_r<N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+        trans_single_side<M, NP, typename L::F1T, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
+        trans_single_side<M, NP, typename L::F1T, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
+        solve_face_r<M, N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
         const long o = a.Fo1.idx(c.i, c.j, c.k);
 #pragma unroll
         for (int n = 0; n < 6; ++n) a.Fo1.at(o, n) = F[n];
@@ -264,9 +239,9 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
         constexpr int sN = L::F2T::stride(N), sT = L::F2T::stride(T2);
         const int oz = L::F2T::off(c.tx + pg, c.ty, c.tz);
         double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
-        trans_single_side<NP, typename L::F2T, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
-        trans_single_side<NP, typename L::F2T, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
-        solve_face_r<N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+        trans_single_side<M, NP, typename L::F2T, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
+        trans_single_side<M, NP, typename L::F2T, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
+        solve_face_r<M, N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
         const long o = a.Fo2.idx(c.i, c.j, c.k);
 #pragma unroll
         for (int n = 0; n < 6; ++n) a.Fo2.at(o, n) = F[n];
@@ -274,6 +249,61 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
         a.Fo2.at(o, FX_PG) = pgd;
 #pragma unroll
         for (int ip = 0; ip < NP; ++ip) a.Fo2.at(o, FX_X + ip) = FX[ip];
+    }
+}
+
+template <int N, int NP>
+static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
+k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
+             const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
+             const Trans2Args a, const TileGrid tg) {
+    using L = Trans2Smem<N, NP>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    const TileCtx c = tile_ctx(tg);
+    // x coordinates of the tile origins in their arrays and their parity shifts (see EXT)
+    const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
+    const int gi = fi - (N == 0), pg = gi & 1;
+    const int qi = c.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); ctu_div_unsafe = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
+#if !CTU_Q_LDG
+        tma::load_4d(smem + L::O_QM, &m_qm, bar, fi - pf, fj, fk, 0);
+        tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
+#endif
+        tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
+    }
+    const bool in1 = a.b1.contains(c.i, c.j, c.k), in2 = a.b2.contains(c.i, c.j, c.k);
+#if CTU_Q_LDG
+    double ql[6], qr[6], xl[NP], xr[NP];
+    if (in1 || in2) {   // own face's states: plain global loads, in flight while the flux tiles land
+        const long oq = a.qm.idx(c.i, c.j, c.k);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) { ql[n] = a.qm.at(oq, n); qr[n] = a.qp.at(oq, n); }
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) { xl[ip] = a.qm.at(oq, IS_X + ip); xr[ip] = a.qp.at(oq, IS_X + ip); }
+    }
+#endif
+    tma::mbar_wait(bar, 0);
+    // speculative pass with the branch-free division / sqrt sequences; exact replay of the tile if any thread met an operand
+    // outside their range (see MathFast in ctu_physics.cuh)
+#if CTU_Q_LDG
+    trans2_body<MathFast, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, ql, qr, xl, xr);
+#else
+    trans2_body<MathFast, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, nullptr, nullptr, nullptr, nullptr);
+#endif
+    __syncthreads();
+    if (ctu_div_unsafe) {
+        if (threadIdx.x == 0 && P.replays) atomicAdd(P.replays, 1);
+#if CTU_Q_LDG
+        trans2_body<MathExact, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, ql, qr, xl, xr);
+#else
+        trans2_body<MathExact, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, nullptr, nullptr, nullptr, nullptr);
+#endif
     }
 }
 
@@ -304,57 +334,18 @@ struct FinalArgs {
     double c1, c2;        // dt/(2 dx_T1), dt/(2 dx_T2)
 };
 
-template <int N, int NP>
-static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
-k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
-            const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
-            const __grid_constant__ CUtensorMap m_d, const FinalArgs a, const TileGrid tg) {
+template <class M, int N, int NP>
+__device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, const unsigned char* smem, const TileCtx& c, const bool active,
+                                           const int pf, const int pg, const int pq, const double* dU, const double* dUX, const double* gql,
+                                           const double* gqr, const double* gxl, const double* gxr) {
     using L = FinalSmem<N, NP>;
     constexpr int T1 = L::T1, T2 = L::T2;
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
-    const TileCtx c = tile_ctx(tg);
-    const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
-    const int gi = fi - (N == 0), pg = gi & 1;
-    const int qi = c.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
-    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
-#if !CTU_Q_LDG
-        tma::load_4d(smem + L::O_QM, &m_qm, bar, fi - pf, fj, fk, 0);
-        tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
-#endif
-        tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
-        tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
-        tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
-        tma::load_4d(smem + L::O_D, &m_d, bar, fi - pf, fj, fk, 1);
-    }
-    const bool active = c.i <= tg.hi0 && c.j <= tg.hi1 && c.k <= tg.hi2;
-    // conserved-state differences for the artificial viscosity: plain global loads, in flight while the tile lands
-    double dU[6], dUX[NP];
-    double ql[6], qr[6], xl[NP], xr[NP];
-    if (active) {
-#if CTU_Q_LDG
-        const long oq = a.qm.idx(c.i, c.j, c.k);
-#pragma unroll
-        for (int n = 0; n < 6; ++n) { ql[n] = a.qm.at(oq, n); qr[n] = a.qp.at(oq, n); }
-#pragma unroll
-        for (int ip = 0; ip < NP; ++ip) { xl[ip] = a.qm.at(oq, IS_X + ip); xr[ip] = a.qp.at(oq, IS_X + ip); }
-#endif
-        const long ou = a.U.idx(c.i, c.j, c.k);
-        const long oum = ou - ((N == 0) ? 1 : (N == 1) ? a.U.sj : a.U.sk);
-#pragma unroll
-        for (int n = 0; n < 6; ++n) dU[n] = a.U.at(ou, n) - a.U.at(oum, n);
-#pragma unroll
-        for (int ip = 0; ip < NP; ++ip) dUX[ip] = a.U.at(ou, UFA + ip) - a.U.at(oum, UFA + ip);
-    }
-    tma::mbar_wait(bar, 0);
     if (!active) return;
     const typename L::F1T sF1{reinterpret_cast<const double*>(smem + L::O_F1)};
     const typename L::F2T sF2{reinterpret_cast<const double*>(smem + L::O_F2)};
     const typename L::CT sC{reinterpret_cast<const double*>(smem + L::O_C)};
     const typename L::DT sD{reinterpret_cast<const double*>(smem + L::O_D)};
+    double ql[6], qr[6], xl[NP], xr[NP];
 #if !CTU_Q_LDG
     const FaceTile sQM{reinterpret_cast<const double*>(smem + L::O_QM)}, sQP{reinterpret_cast<const double*>(smem + L::O_QP)};
     const int of = FaceTile::off(c.tx + pf, c.ty, c.tz);
@@ -362,6 +353,11 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
     for (int n = 0; n < 6; ++n) { ql[n] = sQM(of, n); qr[n] = sQP(of, n); }
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) { xl[ip] = sQM(of, IS_X + ip); xr[ip] = sQP(of, IS_X + ip); }
+#else
+#pragma unroll
+    for (int n = 0; n < 6; ++n) { ql[n] = gql[n]; qr[n] = gqr[n]; }
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) { xl[ip] = gxl[ip]; xr[ip] = gxr[ip]; }
 #endif
     const int oc = L::CT::off(c.tx + pq, c.ty, c.tz);
     const double cl = sC(oc, 0), cr = sC(oc + L::CT::stride(N), 0);
@@ -369,9 +365,9 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
     constexpr int s1N = L::F1T::stride(N), s1T = L::F1T::stride(T1), s2N = L::F2T::stride(N), s2T = L::F2T::stride(T2);
     const int o1 = L::F1T::off(c.tx + pg, c.ty, c.tz), o2 = L::F2T::off(c.tx + pg, c.ty, c.tz);
     double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
-    trans_final_side<NP, typename L::F1T, s1T, typename L::F2T, s2T>(P, sF1, o1, sF2, o2, ql, xl, a.c1, a.c2, qlo, xlo);
-    trans_final_side<NP, typename L::F1T, s1T, typename L::F2T, s2T>(P, sF1, o1 + s1N, sF2, o2 + s2N, qr, xr, a.c1, a.c2, qro, xro);
-    solve_face_r<N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+    trans_final_side<M, NP, typename L::F1T, s1T, typename L::F2T, s2T>(P, sF1, o1, sF2, o2, ql, xl, a.c1, a.c2, qlo, xlo);
+    trans_final_side<M, NP, typename L::F1T, s1T, typename L::F2T, s2T>(P, sF1, o1 + s1N, sF2, o2 + s2N, qr, xr, a.c1, a.c2, qro, xro);
+    solve_face_r<M, N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
 
     // apply_av (advection_util.cpp:354-419): div1 = difmag * min(0, <div u> over the 4 nodes of the face)
     const int od = L::DT::off(c.tx + pf, c.ty, c.tz);
@@ -397,9 +393,81 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
         if (is_species<NP>(P, ip)) sum += FX[ip];
     }
     double fac = 1.0;
-    if (fabs(sum) > 2.220446049250313e-16 * fabs(F[0])) fac = F[0] / sum;
+    if (fabs(sum) > 2.220446049250313e-16 * fabs(F[0])) fac = M::div(F[0], sum);
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) a.Fo.at(o, FX_X + ip) = is_species<NP>(P, ip) ? FX[ip] * fac : FX[ip];
+}
+
+template <int N, int NP>
+static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
+k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
+            const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
+            const __grid_constant__ CUtensorMap m_d, const FinalArgs a, const TileGrid tg) {
+    using L = FinalSmem<N, NP>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    const TileCtx c = tile_ctx(tg);
+    const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
+    const int gi = fi - (N == 0), pg = gi & 1;
+    const int qi = c.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); ctu_div_unsafe = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
+#if !CTU_Q_LDG
+        tma::load_4d(smem + L::O_QM, &m_qm, bar, fi - pf, fj, fk, 0);
+        tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
+#endif
+        tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
+        tma::load_4d(smem + L::O_D, &m_d, bar, fi - pf, fj, fk, 1);
+    }
+    const bool active = c.i <= tg.hi0 && c.j <= tg.hi1 && c.k <= tg.hi2;
+    // conserved-state differences for the artificial viscosity: plain global loads, in flight while the tile lands
+    double dU[6], dUX[NP];
+#if CTU_Q_LDG
+    double ql[6], qr[6], xl[NP], xr[NP];
+#endif
+    if (active) {
+#if CTU_Q_LDG
+        const long oq = a.qm.idx(c.i, c.j, c.k);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) { ql[n] = a.qm.at(oq, n); qr[n] = a.qp.at(oq, n); }
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) { xl[ip] = a.qm.at(oq, IS_X + ip); xr[ip] = a.qp.at(oq, IS_X + ip); }
+#endif
+        const long ou = a.U.idx(c.i, c.j, c.k);
+        const long oum = ou - ((N == 0) ? 1 : (N == 1) ? a.U.sj : a.U.sk);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) dU[n] = a.U.at(ou, n) - a.U.at(oum, n);
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) dUX[ip] = a.U.at(ou, UFA + ip) - a.U.at(oum, UFA + ip);
+    }
+    tma::mbar_wait(bar, 0);
+    // speculative pass / exact replay, as in k_trans2_tma
+#if CTU_Q_LDG
+    final_body<MathFast, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, ql, qr, xl, xr);
+#else
+    final_body<MathFast, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, nullptr, nullptr, nullptr, nullptr);
+#endif
+    __syncthreads();
+    if (ctu_div_unsafe) {
+        if (threadIdx.x == 0 && P.replays) atomicAdd(P.replays, 1);
+        if (active) {
+            const long ou = a.U.idx(c.i, c.j, c.k);
+            const long oum = ou - ((N == 0) ? 1 : (N == 1) ? a.U.sj : a.U.sk);
+#pragma unroll
+            for (int n = 0; n < 6; ++n) dU[n] = a.U.at(ou, n) - a.U.at(oum, n);
+#pragma unroll
+            for (int ip = 0; ip < NP; ++ip) dUX[ip] = a.U.at(ou, UFA + ip) - a.U.at(oum, UFA + ip);
+        }
+#if CTU_Q_LDG
+        final_body<MathExact, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, ql, qr, xl, xr);
+#else
+        final_body<MathExact, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, nullptr, nullptr, nullptr, nullptr);
+#endif
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -576,7 +644,7 @@ struct TraceRiemannArgs {
 // ctu_kernels.cuh with the primitive stencil in shared memory and the results left in registers.
 //   base: &tile(zone, comp 0);  sn: component stride;  st: stride along DIR.   op/om: plus state on the low face, minus
 //   state on the high face (rho u v w p rhoe), xp/xm the passives.
-template <int DIR, int NP, bool SRC>
+template <class M, int DIR, int NP, bool SRC>
 __device__ __forceinline__ void trace_core(const DevPar& P, const double* __restrict__ base, const int sn, const int st, const double flat,
                                            const double dtdL, double* __restrict__ op, double* __restrict__ om, double* __restrict__ xp,
                                            double* __restrict__ xm, const SrcAdd& sa) {
@@ -642,11 +710,11 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
         double rhoe_g_ref = Im_re0 + SA(m_re0);
         double gam_g_ref = Im_gc0;
         rho_ref = smax(rho_ref, P.small_dens);
-        double rho_ref_inv = 1.0 / rho_ref;
+        double rho_ref_inv = M::rcp(rho_ref);
         p_ref = smax(p_ref, P.small_pres);
         double csq_ref = gam_g_ref * (0.0 + p_ref) * rho_ref_inv;
-        double cc_ref = sqrt(csq_ref);
-        double cc_ref_inv = 1.0 / cc_ref;
+        double cc_ref = M::sqrt(csq_ref);
+        double cc_ref_inv = M::rcp(cc_ref);
         double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
         double d_um = un_ref - Im_un0 - SA(m_un0);
         double dptotm = p_ref - Im_p0 - SA(m_p0);
@@ -657,8 +725,8 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
         double dptotp = p_ref - Im_p2 - SA(m_p2);
         double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
         double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
-        double alpha0r = drho - dptot / csq_ref;
-        double alpha0e_g = drhoe_g - dptot * h_g_ref / csq_ref;
+        double alpha0r = drho - M::div(dptot, csq_ref);
+        double alpha0e_g = drhoe_g - M::div(dptot * h_g_ref, csq_ref);
         alpham = un - cc > 0.0 ? 0.0 : -alpham;
         alphap = un + cc > 0.0 ? 0.0 : -alphap;
         alpha0r = un > 0.0 ? 0.0 : -alpha0r;
@@ -677,11 +745,11 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
         double rhoe_g_ref = Ip_re2 + SA(p_re2);
         double gam_g_ref = Ip_gc2;
         rho_ref = smax(rho_ref, P.small_dens);
-        double rho_ref_inv = 1.0 / rho_ref;
+        double rho_ref_inv = M::rcp(rho_ref);
         p_ref = smax(p_ref, P.small_pres);
         double csq_ref = gam_g_ref * (0.0 + p_ref) * rho_ref_inv;
-        double cc_ref = sqrt(csq_ref);
-        double cc_ref_inv = 1.0 / cc_ref;
+        double cc_ref = M::sqrt(csq_ref);
+        double cc_ref_inv = M::rcp(cc_ref);
         double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
         double d_um = un_ref - Ip_un0 - SA(p_un0);
         double dptotm = p_ref - Ip_p0 - SA(p_p0);
@@ -692,8 +760,8 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
         double dptotp = p_ref - Ip_p2 - SA(p_p2);
         double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
         double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
-        double alpha0r = drho - dptot / csq_ref;
-        double alpha0e_g = drhoe_g - dptot * h_g_ref / csq_ref;
+        double alpha0r = drho - M::div(dptot, csq_ref);
+        double alpha0e_g = drhoe_g - M::div(dptot * h_g_ref, csq_ref);
         alpham = un - cc > 0.0 ? -alpham : 0.0;
         alphap = un + cc > 0.0 ? -alphap : 0.0;
         alpha0r = un > 0.0 ? -alpha0r : 0.0;
@@ -708,36 +776,18 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
 #undef SA
 }
 
-template <int D, int NP, bool SRC>
-static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, CTU_TRACE_MINB)
-k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, const TraceRiemannArgs a) {
+// trace + first-pass Riemann solve of one zone of the tile on the staged primitives (M = MathFast: speculative pass, MathExact: replay)
+struct TraceCtx { int i, j, k, tx, ty, tz, dloc, btile, pq; bool active; };
+
+template <class M, int D, int NP, bool SRC>
+__device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceRiemannArgs& a, unsigned char* smem, const TraceCtx& c,
+                                                   const double flat) {
     using L = TraceSmem<D, NP>;
     using TT = TrTile<D>;
     using QT = typename L::QT;
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
     double* sEx = reinterpret_cast<double*>(smem + L::O_EX);
-    // tile and thread coordinates
-    const int bt = blockIdx.x;
-    const int bx = bt % a.ntx, r = bt / a.ntx, by = r % a.nty, bz = r / a.nty;
-    const int i0 = a.obx.lo[0] + bx * TT::SX, j0 = a.obx.lo[1] + by * TT::SY, k0 = a.obx.lo[2] + bz * TT::SZ;
-    const int tx = threadIdx.x % TT::NX, ty = (threadIdx.x / TT::NX) % TT::NY, tz = threadIdx.x / (TT::NX * TT::NY);
-    const int i = i0 + tx, j = j0 + ty, k = k0 + tz;
-    const int dloc = (D == 0) ? tx : (D == 1) ? ty : tz;            // position of the zone along D inside the tile
-    const int btile = (D == 0) ? bx : (D == 1) ? by : bz;
-    // primitive tile: origin = zone-tile origin - 2 e_D, fetched from the even x coordinate at or below it
-    const int qi = i0 - (D == 0 ? 2 : 0) - a.qlo[0], pq = qi & 1;
-    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
-        const int qj = j0 - (D == 1 ? 2 : 0) - a.qlo[1], qk = k0 - (D == 2 ? 2 : 0) - a.qlo[2];
-        tma::load_4d(smem + L::O_Q, &m_q, bar, qi - pq, qj, qk, 0);
-    }
-    const bool active = a.obx.contains(i, j, k);
-    double flat = 0.0;
-    if (active) flat = a.fd(i, j, k, 0);
-    tma::mbar_wait(bar, 0);
+    const int i = c.i, j = c.j, k = c.k, tx = c.tx, ty = c.ty, tz = c.tz, pq = c.pq;
+    const bool active = c.active;
     double qp_own[6], qm_nxt[6], xp_own[NP], xm_nxt[NP];
     const int idx = (D == 0) ? i : (D == 1) ? j : k;
     const bool sym_lo = P.lo_bc[D] == 3, sym_hi = P.hi_bc[D] == 3;
@@ -751,7 +801,7 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
             trace_sources<D>(P, a.srcq.p + a.srcq.idx(i, j, k), a.srcq.sn, sst, flat, sq0[(QS_U + D) * QT::ZONES], sq0[QS_C * QT::ZONES],
                              a.dtdL, a.hdt, sa);
         }
-        trace_core<D, NP, SRC>(P, sq0, QT::ZONES, QT::stride(D), flat, a.dtdL, qp_own, qm_nxt, xp_own, xm_nxt, sa);
+        trace_core<M, D, NP, SRC>(P, sq0, QT::ZONES, QT::stride(D), flat, a.dtdL, qp_own, qm_nxt, xp_own, xm_nxt, sa);
         // hand the minus state to the thread that owns the high face
 #pragma unroll
         for (int n = 0; n < 6; ++n) sEx[n * L::NTHR + threadIdx.x] = qm_nxt[n];
@@ -759,7 +809,7 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
         for (int ip = 0; ip < NP; ++ip) sEx[(6 + ip) * L::NTHR + threadIdx.x] = xm_nxt[ip];
         // interface states to HBM for the transverse stages; a zone shared by two overlapping tiles is written by the tile
         // in which it is not the first zone (same masks as k_trace: trace_ppm.cpp:461-484 + enforce_reflect_states)
-        if (dloc >= 1 || btile == 0) {
+        if (c.dloc >= 1 || c.btile == 0) {
             bool do_p = idx >= a.vlo;
             bool do_m = idx <= a.vhi;
             const bool refl_lo = do_p && sym_lo && idx == P.domlo[D];
@@ -796,7 +846,7 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     }
     __syncthreads();
     // first-pass Riemann problem on the low face of every zone that has its left neighbour in the tile
-    if (!active || dloc < 1) return;
+    if (!active || c.dloc < 1) return;
     constexpr int sEx_D = (D == 0) ? 1 : (D == 1) ? TT::NX : TT::NX * TT::NY;
     double ql[6], xl[NP];
 #pragma unroll
@@ -824,7 +874,7 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     const int oq = QT::off(tx + pq + (D == 0 ? 2 : 0), ty + (D == 1 ? 2 : 0), tz + (D == 2 ? 2 : 0));
     const double cr = sq[QS_C * QT::ZONES + oq], cl = sq[QS_C * QT::ZONES + oq - QT::stride(D)];
     double F[6], FX[NP], ugd, pgd;
-    solve_face_r<D, NP>(P, ql, qr, xl, xr, cl, cr, idx, F, ugd, pgd, FX);
+    solve_face_r<M, D, NP>(P, ql, qr, xl, xr, cl, cr, idx, F, ugd, pgd, FX);
     const long of = a.Fo.idx(i, j, k);
 #pragma unroll
     for (int n = 0; n < 6; ++n) a.Fo.at(of, n) = F[n];
@@ -832,6 +882,46 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     a.Fo.at(of, FX_PG) = pgd;
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) a.Fo.at(of, FX_X + ip) = FX[ip];
+}
+
+template <int D, int NP, bool SRC>
+static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, CTU_TRACE_MINB)
+k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, const TraceRiemannArgs a) {
+    using L = TraceSmem<D, NP>;
+    using TT = TrTile<D>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    // tile and thread coordinates
+    const int bt = blockIdx.x;
+    const int bx = bt % a.ntx, r = bt / a.ntx, by = r % a.nty, bz = r / a.nty;
+    const int i0 = a.obx.lo[0] + bx * TT::SX, j0 = a.obx.lo[1] + by * TT::SY, k0 = a.obx.lo[2] + bz * TT::SZ;
+    TraceCtx c;
+    c.tx = threadIdx.x % TT::NX; c.ty = (threadIdx.x / TT::NX) % TT::NY; c.tz = threadIdx.x / (TT::NX * TT::NY);
+    c.i = i0 + c.tx; c.j = j0 + c.ty; c.k = k0 + c.tz;
+    c.dloc = (D == 0) ? c.tx : (D == 1) ? c.ty : c.tz;            // position of the zone along D inside the tile
+    c.btile = (D == 0) ? bx : (D == 1) ? by : bz;
+    // primitive tile: origin = zone-tile origin - 2 e_D, fetched from the even x coordinate at or below it
+    const int qi = i0 - (D == 0 ? 2 : 0) - a.qlo[0];
+    c.pq = qi & 1;
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); ctu_div_unsafe = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
+        const int qj = j0 - (D == 1 ? 2 : 0) - a.qlo[1], qk = k0 - (D == 2 ? 2 : 0) - a.qlo[2];
+        tma::load_4d(smem + L::O_Q, &m_q, bar, qi - c.pq, qj, qk, 0);
+    }
+    c.active = a.obx.contains(c.i, c.j, c.k);
+    double flat = 0.0;
+    if (c.active) flat = a.fd(c.i, c.j, c.k, 0);
+    tma::mbar_wait(bar, 0);
+    // speculative pass with the branch-free division / sqrt sequences; exact replay of the tile if any thread met an operand
+    // outside their range (see MathFast in ctu_physics.cuh)
+    trace_riemann_body<MathFast, D, NP, SRC>(P, a, smem, c, flat);
+    __syncthreads();
+    if (ctu_div_unsafe) {
+        if (threadIdx.x == 0 && P.replays) atomicAdd(P.replays, 1);
+        trace_riemann_body<MathExact, D, NP, SRC>(P, a, smem, c, flat);
+    }
 }
 
 }  // namespace ctu

@@ -88,6 +88,8 @@ struct DevPar {
     double dx[3];
     int domlo[3], domhi[3];
     int lo_bc[3], hi_bc[3], periodic[3];
+    // diagnostics: number of CTAs that replayed their tile with the exact division / sqrt operators (nullptr = do not count)
+    int* replays;
 };
 
 }  // namespace ctu

@@ -39,6 +39,8 @@ def lib():
         L.ctu_workspace_bytes.argtypes = [C.c_void_p]
         L.ctu_workspace_last_slabs.argtypes = [C.c_void_p]
         L.ctu_workspace_launches.argtypes = [C.c_void_p]
+        L.ctu_workspace_replays.argtypes = [C.c_void_p]
+        L.ctu_workspace_replays.restype = C.c_long
         L.ctu_workspace_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.ctu_stage_name.restype = C.c_char_p
         L.ctu_stage_name.argtypes = [C.c_int]
@@ -99,6 +101,11 @@ def workspace_stage_times(ws_handle, reset=False):
     nl = (C.c_int * NSTAGE)()
     check(lib().ctu_workspace_stage_times(ws_handle, ms, nl, 1 if reset else 0), "ctu_workspace_stage_times")
     return {n: (ms[i], nl[i]) for i, n in enumerate(stage_names())}
+
+
+def workspace_replays(ws_handle):
+    """tiles recomputed with the IEEE division / sqrt operators since the workspace was created (diagnostic)"""
+    return int(lib().ctu_workspace_replays(ws_handle))
 
 
 def default_params():

@@ -13,7 +13,7 @@ v = sys.argv[1]
 try:
     d = json.load(open("gpurun_out/ab_%s.json" % v))
     k = d["roofline"]["kernels"]
-    print(v, "ms/step %.2f" % d["ms_per_step"], " ".join("%s %.1f" % (n[2:], x["ms_per_step"]) for n, x in k.items()), d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+    print(v, "ms/step %.2f" % d["ms_per_step"], " ".join("%s %.1f" % (n[2:], x["ms_per_step"]) for n, x in k.items()), d["clocks"]["sm_mhz"], d["clocks"]["reasons"], "replays/step", d.get("exact_replay_tiles_per_step"))
 except Exception as e:
     print(v, "FAILED", e)
 PY
