@@ -265,7 +265,8 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
     const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
     const int gi = fi - (N == 0), pg = gi & 1;
     const int qi = c.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
-    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); ctu_div_unsafe = 0; }
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
+    if (threadIdx.x < 32) ctu_div_unsafe[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
@@ -289,16 +290,16 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
     }
 #endif
     tma::mbar_wait(bar, 0);
-    // speculative pass with the branch-free division / sqrt sequences; exact replay of the tile if any thread met an operand
-    // outside their range (see MathFast in ctu_physics.cuh)
+    // speculative pass with the branch-free division / sqrt sequences; a warp replays its faces with the exact operators if one
+    // of its threads met an operand outside their range (see MathFast in ctu_physics.cuh; the faces of a tile are independent)
 #if CTU_Q_LDG
-    trans2_body<MathFast, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, ql, qr, xl, xr);
+    trans2_body<MathFastW, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, ql, qr, xl, xr);
 #else
-    trans2_body<MathFast, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, nullptr, nullptr, nullptr, nullptr);
+    trans2_body<MathFastW, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, nullptr, nullptr, nullptr, nullptr);
 #endif
-    __syncthreads();
-    if (ctu_div_unsafe) {
-        if (threadIdx.x == 0 && P.replays) atomicAdd(P.replays, 1);
+    __syncwarp();
+    if (ctu_div_unsafe[threadIdx.x >> 5]) {
+        if ((threadIdx.x & 31) == 0 && P.replays) atomicAdd(P.replays, 1);
 #if CTU_Q_LDG
         trans2_body<MathExact, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, ql, qr, xl, xr);
 #else
@@ -410,7 +411,8 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
     const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
     const int gi = fi - (N == 0), pg = gi & 1;
     const int qi = c.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
-    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); ctu_div_unsafe = 0; }
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
+    if (threadIdx.x < 32) ctu_div_unsafe[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
@@ -445,15 +447,15 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
         for (int ip = 0; ip < NP; ++ip) dUX[ip] = a.U.at(ou, UFA + ip) - a.U.at(oum, UFA + ip);
     }
     tma::mbar_wait(bar, 0);
-    // speculative pass / exact replay, as in k_trans2_tma
+    // speculative pass / exact replay per warp, as in k_trans2_tma
 #if CTU_Q_LDG
-    final_body<MathFast, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, ql, qr, xl, xr);
+    final_body<MathFastW, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, ql, qr, xl, xr);
 #else
-    final_body<MathFast, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, nullptr, nullptr, nullptr, nullptr);
+    final_body<MathFastW, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, nullptr, nullptr, nullptr, nullptr);
 #endif
-    __syncthreads();
-    if (ctu_div_unsafe) {
-        if (threadIdx.x == 0 && P.replays) atomicAdd(P.replays, 1);
+    __syncwarp();
+    if (ctu_div_unsafe[threadIdx.x >> 5]) {
+        if ((threadIdx.x & 31) == 0 && P.replays) atomicAdd(P.replays, 1);
         if (active) {
             const long ou = a.U.idx(c.i, c.j, c.k);
             const long oum = ou - ((N == 0) ? 1 : (N == 1) ? a.U.sj : a.U.sk);
@@ -903,7 +905,7 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     // primitive tile: origin = zone-tile origin - 2 e_D, fetched from the even x coordinate at or below it
     const int qi = i0 - (D == 0 ? 2 : 0) - a.qlo[0];
     c.pq = qi & 1;
-    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); ctu_div_unsafe = 0; }
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); ctu_div_unsafe[0] = 0; }
     __syncthreads();
     if (threadIdx.x == 0) {
         tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
@@ -918,7 +920,7 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     // outside their range (see MathFast in ctu_physics.cuh)
     trace_riemann_body<MathFast, D, NP, SRC>(P, a, smem, c, flat);
     __syncthreads();
-    if (ctu_div_unsafe) {
+    if (ctu_div_unsafe[0]) {
         if (threadIdx.x == 0 && P.replays) atomicAdd(P.replays, 1);
         trace_riemann_body<MathExact, D, NP, SRC>(P, a, smem, c, flat);
     }
