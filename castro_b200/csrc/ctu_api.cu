@@ -302,8 +302,8 @@ int launch_update_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb
     CTU_MAP(m_f0, F[0], ibx, L::NFX, L::F0T, L::NFX)
     CTU_MAP(m_f1, F[1], ibx, L::NFX, L::F1T, L::NFX)
     CTU_MAP(m_f2, F[2], ibx, L::NFX, L::F2T, L::NFX)
-    const TileGrid tg = make_tg(tb);
-    k_update_tma<NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_f0, m_f1, m_f2, Sb, Sin, Sn, ua, ibx.lo[0], ibx.lo[1], ibx.lo[2], tg, dt);
+    const TileGrid tg = make_tg_t<UTY, UTZ>(tb);
+    k_update_tma<NP><<<tg_blocks(tg), UTTHR, L::TOTAL, st>>>(P, m_f0, m_f1, m_f2, Sb, Sin, Sn, ua, ibx.lo[0], ibx.lo[1], ibx.lo[2], tg, dt);
     return 0;
 }
 int launch_update(const DevPar& P, int np, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,

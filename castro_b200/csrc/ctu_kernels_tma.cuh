@@ -21,7 +21,7 @@ namespace ctu {
 #define CTU_TRACE_MINB 3
 #endif
 #ifndef CTU_TMA_MINB
-#define CTU_TMA_MINB 2
+#define CTU_TMA_MINB 4
 #endif
 // CTU_Q_LDG = 1: the interface-state tiles (each element is consumed by exactly one thread) are read with plain coalesced
 // global loads that are in flight while the TMA flux tiles land, instead of being staged through shared memory: the CTA's
@@ -30,14 +30,15 @@ namespace ctu {
 #define CTU_Q_LDG 0
 #endif
 #ifndef CTU_TY
-#define CTU_TY 4
+#define CTU_TY 2
 #endif
 #ifndef CTU_TZ
 #define CTU_TZ 2
 #endif
-constexpr int TX = 32, TY = CTU_TY, TZ = CTU_TZ, TTHR = TX * TY * TZ;
+constexpr int TX = 32, TY = CTU_TY, TZ = CTU_TZ, TTHR = TX * TY * TZ;      // flux-stage kernels: 32x2x2 faces, 4 CTAs per SM
+constexpr int UTY = 4, UTZ = 2, UTTHR = TX * UTY * UTZ;                        // update kernel: 32x4x2 zones, 3 CTAs per SM
 // resident CTAs per SM the flux-stage kernels are compiled for: the second passive scalar makes the flux tiles too large for a third CTA
-template <int NP> struct TmaMinB { static constexpr int value = (NP == 1) ? CTU_TMA_MINB : 2; };
+template <int NP> struct TmaMinB { static constexpr int value = (NP == 1) ? CTU_TMA_MINB : 3; };
 constexpr int ceven(int n) { return (n + 1) & ~1; }
 constexpr size_t al128(size_t b) { return (b + 127) & ~(size_t)127; }
 
@@ -45,24 +46,28 @@ struct TileGrid {
     int lo0, lo1, lo2, hi0, hi1, hi2;   // launch box
     int ntx, nty, ntz;
 };
-inline TileGrid make_tg(const Box3& b) {
+template <int TYv, int TZv>
+inline TileGrid make_tg_t(const Box3& b) {
     TileGrid t;
     t.lo0 = b.lo[0]; t.lo1 = b.lo[1]; t.lo2 = b.lo[2]; t.hi0 = b.hi[0]; t.hi1 = b.hi[1]; t.hi2 = b.hi[2];
-    t.ntx = (b.hi[0] - b.lo[0] + TX) / TX; t.nty = (b.hi[1] - b.lo[1] + TY) / TY; t.ntz = (b.hi[2] - b.lo[2] + TZ) / TZ;
+    t.ntx = (b.hi[0] - b.lo[0] + TX) / TX; t.nty = (b.hi[1] - b.lo[1] + TYv) / TYv; t.ntz = (b.hi[2] - b.lo[2] + TZv) / TZv;
     return t;
 }
+inline TileGrid make_tg(const Box3& b) { return make_tg_t<TY, TZ>(b); }
 inline unsigned tg_blocks(const TileGrid& t) { return (unsigned)t.ntx * (unsigned)t.nty * (unsigned)t.ntz; }
 
 struct TileCtx { int i0, j0, k0, tx, ty, tz, i, j, k; };
-__device__ __forceinline__ TileCtx tile_ctx(const TileGrid& tg) {
+template <int TYv, int TZv>
+__device__ __forceinline__ TileCtx tile_ctx_t(const TileGrid& tg) {
     TileCtx c;
     const int bt = blockIdx.x;
     const int bx = bt % tg.ntx, r = bt / tg.ntx, by = r % tg.nty, bz = r / tg.nty;
-    c.i0 = tg.lo0 + bx * TX; c.j0 = tg.lo1 + by * TY; c.k0 = tg.lo2 + bz * TZ;
-    c.tx = threadIdx.x & (TX - 1); c.ty = (threadIdx.x / TX) % TY; c.tz = threadIdx.x / (TX * TY);
+    c.i0 = tg.lo0 + bx * TX; c.j0 = tg.lo1 + by * TYv; c.k0 = tg.lo2 + bz * TZv;
+    c.tx = threadIdx.x & (TX - 1); c.ty = (threadIdx.x / TX) % TYv; c.tz = threadIdx.x / (TX * TYv);
     c.i = c.i0 + c.tx; c.j = c.j0 + c.ty; c.k = c.k0 + c.tz;
     return c;
 }
+__device__ __forceinline__ TileCtx tile_ctx(const TileGrid& tg) { return tile_ctx_t<TY, TZ>(tg); }
 
 // shared-memory tile [comp][z][y][x], dense
 template <int EX_, int EY_, int EZ_>
@@ -89,7 +94,7 @@ template <int N>
 using NodeTile = STile<EXT, TY + (N != 1), TZ + (N != 2)>;
 // N-face fluxes of the zones of the tile: origin = tile origin, +1 on the high side in N
 template <int N>
-using OwnFluxTile = STile<EXT, TY + (N == 1), TZ + (N == 2)>;
+using OwnFluxTile = STile<EXT, UTY + (N == 1), UTZ + (N == 2)>;     // update kernel's tile
 
 template <int NP>
 __device__ __forceinline__ bool is_species(const DevPar& P, int ip) { return ip >= P.QFS_off && ip < P.QFS_off + P.nspec; }
@@ -511,7 +516,7 @@ struct UpdateSmem {
 };
 
 template <int NP>
-static __global__ void __launch_bounds__(TTHR, 3)
+static __global__ void __launch_bounds__(UTTHR, 3)
 k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __grid_constant__ CUtensorMap m_f1,
              const __grid_constant__ CUtensorMap m_f2, const A4 Sb, const A4 Sin, const A4 Sn, const UpdateArgs a, const int ilo0,
              const int ilo1, const int ilo2, const TileGrid tg, const double dt) {
@@ -519,7 +524,7 @@ k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __g
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
     unsigned long long* red = reinterpret_cast<unsigned long long*>(smem + L::O_RED);
-    const TileCtx c = tile_ctx(tg);
+    const TileCtx c = tile_ctx_t<UTY, UTZ>(tg);
     const int fi = c.i0 - ilo0, fj = c.j0 - ilo1, fk = c.k0 - ilo2, pf = fi & 1;
     if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
     __syncthreads();
@@ -592,8 +597,8 @@ k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __g
         if (nan) atomicAdd(&a.counters[3], 1);
     }
     if (a.want_dt) {
-        block_min_atomic_n<TTHR>(dt0, a.dtmin + 0, red);
-        block_min_atomic_n<TTHR>(dt1, a.dtmin + 1, red);
+        block_min_atomic_n<UTTHR>(dt0, a.dtmin + 0, red);
+        block_min_atomic_n<UTTHR>(dt1, a.dtmin + 1, red);
     }
 }
 
