@@ -2,6 +2,7 @@
 // set-up of Castro::variableSetUp), the inputs-file parser, the problem-setup hooks
 // (problem_initialize / problem_initialize_state_data of Exec/hydro_tests/{Sedov,Sod,KH}) and a single-box
 // time-step driver mirroring Amr::coarseTimeStep -> Castro::advance for amr.max_level = 0.
+#include <cerrno>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +14,7 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#include <sys/stat.h>
 
 #include "ctu_kernels.cuh"
 #include "ctu_internal.h"
@@ -1086,4 +1088,71 @@ int ctu_sim_advance(ctu_sim_t* s, int nsteps, double stop_time, double* time_io,
     return status;
 }
 
+// ---- plotfile (single level, one grid): the layout of amrex::WriteSingleLevelPlotfile as Castro::writePlotFile emits it ------------
+// (Source/driver/Castro_io.cpp:943-; external/amrex/Src/Base/AMReX_PlotFileUtil.cpp:198-330, AMReX_VisMF.cpp header format, FAB header
+//  of AMReX_FabConv).  State variables only (amr.derive_plot_vars = NONE): density xmom ymom zmom rho_E rho_e Temp [adv_i] rho_X..
+// so that external/amrex/Tools/Plotfile/fcompare can diff a run of this library against a run of the reference.
+int ctu_sim_write_plotfile(ctu_sim_t* s, const char* dir, double time, int step) {
+    if (!s || !dir) return CTU_ERR_BAD_ARG;
+    const int nc = s->nstate;
+    const int nx = s->vbx.hi[0] - s->vbx.lo[0] + 1, ny = s->vbx.hi[1] - s->vbx.lo[1] + 1, nz = s->vbx.hi[2] - s->vbx.lo[2] + 1;
+    const size_t nzone = (size_t)nx * ny * nz;
+    std::vector<double> h(nzone * nc);
+    int rc = ctu_sim_download(s, h.data());
+    if (rc) return rc;
+    const std::string root(dir), lev = root + "/Level_0";
+    if (mkdir(root.c_str(), 0755) != 0 && errno != EEXIST) return CTU_ERR_IO;
+    if (mkdir(lev.c_str(), 0755) != 0 && errno != EEXIST) return CTU_ERR_IO;
+    std::vector<std::string> names = {"density", "xmom", "ymom", "zmom", "rho_E", "rho_e", "Temp"};
+    for (int i = 0; i < s->par.nadv; ++i) names.push_back("adv_" + std::to_string(i));
+    for (int i = 0; i < s->par.nspec; ++i) names.push_back(s->par.nspec == 1 ? std::string("rho_X") : "rho_X" + std::to_string(i));
+    for (int i = 0; i < s->par.naux; ++i) names.push_back("rho_aux" + std::to_string(i));
+    const ctu_geom_t& g = s->geom;
+    char buf[256];
+    auto box_str = [&](const Box3& b) {
+        std::snprintf(buf, sizeof(buf), "((%d,%d,%d) (%d,%d,%d) (0,0,0))", b.lo[0], b.lo[1], b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
+        return std::string(buf);
+    };
+    auto num = [&](double v) { std::snprintf(buf, sizeof(buf), "%.15g", v); return std::string(buf); };   // the reference writes its header with 15 significant digits
+    {   std::ofstream f(root + "/Header");
+        if (!f) return CTU_ERR_IO;
+        f << "HyperCLaw-V1.1\n" << nc << "\n";
+        for (auto& n : names) f << n << "\n";
+        f << "3\n" << num(time) << "\n0\n";
+        f << num(g.problo[0]) << " " << num(g.problo[1]) << " " << num(g.problo[2]) << " \n";
+        f << num(g.probhi[0]) << " " << num(g.probhi[1]) << " " << num(g.probhi[2]) << " \n\n";
+        Box3 dom; for (int d = 0; d < 3; ++d) { dom.lo[d] = g.domlo[d]; dom.hi[d] = g.domhi[d]; }
+        f << box_str(dom) << " \n" << step << " \n";
+        f << num(g.dx[0]) << " " << num(g.dx[1]) << " " << num(g.dx[2]) << " \n";
+        f << g.coord << "\n0\n";
+        f << "0 1 " << num(time) << "\n" << step << "\n";
+        for (int d = 0; d < 3; ++d)
+            f << num(g.problo[d] + (s->vbx.lo[d] - g.domlo[d]) * g.dx[d]) << " " << num(g.problo[d] + (s->vbx.hi[d] + 1 - g.domlo[d]) * g.dx[d]) << "\n";
+        f << "Level_0/Cell\n";
+        if (!f) return CTU_ERR_IO; }
+    {   std::ofstream f(lev + "/Cell_D_00000", std::ios::binary);
+        if (!f) return CTU_ERR_IO;
+        f << "FAB ((8, (64 11 52 0 1 12 0 1023)),(8, (8 7 6 5 4 3 2 1)))" << box_str(s->vbx) << " " << nc << "\n";
+        f.write(reinterpret_cast<const char*>(h.data()), (std::streamsize)(h.size() * sizeof(double)));
+        if (!f) return CTU_ERR_IO; }
+    {   std::ofstream f(lev + "/Cell_H");
+        if (!f) return CTU_ERR_IO;
+        f << "1\n1\n" << nc << "\n0\n(1 0\n" << box_str(s->vbx) << "\n)\n1\nFabOnDisk: Cell_D_00000 0\n\n";
+        auto ext = [&](bool mx) {
+            f << "1," << nc << "\n";
+            for (int n = 0; n < nc; ++n) {
+                const double* p = h.data() + (size_t)n * nzone;
+                double v = p[0];
+                for (size_t i = 1; i < nzone; ++i) v = mx ? (p[i] > v ? p[i] : v) : (p[i] < v ? p[i] : v);
+                std::snprintf(buf, sizeof(buf), "%.17e,", v);
+                f << buf;
+            }
+            f << "\n\n";
+        };
+        ext(false); ext(true);
+        if (!f) return CTU_ERR_IO; }
+    return 0;
+}
+
 }  // extern "C"
+

@@ -55,6 +55,7 @@ def lib():
         L.ctu_sim_download.argtypes = [C.c_void_p, C.c_void_p]
         L.ctu_sim_upload.argtypes = [C.c_void_p, C.c_void_p]
         L.ctu_sim_init_problem.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.ctu_sim_write_plotfile.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_int]
         L.ctu_sim_step_hydro.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ctu_sim_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ctu_sim_advance.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -275,6 +276,10 @@ class Sim:
             out = np.empty(self.shape)
         check(lib().ctu_sim_download(self.h, out.ctypes.data), "ctu_sim_download")
         return out
+
+    def write_plotfile(self, path, time, step):
+        """single-level AMReX plotfile of the current state (state variables only), readable by the reference's fcompare"""
+        check(lib().ctu_sim_write_plotfile(self.h, str(path).encode(), float(time), int(step)), "ctu_sim_write_plotfile")
 
     def upload(self, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float64)

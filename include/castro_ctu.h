@@ -247,6 +247,11 @@ int  ctu_sim_step_host(ctu_sim_t* sim, const double* host_in, double* host_out, 
 int  ctu_sim_advance(ctu_sim_t* sim, int nsteps, double stop_time, double* time_inout, double* dt_inout,
                      double* dt_history /* nsteps entries or NULL */, int* steps_done /* or NULL */);
 
+/* Writes the current state as a single-level, single-grid AMReX plotfile (HyperCLaw-V1.1; state variables only, i.e. what
+ * Castro::writePlotFile emits with amr.derive_plot_vars = NONE: Source/driver/Castro_io.cpp:943-, AMReX_PlotFileUtil.cpp:198-330),
+ * so that the reference's own comparator (external/amrex/Tools/Plotfile/fcompare.cpp) can diff the two codes. */
+int  ctu_sim_write_plotfile(ctu_sim_t* sim, const char* dir, double time, int step);
+
 #ifdef __cplusplus
 }
 #endif

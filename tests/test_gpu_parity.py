@@ -400,3 +400,46 @@ def test_hydro_advance_with_sources_vs_oracle(nspec, solver, predictor):
     dSn2 = torch.from_numpy(Sn0).cuda()
     lib.hydro_advance(ws, par, geom, (0, 0, 0), hi, dSb, glo, dSn2, (0, 0, 0), dt, n_clean=1)
     assert not torch.equal(dSn2, dSn)
+
+
+@pytest.mark.parametrize("solver,nsteps", [(2, 10), (0, 25)])
+def test_plotfile_vs_reference_with_fcompare(solver, nsteps, tmp_path):
+    """the north star's own acceptance procedure: run the UNMODIFIED reference executable (oracle/_ref, test infrastructure) and
+    this library on the same inputs file, write a plotfile from each, and let the reference's comparator
+    (external/amrex/Tools/Plotfile/fcompare) judge: every conserved field must agree to rel-Linf <= 1e-12 (it is 0)."""
+    import os
+    import re
+    import subprocess
+    _torch()
+    from castro_b200 import lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "Castro3d_sedov.ex")
+    fcmp = os.path.join(root, "oracle", "_ref", "fcompare.ex")
+    inputs = os.path.join(root, "bench_inputs", "inputs.sedov3d")
+    if not (os.path.exists(exe) and os.path.exists(fcmp)):
+        pytest.skip("oracle/_ref not built (python -c 'import __graft_entry__ as g; g.build()' where /root/reference is mounted)")
+    n = 24
+    over = "amr.n_cell=%d %d %d castro.riemann_solver=%d" % (n, n, n, solver)
+    ref_args = [exe, inputs, "amr.n_cell=%d %d %d" % (n, n, n), "castro.riemann_solver=%d" % solver, "amr.max_grid_size=%d" % n,
+                "max_step=%d" % nsteps, "amr.plot_files_output=1", "amr.plot_int=%d" % nsteps, "amr.plot_file=%s" % (tmp_path / "ref_plt"),
+                "amr.derive_plot_vars=NONE", "castro.v=0", "amr.v=0"]
+    out = subprocess.run(ref_args, cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    ref_pf = str(tmp_path / ("ref_plt%05d" % nsteps))
+    assert os.path.isdir(ref_pf)
+    # the same inputs file through the library's own ParmParse reader
+    par, geom, n_cell, max_step, stop_time, prob = lib.parse_inputs(inputs, over)
+    lib.params_finalize(par)
+    sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in n_cell))
+    sim.init_problem("Sedov", {k: (int(v) if k == "nsub" else float(v)) for k, v in (kv.split("=") for kv in prob.split())})
+    rc, t, dt, hist = sim.advance(nsteps)
+    assert rc == 0 and len(hist) == nsteps
+    my_pf = str(tmp_path / "b200_plt")
+    sim.write_plotfile(my_pf, t, nsteps)
+    sim.close()
+    res = subprocess.run([fcmp, "--rel_tol", "1e-12", "-a", ref_pf, my_pf], capture_output=True, text=True)
+    assert res.returncode == 0 and "PLOTFILE AGREE" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+    rows = re.findall(r"^\s*(\w+)\s+([0-9.eE+-]+)\s+([0-9.eE+-]+)\s*$", res.stdout, flags=re.M)
+    assert len(rows) == 8, res.stdout
+    for name, abs_err, rel_err in rows:
+        assert float(abs_err) == 0.0 and float(rel_err) == 0.0, "fcompare %s: abs %s rel %s" % (name, abs_err, rel_err)
