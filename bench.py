@@ -294,7 +294,11 @@ def gpu_arm(args):
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
             try:
-                roofline["traffic"] = json.load(open(traffic_file)).get("pipeline_dram_bytes_per_zone")
+                # ncu-measured DRAM bytes of one pipeline pass over the box (all kernels), to set beside the algorithmic bytes
+                tpz = json.load(open(traffic_file)).get("pipeline_dram_bytes_per_zone")
+                roofline["traffic"] = tpz * zones_local
+                roofline["traffic_bytes_per_zone"] = tpz
+                roofline["algorithmic_bytes"] = alg_bytes * zones_local
             except Exception:
                 pass
         cpu = None

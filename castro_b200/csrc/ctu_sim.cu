@@ -965,9 +965,9 @@ int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, dou
     HydroRun* run = hydro_begin(s->ws, &s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, &sn, nullptr, nullptr, dt,
                                 2 | CTU_ADV_SNEW_FROM_SBORDER, true, s->st, &rc);
     if (!run) return rc;
-    // chunk size: CTU_HOST_CHUNK planes (default 32), at least the 4 planes a neighbouring slab reads, at most what the
+    // chunk size: CTU_HOST_CHUNK planes (default 16: the step is PCIe-bound, so short chunks shorten the pipeline fill and drain), at least the 4 planes a neighbouring slab reads, at most what the
     // workspace bound allows
-    long kc = 32;
+    long kc = 16;
     if (const char* e = std::getenv("CTU_HOST_CHUNK")) kc = std::max(1L, std::strtol(e, nullptr, 10));
     kc = std::min(kc, hydro_max_slab_planes(run));
     if (kc < 1) { hydro_abort(run); return CTU_ERR_NOMEM; }

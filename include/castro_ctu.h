@@ -238,7 +238,7 @@ int  ctu_sim_step_fill(ctu_sim_t* sim);
 int  ctu_sim_step_hydro(ctu_sim_t* sim, double dt, double dt_est[2], int n_bad[2]);
 /* One step with the state in HOST memory (what a CPU-resident caller of the path does every step), single box == domain:
  * host_in / host_out: valid zones [ncomp][nz][ny][nx] (i fastest; pinned memory recommended; may alias).  Same result as
- * ctu_sim_upload + pre + fill + hydro + ctu_sim_download, but streamed in z-chunks (CTU_HOST_CHUNK planes, default 32) so
+ * ctu_sim_upload + pre + fill + hydro + ctu_sim_download, but streamed in z-chunks (CTU_HOST_CHUNK planes, default 16) so
  * that the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap. */
 int  ctu_sim_step_host(ctu_sim_t* sim, const double* host_in, double* host_out, double dt, double dt_est[2], int n_bad[2]);
 /* Single box covering the whole domain: runs nsteps of pre+fill+hydro with the dt control of
