@@ -443,3 +443,64 @@ def test_plotfile_vs_reference_with_fcompare(solver, nsteps, tmp_path):
     assert len(rows) == 8, res.stdout
     for name, abs_err, rel_err in rows:
         assert float(abs_err) == 0.0 and float(rel_err) == 0.0, "fcompare %s: abs %s rel %s" % (name, abs_err, rel_err)
+
+
+def test_full_size_properties_sedov256():
+    """BASELINE config[1] at its full size (3-D Sedov 256^3, HLLC), through size-independent properties: (a) the z-slab
+    decomposition of the workspace does not change a single bit; (b) the host-streamed step equals the device-resident step bit for
+    bit; (c) mass and total energy are conserved to rounding while the blast is far from the outflow boundaries; (d) the solution
+    keeps the x<->y<->z permutation symmetry of the initial data to 1e-12 (the scheme's operation order is not symmetric, so this
+    is a tolerance test); (e) no exceptional zone: status 0 and finite everywhere."""
+    _torch()
+    from castro_b200 import lib, abi
+    from castro_b200.dist import initial_dt, new_dt
+    from cases import sedov_params
+    n = 256
+    par = sedov_params(2)
+    lib.params_finalize(par)
+    geom = abi.make_geom((n, n, n))
+    prob = dict(r_init=0.01, p_ambient=1.e-5, exp_energy=1.0, dens_ambient=1.0, nsub=10)
+    nsteps = 4
+    # (a) one slab vs several
+    sim = lib.Sim(par, geom, (0, 0, 0), (n - 1,) * 3)
+    sim.init_problem("Sedov", prob)
+    U0 = sim.download()
+    rc, t, dt, hist = sim.advance(nsteps)
+    assert rc == 0
+    U1 = sim.download()
+    slabs1 = sim.last_slabs
+    sim.close()
+    sim = lib.Sim(par, geom, (0, 0, 0), (n - 1,) * 3, workspace_bytes=6 << 30)
+    sim.init_problem("Sedov", prob)
+    rc, t2, dt2, hist2 = sim.advance(nsteps)
+    assert rc == 0 and sim.last_slabs > slabs1
+    U2 = sim.download()
+    assert np.array_equal(U1, U2) and np.array_equal(hist, hist2)
+    # (b) host-streamed step from the same initial data
+    sim.upload(U0)
+    h, h2 = U0.copy(), np.empty_like(U0)
+    tt = 0.0
+    dth = initial_dt(par, sim.estdt(), tt, -1.0)
+    for _ in range(nsteps):
+        rc, est, nbad = sim.step_host(h, h2, (tt + dth) - tt)
+        assert rc == 0
+        h, h2 = h2, h
+        tt += dth
+        dth = new_dt(par, est[1], dth, tt, -1.0)
+    sim.close()
+    assert np.array_equal(h, U1) and tt == t
+    # (c) conservation (sums in extended precision)
+    for comp, name in ((0, "mass"), (4, "total energy")):
+        s0, s1 = np.sum(U0[comp], dtype=np.longdouble), np.sum(U1[comp], dtype=np.longdouble)
+        assert abs(float((s1 - s0) / s0)) < 1e-13, "%s not conserved: %r -> %r" % (name, s0, s1)
+    # (d) permutation symmetry x<->y and y<->z (array axes are [z, y, x])
+    for comp in (0, 4, 5):
+        a = U1[comp]
+        sc = np.abs(a).max()
+        assert np.abs(a - a.transpose(0, 2, 1)).max() <= 1e-12 * sc
+        assert np.abs(a - a.transpose(1, 0, 2)).max() <= 1e-12 * sc
+    sc = np.abs(U1[1]).max()
+    assert np.abs(U1[1] - U1[2].transpose(0, 2, 1)).max() <= 1e-12 * sc      # xmom(x,y,z) = ymom(y,x,z)
+    assert np.abs(U1[2] - U1[3].transpose(1, 0, 2)).max() <= 1e-12 * sc      # ymom(x,y,z) = zmom(x,z,y)
+    # (e)
+    assert np.isfinite(U1).all()
