@@ -134,7 +134,6 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (p->riemann_solver != 0 && p->riemann_solver != 2) return CTU_ERR_UNSUPPORTED;   // CG solver: not in the parity contract
     if (p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->ppm_temp_fix || p->use_pslope || p->ppm_well_balanced)
         return CTU_ERR_UNSUPPORTED;
-    if (p->transverse_use_eos || p->transverse_reset_rhoe) return CTU_ERR_UNSUPPORTED;
     if (p->eos_kind != 0) return CTU_ERR_UNSUPPORTED;                           // helmholtz: SURVEY §8(f) rank 2
     if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
     return 0;

@@ -525,6 +525,10 @@ static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, co
         if (reset_p) return X;
         return (rho_p * X - cdtdx * (Ft.at(ofp + sT_f, FX_X + ip) - Ft.at(ofp, FX_X + ip))) / rrnew_p;
     };
+    if (P.transverse_use_eos || P.transverse_reset_rhoe) {     // non-default edge-state thermodynamics (a17)
+        edge_thermo_post<false>(P, qlo, eos_mu(P, [&](int n) { return xm(P.QFS_off + n); }), reset_m);
+        edge_thermo_post<false>(P, qro, eos_mu(P, [&](int n) { return xp(P.QFS_off + n); }), reset_p);
+    }
     double F[6], ugd, pgd;
     PassiveUpwind pu;
     solve_face<N>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu);
@@ -603,6 +607,10 @@ static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 q
         return (compn - c1 * (F1.at(ofp + s1_f, FX_X + ip) - F1.at(ofp, FX_X + ip)) -
                 c2 * (F2.at(ofp + s2_f, FX_X + ip) - F2.at(ofp, FX_X + ip))) / rrnew_p;
     };
+    if (P.transverse_use_eos || P.transverse_reset_rhoe) {     // non-default edge-state thermodynamics (a17)
+        edge_thermo_post<true>(P, qlo, eos_mu(P, [&](int n) { return xm(P.QFS_off + n); }), reset_m);
+        edge_thermo_post<true>(P, qro, eos_mu(P, [&](int n) { return xp(P.QFS_off + n); }), reset_p);
+    }
     double F[6], ugd, pgd;
     PassiveUpwind pu;
     solve_face<N>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu);

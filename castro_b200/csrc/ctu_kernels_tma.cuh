@@ -147,6 +147,8 @@ __device__ __forceinline__ void trans_single_side(const DevPar& P, const FT& sF,
     trans_single_hydro<M>(P, q, qo, fl, fr, ugm, ugp, pgm, pgp, P.gamma, cdt, rrnew, reset);
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) xo[ip] = reset ? x[ip] : xn[ip];
+    if (P.transverse_use_eos || P.transverse_reset_rhoe)      // non-default edge-state thermodynamics (a17)
+        edge_thermo_post<false>(P, qo, eos_mu(P, [&](int n) { double r = 0.0; for (int ip = 0; ip < NP; ++ip) if (ip == P.QFS_off + n) r = xo[ip]; return r; }), reset);
 }
 
 // actual_trans_final for one state (trans.cpp:559-968)
@@ -169,6 +171,8 @@ __device__ __forceinline__ void trans_final_side(const DevPar& P, const F1T& sF1
                       sF2(o2, FX_UG), sF2(o2 + S2, FX_UG), sF2(o2, FX_PG), sF2(o2 + S2, FX_PG), P.gamma, c1, c2, rrnew, reset);
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) xo[ip] = reset ? x[ip] : xn[ip];
+    if (P.transverse_use_eos || P.transverse_reset_rhoe)
+        edge_thermo_post<true>(P, qo, eos_mu(P, [&](int n) { double r = 0.0; for (int ip = 0; ip < NP; ++ip) if (ip == P.QFS_off + n) r = xo[ip]; return r; }), reset);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -42,6 +42,9 @@ CASES = {
                                                 "castro.init_shrink=0.1", "castro.change_max=1.1", "stop_time=1.e9"]),
     # non-cubic box + anisotropic dx, CGF
     "sedov_24x16x8_cgf": ((24, 16, 8), 6, [6], ["castro.riemann_solver=0", "geometry.prob_hi=1.5 1.0 0.5"]),
+    # edge-state thermodynamics options (reset_edge_state_thermo + the EOS / (rho e) branches of trans_single/final)
+    "sedov16_hllc_eos": (16, 20, [20], ["castro.riemann_solver=2", "castro.transverse_use_eos=1", "castro.transverse_reset_rhoe=1"]),
+    "sedov16_cgf_rhoe": (16, 20, [20], ["castro.riemann_solver=0", "castro.transverse_reset_rhoe=1"]),
 }
 
 

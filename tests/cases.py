@@ -33,6 +33,8 @@ CASES = {
                                   prob=dict(r_init=1.25e8, p_ambient=1.e21, exp_energy=1.e52, dens_ambient=1.e4),
                                   par=dict(init_shrink=0.1)),
     "sedov_24x16x8_cgf": dict(n_cell=(24, 16, 8), solver=0, geom=dict(probhi=(1.5, 1.0, 0.5))),
+    "sedov16_hllc_eos": dict(n_cell=(16, 16, 16), solver=2, par=dict(transverse_use_eos=1, transverse_reset_rhoe=1)),
+    "sedov16_cgf_rhoe": dict(n_cell=(16, 16, 16), solver=0, par=dict(transverse_reset_rhoe=1)),
 }
 
 
