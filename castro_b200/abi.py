@@ -48,6 +48,7 @@ class Params(C.Structure):
         ("nspec", C.c_int), ("naux", C.c_int), ("nadv", C.c_int),
         ("aion", DblS), ("zion", DblS),
         ("do_grav", C.c_int), ("grav_source_type", C.c_int), ("const_grav", C.c_double),
+        ("shock_detection_include_sources", C.c_int), ("shock_detection_threshold", C.c_double),
     ]
 
     @property
@@ -88,6 +89,8 @@ def default_params():
     p.aion[0] = 1.0
     p.zion[0] = 1.0
     p.do_grav, p.grav_source_type, p.const_grav = 0, 4, 0.0
+    p.shock_detection_include_sources = 1
+    p.shock_detection_threshold = 0.6666666666666666666666
     return p
 
 

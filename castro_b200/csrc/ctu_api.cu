@@ -86,6 +86,9 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
     P.use_flattening = par->use_flattening;
     P.ppm_do_limiting = par->ppm_do_limiting;
     P.first_order_hydro = par->first_order_hydro;
+    P.hybrid_riemann = par->hybrid_riemann;
+    P.shock_detection_include_sources = par->shock_detection_include_sources;
+    P.shock_detection_threshold = par->shock_detection_threshold;
     P.transverse_use_eos = par->transverse_use_eos;
     P.transverse_reset_density = par->transverse_reset_density;
     P.transverse_reset_rhoe = par->transverse_reset_rhoe;
@@ -132,7 +135,7 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
         return CTU_ERR_BAD_ARG;
     if (p->ppm_type != 1) return CTU_ERR_UNSUPPORTED;                           // PLM: SURVEY §8(f) rank 4
     if (p->riemann_solver != 0 && p->riemann_solver != 2) return CTU_ERR_UNSUPPORTED;   // CG solver: not in the parity contract
-    if (p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->ppm_temp_fix || p->use_pslope || p->ppm_well_balanced)
+    if (p->limit_fluxes_on_small_dens || p->ppm_temp_fix || p->use_pslope || p->ppm_well_balanced)
         return CTU_ERR_UNSUPPORTED;
     if (p->eos_kind != 0) return CTU_ERR_UNSUPPORTED;                           // helmholtz: SURVEY §8(f) rank 2
     if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
@@ -159,6 +162,7 @@ bool tma_ok(const DevPar& P) {
     static const bool disabled = (std::getenv("CTU_NO_TMA") != nullptr);
     if (disabled || !P.gamc_const) return false;
     if (P.npassive != 1 && P.npassive != 2) return false;
+    if (P.hybrid_riemann) return false;      // the HLL blend lives in the register-staged family only (keeps the tile kernels lean)
     return tma::encode_fn() != nullptr;
 }
 
@@ -448,7 +452,7 @@ HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     r->qpad = (nxg + 8) & 1; r->ipad = (nxg + 3) & 1;
     // per z-plane scratch: qs on grow(tile,4); everything else on ibx = [lo-1, hi+2]
     r->plane_q = (size_t)(nxg + 8 + r->qpad) * (nyg + 8) * (r->NQS + (r->have_src ? NSRCQ : 0)) * sizeof(double);
-    r->plane_i = (size_t)(nxg + 3 + r->ipad) * (nyg + 4) * (size_t)(2 + 6 * r->NIS + 9 * r->NFX) * sizeof(double);
+    r->plane_i = (size_t)(nxg + 3 + r->ipad) * (nyg + 4) * (size_t)((P.hybrid_riemann ? 3 : 2) + 6 * r->NIS + 9 * r->NFX) * sizeof(double);
     r->use_tma = tma_ok(P);
     const double* dx = geom->dx;
     for (int d = 0; d < 3; ++d) { r->hdtd[d] = 0.5 * dt / dx[d]; r->cdtd[d] = dt / dx[d] / 3.0; }
@@ -503,7 +507,8 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
         std::memset(&srcq, 0, sizeof(srcq));
         if (r->have_src) { srcq = make_a4(p, sbx); p += sbx.npts() * NSRCQ; }
         const size_t ni = ibx.npts();
-        const A4 fd = make_a4(p, ibx); p += ni * 2;
+        const int NFD = P.hybrid_riemann ? 3 : 2;      // flattening, div u [, shock flag]
+        const A4 fd = make_a4(p, ibx); p += ni * NFD;
         TraceArgs ta;
         for (int d = 0; d < 3; ++d) {
             ta.qm[d] = make_a4(p, ibx); p += ni * NIS;
@@ -524,7 +529,9 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
             tm.end(r->have_src ? 2 : 1); }
         {   LaunchBox lb = make_lb(obx);
             tm.begin(1);
-            k_flat_div<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb); ++launches; tm.end(1);
+            if (P.hybrid_riemann) k_flat_div<true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb, r->osrc);
+            else k_flat_div<false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb, r->osrc);
+            ++launches; tm.end(1);
             if (use_tma) {
                 tm.begin(2);
                 rc = launch_trace_riemann_all(P, np, ta, qs, qbx_a, fd, F1, tb, dt, r->have_src ? &srcq : nullptr, st);
@@ -548,11 +555,11 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
         if (!use_tma) {
             LaunchBox lb = make_lb(grow(nb[0], 0, 1, 1));
             tm.begin(3);
-            k_riemann1<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb);
+            k_riemann1<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd);
             lb = make_lb(grow(nb[1], 1, 0, 1));
-            k_riemann1<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb);
+            k_riemann1<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd);
             lb = make_lb(grow(nb[2], 1, 1, 0));
-            k_riemann1<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb); launches += 3; tm.end(3); }
+            k_riemann1<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb, fd); launches += 3; tm.end(3); }
         // F^{N|T}: box = nodal(N) grown by one in the third direction
         if (use_tma) {
             tm.begin(4);
@@ -563,17 +570,17 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
         {   LaunchBox lb;
             tm.begin(4);
             lb = make_lb(grow(nb[0], 0, 0, 1));   // F^{x|y}
-            k_trans_riemann<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], F2[0][1], lb, cdtd[1]);
+            k_trans_riemann<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], F2[0][1], lb, cdtd[1], fd);
             lb = make_lb(grow(nb[0], 0, 1, 0));   // F^{x|z}
-            k_trans_riemann<0, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[2], F2[0][2], lb, cdtd[2]);
+            k_trans_riemann<0, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[2], F2[0][2], lb, cdtd[2], fd);
             lb = make_lb(grow(nb[1], 0, 0, 1));   // F^{y|x}
-            k_trans_riemann<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], F2[1][0], lb, cdtd[0]);
+            k_trans_riemann<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], F2[1][0], lb, cdtd[0], fd);
             lb = make_lb(grow(nb[1], 1, 0, 0));   // F^{y|z}
-            k_trans_riemann<1, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[2], F2[1][2], lb, cdtd[2]);
+            k_trans_riemann<1, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[2], F2[1][2], lb, cdtd[2], fd);
             lb = make_lb(grow(nb[2], 0, 1, 0));   // F^{z|x}
-            k_trans_riemann<2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[0], F2[2][0], lb, cdtd[0]);
+            k_trans_riemann<2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[0], F2[2][0], lb, cdtd[0], fd);
             lb = make_lb(grow(nb[2], 1, 0, 0));   // F^{z|y}
-            k_trans_riemann<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1]); launches += 6; tm.end(6); }
+            k_trans_riemann<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1], fd); launches += 6; tm.end(6); }
         // final fluxes overwrite the (now dead) first-pass flux storage
         if (use_tma) {
             tm.begin(5);

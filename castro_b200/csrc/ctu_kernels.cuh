@@ -79,7 +79,8 @@ static __global__ void __launch_bounds__(TPB) k_ctoprim(const DevPar P, const A4
 // ------------------------------------------------------------------------------------------------
 // flattening (flatten.H:6-155; zones of obx) and node-centred div(u) (advection_util.cpp:330-347; nodes of obx)
 // ------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(TPB) k_flat_div(const DevPar P, const A4 qs, const A4 fd, const LaunchBox lb) {
+template <bool HYB>
+static __global__ void __launch_bounds__(TPB) k_flat_div(const DevPar P, const A4 qs, const A4 fd, const LaunchBox lb, const A4 usrc) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
     const long oq = qs.idx(i, j, k), of = fd.idx(i, j, k);
@@ -113,6 +114,39 @@ static __global__ void __launch_bounds__(TPB) k_flat_div(const DevPar P, const A
     double vy = 0.25 * (qv[0] - qv[-sj] + qv[-sk] - qv[-sj - sk] + qv[-1] - qv[-1 - sj] + qv[-1 - sk] - qv[-1 - sj - sk]) * dyinv;
     double wz = 0.25 * (qw[0] - qw[-sk] + qw[-sj] - qw[-sj - sk] + qw[-1] - qw[-1 - sk] + qw[-1 - sj] - qw[-1 - sj - sk]) * dzinv;
     fd.at(of, 1) = ux + vy + wz;
+    // Castro::shock (advection_util.cpp:61-200; hybrid Riemann solver only): |grad P . v| / (|v| P) > threshold and div u < 0
+    if (HYB) {
+        double div_u = 0.0;
+        div_u += 0.5 * (qu[1] - qu[-1]) * dxinv;
+        div_u += 0.5 * (qv[sj] - qv[-sj]) * dyinv;
+        div_u += 0.5 * (qw[sk] - qw[-sk]) * dzinv;
+        double dP_x = 0.5 * (pp[1] - pp[-1]);
+        double dP_y = 0.5 * (pp[sj] - pp[-sj]);
+        double dP_z = 0.5 * (pp[sk] - pp[-sk]);
+        if (P.shock_detection_include_sources == 1) {
+            double sx = 0.0, sy = 0.0, sz = 0.0;     // the conserved old-time momentum sources (zero without source terms)
+            if (usrc.p) {
+                const long os = usrc.idx(i, j, k);
+                const double* __restrict__ mx = usrc.p + os + UMX * usrc.sn;
+                const double* __restrict__ my = usrc.p + os + UMY * usrc.sn;
+                const double* __restrict__ mz = usrc.p + os + UMZ * usrc.sn;
+                sx = mx[1] + 2.0 * mx[0] + mx[-1];
+                sy = my[usrc.sj] + 2.0 * my[0] + my[-usrc.sj];
+                sz = mz[usrc.sk] + 2.0 * mz[0] + mz[-usrc.sk];
+            } else {
+                sx = 0.0 + 2.0 * 0.0 + 0.0; sy = sx; sz = sx;
+            }
+            dP_x += -0.25 * P.dx[0] * sx;
+            dP_y += -0.25 * P.dx[1] * sy;
+            dP_z += -0.25 * P.dx[2] * sz;
+        }
+        const double u0 = qu[0], v0 = qv[0], w0 = qw[0];
+        const double vel = sqrt(u0 * u0 + v0 * v0 + w0 * w0);
+        double g = 0.0;
+        if (vel != 0.0) g = fabs(dP_x * u0 + dP_y * v0 + dP_z * w0) / vel;
+        g /= pp[0];
+        fd.at(of, 2) = (g > P.shock_detection_threshold && div_u < 0.0) ? 1.0 : 0.0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -408,7 +442,8 @@ static __global__ void __launch_bounds__(TPB) k_trace(const DevPar P, const A4 q
 // ------------------------------------------------------------------------------------------------
 template <int DIR, class XM, class XP>
 __device__ __forceinline__ void solve_face(const DevPar& P, const double* qm, const double* qp, const A4& qs, int i, int j, int k,
-                                           XM xm, XP xp, double* F, double& ugd, double& pgd, PassiveUpwind& pu) {
+                                           XM xm, XP xp, double* F, double& ugd, double& pgd, PassiveUpwind& pu, const A4& fd) {
+    pu.hll = 0;
     const long oq = qs.idx(i, j, k);
     const long om = oq - ((DIR == 0) ? 1 : (DIR == 1) ? qs.sj : qs.sk);
     const double cr = qs.at(oq, QS_C), cl = qs.at(om, QS_C);
@@ -424,9 +459,15 @@ __device__ __forceinline__ void solve_face(const DevPar& P, const double* qm, co
     } else {
         riemann_hllc<MathExact, DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, F, ugd, pgd, pu);
     }
+    if (P.hybrid_riemann) {      // HLL flux next to a detected shock (riemann.cpp:144-197)
+        const long of = fd.idx(i, j, k);
+        const long ofm = of - ((DIR == 0) ? 1 : (DIR == 1) ? fd.sj : fd.sk);
+        if (static_cast<int>(fd.at(ofm, 2) + fd.at(of, 2)) >= 1) hll_flux<MathExact, DIR>(qm, qp, cl, cr, F, pu);
+    }
 }
 
 __device__ __forceinline__ double passive_flux(const DevPar& P, const PassiveUpwind& pu, double Xm, double Xp) {
+    if (pu.hll) return passive_flux_hll(pu, Xm, Xp);
     return (P.riemann_solver == 0) ? passive_flux_cgf(pu, Xm, Xp) : passive_flux_hllc(pu, Xm, Xp);
 }
 
@@ -437,7 +478,8 @@ __device__ __forceinline__ void load6(const A4& a, long off, double* q) {
 
 // first-pass fluxes (Castro_ctu_hydro.cpp:674,745,817)
 template <int DIR>
-static __global__ void __launch_bounds__(TPB) k_riemann1(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Fo, const LaunchBox lb) {
+static __global__ void __launch_bounds__(TPB) k_riemann1(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Fo, const LaunchBox lb,
+                                                  const A4 fd) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
     const long o = qm.idx(i, j, k);
@@ -446,7 +488,7 @@ static __global__ void __launch_bounds__(TPB) k_riemann1(const DevPar P, const A
     load6(qm, o, ql);
     load6(qp, o, qr);
     solve_face<DIR>(P, ql, qr, qs, i, j, k, [&](int ip) { return qm.at(o, IS_X + ip); }, [&](int ip) { return qp.at(o, IS_X + ip); },
-                    F, ugd, pgd, pu);
+                    F, ugd, pgd, pu, fd);
     const long of = Fo.idx(i, j, k);
 #pragma unroll
     for (int n = 0; n < 6; ++n) Fo.at(of, n) = F[n];
@@ -475,7 +517,7 @@ __device__ __forceinline__ bool trans_reset(const DevPar& P, double rho, double 
 //   reference: trans_single(...) + cmpflx_plus_godunov(...), Castro_ctu_hydro.cpp:699-880 and :895-1080
 template <int N, int T>
 static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Ft, const A4 Fo,
-                                                       const LaunchBox lb, const double cdtdx) {
+                                                       const LaunchBox lb, const double cdtdx, const A4 fd) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
     const long o = qm.idx(i, j, k);
@@ -531,7 +573,7 @@ static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, co
     }
     double F[6], ugd, pgd;
     PassiveUpwind pu;
-    solve_face<N>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu);
+    solve_face<N>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu, fd);
     const long of = Fo.idx(i, j, k);
 #pragma unroll
     for (int n = 0; n < 6; ++n) Fo.at(of, n) = F[n];
@@ -613,7 +655,7 @@ static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 q
     }
     double F[6], ugd, pgd;
     PassiveUpwind pu;
-    solve_face<N>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu);
+    solve_face<N>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu, fd);
 
     // apply_av (advection_util.cpp:354-419): div1 = difmag * min(0, <div u> over the 4 nodes of the face)
     const long od = fd.idx(i, j, k);

@@ -583,6 +583,8 @@ void ctu_params_defaults(ctu_params_t* p) {
     p->nspec = 1; p->naux = 0; p->nadv = 0;
     p->aion[0] = 1.0; p->zion[0] = 1.0;
     p->do_grav = 0; p->grav_source_type = 4; p->const_grav = 0.0;
+    p->shock_detection_include_sources = 1;
+    p->shock_detection_threshold = 0.6666666666666666666666;
 }
 
 // Castro::variableSetUp, Source/driver/Castro_setup.cpp:226-285 (+ eos_init, Microphysics interfaces/eos.H:17-50)
@@ -688,6 +690,8 @@ int ctu_parse_inputs(const char* path, const char* overrides, ctu_params_t* par,
     gi("castro.check_dt_before_advance", par->check_dt_before_advance); gi("castro.check_dt_after_advance", par->check_dt_after_advance);
     gd("eos.eos_gamma", par->eos_gamma); gi("eos.eos_assume_neutral", par->eos_assume_neutral);
     gd("network.small_x", par->small_x);
+    gi("castro.shock_detection_include_sources", par->shock_detection_include_sources);
+    gd("castro.shock_detection_threshold", par->shock_detection_threshold);
     gi("castro.do_grav", par->do_grav); gi("castro.grav_source_type", par->grav_source_type); gd("gravity.const_grav", par->const_grav);
     int nc[3] = {32, 32, 32};
     gi3("amr.n_cell", nc);

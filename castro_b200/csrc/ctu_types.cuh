@@ -71,6 +71,8 @@ inline A4 make_a4(double* p, const Box3& b) { return make_a4(p, b.lo, b.hi); }
 // parameters passed by value to kernels
 struct DevPar {
     int riemann_solver, use_flattening, ppm_do_limiting, first_order_hydro;
+    int hybrid_riemann, shock_detection_include_sources;
+    double shock_detection_threshold;
     int transverse_use_eos, transverse_reset_density, transverse_reset_rhoe;
     int eos_assume_neutral;
     int nspec, naux, nadv, npassive, nstate;

@@ -77,7 +77,7 @@ typedef struct ctu_params_t {
     int riemann_solver;            /* 0 = CGF (riemannus), 2 = HLLC */
     int use_flattening;
     int ppm_do_limiting;
-    int hybrid_riemann;            /* 0 only */
+    int hybrid_riemann;            /* 1: HLL fluxes on faces next to a detected shock (riemann.cpp:144-197) */
     int transverse_use_eos;
     int transverse_reset_density;
     int transverse_reset_rhoe;
@@ -110,6 +110,9 @@ typedef struct ctu_params_t {
     int do_grav;                   /* 0 = pure hydro */
     int grav_source_type;          /* 1..4 (default 4), Castro_gravity.cpp:316-690 */
     double const_grav;             /* ConstantGrav: acceleration along the LAST dimension (z in 3-D) */
+    /* hybrid Riemann solver (castro.hybrid_riemann = 1): Castro::shock (advection_util.cpp:61-200) + HLL::HLL in shocked zones */
+    int shock_detection_include_sources;   /* default 1 */
+    double shock_detection_threshold;      /* default 2/3 */
 } ctu_params_t;
 
 /* opaque scratch arena (replaces The_Async_Arena() temporaries of Castro_ctu_hydro.cpp:147-189) */

@@ -45,6 +45,9 @@ CASES = {
     # edge-state thermodynamics options (reset_edge_state_thermo + the EOS / (rho e) branches of trans_single/final)
     "sedov16_hllc_eos": (16, 20, [20], ["castro.riemann_solver=2", "castro.transverse_use_eos=1", "castro.transverse_reset_rhoe=1"]),
     "sedov16_cgf_rhoe": (16, 20, [20], ["castro.riemann_solver=0", "castro.transverse_reset_rhoe=1"]),
+    # hybrid Riemann solver (SURVEY §8 a6 + the HLL half of a14b): Castro::shock + HLL fluxes next to shocked zones
+    "sedov16_hllc_hybrid": (16, 20, [1, 20], ["castro.riemann_solver=2", "castro.hybrid_riemann=1"]),
+    "sedov16_cgf_hybrid": (16, 40, [40], ["castro.riemann_solver=0", "castro.hybrid_riemann=1"]),
 }
 
 

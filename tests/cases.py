@@ -35,6 +35,8 @@ CASES = {
     "sedov_24x16x8_cgf": dict(n_cell=(24, 16, 8), solver=0, geom=dict(probhi=(1.5, 1.0, 0.5))),
     "sedov16_hllc_eos": dict(n_cell=(16, 16, 16), solver=2, par=dict(transverse_use_eos=1, transverse_reset_rhoe=1)),
     "sedov16_cgf_rhoe": dict(n_cell=(16, 16, 16), solver=0, par=dict(transverse_reset_rhoe=1)),
+    "sedov16_hllc_hybrid": dict(n_cell=(16, 16, 16), solver=2, par=dict(hybrid_riemann=1)),
+    "sedov16_cgf_hybrid": dict(n_cell=(16, 16, 16), solver=0, par=dict(hybrid_riemann=1)),
 }
 
 
