@@ -14,6 +14,7 @@
 #   oracle/_ref/Castro3d_sedov.ex        serial, -O3, no FMA  (parity oracle, golden generator)
 #   oracle/_ref/Castro3d_sedov_omp.ex    OpenMP build         (CPU baseline for bench.py)
 #   oracle/_ref/Castro3d_kh.ex           Kelvin-Helmholtz problem, serial (golden generator for the 2-passive path)
+#   oracle/_ref/Castro3d_sod.ex          Sod shock-tube problem in 3-D, serial (golden generator for BASELINE config[0])
 #   oracle/_ref/Castro3d_rt.ex           Rayleigh-Taylor problem with constant gravity, serial (golden generator for the source-term path).
 #                                        The reference's RT initial-data header does not compile with DIM=3 (an unqualified `L_x`,
 #                                        problem_initialize_state_data.H:50); the recipe qualifies that one identifier in the SCRATCH COPY of
@@ -43,6 +44,8 @@ if [ "$what" = all ] || [ "$what" = serial ]; then build Sedov Castro3d_sedov DI
 if [ "$what" = all ] || [ "$what" = omp ];    then build Sedov Castro3d_sedov_omp DIM=3 USE_OMP=TRUE; fi
 # KH as shipped: NUMADV := 1 in its GNUmakefile -> NUM_STATE = 9 (one advected scalar + one species): pins the 2-passive path
 if [ "$what" = all ] || [ "$what" = kh ];     then build KH Castro3d_kh DIM=3; fi
+# Sod shock tube (BASELINE config[0]) built in 3-D: the tube along x, y or z exercises the three directional code paths
+if [ "$what" = all ] || [ "$what" = sod ];    then build Sod Castro3d_sod DIM=3; fi
 if [ "$what" = all ] || [ "$what" = rt ]; then
   if [ ! -d "$W/Castro3d_rt" ]; then cp -r "$REF/Exec/hydro_tests/RT" "$W/Castro3d_rt"; fi
   sed -i 's/0.5e0_rt \* L_x/0.5e0_rt * problem::L_x/' "$W/Castro3d_rt/problem_initialize_state_data.H"

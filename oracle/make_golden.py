@@ -97,6 +97,18 @@ def run_case(name, n_cell, max_step, snaps, extra, exe=EXE, inputs=INPUTS, ncomp
         shutil.rmtree(wd)
 
 
+# Sod shock tube (BASELINE config[0]: PPM + CGF) run in 3-D with the tube along x, y and z (slip walls across, outflow along);
+# pins the three directional code paths and the wall boundaries.  Reference inputs files as shipped, single level.
+SOD_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_sod.ex")
+SOD_DIR = "/root/reference/Exec/hydro_tests/Sod"
+SOD_CASES = {
+    "sod_x_cgf": ("inputs-sod-x", (32, 8, 8), 30, [0, 30], ["castro.riemann_solver=0"]),
+    "sod_y_cgf": ("inputs-sod-y", (8, 32, 8), 30, [0, 30], ["castro.riemann_solver=0"]),
+    "sod_z_cgf": ("inputs-sod-z", (8, 8, 32), 30, [0, 30], ["castro.riemann_solver=0"]),
+    "sod_z_hllc": ("inputs-sod-z", (8, 8, 32), 30, [0, 30], ["castro.riemann_solver=2"]),
+}
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     for name, (n, ms, snaps, extra) in CASES.items():
@@ -111,3 +123,7 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case(name, n, ms, snaps, extra, exe=RT_EXE, inputs=RT_INPUTS, ncomp=8)
+    for name, (inp, n, ms, snaps, extra) in SOD_CASES.items():
+        if only and name not in only:
+            continue
+        run_case(name, n, ms, snaps, extra + ["amr.check_int=-1", "castro.sum_interval=-1"], exe=SOD_EXE, inputs=os.path.join(SOD_DIR, inp))

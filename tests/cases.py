@@ -94,3 +94,28 @@ def load_rt_case(name):
     geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), periodic=(1, 1, 0), lo_bc=(0, 0, 4), hi_bc=(0, 0, 4))
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
     return par, geom, g, snaps
+
+
+SOD_CASES = {
+    "sod_x_cgf": dict(solver=0, idir=1), "sod_y_cgf": dict(solver=0, idir=2), "sod_z_cgf": dict(solver=0, idir=3),
+    "sod_z_hllc": dict(solver=2, idir=3),
+}
+
+
+def load_sod_case(name):
+    """Sod shock tube in 3-D (Exec/hydro_tests/Sod/inputs-sod-{x,y,z}: gamma = 1.4, cfl 0.9, init_shrink 0.1, change_max 1.05,
+    outflow along the tube, slip walls across); goldens from the reference's Sod executable (oracle/make_golden.py SOD_CASES)."""
+    c = SOD_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    par = abi.default_params()
+    par.riemann_solver = c["solver"]
+    par.cfl, par.init_shrink, par.change_max = 0.9, 0.1, 1.05
+    par.eos_gamma, par.eos_assume_neutral = 1.4, 1
+    d = c["idir"] - 1
+    lo_bc = [4, 4, 4]
+    lo_bc[d] = 2
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), lo_bc=tuple(lo_bc), hi_bc=tuple(lo_bc))
+    prob = dict(p_l=1.0, u_l=0.0, rho_l=1.0, p_r=0.1, u_r=0.0, rho_r=0.125, idir=c["idir"], frac=0.5)
+    snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
+    return par, geom, prob, g, snaps

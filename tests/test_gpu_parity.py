@@ -504,3 +504,85 @@ def test_full_size_properties_sedov256():
     assert np.abs(U1[2] - U1[3].transpose(1, 0, 2)).max() <= 1e-12 * sc      # ymom(x,y,z) = zmom(x,z,y)
     # (e)
     assert np.isfinite(U1).all()
+
+
+@pytest.mark.parametrize("name", ["sod_x_cgf", "sod_y_cgf", "sod_z_cgf", "sod_z_hllc"])
+def test_sod_shock_tube_matches_reference_golden(name):
+    """BASELINE config[0] (Sod shock tube, PPM + CGF; one HLLC variant) in 3-D with the tube along x, y and z: the "Sod" problem hook
+    vs the reference's initial plotfile, then 30 steps of the full time loop vs the reference's final state, bit for bit; and the
+    tube must stay one-dimensional (no variation across it, no transverse momentum)."""
+    _torch()
+    from castro_b200 import lib
+    from cases import load_sod_case
+    par, geom, prob, g, snaps = load_sod_case(name)
+    lib.params_finalize(par)
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    sim = lib.Sim(par, geom, (0, 0, 0), tuple(n - 1 for n in n_cell))
+    sim.init_problem("Sod", prob)
+    assert_bitwise(sim.download(), g["U0"], name + " initial data")
+    n = snaps[-1]
+    rc, t, dt, hist = sim.advance(n)
+    assert rc == 0
+    U = sim.download()
+    assert_bitwise(U, g["U%d" % n], "%s step %d" % (name, n))
+    np.testing.assert_allclose(np.cumsum(np.concatenate([[0.0], hist])), g["times"][:n + 1], rtol=1e-14, atol=0)
+    d = prob["idir"] - 1                       # tube direction; array axes are [comp, z, y, x]
+    ax = 3 - d
+    prof = np.moveaxis(U, ax, 1).reshape(U.shape[0], U.shape[ax], -1)
+    assert np.all(prof == prof[:, :, :1]), "the tube is not one-dimensional any more"
+    for m in (1, 2, 3):
+        if m != 1 + d:
+            assert np.all(U[m] == 0.0)
+    sim.close()
+
+
+def _sod_exact(x, t, gamma=1.4, rl=1.0, pl=1.0, rr=0.125, pr=0.1, x0=0.5):
+    """exact solution of the Sod Riemann problem (left rarefaction, contact, right shock), density / velocity / pressure at (x, t)"""
+    g = gamma
+    cl, cr = np.sqrt(g * pl / rl), np.sqrt(g * pr / rr)
+
+    def f(p):   # u*_L(p) - u*_R(p)
+        ul = 2.0 * cl / (g - 1.0) * (1.0 - (p / pl) ** ((g - 1.0) / (2.0 * g)))
+        ur = (p - pr) * np.sqrt(2.0 / ((g + 1.0) * rr) / (p + (g - 1.0) / (g + 1.0) * pr))
+        return ul - ur
+    lo, hi = pr, pl
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if f(mid) > 0.0:
+            lo = mid
+        else:
+            hi = mid
+    ps = 0.5 * (lo + hi)
+    us = 2.0 * cl / (g - 1.0) * (1.0 - (ps / pl) ** ((g - 1.0) / (2.0 * g)))
+    rsl = rl * (ps / pl) ** (1.0 / g)
+    rsr = rr * ((ps / pr + (g - 1.0) / (g + 1.0)) / ((g - 1.0) / (g + 1.0) * ps / pr + 1.0))
+    shock = us * rsr / (rsr - rr) if rsr != rr else 0.0
+    csl = cl * (ps / pl) ** ((g - 1.0) / (2.0 * g))
+    xi = (x - x0) / t
+    rho = np.where(xi < -cl, rl, np.where(xi < us - csl, rl * (2.0 / (g + 1.0) - (g - 1.0) / ((g + 1.0) * cl) * xi) ** (2.0 / (g - 1.0)),
+                   np.where(xi < us, rsl, np.where(xi < shock, rsr, rr))))
+    return rho
+
+
+def test_sod_converges_to_exact_solution():
+    """physical sanity beyond bitwise parity (the reference ships Verification/sod-exact.out for the same purpose): the 128-zone
+    Sod tube at t = 0.2 against the exact Riemann solution, L1 density error < 1 %, for CGF and HLLC"""
+    _torch()
+    from castro_b200 import lib, abi
+    for solver in (0, 2):
+        par = abi.default_params()
+        par.riemann_solver = solver
+        par.cfl, par.init_shrink, par.change_max = 0.9, 0.1, 1.05
+        par.eos_gamma, par.eos_assume_neutral = 1.4, 1
+        lib.params_finalize(par)
+        n_cell = (128, 4, 4)
+        geom = abi.make_geom(n_cell, probhi=(1.0, 0.03125, 0.03125), lo_bc=(2, 4, 4), hi_bc=(2, 4, 4))
+        sim = lib.Sim(par, geom, (0, 0, 0), tuple(n - 1 for n in n_cell))
+        sim.init_problem("Sod", dict(p_l=1.0, u_l=0.0, rho_l=1.0, p_r=0.1, u_r=0.0, rho_r=0.125, idir=1, frac=0.5))
+        rc, t, dt, hist = sim.advance(10000, stop_time=0.2)
+        assert rc == 0 and abs(t - 0.2) < 1e-14 and 50 < len(hist) < 400
+        rho = sim.download()[0, 0, 0, :]
+        x = (np.arange(128) + 0.5) / 128.0
+        err = np.abs(rho - _sod_exact(x, t)).mean()
+        assert err < 0.01, "solver %d: L1 density error %g" % (solver, err)
+        sim.close()
