@@ -346,6 +346,69 @@ int kh_init(const ctu_params_t* par, const ctu_geom_t* g, const std::map<std::st
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// RT: Exec/hydro_tests/RT/problem_initialize.H + problem_initialize_state_data.H (3-D branch).  The density profile needs
+// sqrt / cos / tanh per zone: they are evaluated on the host with the libm the reference's CPU build uses (one pass over the
+// box), so the initial data are bit-identical to the reference's; the device kernel only scatters the result into the state.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_rt_init(const DevPar P, const double* __restrict__ rho_h, const double* __restrict__ eint_k, const A4 S,
+                                                 const LaunchBox lb, const double small_temp) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const long o = S.idx(i, j, k);
+    const double rho = rho_h[t];
+    S.at(o, URHO) = rho;
+    S.at(o, UMX) = 0.0; S.at(o, UMY) = 0.0; S.at(o, UMZ) = 0.0;
+    S.at(o, UEDEN) = eint_k[k - lb.lo2];
+    S.at(o, UEINT) = eint_k[k - lb.lo2];
+    S.at(o, UTEMP) = small_temp;
+    for (int ip = 0; ip < P.npassive; ++ip) S.at(o, UFA + ip) = 0.0;
+    S.at(o, P.UFS) = rho;
+}
+
+int rt_init(const ctu_params_t* par, const ctu_geom_t* g, const std::map<std::string, std::string>& kv, const DevPar& P,
+            const A4& S, const LaunchBox& lb, cudaStream_t st) {
+    const double frac = kv_d(kv, "frac", 0.5), rho_1 = kv_d(kv, "rho_1", 1.0), rho_2 = kv_d(kv, "rho_2", 2.0);
+    const double p0_base = kv_d(kv, "p0_base", 5.0);
+    double split[3];
+    for (int n = 0; n < 3; ++n) split[n] = frac * (g->problo[n] + g->probhi[n]);
+    const double L_x = g->probhi[0] - g->problo[0];
+    const double presmid = p0_base - rho_1 * split[2];
+    std::vector<double> rho((size_t)lb.n), eint(lb.nz);
+    for (unsigned kk = 0; kk < lb.nz; ++kk) {
+        const double z = g->problo[2] + g->dx[2] * (static_cast<double>(lb.lo2 + (int)kk) + 0.5);
+        double pres;
+        if (z < split[2]) pres = p0_base - rho_1 * z;
+        else pres = presmid - rho_2 * (z - split[2]);
+        eint[kk] = pres / (par->eos_gamma - 1.0);
+    }
+    for (unsigned jj = 0; jj < lb.ny; ++jj) {
+        const double y = g->problo[1] + g->dx[1] * (static_cast<double>(lb.lo1 + (int)jj) + 0.5);
+        for (unsigned ii = 0; ii < lb.nx; ++ii) {
+            const double x = g->problo[0] + g->dx[0] * (static_cast<double>(lb.lo0 + (int)ii) + 0.5);
+            const double a = 0.5e0 * L_x;
+            const double b = std::sqrt((x - split[0]) * (x - split[0]) + (y - split[1]) * (y - split[1]));
+            const double r2d = (a < b) ? a : b;                       // amrex::min
+            const double pertheight = 0.5 - 0.01 * std::cos(2.0 * M_PI * r2d / L_x);
+            for (unsigned kk = 0; kk < lb.nz; ++kk) {
+                const double z = g->problo[2] + g->dx[2] * (static_cast<double>(lb.lo2 + (int)kk) + 0.5);
+                rho[(size_t)kk * lb.nx * lb.ny + (size_t)jj * lb.nx + ii] =
+                    rho_1 + ((rho_2 - rho_1) / 2.0) * (1 + std::tanh((z - pertheight) / 0.005));
+            }
+        }
+    }
+    double *d_rho = nullptr, *d_e = nullptr;
+    CUDA_TRY(cudaMalloc(&d_rho, rho.size() * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_e, eint.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(d_rho, rho.data(), rho.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_e, eint.data(), eint.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_rt_init<<<nblk(lb.n), TPB, 0, st>>>(P, d_rho, d_e, S, lb, par->small_temp);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_rho); cudaFree(d_e);
+    return 0;
+}
+
 // Castro::initData tail (Castro.cpp:1186-1413): computeTemp -> enforce_consistent_e (:3215-3265) -> clean_state
 __global__ void __launch_bounds__(TPB) k_init_tail(const DevPar P, const A4 S, const LaunchBox lb) {
     int i, j, k;
@@ -623,6 +686,7 @@ int ctu_problem_init(const char* problem, const char* prob_params, const ctu_par
     if (name == "Sedov") rc = sedov_init(par, geom, kv, P, a, lb, st);
     else if (name == "Sod") rc = sod_init(par, geom, kv, P, a, lb, st);
     else if (name == "KH") rc = kh_init(par, geom, kv, P, a, lb, st);
+    else if (name == "RT") rc = rt_init(par, geom, kv, P, a, lb, st);
     else return CTU_ERR_BAD_ARG;
     if (rc) return rc;
     k_init_tail<<<nblk(lb.n), TPB, 0, st>>>(P, a, lb);

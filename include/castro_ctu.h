@@ -203,7 +203,7 @@ int ctu_halo_unpack(ctu_fab_t* S, const int lo[3], const int hi[3], const double
 /* ---- problem hooks (Exec/hydro_tests/<problem>/problem_initialize*.H) ------------------------ */
 /* Fills [lo,hi] of the DEVICE fab S with the named problem's initial data, then computeTemp, exactly like
  * Castro::initData (Castro.cpp:1149-1186).  prob_params: "key=value" pairs separated by blanks/newlines
- * (the `problem.*` namelist of the inputs file).  Known problems: "Sedov", "Sod", "KH". */
+ * (the `problem.*` namelist of the inputs file).  Known problems: "Sedov", "Sod", "KH", "RT". */
 int ctu_problem_init(const char* problem, const char* prob_params, const ctu_params_t* par,
                      const ctu_geom_t* geom, const int lo[3], const int hi[3], ctu_fab_t* S, void* stream);
 

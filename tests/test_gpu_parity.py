@@ -321,7 +321,8 @@ def test_rt_gravity_matches_reference_golden(name):
     lib.params_finalize(par)
     n_cell = tuple(int(x) for x in g["n_cell"])
     sim = lib.Sim(par, geom, (0, 0, 0), tuple(n - 1 for n in n_cell))
-    sim.upload(np.ascontiguousarray(g["U0"]))
+    sim.init_problem("RT", dict(frac=0.5, rho_1=1.0, rho_2=2.0, p0_base=5.0))       # the RT problem hook ...
+    assert_bitwise(sim.download(), g["U0"], name + " initial data")                 # ... against the reference's initial plotfile
     n = snaps[-1]
     rc, t, dt, hist = sim.advance(n)
     assert rc == 0 and len(hist) == n
