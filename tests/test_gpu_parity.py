@@ -587,3 +587,36 @@ def test_sod_converges_to_exact_solution():
         err = np.abs(rho - _sod_exact(x, t)).mean()
         assert err < 0.01, "solver %d: L1 density error %g" % (solver, err)
         sim.close()
+
+
+def test_exact_replay_path_is_exercised():
+    """the flux-stage kernels compute with the branch-free division / sqrt sequences and replay a tile with the IEEE operators when
+    an operand leaves their range (MathFast / MathExact).  The Sedov goldens contain such operands (round-off dust in the subnormal
+    range around the blast): this run must have replayed tiles AND still be bit-identical to the reference; a quiescent uniform
+    state must not replay anything (zero numerators are handled in the fast path)."""
+    _torch()
+    from castro_b200 import lib
+    par, geom, prob, g, snaps = load_case("sedov16_hllc_long")
+    lib.params_finalize(par)
+    sim = lib.Sim(par, geom, (0, 0, 0), (15, 15, 15))
+    sim.init_problem("Sedov", prob)
+    rc, t, dt, hist = sim.advance(snaps[-1])
+    assert rc == 0
+    assert_bitwise(sim.download(), g["U%d" % snaps[-1]], "sedov16_hllc_long")
+    assert lib.workspace_replays(sim.ws_handle) > 0, "expected some tiles to take the exact-replay path"
+    sim.close()
+    # uniform medium at rest: every quotient with a zero numerator stays on the fast path, and the state does not move
+    sim = lib.Sim(par, geom, (0, 0, 0), (15, 15, 15))
+    U0 = np.zeros((par.num_state, 16, 16, 16))
+    U0[0] = 1.0
+    U0[4] = U0[5] = 1.0 / (par.eos_gamma - 1.0)
+    U0[6] = 1.0
+    U0[7] = 1.0
+    sim.upload(U0)
+    rc, t, dt, hist = sim.advance(3)
+    assert rc == 0
+    assert lib.workspace_replays(sim.ws_handle) == 0
+    U1 = sim.download()
+    for m in (0, 1, 2, 3, 4, 5, 7):
+        assert np.array_equal(U0[m], U1[m]), "a uniform state at rest must stay exactly as it is (comp %d)" % m
+    sim.close()
