@@ -49,6 +49,7 @@ class Params(C.Structure):
         ("aion", DblS), ("zion", DblS),
         ("do_grav", C.c_int), ("grav_source_type", C.c_int), ("const_grav", C.c_double),
         ("shock_detection_include_sources", C.c_int), ("shock_detection_threshold", C.c_double),
+        ("riemann_shock_maxiter", C.c_int), ("riemann_cg_blend", C.c_int), ("riemann_pstar_tol", C.c_double),
     ]
 
     @property
@@ -91,6 +92,7 @@ def default_params():
     p.do_grav, p.grav_source_type, p.const_grav = 0, 4, 0.0
     p.shock_detection_include_sources = 1
     p.shock_detection_threshold = 0.6666666666666666666666
+    p.riemann_shock_maxiter, p.riemann_cg_blend, p.riemann_pstar_tol = 12, 2, 1.0e-5
     return p
 
 

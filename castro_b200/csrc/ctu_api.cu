@@ -89,6 +89,8 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
     P.hybrid_riemann = par->hybrid_riemann;
     P.shock_detection_include_sources = par->shock_detection_include_sources;
     P.shock_detection_threshold = par->shock_detection_threshold;
+    P.riemann_shock_maxiter = par->riemann_shock_maxiter; P.riemann_cg_blend = par->riemann_cg_blend;
+    P.riemann_pstar_tol = par->riemann_pstar_tol;
     P.transverse_use_eos = par->transverse_use_eos;
     P.transverse_reset_density = par->transverse_reset_density;
     P.transverse_reset_rhoe = par->transverse_reset_rhoe;
@@ -134,7 +136,8 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (p->nspec < 1 || p->nspec > CTU_MAX_SPEC || p->naux < 0 || p->nadv < 0 || p->nspec + p->naux + p->nadv > 3 * CTU_MAX_SPEC)
         return CTU_ERR_BAD_ARG;
     if (p->ppm_type != 1) return CTU_ERR_UNSUPPORTED;                           // PLM: SURVEY §8(f) rank 4
-    if (p->riemann_solver != 0 && p->riemann_solver != 2) return CTU_ERR_UNSUPPORTED;   // CG solver: not in the parity contract
+    if (p->riemann_solver < 0 || p->riemann_solver > 2) return CTU_ERR_UNSUPPORTED;
+    if (p->riemann_solver == 1 && (p->riemann_shock_maxiter < 6 || p->riemann_shock_maxiter > 40)) return CTU_ERR_BAD_ARG;   // HISTORY_SIZE
     if (p->limit_fluxes_on_small_dens || p->ppm_temp_fix || p->use_pslope || p->ppm_well_balanced)
         return CTU_ERR_UNSUPPORTED;
     if (p->eos_kind != 0) return CTU_ERR_UNSUPPORTED;                           // helmholtz: SURVEY §8(f) rank 2
@@ -162,6 +165,7 @@ bool tma_ok(const DevPar& P) {
     static const bool disabled = (std::getenv("CTU_NO_TMA") != nullptr);
     if (disabled || !P.gamc_const) return false;
     if (P.npassive != 1 && P.npassive != 2) return false;
+    if (P.riemann_solver == 1) return false; // the iterative Colella & Glaz solver lives in the register-staged family only
     if (P.hybrid_riemann) return false;      // the HLL blend lives in the register-staged family only (keeps the tile kernels lean)
     return tma::encode_fn() != nullptr;
 }

@@ -453,9 +453,12 @@ __device__ __forceinline__ void solve_face(const DevPar& P, const double* qm, co
     const bool sp_lo = P.lo_bc[DIR] >= 3 && P.lo_bc[DIR] <= 5, sp_hi = P.hi_bc[DIR] >= 3 && P.hi_bc[DIR] <= 5;
     double bnd_fac = 1.0;
     if ((idx == P.domlo[DIR] && sp_lo) || (idx == P.domhi[DIR] + 1 && sp_hi)) bnd_fac = 0.0;
+    auto xlf = [&](int n) { return xm(P.QFS_off + n); };
+    auto xrf = [&](int n) { return xp(P.QFS_off + n); };
     if (P.riemann_solver == 0) {
-        riemann_cgf<MathExact, DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac,
-                         [&](int n) { return xm(P.QFS_off + n); }, [&](int n) { return xp(P.QFS_off + n); }, F, ugd, pgd, pu);
+        riemann_cgf<MathExact, DIR, decltype(xlf), decltype(xrf), 0>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, xlf, xrf, F, ugd, pgd, pu);
+    } else if (P.riemann_solver == 1) {
+        riemann_cgf<MathExact, DIR, decltype(xlf), decltype(xrf), 1>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, xlf, xrf, F, ugd, pgd, pu);
     } else {
         riemann_hllc<MathExact, DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, F, ugd, pgd, pu);
     }
@@ -468,7 +471,7 @@ __device__ __forceinline__ void solve_face(const DevPar& P, const double* qm, co
 
 __device__ __forceinline__ double passive_flux(const DevPar& P, const PassiveUpwind& pu, double Xm, double Xp) {
     if (pu.hll) return passive_flux_hll(pu, Xm, Xp);
-    return (P.riemann_solver == 0) ? passive_flux_cgf(pu, Xm, Xp) : passive_flux_hllc(pu, Xm, Xp);
+    return (P.riemann_solver != 2) ? passive_flux_cgf(pu, Xm, Xp) : passive_flux_hllc(pu, Xm, Xp);
 }
 
 __device__ __forceinline__ void load6(const A4& a, long off, double* q) {

@@ -74,7 +74,7 @@ typedef struct ctu_geom_t {
 typedef struct ctu_params_t {
     /* hydrodynamics category, _cpp_parameters:36-297 */
     int ppm_type;                  /* 1 (PPM) only */
-    int riemann_solver;            /* 0 = CGF (riemannus), 2 = HLLC */
+    int riemann_solver;            /* 0 = CGF (riemannus), 1 = Colella & Glaz (riemanncg), 2 = HLLC */
     int use_flattening;
     int ppm_do_limiting;
     int hybrid_riemann;            /* 1: HLL fluxes on faces next to a detected shock (riemann.cpp:144-197) */
@@ -113,6 +113,10 @@ typedef struct ctu_params_t {
     /* hybrid Riemann solver (castro.hybrid_riemann = 1): Castro::shock (advection_util.cpp:61-200) + HLL::HLL in shocked zones */
     int shock_detection_include_sources;   /* default 1 */
     double shock_detection_threshold;      /* default 2/3 */
+    /* Colella & Glaz solver (castro.riemann_solver = 1; riemann_2shock_solvers.H:17-514) */
+    int riemann_shock_maxiter;             /* default 12 */
+    int riemann_cg_blend;                  /* default 2: bisection when the secant iteration does not converge */
+    double riemann_pstar_tol;              /* default 1e-5 */
 } ctu_params_t;
 
 /* opaque scratch arena (replaces The_Async_Arena() temporaries of Castro_ctu_hydro.cpp:147-189) */

@@ -48,6 +48,9 @@ CASES = {
     # hybrid Riemann solver (SURVEY §8 a6 + the HLL half of a14b): Castro::shock + HLL fluxes next to shocked zones
     "sedov16_hllc_hybrid": (16, 20, [1, 20], ["castro.riemann_solver=2", "castro.hybrid_riemann=1"]),
     "sedov16_cgf_hybrid": (16, 40, [40], ["castro.riemann_solver=0", "castro.hybrid_riemann=1"]),
+    # Colella & Glaz solver: secant iteration + the CPU build's bisection fallback
+    "sedov16_cg": (16, 40, [1, 40], ["castro.riemann_solver=1"]),
+    "sedov_24x16x8_cg": ((24, 16, 8), 12, [12], ["castro.riemann_solver=1", "geometry.prob_hi=1.5 1.0 0.5"]),
 }
 
 

@@ -37,6 +37,8 @@ CASES = {
     "sedov16_cgf_rhoe": dict(n_cell=(16, 16, 16), solver=0, par=dict(transverse_reset_rhoe=1)),
     "sedov16_hllc_hybrid": dict(n_cell=(16, 16, 16), solver=2, par=dict(hybrid_riemann=1)),
     "sedov16_cgf_hybrid": dict(n_cell=(16, 16, 16), solver=0, par=dict(hybrid_riemann=1)),
+    "sedov16_cg": dict(n_cell=(16, 16, 16), solver=1),
+    "sedov_24x16x8_cg": dict(n_cell=(24, 16, 8), solver=1, geom=dict(probhi=(1.5, 1.0, 0.5))),
 }
 
 
