@@ -87,6 +87,7 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
     P.ppm_do_limiting = par->ppm_do_limiting;
     P.first_order_hydro = par->first_order_hydro;
     P.hybrid_riemann = par->hybrid_riemann;
+    P.limit_fluxes_on_small_dens = par->limit_fluxes_on_small_dens;
     P.shock_detection_include_sources = par->shock_detection_include_sources;
     P.shock_detection_threshold = par->shock_detection_threshold;
     P.riemann_shock_maxiter = par->riemann_shock_maxiter; P.riemann_cg_blend = par->riemann_cg_blend;
@@ -138,7 +139,7 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (p->ppm_type != 1) return CTU_ERR_UNSUPPORTED;                           // PLM: SURVEY §8(f) rank 4
     if (p->riemann_solver < 0 || p->riemann_solver > 2) return CTU_ERR_UNSUPPORTED;
     if (p->riemann_solver == 1 && (p->riemann_shock_maxiter < 6 || p->riemann_shock_maxiter > 40)) return CTU_ERR_BAD_ARG;   // HISTORY_SIZE
-    if (p->limit_fluxes_on_small_dens || p->ppm_temp_fix || p->use_pslope || p->ppm_well_balanced)
+    if (p->ppm_temp_fix || p->use_pslope || p->ppm_well_balanced)
         return CTU_ERR_UNSUPPORTED;
     if (p->eos_kind != 0) return CTU_ERR_UNSUPPORTED;                           // helmholtz: SURVEY §8(f) rank 2
     if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
@@ -166,6 +167,7 @@ bool tma_ok(const DevPar& P) {
     if (disabled || !P.gamc_const) return false;
     if (P.npassive != 1 && P.npassive != 2) return false;
     if (P.riemann_solver == 1) return false; // the iterative Colella & Glaz solver lives in the register-staged family only
+    if (P.limit_fluxes_on_small_dens) return false;     // ditto the density-floor flux limiter
     if (P.hybrid_riemann) return false;      // the HLL blend lives in the register-staged family only (keeps the tile kernels lean)
     return tma::encode_fn() != nullptr;
 }
@@ -595,11 +597,11 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
         {   LaunchBox lb;
             tm.begin(5);
             lb = make_lb(nb[0]);
-            k_final<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F2[1][2], F2[2][1], fd, Sb, F1[0], lb, hdtd[1], hdtd[2]);
+            k_final<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F2[1][2], F2[2][1], fd, Sb, F1[0], lb, hdtd[1], hdtd[2], dt);
             lb = make_lb(nb[1]);
-            k_final<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F2[0][2], F2[2][0], fd, Sb, F1[1], lb, hdtd[0], hdtd[2]);
+            k_final<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F2[0][2], F2[2][0], fd, Sb, F1[1], lb, hdtd[0], hdtd[2], dt);
             lb = make_lb(nb[2]);
-            k_final<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F2[0][1], F2[1][0], fd, Sb, F1[2], lb, hdtd[0], hdtd[1]); launches += 3; tm.end(3); }
+            k_final<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F2[0][1], F2[1][0], fd, Sb, F1[2], lb, hdtd[0], hdtd[1], dt); launches += 3; tm.end(3); }
         {   UpdateArgs ua;
             for (int d = 0; d < 3; ++d) ua.F[d] = F1[d];
             ua.dtmin = ws->d_dtmin; ua.counters = ws->d_counters;

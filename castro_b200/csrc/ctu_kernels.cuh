@@ -590,7 +590,8 @@ static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, co
 //   F1 = F^{T1|T2}, F2 = F^{T2|T1};  c1 = dt/(2 dx_T1), c2 = dt/(2 dx_T2)
 template <int N>
 static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 F1, const A4 F2,
-                                               const A4 fd, const A4 U, const A4 Fo, const LaunchBox lb, const double c1, const double c2) {
+                                               const A4 fd, const A4 U, const A4 Fo, const LaunchBox lb, const double c1, const double c2,
+                                               const double dt) {
     constexpr int T1 = (N == 0) ? 1 : 0;
     constexpr int T2 = (N == 2) ? 1 : 2;
     int i, j, k;
@@ -677,6 +678,28 @@ static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 q
     for (int n = 0; n < 6; ++n) {
         const double div_var = div1 * (U.at(ou, n) - U.at(oum, n));
         F[n] += dL * div_var;
+    }
+    // limit_hydro_fluxes_on_small_dens (advection_util.cpp:543-645; default off): scale every flux of the face so that neither
+    // neighbour can be drained below 1.1 * small_dens even if all six of its faces evacuate it
+    double lf = 1.0;
+    bool limited = false;
+    if (P.limit_fluxes_on_small_dens == 1) {
+        const double density_floor = P.small_dens * 1.1;
+        const double vol = P.dx[0] * P.dx[1] * P.dx[2];
+        const double area = (N == 0) ? P.dx[1] * P.dx[2] : (N == 1) ? P.dx[0] * P.dx[2] : P.dx[0] * P.dx[1];
+        const double rhoR = U.at(ou, URHO), rhoL = U.at(oum, URHO);
+        double flux_coef = 1.0 / vol;
+        flux_coef *= dt * area;
+        const double drho = flux_coef * F[0];
+        if (rhoR >= density_floor && fabs(drho) > 0.0 && rhoR + 2 * 3 * drho < density_floor) {
+            lf = fabs((density_floor - rhoR) / (2 * 3 * drho)); limited = true;
+        } else if (rhoL >= density_floor && fabs(drho) > 0.0 && rhoL - 2 * 3 * drho < density_floor) {
+            lf = fabs((density_floor - rhoL) / (2 * 3 * drho)); limited = true;
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+        if (limited) F[n] = F[n] * lf;
         Fo.at(of, n) = F[n];
     }
     Fo.at(of, FX_UG) = ugd;
@@ -687,6 +710,7 @@ static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 q
         double f = passive_flux(P, pu, xm(ip), xp(ip));
         const double div_var = div1 * (U.at(ou, UFA + ip) - U.at(oum, UFA + ip));
         f += dL * div_var;
+        if (limited) f = f * lf;
         Fo.at(of, FX_X + ip) = f;
         if (ip >= P.QFS_off && ip < P.QFS_off + P.nspec) sum += f;
     }

@@ -71,7 +71,7 @@ inline A4 make_a4(double* p, const Box3& b) { return make_a4(p, b.lo, b.hi); }
 // parameters passed by value to kernels
 struct DevPar {
     int riemann_solver, use_flattening, ppm_do_limiting, first_order_hydro;
-    int hybrid_riemann, shock_detection_include_sources;
+    int hybrid_riemann, shock_detection_include_sources, limit_fluxes_on_small_dens;
     double shock_detection_threshold;
     int riemann_shock_maxiter, riemann_cg_blend;
     double riemann_pstar_tol;

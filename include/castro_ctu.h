@@ -81,7 +81,7 @@ typedef struct ctu_params_t {
     int transverse_use_eos;
     int transverse_reset_density;
     int transverse_reset_rhoe;
-    int limit_fluxes_on_small_dens; /* 0 only */
+    int limit_fluxes_on_small_dens; /* 1: density-floor flux limiter (advection_util.cpp:543-645) */
     int first_order_hydro;
     int ppm_temp_fix;              /* 0 only */
     int use_pslope;                /* 0 only */

@@ -51,6 +51,8 @@ CASES = {
     # Colella & Glaz solver: secant iteration + the CPU build's bisection fallback
     "sedov16_cg": (16, 40, [1, 40], ["castro.riemann_solver=1"]),
     "sedov_24x16x8_cg": ((24, 16, 8), 12, [12], ["castro.riemann_solver=1", "geometry.prob_hi=1.5 1.0 0.5"]),
+    # density-floor flux limiter (advection_util.cpp:543-645) with a floor high enough for the evacuated centre to reach it
+    "sedov16_hllc_limit": (16, 60, [60], ["castro.riemann_solver=2", "castro.limit_fluxes_on_small_dens=1", "castro.small_dens=0.3"]),
 }
 
 

@@ -39,6 +39,7 @@ CASES = {
     "sedov16_cgf_hybrid": dict(n_cell=(16, 16, 16), solver=0, par=dict(hybrid_riemann=1)),
     "sedov16_cg": dict(n_cell=(16, 16, 16), solver=1),
     "sedov_24x16x8_cg": dict(n_cell=(24, 16, 8), solver=1, geom=dict(probhi=(1.5, 1.0, 0.5))),
+    "sedov16_hllc_limit": dict(n_cell=(16, 16, 16), solver=2, par=dict(limit_fluxes_on_small_dens=1, small_dens=0.3)),
 }
 
 
