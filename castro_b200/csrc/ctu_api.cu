@@ -92,6 +92,7 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
     P.shock_detection_threshold = par->shock_detection_threshold;
     P.riemann_shock_maxiter = par->riemann_shock_maxiter; P.riemann_cg_blend = par->riemann_cg_blend;
     P.riemann_pstar_tol = par->riemann_pstar_tol;
+    P.ppm_type = par->ppm_type; P.plm_iorder = par->plm_iorder; P.plm_limiter = par->plm_limiter;
     P.transverse_use_eos = par->transverse_use_eos;
     P.transverse_reset_density = par->transverse_reset_density;
     P.transverse_reset_rhoe = par->transverse_reset_rhoe;
@@ -136,7 +137,8 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (!p) return CTU_ERR_BAD_ARG;
     if (p->nspec < 1 || p->nspec > CTU_MAX_SPEC || p->naux < 0 || p->nadv < 0 || p->nspec + p->naux + p->nadv > 3 * CTU_MAX_SPEC)
         return CTU_ERR_BAD_ARG;
-    if (p->ppm_type != 1) return CTU_ERR_UNSUPPORTED;                           // PLM: SURVEY §8(f) rank 4
+    if (p->ppm_type != 0 && p->ppm_type != 1) return CTU_ERR_UNSUPPORTED;
+    if (p->ppm_type == 0 && (p->plm_iorder < 1 || p->plm_iorder > 2 || p->plm_limiter < 1 || p->plm_limiter > 2)) return CTU_ERR_BAD_ARG;
     if (p->riemann_solver < 0 || p->riemann_solver > 2) return CTU_ERR_UNSUPPORTED;
     if (p->riemann_solver == 1 && (p->riemann_shock_maxiter < 6 || p->riemann_shock_maxiter > 40)) return CTU_ERR_BAD_ARG;   // HISTORY_SIZE
     if (p->ppm_temp_fix || p->use_pslope || p->ppm_well_balanced)
@@ -166,6 +168,7 @@ bool tma_ok(const DevPar& P) {
     static const bool disabled = (std::getenv("CTU_NO_TMA") != nullptr);
     if (disabled || !P.gamc_const) return false;
     if (P.npassive != 1 && P.npassive != 2) return false;
+    if (P.ppm_type == 0) return false;       // piecewise-linear reconstruction: register-staged family
     if (P.riemann_solver == 1) return false; // the iterative Colella & Glaz solver lives in the register-staged family only
     if (P.limit_fluxes_on_small_dens) return false;     // ditto the density-floor flux limiter
     if (P.hybrid_riemann) return false;      // the HLL blend lives in the register-staged family only (keeps the tile kernels lean)
@@ -545,7 +548,17 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
                 launches += 3; tm.end(3);
             } else {
             tm.begin(2);
-            if (r->have_src) {
+            if (P.ppm_type == 0) {
+                if (r->have_src) {
+                    k_trace_plm<0, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                    k_trace_plm<1, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                    k_trace_plm<2, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                } else {
+                    k_trace_plm<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                    k_trace_plm<1, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                    k_trace_plm<2, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                }
+            } else if (r->have_src) {
                 k_trace<0, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
                 k_trace<1, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
                 k_trace<2, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);

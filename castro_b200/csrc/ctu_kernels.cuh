@@ -437,6 +437,184 @@ static __global__ void __launch_bounds__(TPB) k_trace(const DevPar P, const A4 q
 }
 
 // ------------------------------------------------------------------------------------------------
+// Piecewise-linear reconstruction (castro.ppm_type = 0): uslope (slope.H:29-118) and Castro::trace_plm (trace_plm.cpp:17-393),
+// 3-D Cartesian, with the half-step source terms; enforce_reflect_states is folded into the stores like in k_trace.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double plm_uslope(const DevPar& P, double qm2, double qm1, double q0, double qp1, double qp2, double flatn,
+                                             bool bnd_lo_reflect, bool bnd_hi_reflect) {
+    if (P.plm_iorder == 1) return 0.0;
+    if (P.plm_limiter == 1) {
+        const double dlft = 2.0 * (q0 - qm1), drgt = 2.0 * (qp1 - q0);
+        const double dcen = 0.25 * (dlft + drgt);
+        const double dsgn = copysign(1.0, dcen);
+        const double slop = smin(fabs(dlft), fabs(drgt));
+        const double dlim = dlft * drgt >= 0.0 ? slop : 0.0;
+        return flatn * dsgn * smin(dlim, fabs(dcen));
+    }
+    if (bnd_lo_reflect) {
+        qm2 = -qp1;
+        qm1 = -3.0 * q0 + qp1 - 0.125 * (qp2 + qp1);
+    }
+    if (bnd_hi_reflect) {
+        qp2 = -qm1;
+        qp1 = -3.0 * q0 + qm1 - 0.125 * (qm2 + qm1);
+    }
+    const double dlftp1 = 2.0 * (qp1 - q0), drgtp1 = 2.0 * (qp2 - qp1);
+    double dcen = 0.25 * (dlftp1 + drgtp1);
+    double dsgn = copysign(1.0, dcen);
+    double slop = smin(fabs(dlftp1), fabs(drgtp1));
+    double dlim = dlftp1 * drgtp1 >= 0.0 ? slop : 0.0;
+    const double dfp1 = dsgn * smin(dlim, fabs(dcen));
+    const double dlftm1 = 2.0 * (qm1 - qm2), drgtm1 = 2.0 * (q0 - qm1);
+    dcen = 0.25 * (dlftm1 + drgtm1);
+    dsgn = copysign(1.0, dcen);
+    slop = smin(fabs(dlftm1), fabs(drgtm1));
+    dlim = dlftm1 * drgtm1 >= 0.0 ? slop : 0.0;
+    const double dfm1 = dsgn * smin(dlim, fabs(dcen));
+    const double dlft = drgtm1, drgt = dlftp1;
+    dcen = 0.25 * (dlft + drgt);
+    dsgn = copysign(1.0, dcen);
+    slop = smin(fabs(dlft), fabs(drgt));
+    dlim = dlft * drgt >= 0.0 ? slop : 0.0;
+    const double dq1 = (4.0 / 3.0) * dcen - (1.0 / 6.0) * (dfp1 + dfm1);
+    return flatn * dsgn * smin(dlim, fabs(dq1));
+}
+
+template <int DIR, bool SRC>
+static __global__ void __launch_bounds__(TPB) k_trace_plm(const DevPar P, const A4 qs, const A4 fd, const TraceArgs ta, const LaunchBox lb,
+                                                   const double dt, const A4 srcq) {
+    constexpr int QUN = QS_U + DIR;
+    constexpr int QUT = QS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
+    constexpr int QUTT = QS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
+    constexpr int IUN = IS_U + DIR;
+    constexpr int IUT = IS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
+    constexpr int IUTT = IS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long oq = qs.idx(i, j, k);
+    const double flat = fd(i, j, k, 0);
+    const int idx = (DIR == 0) ? i : (DIR == 1) ? j : k;
+    const long st = (DIR == 0) ? 1 : (DIR == 1) ? qs.sj : qs.sk;
+    const A4& qm = ta.qm[DIR];
+    const A4& qp = ta.qp[DIR];
+    const long op = qp.idx(i, j, k);
+    const long om = op + ((DIR == 0) ? 1 : (DIR == 1) ? qp.sj : qp.sk);
+    const bool sym_lo = P.lo_bc[DIR] == 3, sym_hi = P.hi_bc[DIR] == 3;
+    bool do_p = idx >= ta.vlo[DIR];
+    bool do_m = idx <= ta.vhi[DIR];
+    const bool refl_lo = do_p && sym_lo && idx == P.domlo[DIR];
+    const bool refl_hi = do_m && sym_hi && idx + 1 == P.domhi[DIR] + 1;
+    if (sym_lo && idx + 1 == P.domlo[DIR]) do_m = false;
+    if (sym_hi && idx == P.domhi[DIR] + 1) do_p = false;
+    const bool lo_bc_test = sym_lo && idx == P.domlo[DIR];
+    const bool hi_bc_test = sym_hi && idx == P.domhi[DIR];
+    const double dtdL = dt / P.dx[DIR];
+    const double* __restrict__ base = qs.p + oq;
+    const long sn = qs.sn;
+    const double cc = base[QS_C * sn];
+    const double csq = cc * cc;
+    const double rho = base[QS_RHO * sn];
+    const double un = base[QUN * sn], ut = base[QUT * sn], utt = base[QUTT * sn];
+    const double p = base[QS_P * sn];
+    const double rhoe = base[QS_RE * sn];
+    const double enth = (rhoe + p) / (rho * csq);
+    auto slope = [&](int comp, bool vtest) {
+        const double* __restrict__ a = base + comp * sn;
+        return plm_uslope(P, a[-2 * st], a[-st], a[0], a[st], a[2 * st], flat, lo_bc_test && vtest, hi_bc_test && vtest);
+    };
+    const double dq_rho = slope(QS_RHO, false), dq_un = slope(QUN, true), dq_ut = slope(QUT, false), dq_utt = slope(QUTT, false);
+    const double dq_p = slope(QS_P, false), dq_re = slope(QS_RE, false);
+    const double alpham = 0.5 * (dq_p / (rho * cc) - dq_un) * (rho / cc);
+    const double alphap = 0.5 * (dq_p / (rho * cc) + dq_un) * (rho / cc);
+    const double alpha0r = dq_rho - dq_p / csq;
+    const double alpha0e = dq_re - dq_p * enth;
+    const double e0 = un - cc, e1 = un, e2 = un + cc;
+    // half-step source terms (zero without sources: the additions are kept because they turn -0.0 into +0.0 like the reference)
+    double s_rho = 0.0, s_un = 0.0, s_ut = 0.0, s_utt = 0.0, s_p = 0.0, s_re = 0.0;
+    if (SRC) {
+        const long os = srcq.idx(i, j, k);
+        s_rho = srcq.at(os, QS_RHO); s_un = srcq.at(os, QUN); s_ut = srcq.at(os, QUT); s_utt = srcq.at(os, QUTT);
+        s_p = srcq.at(os, QS_P); s_re = srcq.at(os, QS_RE);
+    }
+    if (do_p) {   // right state on face i (trace_plm.cpp:209-248)
+        const double ref_fac = 0.5 * (1.0 + dtdL * smin(e0, 0.0));
+        const double rho_ref = rho - ref_fac * dq_rho, un_ref = un - ref_fac * dq_un, ut_ref = ut - ref_fac * dq_ut;
+        const double utt_ref = utt - ref_fac * dq_utt, p_ref = p - ref_fac * dq_p, rhoe_ref = rhoe - ref_fac * dq_re;
+        const double trace_fac0 = 0.0;
+        const double trace_fac1 = 0.25 * dtdL * (e0 - e1) * (1.0 - copysign(1.0, e1));
+        const double trace_fac2 = 0.25 * dtdL * (e0 - e2) * (1.0 - copysign(1.0, e2));
+        const double apright = trace_fac2 * alphap, amright = trace_fac0 * alpham;
+        const double azrright = trace_fac1 * alpha0r, azeright = trace_fac1 * alpha0e;
+        const double azut1rght = trace_fac1 * dq_ut, azutt1rght = trace_fac1 * dq_utt;
+        double o_rho = smax(P.small_dens, rho_ref + apright + amright + azrright);
+        double o_un = un_ref + (apright - amright) * cc / rho;
+        double o_ut = ut_ref + azut1rght;
+        double o_utt = utt_ref + azutt1rght;
+        double o_p = smax(P.small_pres, p_ref + (apright + amright) * csq);
+        double o_re = rhoe_ref + (apright + amright) * enth * csq + azeright;
+        o_rho += 0.5 * dt * s_rho;
+        o_rho = smax(P.small_dens, o_rho);
+        o_un += 0.5 * dt * s_un;
+        o_ut += 0.5 * dt * s_ut;
+        o_utt += 0.5 * dt * s_utt;
+        o_re += 0.5 * dt * s_re;
+        o_p += 0.5 * dt * s_p;
+        qp.at(op, IS_RHO) = o_rho; qp.at(op, IUN) = o_un; qp.at(op, IUT) = o_ut; qp.at(op, IUTT) = o_utt;
+        qp.at(op, IS_P) = o_p; qp.at(op, IS_RE) = o_re;
+        if (refl_lo) {
+            qm.at(op, IS_RHO) = o_rho; qm.at(op, IUN) = -o_un; qm.at(op, IUT) = o_ut; qm.at(op, IUTT) = o_utt;
+            qm.at(op, IS_P) = o_p; qm.at(op, IS_RE) = o_re;
+        }
+    }
+    if (do_m) {   // left state on face i+1 (trace_plm.cpp:252-320)
+        const double ref_fac = 0.5 * (1.0 - dtdL * smax(e2, 0.0));
+        const double rho_ref = rho + ref_fac * dq_rho, un_ref = un + ref_fac * dq_un, ut_ref = ut + ref_fac * dq_ut;
+        const double utt_ref = utt + ref_fac * dq_utt, p_ref = p + ref_fac * dq_p, rhoe_ref = rhoe + ref_fac * dq_re;
+        const double trace_fac0 = 0.25 * dtdL * (e2 - e0) * (1.0 + copysign(1.0, e0));
+        const double trace_fac1 = 0.25 * dtdL * (e2 - e1) * (1.0 + copysign(1.0, e1));
+        const double trace_fac2 = 0.0;
+        const double apleft = trace_fac2 * alphap, amleft = trace_fac0 * alpham;
+        const double azrleft = trace_fac1 * alpha0r, azeleft = trace_fac1 * alpha0e;
+        const double azut1left = trace_fac1 * dq_ut, azutt1left = trace_fac1 * dq_utt;
+        double o_rho = smax(P.small_dens, rho_ref + apleft + amleft + azrleft);
+        double o_un = un_ref + (apleft - amleft) * cc / rho;
+        double o_ut = ut_ref + azut1left;
+        double o_utt = utt_ref + azutt1left;
+        double o_p = smax(P.small_pres, p_ref + (apleft + amleft) * csq);
+        double o_re = rhoe_ref + (apleft + amleft) * enth * csq + azeleft;
+        o_rho = smax(P.small_dens, o_rho + 0.5 * dt * s_rho);
+        o_un += 0.5 * dt * s_un;
+        o_ut += 0.5 * dt * s_ut;
+        o_utt += 0.5 * dt * s_utt;
+        o_re += 0.5 * dt * s_re;
+        o_p += 0.5 * dt * s_p;
+        qm.at(om, IS_RHO) = o_rho; qm.at(om, IUN) = o_un; qm.at(om, IUT) = o_ut; qm.at(om, IUTT) = o_utt;
+        qm.at(om, IS_P) = o_p; qm.at(om, IS_RE) = o_re;
+        if (refl_hi) {
+            qp.at(om, IS_RHO) = o_rho; qp.at(om, IUN) = -o_un; qp.at(om, IUT) = o_ut; qp.at(om, IUTT) = o_utt;
+            qp.at(om, IS_P) = o_p; qp.at(om, IS_RE) = o_re;
+        }
+    }
+    for (int ip = 0; ip < P.npassive; ++ip) {   // trace_plm.cpp:361-389
+        const double* __restrict__ a = base + (QS_X + ip) * sn;
+        const double s0 = a[0];
+        const double dX = plm_uslope(P, a[-2 * st], a[-st], s0, a[st], a[2 * st], flat, false, false);
+        if (do_p) {
+            const double spzero = un >= 0.0 ? -1.0 : un * dtdL;
+            const double v = s0 + 0.5 * (-1.0 - spzero) * dX;
+            qp.at(op, IS_X + ip) = v;
+            if (refl_lo) qm.at(op, IS_X + ip) = v;
+        }
+        if (do_m) {
+            const double spzero = un >= 0.0 ? un * dtdL : 1.0;
+            const double v = s0 + 0.5 * (1.0 - spzero) * dX;
+            qm.at(om, IS_X + ip) = v;
+            if (refl_hi) qp.at(om, IS_X + ip) = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Riemann driver shared by the three flux kernels: Castro::cmpflx_plus_godunov (riemann.cpp:15-200)
 //   XM(ip)/XP(ip): passive ip (mass fraction etc.) of the minus/plus state
 // ------------------------------------------------------------------------------------------------

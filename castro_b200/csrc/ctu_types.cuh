@@ -73,7 +73,7 @@ struct DevPar {
     int riemann_solver, use_flattening, ppm_do_limiting, first_order_hydro;
     int hybrid_riemann, shock_detection_include_sources, limit_fluxes_on_small_dens;
     double shock_detection_threshold;
-    int riemann_shock_maxiter, riemann_cg_blend;
+    int riemann_shock_maxiter, riemann_cg_blend, ppm_type, plm_iorder, plm_limiter;
     double riemann_pstar_tol;
     int transverse_use_eos, transverse_reset_density, transverse_reset_rhoe;
     int eos_assume_neutral;

@@ -73,7 +73,7 @@ typedef struct ctu_geom_t {
 /* castro.* (Source/driver/_cpp_parameters), eos.* and network table values read by the hot path */
 typedef struct ctu_params_t {
     /* hydrodynamics category, _cpp_parameters:36-297 */
-    int ppm_type;                  /* 1 (PPM) only */
+    int ppm_type;                  /* 1 = PPM (default), 0 = piecewise linear (trace_plm.cpp, slope.H) */
     int riemann_solver;            /* 0 = CGF (riemannus), 1 = Colella & Glaz (riemanncg), 2 = HLLC */
     int use_flattening;
     int ppm_do_limiting;
@@ -117,6 +117,9 @@ typedef struct ctu_params_t {
     int riemann_shock_maxiter;             /* default 12 */
     int riemann_cg_blend;                  /* default 2: bisection when the secant iteration does not converge */
     double riemann_pstar_tol;              /* default 1e-5 */
+    /* piecewise-linear reconstruction (castro.ppm_type = 0; slope.H:29-118) */
+    int plm_iorder;                        /* 1 = piecewise constant, 2 = piecewise linear (default) */
+    int plm_limiter;                       /* 1 = 2nd-order MC, 2 = 4th-order MC (default) */
 } ctu_params_t;
 
 /* opaque scratch arena (replaces The_Async_Arena() temporaries of Castro_ctu_hydro.cpp:147-189) */

@@ -52,6 +52,9 @@ CASES = {
     "sedov16_cg": (16, 40, [1, 40], ["castro.riemann_solver=1"]),
     "sedov_24x16x8_cg": ((24, 16, 8), 12, [12], ["castro.riemann_solver=1", "geometry.prob_hi=1.5 1.0 0.5"]),
     # density-floor flux limiter (advection_util.cpp:543-645) with a floor high enough for the evacuated centre to reach it
+    # piecewise-linear reconstruction (ppm_type = 0: trace_plm.cpp + slope.H), 4th-order MC limiter and the 2nd-order one
+    "sedov16_plm_hllc": (16, 30, [30], ["castro.riemann_solver=2", "castro.ppm_type=0"]),
+    "sedov16_plm_cgf_lim1": (16, 30, [30], ["castro.riemann_solver=0", "castro.ppm_type=0", "castro.plm_limiter=1"]),
     "sedov16_hllc_limit": (16, 60, [60], ["castro.riemann_solver=2", "castro.limit_fluxes_on_small_dens=1", "castro.small_dens=0.3"]),
 }
 
@@ -111,6 +114,11 @@ SOD_CASES = {
     "sod_y_cgf": ("inputs-sod-y", (8, 32, 8), 30, [0, 30], ["castro.riemann_solver=0"]),
     "sod_z_cgf": ("inputs-sod-z", (8, 8, 32), 30, [0, 30], ["castro.riemann_solver=0"]),
     "sod_z_hllc": ("inputs-sod-z", (8, 8, 32), 30, [0, 30], ["castro.riemann_solver=2"]),
+    # symmetry (reflecting) boundaries at both ends of the tube, long enough for the shock and the rarefaction to bounce:
+    # enforce_reflect_states, reflect_odd ghost fill and (PLM) the reflecting-boundary slopes of uslope
+    "sod_x_symm_ppm": ("inputs-sod-x", (32, 8, 8), 70, [0, 70], ["castro.riemann_solver=0", "castro.lo_bc=3 4 4", "castro.hi_bc=3 4 4"]),
+    "sod_y_symm_plm": ("inputs-sod-y", (8, 32, 8), 70, [0, 70], ["castro.riemann_solver=2", "castro.ppm_type=0", "castro.lo_bc=4 3 4",
+                                                           "castro.hi_bc=4 3 4"]),
 }
 
 

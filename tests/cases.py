@@ -39,6 +39,8 @@ CASES = {
     "sedov16_cgf_hybrid": dict(n_cell=(16, 16, 16), solver=0, par=dict(hybrid_riemann=1)),
     "sedov16_cg": dict(n_cell=(16, 16, 16), solver=1),
     "sedov_24x16x8_cg": dict(n_cell=(24, 16, 8), solver=1, geom=dict(probhi=(1.5, 1.0, 0.5))),
+    "sedov16_plm_hllc": dict(n_cell=(16, 16, 16), solver=2, par=dict(ppm_type=0)),
+    "sedov16_plm_cgf_lim1": dict(n_cell=(16, 16, 16), solver=0, par=dict(ppm_type=0, plm_limiter=1)),
     "sedov16_hllc_limit": dict(n_cell=(16, 16, 16), solver=2, par=dict(limit_fluxes_on_small_dens=1, small_dens=0.3)),
 }
 
@@ -102,6 +104,7 @@ def load_rt_case(name):
 SOD_CASES = {
     "sod_x_cgf": dict(solver=0, idir=1), "sod_y_cgf": dict(solver=0, idir=2), "sod_z_cgf": dict(solver=0, idir=3),
     "sod_z_hllc": dict(solver=2, idir=3),
+    "sod_x_symm_ppm": dict(solver=0, idir=1, tube_bc=3), "sod_y_symm_plm": dict(solver=2, idir=2, tube_bc=3, par=dict(ppm_type=0)),
 }
 
 
@@ -116,7 +119,9 @@ def load_sod_case(name):
     par.eos_gamma, par.eos_assume_neutral = 1.4, 1
     d = c["idir"] - 1
     lo_bc = [4, 4, 4]
-    lo_bc[d] = 2
+    lo_bc[d] = c.get("tube_bc", 2)
+    for k, v in c.get("par", {}).items():
+        setattr(par, k, v)
     n_cell = tuple(int(x) for x in g["n_cell"])
     geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), lo_bc=tuple(lo_bc), hi_bc=tuple(lo_bc))
     prob = dict(p_l=1.0, u_l=0.0, rho_l=1.0, p_r=0.1, u_r=0.0, rho_r=0.125, idir=c["idir"], frac=0.5)

@@ -77,7 +77,7 @@ def test_oracle_gravity_sources_match_rt_golden(name):
     np.testing.assert_allclose(np.cumsum(np.concatenate([[0.0], hist])), g["times"][:n + 1], rtol=1e-14, atol=0)
 
 
-@pytest.mark.parametrize("name", ["sod_x_cgf", "sod_y_cgf", "sod_z_cgf", "sod_z_hllc"])
+@pytest.mark.parametrize("name", ["sod_x_cgf", "sod_y_cgf", "sod_z_cgf", "sod_z_hllc", "sod_x_symm_ppm", "sod_y_symm_plm"])
 def test_oracle_sod_shock_tube_matches_golden(name):
     """BASELINE config[0]: the Sod shock tube (PPM + CGF; one HLLC variant), run in 3-D with the tube along x, y and z -- the oracle,
     started from the reference's own initial plotfile, must land bit for bit on the reference's state after 30 steps (pins the three
