@@ -50,7 +50,7 @@ class Params(C.Structure):
         ("do_grav", C.c_int), ("grav_source_type", C.c_int), ("const_grav", C.c_double),
         ("shock_detection_include_sources", C.c_int), ("shock_detection_threshold", C.c_double),
         ("riemann_shock_maxiter", C.c_int), ("riemann_cg_blend", C.c_int), ("riemann_pstar_tol", C.c_double),
-        ("plm_iorder", C.c_int), ("plm_limiter", C.c_int),
+        ("plm_iorder", C.c_int), ("plm_limiter", C.c_int), ("pslope_cutoff_density", C.c_double),
     ]
 
     @property
@@ -95,6 +95,7 @@ def default_params():
     p.shock_detection_threshold = 0.6666666666666666666666
     p.riemann_shock_maxiter, p.riemann_cg_blend, p.riemann_pstar_tol = 12, 2, 1.0e-5
     p.plm_iorder, p.plm_limiter = 2, 2
+    p.pslope_cutoff_density = -1.e20
     return p
 
 

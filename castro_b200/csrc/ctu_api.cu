@@ -92,6 +92,7 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
     P.shock_detection_threshold = par->shock_detection_threshold;
     P.riemann_shock_maxiter = par->riemann_shock_maxiter; P.riemann_cg_blend = par->riemann_cg_blend;
     P.riemann_pstar_tol = par->riemann_pstar_tol;
+    P.use_pslope = par->use_pslope; P.ppm_well_balanced = par->ppm_well_balanced; P.pslope_cutoff_density = par->pslope_cutoff_density;
     P.ppm_type = par->ppm_type; P.plm_iorder = par->plm_iorder; P.plm_limiter = par->plm_limiter;
     P.transverse_use_eos = par->transverse_use_eos;
     P.transverse_reset_density = par->transverse_reset_density;
@@ -141,7 +142,7 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (p->ppm_type == 0 && (p->plm_iorder < 1 || p->plm_iorder > 2 || p->plm_limiter < 1 || p->plm_limiter > 2)) return CTU_ERR_BAD_ARG;
     if (p->riemann_solver < 0 || p->riemann_solver > 2) return CTU_ERR_UNSUPPORTED;
     if (p->riemann_solver == 1 && (p->riemann_shock_maxiter < 6 || p->riemann_shock_maxiter > 40)) return CTU_ERR_BAD_ARG;   // HISTORY_SIZE
-    if (p->ppm_temp_fix || p->use_pslope || p->ppm_well_balanced)
+    if (p->ppm_temp_fix)
         return CTU_ERR_UNSUPPORTED;
     if (p->eos_kind != 0) return CTU_ERR_UNSUPPORTED;                           // helmholtz: SURVEY §8(f) rank 2
     if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
@@ -168,6 +169,7 @@ bool tma_ok(const DevPar& P) {
     static const bool disabled = (std::getenv("CTU_NO_TMA") != nullptr);
     if (disabled || !P.gamc_const) return false;
     if (P.npassive != 1 && P.npassive != 2) return false;
+    if (P.use_pslope || P.ppm_well_balanced) return false;   // hydrostatic-pressure-aware reconstruction: register-staged family
     if (P.ppm_type == 0) return false;       // piecewise-linear reconstruction: register-staged family
     if (P.riemann_solver == 1) return false; // the iterative Colella & Glaz solver lives in the register-staged family only
     if (P.limit_fluxes_on_small_dens) return false;     // ditto the density-floor flux limiter

@@ -240,8 +240,10 @@ __device__ __forceinline__ void trace_sources(const DevPar& P, const double* __r
 template <int DIR, bool SRC>
 __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq, long st, double flat, double dtdL,
                                           const A4& qm, const A4& qp, long op, long om, bool do_p, bool do_m,
-                                          bool refl_lo, bool refl_hi, const SrcAdd& sa) {
+                                          bool refl_lo, bool refl_hi, const SrcAdd& sa, const double* __restrict__ sb, long ssn, long sst) {
 #define SA(x) (SRC ? sa.x : 0.0)
+// velocity-source terms: fac * hdt * I_src with fac = 0 in hydrostatic zones of the well-balanced method (trace_ppm.cpp:490)
+#define SAU(x) (SRC ? (wb_hse ? 0.0 * sa.x : sa.x) : 0.0)
     constexpr int QUN = QS_U + DIR;
     constexpr int QUT = QS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
     constexpr int QUTT = QS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
@@ -275,7 +277,44 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
     pb.integ(un + cc, dtdL, Ip_un2, Im_un2);
 
     double Ip_p0, Im_p0, Ip_p1, Im_p1, Ip_p2, Im_p2;
-    CTU_RECON(QS_P);
+    double p_m_hse = 0.0, p_p_hse = 0.0;      // HSE pressure on the interfaces (castro.ppm_well_balanced)
+    bool wb_hse = false;
+    if (P.use_pslope || P.ppm_well_balanced) {
+        // ppm_reconstruct_pslope (ppm.H:171-244) + trace_ppm.cpp:248-267: limit the pressure with the hydrostatic part removed;
+        // the source of the normal velocity (g) comes from the primitive source array (zero without sources)
+        const double* __restrict__ a = base + QS_P * sn;
+        const double* __restrict__ r = base + QS_RHO * sn;
+        const double dL = P.dx[DIR];
+        double src[5], pz[5], rz[5];
+#pragma unroll
+        for (int m = -2; m <= 2; ++m) {
+            src[m + 2] = sb ? sb[QUN * ssn + m * sst] : 0.0;
+            pz[m + 2] = a[m * st];
+            rz[m + 2] = r[m * st];
+        }
+        const double p0_hse = pz[2];
+        const double pp1_hse = p0_hse + 0.25 * dL * (rz[2] + rz[3]) * (src[2] + src[3]);
+        const double pp2_hse = pp1_hse + 0.25 * dL * (rz[3] + rz[4]) * (src[3] + src[4]);
+        const double pm1_hse = p0_hse - 0.25 * dL * (rz[2] + rz[1]) * (src[2] + src[1]);
+        const double pm2_hse = pm1_hse - 0.25 * dL * (rz[1] + rz[0]) * (src[1] + src[0]);
+        const double pph = p0_hse + 0.5 * dL * rz[2] * src[2];
+        const double pmh = p0_hse - 0.5 * dL * rz[2] * src[2];
+        const bool ptest = p0_hse < 0.0 || pp1_hse < 0.0 || pp2_hse < 0.0 || pm1_hse < 0.0 || pm2_hse < 0.0 || pph < 0.0 || pmh < 0.0;
+        const bool do_hse = !ptest && rz[2] >= P.pslope_cutoff_density;
+        if (do_hse) ppm_reconstruct(P, pz[0] - pm2_hse, pz[1] - pm1_hse, pz[2] - p0_hse, pz[3] - pp1_hse, pz[4] - pp2_hse, flat, sm, sp);
+        else ppm_reconstruct(P, pz[0], pz[1], pz[2], pz[3], pz[4], flat, sm, sp);
+        if (do_hse && !P.ppm_well_balanced) { sp += pph; sm += pmh; }
+        if (do_hse && P.ppm_well_balanced) {
+            pb.set(sm, sp, 0.0);
+            p_m_hse = pz[2] - 0.5 * dL * rz[2] * src[2];
+            p_p_hse = pz[2] + 0.5 * dL * rz[2] * src[2];
+            wb_hse = true;
+        } else {
+            pb.set(sm, sp, pz[2]);
+        }
+    } else {
+        CTU_RECON(QS_P);
+    }
     pb.integ(un - cc, dtdL, Ip_p0, Im_p0);
     pb.integ(un, dtdL, Ip_p1, Im_p1);
     pb.integ(un + cc, dtdL, Ip_p2, Im_p2);
@@ -318,23 +357,23 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
     // because it turns -0.0 into +0.0 exactly like the reference does.
     if (do_p) {   // plus state on face i (trace_ppm.cpp:494-581)
         double rho_ref = Im_rho0 + SA(m_rho0);
-        double un_ref = Im_un0 + SA(m_un0);
+        double un_ref = Im_un0 + SAU(m_un0);
         double p_ref = Im_p0 + SA(m_p0);
         double rhoe_g_ref = Im_re0 + SA(m_re0);
         double gam_g_ref = Im_gc0;
         rho_ref = smax(rho_ref, P.small_dens);
         double rho_ref_inv = 1.0 / rho_ref;
         p_ref = smax(p_ref, P.small_pres);
-        double csq_ref = gam_g_ref * (0.0 + p_ref) * rho_ref_inv;
+        double csq_ref = gam_g_ref * (p_m_hse + p_ref) * rho_ref_inv;
         double cc_ref = sqrt(csq_ref);
         double cc_ref_inv = 1.0 / cc_ref;
-        double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
-        double d_um = un_ref - Im_un0 - SA(m_un0);
+        double h_g_ref = ((p_m_hse + p_ref) + rhoe_g_ref) * rho_ref_inv;
+        double d_um = un_ref - Im_un0 - SAU(m_un0);
         double dptotm = p_ref - Im_p0 - SA(m_p0);
         double drho = rho_ref - Im_rho1 - SA(m_rho1);
         double dptot = p_ref - Im_p1 - SA(m_p1);
         double drhoe_g = rhoe_g_ref - Im_re1 - SA(m_re1);
-        double d_up = un_ref - Im_un2 - SA(m_un2);
+        double d_up = un_ref - Im_un2 - SAU(m_un2);
         double dptotp = p_ref - Im_p2 - SA(m_p2);
         double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
         double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
@@ -347,7 +386,7 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
         const double o_rho = smax(P.small_dens, rho_ref + alphap + alpham + alpha0r);
         const double o_un = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
         const double o_re = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
-        const double o_p = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
+        const double o_p = smax(P.small_pres, p_m_hse + p_ref + (alphap + alpham) * csq_ref);
         const double o_ut = Im_ut + SA(m_ut);
         const double o_utt = Im_utt + SA(m_utt);
         qp.at(op, IS_RHO) = o_rho; qp.at(op, IUN) = o_un; qp.at(op, IS_RE) = o_re; qp.at(op, IS_P) = o_p;
@@ -359,23 +398,23 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
     }
     if (do_m) {   // minus state on face i+1 (trace_ppm.cpp:583-675)
         double rho_ref = Ip_rho2 + SA(p_rho2);
-        double un_ref = Ip_un2 + SA(p_un2);
+        double un_ref = Ip_un2 + SAU(p_un2);
         double p_ref = Ip_p2 + SA(p_p2);
         double rhoe_g_ref = Ip_re2 + SA(p_re2);
         double gam_g_ref = Ip_gc2;
         rho_ref = smax(rho_ref, P.small_dens);
         double rho_ref_inv = 1.0 / rho_ref;
         p_ref = smax(p_ref, P.small_pres);
-        double csq_ref = gam_g_ref * (0.0 + p_ref) * rho_ref_inv;
+        double csq_ref = gam_g_ref * (p_p_hse + p_ref) * rho_ref_inv;
         double cc_ref = sqrt(csq_ref);
         double cc_ref_inv = 1.0 / cc_ref;
-        double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
-        double d_um = un_ref - Ip_un0 - SA(p_un0);
+        double h_g_ref = ((p_p_hse + p_ref) + rhoe_g_ref) * rho_ref_inv;
+        double d_um = un_ref - Ip_un0 - SAU(p_un0);
         double dptotm = p_ref - Ip_p0 - SA(p_p0);
         double drho = rho_ref - Ip_rho1 - SA(p_rho1);
         double dptot = p_ref - Ip_p1 - SA(p_p1);
         double drhoe_g = rhoe_g_ref - Ip_re1 - SA(p_re1);
-        double d_up = un_ref - Ip_un2 - SA(p_un2);
+        double d_up = un_ref - Ip_un2 - SAU(p_un2);
         double dptotp = p_ref - Ip_p2 - SA(p_p2);
         double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
         double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
@@ -388,7 +427,7 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
         const double o_rho = smax(P.small_dens, rho_ref + alphap + alpham + alpha0r);
         const double o_un = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
         const double o_re = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
-        const double o_p = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
+        const double o_p = smax(P.small_pres, p_p_hse + p_ref + (alphap + alpham) * csq_ref);
         const double o_ut = Ip_ut + SA(p_ut);
         const double o_utt = Ip_utt + SA(p_utt);
         qm.at(om, IS_RHO) = o_rho; qm.at(om, IUN) = o_un; qm.at(om, IS_RE) = o_re; qm.at(om, IS_P) = o_p;
@@ -398,6 +437,7 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
             qp.at(om, IUT) = o_ut; qp.at(om, IUTT) = o_utt;
         }
     }
+#undef SAU
 #undef SA
 }
 
@@ -433,7 +473,9 @@ static __global__ void __launch_bounds__(TPB) k_trace(const DevPar P, const A4 q
         trace_sources<DIR>(P, srcq.p + srcq.idx(i, j, k), srcq.sn, sst, flat, qs.at(oq, QS_U + DIR), qs.at(oq, QS_C), dt / P.dx[DIR],
                            0.5 * dt, sa);
     }
-    trace_dir<DIR, SRC>(P, qs, oq, st, flat, dt / P.dx[DIR], qm, qp, op, om, do_p, do_m, refl_lo, refl_hi, sa);
+    const long sst_ = (DIR == 0) ? 1 : (DIR == 1) ? srcq.sj : srcq.sk;
+    trace_dir<DIR, SRC>(P, qs, oq, st, flat, dt / P.dx[DIR], qm, qp, op, om, do_p, do_m, refl_lo, refl_hi, sa,
+                        SRC ? srcq.p + srcq.idx(i, j, k) : nullptr, srcq.sn, sst_);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -523,7 +565,44 @@ static __global__ void __launch_bounds__(TPB) k_trace_plm(const DevPar P, const 
         return plm_uslope(P, a[-2 * st], a[-st], a[0], a[st], a[2 * st], flat, lo_bc_test && vtest, hi_bc_test && vtest);
     };
     const double dq_rho = slope(QS_RHO, false), dq_un = slope(QUN, true), dq_ut = slope(QUT, false), dq_utt = slope(QUTT, false);
-    const double dq_p = slope(QS_P, false), dq_re = slope(QS_RE, false);
+    double dq_p = slope(QS_P, false);
+    const double dq_re = slope(QS_RE, false);
+    if (P.use_pslope == 1 && P.plm_iorder != 1 && rho >= P.pslope_cutoff_density) {   // pslope (slope.H:120-245), trace_plm.cpp:177-190
+        const double* __restrict__ a = base + QS_P * sn;
+        const double* __restrict__ r = base + QS_RHO * sn;
+        const double dL = P.dx[DIR];
+        double src[5];
+#pragma unroll
+        for (int m = -2; m <= 2; ++m) src[m + 2] = SRC ? srcq.at(srcq.idx(i, j, k) + m * ((DIR == 0) ? 1 : (DIR == 1) ? srcq.sj : srcq.sk), QUN) : 0.0;
+        const double p0_hse = a[0];
+        const double pp1_hse = p0_hse + 0.25 * dL * (r[0] + r[st]) * (src[2] + src[3]);
+        const double pp2_hse = pp1_hse + 0.25 * dL * (r[st] + r[2 * st]) * (src[3] + src[4]);
+        const double pm1_hse = p0_hse - 0.25 * dL * (r[0] + r[-st]) * (src[2] + src[1]);
+        const double pm2_hse = pm1_hse - 0.25 * dL * (r[-st] + r[-2 * st]) * (src[1] + src[0]);
+        const double p0 = 0.0;
+        double pp1 = a[st] - pp1_hse, pp2 = a[2 * st] - pp2_hse, pm1 = a[-st] - pm1_hse, pm2 = a[-2 * st] - pm2_hse;
+        if (lo_bc_test) { pm1 = 0.0; pm2 = 0.0; }
+        if (hi_bc_test) { pp1 = 0.0; pp2 = 0.0; }
+        const double dlftp1 = pp1 - p0, drgtp1 = pp2 - pp1;
+        double dcen = 0.5 * (dlftp1 + drgtp1);
+        double dsgn = copysign(1.0, dcen);
+        double dlim = dlftp1 * drgtp1 >= 0.0 ? 2.0 * smin(fabs(dlftp1), fabs(drgtp1)) : 0.0;
+        const double dfp1 = dsgn * smin(dlim, fabs(dcen));
+        const double dlftm1 = pm1 - pm2, drgtm1 = p0 - pm1;
+        dcen = 0.5 * (dlftm1 + drgtm1);
+        dsgn = copysign(1.0, dcen);
+        dlim = dlftm1 * drgtm1 >= 0.0 ? 2.0 * smin(fabs(dlftm1), fabs(drgtm1)) : 0.0;
+        const double dfm1 = dsgn * smin(dlim, fabs(dcen));
+        const double dlft = drgtm1, drgt = dlftp1;
+        dcen = 0.5 * (dlft + drgt);
+        dsgn = copysign(1.0, dcen);
+        dlim = dlft * drgt >= 0.0 ? 2.0 * smin(fabs(dlft), fabs(drgt)) : 0.0;
+        const double dp1 = (4.0 / 3.0) * dcen - (1.0 / 6.0) * (dfp1 + dfm1);
+        dq_p = flat * dsgn * smin(dlim, fabs(dp1));
+        dq_p += r[0] * src[2] * dL;
+    } else if (P.use_pslope == 1 && P.plm_iorder == 1) {
+        dq_p = 0.0;
+    }
     const double alpham = 0.5 * (dq_p / (rho * cc) - dq_un) * (rho / cc);
     const double alphap = 0.5 * (dq_p / (rho * cc) + dq_un) * (rho / cc);
     const double alpha0r = dq_rho - dq_p / csq;

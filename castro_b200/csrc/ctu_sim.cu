@@ -650,6 +650,7 @@ void ctu_params_defaults(ctu_params_t* p) {
     p->shock_detection_threshold = 0.6666666666666666666666;
     p->riemann_shock_maxiter = 12; p->riemann_cg_blend = 2; p->riemann_pstar_tol = 1.0e-5;
     p->plm_iorder = 2; p->plm_limiter = 2;
+    p->pslope_cutoff_density = -1.e20;
 }
 
 // Castro::variableSetUp, Source/driver/Castro_setup.cpp:226-285 (+ eos_init, Microphysics interfaces/eos.H:17-50)
@@ -760,6 +761,7 @@ int ctu_parse_inputs(const char* path, const char* overrides, ctu_params_t* par,
     gd("castro.shock_detection_threshold", par->shock_detection_threshold);
     gi("castro.riemann_shock_maxiter", par->riemann_shock_maxiter); gi("castro.riemann_cg_blend", par->riemann_cg_blend);
     gd("castro.riemann_pstar_tol", par->riemann_pstar_tol);
+    gd("castro.pslope_cutoff_density", par->pslope_cutoff_density);
     gi("castro.plm_iorder", par->plm_iorder); gi("castro.plm_limiter", par->plm_limiter);
     gi("castro.do_grav", par->do_grav); gi("castro.grav_source_type", par->grav_source_type); gd("gravity.const_grav", par->const_grav);
     int nc[3] = {32, 32, 32};

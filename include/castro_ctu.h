@@ -84,8 +84,8 @@ typedef struct ctu_params_t {
     int limit_fluxes_on_small_dens; /* 1: density-floor flux limiter (advection_util.cpp:543-645) */
     int first_order_hydro;
     int ppm_temp_fix;              /* 0 only */
-    int use_pslope;                /* 0 only */
-    int ppm_well_balanced;         /* 0 only */
+    int use_pslope;                /* 1: subtract the hydrostatic pressure before limiting the pressure profile */
+    int ppm_well_balanced;         /* 1: trace the perturbational pressure (PPM only) */
     int source_term_predictor;
     double difmag;
     double small_dens, small_temp, small_pres, small_ener;
@@ -120,6 +120,8 @@ typedef struct ctu_params_t {
     /* piecewise-linear reconstruction (castro.ppm_type = 0; slope.H:29-118) */
     int plm_iorder;                        /* 1 = piecewise constant, 2 = piecewise linear (default) */
     int plm_limiter;                       /* 1 = 2nd-order MC, 2 = 4th-order MC (default) */
+    /* hydrostatic-pressure-aware reconstruction (castro.use_pslope / castro.ppm_well_balanced; ppm.H:171-244, slope.H:120-245) */
+    double pslope_cutoff_density;          /* default -1e20 */
 } ctu_params_t;
 
 /* opaque scratch arena (replaces The_Async_Arena() temporaries of Castro_ctu_hydro.cpp:147-189) */

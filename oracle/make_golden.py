@@ -71,6 +71,10 @@ RT_INPUTS = os.path.join(ROOT, "bench_inputs", "inputs.rt3d")
 RT_CASES = {
     "rt16_cgf": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=0"]),                                # grav_source_type = 4 (default)
     "rt16_hllc_gst2": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=2", "castro.grav_source_type=2"]),
+    # hydrostatic-pressure-aware reconstruction: use_pslope (PPM and PLM) and ppm_well_balanced
+    "rt16_pslope": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=0", "castro.use_pslope=1"]),
+    "rt16_wellbal": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=2", "castro.ppm_well_balanced=1"]),
+    "rt16_plm_pslope": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=0", "castro.ppm_type=0", "castro.use_pslope=1"]),
 }
 
 

@@ -83,6 +83,9 @@ def load_kh_case(name):
 RT_CASES = {
     "rt16_cgf": dict(solver=0, grav_source_type=4),
     "rt16_hllc_gst2": dict(solver=2, grav_source_type=2),
+    "rt16_pslope": dict(solver=0, grav_source_type=4, par=dict(use_pslope=1)),
+    "rt16_wellbal": dict(solver=2, grav_source_type=4, par=dict(ppm_well_balanced=1)),
+    "rt16_plm_pslope": dict(solver=0, grav_source_type=4, par=dict(ppm_type=0, use_pslope=1)),
 }
 
 
@@ -95,6 +98,8 @@ def load_rt_case(name):
     par.riemann_solver = c["solver"]
     par.cfl, par.init_shrink, par.change_max = 0.8, 0.3, 1.1
     par.do_grav, par.grav_source_type, par.const_grav = 1, c["grav_source_type"], -1.0
+    for k, v in c.get("par", {}).items():
+        setattr(par, k, v)
     n_cell = tuple(int(x) for x in g["n_cell"])
     geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), periodic=(1, 1, 0), lo_bc=(0, 0, 4), hi_bc=(0, 0, 4))
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
