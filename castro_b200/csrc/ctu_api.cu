@@ -92,6 +92,7 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
     P.shock_detection_threshold = par->shock_detection_threshold;
     P.riemann_shock_maxiter = par->riemann_shock_maxiter; P.riemann_cg_blend = par->riemann_cg_blend;
     P.riemann_pstar_tol = par->riemann_pstar_tol;
+    P.ppm_temp_fix = par->ppm_temp_fix;
     P.use_pslope = par->use_pslope; P.ppm_well_balanced = par->ppm_well_balanced; P.pslope_cutoff_density = par->pslope_cutoff_density;
     P.ppm_type = par->ppm_type; P.plm_iorder = par->plm_iorder; P.plm_limiter = par->plm_limiter;
     P.transverse_use_eos = par->transverse_use_eos;
@@ -142,8 +143,7 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (p->ppm_type == 0 && (p->plm_iorder < 1 || p->plm_iorder > 2 || p->plm_limiter < 1 || p->plm_limiter > 2)) return CTU_ERR_BAD_ARG;
     if (p->riemann_solver < 0 || p->riemann_solver > 2) return CTU_ERR_UNSUPPORTED;
     if (p->riemann_solver == 1 && (p->riemann_shock_maxiter < 6 || p->riemann_shock_maxiter > 40)) return CTU_ERR_BAD_ARG;   // HISTORY_SIZE
-    if (p->ppm_temp_fix)
-        return CTU_ERR_UNSUPPORTED;
+    if (p->ppm_temp_fix != 0 && p->ppm_temp_fix != 2) return CTU_ERR_UNSUPPORTED;   // 1 and 3 only exist in the MOL integrator
     if (p->eos_kind != 0) return CTU_ERR_UNSUPPORTED;                           // helmholtz: SURVEY §8(f) rank 2
     if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
     return 0;
@@ -169,6 +169,7 @@ bool tma_ok(const DevPar& P) {
     static const bool disabled = (std::getenv("CTU_NO_TMA") != nullptr);
     if (disabled || !P.gamc_const) return false;
     if (P.npassive != 1 && P.npassive != 2) return false;
+    if (P.ppm_temp_fix) return false;        // EOS re-sync of the interface states before each solve: register-staged family
     if (P.use_pslope || P.ppm_well_balanced) return false;   // hydrostatic-pressure-aware reconstruction: register-staged family
     if (P.ppm_type == 0) return false;       // piecewise-linear reconstruction: register-staged family
     if (P.riemann_solver == 1) return false; // the iterative Colella & Glaz solver lives in the register-staged family only
@@ -572,36 +573,42 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
             launches += 3; tm.end(3); } }
         const Box3 nb[3] = {[&] { Box3 b = tb; b.hi[0] += 1; return b; }(), [&] { Box3 b = tb; b.hi[1] += 1; return b; }(),
                             [&] { Box3 b = tb; b.hi[2] += 1; return b; }()};
-        // first-pass fluxes: cxbx = grow(xbx,(0,1,1)), cybx = grow(ybx,(1,0,1)), czbx = grow(zbx,(1,1,0))
-        if (!use_tma) {
-            LaunchBox lb = make_lb(grow(nb[0], 0, 1, 1));
-            tm.begin(3);
-            k_riemann1<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd);
-            lb = make_lb(grow(nb[1], 1, 0, 1));
-            k_riemann1<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd);
-            lb = make_lb(grow(nb[2], 1, 1, 0));
-            k_riemann1<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb, fd); launches += 3; tm.end(3); }
+        // first-pass fluxes: cxbx = grow(xbx,(0,1,1)), cybx = grow(ybx,(1,0,1)), czbx = grow(zbx,(1,1,0));
         // F^{N|T}: box = nodal(N) grown by one in the third direction
         if (use_tma) {
             tm.begin(4);
             rc = launch_trans2_all(P, np, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
             if (rc) return rc;
             launches += 3; tm.end(3);
-        } else
-        {   LaunchBox lb;
+        } else {
+            // register-staged family, in the reference's own order (Castro_ctu_hydro.cpp:667-880): F^x, the states it corrects, F^y, ...
+            // The order matters when castro.ppm_temp_fix = 2 re-syncs q?m / q?p in place during the first-pass solve.
+            LaunchBox lb;
+            tm.begin(3);
+            lb = make_lb(grow(nb[0], 0, 1, 1));
+            k_riemann1<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd); ++launches; tm.end(1);
+            tm.begin(4);
+            lb = make_lb(grow(nb[1], 0, 0, 1));   // F^{y|x}
+            k_trans_riemann<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], F2[1][0], lb, cdtd[0], fd);
+            lb = make_lb(grow(nb[2], 0, 1, 0));   // F^{z|x}
+            k_trans_riemann<2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[0], F2[2][0], lb, cdtd[0], fd); launches += 2; tm.end(2);
+            tm.begin(3);
+            lb = make_lb(grow(nb[1], 1, 0, 1));
+            k_riemann1<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd); ++launches; tm.end(1);
             tm.begin(4);
             lb = make_lb(grow(nb[0], 0, 0, 1));   // F^{x|y}
             k_trans_riemann<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], F2[0][1], lb, cdtd[1], fd);
+            lb = make_lb(grow(nb[2], 1, 0, 0));   // F^{z|y}
+            k_trans_riemann<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1], fd); launches += 2; tm.end(2);
+            tm.begin(3);
+            lb = make_lb(grow(nb[2], 1, 1, 0));
+            k_riemann1<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb, fd); ++launches; tm.end(1);
+            tm.begin(4);
             lb = make_lb(grow(nb[0], 0, 1, 0));   // F^{x|z}
             k_trans_riemann<0, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[2], F2[0][2], lb, cdtd[2], fd);
-            lb = make_lb(grow(nb[1], 0, 0, 1));   // F^{y|x}
-            k_trans_riemann<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], F2[1][0], lb, cdtd[0], fd);
             lb = make_lb(grow(nb[1], 1, 0, 0));   // F^{y|z}
-            k_trans_riemann<1, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[2], F2[1][2], lb, cdtd[2], fd);
-            lb = make_lb(grow(nb[2], 0, 1, 0));   // F^{z|x}
-            k_trans_riemann<2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[0], F2[2][0], lb, cdtd[0], fd);
-            lb = make_lb(grow(nb[2], 1, 0, 0));   // F^{z|y}
-            k_trans_riemann<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1], fd); launches += 6; tm.end(6); }
+            k_trans_riemann<1, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[2], F2[1][2], lb, cdtd[2], fd); launches += 2; tm.end(2);
+        }
         // final fluxes overwrite the (now dead) first-pass flux storage
         if (use_tma) {
             tm.begin(5);

@@ -698,9 +698,21 @@ static __global__ void __launch_bounds__(TPB) k_trace_plm(const DevPar P, const 
 //   XM(ip)/XP(ip): passive ip (mass fraction etc.) of the minus/plus state
 // ------------------------------------------------------------------------------------------------
 template <int DIR, class XM, class XP>
-__device__ __forceinline__ void solve_face(const DevPar& P, const double* qm, const double* qp, const A4& qs, int i, int j, int k,
+__device__ __forceinline__ void solve_face(const DevPar& P, double* qm, double* qp, const A4& qs, int i, int j, int k,
                                            XM xm, XP xp, double* F, double& ugd, double& pgd, PassiveUpwind& pu, const A4& fd) {
     pu.hll = 0;
+    if (P.ppm_temp_fix == 2 && P.riemann_solver != 2) {
+        // riemann_state (riemann_solvers.H:239-282): make (rho e, p) of both interface states consistent with the EOS, IN PLACE -- the
+        // caller's copies change, and the first-pass kernel stores them back because the reference modifies qm / qp themselves
+        {   Eos s; s.T = P.T_guess; s.rho = qm[IS_RHO]; s.e = qm[IS_RE] / qm[IS_RHO];
+            s.mu = eos_mu(P, [&](int n) { return xm(P.QFS_off + n); });
+            eos_re<false>(P, s);
+            qm[IS_RE] = s.e * s.rho; qm[IS_P] = s.p; }
+        {   Eos s; s.T = P.T_guess; s.rho = qp[IS_RHO]; s.e = qp[IS_RE] / qp[IS_RHO];
+            s.mu = eos_mu(P, [&](int n) { return xp(P.QFS_off + n); });
+            eos_re<false>(P, s);
+            qp[IS_RE] = s.e * s.rho; qp[IS_P] = s.p; }
+    }
     const long oq = qs.idx(i, j, k);
     const long om = oq - ((DIR == 0) ? 1 : (DIR == 1) ? qs.sj : qs.sk);
     const double cr = qs.at(oq, QS_C), cl = qs.at(om, QS_C);
@@ -749,6 +761,10 @@ static __global__ void __launch_bounds__(TPB) k_riemann1(const DevPar P, const A
     load6(qp, o, qr);
     solve_face<DIR>(P, ql, qr, qs, i, j, k, [&](int ip) { return qm.at(o, IS_X + ip); }, [&](int ip) { return qp.at(o, IS_X + ip); },
                     F, ugd, pgd, pu, fd);
+    if (P.ppm_temp_fix == 2 && P.riemann_solver != 2) {      // the re-synced states replace the traced ones for the later stages
+        qm.at(o, IS_P) = ql[IS_P]; qm.at(o, IS_RE) = ql[IS_RE];
+        qp.at(o, IS_P) = qr[IS_P]; qp.at(o, IS_RE) = qr[IS_RE];
+    }
     const long of = Fo.idx(i, j, k);
 #pragma unroll
     for (int n = 0; n < 6; ++n) Fo.at(of, n) = F[n];

@@ -75,7 +75,7 @@ struct DevPar {
     double shock_detection_threshold;
     int riemann_shock_maxiter, riemann_cg_blend, ppm_type, plm_iorder, plm_limiter;
     double riemann_pstar_tol;
-    int use_pslope, ppm_well_balanced;
+    int use_pslope, ppm_well_balanced, ppm_temp_fix;
     double pslope_cutoff_density;
     int transverse_use_eos, transverse_reset_density, transverse_reset_rhoe;
     int eos_assume_neutral;

@@ -83,7 +83,7 @@ typedef struct ctu_params_t {
     int transverse_reset_rhoe;
     int limit_fluxes_on_small_dens; /* 1: density-floor flux limiter (advection_util.cpp:543-645) */
     int first_order_hydro;
-    int ppm_temp_fix;              /* 0 only */
+    int ppm_temp_fix;              /* 0, or 2: EOS re-sync of the interface states before each CGF / CG solve */
     int use_pslope;                /* 1: subtract the hydrostatic pressure before limiting the pressure profile */
     int ppm_well_balanced;         /* 1: trace the perturbational pressure (PPM only) */
     int source_term_predictor;

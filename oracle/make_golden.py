@@ -55,6 +55,8 @@ CASES = {
     # piecewise-linear reconstruction (ppm_type = 0: trace_plm.cpp + slope.H), 4th-order MC limiter and the 2nd-order one
     "sedov16_plm_hllc": (16, 30, [30], ["castro.riemann_solver=2", "castro.ppm_type=0"]),
     "sedov16_plm_cgf_lim1": (16, 30, [30], ["castro.riemann_solver=0", "castro.ppm_type=0", "castro.plm_limiter=1"]),
+    # EOS re-sync of the interface states before every CGF / CG solve (riemann_solvers.H:239-282)
+    "sedov16_cgf_tempfix": (16, 30, [30], ["castro.riemann_solver=0", "castro.ppm_temp_fix=2"]),
     "sedov16_hllc_limit": (16, 60, [60], ["castro.riemann_solver=2", "castro.limit_fluxes_on_small_dens=1", "castro.small_dens=0.3"]),
 }
 

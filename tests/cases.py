@@ -41,6 +41,7 @@ CASES = {
     "sedov_24x16x8_cg": dict(n_cell=(24, 16, 8), solver=1, geom=dict(probhi=(1.5, 1.0, 0.5))),
     "sedov16_plm_hllc": dict(n_cell=(16, 16, 16), solver=2, par=dict(ppm_type=0)),
     "sedov16_plm_cgf_lim1": dict(n_cell=(16, 16, 16), solver=0, par=dict(ppm_type=0, plm_limiter=1)),
+    "sedov16_cgf_tempfix": dict(n_cell=(16, 16, 16), solver=0, par=dict(ppm_temp_fix=2)),
     "sedov16_hllc_limit": dict(n_cell=(16, 16, 16), solver=2, par=dict(limit_fluxes_on_small_dens=1, small_dens=0.3)),
 }
 

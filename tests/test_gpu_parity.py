@@ -190,7 +190,7 @@ def test_register_staged_kernels_match_golden():
         "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
         "from cases import load_case\n"
         "from castro_b200 import lib\n"
-        "for name in ('sedov16_hllc', 'sedov_24x16x8_cgf', 'sedov16_hllc_eos', 'sedov16_hllc_hybrid', 'sedov_24x16x8_cg', 'sedov16_hllc_limit', 'sedov16_plm_hllc'):\n"
+        "for name in ('sedov16_hllc', 'sedov_24x16x8_cgf', 'sedov16_hllc_eos', 'sedov16_hllc_hybrid', 'sedov_24x16x8_cg', 'sedov16_hllc_limit', 'sedov16_plm_hllc', 'sedov16_cgf_tempfix'):\n"
         "    par, geom, prob, g, snaps = load_case(name)\n"
         "    lib.params_finalize(par)\n"
         "    n = tuple(int(x) for x in g['n_cell'])\n"
