@@ -57,6 +57,11 @@ CASES = {
     "sedov16_plm_cgf_lim1": (16, 30, [30], ["castro.riemann_solver=0", "castro.ppm_type=0", "castro.plm_limiter=1"]),
     # EOS re-sync of the interface states before every CGF / CG solve (riemann_solvers.H:239-282)
     "sedov16_cgf_tempfix": (16, 30, [30], ["castro.riemann_solver=0", "castro.ppm_temp_fix=2"]),
+    # switches of the default (tile-staged) path
+    "sedov16_hllc_noflat": (16, 20, [20], ["castro.riemann_solver=2", "castro.use_flattening=0"]),
+    "sedov16_hllc_first": (16, 20, [20], ["castro.riemann_solver=2", "castro.first_order_hydro=1"]),
+    "sedov16_cgf_misc": (16, 30, [30], ["castro.riemann_solver=0", "castro.difmag=0.3", "castro.transverse_reset_density=0",
+                                        "castro.dual_energy_eta1=1.e-3", "castro.dual_energy_eta2=1.e-2"]),
     "sedov16_hllc_limit": (16, 60, [60], ["castro.riemann_solver=2", "castro.limit_fluxes_on_small_dens=1", "castro.small_dens=0.3"]),
 }
 
@@ -64,6 +69,8 @@ CASES = {
 KH_CASES = {
     "kh16_cgf": ((16, 16, 8), 10, [0, 10], ["castro.riemann_solver=0"]),
     "kh16_hllc": ((16, 16, 8), 10, [0, 10], ["castro.riemann_solver=2", "problem.bulk_velocity=0.3"]),
+    # unlimited PPM (ppm_do_limiting = 0) on the smooth KH flow (it is unstable on the Sedov blast: the reference aborts there)
+    "kh16_cgf_nolim": ((16, 16, 8), 10, [0, 10], ["castro.riemann_solver=0", "castro.ppm_do_limiting=0"]),
 }
 
 

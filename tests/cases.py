@@ -42,6 +42,10 @@ CASES = {
     "sedov16_plm_hllc": dict(n_cell=(16, 16, 16), solver=2, par=dict(ppm_type=0)),
     "sedov16_plm_cgf_lim1": dict(n_cell=(16, 16, 16), solver=0, par=dict(ppm_type=0, plm_limiter=1)),
     "sedov16_cgf_tempfix": dict(n_cell=(16, 16, 16), solver=0, par=dict(ppm_temp_fix=2)),
+    "sedov16_hllc_noflat": dict(n_cell=(16, 16, 16), solver=2, par=dict(use_flattening=0)),
+    "sedov16_hllc_first": dict(n_cell=(16, 16, 16), solver=2, par=dict(first_order_hydro=1)),
+    "sedov16_cgf_misc": dict(n_cell=(16, 16, 16), solver=0, par=dict(difmag=0.3, transverse_reset_density=0, dual_energy_eta1=1.e-3,
+                                                                      dual_energy_eta2=1.e-2)),
     "sedov16_hllc_limit": dict(n_cell=(16, 16, 16), solver=2, par=dict(limit_fluxes_on_small_dens=1, small_dens=0.3)),
 }
 
@@ -62,6 +66,7 @@ def load_case(name):
 KH_CASES = {
     "kh16_cgf": dict(solver=0, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0)),
     "kh16_hllc": dict(solver=2, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.3)),
+    "kh16_cgf_nolim": dict(solver=0, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0), par=dict(ppm_do_limiting=0)),
 }
 
 
@@ -75,6 +80,8 @@ def load_kh_case(name):
     par.cfl, par.init_shrink, par.change_max = 0.5, 0.1, 1.1
     par.small_dens, par.small_temp = 1.e-10, 1.e-10
     par.nadv, par.nspec = 1, 1
+    for k, v in c.get("par", {}).items():
+        setattr(par, k, v)
     n_cell = tuple(int(x) for x in g["n_cell"])
     geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), periodic=(1, 1, 1), lo_bc=(0, 0, 0), hi_bc=(0, 0, 0))
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())

@@ -238,7 +238,7 @@ def test_host_streaming_step_matches_golden(name, chunk, monkeypatch):
     sim.close()
 
 
-@pytest.mark.parametrize("name", ["kh16_cgf", "kh16_hllc"])
+@pytest.mark.parametrize("name", ["kh16_cgf", "kh16_hllc", "kh16_cgf_nolim"])
 def test_kh_two_passives_matches_reference_golden(name):
     """KH as shipped (advected scalar + species, periodic): problem hook vs the reference's initial plotfile, then 10 steps
     of the full time loop vs the reference's final state -- exercises the NP = 2 instances of the tile-staged kernels"""
