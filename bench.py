@@ -111,7 +111,7 @@ def workload_config(args, world):
     return {"workload": "Exec/hydro_tests/Sedov 3-D, %d^3 zones per GPU (global %s), gamma-law EOS gamma=1.4, CTU-PPM + %s, "
                         "single level, outflow BCs, cfl 0.5" % (args.n, "x".join(str(args.n * d) for d in dims),
                                                                 "HLLC" if args.solver == 2 else "CGF"),
-            "zones_per_gpu": args.n ** 3, "num_state": 8, "proc_grid": list(dims),
+            "zones_per_gpu": args.n ** 3, "num_state": 7 + getattr(args, "nspec", 1), "proc_grid": list(dims),
             "l2": "inputs larger than L2 (state %.1f GB per GPU); no explicit flush" % (8 * 8 * (args.n + 8) ** 3 / 1e9)}
 
 
@@ -186,6 +186,10 @@ def gpu_arm(args):
     par.riemann_solver = args.solver
     par.cfl, par.init_shrink, par.change_max = 0.5, 0.01, 1.1
     par.eos_gamma, par.eos_assume_neutral = 1.4, 1
+    if args.nspec != 1:          # developer option (NOT the benchmark configuration): a multi-species network
+        par.nspec = args.nspec
+        for m in range(args.nspec):
+            par.aion[m], par.zion[m] = 1.0 + 3.0 * m, 1.0 + m
     lib.params_finalize(par)
     geom = abi.make_geom(n_cell, probhi=tuple(float(d) for d in dims))     # dx = 1/n whatever the process grid
     prob = dict(r_init=0.01, p_ambient=1.e-5, exp_energy=1.0, dens_ambient=1.0, nsub=10)
@@ -335,6 +339,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nspec", type=int, default=1, help="developer option: species in the network (default 1 = gammalaw.net, the benchmark)")
     ap.add_argument("--profile-mode", action="store_true", help="allow warmup < 3 (ncu runs only; never a bench value)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and not args.profile_mode:

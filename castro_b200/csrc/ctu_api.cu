@@ -165,10 +165,24 @@ namespace {
 // The tile-staged kernels cover the gamma-law EOS (Gamma_1 constant) with 1 or 2 passive scalars (Sod/Sedov: 1 species;
 // KH as shipped: 1 advected + 1 species); other set-ups run the register-staged kernels of ctu_kernels.cuh.
 // CTU_NO_TMA=1 forces the register-staged kernels (A/B measurements).
+// number of passively advected scalars the tile-staged kernels are instantiated for (1 .. CTU_TMA_MAX_NP; beyond that the
+// register-staged family takes over): gammalaw.net = 1, KH as shipped = 2, a 4-species network = 4 (+1 with an advected scalar)
+#ifndef CTU_TMA_MAX_NP
+#define CTU_TMA_MAX_NP 5
+#endif
+#define CTU_NP_CASE(N, fn, args) case N: return fn<N> args;
+#if CTU_TMA_MAX_NP >= 5
+#define CTU_NP_DISPATCH(np, fn, args) switch (np) { CTU_NP_CASE(1, fn, args) CTU_NP_CASE(2, fn, args) CTU_NP_CASE(3, fn, args) CTU_NP_CASE(4, fn, args) CTU_NP_CASE(5, fn, args) } return CTU_ERR_UNSUPPORTED;
+#elif CTU_TMA_MAX_NP >= 4
+#define CTU_NP_DISPATCH(np, fn, args) switch (np) { CTU_NP_CASE(1, fn, args) CTU_NP_CASE(2, fn, args) CTU_NP_CASE(3, fn, args) CTU_NP_CASE(4, fn, args) } return CTU_ERR_UNSUPPORTED;
+#else
+#define CTU_NP_DISPATCH(np, fn, args) switch (np) { CTU_NP_CASE(1, fn, args) CTU_NP_CASE(2, fn, args) } return CTU_ERR_UNSUPPORTED;
+#endif
+
 bool tma_ok(const DevPar& P) {
     static const bool disabled = (std::getenv("CTU_NO_TMA") != nullptr);
     if (disabled || !P.gamc_const) return false;
-    if (P.npassive != 1 && P.npassive != 2) return false;
+    if (P.npassive < 1 || P.npassive > CTU_TMA_MAX_NP) return false;
     if (P.ppm_temp_fix) return false;        // EOS re-sync of the interface states before each solve: register-staged family
     if (P.use_pslope || P.ppm_well_balanced) return false;   // hydrostatic-pressure-aware reconstruction: register-staged family
     if (P.ppm_type == 0) return false;       // piecewise-linear reconstruction: register-staged family
@@ -225,8 +239,7 @@ int launch_trans2_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const B
 }
 int launch_trans2_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1,
                       A4 (*F2)[3], const Box3* nb, const double* cdtd, cudaStream_t st) {
-    if (np == 1) return launch_trans2_np<1>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
-    return launch_trans2_np<2>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    CTU_NP_DISPATCH(np, launch_trans2_np, (P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st))
 }
 
 template <int D, int NP, bool SRC>
@@ -262,14 +275,26 @@ int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, 
 }
 int launch_trace_riemann_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
                              const Box3& tb, double dt, const A4* srcq, cudaStream_t st) {
-    if (srcq) {
-        if (np == 1) return launch_trace_riemann_np<1, true>(P, ta, qs, qbx_a, fd, F1, tb, dt, *srcq, st);
-        return launch_trace_riemann_np<2, true>(P, ta, qs, qbx_a, fd, F1, tb, dt, *srcq, st);
-    }
     A4 none;
     std::memset(&none, 0, sizeof(none));
-    if (np == 1) return launch_trace_riemann_np<1, false>(P, ta, qs, qbx_a, fd, F1, tb, dt, none, st);
-    return launch_trace_riemann_np<2, false>(P, ta, qs, qbx_a, fd, F1, tb, dt, none, st);
+    switch (np) {
+#define CTU_CASE(N)                                                                                                         \
+    case N:                                                                                                                 \
+        return srcq ? launch_trace_riemann_np<N, true>(P, ta, qs, qbx_a, fd, F1, tb, dt, *srcq, st)                          \
+                    : launch_trace_riemann_np<N, false>(P, ta, qs, qbx_a, fd, F1, tb, dt, none, st);
+        CTU_CASE(1) CTU_CASE(2)
+#if CTU_TMA_MAX_NP >= 3
+        CTU_CASE(3)
+#endif
+#if CTU_TMA_MAX_NP >= 4
+        CTU_CASE(4)
+#endif
+#if CTU_TMA_MAX_NP >= 5
+        CTU_CASE(5)
+#endif
+#undef CTU_CASE
+    }
+    return CTU_ERR_UNSUPPORTED;
 }
 
 template <int N, int NP>
@@ -304,8 +329,7 @@ int launch_final_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Bo
 }
 int launch_final_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd,
                      const A4& Sb, const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
-    if (np == 1) return launch_final_np<1>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
-    return launch_final_np<2>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    CTU_NP_DISPATCH(np, launch_final_np, (P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st))
 }
 
 template <int NP>
@@ -323,8 +347,7 @@ int launch_update_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb
 }
 int launch_update(const DevPar& P, int np, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,
                   const Box3& tb, double dt, cudaStream_t st) {
-    if (np == 1) return launch_update_np<1>(P, F, ibx, Sb, Sin, Sn, ua, tb, dt, st);
-    return launch_update_np<2>(P, F, ibx, Sb, Sin, Sn, ua, tb, dt, st);
+    CTU_NP_DISPATCH(np, launch_update_np, (P, F, ibx, Sb, Sin, Sn, ua, tb, dt, st))
 }
 
 }  // namespace

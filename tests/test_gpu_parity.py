@@ -259,10 +259,10 @@ def test_kh_two_passives_matches_reference_golden(name):
     sim.close()
 
 
-@pytest.mark.parametrize("nadv,nspec,solver", [(1, 1, 2), (1, 1, 0), (0, 2, 2), (1, 3, 0), (0, 4, 2)])
+@pytest.mark.parametrize("nadv,nspec,solver", [(1, 1, 2), (1, 1, 0), (0, 2, 2), (0, 3, 2), (1, 3, 0), (0, 4, 2), (1, 4, 0), (2, 4, 2)])
 def test_passives_vs_oracle(nadv, nspec, solver):
     """evolved 3-D Sedov state with non-trivial advected scalars / several species: one ctu_hydro_advance vs the oracle.
-    (1,1) and (0,2) run the NP = 2 tile-staged kernels, the others the register-staged ones."""
+    Up to five passives run the tile-staged kernels (NP = 2, 3, 4, 5 here), (2,4) = six passives the register-staged ones."""
     torch = _torch()
     import oracle_lib as O
     from castro_b200 import lib, abi
