@@ -111,7 +111,8 @@ def workload_config(args, world):
     return {"workload": "Exec/hydro_tests/Sedov 3-D, %d^3 zones per GPU (global %s), gamma-law EOS gamma=1.4, CTU-PPM + %s, "
                         "single level, outflow BCs, cfl 0.5" % (args.n, "x".join(str(args.n * d) for d in dims),
                                                                 "HLLC" if args.solver == 2 else "CGF"),
-            "zones_per_gpu": args.n ** 3, "num_state": 7 + getattr(args, "nspec", 1), "proc_grid": list(dims),
+            "zones_per_gpu": args.n ** 3, "num_state": 7 + getattr(args, "nspec", 1) + (1 if getattr(args, "problem", "sedov") == "kh" else 0),
+            "problem": getattr(args, "problem", "sedov"), "proc_grid": list(dims),
             "l2": "inputs larger than L2 (state %.1f GB per GPU); no explicit flush" % (8 * 8 * (args.n + 8) ** 3 / 1e9)}
 
 
@@ -190,9 +191,26 @@ def gpu_arm(args):
         par.nspec = args.nspec
         for m in range(args.nspec):
             par.aion[m], par.zion[m] = 1.0 + 3.0 * m, 1.0 + m
-    lib.params_finalize(par)
-    geom = abi.make_geom(n_cell, probhi=tuple(float(d) for d in dims))     # dx = 1/n whatever the process grid
+    problem = "Sedov"
+    geom_kw = {}
     prob = dict(r_init=0.01, p_ambient=1.e-5, exp_energy=1.0, dens_ambient=1.0, nsub=10)
+    if args.problem == "kh":      # developer option: bench_inputs/inputs.kh3d at n^3 (NUM_STATE = 9)
+        problem = "KH"
+        par.cfl, par.init_shrink, par.change_max = 0.5, 0.1, 1.1
+        par.small_dens, par.small_temp = 1.e-10, 1.e-10
+        par.eos_gamma = 5.0 / 3.0
+        par.nadv, par.nspec = 1, 1
+        geom_kw = dict(periodic=(1, 1, 1), lo_bc=(0, 0, 0), hi_bc=(0, 0, 0))
+        prob = dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0)
+    elif args.problem == "rt":    # developer option: bench_inputs/inputs.rt3d on a cube of n^3 zones, constant gravity, grav_source_type 4
+        problem = "RT"
+        par.cfl, par.init_shrink, par.change_max = 0.8, 0.3, 1.1
+        par.eos_gamma = 5.0 / 3.0
+        par.do_grav, par.grav_source_type, par.const_grav = 1, 4, -1.0
+        geom_kw = dict(periodic=(1, 1, 0), lo_bc=(0, 0, 4), hi_bc=(0, 0, 4))
+        prob = dict(frac=0.5, rho_1=1.0, rho_2=2.0, p0_base=5.0)
+    lib.params_finalize(par)
+    geom = abi.make_geom(n_cell, probhi=tuple(float(d) for d in dims), **geom_kw)     # dx = 1/n whatever the process grid
 
     def barrier():
         if dist is not None:
@@ -201,7 +219,7 @@ def gpu_arm(args):
 
     sim = DistSim(par, geom, n_cell, lambda p, g, lo, hi: CudaBoxEngine(p, g, lo, hi, workspace_bytes=args.workspace_gb << 30),
                   comm=dist, rank=rank, world=world, dims=dims)
-    sim.init_problem("Sedov", prob)
+    sim.init_problem(problem, prob)
     eng = sim.engine
     ws = eng.sim.ws_handle
     zones_local = n ** 3
@@ -246,9 +264,10 @@ def gpu_arm(args):
     host = torch.empty((2, par.num_state, n, n, n), dtype=torch.float64, pin_memory=True)
     hin, hout = host[0].numpy(), host[1].numpy()
     eng.sim.download(out=hin)
-    e2e_mode = "streamed z-chunks (ctu_sim_step_host)" if world == 1 else "upload + step + download"
+    streamed = world == 1 and not par.do_grav      # the host-streamed step covers pure hydro on a single box
+    e2e_mode = "streamed z-chunks (ctu_sim_step_host)" if streamed else "upload + step + download"
     # one untimed step (allocates the staging buffers)
-    if world == 1:
+    if streamed:
         rc, est, _ = eng.sim.step_host(hin, hout, (sim.time + sim.dt) - sim.time)
         assert rc == 0
         sim.time += sim.dt
@@ -258,7 +277,7 @@ def gpu_arm(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(e2e_steps):
-        if world == 1:
+        if streamed:
             rc, est, _ = eng.sim.step_host(hin, hout, (sim.time + sim.dt) - sim.time)
             assert rc == 0
             sim.time += sim.dt
@@ -339,6 +358,9 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--problem", default="sedov", choices=["sedov", "kh", "rt"],
+                    help="developer option: kh = Kelvin-Helmholtz as shipped (advected scalar + species, periodic), rt = Rayleigh-Taylor with "
+                         "constant gravity (cube of n^3 zones); the benchmark configuration is sedov")
     ap.add_argument("--nspec", type=int, default=1, help="developer option: species in the network (default 1 = gammalaw.net, the benchmark)")
     ap.add_argument("--profile-mode", action="store_true", help="allow warmup < 3 (ncu runs only; never a bench value)")
     args = ap.parse_args()
