@@ -244,7 +244,7 @@ int launch_trans2_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs
 
 template <int D, int NP, bool SRC>
 int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1, const Box3& tb,
-                         double dt, const A4& srcq, cudaStream_t st) {
+                         double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
     using L = TraceSmem<D, NP>;
     using TT = TrTile<D>;
     static bool attr = false;
@@ -261,27 +261,27 @@ int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, con
     a.nty = (D == 1) ? (n[1] - 1 + TT::SY - 1) / TT::SY : (n[1] + TT::SY - 1) / TT::SY;
     a.ntz = (D == 2) ? (n[2] - 1 + TT::SZ - 1) / TT::SZ : (n[2] + TT::SZ - 1) / TT::SZ;
     a.dtdL = dt / P.dx[D];
-    a.srcq = srcq; a.hdt = 0.5 * dt;
+    a.srcq = srcq; a.hdt = 0.5 * dt; a.src_mask = src_mask;
     k_trace_riemann_tma<D, NP, SRC><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
     return 0;
 }
 template <int NP, bool SRC>
 int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
-                            const Box3& tb, double dt, const A4& srcq, cudaStream_t st) {
-    int rc = launch_trace_riemann<0, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, st);
-    if (!rc) rc = launch_trace_riemann<1, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, st);
-    if (!rc) rc = launch_trace_riemann<2, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, st);
+                            const Box3& tb, double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
+    int rc = launch_trace_riemann<0, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    if (!rc) rc = launch_trace_riemann<1, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    if (!rc) rc = launch_trace_riemann<2, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
     return rc;
 }
 int launch_trace_riemann_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
-                             const Box3& tb, double dt, const A4* srcq, cudaStream_t st) {
+                             const Box3& tb, double dt, const A4* srcq, const int* src_mask, cudaStream_t st) {
     A4 none;
     std::memset(&none, 0, sizeof(none));
     switch (np) {
 #define CTU_CASE(N)                                                                                                         \
     case N:                                                                                                                 \
-        return srcq ? launch_trace_riemann_np<N, true>(P, ta, qs, qbx_a, fd, F1, tb, dt, *srcq, st)                          \
-                    : launch_trace_riemann_np<N, false>(P, ta, qs, qbx_a, fd, F1, tb, dt, none, st);
+        return srcq ? launch_trace_riemann_np<N, true>(P, ta, qs, qbx_a, fd, F1, tb, dt, *srcq, src_mask, st)                \
+                    : launch_trace_riemann_np<N, false>(P, ta, qs, qbx_a, fd, F1, tb, dt, none, src_mask, st);
         CTU_CASE(1) CTU_CASE(2)
 #if CTU_TMA_MAX_NP >= 3
         CTU_CASE(3)
@@ -559,7 +559,7 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
             k_ctoprim<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, qs, lb); ++launches;
             if (r->have_src) {   // src_to_prim on grow(slab, 3) (Castro_ctu_hydro.cpp:282); timed with ctoprim
                 const LaunchBox ls = make_lb(sbx);
-                k_src_to_prim<<<nblocks(ls.n), TPB, 0, st>>>(P, Sb, qs, r->osrc, r->scorr, r->P_predictor, srcq, ls, dt); ++launches;
+                k_src_to_prim<<<nblocks(ls.n), TPB, 0, st>>>(P, Sb, qs, r->osrc, r->scorr, r->P_predictor, srcq, ls, dt, ws->d_counters + 5); ++launches;
             }
             tm.end(r->have_src ? 2 : 1); }
         {   LaunchBox lb = make_lb(obx);
@@ -569,7 +569,7 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
             ++launches; tm.end(1);
             if (use_tma) {
                 tm.begin(2);
-                rc = launch_trace_riemann_all(P, np, ta, qs, qbx_a, fd, F1, tb, dt, r->have_src ? &srcq : nullptr, st);
+                rc = launch_trace_riemann_all(P, np, ta, qs, qbx_a, fd, F1, tb, dt, r->have_src ? &srcq : nullptr, ws->d_counters + 5, st);
                 if (rc) return rc;
                 launches += 3; tm.end(3);
             } else {
@@ -585,13 +585,13 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
                     k_trace_plm<2, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
                 }
             } else if (r->have_src) {
-                k_trace<0, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
-                k_trace<1, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
-                k_trace<2, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                k_trace<0, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq, ws->d_counters + 5);
+                k_trace<1, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq, ws->d_counters + 5);
+                k_trace<2, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq, ws->d_counters + 5);
             } else {
-                k_trace<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
-                k_trace<1, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
-                k_trace<2, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq);
+                k_trace<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq, ws->d_counters + 5);
+                k_trace<1, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq, ws->d_counters + 5);
+                k_trace<2, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, dt, srcq, ws->d_counters + 5);
             }
             launches += 3; tm.end(3); } }
         const Box3 nb[3] = {[&] { Box3 b = tb; b.hi[0] += 1; return b; }(), [&] { Box3 b = tb; b.hi[1] += 1; return b; }(),

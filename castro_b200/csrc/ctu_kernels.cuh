@@ -157,9 +157,11 @@ constexpr int NSRCQ = 6;
 
 // one thread = one zone of grow(slab, 3)
 static __global__ void __launch_bounds__(TPB) k_src_to_prim(const DevPar P, const A4 U, const A4 qs, const A4 osrc, const A4 scorr,
-                                                     const int predictor, const A4 srcq, const LaunchBox lb, const double dt) {
+                                                     const int predictor, const A4 srcq, const LaunchBox lb, const double dt, int* __restrict__ src_mask) {
     int i, j, k;
-    if (!thread_zone(lb, i, j, k)) return;
+    const bool active = thread_zone(lb, i, j, k);
+    unsigned nz = 0;      // which primitive source components are non-zero somewhere (bit QS_*): lets the tracing skip the others
+    if (active) {
     const long ou = U.idx(i, j, k), oq = qs.idx(i, j, k), oo = osrc.idx(i, j, k), os = srcq.idx(i, j, k);
     double srcU[7];
 #pragma unroll
@@ -183,7 +185,14 @@ static __global__ void __launch_bounds__(TPB) k_src_to_prim(const DevPar P, cons
     srcq.at(os, QS_W) = (srcU[UMZ] - qs.at(oq, QS_W) * s_rho) * rhoinv;
     const double s_re = srcU[UEINT];
     srcq.at(os, QS_RE) = s_re;
-    srcq.at(os, QS_P) = s.dpde * (s_re - qre * s_rho * rhoinv) * rhoinv + s.dpdr_e * s_rho;
+    const double s_p = s.dpde * (s_re - qre * s_rho * rhoinv) * rhoinv + s.dpdr_e * s_rho;
+    srcq.at(os, QS_P) = s_p;
+    nz = (fabs(s_rho) > 0.0 ? 1u << QS_RHO : 0u) | (fabs(srcq.at(os, QS_U)) > 0.0 ? 1u << QS_U : 0u) | (fabs(srcq.at(os, QS_V)) > 0.0 ? 1u << QS_V : 0u) |
+         (fabs(srcq.at(os, QS_W)) > 0.0 ? 1u << QS_W : 0u) | (fabs(s_p) > 0.0 ? 1u << QS_P : 0u) | (fabs(s_re) > 0.0 ? 1u << QS_RE : 0u);
+    }
+    nz = __reduce_or_sync(0xffffffffu, nz);
+    // one atomic per warp only while it still has a new bit to contribute (4 M warps would otherwise serialise on one address)
+    if ((threadIdx.x & 31) == 0 && (nz & ~(unsigned)*(volatile const int*)src_mask)) atomicOr(src_mask, (int)nz);
 }
 
 // hdt * (Im_src_*, Ip_src_*) of trace_ppm.cpp:494-675; all +0.0 when a source component is not traced, which is exactly
@@ -198,14 +207,16 @@ struct SrcAdd {
 // sb: &srcq(zone, comp 0); sn component stride; st stride along DIR.  Per-zone check_trace_source (ppm.H:13-43).
 template <int DIR>
 __device__ __forceinline__ void trace_sources(const DevPar& P, const double* __restrict__ sb, const long sn, const long st, const double flat,
-                                              const double un, const double cc, const double dtdL, const double hdt, SrcAdd& sa) {
+                                              const double un, const double cc, const double dtdL, const double hdt, SrcAdd& sa, const int mask) {
     constexpr int QUN = QS_U + DIR;
     constexpr int QUT = QS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
     constexpr int QUTT = QS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
     double sm, sp, Ip, Im;
     Parabola pb;
+    // mask: components that are non-zero somewhere in the slab (from k_src_to_prim); a component outside it cannot have a non-zero
+    // stencil, so skipping it gives exactly the result of the per-zone test below (and is the reference's CPU per-tile switch)
 #define CTU_SRC_RECON(comp, BODY)                                                                \
-    {                                                                                            \
+    if (mask & (1 << (comp))) {                                                                  \
         const double* __restrict__ a = sb + (comp) * sn;                                         \
         const double s2m = a[-2 * st], s1m = a[-st], s0 = a[0], s1p = a[st], s2p = a[2 * st];    \
         if (fabs(s2m) > 0.0 || fabs(s1m) > 0.0 || fabs(s0) > 0.0 || fabs(s1p) > 0.0 || fabs(s2p) > 0.0) { \
@@ -449,7 +460,7 @@ struct TraceArgs {
 // one thread = one zone of obx, one direction per launch (blockIdx.y)
 template <int DIR, bool SRC>
 static __global__ void __launch_bounds__(TPB) k_trace(const DevPar P, const A4 qs, const A4 fd, const TraceArgs ta, const LaunchBox lb,
-                                               const double dt, const A4 srcq) {
+                                               const double dt, const A4 srcq, const int* __restrict__ src_mask) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
     const long oq = qs.idx(i, j, k);
@@ -471,7 +482,7 @@ static __global__ void __launch_bounds__(TPB) k_trace(const DevPar P, const A4 q
     if (SRC) {
         const long sst = (DIR == 0) ? 1 : (DIR == 1) ? srcq.sj : srcq.sk;
         trace_sources<DIR>(P, srcq.p + srcq.idx(i, j, k), srcq.sn, sst, flat, qs.at(oq, QS_U + DIR), qs.at(oq, QS_C), dt / P.dx[DIR],
-                           0.5 * dt, sa);
+                           0.5 * dt, sa, *src_mask);
     }
     const long sst_ = (DIR == 0) ? 1 : (DIR == 1) ? srcq.sj : srcq.sk;
     trace_dir<DIR, SRC>(P, qs, oq, st, flat, dt / P.dx[DIR], qm, qp, op, om, do_p, do_m, refl_lo, refl_hi, sa,

@@ -650,6 +650,7 @@ struct TraceRiemannArgs {
     double dtdL;          // dt / dx_D
     A4 srcq;              // primitive source terms on grow(slab, 3) (SRC instances only)
     double hdt;           // dt / 2
+    const int* src_mask;  // bit n set: primitive source component n is non-zero somewhere in the slab (k_src_to_prim)
 };
 
 // Castro::trace_ppm for one zone and direction, zero source terms (trace_ppm.cpp:17-678): the arithmetic of trace_dir in
@@ -811,7 +812,7 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
         if (SRC) {   // traced source terms (trace_ppm.cpp:309-440): the primitive sources come straight from HBM / L2
             const long sst = (D == 0) ? 1 : (D == 1) ? a.srcq.sj : a.srcq.sk;
             trace_sources<D>(P, a.srcq.p + a.srcq.idx(i, j, k), a.srcq.sn, sst, flat, sq0[(QS_U + D) * QT::ZONES], sq0[QS_C * QT::ZONES],
-                             a.dtdL, a.hdt, sa);
+                             a.dtdL, a.hdt, sa, *a.src_mask);
         }
         trace_core<M, D, NP, SRC>(P, sq0, QT::ZONES, QT::stride(D), flat, a.dtdL, qp_own, qm_nxt, xp_own, xm_nxt, sa);
         // hand the minus state to the thread that owns the high face
