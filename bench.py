@@ -322,6 +322,14 @@ def gpu_arm(args):
                 roofline["traffic"] = tpz * zones_local
                 roofline["traffic_bytes_per_zone"] = tpz
                 roofline["algorithmic_bytes"] = alg_bytes * zones_local
+                # the binding resource is the FP64 pipe / issue rate, not HBM: ncu-measured FP64-pipe busy time of one
+                # pipeline pass, against the time the pass took live
+                tj = json.load(open(traffic_file))
+                if "fp64_pipe_busy_ns_per_zone" in tj and hydro_ms > 0:
+                    busy_ms = tj["fp64_pipe_busy_ns_per_zone"] * zones_local * 1e-6
+                    roofline["fp64_pipe"] = {"busy_ms_per_step": busy_ms, "frac": busy_ms / (hydro_ms / args.steps),
+                                             "note": "fraction of the pipeline time the FP64 pipe would need at 100 % utilisation (ncu)"}
+                    roofline["binding"] = "fp64 pipe / issue rate (flux-stage kernels), HBM for k_final, k_update, k_ctoprim" 
             except Exception:
                 pass
         cpu = None
