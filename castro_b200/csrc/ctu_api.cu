@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include "ctu_kernels.cuh"
 #include "ctu_kernels_tma.cuh"
+#include "ctu_launch.cuh"
 #include "ctu_internal.h"
 
 using namespace ctu;
@@ -159,8 +160,13 @@ bool fab_covers(const ctu_fab_t* f, const Box3& b) {
 }  // namespace ctu
 
 
-// ---- launchers of the TMA-staged kernels (ctu_kernels_tma.cuh) ---------------------------------------------------
+// ---- launchers of the TMA-staged kernels (ctu_launch.cuh); NP = 3, 4, 5 are compiled in their own translation units ------
+CTU_INSTANTIATE_NP(extern, 3)
+CTU_INSTANTIATE_NP(extern, 4)
+CTU_INSTANTIATE_NP(extern, 5)
+
 namespace {
+using namespace ctu;
 
 // The tile-staged kernels cover the gamma-law EOS (Gamma_1 constant) with 1 or 2 passive scalars (Sod/Sedov: 1 species;
 // KH as shipped: 1 advected + 1 species); other set-ups run the register-staged kernels of ctu_kernels.cuh.
@@ -192,87 +198,11 @@ bool tma_ok(const DevPar& P) {
     return tma::encode_fn() != nullptr;
 }
 
-template <class K>
-int set_smem(K kernel, size_t bytes) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) { std::fprintf(stderr, "[castro_ctu] cudaFuncSetAttribute: %s\n", cudaGetErrorString(e)); return CTU_ERR_CUDA; }
-    return 0;
-}
-
-#define CTU_MAP(var, arr, abx, ncomp, Tile, nc)                                                              \
-    CUtensorMap var;                                                                                         \
-    if (!tma::make_map(&var, arr, abx, ncomp, Tile::EX, Tile::EY, Tile::EZ, nc)) return CTU_ERR_CUDA;
-
-template <int N, int NP>
-int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
-                  const Box3* nb, const double* cdtd, cudaStream_t st) {
-    using L = Trans2Smem<N, NP>;
-    constexpr int T1 = L::T1, T2 = L::T2;
-    static bool attr = false;
-    if (!attr) { int rc = set_smem(k_trans2_tma<N, NP>, L::TOTAL); if (rc) return rc; attr = true; }
-    CTU_MAP(m_qm, ta.qm[N], ibx, L::NIS, FaceTile, L::NIS)
-    CTU_MAP(m_qp, ta.qp[N], ibx, L::NIS, FaceTile, L::NIS)
-    CTU_MAP(m_f1, F1[T1], ibx, L::NFX, L::F1T, L::NFX)
-    CTU_MAP(m_f2, F1[T2], ibx, L::NFX, L::F2T, L::NFX)
-    CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
-    Trans2Args a;
-    a.qm = ta.qm[N]; a.qp = ta.qp[N];
-    a.Fo1 = F2[N][T1]; a.Fo2 = F2[N][T2];
-    int g1[3] = {0, 0, 0}, g2[3] = {0, 0, 0}, gu[3] = {0, 0, 0};
-    g1[T2] = 1; g2[T1] = 1; gu[T1] = 1; gu[T2] = 1;
-    a.b1 = grow(nb[N], g1[0], g1[1], g1[2]);       // F^{N|T1} lives on nodal(N) grown by one in T2
-    a.b2 = grow(nb[N], g2[0], g2[1], g2[2]);
-    for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
-    a.cdt1 = cdtd[T1]; a.cdt2 = cdtd[T2];
-    const TileGrid tg = make_tg(grow(nb[N], gu[0], gu[1], gu[2]));
-    k_trans2_tma<N, NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg);
-    return 0;
-}
-
-template <int NP>
-int launch_trans2_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
-                     const Box3* nb, const double* cdtd, cudaStream_t st) {
-    int rc = launch_trans2<0, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
-    if (!rc) rc = launch_trans2<1, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
-    if (!rc) rc = launch_trans2<2, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
-    return rc;
-}
 int launch_trans2_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1,
                       A4 (*F2)[3], const Box3* nb, const double* cdtd, cudaStream_t st) {
     CTU_NP_DISPATCH(np, launch_trans2_np, (P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st))
 }
 
-template <int D, int NP, bool SRC>
-int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1, const Box3& tb,
-                         double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
-    using L = TraceSmem<D, NP>;
-    using TT = TrTile<D>;
-    static bool attr = false;
-    if (!attr) { int rc = set_smem(k_trace_riemann_tma<D, NP, SRC>, L::TOTAL); if (rc) return rc; attr = true; }
-    CTU_MAP(m_q, qs, qbx_a, L::NQC, L::QT, L::NQC)
-    TraceRiemannArgs a;
-    a.fd = fd; a.qm = ta.qm[D]; a.qp = ta.qp[D]; a.Fo = F1[D];
-    a.obx = grow(tb, 1);
-    a.vlo = tb.lo[D]; a.vhi = tb.hi[D];
-    for (int d = 0; d < 3; ++d) a.qlo[d] = qbx_a.lo[d];
-    const int n[3] = {a.obx.hi[0] - a.obx.lo[0] + 1, a.obx.hi[1] - a.obx.lo[1] + 1, a.obx.hi[2] - a.obx.lo[2] + 1};
-    // along D the tiles overlap by one zone (N zones -> N-1 faces): the zones must reach index n[D]-1
-    a.ntx = (D == 0) ? (n[0] - 1 + TT::SX - 1) / TT::SX : (n[0] + TT::SX - 1) / TT::SX;
-    a.nty = (D == 1) ? (n[1] - 1 + TT::SY - 1) / TT::SY : (n[1] + TT::SY - 1) / TT::SY;
-    a.ntz = (D == 2) ? (n[2] - 1 + TT::SZ - 1) / TT::SZ : (n[2] + TT::SZ - 1) / TT::SZ;
-    a.dtdL = dt / P.dx[D];
-    a.srcq = srcq; a.hdt = 0.5 * dt; a.src_mask = src_mask;
-    k_trace_riemann_tma<D, NP, SRC><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
-    return 0;
-}
-template <int NP, bool SRC>
-int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
-                            const Box3& tb, double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
-    int rc = launch_trace_riemann<0, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
-    if (!rc) rc = launch_trace_riemann<1, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
-    if (!rc) rc = launch_trace_riemann<2, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
-    return rc;
-}
 int launch_trace_riemann_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
                              const Box3& tb, double dt, const A4* srcq, const int* src_mask, cudaStream_t st) {
     A4 none;
@@ -297,54 +227,11 @@ int launch_trace_riemann_all(const DevPar& P, int np, const TraceArgs& ta, const
     return CTU_ERR_UNSUPPORTED;
 }
 
-template <int N, int NP>
-int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
-                 const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
-    using L = FinalSmem<N, NP>;
-    constexpr int T1 = L::T1, T2 = L::T2;
-    static bool attr = false;
-    if (!attr) { int rc = set_smem(k_final_tma<N, NP>, L::TOTAL); if (rc) return rc; attr = true; }
-    CTU_MAP(m_qm, ta.qm[N], ibx, L::NIS, FaceTile, L::NIS)
-    CTU_MAP(m_qp, ta.qp[N], ibx, L::NIS, FaceTile, L::NIS)
-    CTU_MAP(m_f1, F2[T1][T2], ibx, L::NFX, L::F1T, L::NFX)
-    CTU_MAP(m_f2, F2[T2][T1], ibx, L::NFX, L::F2T, L::NFX)
-    CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
-    CTU_MAP(m_d, fd, ibx, 2, L::DT, 1)
-    FinalArgs a;
-    a.qm = ta.qm[N]; a.qp = ta.qp[N];
-    a.U = Sb; a.Fo = F1[N];
-    for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
-    a.c1 = hdtd[T1]; a.c2 = hdtd[T2];
-    const TileGrid tg = make_tg(nb[N]);
-    k_final_tma<N, NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, m_d, a, tg);
-    return 0;
-}
-template <int NP>
-int launch_final_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
-                    const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
-    int rc = launch_final<0, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
-    if (!rc) rc = launch_final<1, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
-    if (!rc) rc = launch_final<2, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
-    return rc;
-}
 int launch_final_all(const DevPar& P, int np, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd,
                      const A4& Sb, const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
     CTU_NP_DISPATCH(np, launch_final_np, (P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st))
 }
 
-template <int NP>
-int launch_update_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,
-                     const Box3& tb, double dt, cudaStream_t st) {
-    using L = UpdateSmem<NP>;
-    static bool attr = false;
-    if (!attr) { int rc = set_smem(k_update_tma<NP>, L::TOTAL); if (rc) return rc; attr = true; }
-    CTU_MAP(m_f0, F[0], ibx, L::NFX, L::F0T, L::NFX)
-    CTU_MAP(m_f1, F[1], ibx, L::NFX, L::F1T, L::NFX)
-    CTU_MAP(m_f2, F[2], ibx, L::NFX, L::F2T, L::NFX)
-    const TileGrid tg = make_tg_t<UTY, UTZ>(tb);
-    k_update_tma<NP><<<tg_blocks(tg), UTTHR, L::TOTAL, st>>>(P, m_f0, m_f1, m_f2, Sb, Sin, Sn, ua, ibx.lo[0], ibx.lo[1], ibx.lo[2], tg, dt);
-    return 0;
-}
 int launch_update(const DevPar& P, int np, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,
                   const Box3& tb, double dt, cudaStream_t st) {
     CTU_NP_DISPATCH(np, launch_update_np, (P, F, ibx, Sb, Sin, Sn, ua, tb, dt, st))

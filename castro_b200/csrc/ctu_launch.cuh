@@ -1,0 +1,150 @@
+// ctu_launch.cuh -- host-side launchers of the tile-staged (TMA) kernels, as templates on the number of passive scalars NP.
+// ctu_api.cu instantiates NP = 1, 2; ctu_np3.cu / ctu_np4.cu / ctu_np5.cu instantiate one NP each, so that `make -j` compiles the
+// five families in parallel (one translation unit with all of them takes 4m40 to compile, and nvcc's -split-compile, which would
+// parallelise it, was found to change the generated code from build to build).
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include "ctu_kernels.cuh"
+#include "ctu_kernels_tma.cuh"
+
+namespace ctu {
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { std::fprintf(stderr, "[castro_ctu] cudaFuncSetAttribute: %s\n", cudaGetErrorString(e)); return CTU_ERR_CUDA; }
+    return 0;
+}
+
+#define CTU_MAP(var, arr, abx, ncomp, Tile, nc)                                                              \
+    CUtensorMap var;                                                                                         \
+    if (!tma::make_map(&var, arr, abx, ncomp, Tile::EX, Tile::EY, Tile::EZ, nc)) return CTU_ERR_CUDA;
+
+template <int N, int NP>
+int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
+                  const Box3* nb, const double* cdtd, cudaStream_t st) {
+    using L = Trans2Smem<N, NP>;
+    constexpr int T1 = L::T1, T2 = L::T2;
+    static bool attr = false;
+    if (!attr) { int rc = set_smem(k_trans2_tma<N, NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    CTU_MAP(m_qm, ta.qm[N], ibx, L::NIS, FaceTile, L::NIS)
+    CTU_MAP(m_qp, ta.qp[N], ibx, L::NIS, FaceTile, L::NIS)
+    CTU_MAP(m_f1, F1[T1], ibx, L::NFX, L::F1T, L::NFX)
+    CTU_MAP(m_f2, F1[T2], ibx, L::NFX, L::F2T, L::NFX)
+    CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
+    Trans2Args a;
+    a.qm = ta.qm[N]; a.qp = ta.qp[N];
+    a.Fo1 = F2[N][T1]; a.Fo2 = F2[N][T2];
+    int g1[3] = {0, 0, 0}, g2[3] = {0, 0, 0}, gu[3] = {0, 0, 0};
+    g1[T2] = 1; g2[T1] = 1; gu[T1] = 1; gu[T2] = 1;
+    a.b1 = grow(nb[N], g1[0], g1[1], g1[2]);       // F^{N|T1} lives on nodal(N) grown by one in T2
+    a.b2 = grow(nb[N], g2[0], g2[1], g2[2]);
+    for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
+    a.cdt1 = cdtd[T1]; a.cdt2 = cdtd[T2];
+    const TileGrid tg = make_tg(grow(nb[N], gu[0], gu[1], gu[2]));
+    k_trans2_tma<N, NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg);
+    return 0;
+}
+
+template <int NP>
+int launch_trans2_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
+                     const Box3* nb, const double* cdtd, cudaStream_t st) {
+    int rc = launch_trans2<0, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    if (!rc) rc = launch_trans2<1, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    if (!rc) rc = launch_trans2<2, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    return rc;
+}
+template <int D, int NP, bool SRC>
+int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1, const Box3& tb,
+                         double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
+    using L = TraceSmem<D, NP>;
+    using TT = TrTile<D>;
+    static bool attr = false;
+    if (!attr) { int rc = set_smem(k_trace_riemann_tma<D, NP, SRC>, L::TOTAL); if (rc) return rc; attr = true; }
+    CTU_MAP(m_q, qs, qbx_a, L::NQC, L::QT, L::NQC)
+    TraceRiemannArgs a;
+    a.fd = fd; a.qm = ta.qm[D]; a.qp = ta.qp[D]; a.Fo = F1[D];
+    a.obx = grow(tb, 1);
+    a.vlo = tb.lo[D]; a.vhi = tb.hi[D];
+    for (int d = 0; d < 3; ++d) a.qlo[d] = qbx_a.lo[d];
+    const int n[3] = {a.obx.hi[0] - a.obx.lo[0] + 1, a.obx.hi[1] - a.obx.lo[1] + 1, a.obx.hi[2] - a.obx.lo[2] + 1};
+    // along D the tiles overlap by one zone (N zones -> N-1 faces): the zones must reach index n[D]-1
+    a.ntx = (D == 0) ? (n[0] - 1 + TT::SX - 1) / TT::SX : (n[0] + TT::SX - 1) / TT::SX;
+    a.nty = (D == 1) ? (n[1] - 1 + TT::SY - 1) / TT::SY : (n[1] + TT::SY - 1) / TT::SY;
+    a.ntz = (D == 2) ? (n[2] - 1 + TT::SZ - 1) / TT::SZ : (n[2] + TT::SZ - 1) / TT::SZ;
+    a.dtdL = dt / P.dx[D];
+    a.srcq = srcq; a.hdt = 0.5 * dt; a.src_mask = src_mask;
+    k_trace_riemann_tma<D, NP, SRC><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
+    return 0;
+}
+template <int NP, bool SRC>
+int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
+                            const Box3& tb, double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
+    int rc = launch_trace_riemann<0, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    if (!rc) rc = launch_trace_riemann<1, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    if (!rc) rc = launch_trace_riemann<2, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    return rc;
+}
+template <int N, int NP>
+int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
+                 const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
+    using L = FinalSmem<N, NP>;
+    constexpr int T1 = L::T1, T2 = L::T2;
+    static bool attr = false;
+    if (!attr) { int rc = set_smem(k_final_tma<N, NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    CTU_MAP(m_qm, ta.qm[N], ibx, L::NIS, FaceTile, L::NIS)
+    CTU_MAP(m_qp, ta.qp[N], ibx, L::NIS, FaceTile, L::NIS)
+    CTU_MAP(m_f1, F2[T1][T2], ibx, L::NFX, L::F1T, L::NFX)
+    CTU_MAP(m_f2, F2[T2][T1], ibx, L::NFX, L::F2T, L::NFX)
+    CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
+    CTU_MAP(m_d, fd, ibx, 2, L::DT, 1)
+    FinalArgs a;
+    a.qm = ta.qm[N]; a.qp = ta.qp[N];
+    a.U = Sb; a.Fo = F1[N];
+    for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
+    a.c1 = hdtd[T1]; a.c2 = hdtd[T2];
+    const TileGrid tg = make_tg(nb[N]);
+    k_final_tma<N, NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, m_d, a, tg);
+    return 0;
+}
+template <int NP>
+int launch_final_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
+                    const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
+    int rc = launch_final<0, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    if (!rc) rc = launch_final<1, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    if (!rc) rc = launch_final<2, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    return rc;
+}
+template <int NP>
+int launch_update_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,
+                     const Box3& tb, double dt, cudaStream_t st) {
+    using L = UpdateSmem<NP>;
+    static bool attr = false;
+    if (!attr) { int rc = set_smem(k_update_tma<NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    CTU_MAP(m_f0, F[0], ibx, L::NFX, L::F0T, L::NFX)
+    CTU_MAP(m_f1, F[1], ibx, L::NFX, L::F1T, L::NFX)
+    CTU_MAP(m_f2, F[2], ibx, L::NFX, L::F2T, L::NFX)
+    const TileGrid tg = make_tg_t<UTY, UTZ>(tb);
+    k_update_tma<NP><<<tg_blocks(tg), UTTHR, L::TOTAL, st>>>(P, m_f0, m_f1, m_f2, Sb, Sin, Sn, ua, ibx.lo[0], ibx.lo[1], ibx.lo[2], tg, dt);
+    return 0;
+}
+
+}  // namespace ctu
+
+// explicit instantiation (definition in ctu_npN.cu, declaration in ctu_api.cu) of every launcher for one NP
+#define CTU_INSTANTIATE_NP(KW, N)                                                                                                      \
+    KW template int ctu::launch_trans2_np<N>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&,               \
+                                             const ctu::Box3&, const ctu::A4*, ctu::A4 (*)[3], const ctu::Box3*, const double*,         \
+                                             cudaStream_t);                                                                            \
+    KW template int ctu::launch_trace_riemann_np<N, true>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&,  \
+                                                          const ctu::A4&, const ctu::A4*, const ctu::Box3&, double, const ctu::A4&,     \
+                                                          const int*, cudaStream_t);                                                   \
+    KW template int ctu::launch_trace_riemann_np<N, false>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&, \
+                                                           const ctu::A4&, const ctu::A4*, const ctu::Box3&, double, const ctu::A4&,    \
+                                                           const int*, cudaStream_t);                                                  \
+    KW template int ctu::launch_final_np<N>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&,                \
+                                            const ctu::Box3&, const ctu::A4&, const ctu::A4&, const ctu::A4*, ctu::A4 (*)[3],           \
+                                            const ctu::Box3*, const double*, cudaStream_t);                                            \
+    KW template int ctu::launch_update_np<N>(const ctu::DevPar&, const ctu::A4*, const ctu::Box3&, const ctu::A4&, const ctu::A4&,      \
+                                             const ctu::A4&, const ctu::UpdateArgs&, const ctu::Box3&, double, cudaStream_t);
