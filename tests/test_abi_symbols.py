@@ -73,3 +73,27 @@ def test_parse_inputs_file():
     assert nc == (48, 32, 16) and p.cfl == 0.4 and p.riemann_solver == 2 and p.eos_gamma == 1.4
     assert list(g.lo_bc) == [2, 2, 2] and g.dx[0] == 1.0 / 48 and ms == 10
     assert "r_init=0.01" in prob and "nsub=10" in prob
+
+
+def test_parse_inputs_all_hydro_options():
+    """every castro.* / gravity.* key of the hot path that the library honours is picked up from an inputs file (the RT file carries
+    the gravity keys) and from command-line style overrides, with the reference's defaults for the rest"""
+    from castro_b200 import lib
+    p, g, nc, ms, stop, prob = lib.parse_inputs(os.path.join(ROOT, "bench_inputs", "inputs.rt3d"), "")
+    assert p.do_grav == 1 and p.const_grav == -1.0 and p.grav_source_type == 4
+    assert list(g.periodic) == [1, 1, 0] and list(g.lo_bc) == [0, 0, 4] and nc == (16, 16, 32)
+    assert (p.ppm_type, p.riemann_solver, p.hybrid_riemann, p.use_pslope, p.ppm_well_balanced, p.ppm_temp_fix) == (1, 0, 0, 0, 0, 0)
+    assert (p.plm_iorder, p.plm_limiter, p.riemann_shock_maxiter, p.riemann_cg_blend) == (2, 2, 12, 2)
+    assert p.riemann_pstar_tol == 1.0e-5 and p.shock_detection_threshold == 2.0 / 3.0 and p.shock_detection_include_sources == 1
+    assert p.pslope_cutoff_density == -1.e20 and p.limit_fluxes_on_small_dens == 0
+    over = ("castro.ppm_type=0 castro.plm_limiter=1 castro.riemann_solver=1 castro.riemann_cg_blend=1 castro.riemann_shock_maxiter=20 "
+            "castro.hybrid_riemann=1 castro.shock_detection_threshold=0.5 castro.use_pslope=1 castro.ppm_well_balanced=1 "
+            "castro.pslope_cutoff_density=1.e-3 castro.ppm_temp_fix=2 castro.limit_fluxes_on_small_dens=1 castro.transverse_use_eos=1 "
+            "castro.transverse_reset_rhoe=1 castro.source_term_predictor=1 castro.grav_source_type=2 gravity.const_grav=-9.8 "
+            "castro.first_order_hydro=1 castro.use_flattening=0 castro.ppm_do_limiting=0 castro.difmag=0.2")
+    p, g, nc, ms, stop, prob = lib.parse_inputs(os.path.join(ROOT, "bench_inputs", "inputs.rt3d"), over)
+    assert (p.ppm_type, p.plm_limiter, p.riemann_solver, p.riemann_cg_blend, p.riemann_shock_maxiter) == (0, 1, 1, 1, 20)
+    assert (p.hybrid_riemann, p.use_pslope, p.ppm_well_balanced, p.ppm_temp_fix, p.limit_fluxes_on_small_dens) == (1, 1, 1, 2, 1)
+    assert (p.transverse_use_eos, p.transverse_reset_rhoe, p.source_term_predictor, p.grav_source_type) == (1, 1, 1, 2)
+    assert (p.first_order_hydro, p.use_flattening, p.ppm_do_limiting) == (1, 0, 0)
+    assert p.shock_detection_threshold == 0.5 and p.pslope_cutoff_density == 1.e-3 and p.const_grav == -9.8 and p.difmag == 0.2
