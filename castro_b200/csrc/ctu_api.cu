@@ -168,8 +168,8 @@ CTU_INSTANTIATE_NP(extern, 5)
 namespace {
 using namespace ctu;
 
-// The tile-staged kernels cover the gamma-law EOS (Gamma_1 constant) with 1 or 2 passive scalars (Sod/Sedov: 1 species;
-// KH as shipped: 1 advected + 1 species); other set-ups run the register-staged kernels of ctu_kernels.cuh.
+// The tile-staged kernels cover the default hydrodynamics options with the gamma-law EOS (Gamma_1 constant) and up to CTU_TMA_MAX_NP
+// passive scalars; everything else (see tma_ok) runs the register-staged kernels of ctu_kernels.cuh.
 // CTU_NO_TMA=1 forces the register-staged kernels (A/B measurements).
 // number of passively advected scalars the tile-staged kernels are instantiated for (1 .. CTU_TMA_MAX_NP; beyond that the
 // register-staged family takes over): gammalaw.net = 1, KH as shipped = 2, a 4-species network = 4 (+1 with an advected scalar)
