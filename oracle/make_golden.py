@@ -62,6 +62,9 @@ CASES = {
     "sedov16_hllc_first": (16, 20, [20], ["castro.riemann_solver=2", "castro.first_order_hydro=1"]),
     "sedov16_cgf_misc": (16, 30, [30], ["castro.riemann_solver=0", "castro.difmag=0.3", "castro.transverse_reset_density=0",
                                         "castro.dual_energy_eta1=1.e-3", "castro.dual_energy_eta2=1.e-2"]),
+    # several non-default options at once (their interactions)
+    "sedov16_combo": (16, 40, [40], ["castro.riemann_solver=1", "castro.ppm_type=0", "castro.hybrid_riemann=1",
+                                     "castro.limit_fluxes_on_small_dens=1", "castro.small_dens=0.3", "castro.transverse_use_eos=1"]),
     "sedov16_hllc_limit": (16, 60, [60], ["castro.riemann_solver=2", "castro.limit_fluxes_on_small_dens=1", "castro.small_dens=0.3"]),
 }
 
@@ -84,6 +87,9 @@ RT_CASES = {
     "rt16_pslope": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=0", "castro.use_pslope=1"]),
     "rt16_wellbal": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=2", "castro.ppm_well_balanced=1"]),
     "rt16_plm_pslope": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=0", "castro.ppm_type=0", "castro.use_pslope=1"]),
+    # interactions: shock detection with the gravity source subtracted, HLL blend, well-balanced PPM, EOS re-sync, gst 3
+    "rt16_combo": ((16, 16, 32), 20, [0, 20], ["castro.riemann_solver=0", "castro.hybrid_riemann=1", "castro.use_pslope=1",
+                                               "castro.ppm_well_balanced=1", "castro.ppm_temp_fix=2", "castro.grav_source_type=3"]),
 }
 
 

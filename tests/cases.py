@@ -46,6 +46,8 @@ CASES = {
     "sedov16_hllc_first": dict(n_cell=(16, 16, 16), solver=2, par=dict(first_order_hydro=1)),
     "sedov16_cgf_misc": dict(n_cell=(16, 16, 16), solver=0, par=dict(difmag=0.3, transverse_reset_density=0, dual_energy_eta1=1.e-3,
                                                                       dual_energy_eta2=1.e-2)),
+    "sedov16_combo": dict(n_cell=(16, 16, 16), solver=1, par=dict(ppm_type=0, hybrid_riemann=1, limit_fluxes_on_small_dens=1, small_dens=0.3,
+                                                                   transverse_use_eos=1)),
     "sedov16_hllc_limit": dict(n_cell=(16, 16, 16), solver=2, par=dict(limit_fluxes_on_small_dens=1, small_dens=0.3)),
 }
 
@@ -94,6 +96,7 @@ RT_CASES = {
     "rt16_pslope": dict(solver=0, grav_source_type=4, par=dict(use_pslope=1)),
     "rt16_wellbal": dict(solver=2, grav_source_type=4, par=dict(ppm_well_balanced=1)),
     "rt16_plm_pslope": dict(solver=0, grav_source_type=4, par=dict(ppm_type=0, use_pslope=1)),
+    "rt16_combo": dict(solver=0, grav_source_type=3, par=dict(hybrid_riemann=1, use_pslope=1, ppm_well_balanced=1, ppm_temp_fix=2)),
 }
 
 

@@ -309,7 +309,7 @@ def test_passives_vs_oracle(nadv, nspec, solver):
     assert est[1] == dt_ref
 
 
-@pytest.mark.parametrize("name", ["rt16_cgf", "rt16_hllc_gst2", "rt16_pslope", "rt16_wellbal", "rt16_plm_pslope"])
+@pytest.mark.parametrize("name", ["rt16_cgf", "rt16_hllc_gst2", "rt16_pslope", "rt16_wellbal", "rt16_plm_pslope", "rt16_combo"])
 def test_rt_gravity_matches_reference_golden(name):
     """Rayleigh-Taylor with constant gravity: old-time source + src_to_prim + traced sources inside
     the hydro + new-time corrector (grav_source_type 4 from the mass fluxes, or 2), 20 steps of the full time loop started from

@@ -56,7 +56,7 @@ def test_oracle_two_passives_matches_kh_golden(name):
     np.testing.assert_allclose(np.cumsum(np.concatenate([[0.0], hist])), g["times"][:n + 1], rtol=1e-14, atol=0)
 
 
-@pytest.mark.parametrize("name", ["rt16_cgf", "rt16_hllc_gst2", "rt16_pslope", "rt16_wellbal", "rt16_plm_pslope"])
+@pytest.mark.parametrize("name", ["rt16_cgf", "rt16_hllc_gst2", "rt16_pslope", "rt16_wellbal", "rt16_plm_pslope", "rt16_combo"])
 def test_oracle_gravity_sources_match_rt_golden(name):
     """Constant gravity (Rayleigh-Taylor): old-time source predictor, src_to_prim + traced sources inside the hydro, and the
     new-time corrector (grav_source_type 4 from the mass fluxes, or 2) -- 20 steps from the reference's own initial plotfile."""
