@@ -907,6 +907,9 @@ int ctu_sim_step_fill(ctu_sim_t* s) {
 // do_old_sources -> construct_ctu_hydro_source (sources traced) + clean_state -> do_new_sources + clean_state -> post_timestep
 static int sim_step_hydro_grav(ctu_sim_t* s, double dt, double dt_est[2], int n_bad[2]) {
     const ctu_params_t& par = s->par;
+    // castro.source_term_predictor = 1 needs the source corrector of the previous step (Castro_advance.cpp: source_corrector), which
+    // this single-level driver does not keep; ctu_hydro_advance itself accepts src_corr from a caller that has it
+    if (par.source_term_predictor != 0) return CTU_ERR_UNSUPPORTED;
     const DevPar P = make_devpar(&s->par, &s->geom);
     ctu_fab_t sb = s->fab(s->cur), sn = s->fab(1 - s->cur);
     const A4 Sb = make_a4(sb), Sn = make_a4(sn);
