@@ -51,17 +51,22 @@ def measured_peaks():
 
 
 # ---- reference CPU arm ------------------------------------------------------------------------------------------
-def run_reference_cpu(n_sample, steps, warmup, solver, threads=None):
+def run_reference_cpu(n_sample, steps, warmup, solver, threads=None, plot_dir=None):
     """Runs the unmodified reference executable on a bounded sample (n_sample^3 zones) for warmup+steps coarse steps and
-    returns (zones/s over the timed steps, mean s/step, threads, description).  Falls back to the CPU port (liboracle,
-    1 thread) when the reference executable is not present."""
+    returns (zones/s over the timed steps, mean s/step, threads, kind, description).  With plot_dir the run also writes its final
+    state as plot_dir/ref_pltNNNNN (after the last timed step; Amr::coarseTimeStep prints the step time before it writes), which
+    the GPU arm compares its own run of the same inputs against (parity_check).  Falls back to the CPU port (liboracle, 1 thread)
+    when the reference executable is not present."""
     threads = threads or (os.cpu_count() or 1)
     if os.path.exists(REF_EXE):
-        wd = tempfile.mkdtemp(prefix="refbench_")
+        wd = plot_dir or tempfile.mkdtemp(prefix="refbench_")
         mgs = 32 if n_sample >= 64 else 16
         env = dict(os.environ, OMP_NUM_THREADS=str(threads))
         args = [REF_EXE, REF_INPUTS, "amr.n_cell=%d %d %d" % ((n_sample,) * 3), "amr.max_grid_size=%d" % mgs,
                 "max_step=%d" % (warmup + steps), "castro.riemann_solver=%d" % solver]
+        if plot_dir:
+            args += ["amr.plot_files_output=1", "amr.plot_int=%d" % (warmup + steps), "amr.plot_file=%s" % os.path.join(plot_dir, "ref_plt"),
+                     "amr.derive_plot_vars=NONE"]
         out = subprocess.run(args, cwd=wd, env=env, capture_output=True, text=True)
         if out.returncode != 0:
             raise RuntimeError("reference executable failed: " + out.stdout[-2000:] + out.stderr[-2000:])
@@ -97,7 +102,7 @@ def reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": workload_config(args, args.gpus, cpu_sample=desc),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -105,12 +110,14 @@ def reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
+def workload_config(args, world, cpu_sample=None):
     from castro_b200.dist import proc_grid
     dims = proc_grid(world)
-    return {"workload": "Exec/hydro_tests/Sedov 3-D, %d^3 zones per GPU (global %s), gamma-law EOS gamma=1.4, CTU-PPM + %s, "
-                        "single level, outflow BCs, cfl 0.5" % (args.n, "x".join(str(args.n * d) for d in dims),
-                                                                "HLLC" if args.solver == 2 else "CGF"),
+    w = ("Exec/hydro_tests/Sedov 3-D, %d^3 zones per GPU (global %s), gamma-law EOS gamma=1.4, CTU-PPM + %s, "
+         "single level, outflow BCs, cfl 0.5" % (args.n, "x".join(str(args.n * d) for d in dims), "HLLC" if args.solver == 2 else "CGF"))
+    if cpu_sample:      # the reference CPU arm times a bounded sample of that workload (its zone rate does not depend on the box size)
+        w += "; TIMED HERE ON THE HOST CORES AS A BOUNDED SAMPLE: " + cpu_sample
+    return {"workload": w,
             "zones_per_gpu": args.n ** 3, "num_state": 7 + getattr(args, "nspec", 1) + (1 if getattr(args, "problem", "sedov") == "kh" else 0),
             "problem": getattr(args, "problem", "sedov"), "proc_grid": list(dims),
             "l2": "inputs larger than L2 (state %.1f GB per GPU); no explicit flush" % (8 * 8 * (args.n + 8) ** 3 / 1e9)}
@@ -158,6 +165,64 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
                 "reasons": sorted(reasons)}
+
+
+# ---- checks that travel with the bench line ----------------------------------------------------------------------------
+def parity_check(par_factory, n, steps, solver, ref_plot_dir):
+    """The GPU path on the inputs the reference CPU arm just ran (n^3 Sedov, `steps` coarse steps), judged by the reference's own
+    comparator: fcompare --rel_tol 1e-12 between the reference's plotfile and ours.  -> dict for the JSON line."""
+    from castro_b200 import lib
+    fcmp = os.path.join(ROOT, "oracle", "_ref", "fcompare.ex")
+    ref_pf = os.path.join(ref_plot_dir, "ref_plt%05d" % steps)
+    if not (os.path.exists(fcmp) and os.path.isdir(ref_pf)):
+        return {"n": n, "steps": steps, "max_rel": None, "agree": None, "note": "reference plotfile or fcompare missing"}
+    over = "amr.n_cell=%d %d %d castro.riemann_solver=%d" % (n, n, n, solver)
+    par, geom, nc, _, _, prob = lib.parse_inputs(REF_INPUTS, over)
+    lib.params_finalize(par)
+    sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in nc))
+    sim.init_problem("Sedov", {k: (int(v) if k == "nsub" else float(v)) for k, v in (kv.split("=") for kv in prob.split())})
+    rc, t, dt, hist = sim.advance(steps)
+    my_pf = os.path.join(ref_plot_dir, "b200_plt%05d" % steps)
+    sim.write_plotfile(my_pf, t, steps)
+    sim.close()
+    res = subprocess.run([fcmp, "--rel_tol", "1e-12", "-a", ref_pf, my_pf], capture_output=True, text=True)
+    rows = re.findall(r"^\s*(\w+)\s+([0-9.eE+-]+)\s+([0-9.eE+-]+)\s*$", res.stdout, flags=re.M)
+    return {"n": n, "steps": steps, "status": rc, "fields": len(rows),
+            "max_rel": max(float(r[2]) for r in rows) if rows else None, "max_abs": max(float(r[1]) for r in rows) if rows else None,
+            "agree": res.returncode == 0 and "PLOTFILE AGREE" in res.stdout and len(rows) == 8,
+            "tool": "oracle/_ref/fcompare.ex --rel_tol 1e-12 (reference executable's plotfile vs this library's, same inputs file)"}
+
+
+def decomp_check(torch, dist, rank, world, dims, args, n_global=128, steps=5):
+    """N > 1: a 128^3 global box split over the N ranks (halo exchange over NCCL) against the same box run whole on every rank:
+    each rank compares its own part bit for bit; the verdicts are AND-reduced."""
+    from castro_b200 import lib, abi
+    from castro_b200.dist import DistSim, CudaBoxEngine, box_of, rank_coords
+    par = lib.default_params()
+    par.riemann_solver = args.solver
+    par.cfl, par.init_shrink, par.change_max = 0.5, 0.01, 1.1
+    par.eos_gamma, par.eos_assume_neutral = 1.4, 1
+    lib.params_finalize(par)
+    prob = dict(r_init=0.01, p_ambient=1.e-5, exp_energy=1.0, dens_ambient=1.0, nsub=10)
+    n_cell = (n_global,) * 3
+    geom = abi.make_geom(n_cell)
+    whole = lib.Sim(par, geom, (0, 0, 0), tuple(n - 1 for n in n_cell))
+    whole.init_problem("Sedov", prob)
+    rc0, t0, dt0, hist0 = whole.advance(steps)
+    U = whole.download()
+    whole.close()
+    ds = DistSim(par, geom, n_cell, lambda p, g, lo, hi: CudaBoxEngine(p, g, lo, hi), comm=dist, rank=rank, world=world, dims=dims)
+    ds.init_problem("Sedov", prob)
+    st, hist = ds.advance(steps)
+    mine = ds.engine.download()
+    lo, hi = box_of(rank_coords(rank, dims), dims, n_cell)
+    ref = U[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]
+    ok = (st == 0 and rc0 == 0 and list(hist) == list(hist0) and mine.shape == ref.shape and bool((mine == ref).all()))
+    ds.close()
+    t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return {"verdict": "bitwise" if float(t.item()) == 1.0 else "MISMATCH", "global_box": "%d^3" % n_global, "steps": steps,
+            "proc_grid": list(dims), "halo_exchange": "NCCL send/recv, %d ranks" % world}
 
 
 # ---- GPU arm ------------------------------------------------------------------------------------------------------
@@ -216,6 +281,9 @@ def gpu_arm(args):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # N > 1: the decomposed run must reproduce the single-box run bit for bit (before anything is timed)
+    dcheck = decomp_check(torch, dist, rank, world, dims, args) if (dist is not None and not args.no_checks) else None
 
     sim = DistSim(par, geom, n_cell, lambda p, g, lo, hi: CudaBoxEngine(p, g, lo, hi, workspace_bytes=args.workspace_gb << 30),
                   comm=dist, rank=rank, world=world, dims=dims)
@@ -333,9 +401,16 @@ def gpu_arm(args):
             except Exception:
                 pass
         cpu = None
+        pcheck = None
         if world == 1 and not args.no_cpu:
-            v, spp, threads, kind, desc = run_reference_cpu(args.cpu_n, args.cpu_steps, 1, args.solver)
+            # the reference executable on the host cores (bounded sample); its final plotfile then judges the GPU path on the same inputs
+            pdir = tempfile.mkdtemp(prefix="parity_")
+            v, spp, threads, kind, desc = run_reference_cpu(args.cpu_n, args.cpu_steps, 1, args.solver, plot_dir=pdir)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc}
+            if kind == "reference" and not args.no_checks and args.problem == "sedov" and args.nspec == 1:
+                pcheck = parity_check(None, args.cpu_n, args.cpu_steps + 1, args.solver, pdir)
+            import shutil
+            shutil.rmtree(pdir, ignore_errors=True)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -346,6 +421,7 @@ def gpu_arm(args):
             "gpu_launches": launches, "clocks": clk,
             "halo_bytes_per_step_per_gpu": sim.halo_bytes_per_step,
             "exact_replay_tiles_per_step": replays / args.steps,
+            "parity_check": pcheck, "decomp_check": dcheck,
         }
         print(json.dumps(line), flush=True)
     sim.close()
@@ -366,6 +442,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-checks", action="store_true", help="skip parity_check (N = 1) / decomp_check (N > 1)")
     ap.add_argument("--problem", default="sedov", choices=["sedov", "kh", "rt"],
                     help="developer option: kh = Kelvin-Helmholtz as shipped (advected scalar + species, periodic), rt = Rayleigh-Taylor with "
                          "constant gravity (cube of n^3 zones); the benchmark configuration is sedov")

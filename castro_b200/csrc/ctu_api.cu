@@ -185,6 +185,51 @@ using namespace ctu;
 #define CTU_NP_DISPATCH(np, fn, args) switch (np) { CTU_NP_CASE(1, fn, args) CTU_NP_CASE(2, fn, args) } return CTU_ERR_UNSUPPORTED;
 #endif
 
+// ctu_selftest_mathfast: MathFast (ctu_physics.cuh) against the language operators on random + exceptional operands
+__device__ __forceinline__ unsigned long long st_rng(unsigned long long& s) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+__device__ __forceinline__ bool st_same(double a, double b) {
+    return (a != a && b != b) || __double_as_longlong(a) == __double_as_longlong(b);
+}
+__global__ void __launch_bounds__(128) k_selftest_mathfast(const int elo, const int ehi, const int iters, unsigned long long* cnt) {
+    unsigned long long s = 0x9e3779b97f4a7c15ull * (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x + 1);
+    volatile int* flag = &ctu_div_unsafe[threadIdx.x >> 5];     // one flag per warp (MathFastW); lanes run in lockstep below
+    unsigned long long bad_div = 0, bad_rcp = 0, bad_sqrt = 0, flagged = 0;
+    const unsigned long long special[12] = {0x0000000000000000ull, 0x8000000000000000ull, 0x0000000000000001ull, 0x800fffffffffffffull,
+                                            0x0010000000000000ull, 0x7fefffffffffffffull, 0x7ff0000000000000ull, 0xfff0000000000000ull,
+                                            0x7ff8000000000000ull, 0x3ff0000000000000ull, 0x0360000000000000ull, 0x7fd0000000000001ull};
+    for (int it = 0; it < iters; ++it) {
+        auto draw = [&]() {
+            const unsigned long long m = st_rng(s);
+            const unsigned long long e = (unsigned long long)(elo + (int)(st_rng(s) % (unsigned long long)(ehi - elo + 1)) + 1023);
+            return __longlong_as_double((long long)((m & 0x800fffffffffffffull) | (e << 52)));
+        };
+        double a = draw(), b = draw();
+        // exceptional operands in either position (every 16th sample)
+        if ((it & 15) == 0) a = __longlong_as_double((long long)special[(it >> 4) % 12]);
+        if ((it & 15) == 1) b = __longlong_as_double((long long)special[(it >> 4) % 12]);
+        // each lane tests its own operands: serialise the lanes' flag accesses by testing one lane at a time per primitive
+        for (int lane = 0; lane < 32; ++lane) {
+            __syncwarp();
+            if ((threadIdx.x & 31) != lane) continue;
+            *flag = 0;
+            const double q = MathFastW::div(a, b);
+            const int fq = *flag;
+            *flag = 0;
+            const double r = MathFastW::rcp(b);
+            const int fr = *flag;
+            *flag = 0;
+            const double y = MathFastW::sqrt(fabs(b));
+            const int fy = *flag;
+            flagged += (fq != 0) + (fr != 0) + (fy != 0);
+            if (!fq && !st_same(q, a / b)) bad_div++;
+            if (!fr && !st_same(r, 1.0 / b)) bad_rcp++;
+            if (!fy && !st_same(y, sqrt(fabs(b)))) bad_sqrt++;
+        }
+        __syncwarp();
+    }
+    atomicAdd(&cnt[0], bad_div); atomicAdd(&cnt[1], bad_rcp); atomicAdd(&cnt[2], bad_sqrt); atomicAdd(&cnt[3], flagged);
+}
+
 bool tma_ok(const DevPar& P) {
     static const bool disabled = (std::getenv("CTU_NO_TMA") != nullptr);
     if (disabled || !P.gamc_const) return false;
@@ -669,8 +714,13 @@ int ctu_estdt(const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3], 
     const DevPar P = make_devpar(par, geom);
     const Box3 bx = make_box(lo, hi);
     if (!bx.ok() || !fab_covers(S, bx)) return CTU_ERR_BAD_ARG;
-    unsigned long long* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    // reduction scratch: one small buffer per device, kept for the life of the process (no cudaMalloc / cudaFree per call)
+    static unsigned long long* d_cache[64] = {nullptr};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return CTU_ERR_BAD_ARG;
+    if (!d_cache[dev]) CUDA_TRY(cudaMalloc(&d_cache[dev], 2 * sizeof(unsigned long long)));
+    unsigned long long* d = d_cache[dev];
     unsigned long long init[2] = {0x7fefffffffffffffull, 0xffffffffffffffffull};
     CUDA_TRY(cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, st));
     const A4 a = make_a4(*S);
@@ -680,7 +730,6 @@ int ctu_estdt(const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3], 
     unsigned long long h[2];
     CUDA_TRY(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaFree(d));
     std::memcpy(dt_min, &h[0], sizeof(double));
     if (ijk) {
         const unsigned long long nx = lb.nx, ny = lb.ny, t = h[1];
@@ -688,6 +737,20 @@ int ctu_estdt(const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3], 
         ijk[1] = bx.lo[1] + (int)((t % (nx * ny)) / nx);
         ijk[0] = bx.lo[0] + (int)(t % nx);
     }
+    return 0;
+}
+
+int ctu_selftest_mathfast(int exp_lo, int exp_hi, int iters, unsigned long long counts[5]) {
+    if (!counts || exp_lo < -1022 || exp_hi > 1023 || exp_lo > exp_hi || iters < 1) return CTU_ERR_BAD_ARG;
+    if (!device_ok()) return CTU_ERR_NO_DEVICE;
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d, 0, 4 * sizeof(unsigned long long)));
+    k_selftest_mathfast<<<1024, 128>>>(exp_lo, exp_hi, iters, d);
+    cudaError_t e = cudaMemcpy(counts, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { cudaGetLastError(); return CTU_ERR_CUDA; }
+    counts[4] = 1024ull * 128ull * (unsigned long long)iters;
     return 0;
 }
 

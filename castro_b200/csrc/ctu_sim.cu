@@ -885,22 +885,27 @@ int ctu_sim_init_problem(ctu_sim_t* s, const char* problem, const char* prob_par
     return ctu_problem_init(problem, prob_params, &s->par, &s->geom, s->vbx.lo, s->vbx.hi, &f, s->st);
 }
 
-// Castro::initialize_advance: clean_state(S_old) (Castro_advance.cpp:487)
+// The reference cleans the state twice before the hydro: clean_state(S_old) on the valid zones (Castro::initialize_advance,
+// Castro_advance.cpp:487), then FillPatch into Sborder and clean_state(Sborder, NUM_GROW) on valid + ghost zones
+// (initialize_do_advance, Castro_advance.cpp:167-170).  clean_state is a pointwise function of the zone's state that commutes with
+// every boundary map this library fills with (copy of an interior / periodic-image / neighbour-box zone; reflection, which only
+// negates a momentum component that clean_state uses squared), so a ghost zone ends up holding map(clean(clean(source zone))).
+// The two passes are therefore ONE pass over the valid zones that applies clean_state twice in registers (step_pre), and the ghost
+// zones -- halo exchange, then the physical-boundary fill (step_fill) -- are copies of twice-cleaned zones: one read + one write
+// of the state instead of two, bit-identical (every golden test runs through this).
 int ctu_sim_step_pre(ctu_sim_t* s) {
     if (!s) return CTU_ERR_BAD_ARG;
     ctu_fab_t f = s->fab(s->cur);
     s->launches += 1;
-    return ctu_clean_state(&s->par, s->vbx.lo, s->vbx.hi, &f, 1, s->st);
+    return ctu_clean_state(&s->par, s->vbx.lo, s->vbx.hi, &f, 2, s->st);
 }
 
-// Castro::initialize_do_advance: FillPatch (local part) + clean_state(Sborder, NUM_GROW) (Castro_advance.cpp:167-170)
+// Castro::initialize_do_advance: FillPatch (local part: periodic self-wrap + physical boundaries)
 int ctu_sim_step_fill(ctu_sim_t* s) {
     if (!s) return CTU_ERR_BAD_ARG;
     ctu_fab_t f = s->fab(s->cur);
-    int rc = ctu_fill_boundary(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &f, CTU_NGROW, s->st);
-    if (rc) return rc;
-    s->launches += 3;
-    return ctu_clean_state(&s->par, s->gbx.lo, s->gbx.hi, &f, 1, s->st);
+    s->launches += 2;
+    return ctu_fill_boundary(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &f, CTU_NGROW, s->st);
 }
 
 // the same step with gravitational source terms around the hydro (Castro::do_advance_ctu, Castro_advance_ctu.cpp:60-130):
@@ -1028,7 +1033,7 @@ static int host_upload_planes(ctu_sim_t* s, const double* host, int b, int k0, i
     CUDA_TRY(cudaEventRecord(s->ev_upfree[b], s->st));
     s->upfree_rec[b] = true;
     s->launches += 1;
-    return ctu_clean_state(&s->par, lo, hi, f, 1, s->st);          // Castro::initialize_advance: clean_state(S_old)
+    return ctu_clean_state(&s->par, lo, hi, f, 2, s->st);          // both clean_state passes of the reference (see ctu_sim_step_pre)
 }
 
 int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, double dt, double dt_est[2], int n_bad[2]) {
@@ -1056,20 +1061,16 @@ int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, dou
     if (rc) { hydro_abort(run); return rc; }
     hydro_set_slab_info(run, (int)kc, nchunk);
     const int np4 = std::min(CTU_NGROW, nz);
-    const int glo[3] = {s->gbx.lo[0], s->gbx.lo[1], 0}, ghi[3] = {s->gbx.hi[0], s->gbx.hi[1], 0};
-    auto clean_planes = [&](int k0, int k1) {      // clean_state over the full ghosted x-y extent of planes [k0,k1]
-        int lo[3] = {glo[0], glo[1], k0}, hi[3] = {ghi[0], ghi[1], k1};
-        s->launches += 1;
-        return ctu_clean_state(&s->par, lo, hi, &sb, 1, s->st);
-    };
-    // prologue: z-ghost planes
+    // prologue: z-ghost planes.  The x/y ghosts of the first / last four valid planes come first: a z-ghost zone that is also an
+    // x- or y-ghost zone of a periodic (or, in a multi-box run, exchanged) direction is filled from the x/y ghost zone of the
+    // boundary plane (k_fill<1> maps only the non-periodic dimensions), so that zone must already hold this step's data.
     rc = host_upload_planes(s, host_in, 0, zlo, zlo + np4 - 1, &sb);
     if (!rc) rc = host_upload_planes(s, host_in, 1, zhi - np4 + 1, zhi, &sb);
+    if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, zlo, zlo + np4 - 1, s->st);
+    if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, zhi - np4 + 1, zhi, s->st);
     if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, zlo - CTU_NGROW, zlo - 1, s->st);
     if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, zhi + 1, zhi + CTU_NGROW, s->st);
-    if (!rc) rc = clean_planes(zlo - CTU_NGROW, zlo - 1);
-    if (!rc) rc = clean_planes(zhi + 1, zhi + CTU_NGROW);
-    s->launches += 4;
+    s->launches += 8;
     auto slab = [&](int c) {
         const int k0 = zlo + (int)(c * kc), k1 = std::min(zhi, k0 + (int)kc - 1), b = c & 1;
         int r = hydro_slab(run, k0, k1, c == nchunk - 1);
@@ -1094,9 +1095,8 @@ int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, dou
     for (int c = 0; c < nchunk && !rc; ++c) {
         const int k0 = zlo + (int)(c * kc), k1 = std::min(zhi, k0 + (int)kc - 1);
         rc = host_upload_planes(s, host_in, c & 1, k0, k1, &sb);
-        // Castro::initialize_do_advance: boundary fill + clean_state(Sborder, NUM_GROW) on these planes
+        // Castro::initialize_do_advance: boundary fill of the x/y ghosts of these planes (already twice cleaned, see ctu_sim_step_pre)
         if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, k0, k1, s->st);
-        if (!rc) rc = clean_planes(k0, k1);
         s->launches += 2;
         if (!rc && c >= 1) rc = slab(c - 1);
     }

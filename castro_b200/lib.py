@@ -71,6 +71,7 @@ def lib():
                                         C.c_int, C.c_void_p]
         L.ctu_halo_pack.argtypes = [C.POINTER(abi.Fab), abi.Int3, abi.Int3, C.c_void_p, C.c_void_p]
         L.ctu_halo_unpack.argtypes = [C.POINTER(abi.Fab), abi.Int3, abi.Int3, C.c_void_p, C.c_void_p]
+        L.ctu_selftest_mathfast.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
         L.ctu_problem_init.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3,
                                        C.POINTER(abi.Fab), C.c_void_p]
         L.ctu_parse_inputs.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), C.POINTER(C.c_int),

@@ -239,9 +239,11 @@ int  ctu_sim_download(ctu_sim_t* sim, double* host);
 int  ctu_sim_upload(ctu_sim_t* sim, const double* host);
 int  ctu_sim_init_problem(ctu_sim_t* sim, const char* problem, const char* prob_params);
 /* One step in three phases, so that a multi-rank caller can put its halo exchange and allreduce between them:
- *   pre  : clean_state(S_old)                                   [Castro::initialize_advance, Castro_advance.cpp:487]
+ *   pre  : clean_state(S_old) [Castro::initialize_advance, Castro_advance.cpp:487] AND the clean_state(Sborder) of
+ *          initialize_do_advance (Castro_advance.cpp:170) on the valid zones, in one pass (clean_state is pointwise and
+ *          commutes with every ghost fill below, so ghost zones are copies / reflections of twice-cleaned zones)
  *   (caller: exchange the 4-zone halos with the other boxes -- ctu_halo_pack / ctu_halo_unpack)
- *   fill : periodic self-wrap + physical BCs, clean_state(Sborder, 4) [initialize_do_advance, Castro_advance.cpp:167-170]
+ *   fill : periodic self-wrap + physical BCs                     [FillPatch, Castro_advance.cpp:167-169]
  *   hydro: construct_ctu_hydro_source + clean_state (Castro_ctu_hydro.cpp:1444) + post_timestep's clean_state
  *          (Castro.cpp:2043-2050); dt_est[0] / dt_est[1] = local min of dx/(c+|u|) after the first / second clean
  *          (caller: min-allreduce dt_est, max-allreduce the returned status)                                      */
@@ -263,6 +265,13 @@ int  ctu_sim_advance(ctu_sim_t* sim, int nsteps, double stop_time, double* time_
  * Castro::writePlotFile emits with amr.derive_plot_vars = NONE: Source/driver/Castro_io.cpp:943-, AMReX_PlotFileUtil.cpp:198-330),
  * so that the reference's own comparator (external/amrex/Tools/Plotfile/fcompare.cpp) can diff the two codes. */
 int  ctu_sim_write_plotfile(ctu_sim_t* sim, const char* dir, double time, int step);
+
+/* Self-test of the branch-free FP64 division / reciprocal / square-root sequences the flux-stage kernels compute with (they
+ * restate the fast path of nvcc's own IEEE operators; a kernel replays a tile with the language operators whenever a sequence
+ * flags an operand).  Draws `iters` random operand pairs per thread (131072 threads) with binary exponents uniform in
+ * [exp_lo, exp_hi], plus signed zeros, subnormals, infinities and NaNs, and compares every UNFLAGGED result bit for bit with
+ * a / b, 1 / b, sqrt(|b|).  counts = {mismatches div, rcp, sqrt, flagged operands, samples}.  Returns 0 or CTU_ERR_*. */
+int  ctu_selftest_mathfast(int exp_lo, int exp_hi, int iters, unsigned long long counts[5]);
 
 #ifdef __cplusplus
 }

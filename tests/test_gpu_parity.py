@@ -403,47 +403,140 @@ def test_hydro_advance_with_sources_vs_oracle(nspec, solver, predictor):
     assert not torch.equal(dSn2, dSn)
 
 
-@pytest.mark.parametrize("solver,nsteps", [(2, 10), (0, 25)])
-def test_plotfile_vs_reference_with_fcompare(solver, nsteps, tmp_path):
-    """the north star's own acceptance procedure: run the UNMODIFIED reference executable (oracle/_ref, test infrastructure) and
-    this library on the same inputs file, write a plotfile from each, and let the reference's comparator
-    (external/amrex/Tools/Plotfile/fcompare) judge: every conserved field must agree to rel-Linf <= 1e-12 (it is 0)."""
+def _run_reference_plotfile(tmp_path, n_cell, solver, nsteps, extra=()):
+    """runs the UNMODIFIED reference executable (oracle/_ref, test infrastructure; the OpenMP build for the larger boxes -- its results
+    do not depend on the tiling) on bench_inputs/inputs.sedov3d and returns (plotfile dir, fcompare path, inputs path) or skips"""
     import os
-    import re
     import subprocess
-    _torch()
-    from castro_b200 import lib
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = os.path.join(root, "oracle", "_ref", "Castro3d_sedov.ex")
+    big = n_cell[0] * n_cell[1] * n_cell[2] > 32 ** 3
+    exe = os.path.join(root, "oracle", "_ref", "Castro3d_sedov_omp.ex" if big else "Castro3d_sedov.ex")
+    if not os.path.exists(exe):
+        exe = os.path.join(root, "oracle", "_ref", "Castro3d_sedov.ex")
     fcmp = os.path.join(root, "oracle", "_ref", "fcompare.ex")
     inputs = os.path.join(root, "bench_inputs", "inputs.sedov3d")
     if not (os.path.exists(exe) and os.path.exists(fcmp)):
         pytest.skip("oracle/_ref not built (python -c 'import __graft_entry__ as g; g.build()' where /root/reference is mounted)")
-    n = 24
-    over = "amr.n_cell=%d %d %d castro.riemann_solver=%d" % (n, n, n, solver)
-    ref_args = [exe, inputs, "amr.n_cell=%d %d %d" % (n, n, n), "castro.riemann_solver=%d" % solver, "amr.max_grid_size=%d" % n,
+    ref_args = [exe, inputs, "amr.n_cell=%d %d %d" % tuple(n_cell), "castro.riemann_solver=%d" % solver,
+                "amr.max_grid_size=%d" % (32 if big else max(n_cell)), "amr.blocking_factor=4",
                 "max_step=%d" % nsteps, "amr.plot_files_output=1", "amr.plot_int=%d" % nsteps, "amr.plot_file=%s" % (tmp_path / "ref_plt"),
-                "amr.derive_plot_vars=NONE", "castro.v=0", "amr.v=0"]
-    out = subprocess.run(ref_args, cwd=tmp_path, capture_output=True, text=True)
+                "amr.derive_plot_vars=NONE", "castro.v=0", "amr.v=0"] + list(extra)
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+    out = subprocess.run(ref_args, cwd=tmp_path, capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     ref_pf = str(tmp_path / ("ref_plt%05d" % nsteps))
     assert os.path.isdir(ref_pf)
-    # the same inputs file through the library's own ParmParse reader
-    par, geom, n_cell, max_step, stop_time, prob = lib.parse_inputs(inputs, over)
-    lib.params_finalize(par)
-    sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in n_cell))
-    sim.init_problem("Sedov", {k: (int(v) if k == "nsub" else float(v)) for k, v in (kv.split("=") for kv in prob.split())})
-    rc, t, dt, hist = sim.advance(nsteps)
-    assert rc == 0 and len(hist) == nsteps
-    my_pf = str(tmp_path / "b200_plt")
-    sim.write_plotfile(my_pf, t, nsteps)
-    sim.close()
+    return ref_pf, fcmp, inputs
+
+
+def _fcompare_exact(fcmp, ref_pf, my_pf, ncomp=8):
+    import re
+    import subprocess
     res = subprocess.run([fcmp, "--rel_tol", "1e-12", "-a", ref_pf, my_pf], capture_output=True, text=True)
     assert res.returncode == 0 and "PLOTFILE AGREE" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
     rows = re.findall(r"^\s*(\w+)\s+([0-9.eE+-]+)\s+([0-9.eE+-]+)\s*$", res.stdout, flags=re.M)
-    assert len(rows) == 8, res.stdout
+    assert len(rows) == ncomp, res.stdout
     for name, abs_err, rel_err in rows:
         assert float(abs_err) == 0.0 and float(rel_err) == 0.0, "fcompare %s: abs %s rel %s" % (name, abs_err, rel_err)
+
+
+# (solver, n_cell, steps, workspace bytes): the 64^3 and 72x40x36 boxes span several 32-wide TMA tiles in x, tiles that straddle the
+# box edge in every direction and odd tile-origin parities; the last two force the multi-slab path (workspace bound) at that size
+@pytest.mark.parametrize("solver,n_cell,nsteps,wsb", [
+    (2, (24, 24, 24), 10, 0), (0, (24, 24, 24), 25, 0),
+    (2, (64, 64, 64), 10, 0), (0, (64, 64, 64), 10, 0),
+    (2, (72, 40, 36), 10, 0), (0, (72, 40, 36), 10, 0),
+    (2, (64, 64, 64), 10, 96 << 20), (0, (72, 40, 36), 10, 40 << 20)])
+def test_plotfile_vs_reference_with_fcompare(solver, n_cell, nsteps, wsb, tmp_path):
+    """the north star's own acceptance procedure: run the UNMODIFIED reference executable (oracle/_ref, test infrastructure) and
+    this library on the same inputs file, write a plotfile from each, and let the reference's comparator
+    (external/amrex/Tools/Plotfile/fcompare) judge: every conserved field must agree to rel-Linf <= 1e-12 (it is 0)."""
+    _torch()
+    from castro_b200 import lib
+    ref_pf, fcmp, inputs = _run_reference_plotfile(tmp_path, n_cell, solver, nsteps)
+    # the same inputs file through the library's own ParmParse reader
+    over = "amr.n_cell=%d %d %d castro.riemann_solver=%d" % (n_cell + (solver,))
+    par, geom, nc, max_step, stop_time, prob = lib.parse_inputs(inputs, over)
+    assert tuple(nc) == tuple(n_cell)
+    lib.params_finalize(par)
+    sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in nc), workspace_bytes=wsb)
+    sim.init_problem("Sedov", {k: (int(v) if k == "nsub" else float(v)) for k, v in (kv.split("=") for kv in prob.split())})
+    rc, t, dt, hist = sim.advance(nsteps)
+    assert rc == 0 and len(hist) == nsteps
+    if wsb:
+        assert sim.last_slabs > 1, "meant to exercise the multi-slab path"
+    my_pf = str(tmp_path / "b200_plt")
+    sim.write_plotfile(my_pf, t, nsteps)
+    sim.close()
+    _fcompare_exact(fcmp, ref_pf, my_pf)
+
+
+def test_host_streaming_mixed_boundaries():
+    """ctu_sim_step_host promises the bits of upload + pre + fill + hydro + download.  Periodic x/y with a physical boundary in z
+    (reflecting wall below, outflow above) is the case where a z-ghost zone is filled from an x/y-ghost zone of the boundary plane:
+    an off-centre blast puts non-trivial data into those edge and corner zones."""
+    _torch()
+    from castro_b200 import lib, abi
+    from castro_b200.dist import initial_dt, new_dt
+    from cases import sedov_params
+    import os
+    n_cell = (24, 16, 20)
+    for solver in (2, 0):
+        par = sedov_params(solver)
+        par.init_shrink = 0.3
+        lib.params_finalize(par)
+        geom = abi.make_geom(n_cell, probhi=(1.5, 1.0, 1.25), periodic=(1, 1, 0), lo_bc=(0, 0, 3), hi_bc=(0, 0, 2))
+        prob = dict(r_init=0.12, p_ambient=1.e-2, exp_energy=1.0, dens_ambient=1.0, nsub=4)
+        hi = tuple(n - 1 for n in n_cell)
+        ref = lib.Sim(par, geom, (0, 0, 0), hi)
+        ref.init_problem("Sedov", prob)
+        U = ref.download()
+        # move the blast into a corner of the periodic directions, next to the lower z boundary
+        U = np.roll(U, (-7, -6, -11), axis=(1, 2, 3)).copy()
+        ref.upload(U)
+        os.environ["CTU_HOST_CHUNK"] = "4"
+        try:
+            sim = lib.Sim(par, geom, (0, 0, 0), hi)
+            sim.upload(U)
+            h, h2 = U.copy(), np.empty_like(U)
+            t = 0.0
+            dt = initial_dt(par, sim.estdt(), t, -1.0)
+            rc, t_ref, dt_ref, hist = ref.advance(12)
+            assert rc == 0
+            for _ in range(12):
+                rc, est, nbad = sim.step_host(h, h2, (t + dt) - t)
+                assert rc == 0
+                h, h2 = h2, h
+                t += dt
+                dt = new_dt(par, est[1], dt, t, -1.0)
+            assert sim.last_slabs > 1
+        finally:
+            del os.environ["CTU_HOST_CHUNK"]
+        got = ref.download()
+        assert np.abs(got[1:4, :, :, :]).max() > 0 and np.abs(got[3, :2]).max() > 0, "the blast must have reached the z boundary"
+        assert_bitwise(h, got, "host-streamed step with periodic x/y + physical z (solver %d)" % solver)
+        assert t == t_ref
+        sim.close()
+        ref.close()
+
+
+def test_mathfast_sequences_match_ieee_operators():
+    """the branch-free division / reciprocal / sqrt sequences of the flux-stage kernels (MathFast, ctu_physics.cuh) restate the fast
+    path of nvcc's IEEE operators; every result they do not flag for the exact replay must equal the operator's bit for bit --
+    random operands over the whole exponent range plus zeros, subnormals, infinities and NaNs"""
+    _torch()
+    import ctypes as C
+    from castro_b200 import lib
+    L = lib.lib()
+    for lo, hi in ((-20, 20), (-200, 200), (-500, 500), (-1022, 1023)):
+        c = (C.c_ulonglong * 5)()
+        rc = L.ctu_selftest_mathfast(lo, hi, 128, c)
+        assert rc == 0
+        assert c[4] == 1024 * 128 * 128
+        assert c[0] == 0 and c[1] == 0 and c[2] == 0, "exp [%d,%d]: mismatches div %d rcp %d sqrt %d" % (lo, hi, c[0], c[1], c[2])
+        assert c[3] < 3 * c[4], "every operand flagged?"
+        if hi <= 200:
+            assert c[3] < 0.3 * c[4], "ordinary operands must stay on the fast path (flagged %d of %d)" % (c[3], 3 * c[4])
 
 
 def test_full_size_properties_sedov256():
