@@ -94,6 +94,34 @@ def run_reference_cpu(n_sample, steps, warmup, solver, threads=None, plot_dir=No
     return n ** 3 * steps / el, el / steps, 1, "port", "%d^3 Sedov, %d steps, oracle/liboracle.so single thread" % (n, steps)
 
 
+REF_GPU_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_sedov_cuda.ex")
+
+
+def run_reference_gpu(n, steps, warmup, solver, mgs=128):
+    """The UNMODIFIED reference built with its own GPU back end (oracle/build_ref.sh gpu: USE_CUDA=TRUE CUDA_ARCH=100) on this
+    box's GPU 0: Castro's stock unfused ParallelFor pipeline, the same inputs file, n^3 zones.  -> dict or None."""
+    if not os.path.exists(REF_GPU_EXE):
+        return None
+    wd = tempfile.mkdtemp(prefix="refgpu_")
+    a = [REF_GPU_EXE, REF_INPUTS, "amr.n_cell=%d %d %d" % ((n,) * 3), "amr.max_grid_size=%d" % mgs, "amr.blocking_factor=32",
+         "max_step=%d" % (warmup + steps), "castro.riemann_solver=%d" % solver]
+    try:
+        out = subprocess.run(a, cwd=wd, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]),
+                             capture_output=True, text=True, timeout=600)
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": "run failed: %r" % (e,)}
+    if out.returncode != 0:
+        return {"unavailable": "exit %d: %s" % (out.returncode, (out.stdout[-300:] + out.stderr[-300:]).replace("\n", " | "))}
+    ts = [float(x) for x in re.findall(r"\[STEP \d+\] Coarse TimeStep time: ([0-9.eE+-]+)", out.stdout)][warmup:warmup + steps]
+    if len(ts) != steps:
+        return {"unavailable": "could not parse step times"}
+    tot = sum(ts)
+    return {"value": n ** 3 * steps / tot, "unit": UNIT, "ms_per_step": 1e3 * tot / steps,
+            "kind": "reference, its own CUDA back end (USE_CUDA=TRUE CUDA_ARCH=100, stock code path, --use_fast_math as its build system sets)",
+            "sample": "%d^3 Sedov, max_grid_size %d, %d timed coarse steps after %d warm-up, whole coarse step (as [STEP] lines report), "
+                      "one GPU" % (n, mgs, steps, warmup)}
+
+
 def reference_arm(args, rank):
     if rank != 0:
         return
@@ -197,7 +225,7 @@ def decomp_check(torch, dist, rank, world, dims, args, n_global=128, steps=5):
     """N > 1: a 128^3 global box split over the N ranks (halo exchange over NCCL) against the same box run whole on every rank:
     each rank compares its own part bit for bit; the verdicts are AND-reduced."""
     from castro_b200 import lib, abi
-    from castro_b200.dist import DistSim, CudaBoxEngine, box_of, rank_coords
+    from castro_b200.dist import box_of, rank_coords
     par = lib.default_params()
     par.riemann_solver = args.solver
     par.cfl, par.init_shrink, par.change_max = 0.5, 0.01, 1.1
@@ -211,10 +239,10 @@ def decomp_check(torch, dist, rank, world, dims, args, n_global=128, steps=5):
     rc0, t0, dt0, hist0 = whole.advance(steps)
     U = whole.download()
     whole.close()
-    ds = DistSim(par, geom, n_cell, lambda p, g, lo, hi: CudaBoxEngine(p, g, lo, hi), comm=dist, rank=rank, world=world, dims=dims)
+    ds = lib.Dist(par, geom, dims, rank=rank, world=world, comm=dist)
     ds.init_problem("Sedov", prob)
     st, hist = ds.advance(steps)
-    mine = ds.engine.download()
+    mine = ds.sim.download()
     lo, hi = box_of(rank_coords(rank, dims), dims, n_cell)
     ref = U[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]
     ok = (st == 0 and rc0 == 0 and list(hist) == list(hist0) and mine.shape == ref.shape and bool((mine == ref).all()))
@@ -222,7 +250,7 @@ def decomp_check(torch, dist, rank, world, dims, args, n_global=128, steps=5):
     t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return {"verdict": "bitwise" if float(t.item()) == 1.0 else "MISMATCH", "global_box": "%d^3" % n_global, "steps": steps,
-            "proc_grid": list(dims), "halo_exchange": "NCCL send/recv, %d ranks" % world}
+            "proc_grid": list(dims), "halo_exchange": "ctu_dist_* (C++): fused pack, one ncclGroup of send/recv, fused unpack; %d ranks" % world}
 
 
 # ---- GPU arm ------------------------------------------------------------------------------------------------------
@@ -242,7 +270,7 @@ def gpu_arm(args):
     assert world == args.gpus, "--gpus %d but WORLD_SIZE %d" % (args.gpus, world)
 
     from castro_b200 import lib, abi
-    from castro_b200.dist import DistSim, CudaBoxEngine, proc_grid
+    from castro_b200.dist import proc_grid
     sys.path.insert(0, os.path.join(ROOT, "tests"))
 
     dims = proc_grid(world)
@@ -285,11 +313,11 @@ def gpu_arm(args):
     # N > 1: the decomposed run must reproduce the single-box run bit for bit (before anything is timed)
     dcheck = decomp_check(torch, dist, rank, world, dims, args) if (dist is not None and not args.no_checks) else None
 
-    sim = DistSim(par, geom, n_cell, lambda p, g, lo, hi: CudaBoxEngine(p, g, lo, hi, workspace_bytes=args.workspace_gb << 30),
-                  comm=dist, rank=rank, world=world, dims=dims)
+    # the C++ multi-box driver (ctu_dist_*): one box per rank, halo exchange + dt/status all-reduce over NCCL inside the library
+    sim = lib.Dist(par, geom, dims, rank=rank, world=world, comm=dist, workspace_bytes=args.workspace_gb << 30)
     sim.init_problem(problem, prob)
-    eng = sim.engine
-    ws = eng.sim.ws_handle
+    eng = sim.sim
+    ws = eng.ws_handle
     zones_local = n ** 3
     zones_total = zones_local * world
 
@@ -301,7 +329,7 @@ def gpu_arm(args):
     # ---- timed region: K steps, device-resident state --------------------------------------------------------------
     lib.workspace_set_profiling(ws, True)
     lib.workspace_stage_times(ws, reset=True)
-    l0 = eng.launches + sim.exchange_launches
+    l0 = eng.launches
     r0 = lib.workspace_replays(ws)
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -313,7 +341,7 @@ def gpu_arm(args):
     clk = clocks.stop() if clocks else None
     assert st == 0 and len(hist) == args.steps, "timed steps failed with status %d" % st
     ms = e0.elapsed_time(e1)
-    launches = eng.launches + sim.exchange_launches - l0
+    launches = eng.launches - l0
     replays = lib.workspace_replays(ws) - r0
     stages = lib.workspace_stage_times(ws, reset=True)
     lib.workspace_set_profiling(ws, False)
@@ -324,38 +352,37 @@ def gpu_arm(args):
     value = zones_total * args.steps / (ms * 1e-3)
 
     # ---- e2e: host buffers through the C ABI, H2D + step + D2H per step ------------------------------------------
-    # N = 1: ctu_sim_step_host streams the box through the device in z-chunks (copy-in, kernels, copy-out overlap).
-    # N > 1: upload -> step with halo exchange -> download (the exchange sits between the phases of a step).
+    # ctu_dist_step_host streams this rank's box through the device in z-chunks (copy-in, kernels, copy-out overlap); at N > 1 the
+    # halo exchange runs inside the pipeline (boundary planes first, then every chunk's x/y halos as soon as it is on the device).
     from castro_b200.dist import new_dt
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     nbytes = 8 * par.num_state * zones_local
     host = torch.empty((2, par.num_state, n, n, n), dtype=torch.float64, pin_memory=True)
     hin, hout = host[0].numpy(), host[1].numpy()
-    eng.sim.download(out=hin)
-    streamed = world == 1 and not par.do_grav      # the host-streamed step covers pure hydro on a single box
-    e2e_mode = "streamed z-chunks (ctu_sim_step_host)" if streamed else "upload + step + download"
-    # one untimed step (allocates the staging buffers)
-    if streamed:
-        rc, est, _ = eng.sim.step_host(hin, hout, (sim.time + sim.dt) - sim.time)
-        assert rc == 0
-        sim.time += sim.dt
-        sim.dt = new_dt(par, est[1], sim.dt, sim.time, -1.0)
-        hin, hout = hout, hin
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(e2e_steps):
+    eng.download(out=hin)
+    streamed = not par.do_grav                      # the host-streamed step covers pure hydro
+    e2e_mode = "streamed z-chunks (ctu_dist_step_host%s)" % (", halo exchange inside the pipeline" if world > 1 else "") if streamed \
+        else "upload + step + download"
+
+    def e2e_step():
+        nonlocal hin, hout
         if streamed:
-            rc, est, _ = eng.sim.step_host(hin, hout, (sim.time + sim.dt) - sim.time)
-            assert rc == 0
+            st_, est = sim.step_host(hin, hout, (sim.time + sim.dt) - sim.time)
+            assert st_ == 0
             sim.time += sim.dt
             sim.dt = new_dt(par, est[1], sim.dt, sim.time, -1.0)
             hin, hout = hout, hin
         else:
-            eng.sim.upload(hin)                 # pinned host -> device (valid zones of this rank's box)
-            st, _ = sim.advance(1)
-            assert st == 0
-            eng.sim.download(out=hin)           # device -> pinned host
+            eng.upload(hin)                 # pinned host -> device (valid zones of this rank's box)
+            st_, _ = sim.advance(1)
+            assert st_ == 0
+            eng.download(out=hin)           # device -> pinned host
+    e2e_step()                              # one untimed step (allocates the staging buffers)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
     f1.record()
     barrier()
     t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
@@ -363,6 +390,27 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     e2e_value = zones_total * e2e_steps / (e2e_ms * 1e-3)
+    # what the host side can deliver when all N ranks copy at once: 1 GiB up and 1 GiB down per rank, concurrently (explains e2e)
+    pc_n = 1 << 27
+    pc_h = host.view(-1)[:2 * pc_n]
+    pc_d = torch.empty(2 * pc_n, dtype=torch.float64, device="cuda")
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    s_up.wait_stream(torch.cuda.current_stream()); s_dn.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s_up):
+        pc_d[:pc_n].copy_(pc_h[:pc_n], non_blocking=True)
+    with torch.cuda.stream(s_dn):
+        pc_h[pc_n:].copy_(pc_d[pc_n:], non_blocking=True)
+    torch.cuda.current_stream().wait_stream(s_up); torch.cuda.current_stream().wait_stream(s_dn)
+    g1.record()
+    barrier()
+    t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pcie_gbs = 8.0 * pc_n / (float(t.item()) * 1e-3) / 1e9          # per rank, each direction, all ranks copying both ways at once
+    del pc_d
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -417,14 +465,23 @@ def gpu_arm(args):
             "data": "synthetic", "config": workload_config(args, world),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "mode": e2e_mode},
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "mode": e2e_mode,
+                    "host_copy_gbs_per_rank_each_way": pcie_gbs,
+                    "copy_floor_ms_per_step": nbytes / (pcie_gbs * 1e9) * 1e3,
+                    "note": "host_copy_gbs = measured here with all N ranks copying 1 GiB up and 1 GiB down at once from pinned memory; "
+                            "copy_floor = this step's bytes at that rate"},
             "gpu_launches": launches, "clocks": clk,
             "halo_bytes_per_step_per_gpu": sim.halo_bytes_per_step,
             "exact_replay_tiles_per_step": replays / args.steps,
             "parity_check": pcheck, "decomp_check": dcheck,
         }
-        print(json.dumps(line), flush=True)
     sim.close()
+    if rank == 0:
+        if world == 1 and not args.no_cpu and not args.no_ref_gpu:
+            # Castro's own GPU build on the same B200 (after this arm's device memory has been released)
+            torch.cuda.empty_cache()
+            line["reference_gpu"] = run_reference_gpu(args.ref_gpu_n, args.steps, 3, args.solver)
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -442,6 +499,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the run of the reference's own CUDA build (reference_gpu)")
+    ap.add_argument("--ref-gpu-n", type=int, default=256, help="edge of the box the reference's CUDA build is timed on")
     ap.add_argument("--no-checks", action="store_true", help="skip parity_check (N = 1) / decomp_check (N > 1)")
     ap.add_argument("--problem", default="sedov", choices=["sedov", "kh", "rt"],
                     help="developer option: kh = Kelvin-Helmholtz as shipped (advected scalar + species, periodic), rt = Rayleigh-Taylor with "

@@ -740,6 +740,16 @@ int ctu_estdt(const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3], 
     return 0;
 }
 
+#ifdef CTU_PHASE_TIMING
+// developer builds only: {TMA-wait ticks, compute ticks, CTAs} per kernel family (trace, trans2, final, update), NP <= 2 instances
+int ctu_debug_phase_ticks(unsigned long long out[12], int reset) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out, ctu::ctu_phase_ticks, 12 * sizeof(unsigned long long)));
+    if (reset) { unsigned long long z[12] = {0}; CUDA_TRY(cudaMemcpyToSymbol(ctu::ctu_phase_ticks, z, sizeof(z))); }
+    return 0;
+}
+#endif
+
 int ctu_selftest_mathfast(int exp_lo, int exp_hi, int iters, unsigned long long counts[5]) {
     if (!counts || exp_lo < -1022 || exp_hi > 1023 || exp_lo > exp_hi || iters < 1) return CTU_ERR_BAD_ARG;
     if (!device_ok()) return CTU_ERR_NO_DEVICE;

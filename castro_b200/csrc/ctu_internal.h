@@ -24,3 +24,54 @@ void hydro_set_slab_info(HydroRun* r, int planes, int nslab);
 int fill_boundary_planes(const ctu_params_t* par, const ctu_geom_t* geom, const int valid_lo[3], const int valid_hi[3], ctu_fab_t* S,
                          int ng, int zlo, int zhi, cudaStream_t st);
 }  // namespace ctu
+
+// ---- the single-box driver's state (ctu_sim.cu), shared with the multi-box layer (ctu_dist.cu) -----------------------------
+struct ctu_sim {
+    ctu_params_t par;
+    ctu_geom_t geom;
+    ctu::Box3 vbx, gbx;
+    int nstate = 0;
+    double* buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    ctu_workspace_t* ws = nullptr;
+    cudaStream_t st = 0;
+    int step = 0;
+    int launches = 0;     // kernels launched by the sim itself (clean / fill / init), on top of the workspace's count
+    // constant gravity (par.do_grav): old-time source on grow(valid, NUM_GROW_SRC), mass fluxes for grav_source_type 4, dt reduction
+    double* osrc = nullptr;
+    double* mflux[3] = {nullptr, nullptr, nullptr};
+    unsigned long long* d_dt2 = nullptr;
+    // host-streaming step (ctu_sim_step_host): copy streams, double-buffered staging, hand-over events
+    cudaStream_t s_up = nullptr, s_dn = nullptr;
+    double* stage_up[2] = {nullptr, nullptr};
+    double* stage_dn[2] = {nullptr, nullptr};
+    size_t stage_doubles = 0;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_upfree[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr}, ev_dnfree[2] = {nullptr, nullptr};
+    bool upfree_rec[2] = {false, false}, dnfree_rec[2] = {false, false};
+    ctu_fab_t fab(int which) const {
+        ctu_fab_t f;
+        f.p = buf[which];
+        for (int d = 0; d < 3; ++d) { f.lo[d] = gbx.lo[d]; f.hi[d] = gbx.hi[d]; }
+        f.ncomp = nstate;
+        return f;
+    }
+};
+
+
+namespace ctu {
+// What a multi-box run adds to the single-box time loop (ctu_dist.cu implements it over NCCL; nullptr = single box):
+//   exchange        : fill the ghost zones owned by other boxes from their (twice-cleaned) valid zones, all 26 directions
+//   exchange_planes : the same restricted to the in-plane directions (d_z = 0) and to the planes [k0, k1] (host-streamed step)
+//   exchange_z      : the directions with d_z != 0 (host-streamed step: the first / last four planes travel ahead of the pipeline)
+//   allreduce_min   : element-wise MIN over the ranks of n doubles (host values in, host values out)
+struct SimHooks {
+    virtual ~SimHooks() {}
+    virtual int exchange(ctu_sim* s) = 0;
+    virtual int exchange_planes(ctu_sim* s, int k0, int k1) = 0;
+    virtual int exchange_z(ctu_sim* s) = 0;
+    virtual int allreduce_min(double* v, int n) = 0;
+};
+int sim_advance_impl(ctu_sim* s, SimHooks* hooks, int nsteps, double stop_time, double* time_io, double* dt_io, double* dt_hist, int* steps_done);
+int sim_step_host_impl(ctu_sim* s, SimHooks* hooks, const double* host_in, double* host_out, double dt, double dt_est[2], int n_bad[2]);
+}  // namespace ctu
+

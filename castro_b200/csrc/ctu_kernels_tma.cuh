@@ -43,6 +43,25 @@ template <int NP> struct TmaMinB { static constexpr int value = (NP == 1) ? CTU_
 constexpr int ceven(int n) { return (n + 1) & ~1; }
 constexpr size_t al128(size_t b) { return (b + 127) & ~(size_t)127; }
 
+// CTU_PHASE_TIMING (developer builds only, tools/build_variant.sh): per-CTA clock ticks spent waiting for the TMA tiles vs computing,
+// accumulated per kernel family (0 trace, 1 trans2, 2 final, 3 update) -> ctu_debug_phase_ticks()
+#ifdef CTU_PHASE_TIMING
+__device__ unsigned long long ctu_phase_ticks[4][3];
+#define CTU_PT_BEGIN long long pt0_ = clock64(), pt1_ = pt0_;
+#define CTU_PT_LOADED pt1_ = clock64();
+#define CTU_PT_END(id)                                                                                     \
+    if (threadIdx.x == 0) {                                                                                \
+        const long long pt2_ = clock64();                                                                  \
+        atomicAdd(&ctu_phase_ticks[id][0], (unsigned long long)(pt1_ - pt0_));                             \
+        atomicAdd(&ctu_phase_ticks[id][1], (unsigned long long)(pt2_ - pt1_));                             \
+        atomicAdd(&ctu_phase_ticks[id][2], 1ull);                                                          \
+    }
+#else
+#define CTU_PT_BEGIN
+#define CTU_PT_LOADED
+#define CTU_PT_END(id)
+#endif
+
 struct TileGrid {
     int lo0, lo1, lo2, hi0, hi1, hi2;   // launch box
     int ntx, nty, ntz;
@@ -270,6 +289,7 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
     using L = Trans2Smem<N, NP>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    CTU_PT_BEGIN
     const TileCtx c = tile_ctx(tg);
     // x coordinates of the tile origins in their arrays and their parity shifts (see EXT)
     const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
@@ -300,6 +320,7 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
     }
 #endif
     tma::mbar_wait(bar, 0);
+    CTU_PT_LOADED
     // speculative pass with the branch-free division / sqrt sequences; a warp replays its faces with the exact operators if one
     // of its threads met an operand outside their range (see MathFast in ctu_physics.cuh; the faces of a tile are independent)
 #if CTU_Q_LDG
@@ -316,6 +337,7 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
         trans2_body<MathExact, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, nullptr, nullptr, nullptr, nullptr);
 #endif
     }
+    CTU_PT_END(1)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,6 +439,7 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
     using L = FinalSmem<N, NP>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    CTU_PT_BEGIN
     const TileCtx c = tile_ctx(tg);
     const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
     const int gi = fi - (N == 0), pg = gi & 1;
@@ -457,6 +480,7 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
         for (int ip = 0; ip < NP; ++ip) dUX[ip] = a.U.at(ou, UFA + ip) - a.U.at(oum, UFA + ip);
     }
     tma::mbar_wait(bar, 0);
+    CTU_PT_LOADED
     // speculative pass / exact replay per warp, as in k_trans2_tma
 #if CTU_Q_LDG
     final_body<MathFastW, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, ql, qr, xl, xr);
@@ -480,6 +504,7 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
         final_body<MathExact, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, nullptr, nullptr, nullptr, nullptr);
 #endif
     }
+    CTU_PT_END(2)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -529,6 +554,7 @@ k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __g
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
     unsigned long long* red = reinterpret_cast<unsigned long long*>(smem + L::O_RED);
+    CTU_PT_BEGIN
     const TileCtx c = tile_ctx_t<UTY, UTZ>(tg);
     const int fi = c.i0 - ilo0, fj = c.j0 - ilo1, fk = c.k0 - ilo2, pf = fi & 1;
     if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
@@ -553,6 +579,7 @@ k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __g
         for (int ip = 0; ip < NP; ++ip) ux[ip] = Sin.at(oi, UFA + ip);
     }
     tma::mbar_wait(bar, 0);
+    CTU_PT_LOADED
     if (active) {
         const typename L::F0T F0{reinterpret_cast<const double*>(smem + L::O_0)};
         const typename L::F1T F1{reinterpret_cast<const double*>(smem + L::O_1)};
@@ -605,6 +632,7 @@ k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __g
         block_min_atomic_n<UTTHR>(dt0, a.dtmin + 0, red);
         block_min_atomic_n<UTTHR>(dt1, a.dtmin + 1, red);
     }
+    CTU_PT_END(3)
 }
 
 }  // namespace ctu
@@ -904,6 +932,7 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     using TT = TrTile<D>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    CTU_PT_BEGIN
     // tile and thread coordinates
     const int bt = blockIdx.x;
     const int bx = bt % a.ntx, r = bt / a.ntx, by = r % a.nty, bz = r / a.nty;
@@ -927,6 +956,7 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     double flat = 0.0;
     if (c.active) flat = a.fd(c.i, c.j, c.k, 0);
     tma::mbar_wait(bar, 0);
+    CTU_PT_LOADED
     // speculative pass with the branch-free division / sqrt sequences; exact replay of the tile if any thread met an operand
     // outside their range (see MathFast in ctu_physics.cuh)
     trace_riemann_body<MathFast, D, NP, SRC>(P, a, smem, c, flat);
@@ -935,6 +965,7 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
         if (threadIdx.x == 0 && P.replays) atomicAdd(P.replays, 1);
         trace_riemann_body<MathExact, D, NP, SRC>(P, a, smem, c, flat);
     }
+    CTU_PT_END(0)
 }
 
 }  // namespace ctu

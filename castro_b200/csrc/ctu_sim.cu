@@ -582,37 +582,6 @@ __global__ void __launch_bounds__(TPB) k_grav_new(const DevPar P, const A4 Sb, c
 }  // namespace
 
 // ================================================================================================
-struct ctu_sim {
-    ctu_params_t par;
-    ctu_geom_t geom;
-    Box3 vbx, gbx;
-    int nstate = 0;
-    double* buf[2] = {nullptr, nullptr};
-    int cur = 0;
-    ctu_workspace_t* ws = nullptr;
-    cudaStream_t st = 0;
-    int step = 0;
-    int launches = 0;     // kernels launched by the sim itself (clean / fill / init), on top of the workspace's count
-    // constant gravity (par.do_grav): old-time source on grow(valid, NUM_GROW_SRC), mass fluxes for grav_source_type 4, dt reduction
-    double* osrc = nullptr;
-    double* mflux[3] = {nullptr, nullptr, nullptr};
-    unsigned long long* d_dt2 = nullptr;
-    // host-streaming step (ctu_sim_step_host): copy streams, double-buffered staging, hand-over events
-    cudaStream_t s_up = nullptr, s_dn = nullptr;
-    double* stage_up[2] = {nullptr, nullptr};
-    double* stage_dn[2] = {nullptr, nullptr};
-    size_t stage_doubles = 0;
-    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_upfree[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr}, ev_dnfree[2] = {nullptr, nullptr};
-    bool upfree_rec[2] = {false, false}, dnfree_rec[2] = {false, false};
-    ctu_fab_t fab(int which) const {
-        ctu_fab_t f;
-        f.p = buf[which];
-        for (int d = 0; d < 3; ++d) { f.lo[d] = gbx.lo[d]; f.hi[d] = gbx.hi[d]; }
-        f.ncomp = nstate;
-        return f;
-    }
-};
-
 extern "C" {
 
 // Source/driver/_cpp_parameters defaults; EOS/gamma_law/_parameters; networks/general_null/gammalaw.net
@@ -1036,10 +1005,13 @@ static int host_upload_planes(ctu_sim_t* s, const double* host, int b, int k0, i
     return ctu_clean_state(&s->par, lo, hi, f, 2, s->st);          // both clean_state passes of the reference (see ctu_sim_step_pre)
 }
 
-int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, double dt, double dt_est[2], int n_bad[2]) {
+}  // extern "C"
+
+int ctu::sim_step_host_impl(ctu_sim* s, SimHooks* hooks, const double* host_in, double* host_out, double dt, double dt_est[2], int n_bad[2]) {
     if (!s || !host_in || !host_out) return CTU_ERR_BAD_ARG;
-    for (int d = 0; d < 3; ++d)
-        if (s->vbx.lo[d] != s->geom.domlo[d] || s->vbx.hi[d] != s->geom.domhi[d]) return CTU_ERR_UNSUPPORTED;
+    if (!hooks)      // a single box must be the whole domain; with hooks the other boxes' zones arrive through the exchanges
+        for (int d = 0; d < 3; ++d)
+            if (s->vbx.lo[d] != s->geom.domlo[d] || s->vbx.hi[d] != s->geom.domhi[d]) return CTU_ERR_UNSUPPORTED;
     if (s->par.do_grav) return CTU_ERR_UNSUPPORTED;     // the streamed step covers pure hydro only
     const int nz = s->vbx.hi[2] - s->vbx.lo[2] + 1;
     const int zlo = s->vbx.lo[2], zhi = s->vbx.hi[2];
@@ -1055,6 +1027,7 @@ int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, dou
     kc = std::min(kc, hydro_max_slab_planes(run));
     if (kc < 1) { hydro_abort(run); return CTU_ERR_NOMEM; }
     if (kc < CTU_NGROW || kc > nz) kc = nz;
+    if (hooks && nz < 2 * CTU_NGROW) { hydro_abort(run); return CTU_ERR_UNSUPPORTED; }
     const int nchunk = (int)((nz + kc - 1) / kc);
     rc = hydro_reserve(run, kc);
     if (!rc) rc = host_step_setup(s, (int)kc);
@@ -1066,8 +1039,11 @@ int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, dou
     // boundary plane (k_fill<1> maps only the non-periodic dimensions), so that zone must already hold this step's data.
     rc = host_upload_planes(s, host_in, 0, zlo, zlo + np4 - 1, &sb);
     if (!rc) rc = host_upload_planes(s, host_in, 1, zhi - np4 + 1, zhi, &sb);
+    if (!rc && hooks) rc = hooks->exchange_planes(s, zlo, zlo + np4 - 1);      // x/y neighbours' zones of the boundary planes
+    if (!rc && hooks) rc = hooks->exchange_planes(s, zhi - np4 + 1, zhi);
     if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, zlo, zlo + np4 - 1, s->st);
     if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, zhi - np4 + 1, zhi, s->st);
+    if (!rc && hooks) rc = hooks->exchange_z(s);          // the z-ghost planes owned by other boxes (9 directions on each side)
     if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, zlo - CTU_NGROW, zlo - 1, s->st);
     if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, zhi + 1, zhi + CTU_NGROW, s->st);
     s->launches += 8;
@@ -1095,6 +1071,7 @@ int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, dou
     for (int c = 0; c < nchunk && !rc; ++c) {
         const int k0 = zlo + (int)(c * kc), k1 = std::min(zhi, k0 + (int)kc - 1);
         rc = host_upload_planes(s, host_in, c & 1, k0, k1, &sb);
+        if (!rc && hooks) rc = hooks->exchange_planes(s, k0, k1);
         // Castro::initialize_do_advance: boundary fill of the x/y ghosts of these planes (already twice cleaned, see ctu_sim_step_pre)
         if (!rc) rc = fill_boundary_planes(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, CTU_NGROW, k0, k1, s->st);
         s->launches += 2;
@@ -1109,6 +1086,12 @@ int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, dou
     return rc;
 }
 
+extern "C" {
+
+int ctu_sim_step_host(ctu_sim_t* s, const double* host_in, double* host_out, double dt, double dt_est[2], int n_bad[2]) {
+    return ctu::sim_step_host_impl(s, nullptr, host_in, host_out, dt, dt_est, n_bad);
+}
+
 // Castro::estTimeStep (Castro.cpp:1576-1668) given the raw CFL minimum
 static double est_time_step(const ctu_params_t& p, double raw) {
     if (p.fixed_dt > 0.0) return p.fixed_dt;
@@ -1119,15 +1102,44 @@ static double est_time_step(const ctu_params_t& p, double raw) {
     return r;
 }
 
-int ctu_sim_advance(ctu_sim_t* s, int nsteps, double stop_time, double* time_io, double* dt_io, double* dt_hist, int* steps_done) {
+}  // extern "C"
+
+// status bits and dt estimates agreed between the boxes: one MIN all-reduce of {est0, est1, -bit_k ..., -fatal}
+static int reduce_step(SimHooks* hooks, int& rc, double est[2]) {
+    if (!hooks) return 0;
+    double v[9];
+    v[0] = est[0]; v[1] = est[1];
+    const int bits = rc > 0 ? rc : 0;
+    for (int b = 0; b < 6; ++b) v[2 + b] = (bits >> b) & 1 ? -1.0 : 0.0;
+    v[8] = rc < 0 ? (double)rc : 0.0;                  // most negative error code wins
+    if (rc != 0) { v[0] = 1.e300; v[1] = 1.e300; }      // a failed box wrote no estimates
+    const int r = hooks->allreduce_min(v, 9);
+    if (r) return r;
+    est[0] = v[0]; est[1] = v[1];
+    if (v[8] < 0.0) { rc = (int)v[8]; return 0; }
+    int all = 0;
+    for (int b = 0; b < 6; ++b) if (v[2 + b] < 0.0) all |= 1 << b;
+    rc = all;
+    return 0;
+}
+
+int ctu::sim_advance_impl(ctu_sim* s, SimHooks* hooks, int nsteps, double stop_time, double* time_io, double* dt_io, double* dt_hist,
+                          int* steps_done) {
     if (!s || !time_io || !dt_io) return CTU_ERR_BAD_ARG;
     const ctu_params_t& p = s->par;
     double time = *time_io, dt = *dt_io;
     int status = 0, n = 0;
     if (dt <= 0.0) {   // computeInitialDt + initialTimeStep (Castro.cpp:1559-1573,1947-1992)
-        double raw;
+        double raw = 1.e300;
         ctu_fab_t f = s->fab(s->cur);
         int rc = ctu_estdt(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &f, &raw, nullptr, s->st);
+        if (hooks) {        // ParallelAllReduce::Min (Castro.cpp:1640); a failed rank makes everybody return
+            double v[2] = {rc ? 1.e300 : raw, rc < 0 ? (double)rc : 0.0};
+            const int r = hooks->allreduce_min(v, 2);
+            if (r) return r;
+            raw = v[0];
+            if (v[1] < 0.0) rc = (int)v[1];
+        }
         if (rc) return rc;
         double init_dt = (p.initial_dt > 0.0) ? p.initial_dt : p.init_shrink * est_time_step(p, raw);
         double dt_0 = std::min(1.0e+100, init_dt);
@@ -1137,15 +1149,16 @@ int ctu_sim_advance(ctu_sim_t* s, int nsteps, double stop_time, double* time_io,
     }
     for (; n < nsteps; ++n) {
         if (stop_time >= 0.0 && time >= stop_time) break;
-        int rc = ctu_sim_step_pre(s);
-        if (rc) return rc;
-        rc = ctu_sim_step_fill(s);
-        if (rc) return rc;
         // Castro::subcycle_advance_ctu (Castro_advance_ctu.cpp:301-303): the hydro sees the rounded time difference
         const double dt_sub = (time + dt) - time;
-        double est[2];
+        double est[2] = {1.e300, 1.e300};
         int nb[2];
-        rc = ctu_sim_step_hydro(s, dt_sub, est, nb);
+        // a box that fails keeps taking part in the collectives of the step, so that no peer is left waiting
+        int rc = ctu_sim_step_pre(s);
+        if (hooks) { const int r = hooks->exchange(s); if (!rc) rc = r; }
+        if (!rc) rc = ctu_sim_step_fill(s);
+        if (!rc) rc = ctu_sim_step_hydro(s, dt_sub, est, nb);
+        { const int r = reduce_step(hooks, rc, est); if (r) return r; }
         if (rc < 0) return rc;
         if (rc > 0) { status |= rc; break; }
         if (dt_hist) dt_hist[n] = dt;
@@ -1164,6 +1177,12 @@ int ctu_sim_advance(ctu_sim_t* s, int nsteps, double stop_time, double* time_io,
     *time_io = time; *dt_io = dt;
     if (steps_done) *steps_done = n;
     return status;
+}
+
+extern "C" {
+
+int ctu_sim_advance(ctu_sim_t* s, int nsteps, double stop_time, double* time_io, double* dt_io, double* dt_hist, int* steps_done) {
+    return ctu::sim_advance_impl(s, nullptr, nsteps, stop_time, time_io, dt_io, dt_hist, steps_done);
 }
 
 // ---- plotfile (single level, one grid): the layout of amrex::WriteSingleLevelPlotfile as Castro::writePlotFile emits it ------------

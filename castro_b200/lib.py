@@ -71,6 +71,21 @@ def lib():
                                         C.c_int, C.c_void_p]
         L.ctu_halo_pack.argtypes = [C.POINTER(abi.Fab), abi.Int3, abi.Int3, C.c_void_p, C.c_void_p]
         L.ctu_halo_unpack.argtypes = [C.POINTER(abi.Fab), abi.Int3, abi.Int3, C.c_void_p, C.c_void_p]
+        L.ctu_dist_unique_id.argtypes = [C.c_char_p]
+        L.ctu_dist_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, C.c_int, C.c_int,
+                                      C.c_char_p, C.c_size_t, C.c_void_p]
+        L.ctu_dist_destroy.argtypes = [C.c_void_p]
+        L.ctu_dist_sim.argtypes = [C.c_void_p]
+        L.ctu_dist_sim.restype = C.c_void_p
+        L.ctu_dist_box.argtypes = [C.c_void_p, abi.Int3, abi.Int3]
+        L.ctu_dist_halo_bytes.argtypes = [C.c_void_p]
+        L.ctu_dist_halo_bytes.restype = C.c_long
+        L.ctu_dist_exchange.argtypes = [C.c_void_p]
+        L.ctu_dist_allreduce_min.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        L.ctu_dist_advance.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ctu_dist_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ctu_dist_halo_plan.argtypes = [abi.Int3, C.c_int, abi.Int3, abi.Int3, abi.Int3, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ctu_selftest_mathfast.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
         L.ctu_problem_init.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3,
                                        C.POINTER(abi.Fab), C.c_void_p]
@@ -241,21 +256,39 @@ def problem_init(problem, prob, par, geom, lo, hi, S, s_lo, stream=0):
                                  abi.Int3(*hi), C.byref(f), stream), "ctu_problem_init")
 
 
+def dist_halo_plan(dims, rank, n_cell, periodic):
+    """the C++ neighbour table of one rank (ctu_dist_halo_plan; host logic only) -> (messages, receive order);
+    message = (direction, peer, send_lo, send_hi, recv_lo, recv_hi) like castro_b200.dist.halo_plan"""
+    out = (C.c_int * (16 * 26))()
+    ro = (C.c_int * 26)()
+    n = check(lib().ctu_dist_halo_plan(abi.Int3(*dims), rank, abi.Int3(0, 0, 0), abi.Int3(*[x - 1 for x in n_cell]), abi.Int3(*periodic),
+                                      26, out, ro), "ctu_dist_halo_plan")
+    msgs = []
+    for m in range(n):
+        o = out[16 * m:16 * m + 16]
+        msgs.append((tuple(o[0:3]), o[3], tuple(o[4:7]), tuple(o[7:10]), tuple(o[10:13]), tuple(o[13:16])))
+    return msgs, list(ro[:n])
+
+
 class Sim:
     """Single-box driver (one per rank): owns the ghosted ping-pong state buffers on the device."""
 
-    def __init__(self, par, geom, lo, hi, workspace_bytes=0, stream=0):
+    def __init__(self, par, geom, lo, hi, workspace_bytes=0, stream=0, _borrowed=None):
         self.par, self.geom = par, geom
         self.lo, self.hi = tuple(lo), tuple(hi)
         self.h = C.c_void_p()
-        check(lib().ctu_sim_create(C.byref(self.h), C.byref(par), C.byref(geom), abi.Int3(*lo), abi.Int3(*hi), workspace_bytes,
-                                   stream), "ctu_sim_create")
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self.h = C.c_void_p(_borrowed)          # the box of a Dist (owned by it)
+        else:
+            check(lib().ctu_sim_create(C.byref(self.h), C.byref(par), C.byref(geom), abi.Int3(*lo), abi.Int3(*hi), workspace_bytes,
+                                       stream), "ctu_sim_create")
         self.shape = (par.num_state,) + tuple(hi[d] - lo[d] + 1 for d in (2, 1, 0))
 
     def close(self):
-        if self.h:
+        if self.h and self._owned:
             lib().ctu_sim_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -343,3 +376,69 @@ class Sim:
     @property
     def last_slabs(self):
         return lib().ctu_workspace_last_slabs(lib().ctu_sim_workspace(self.h))
+
+
+class Dist:
+    """Multi-box driver in C++ over NCCL (ctu_dist_*): one process per GPU, one equal box per process.  `comm` is an initialised
+    torch.distributed (used once, as plumbing, to carry the ncclUniqueId from rank 0 to the other ranks) or None for one box."""
+
+    def __init__(self, par, geom, dims, rank=0, world=1, comm=None, workspace_bytes=0, stream=0):
+        self.par, self.geom, self.dims, self.rank, self.world = par, geom, tuple(dims), rank, world
+        idbuf = C.create_string_buffer(128)
+        if world > 1:
+            import torch
+            t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                check(lib().ctu_dist_unique_id(idbuf), "ctu_dist_unique_id")
+                t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
+            comm.broadcast(t, src=0)
+            idbuf = C.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+        self.h = C.c_void_p()
+        check(lib().ctu_dist_create(C.byref(self.h), C.byref(par), C.byref(geom), abi.Int3(*dims), rank, world, idbuf, workspace_bytes,
+                                    stream), "ctu_dist_create")
+        lo, hi = abi.Int3(), abi.Int3()
+        check(lib().ctu_dist_box(self.h, lo, hi), "ctu_dist_box")
+        self.lo, self.hi = tuple(lo), tuple(hi)
+        self.sim = Sim(par, geom, self.lo, self.hi, _borrowed=lib().ctu_dist_sim(self.h))
+        self.time, self.dt = 0.0, -1.0
+
+    def close(self):
+        if self.h:
+            self.sim.close()
+            lib().ctu_dist_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init_problem(self, problem, prob):
+        self.sim.init_problem(problem, prob)
+
+    @property
+    def halo_bytes_per_step(self):
+        return int(lib().ctu_dist_halo_bytes(self.h))
+
+    def advance(self, nsteps, stop_time=-1.0):
+        """-> (status, dt history); time and dt are kept on the object"""
+        t, d = C.c_double(self.time), C.c_double(self.dt)
+        hist = (C.c_double * max(nsteps, 1))()
+        done = C.c_int(0)
+        rc = check(lib().ctu_dist_advance(self.h, nsteps, stop_time, C.byref(t), C.byref(d), hist, C.byref(done)), "ctu_dist_advance")
+        self.time, self.dt = t.value, d.value
+        return rc, list(hist[:done.value])
+
+    def estdt_global(self):
+        v = (C.c_double * 1)(self.sim.estdt())
+        check(lib().ctu_dist_allreduce_min(self.h, v, 1), "ctu_dist_allreduce_min")
+        return v[0]
+
+    def step_host(self, host_in, host_out, dt):
+        """one step of this rank's box with the state in host memory (streamed z-chunks, halo exchange inside the pipeline)"""
+        assert host_in.shape == self.sim.shape and host_out.shape == self.sim.shape
+        est = (C.c_double * 2)()
+        st = C.c_int(0)
+        check(lib().ctu_dist_step_host(self.h, host_in.ctypes.data, host_out.ctypes.data, dt, est, C.byref(st)), "ctu_dist_step_host")
+        return st.value, (est[0], est[1])

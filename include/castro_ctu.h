@@ -266,6 +266,40 @@ int  ctu_sim_advance(ctu_sim_t* sim, int nsteps, double stop_time, double* time_
  * so that the reference's own comparator (external/amrex/Tools/Plotfile/fcompare.cpp) can diff the two codes. */
 int  ctu_sim_write_plotfile(ctu_sim_t* sim, const char* dir, double time, int step);
 
+/* ---- multi-box driver: one process per GPU, one equal box per process, NCCL over NVLink -----------------------
+ * Replaces, for amr.max_level = 0 and a uniform decomposition px x py x pz of the domain:
+ *   AmrLevel::FillPatch -> FabArray::FillBoundary   (Castro_advance.cpp:169; AMReX_FabArrayCommI.H:11-320, AMReX_FBI.H:534-900):
+ *       NUM_STATE x 4 ghost layers from up to 26 neighbour boxes (faces, edges, corners; periodic wrap), one fused pack kernel,
+ *       one ncclGroup of send/recv, one fused unpack kernel;
+ *   ParallelAllReduce::Min(dt) (Castro.cpp:1640) and ParallelDescriptor::ReduceIntMax(status) (Castro.cpp:3387): one small
+ *       ncclAllReduce(min) per step that carries both dt estimates, every status bit and the fatal-error code.
+ * geom describes the WHOLE domain; rank r owns the box at process-grid coordinates (r % px, (r / px) % py, r / (px py)).
+ * NCCL is bound at run time (libnccl.so.2); the caller carries the 128-byte ncclUniqueId from rank 0 to the other ranks
+ * (any launcher mechanism: torch.distributed broadcast, a file, MPI_Bcast) and every rank then calls ctu_dist_create. */
+typedef struct ctu_dist ctu_dist_t;
+int  ctu_dist_unique_id(char id[128]);                      /* rank 0: ncclGetUniqueId */
+int  ctu_dist_create(ctu_dist_t** dist, const ctu_params_t* par, const ctu_geom_t* geom, const int dims[3], int rank, int world,
+                     const char id[128] /* ignored when world == 1 */, size_t workspace_bytes, void* stream);
+void ctu_dist_destroy(ctu_dist_t* dist);
+ctu_sim_t* ctu_dist_sim(ctu_dist_t* dist);                  /* this rank's box (ctu_sim_init_problem, ctu_sim_download, ...) */
+int  ctu_dist_box(const ctu_dist_t* dist, int lo[3], int hi[3]);
+long ctu_dist_halo_bytes(const ctu_dist_t* dist);           /* bytes this rank sends per exchange */
+int  ctu_dist_exchange(ctu_dist_t* dist);                   /* FillBoundary of the current state (collective) */
+int  ctu_dist_allreduce_min(ctu_dist_t* dist, double* v, int n /* <= 16 */);   /* host values in / out (collective) */
+/* ctu_sim_advance over all boxes: pre -> exchange -> fill -> hydro -> all-reduce -> dt control; every rank returns the same
+ * status, time and dt history.  Collective. */
+int  ctu_dist_advance(ctu_dist_t* dist, int nsteps, double stop_time, double* time_inout, double* dt_inout,
+                      double* dt_history, int* steps_done);
+/* ctu_sim_step_host for this rank's box of a multi-box run (host_in / host_out: the box's valid zones): the z-chunk pipeline with
+ * the halo exchange inside it -- the first / last four planes travel ahead and feed the z-neighbours, every chunk exchanges its
+ * x/y halos as soon as it is on the device.  dt_est and *status are already reduced over the ranks.  Collective. */
+int  ctu_dist_step_host(ctu_dist_t* dist, const double* host_in, double* host_out, double dt, double dt_est[2], int* status);
+/* the neighbour table of one rank (pure host logic, no GPU needed): out[16 * m] = {d[3], peer, send_lo[3], send_hi[3], recv_lo[3],
+ * recv_hi[3]} for message m in the order the sends are posted; recv_order[m] = index of the m-th receive posted.  Returns the
+ * number of messages (<= 26) or CTU_ERR_*. */
+int  ctu_dist_halo_plan(const int dims[3], int rank, const int domlo[3], const int domhi[3], const int periodic[3], int max_msgs,
+                        int* out, int* recv_order);
+
 /* Self-test of the branch-free FP64 division / reciprocal / square-root sequences the flux-stage kernels compute with (they
  * restate the fast path of nvcc's own IEEE operators; a kernel replays a tile with the language operators whenever a sequence
  * flags an operand).  Draws `iters` random operand pairs per thread (131072 threads) with binary exponents uniform in

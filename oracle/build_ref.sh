@@ -20,6 +20,13 @@
 #                                        problem_initialize_state_data.H:50); the recipe qualifies that one identifier in the SCRATCH COPY of
 #                                        the problem directory.  No file of the hot path (Source/hydro, Source/driver, Source/gravity) is touched.
 #   oracle/_ref/fcompare.ex              AMReX plotfile comparator (DIM=3)
+#   oracle/_ref/Castro3d_sedov_cuda.ex   (`gpu`)  the UNMODIFIED reference built with its own GPU back end (USE_CUDA=TRUE CUDA_ARCH=100):
+#                                        Castro's stock unfused ParallelFor pipeline on the same B200 -- the "reference_gpu" baseline
+#   oracle/_ref/Castro3d_sedov_stub.ex   (`stub`) the same GPU build with ONE source file swapped: integration/Castro_ctu_hydro.cpp (this
+#                                        repository's binding of Castro::construct_ctu_hydro_source to libcastro_ctu.so) is copied into the
+#                                        scratch problem directory, where Castro's VPATH finds it before Source/hydro/Castro_ctu_hydro.cpp.
+#                                        Everything else (driver, FillPatch, clean_state, estdt, plotfile I/O) is the reference's own code.
+#                                        Neither is built by `all` (20 min of nvcc); build() asks for them when they are missing.
 set -euo pipefail
 REF=${REF:-/root/reference}
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -50,6 +57,21 @@ if [ "$what" = all ] || [ "$what" = rt ]; then
   if [ ! -d "$W/Castro3d_rt" ]; then cp -r "$REF/Exec/hydro_tests/RT" "$W/Castro3d_rt"; fi
   sed -i 's/0.5e0_rt \* L_x/0.5e0_rt * problem::L_x/' "$W/Castro3d_rt/problem_initialize_state_data.H"
   build RT Castro3d_rt DIM=3
+fi
+if [ "$what" = gpu ]; then build Sedov Castro3d_sedov_cuda DIM=3 USE_CUDA=TRUE CUDA_ARCH=100; fi
+if [ "$what" = stub ]; then
+  REPO="$(cd "$HERE/.." && pwd)"
+  d="$W/Castro3d_sedov_stub"
+  if [ ! -d "$d" ]; then
+    if [ -d "$W/Castro3d_sedov_cuda" ]; then cp -r "$W/Castro3d_sedov_cuda" "$d"; rm -f "$d"/Castro*.ex;      # reuse the objects of the stock GPU build
+    else cp -r "$REF/Exec/hydro_tests/Sedov" "$d"; fi
+  fi
+  cp "$REPO/integration/Castro_ctu_hydro.cpp" "$d/Castro_ctu_hydro.cpp"
+  if ! grep -q castro_ctu "$d/GNUmakefile"; then
+    sed -i "s|^include \$(CASTRO_HOME)/Exec/Make.Castro|INCLUDE_LOCATIONS += $REPO/include\nLIBRARIES += -L$REPO/castro_b200 -lcastro_ctu -Xlinker -rpath -Xlinker /root/repo/castro_b200\n&|" "$d/GNUmakefile"
+  fi
+  [ -f "$REPO/castro_b200/libcastro_ctu.so" ] || make -C "$REPO/castro_b200/csrc" -j"$J"
+  build Sedov Castro3d_sedov_stub DIM=3 USE_CUDA=TRUE CUDA_ARCH=100
 fi
 if [ "$what" = all ] || [ "$what" = fcompare ]; then
   d="$W/fcompare"; mkdir -p "$d"; cp -r "$REF/external/amrex/Tools/Plotfile/"* "$d"/

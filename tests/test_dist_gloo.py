@@ -84,3 +84,33 @@ def test_halo_plan_symmetry():
                 m = match[0]
                 sz = lambda lo, hi: tuple(hi[a] - lo[a] + 1 for a in range(3))
                 assert sz(slo, shi) == sz(m[4], m[5])
+
+
+@pytest.mark.parametrize("dims,n_cell,periodic", [((2, 1, 1), (16, 16, 16), (0, 0, 0)), ((2, 1, 1), (16, 16, 16), (1, 1, 1)),
+                                                   ((2, 2, 1), (32, 16, 8), (1, 0, 1)), ((2, 2, 2), (16, 16, 16), (1, 1, 1)),
+                                                   ((2, 2, 2), (16, 32, 16), (0, 0, 0)), ((1, 1, 2), (8, 8, 16), (1, 1, 0)),
+                                                   ((3, 1, 2), (24, 8, 16), (1, 1, 1))])
+def test_cpp_halo_plan_matches_python_plan(dims, n_cell, periodic):
+    """the neighbour table of the C++ multi-box layer (ctu_dist_halo_plan, the one the GPUs run) against castro_b200.dist.halo_plan
+    (the one the gloo tests above exercise end to end): same messages in the same send order, same receive order, and every
+    message has its mirror image on the peer (sizes agree, pairs of ranks match their messages in posting order)"""
+    from castro_b200 import lib
+    from castro_b200.dist import halo_plan, DIRECTIONS
+    world = dims[0] * dims[1] * dims[2]
+    plans = {}
+    for rank in range(world):
+        msgs, ro = lib.dist_halo_plan(dims, rank, n_cell, periodic)
+        ref = halo_plan(rank, dims, n_cell, periodic)
+        assert msgs == [(tuple(m[0]), m[1], tuple(m[2]), tuple(m[3]), tuple(m[4]), tuple(m[5])) for m in ref]
+        want = sorted(range(len(ref)), key=lambda i: DIRECTIONS.index(tuple(-x for x in ref[i][0])))
+        assert ro == want
+        plans[rank] = (msgs, ro)
+    # NCCL matches the k-th send from a to b with the k-th receive b posts from a
+    for a in range(world):
+        for b in range(world):
+            sends = [m for m in plans[a][0] if m[1] == b]
+            recvs = [plans[b][0][i] for i in plans[b][1] if plans[b][0][i][1] == a]
+            assert len(sends) == len(recvs)
+            for s_, r_ in zip(sends, recvs):
+                assert tuple(-x for x in s_[0]) == r_[0]
+                assert [s_[3][d] - s_[2][d] for d in range(3)] == [r_[5][d] - r_[4][d] for d in range(3)]

@@ -471,6 +471,38 @@ def test_plotfile_vs_reference_with_fcompare(solver, n_cell, nsteps, wsb, tmp_pa
     _fcompare_exact(fcmp, ref_pf, my_pf)
 
 
+def test_reference_executable_with_stub_binding(tmp_path):
+    """The drop-in boundary compiled and run for real: oracle/_ref/Castro3d_sedov_stub.ex is the reference's own GPU build
+    (USE_CUDA=TRUE) with ONE source file swapped -- integration/Castro_ctu_hydro.cpp, which binds Castro::construct_ctu_hydro_source to
+    ctu_hydro_advance of libcastro_ctu.so (oracle/build_ref.sh stub).  Driver, FillPatch, clean_state, estdt, dt control and plotfile
+    I/O are the reference's.  Its plotfile must agree with the stock CPU executable's to the north star's 1e-12 (not bitwise: the
+    reference's own device code around the call is compiled by nvcc with FMA contraction)."""
+    import os
+    import re
+    import subprocess
+    _torch()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stub = os.path.join(root, "oracle", "_ref", "Castro3d_sedov_stub.ex")
+    if not os.path.exists(stub):
+        pytest.skip("oracle/_ref/Castro3d_sedov_stub.ex not built (oracle/build_ref.sh gpu && oracle/build_ref.sh stub)")
+    n_cell, nsteps = (64, 64, 64), 10
+    for solver in (2, 0):
+        d = tmp_path / ("s%d" % solver)
+        d.mkdir()
+        ref_pf, fcmp, inputs = _run_reference_plotfile(d, n_cell, solver, nsteps)
+        args = [stub, inputs, "amr.n_cell=%d %d %d" % n_cell, "castro.riemann_solver=%d" % solver, "amr.max_grid_size=32",
+                "amr.blocking_factor=4", "max_step=%d" % nsteps, "amr.plot_files_output=1", "amr.plot_int=%d" % nsteps,
+                "amr.plot_file=%s" % (d / "stub_plt"), "amr.derive_plot_vars=NONE", "castro.v=1", "amr.v=0"]
+        env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(root, "castro_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        out = subprocess.run(args, cwd=d, capture_output=True, text=True, env=env)
+        assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+        assert "[libcastro_ctu]" in out.stdout, "the run did not go through the binding"
+        res = subprocess.run([fcmp, "--rel_tol", "1e-12", str(ref_pf), str(d / ("stub_plt%05d" % nsteps))], capture_output=True, text=True)
+        assert res.returncode == 0 and "PLOTFILE AGREE" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+        rows = re.findall(r"^\s*(\w+)\s+([0-9.eE+-]+)\s+([0-9.eE+-]+)\s*$", res.stdout, flags=re.M)
+        assert len(rows) == 8 and max(float(r[2]) for r in rows) <= REL_TOL, res.stdout
+
+
 def test_host_streaming_mixed_boundaries():
     """ctu_sim_step_host promises the bits of upload + pre + fill + hydro + download.  Periodic x/y with a physical boundary in z
     (reflecting wall below, outflow above) is the case where a z-ghost zone is filled from an x/y-ghost zone of the boundary plane:
