@@ -141,12 +141,21 @@ def reference_arm(args, rank):
 def workload_config(args, world, cpu_sample=None):
     from castro_b200.dist import proc_grid
     dims = proc_grid(world)
-    w = ("Exec/hydro_tests/Sedov 3-D, %d^3 zones per GPU (global %s), gamma-law EOS gamma=1.4, CTU-PPM + %s, "
-         "single level, outflow BCs, cfl 0.5" % (args.n, "x".join(str(args.n * d) for d in dims), "HLLC" if args.solver == 2 else "CGF"))
+    prob = getattr(args, "problem", "sedov")
+    if getattr(args, "scaling", "weak") == "strong":
+        w = ("Exec/hydro_tests/%s 3-D, global %d^3 zones cut over %d GPU(s) as %s, gamma-law EOS, CTU-PPM + %s, single level" % (
+            {"sedov": "Sedov", "kh": "KH (NUMADV=1 + %d species)" % args.nspec, "rt": "RT"}[prob], args.global_n, world,
+            "x".join(str(d) for d in dims), "HLLC" if args.solver == 2 else "CGF"))
+    elif prob != "sedov":
+        w = ("Exec/hydro_tests/%s 3-D, %d^3 zones per GPU, gamma-law EOS, CTU-PPM + %s, single level (developer option, not the "
+             "benchmark configuration)" % (prob.upper(), args.n, "HLLC" if args.solver == 2 else "CGF"))
+    else:
+        w = ("Exec/hydro_tests/Sedov 3-D, %d^3 zones per GPU (global %s), gamma-law EOS gamma=1.4, CTU-PPM + %s, "
+             "single level, outflow BCs, cfl 0.5" % (args.n, "x".join(str(args.n * d) for d in dims), "HLLC" if args.solver == 2 else "CGF"))
     if cpu_sample:      # the reference CPU arm times a bounded sample of that workload (its zone rate does not depend on the box size)
         w += "; TIMED HERE ON THE HOST CORES AS A BOUNDED SAMPLE: " + cpu_sample
     return {"workload": w,
-            "zones_per_gpu": args.n ** 3, "num_state": 7 + getattr(args, "nspec", 1) + (1 if getattr(args, "problem", "sedov") == "kh" else 0),
+            "zones_per_gpu": (args.global_n ** 3 // world) if getattr(args, "scaling", "weak") == "strong" else args.n ** 3, "num_state": 7 + getattr(args, "nspec", 1) + (1 if getattr(args, "problem", "sedov") == "kh" else 0),
             "problem": getattr(args, "problem", "sedov"), "proc_grid": list(dims),
             "l2": "inputs larger than L2 (state %.1f GB per GPU); no explicit flush" % (8 * 8 * (args.n + 8) ** 3 / 1e9)}
 
@@ -275,7 +284,13 @@ def gpu_arm(args):
 
     dims = proc_grid(world)
     n = args.n
-    n_cell = tuple(n * d for d in dims)
+    strong = args.scaling == "strong"
+    if strong:       # fixed global box (BASELINE config[3]: KH 1024^3 over the GPUs of the node), cut into equal boxes
+        assert all(args.global_n % d == 0 for d in dims)
+        n_cell = (args.global_n,) * 3
+    else:
+        n_cell = tuple(n * d for d in dims)
+    box = tuple(n_cell[a] // dims[a] for a in range(3))          # zones of one rank's box (x, y, z)
     par = lib.default_params()
     par.riemann_solver = args.solver
     par.cfl, par.init_shrink, par.change_max = 0.5, 0.01, 1.1
@@ -292,7 +307,10 @@ def gpu_arm(args):
         par.cfl, par.init_shrink, par.change_max = 0.5, 0.1, 1.1
         par.small_dens, par.small_temp = 1.e-10, 1.e-10
         par.eos_gamma = 5.0 / 3.0
-        par.nadv, par.nspec = 1, 1
+        par.nadv, par.nspec = 1, args.nspec
+        if args.nspec == 4:       # networks/general_null/triple_alpha_plus_o.net: He4 C12 O16 Fe56 (BASELINE config[3])
+            for m, (a_, z_) in enumerate(((4.0, 2.0), (12.0, 6.0), (16.0, 8.0), (56.0, 26.0))):
+                par.aion[m], par.zion[m] = a_, z_
         geom_kw = dict(periodic=(1, 1, 1), lo_bc=(0, 0, 0), hi_bc=(0, 0, 0))
         prob = dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0)
     elif args.problem == "rt":    # developer option: bench_inputs/inputs.rt3d on a cube of n^3 zones, constant gravity, grav_source_type 4
@@ -303,7 +321,8 @@ def gpu_arm(args):
         geom_kw = dict(periodic=(1, 1, 0), lo_bc=(0, 0, 4), hi_bc=(0, 0, 4))
         prob = dict(frac=0.5, rho_1=1.0, rho_2=2.0, p0_base=5.0)
     lib.params_finalize(par)
-    geom = abi.make_geom(n_cell, probhi=tuple(float(d) for d in dims), **geom_kw)     # dx = 1/n whatever the process grid
+    # weak scaling: dx = 1/n whatever the process grid; strong scaling: the unit cube
+    geom = abi.make_geom(n_cell, probhi=(1.0, 1.0, 1.0) if strong else tuple(float(d) for d in dims), **geom_kw)
 
     def barrier():
         if dist is not None:
@@ -318,7 +337,7 @@ def gpu_arm(args):
     sim.init_problem(problem, prob)
     eng = sim.sim
     ws = eng.ws_handle
-    zones_local = n ** 3
+    zones_local = box[0] * box[1] * box[2]
     zones_total = zones_local * world
 
     # ---- warm-up -------------------------------------------------------------------------------------------------
@@ -357,9 +376,13 @@ def gpu_arm(args):
     from castro_b200.dist import new_dt
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     nbytes = 8 * par.num_state * zones_local
-    host = torch.empty((2, par.num_state, n, n, n), dtype=torch.float64, pin_memory=True)
+    do_e2e = args.e2e_steps > 0 and 2 * nbytes <= (args.e2e_max_gb << 30)     # two pinned copies of the box per rank must fit the host
+    if not do_e2e:
+        e2e_steps = 0
+    host = torch.empty((2, par.num_state, box[2], box[1], box[0]) if do_e2e else (2, 1, 1, 1, 1 << 27), dtype=torch.float64, pin_memory=True)
     hin, hout = host[0].numpy(), host[1].numpy()
-    eng.download(out=hin)
+    if do_e2e:
+        eng.download(out=hin)
     streamed = not par.do_grav                      # the host-streamed step covers pure hydro
     e2e_mode = "streamed z-chunks (ctu_dist_step_host%s)" % (", halo exchange inside the pipeline" if world > 1 else "") if streamed \
         else "upload + step + download"
@@ -377,7 +400,8 @@ def gpu_arm(args):
             st_, _ = sim.advance(1)
             assert st_ == 0
             eng.download(out=hin)           # device -> pinned host
-    e2e_step()                              # one untimed step (allocates the staging buffers)
+    if do_e2e:
+        e2e_step()                          # one untimed step (allocates the staging buffers)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
@@ -389,9 +413,9 @@ def gpu_arm(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    e2e_value = zones_total * e2e_steps / (e2e_ms * 1e-3)
+    e2e_value = zones_total * e2e_steps / (e2e_ms * 1e-3) if do_e2e else None
     # what the host side can deliver when all N ranks copy at once: 1 GiB up and 1 GiB down per rank, concurrently (explains e2e)
-    pc_n = 1 << 27
+    pc_n = min(1 << 27, host.numel() // 2)
     pc_h = host.view(-1)[:2 * pc_n]
     pc_d = torch.empty(2 * pc_n, dtype=torch.float64, device="cuda")
     s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
@@ -460,12 +484,15 @@ def gpu_arm(args):
             import shutil
             shutil.rmtree(pdir, ignore_errors=True)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "metric": METRIC if (args.problem == "sedov" and not strong) else
+            "zone-updates/sec (FP64 CTU-PPM, 3D %s, %s)" % (args.problem.upper(), "global %d^3 strong scaling" % args.global_n if strong
+                                                             else "%d^3 per GPU" % n),
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "mode": e2e_mode,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps if do_e2e else None, "mode": e2e_mode,
                     "host_copy_gbs_per_rank_each_way": pcie_gbs,
                     "copy_floor_ms_per_step": nbytes / (pcie_gbs * 1e9) * 1e3,
                     "note": "host_copy_gbs = measured here with all N ranks copying 1 GiB up and 1 GiB down at once from pinned memory; "
@@ -496,6 +523,10 @@ def main():
     ap.add_argument("--solver", type=int, default=2, help="castro.riemann_solver: 2 = HLLC, 0 = CGF")
     ap.add_argument("--workspace-gb", type=int, default=48, help="device scratch bound for the z-slab pipeline")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-max-gb", type=int, default=24, help="skip the e2e leg when two pinned host copies of a rank's box exceed this")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --n^3 zones per GPU (the benchmark); strong: a fixed --global-n^3 box cut over the GPUs (config[3])")
+    ap.add_argument("--global-n", type=int, default=1024)
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")

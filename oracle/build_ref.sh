@@ -14,6 +14,8 @@
 #   oracle/_ref/Castro3d_sedov.ex        serial, -O3, no FMA  (parity oracle, golden generator)
 #   oracle/_ref/Castro3d_sedov_omp.ex    OpenMP build         (CPU baseline for bench.py)
 #   oracle/_ref/Castro3d_kh.ex           Kelvin-Helmholtz problem, serial (golden generator for the 2-passive path)
+#   oracle/_ref/Castro3d_kh4.ex          (`kh4`) KH built with NETWORK_INPUTS=triple_alpha_plus_o.net (4 species + 1 advected scalar: NUM_STATE = 12,
+#                                        BASELINE config[3]); golden generator for the 5-passive tile kernels
 #   oracle/_ref/Castro3d_sod.ex          Sod shock-tube problem in 3-D, serial (golden generator for BASELINE config[0])
 #   oracle/_ref/Castro3d_rt.ex           Rayleigh-Taylor problem with constant gravity, serial (golden generator for the source-term path).
 #                                        The reference's RT initial-data header does not compile with DIM=3 (an unqualified `L_x`,
@@ -52,6 +54,8 @@ if [ "$what" = all ] || [ "$what" = omp ];    then build Sedov Castro3d_sedov_om
 # KH as shipped: NUMADV := 1 in its GNUmakefile -> NUM_STATE = 9 (one advected scalar + one species): pins the 2-passive path
 if [ "$what" = all ] || [ "$what" = kh ];     then build KH Castro3d_kh DIM=3; fi
 # Sod shock tube (BASELINE config[0]) built in 3-D: the tube along x, y or z exercises the three directional code paths
+# KH with a 4-species network (BASELINE config[3]: NUMADV=1 + triple_alpha_plus_o.net -> NUM_STATE = 12): golden generator for the 5-passive path
+if [ "$what" = kh4 ]; then build KH Castro3d_kh4 DIM=3 NETWORK_INPUTS=triple_alpha_plus_o.net; fi
 if [ "$what" = all ] || [ "$what" = sod ];    then build Sod Castro3d_sod DIM=3; fi
 if [ "$what" = all ] || [ "$what" = rt ]; then
   if [ ! -d "$W/Castro3d_rt" ]; then cp -r "$REF/Exec/hydro_tests/RT" "$W/Castro3d_rt"; fi

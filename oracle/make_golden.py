@@ -77,6 +77,15 @@ KH_CASES = {
 }
 
 
+# KH with the 4-species network of BASELINE config[3] (NETWORK_INPUTS=triple_alpha_plus_o.net + NUMADV=1 -> NUM_STATE = 12): pins the
+# 5-passive path (species-flux normalisation over 4 species, mean molecular weight of a mixture) against the reference
+KH4_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_kh4.ex")
+KH4_CASES = {
+    "kh16_4spec_cgf": ((16, 16, 8), 10, [0, 10], ["castro.riemann_solver=0", "problem.bulk_velocity=0.2"]),
+    "kh16_4spec_hllc": ((32, 16, 8), 10, [0, 10], ["castro.riemann_solver=2", "geometry.prob_hi=2.0 1.0 0.5"]),
+}
+
+
 # Rayleigh-Taylor with constant gravity (pins the source-term path: old/new gravity sources, src_to_prim, traced sources)
 RT_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_rt.ex")
 RT_INPUTS = os.path.join(ROOT, "bench_inputs", "inputs.rt3d")
@@ -151,6 +160,10 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case(name, n, ms, snaps, extra, exe=KH_EXE, inputs=KH_INPUTS)
+    for name, (n, ms, snaps, extra) in KH4_CASES.items():
+        if only and name not in only:
+            continue
+        run_case(name, n, ms, snaps, extra, exe=KH4_EXE, inputs=KH_INPUTS)
     for name, (n, ms, snaps, extra) in RT_CASES.items():
         if only and name not in only:
             continue

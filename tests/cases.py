@@ -69,7 +69,11 @@ KH_CASES = {
     "kh16_cgf": dict(solver=0, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0)),
     "kh16_hllc": dict(solver=2, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.3)),
     "kh16_cgf_nolim": dict(solver=0, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0), par=dict(ppm_do_limiting=0)),
+    # BASELINE config[3]'s build: NUMADV = 1 + the 4 species of triple_alpha_plus_o.net (He4 C12 O16 Fe56) -> NUM_STATE = 12
+    "kh16_4spec_cgf": dict(solver=0, nspec=4, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.2)),
+    "kh16_4spec_hllc": dict(solver=2, nspec=4, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0)),
 }
+KH4_NET = ((4.0, 2.0), (12.0, 6.0), (16.0, 8.0), (56.0, 26.0))      # networks/general_null/triple_alpha_plus_o.net: aion, zion
 
 
 def load_kh_case(name):
@@ -81,7 +85,10 @@ def load_kh_case(name):
     par.riemann_solver = c["solver"]
     par.cfl, par.init_shrink, par.change_max = 0.5, 0.1, 1.1
     par.small_dens, par.small_temp = 1.e-10, 1.e-10
-    par.nadv, par.nspec = 1, 1
+    par.nadv, par.nspec = 1, c.get("nspec", 1)
+    if par.nspec == 4:
+        for m, (a, z) in enumerate(KH4_NET):
+            par.aion[m], par.zion[m] = a, z
     for k, v in c.get("par", {}).items():
         setattr(par, k, v)
     n_cell = tuple(int(x) for x in g["n_cell"])

@@ -37,7 +37,7 @@ def test_oracle_matches_reference_bitwise(name):
     np.testing.assert_allclose(np.array(times), g["times"][:len(times)], rtol=1e-14, atol=0)
 
 
-@pytest.mark.parametrize("name", ["kh16_cgf", "kh16_hllc", "kh16_cgf_nolim"])
+@pytest.mark.parametrize("name", ["kh16_cgf", "kh16_hllc", "kh16_cgf_nolim", "kh16_4spec_cgf", "kh16_4spec_hllc"])
 def test_oracle_two_passives_matches_kh_golden(name):
     """NUM_STATE = 9 (advected scalar + species): the oracle, started from the reference's own initial plotfile, must land
     bit for bit on the reference's state after 10 steps (pins the passive indexing and the periodic time loop)."""
