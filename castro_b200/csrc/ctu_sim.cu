@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 #include <sys/stat.h>
+#include <dlfcn.h>
 
 #include "ctu_kernels.cuh"
 #include "ctu_internal.h"
@@ -409,6 +410,35 @@ int rt_init(const ctu_params_t* par, const ctu_geom_t* g, const std::map<std::st
     return 0;
 }
 
+// Source-compatible problem hooks: "hook:<path>" names a library built by tools/build_problem_hook.sh from the reference's UNMODIFIED
+// Exec/<problem>/problem_initialize.H + problem_initialize_state_data.H (castro_b200/hooks/).  The hook fills the box on the host
+// (host libm = the reference CPU executable's bits), the box is uploaded, and the common tail of Castro::initData follows.
+int hook_init(const std::string& path, const char* prob_params, const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3],
+              const int hi[3], ctu_fab_t* S, cudaStream_t st) {
+    void* h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!h) { std::fprintf(stderr, "[castro_ctu] problem hook %s: %s\n", path.c_str(), dlerror()); return CTU_ERR_IO; }
+    typedef int (*InitFn)(const char*, const ctu_params_t*, const ctu_geom_t*, const int*, const int*, double*, const int*, const int*);
+    typedef int (*NsFn)(void);
+    InitFn init = (InitFn)dlsym(h, "ctu_hook_init");
+    NsFn ns = (NsFn)dlsym(h, "ctu_hook_num_state");
+    if (!init || !ns) { dlclose(h); return CTU_ERR_IO; }
+    const int nc = ctu_num_state(par);
+    if (ns() != nc) { std::fprintf(stderr, "[castro_ctu] problem hook %s is built for NUM_STATE = %d, the run has %d\n", path.c_str(), ns(), nc); dlclose(h); return CTU_ERR_BAD_ARG; }
+    const Box3 bx = make_box(lo, hi);
+    const size_t n = (size_t)bx.npts() * nc;
+    std::vector<double> host(n);
+    int rc = init(prob_params, par, geom, lo, hi, host.data(), lo, hi);
+    dlclose(h);
+    if (rc) return rc;
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, n * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(d, host.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = ctu_halo_unpack(S, lo, hi, d, st);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaFree(d));
+    return rc;
+}
+
 // Castro::initData tail (Castro.cpp:1186-1413): computeTemp -> enforce_consistent_e (:3215-3265) -> clean_state
 __global__ void __launch_bounds__(TPB) k_init_tail(const DevPar P, const A4 S, const LaunchBox lb) {
     int i, j, k;
@@ -655,7 +685,8 @@ int ctu_problem_init(const char* problem, const char* prob_params, const ctu_par
     cudaStream_t st = (cudaStream_t)stream;
     auto kv = parse_kv(prob_params);
     std::string name(problem);
-    if (name == "Sedov") rc = sedov_init(par, geom, kv, P, a, lb, st);
+    if (name.rfind("hook:", 0) == 0) rc = hook_init(name.substr(5), prob_params, par, geom, lo, hi, S, st);
+    else if (name == "Sedov") rc = sedov_init(par, geom, kv, P, a, lb, st);
     else if (name == "Sod") rc = sod_init(par, geom, kv, P, a, lb, st);
     else if (name == "KH") rc = kh_init(par, geom, kv, P, a, lb, st);
     else if (name == "RT") rc = rt_init(par, geom, kv, P, a, lb, st);

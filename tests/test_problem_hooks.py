@@ -1,0 +1,102 @@
+"""Source-compatible problem hooks (north star: "keeps Castro's problem-setup hooks"): the reference's UNMODIFIED
+Exec/hydro_tests/<problem>/problem_initialize.H + problem_initialize_state_data.H are compiled against castro_b200/hooks/shim by
+tools/build_problem_hook.sh (done by build() where /root/reference is mounted; the .so files travel to the GPU box).
+CPU tests: hook output + the tail of Castro::initData (oracle) == the reference's initial plotfile, bit for bit.
+GPU test: ctu_problem_init("hook:<lib>") == the reference's initial plotfile and == the library's built-in problem kernels."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from castro_b200 import abi
+from cases import GOLDEN, load_case, load_kh_case, load_sod_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOOKS = os.path.join(ROOT, "castro_b200", "hooks")
+
+
+def hook_path(name):
+    p = os.path.join(HOOKS, "libctu_hook_%s.so" % name)
+    if not os.path.exists(p):
+        pytest.skip("%s not built (tools/build_problem_hook.sh; needs /root/reference)" % p)
+    return p
+
+
+def prob_string(d):
+    return " ".join("%s=%r" % (k, v) for k, v in d.items())
+
+
+# (hook library, problem name of the built-in kernels, golden with the reference's initial plotfile, loader)
+HOOK_CASES = [("sedov", "Sedov", "sedov16_hllc", "sedov"), ("sedov", "Sedov", "sedov16_periodic_hllc", "sedov"),
+              ("sod", "Sod", "sod_x_cgf", "sod"), ("sod", "Sod", "sod_z_hllc", "sod"), ("sod", "Sod", "sod_y_symm_plm", "sod"),
+              ("kh", "KH", "kh16_cgf", "kh"), ("kh", "KH", "kh16_hllc", "kh"), ("kh4", "KH", "kh16_4spec_cgf", "kh"),
+              ("kh4", "KH", "kh16_4spec_hllc", "kh"), ("rt", "RT", "rt16_cgf", "rt")]
+
+
+def load_any(golden, kind):
+    if kind == "sedov":
+        par, geom, prob, g, snaps = load_case(golden)
+    elif kind == "sod":
+        par, geom, prob, g, snaps = load_sod_case(golden)
+    elif kind == "rt":      # (built from build_ref.sh's scratch copy: the shipped RT header needs `problem::` in front of one L_x to compile in 3-D)
+        from cases import load_rt_case
+        par, geom, g, snaps = load_rt_case(golden)
+        prob = dict(frac=0.5, rho_1=1.0, rho_2=2.0, p0_base=5.0)
+    else:
+        par, geom, prob, g, snaps = load_kh_case(golden)
+    return par, geom, prob, g
+
+
+@pytest.mark.parametrize("hook,builtin,golden,kind", HOOK_CASES)
+def test_reference_hook_reproduces_reference_initial_plotfile(hook, builtin, golden, kind):
+    import oracle_lib as O
+    par, geom, prob, g = load_any(golden, kind)
+    O.params_finalize(par)
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    L = C.CDLL(hook_path(hook))
+    assert L.ctu_hook_num_state() == par.num_state
+    U = np.full((par.num_state, n_cell[2], n_cell[1], n_cell[0]), np.nan)
+    lo, hi = abi.Int3(0, 0, 0), abi.Int3(*[n - 1 for n in n_cell])
+    L.ctu_hook_init.argtypes = [C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3, C.c_void_p, abi.Int3, abi.Int3]
+    rc = L.ctu_hook_init(prob_string(prob).encode(), C.byref(par), C.byref(geom), lo, hi, U.ctypes.data, lo, hi)
+    assert rc == 0
+    f = O.fab(U, (0, 0, 0))
+    O.lib().orc_init_tail(C.byref(par), C.byref(geom), lo, hi, C.byref(f))
+    assert np.array_equal(U, g["U0"]), "hook %s vs the reference's plt00000 of %s" % (hook, golden)
+
+
+def test_hook_rejects_wrong_network_and_unknown_parameter():
+    par, geom, prob, g = load_any("sedov16_hllc", "sedov")
+    L = C.CDLL(hook_path("kh4"))
+    L.ctu_hook_init.argtypes = [C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3, C.c_void_p, abi.Int3, abi.Int3]
+    U = np.zeros((12, 4, 4, 4))
+    lo, hi = abi.Int3(0, 0, 0), abi.Int3(3, 3, 3)
+    assert L.ctu_hook_init(b"", C.byref(par), C.byref(geom), lo, hi, U.ctypes.data, lo, hi) == -1      # NumSpec mismatch
+    L = C.CDLL(hook_path("sedov"))
+    L.ctu_hook_init.argtypes = [C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3, C.c_void_p, abi.Int3, abi.Int3]
+    U = np.zeros((8, 4, 4, 4))
+    assert L.ctu_hook_init(b"no_such_parameter=1", C.byref(par), C.byref(geom), lo, hi, U.ctypes.data, lo, hi) == -1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hook,builtin,golden,kind", HOOK_CASES)
+def test_problem_init_through_hook_on_gpu(hook, builtin, golden, kind):
+    """ctu_problem_init("hook:<lib>") (hook on the host, upload, initData tail on the device) against the reference's initial
+    plotfile and against the built-in problem kernels"""
+    import torch
+    assert torch.cuda.is_available()
+    from castro_b200 import lib
+    par, geom, prob, g = load_any(golden, kind)
+    lib.params_finalize(par)
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    hi = tuple(n - 1 for n in n_cell)
+    a = lib.Sim(par, geom, (0, 0, 0), hi)
+    a.init_problem("hook:" + hook_path(hook), prob)
+    b = lib.Sim(par, geom, (0, 0, 0), hi)
+    b.init_problem(builtin, prob)
+    Ua, Ub = a.download(), b.download()
+    assert np.array_equal(Ua, g["U0"])
+    assert np.array_equal(Ua, Ub)
+    a.close()
+    b.close()
