@@ -23,11 +23,14 @@ using namespace ctu;
         }                                                                                                 \
     } while (0)
 
+constexpr int REPLAY_CAP = 1 << 20;      // tiles a single persistent-kernel launch may list for the exact replay (typical: hundreds)
+
 struct ctu_workspace {
     double* arena = nullptr;
     size_t arena_bytes = 0;
     size_t max_bytes = 0;
     unsigned long long* d_dtmin = nullptr;   // 2 entries + 1 for location
+    int* d_replay_list = nullptr;            // exact-replay list of the persistent kernels: count, overflow flag, REPLAY_CAP tile indices
     int* d_counters = nullptr;               // 8 entries: bad rho, bad X, invalid X, NaN, tiles replayed with exact division, -
     unsigned long long* h_dtmin = nullptr;   // pinned
     int* h_counters = nullptr;               // pinned
@@ -304,6 +307,8 @@ int ctu_workspace_create(ctu_workspace_t** ws, size_t max_bytes) {
     w->max_bytes = max_bytes ? max_bytes : ((size_t)32 << 30);
     CUDA_TRY(cudaMalloc(&w->d_dtmin, 4 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&w->d_counters, 8 * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&w->d_replay_list, (RL_HDR + REPLAY_CAP) * sizeof(int)));
+    CUDA_TRY(cudaMemset(w->d_replay_list, 0, RL_HDR * sizeof(int)));
     CUDA_TRY(cudaMallocHost(&w->h_dtmin, 4 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMallocHost(&w->h_counters, 8 * sizeof(int)));
     *ws = w;
@@ -316,6 +321,7 @@ void ctu_workspace_destroy(ctu_workspace_t* w) {
     if (w->arena) cudaFree(w->arena);
     if (w->d_dtmin) cudaFree(w->d_dtmin);
     if (w->d_counters) cudaFree(w->d_counters);
+    if (w->d_replay_list) cudaFree(w->d_replay_list);
     if (w->h_dtmin) cudaFreeHost(w->h_dtmin);
     if (w->h_counters) cudaFreeHost(w->h_counters);
     delete w;
@@ -390,6 +396,7 @@ HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     HydroRun* r = new HydroRun(ws, st);
     r->P = make_devpar(par, geom);
     r->P.replays = ws->d_counters + 4;
+    r->P.replay_list = ws->d_replay_list; r->P.replay_cap = REPLAY_CAP;
     const DevPar& P = r->P;
     r->P_predictor = par->source_term_predictor;
     r->np = P.npassive;
@@ -625,8 +632,15 @@ int hydro_end(HydroRun* r, double dt_est[2], int dt_loc[3], int n_bad[2]) {
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(ws->h_dtmin, ws->d_dtmin, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(ws->h_counters, ws->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    int rl_overflow = 0;
+    CUDA_TRY(cudaMemcpyAsync(&rl_overflow, ws->d_replay_list + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     r->tm.fold();
+    if (rl_overflow) {      // more tiles asked for the exact replay than the list holds: the results are not trustworthy -- fail loudly
+        std::fprintf(stderr, "[castro_ctu] exact-replay list overflow (> %d tiles in one launch); rerun with CTU_NO_PERSIST=1\n", REPLAY_CAP);
+        cudaMemsetAsync(ws->d_replay_list, 0, RL_HDR * sizeof(int), st);
+        return CTU_ERR_CUDA;
+    }
     int status = 0;
     if (ws->h_counters[0]) status |= CTU_STATUS_INVALID_DENSITY;
     if (ws->h_counters[1]) status |= CTU_STATUS_INVALID_X;

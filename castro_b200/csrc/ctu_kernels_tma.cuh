@@ -78,16 +78,30 @@ inline unsigned tg_blocks(const TileGrid& t) { return (unsigned)t.ntx * (unsigne
 
 struct TileCtx { int i0, j0, k0, tx, ty, tz, i, j, k; };
 template <int TYv, int TZv>
-__device__ __forceinline__ TileCtx tile_ctx_t(const TileGrid& tg) {
+__device__ __forceinline__ TileCtx tile_ctx_t(const TileGrid& tg, const int bt) {
     TileCtx c;
-    const int bt = blockIdx.x;
     const int bx = bt % tg.ntx, r = bt / tg.ntx, by = r % tg.nty, bz = r / tg.nty;
     c.i0 = tg.lo0 + bx * TX; c.j0 = tg.lo1 + by * TYv; c.k0 = tg.lo2 + bz * TZv;
     c.tx = threadIdx.x & (TX - 1); c.ty = (threadIdx.x / TX) % TYv; c.tz = threadIdx.x / (TX * TYv);
     c.i = c.i0 + c.tx; c.j = c.j0 + c.ty; c.k = c.k0 + c.tz;
     return c;
 }
+template <int TYv, int TZv>
+__device__ __forceinline__ TileCtx tile_ctx_t(const TileGrid& tg) { return tile_ctx_t<TYv, TZv>(tg, (int)blockIdx.x); }
 __device__ __forceinline__ TileCtx tile_ctx(const TileGrid& tg) { return tile_ctx_t<TY, TZ>(tg); }
+__device__ __forceinline__ TileCtx tile_ctx(const TileGrid& tg, const int bt) { return tile_ctx_t<TY, TZ>(tg, bt); }
+
+// Exact-replay list of the persistent kernels: [0] = number of entries, [1] = overflow flag, [2 ...] = tile indices.  A persistent
+// CTA cannot replay a tile in place (its shared-memory buffers already receive the next tile), so a warp that met an operand outside
+// the range of the branch-free division / sqrt sequences appends its tile, and the replay kernel of the same stage, launched right
+// behind it, recomputes the listed tiles with the IEEE operators (about a thousand tiles of the 15 million of a 512^3 step).
+constexpr int RL_HDR = 4;      // [2] = next tile of the persistent kernels' dynamic tile scheduler, [3] unused
+__device__ __forceinline__ void replay_push(const DevPar& P, const int tile) {
+    if (P.replays) atomicAdd(P.replays, 1);
+    const int idx = atomicAdd(&P.replay_list[0], 1);
+    if (idx < P.replay_cap) P.replay_list[RL_HDR + idx] = tile;
+    else P.replay_list[1] = 1;
+}
 
 // shared-memory tile [comp][z][y][x], dense
 template <int EX_, int EY_, int EZ_>
@@ -338,6 +352,169 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
 #endif
     }
     CTU_PT_END(1)
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_trans2_persist: the same stage as k_trans2_tma with PERSISTENT CTAs (one wave of CTAs strides over the tiles) that prefetch
+// the next tile INTO THE SAME shared-memory buffers as soon as every thread has moved its operands of the current tile into
+// registers.  Measured with clock64 on the one-tile-per-CTA kernel (profiles/r2_phase_ticks.json): a CTA spends 26 % of its life
+// waiting for its TMA tiles, i.e. one of the four resident CTAs of an SM is idle at any time; a second set of buffers does not
+// fit (4 x 46 KB of 227 KB), reusing the first one does.  Two barrier groups: {q-, q+, F^T1, c} are free again once the
+// trans_single updates of the first transverse direction have read them (before the first Riemann solve), {F^T2} once those of
+// the second have (before the second solve); each group's next tile is in flight during the solve that follows.
+// The arithmetic per face is that of trans2_body, in the same order.
+// ------------------------------------------------------------------------------------------------
+template <int N, int NP>
+static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
+k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
+                 const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
+                 const Trans2Args a, const TileGrid tg, const int ntiles) {
+    using L = Trans2Smem<N, NP>;
+    using M = MathFastW;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar1 = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    uint64_t* bar2 = bar1 + 1;
+    const typename L::F1T sF1{reinterpret_cast<const double*>(smem + L::O_F1)};
+    const typename L::F2T sF2{reinterpret_cast<const double*>(smem + L::O_F2)};
+    const typename L::CT sC{reinterpret_cast<const double*>(smem + L::O_C)};
+    const FaceTile sQM{reinterpret_cast<const double*>(smem + L::O_QM)}, sQP{reinterpret_cast<const double*>(smem + L::O_QP)};
+    constexpr unsigned TX1 = (unsigned)(2 * L::B_Q + L::B_F1 + L::B_C), TX2 = (unsigned)L::B_F2;
+    auto issue1 = [&](const int t) {      // q-, q+, F^{T1}, c of tile t
+        const TileCtx n = tile_ctx(tg, t);
+        const int fi = n.i0 - a.ilo[0], fj = n.j0 - a.ilo[1], fk = n.k0 - a.ilo[2], pf = fi & 1;
+        const int gi = fi - (N == 0), pg = gi & 1;
+        const int qi = n.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
+        tma::mbar_arrive_expect_tx(bar1, TX1);
+        tma::load_4d(smem + L::O_QM, &m_qm, bar1, fi - pf, fj, fk, 0);
+        tma::load_4d(smem + L::O_QP, &m_qp, bar1, fi - pf, fj, fk, 0);
+        tma::load_4d(smem + L::O_F1, &m_f1, bar1, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_C, &m_c, bar1, qi - pq, n.j0 - (N == 1) - a.qlo[1], n.k0 - (N == 2) - a.qlo[2], QS_C);
+    };
+    auto issue2 = [&](const int t) {      // F^{T2} of tile t
+        const TileCtx n = tile_ctx(tg, t);
+        const int fi = n.i0 - a.ilo[0], fj = n.j0 - a.ilo[1], fk = n.k0 - a.ilo[2];
+        const int gi = fi - (N == 0), pg = gi & 1;
+        tma::mbar_arrive_expect_tx(bar2, TX2);
+        tma::load_4d(smem + L::O_F2, &m_f2, bar2, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+    };
+    // tiles are handed out dynamically (one global counter per launch): SMs do not run at the same speed (two dies, far L2 partitions,
+    // replays), and a static stride would make every launch wait for its slowest CTA.  A CTA always knows its current and its next
+    // tile; thread 0 draws the one after that while the first Riemann solve runs.
+    int* s_next = reinterpret_cast<int*>(smem + L::O_BAR + 64);
+    if (threadIdx.x == 0) {
+        tma::mbar_init(bar1, 1); tma::mbar_init(bar2, 1); tma::fence_barrier_init();
+        s_next[0] = atomicAdd(&P.replay_list[2], 1);
+        s_next[1] = atomicAdd(&P.replay_list[2], 1);
+    }
+    if (threadIdx.x < 32) ctu_div_unsafe[threadIdx.x] = 0;
+    __syncthreads();
+    int t = s_next[0], tn = s_next[1];
+    __syncthreads();
+    if (threadIdx.x == 0 && t < ntiles) { issue1(t); issue2(t); }
+    for (unsigned it = 0; t < ntiles; ++it) {
+        const TileCtx c = tile_ctx(tg, t);
+        const int fi = c.i0 - a.ilo[0], pf = fi & 1;
+        const int gi = fi - (N == 0), pg = gi & 1;
+        const int qi = c.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
+        const bool in1 = a.b1.contains(c.i, c.j, c.k), in2 = a.b2.contains(c.i, c.j, c.k);
+        const int idx = (N == 0) ? c.i : (N == 1) ? c.j : c.k;
+        double ql[6], qr[6], xl[NP], xr[NP], cl = 0.0, cr = 0.0;
+        double qlo[6], qro[6], xlo[NP], xro[NP];
+        tma::mbar_wait(bar1, it & 1);
+        if (in1 || in2) {
+            const int of = FaceTile::off(c.tx + pf, c.ty, c.tz);
+#pragma unroll
+            for (int n = 0; n < 6; ++n) { ql[n] = sQM(of, n); qr[n] = sQP(of, n); }
+#pragma unroll
+            for (int ip = 0; ip < NP; ++ip) { xl[ip] = sQM(of, IS_X + ip); xr[ip] = sQP(of, IS_X + ip); }
+            const int oc = L::CT::off(c.tx + pq, c.ty, c.tz);
+            cl = sC(oc, 0); cr = sC(oc + L::CT::stride(N), 0);
+        }
+        if (in1) {
+            constexpr int sN = L::F1T::stride(N), sT = L::F1T::stride(L::T1);
+            const int oz = L::F1T::off(c.tx + pg, c.ty, c.tz);
+            trans_single_side<M, NP, typename L::F1T, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
+            trans_single_side<M, NP, typename L::F1T, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
+        }
+        __syncthreads();                                  // group 1 is in registers everywhere: its buffers take the next tile
+        if (threadIdx.x == 0) {
+            if (tn < ntiles) issue1(tn);
+            s_next[0] = atomicAdd(&P.replay_list[2], 1);
+        }
+        if (in1) {
+            double F[6], FX[NP], ugd, pgd;
+            solve_face_r<M, N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+            const long o = a.Fo1.idx(c.i, c.j, c.k);
+#pragma unroll
+            for (int n = 0; n < 6; ++n) a.Fo1.at(o, n) = F[n];
+            a.Fo1.at(o, FX_UG) = ugd;
+            a.Fo1.at(o, FX_PG) = pgd;
+#pragma unroll
+            for (int ip = 0; ip < NP; ++ip) a.Fo1.at(o, FX_X + ip) = FX[ip];
+        }
+        tma::mbar_wait(bar2, it & 1);
+        if (in2) {
+            constexpr int sN = L::F2T::stride(N), sT = L::F2T::stride(L::T2);
+            const int oz = L::F2T::off(c.tx + pg, c.ty, c.tz);
+            trans_single_side<M, NP, typename L::F2T, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
+            trans_single_side<M, NP, typename L::F2T, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && tn < ntiles) issue2(tn);
+        const int tnn = s_next[0];
+        if (in2) {
+            double F[6], FX[NP], ugd, pgd;
+            solve_face_r<M, N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+            const long o = a.Fo2.idx(c.i, c.j, c.k);
+#pragma unroll
+            for (int n = 0; n < 6; ++n) a.Fo2.at(o, n) = F[n];
+            a.Fo2.at(o, FX_UG) = ugd;
+            a.Fo2.at(o, FX_PG) = pgd;
+#pragma unroll
+            for (int ip = 0; ip < NP; ++ip) a.Fo2.at(o, FX_X + ip) = FX[ip];
+        }
+        __syncwarp();
+        if (ctu_div_unsafe[threadIdx.x >> 5]) {           // this warp's faces need the exact operators: list the tile
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) { replay_push(P, t); ctu_div_unsafe[threadIdx.x >> 5] = 0; }
+            __syncwarp();
+        }
+        t = tn; tn = tnn;
+    }
+}
+
+// exact recomputation of the tiles k_trans2_persist listed (a small grid strides over the list)
+template <int N, int NP>
+static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
+k_trans2_replay(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
+                const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
+                const Trans2Args a, const TileGrid tg) {
+    using L = Trans2Smem<N, NP>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
+    const int cnt = min(P.replay_list[0], P.replay_cap);
+    if ((int)blockIdx.x >= cnt) return;
+    if (threadIdx.x == 0) { tma::mbar_init(bar, 1); tma::fence_barrier_init(); }
+    __syncthreads();
+    unsigned it = 0;
+    for (int r = blockIdx.x; r < cnt; r += gridDim.x, ++it) {
+        const TileCtx c = tile_ctx(tg, P.replay_list[RL_HDR + r]);
+        const int fi = c.i0 - a.ilo[0], fj = c.j0 - a.ilo[1], fk = c.k0 - a.ilo[2], pf = fi & 1;
+        const int gi = fi - (N == 0), pg = gi & 1;
+        const int qi = c.i0 - (N == 0) - a.qlo[0], pq = qi & 1;
+        if (threadIdx.x == 0) {
+            tma::mbar_arrive_expect_tx(bar, L::TX_BYTES);
+            tma::load_4d(smem + L::O_QM, &m_qm, bar, fi - pf, fj, fk, 0);
+            tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
+            tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+            tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+            tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
+        }
+        const bool in1 = a.b1.contains(c.i, c.j, c.k), in2 = a.b2.contains(c.i, c.j, c.k);
+        tma::mbar_wait(bar, it & 1);
+        trans2_body<MathExact, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, nullptr, nullptr, nullptr, nullptr);
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

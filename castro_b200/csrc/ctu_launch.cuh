@@ -5,10 +5,29 @@
 #pragma once
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <algorithm>
 #include "ctu_kernels.cuh"
 #include "ctu_kernels_tma.cuh"
 
 namespace ctu {
+
+// CTU_PERSIST=1 selects the persistent variant of k_trans2 (one wave of CTAs, dynamic tile scheduler, next tile prefetched into the
+// same shared-memory buffers; exact replays through a list).  It is NOT the default: measured on B200 at 512^3 (profiles/r2_*):
+// one tile per CTA 41.2 ms/step, persistent with a static tile stride 53.6 ms (the SMs of the two dies do not run at the same
+// speed: every launch waits for its slowest CTA), persistent with the dynamic scheduler and the prefetch 43.6 ms -- the 26 % of a
+// CTA's life spent waiting for TMA is already covered by the other three CTAs of the SM, and the two extra __syncthreads per tile
+// cost more than the prefetch returns.  Kept for A/B runs and as the record of that experiment.
+inline bool persist_on() {
+    static const bool on = (std::getenv("CTU_PERSIST") != nullptr);
+    return on;
+}
+inline int num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+constexpr int REPLAY_GRID = 296;      // CTAs of a replay kernel (they return at once when the list is empty)
 
 template <class K>
 int set_smem(K kernel, size_t bytes) {
@@ -43,6 +62,20 @@ int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3
     for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
     a.cdt1 = cdtd[T1]; a.cdt2 = cdtd[T2];
     const TileGrid tg = make_tg(grow(nb[N], gu[0], gu[1], gu[2]));
+    if (persist_on() && !CTU_Q_LDG && P.replay_list) {
+        static bool attr2 = false;
+        if (!attr2) {
+            int rc = set_smem(k_trans2_persist<N, NP>, L::TOTAL); if (rc) return rc;
+            rc = set_smem(k_trans2_replay<N, NP>, L::TOTAL); if (rc) return rc;
+            attr2 = true;
+        }
+        const unsigned ntiles = tg_blocks(tg);
+        const unsigned grid = std::min<unsigned>(ntiles, (unsigned)num_sms() * TmaMinB<NP>::value);
+        if (cudaMemsetAsync(P.replay_list, 0, sizeof(int), st) != cudaSuccess || cudaMemsetAsync(P.replay_list + 2, 0, sizeof(int), st) != cudaSuccess) return CTU_ERR_CUDA;   // list length and tile counter; the overflow flag [1] is sticky
+        k_trans2_persist<N, NP><<<grid, TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg, (int)ntiles);
+        k_trans2_replay<N, NP><<<REPLAY_GRID, TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg);
+        return 0;
+    }
     k_trans2_tma<N, NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg);
     return 0;
 }

@@ -96,6 +96,9 @@ struct DevPar {
     int lo_bc[3], hi_bc[3], periodic[3];
     // diagnostics: number of CTAs that replayed their tile with the exact division / sqrt operators (nullptr = do not count)
     int* replays;
+    // exact-replay list of the persistent tile kernels: [0] count, [1] overflow flag, [2 ..] tile indices (see ctu_kernels_tma.cuh)
+    int* replay_list;
+    int replay_cap;
 };
 
 }  // namespace ctu

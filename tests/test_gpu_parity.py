@@ -205,6 +205,34 @@ def test_register_staged_kernels_match_golden():
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_persistent_trans2_variant_matches_golden():
+    """CTU_PERSIST=1 selects the persistent / prefetching variant of the transverse-flux kernel (dynamic tile scheduler, exact replays
+    through a list); not the default (it measured slower), but it must stay bit-identical.  Subprocess: the switch is read once."""
+    import os
+    import subprocess
+    import sys
+    _torch()
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from cases import load_case\n"
+        "from castro_b200 import lib\n"
+        "for name in ('sedov16_hllc_long', 'sedov32_hllc', 'sedov_24x16x8_cgf', 'sedov16_periodic_hllc'):\n"
+        "    par, geom, prob, g, snaps = load_case(name)\n"
+        "    lib.params_finalize(par)\n"
+        "    n = tuple(int(x) for x in g['n_cell'])\n"
+        "    sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in n))\n"
+        "    sim.init_problem('Sedov', prob)\n"
+        "    rc, t, dt, hist = sim.advance(snaps[-1])\n"
+        "    assert rc == 0\n"
+        "    assert np.array_equal(sim.download(), g['U%%d' %% snaps[-1]]), name\n"
+        "    assert name != 'sedov16_hllc_long' or lib.workspace_replays(sim.ws_handle) > 0\n"
+        "print('ok')\n") % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, CTU_PERSIST="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.parametrize("name,chunk", [("sedov16_hllc", 4), ("sedov16_periodic_hllc", 8), ("sedov_24x16x8_cgf", 4), ("sedov32_hllc", 32)])
 def test_host_streaming_step_matches_golden(name, chunk, monkeypatch):
     """ctu_sim_step_host: state in host memory, streamed through the device in z-chunks with copy/compute overlap"""
