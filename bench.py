@@ -457,19 +457,32 @@ def gpu_arm(args):
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
             try:
-                # ncu-measured DRAM bytes of one pipeline pass over the box (all kernels), to set beside the algorithmic bytes
-                tpz = json.load(open(traffic_file)).get("pipeline_dram_bytes_per_zone")
+                # ncu-measured DRAM bytes and FP64-pipe busy time of ONE coarse step of this workload (profiles/r2_ncu_raw_512.csv ->
+                # tools/ncu_traffic.py -> profiles/traffic.json, with the commit it was captured at), beside the algorithmic bytes
+                tj = json.load(open(traffic_file))
+                tpz = tj.get("pipeline_dram_bytes_per_zone")
                 roofline["traffic"] = tpz * zones_local
                 roofline["traffic_bytes_per_zone"] = tpz
+                roofline["traffic_source"] = {"file": "profiles/traffic.json", "raw": tj.get("source"), "captured_at_commit": tj.get("commit"),
+                                              "workload": tj.get("workload")}
                 roofline["algorithmic_bytes"] = alg_bytes * zones_local
-                # the binding resource is the FP64 pipe / issue rate, not HBM: ncu-measured FP64-pipe busy time of one
-                # pipeline pass, against the time the pass took live
-                tj = json.load(open(traffic_file))
+                fam = {"k_ctoprim": "k_ctoprim", "k_flat_div": "k_flat_div", "k_trace": "k_trace_riemann_tma", "k_trans_riemann": "k_trans2_tma",
+                       "k_final": "k_final_tma", "k_update": "k_update_tma"}
+                for k, v in roofline["kernels"].items():
+                    t = tj.get("kernels", {}).get(fam.get(k, ""), None)
+                    if t:
+                        v["bytes_per_zone"] = t["bytes_per_zone"]
+                        v["dram_GBps_live"] = t["bytes_per_zone"] * zones_local / (v["ms_per_step"] * 1e-3) / 1e9 if v["ms_per_step"] else None
+                        v["hbm_frac_live"] = v["dram_GBps_live"] / peak if v["dram_GBps_live"] else None
+                        v["fp64_pipe_pct_ncu"] = t["fp64_pipe_pct"]
+                        v["l2_hit_pct_ncu"] = t["l2_hit_pct"]
                 if "fp64_pipe_busy_ns_per_zone" in tj and hydro_ms > 0:
                     busy_ms = tj["fp64_pipe_busy_ns_per_zone"] * zones_local * 1e-6
                     roofline["fp64_pipe"] = {"busy_ms_per_step": busy_ms, "frac": busy_ms / (hydro_ms / args.steps),
                                              "note": "fraction of the pipeline time the FP64 pipe would need at 100 % utilisation (ncu)"}
-                    roofline["binding"] = "fp64 pipe / issue rate (flux-stage kernels), HBM for k_final, k_update, k_ctoprim" 
+                    roofline["binding"] = ("k_final: HBM (its ncu bytes over its live time: see kernels.k_final.hbm_frac_live); k_trace / k_trans2: "
+                                           "mixed FP64 + integer/select instruction issue at the 16-27 warps/SM the register file allows; "
+                                           "k_ctoprim / k_update: HBM")
             except Exception:
                 pass
         cpu = None
