@@ -240,7 +240,7 @@ bool tma_ok(const DevPar& P) {
     if (P.ppm_temp_fix) return false;        // EOS re-sync of the interface states before each solve: register-staged family
     if (P.use_pslope || P.ppm_well_balanced) return false;   // hydrostatic-pressure-aware reconstruction: register-staged family
     if (P.ppm_type == 0) return false;       // piecewise-linear reconstruction: register-staged family
-    if (P.riemann_solver == 1) return false; // the iterative Colella & Glaz solver lives in the register-staged family only
+    if (P.riemann_solver == 1 && P.npassive > CTU_TMA_CG_MAX_NP) return false;   // Colella & Glaz: tile kernels instantiated for 1-2 passives
     if (P.limit_fluxes_on_small_dens) return false;     // ditto the density-floor flux limiter
     if (P.hybrid_riemann) return false;      // the HLL blend lives in the register-staged family only (keeps the tile kernels lean)
     return tma::encode_fn() != nullptr;
@@ -786,8 +786,16 @@ int ctu_clean_state(const ctu_params_t* par, const int lo[3], const int hi[3], c
     const DevPar P = make_devpar(par, nullptr);
     const Box3 bx = make_box(lo, hi);
     if (!bx.ok() || !fab_covers(S, bx)) return CTU_ERR_BAD_ARG;
-    LaunchBox lb = make_lb(bx);
-    k_clean<<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(P, make_a4(*S), lb, npass, nullptr);
+    const A4 a = make_a4(*S);
+    if (clean_pair_ok(a, bx)) {        // 128-bit path: one thread per pair of zones
+        Box3 pb = bx;
+        pb.hi[0] = bx.lo[0] + (bx.hi[0] - bx.lo[0] + 1) / 2 - 1;
+        LaunchBox lb = make_lb(pb);
+        k_clean2<<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(P, a, lb, npass, nullptr);
+    } else {
+        LaunchBox lb = make_lb(bx);
+        k_clean<<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(P, a, lb, npass, nullptr);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

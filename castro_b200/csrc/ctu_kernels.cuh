@@ -16,6 +16,7 @@
 //
 // Threads map 1:1 to zones/faces with i fastest, so every global access is coalesced along x.
 #pragma once
+#include <cstdint>
 #include "ctu_physics.cuh"
 
 namespace ctu {
@@ -1210,6 +1211,33 @@ static __global__ void __launch_bounds__(TPB) k_clean(const DevPar P, const A4 S
 #pragma unroll
     for (int n = 0; n < 7; ++n) S.at(o, n) = u[n];
     if (nf && counters) atomicAdd(&counters[2], nf);
+}
+
+// the same with 128-bit accesses: one thread owns the zone pair (i, i+1) of a row and moves the seven thermodynamic components as
+// double2.  Requires an even row length, even strides, an even x offset of the box in its array and a 16-byte aligned base
+// (clean_pair_ok); anything else takes the scalar kernel.
+static __global__ void __launch_bounds__(TPB) k_clean2(const DevPar P, const A4 S, const LaunchBox lb, const int npass, int* counters) {
+    // lb.nx counts zone PAIRS here
+    int ip2, j, k;
+    if (!thread_zone(lb, ip2, j, k)) return;
+    const int i = lb.lo0 + 2 * (ip2 - lb.lo0);
+    const long o = S.idx(i, j, k);
+    double ua[7], ub[7];
+#pragma unroll
+    for (int n = 0; n < 7; ++n) {
+        const double2 v = *reinterpret_cast<const double2*>(&S.at(o, n));
+        ua[n] = v.x; ub[n] = v.y;
+    }
+    int nf = 0;
+    for (int c = 0; c < npass; ++c) { nf += clean_zone(P, ua, S, o); nf += clean_zone(P, ub, S, o + 1); }
+#pragma unroll
+    for (int n = 0; n < 7; ++n) *reinterpret_cast<double2*>(&S.at(o, n)) = make_double2(ua[n], ub[n]);
+    if (nf && counters) atomicAdd(&counters[2], nf);
+}
+inline bool clean_pair_ok(const A4& S, const Box3& bx) {
+    const long nx = bx.hi[0] - bx.lo[0] + 1;
+    return (nx % 2 == 0) && (S.sj % 2 == 0) && (S.sk % 2 == 0) && (S.sn % 2 == 0) && (((bx.lo[0] - S.lo0) & 1) == 0) &&
+           ((reinterpret_cast<uintptr_t>(S.p) & 15) == 0);
 }
 
 static __global__ void __launch_bounds__(TPB) k_estdt(const DevPar P, const A4 S, const LaunchBox lb, unsigned long long* dtmin) {

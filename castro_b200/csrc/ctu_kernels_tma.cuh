@@ -133,21 +133,30 @@ using OwnFluxTile = STile<EXT, UTY + (N == 1), UTZ + (N == 2)>;     // update ke
 template <int NP>
 __device__ __forceinline__ bool is_species(const DevPar& P, int ip) { return ip >= P.QFS_off && ip < P.QFS_off + P.nspec; }
 
-// Riemann solve on register states with register passives (Castro::cmpflx_plus_godunov, riemann.cpp:15-200)
-template <class M, int DIR, int NP>
+// Riemann solve on register states with register passives (Castro::cmpflx_plus_godunov, riemann.cpp:15-200).
+// RS = 0: castro.riemann_solver 0 (CGF) or 2 (HLLC), chosen at run time; RS = 1: the iterative Colella & Glaz solver
+// (castro.riemann_solver = 1) -- its own instantiation of every tile kernel, because the out-of-line iteration inside the default
+// kernels was measured to wreck their register allocation (141 -> 261 ms/step).
+template <class M, int DIR, int NP, int RS = 0>
 __device__ __forceinline__ void solve_face_r(const DevPar& P, const double* ql, const double* qr, const double* xl, const double* xr,
                                              double cl, double cr, int idx, double* F, double& ugd, double& pgd, double* FX) {
     const bool sp_lo = P.lo_bc[DIR] >= 3 && P.lo_bc[DIR] <= 5, sp_hi = P.hi_bc[DIR] >= 3 && P.hi_bc[DIR] <= 5;
     double bnd_fac = 1.0;
     if ((idx == P.domlo[DIR] && sp_lo) || (idx == P.domhi[DIR] + 1 && sp_hi)) bnd_fac = 0.0;
     PassiveUpwind pu;
-    if (P.riemann_solver == 0) {
-        auto sel = [&](const double* x, int n) {
-            double r = 0.0;
+    auto sel = [&](const double* x, int n) {
+        double r = 0.0;
 #pragma unroll
-            for (int ip = 0; ip < NP; ++ip) if (ip == P.QFS_off + n) r = x[ip];
-            return r;
-        };
+        for (int ip = 0; ip < NP; ++ip) if (ip == P.QFS_off + n) r = x[ip];
+        return r;
+    };
+    if (RS == 1) {
+        auto fl = [&](int n) { return sel(xl, n); };
+        auto fr = [&](int n) { return sel(xr, n); };
+        riemann_cgf<M, DIR, decltype(fl), decltype(fr), 1>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, fl, fr, F, ugd, pgd, pu);
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) FX[ip] = passive_flux_cgf(pu, xl[ip], xr[ip]);
+    } else if (P.riemann_solver == 0) {
         riemann_cgf<M, DIR>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, [&](int n) { return sel(xl, n); }, [&](int n) { return sel(xr, n); },
                          F, ugd, pgd, pu);
 #pragma unroll
@@ -236,7 +245,7 @@ struct Trans2Args {
 };
 
 // the arithmetic of one face of the tile, on the staged operands (M = MathFast: speculative pass, MathExact: replay)
-template <class M, int N, int NP>
+template <class M, int N, int NP, int RS = 0>
 __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a, const unsigned char* smem, const TileCtx& c, const bool in1,
                                             const bool in2, const int pf, const int pg, const int pq, const double* gql, const double* gqr,
                                             const double* gxl, const double* gxr) {
@@ -269,7 +278,7 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
         double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
         trans_single_side<M, NP, typename L::F1T, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
         trans_single_side<M, NP, typename L::F1T, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
-        solve_face_r<M, N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+        solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
         const long o = a.Fo1.idx(c.i, c.j, c.k);
 #pragma unroll
         for (int n = 0; n < 6; ++n) a.Fo1.at(o, n) = F[n];
@@ -284,7 +293,7 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
         double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
         trans_single_side<M, NP, typename L::F2T, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
         trans_single_side<M, NP, typename L::F2T, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
-        solve_face_r<M, N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+        solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
         const long o = a.Fo2.idx(c.i, c.j, c.k);
 #pragma unroll
         for (int n = 0; n < 6; ++n) a.Fo2.at(o, n) = F[n];
@@ -295,7 +304,7 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
     }
 }
 
-template <int N, int NP>
+template <int N, int NP, int RS = 0>
 static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
 k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
              const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
@@ -338,17 +347,17 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
     // speculative pass with the branch-free division / sqrt sequences; a warp replays its faces with the exact operators if one
     // of its threads met an operand outside their range (see MathFast in ctu_physics.cuh; the faces of a tile are independent)
 #if CTU_Q_LDG
-    trans2_body<MathFastW, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, ql, qr, xl, xr);
+    trans2_body<MathFastW, N, NP, RS>(P, a, smem, c, in1, in2, pf, pg, pq, ql, qr, xl, xr);
 #else
-    trans2_body<MathFastW, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, nullptr, nullptr, nullptr, nullptr);
+    trans2_body<MathFastW, N, NP, RS>(P, a, smem, c, in1, in2, pf, pg, pq, nullptr, nullptr, nullptr, nullptr);
 #endif
     __syncwarp();
     if (ctu_div_unsafe[threadIdx.x >> 5]) {
         if ((threadIdx.x & 31) == 0 && P.replays) atomicAdd(P.replays, 1);
 #if CTU_Q_LDG
-        trans2_body<MathExact, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, ql, qr, xl, xr);
+        trans2_body<MathExact, N, NP, RS>(P, a, smem, c, in1, in2, pf, pg, pq, ql, qr, xl, xr);
 #else
-        trans2_body<MathExact, N, NP>(P, a, smem, c, in1, in2, pf, pg, pq, nullptr, nullptr, nullptr, nullptr);
+        trans2_body<MathExact, N, NP, RS>(P, a, smem, c, in1, in2, pf, pg, pq, nullptr, nullptr, nullptr, nullptr);
 #endif
     }
     CTU_PT_END(1)
@@ -544,7 +553,7 @@ struct FinalArgs {
     double c1, c2;        // dt/(2 dx_T1), dt/(2 dx_T2)
 };
 
-template <class M, int N, int NP>
+template <class M, int N, int NP, int RS = 0>
 __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, const unsigned char* smem, const TileCtx& c, const bool active,
                                            const int pf, const int pg, const int pq, const double* dU, const double* dUX, const double* gql,
                                            const double* gqr, const double* gxl, const double* gxr) {
@@ -577,7 +586,7 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
     double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
     trans_final_side<M, NP, typename L::F1T, s1T, typename L::F2T, s2T>(P, sF1, o1, sF2, o2, ql, xl, a.c1, a.c2, qlo, xlo);
     trans_final_side<M, NP, typename L::F1T, s1T, typename L::F2T, s2T>(P, sF1, o1 + s1N, sF2, o2 + s2N, qr, xr, a.c1, a.c2, qro, xro);
-    solve_face_r<M, N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+    solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
 
     // apply_av (advection_util.cpp:354-419): div1 = difmag * min(0, <div u> over the 4 nodes of the face)
     const int od = L::DT::off(c.tx + pf, c.ty, c.tz);
@@ -608,7 +617,7 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
     for (int ip = 0; ip < NP; ++ip) a.Fo.at(o, FX_X + ip) = is_species<NP>(P, ip) ? FX[ip] * fac : FX[ip];
 }
 
-template <int N, int NP>
+template <int N, int NP, int RS = 0>
 static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
 k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
             const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
@@ -660,9 +669,9 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
     CTU_PT_LOADED
     // speculative pass / exact replay per warp, as in k_trans2_tma
 #if CTU_Q_LDG
-    final_body<MathFastW, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, ql, qr, xl, xr);
+    final_body<MathFastW, N, NP, RS>(P, a, smem, c, active, pf, pg, pq, dU, dUX, ql, qr, xl, xr);
 #else
-    final_body<MathFastW, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, nullptr, nullptr, nullptr, nullptr);
+    final_body<MathFastW, N, NP, RS>(P, a, smem, c, active, pf, pg, pq, dU, dUX, nullptr, nullptr, nullptr, nullptr);
 #endif
     __syncwarp();
     if (ctu_div_unsafe[threadIdx.x >> 5]) {
@@ -676,9 +685,9 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
             for (int ip = 0; ip < NP; ++ip) dUX[ip] = a.U.at(ou, UFA + ip) - a.U.at(oum, UFA + ip);
         }
 #if CTU_Q_LDG
-        final_body<MathExact, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, ql, qr, xl, xr);
+        final_body<MathExact, N, NP, RS>(P, a, smem, c, active, pf, pg, pq, dU, dUX, ql, qr, xl, xr);
 #else
-        final_body<MathExact, N, NP>(P, a, smem, c, active, pf, pg, pq, dU, dUX, nullptr, nullptr, nullptr, nullptr);
+        final_body<MathExact, N, NP, RS>(P, a, smem, c, active, pf, pg, pq, dU, dUX, nullptr, nullptr, nullptr, nullptr);
 #endif
     }
     CTU_PT_END(2)
@@ -997,7 +1006,7 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
 // trace + first-pass Riemann solve of one zone of the tile on the staged primitives (M = MathFast: speculative pass, MathExact: replay)
 struct TraceCtx { int i, j, k, tx, ty, tz, dloc, btile, pq; bool active; };
 
-template <class M, int D, int NP, bool SRC>
+template <class M, int D, int NP, bool SRC, int RS = 0>
 __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceRiemannArgs& a, unsigned char* smem, const TraceCtx& c,
                                                    const double flat) {
     using L = TraceSmem<D, NP>;
@@ -1092,7 +1101,7 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
     const int oq = QT::off(tx + pq + (D == 0 ? 2 : 0), ty + (D == 1 ? 2 : 0), tz + (D == 2 ? 2 : 0));
     const double cr = sq[QS_C * QT::ZONES + oq], cl = sq[QS_C * QT::ZONES + oq - QT::stride(D)];
     double F[6], FX[NP], ugd, pgd;
-    solve_face_r<M, D, NP>(P, ql, qr, xl, xr, cl, cr, idx, F, ugd, pgd, FX);
+    solve_face_r<M, D, NP, RS>(P, ql, qr, xl, xr, cl, cr, idx, F, ugd, pgd, FX);
     const long of = a.Fo.idx(i, j, k);
 #pragma unroll
     for (int n = 0; n < 6; ++n) a.Fo.at(of, n) = F[n];
@@ -1102,7 +1111,7 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
     for (int ip = 0; ip < NP; ++ip) a.Fo.at(of, FX_X + ip) = FX[ip];
 }
 
-template <int D, int NP, bool SRC>
+template <int D, int NP, bool SRC, int RS = 0>
 static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, CTU_TRACE_MINB)
 k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, const TraceRiemannArgs a) {
     using L = TraceSmem<D, NP>;
@@ -1136,11 +1145,11 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     CTU_PT_LOADED
     // speculative pass with the branch-free division / sqrt sequences; exact replay of the tile if any thread met an operand
     // outside their range (see MathFast in ctu_physics.cuh)
-    trace_riemann_body<MathFast, D, NP, SRC>(P, a, smem, c, flat);
+    trace_riemann_body<MathFast, D, NP, SRC, RS>(P, a, smem, c, flat);
     __syncthreads();
     if (ctu_div_unsafe[0]) {
         if (threadIdx.x == 0 && P.replays) atomicAdd(P.replays, 1);
-        trace_riemann_body<MathExact, D, NP, SRC>(P, a, smem, c, flat);
+        trace_riemann_body<MathExact, D, NP, SRC, RS>(P, a, smem, c, flat);
     }
     CTU_PT_END(0)
 }

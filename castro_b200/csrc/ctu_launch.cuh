@@ -40,13 +40,17 @@ int set_smem(K kernel, size_t bytes) {
     CUtensorMap var;                                                                                         \
     if (!tma::make_map(&var, arr, abx, ncomp, Tile::EX, Tile::EY, Tile::EZ, nc)) return CTU_ERR_CUDA;
 
-template <int N, int NP>
+// Colella & Glaz instantiations (RS = 1) exist for up to CTU_TMA_CG_MAX_NP passive scalars
+#ifndef CTU_TMA_CG_MAX_NP
+#define CTU_TMA_CG_MAX_NP 2
+#endif
+template <int N, int NP, int RS = 0>
 int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
                   const Box3* nb, const double* cdtd, cudaStream_t st) {
     using L = Trans2Smem<N, NP>;
     constexpr int T1 = L::T1, T2 = L::T2;
     static bool attr = false;
-    if (!attr) { int rc = set_smem(k_trans2_tma<N, NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    if (!attr) { int rc = set_smem(k_trans2_tma<N, NP, RS>, L::TOTAL); if (rc) return rc; attr = true; }
     CTU_MAP(m_qm, ta.qm[N], ibx, L::NIS, FaceTile, L::NIS)
     CTU_MAP(m_qp, ta.qp[N], ibx, L::NIS, FaceTile, L::NIS)
     CTU_MAP(m_f1, F1[T1], ibx, L::NFX, L::F1T, L::NFX)
@@ -62,7 +66,7 @@ int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3
     for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
     a.cdt1 = cdtd[T1]; a.cdt2 = cdtd[T2];
     const TileGrid tg = make_tg(grow(nb[N], gu[0], gu[1], gu[2]));
-    if (persist_on() && !CTU_Q_LDG && P.replay_list) {
+    if (RS == 0 && persist_on() && !CTU_Q_LDG && P.replay_list) {
         static bool attr2 = false;
         if (!attr2) {
             int rc = set_smem(k_trans2_persist<N, NP>, L::TOTAL); if (rc) return rc;
@@ -76,25 +80,33 @@ int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3
         k_trans2_replay<N, NP><<<REPLAY_GRID, TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg);
         return 0;
     }
-    k_trans2_tma<N, NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg);
+    k_trans2_tma<N, NP, RS><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg);
     return 0;
 }
 
 template <int NP>
 int launch_trans2_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
                      const Box3* nb, const double* cdtd, cudaStream_t st) {
+    if constexpr (NP <= CTU_TMA_CG_MAX_NP) {
+        if (P.riemann_solver == 1) {
+            int rc = launch_trans2<0, NP, 1>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+            if (!rc) rc = launch_trans2<1, NP, 1>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+            if (!rc) rc = launch_trans2<2, NP, 1>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+            return rc;
+        }
+    }
     int rc = launch_trans2<0, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
     if (!rc) rc = launch_trans2<1, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
     if (!rc) rc = launch_trans2<2, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
     return rc;
 }
-template <int D, int NP, bool SRC>
+template <int D, int NP, bool SRC, int RS = 0>
 int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1, const Box3& tb,
                          double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
     using L = TraceSmem<D, NP>;
     using TT = TrTile<D>;
     static bool attr = false;
-    if (!attr) { int rc = set_smem(k_trace_riemann_tma<D, NP, SRC>, L::TOTAL); if (rc) return rc; attr = true; }
+    if (!attr) { int rc = set_smem(k_trace_riemann_tma<D, NP, SRC, RS>, L::TOTAL); if (rc) return rc; attr = true; }
     CTU_MAP(m_q, qs, qbx_a, L::NQC, L::QT, L::NQC)
     TraceRiemannArgs a;
     a.fd = fd; a.qm = ta.qm[D]; a.qp = ta.qp[D]; a.Fo = F1[D];
@@ -108,24 +120,32 @@ int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, con
     a.ntz = (D == 2) ? (n[2] - 1 + TT::SZ - 1) / TT::SZ : (n[2] + TT::SZ - 1) / TT::SZ;
     a.dtdL = dt / P.dx[D];
     a.srcq = srcq; a.hdt = 0.5 * dt; a.src_mask = src_mask;
-    k_trace_riemann_tma<D, NP, SRC><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
+    k_trace_riemann_tma<D, NP, SRC, RS><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
     return 0;
 }
 template <int NP, bool SRC>
 int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
                             const Box3& tb, double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
+    if constexpr (NP <= CTU_TMA_CG_MAX_NP) {
+        if (P.riemann_solver == 1) {
+            int rc = launch_trace_riemann<0, NP, SRC, 1>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+            if (!rc) rc = launch_trace_riemann<1, NP, SRC, 1>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+            if (!rc) rc = launch_trace_riemann<2, NP, SRC, 1>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+            return rc;
+        }
+    }
     int rc = launch_trace_riemann<0, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
     if (!rc) rc = launch_trace_riemann<1, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
     if (!rc) rc = launch_trace_riemann<2, NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
     return rc;
 }
-template <int N, int NP>
+template <int N, int NP, int RS = 0>
 int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
                  const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
     using L = FinalSmem<N, NP>;
     constexpr int T1 = L::T1, T2 = L::T2;
     static bool attr = false;
-    if (!attr) { int rc = set_smem(k_final_tma<N, NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    if (!attr) { int rc = set_smem(k_final_tma<N, NP, RS>, L::TOTAL); if (rc) return rc; attr = true; }
     CTU_MAP(m_qm, ta.qm[N], ibx, L::NIS, FaceTile, L::NIS)
     CTU_MAP(m_qp, ta.qp[N], ibx, L::NIS, FaceTile, L::NIS)
     CTU_MAP(m_f1, F2[T1][T2], ibx, L::NFX, L::F1T, L::NFX)
@@ -138,12 +158,20 @@ int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3&
     for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
     a.c1 = hdtd[T1]; a.c2 = hdtd[T2];
     const TileGrid tg = make_tg(nb[N]);
-    k_final_tma<N, NP><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, m_d, a, tg);
+    k_final_tma<N, NP, RS><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, m_d, a, tg);
     return 0;
 }
 template <int NP>
 int launch_final_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
                     const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
+    if constexpr (NP <= CTU_TMA_CG_MAX_NP) {
+        if (P.riemann_solver == 1) {
+            int rc = launch_final<0, NP, 1>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+            if (!rc) rc = launch_final<1, NP, 1>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+            if (!rc) rc = launch_final<2, NP, 1>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+            return rc;
+        }
+    }
     int rc = launch_final<0, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
     if (!rc) rc = launch_final<1, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
     if (!rc) rc = launch_final<2, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);

@@ -86,6 +86,9 @@ def lib():
                                        C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ctu_dist_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ctu_dist_halo_plan.argtypes = [abi.Int3, C.c_int, abi.Int3, abi.Int3, abi.Int3, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ctu_sim_read_plotfile.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ctu_sim_diag.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+        L.ctu_write_grid_diag.argtypes = [C.c_char_p, C.c_int, C.c_double, C.POINTER(C.c_double)]
         L.ctu_selftest_mathfast.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
         L.ctu_problem_init.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3,
                                        C.POINTER(abi.Fab), C.c_void_p]
@@ -314,6 +317,18 @@ class Sim:
     def write_plotfile(self, path, time, step):
         """single-level AMReX plotfile of the current state (state variables only), readable by the reference's fcompare"""
         check(lib().ctu_sim_write_plotfile(self.h, str(path).encode(), float(time), int(step)), "ctu_sim_write_plotfile")
+
+    def read_plotfile(self, path):
+        """single-level plotfile (the reference's or this library's) -> the sim's box; returns (time, step)"""
+        t, st = C.c_double(0), C.c_int(0)
+        check(lib().ctu_sim_read_plotfile(self.h, str(path).encode(), C.byref(t), C.byref(st)), "ctu_sim_read_plotfile")
+        return t.value, st.value
+
+    def diag(self, center, local_only=False):
+        """columns 3-20 of the reference's grid_diag.out for the current state (Castro::sum_integrated_quantities)"""
+        out = (C.c_double * 18)()
+        check(lib().ctu_sim_diag(self.h, (C.c_double * 3)(*center), 1 if local_only else 0, out), "ctu_sim_diag")
+        return list(out)
 
     def upload(self, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float64)

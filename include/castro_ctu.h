@@ -266,6 +266,18 @@ int  ctu_sim_advance(ctu_sim_t* sim, int nsteps, double stop_time, double* time_
  * so that the reference's own comparator (external/amrex/Tools/Plotfile/fcompare.cpp) can diff the two codes. */
 int  ctu_sim_write_plotfile(ctu_sim_t* sim, const char* dir, double time, int step);
 
+/* Reads a single-level plotfile (any number of grids; state variables first, as Castro::writePlotFile and ctu_sim_write_plotfile
+ * store them: Source/driver/Castro_io.cpp:943-, AMReX_VisMF.cpp) into the sim's box; returns the file's time and step. */
+int  ctu_sim_read_plotfile(ctu_sim_t* sim, const char* dir, double* time, int* step);
+
+/* Integrated diagnostics of Castro::sum_integrated_quantities (Source/driver/sum_integrated_quantities.cpp:51-389; derived fields
+ * Derive.cpp:707-850) over the sim's box: out = mass, xmom, ymom, zmom, angular momentum x y z about `center`, kinetic, internal and
+ * gas energy, centre of mass x y z, its velocity x y z, max T, max rho (columns 3-20 of grid_diag.out).  local_only != 0 leaves
+ * the centre-of-mass slots un-normalised (rho*x*vol sums and momenta) so that a multi-box caller can add the boxes first.
+ * Deterministic (fixed reduction tree).  ctu_write_grid_diag appends one line in the reference's grid_diag.out format. */
+int  ctu_sim_diag(ctu_sim_t* sim, const double center[3], int local_only, double out[18]);
+int  ctu_write_grid_diag(const char* path, int timestep, double time, const double values[18]);
+
 /* ---- multi-box driver: one process per GPU, one equal box per process, NCCL over NVLink -----------------------
  * Replaces, for amr.max_level = 0 and a uniform decomposition px x py x pz of the domain:
  *   AmrLevel::FillPatch -> FabArray::FillBoundary   (Castro_advance.cpp:169; AMReX_FabArrayCommI.H:11-320, AMReX_FBI.H:534-900):
