@@ -43,6 +43,7 @@ class Params(C.Structure):
         ("cfl", C.c_double), ("init_shrink", C.c_double), ("change_max", C.c_double), ("max_dt", C.c_double),
         ("fixed_dt", C.c_double), ("initial_dt", C.c_double),
         ("check_dt_before_advance", C.c_int), ("check_dt_after_advance", C.c_int),
+        ("use_retry", C.c_int), ("max_subcycles", C.c_int), ("retry_subcycle_factor", C.c_double), ("dt_cutoff", C.c_double),
         ("eos_kind", C.c_int), ("eos_gamma", C.c_double), ("eos_assume_neutral", C.c_int),
         ("small_x", C.c_double),
         ("nspec", C.c_int), ("naux", C.c_int), ("nadv", C.c_int),
@@ -83,6 +84,7 @@ def default_params():
     p.initial_dt = -1.0
     p.check_dt_before_advance = 1
     p.check_dt_after_advance = 1
+    p.use_retry, p.max_subcycles, p.retry_subcycle_factor, p.dt_cutoff = 1, 10, 0.5, 1.e-12
     p.eos_kind = 0
     p.eos_gamma = 5.0 / 3.0
     p.eos_assume_neutral = 1

@@ -292,6 +292,9 @@ extern "C" {
 
 const char* ctu_version(void) { return "castro_ctu_b200 0.1 (sm_100a, fp64, fmad=false)"; }
 
+size_t ctu_abi_sizeof_params(void) { return sizeof(ctu_params_t); }
+size_t ctu_abi_sizeof_geom(void) { return sizeof(ctu_geom_t); }
+
 int ctu_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -36,6 +36,7 @@ struct ctu_sim {
     ctu_workspace_t* ws = nullptr;
     cudaStream_t st = 0;
     int step = 0;
+    int last_subcycles = 1, retries = 0;     // subcycles of the last coarse step; advances rejected and retried so far (castro.use_retry)
     int launches = 0;     // kernels launched by the sim itself (clean / fill / init), on top of the workspace's count
     // constant gravity (par.do_grav): old-time source on grow(valid, NUM_GROW_SRC), mass fluxes for grav_source_type 4, dt reduction
     double* osrc = nullptr;

@@ -419,9 +419,16 @@ int hook_init(const std::string& path, const char* prob_params, const ctu_params
     if (!h) { std::fprintf(stderr, "[castro_ctu] problem hook %s: %s\n", path.c_str(), dlerror()); return CTU_ERR_IO; }
     typedef int (*InitFn)(const char*, const ctu_params_t*, const ctu_geom_t*, const int*, const int*, double*, const int*, const int*);
     typedef int (*NsFn)(void);
+    typedef size_t (*SzFn)(void);
     InitFn init = (InitFn)dlsym(h, "ctu_hook_init");
     NsFn ns = (NsFn)dlsym(h, "ctu_hook_num_state");
-    if (!init || !ns) { dlclose(h); return CTU_ERR_IO; }
+    SzFn psz = (SzFn)dlsym(h, "ctu_hook_sizeof_params");
+    if (!init || !ns || !psz) { dlclose(h); return CTU_ERR_IO; }
+    if (psz() != sizeof(ctu_params_t)) {
+        std::fprintf(stderr, "[castro_ctu] problem hook %s was compiled against another revision of castro_ctu.h: rebuild it\n", path.c_str());
+        dlclose(h);
+        return CTU_ERR_BAD_ARG;
+    }
     const int nc = ctu_num_state(par);
     if (ns() != nc) { std::fprintf(stderr, "[castro_ctu] problem hook %s is built for NUM_STATE = %d, the run has %d\n", path.c_str(), ns(), nc); dlclose(h); return CTU_ERR_BAD_ARG; }
     const Box3 bx = make_box(lo, hi);
@@ -638,6 +645,7 @@ void ctu_params_defaults(ctu_params_t* p) {
     p->initial_dt = -1.0;
     p->check_dt_before_advance = 1;
     p->check_dt_after_advance = 1;
+    p->use_retry = 1; p->max_subcycles = 10; p->retry_subcycle_factor = 0.5; p->dt_cutoff = 1.e-12;      // _cpp_parameters:312,347-369
     p->eos_kind = 0;
     p->eos_gamma = 5.0 / 3.0;
     p->eos_assume_neutral = 1;
@@ -755,6 +763,8 @@ int ctu_parse_inputs(const char* path, const char* overrides, ctu_params_t* par,
     gd("castro.cfl", par->cfl); gd("castro.init_shrink", par->init_shrink); gd("castro.change_max", par->change_max);
     gd("castro.max_dt", par->max_dt); gd("castro.fixed_dt", par->fixed_dt); gd("castro.initial_dt", par->initial_dt);
     gi("castro.check_dt_before_advance", par->check_dt_before_advance); gi("castro.check_dt_after_advance", par->check_dt_after_advance);
+    gi("castro.use_retry", par->use_retry); gi("castro.max_subcycles", par->max_subcycles);
+    gd("castro.retry_subcycle_factor", par->retry_subcycle_factor); gd("castro.dt_cutoff", par->dt_cutoff);
     gd("eos.eos_gamma", par->eos_gamma); gi("eos.eos_assume_neutral", par->eos_assume_neutral);
     gd("network.small_x", par->small_x);
     gi("castro.shock_detection_include_sources", par->shock_detection_include_sources);
@@ -855,6 +865,8 @@ int ctu_sim_state(ctu_sim_t* s, ctu_fab_t* out) {
 }
 
 ctu_workspace_t* ctu_sim_workspace(ctu_sim_t* s) { return s ? s->ws : nullptr; }
+int ctu_sim_last_subcycles(const ctu_sim_t* s) { return s ? s->last_subcycles : 0; }
+int ctu_sim_retries(const ctu_sim_t* s) { return s ? s->retries : 0; }
 int ctu_sim_launches(const ctu_sim_t* s) { return s ? s->launches + ctu_workspace_launches(s->ws) : 0; }
 
 // valid zones <-> contiguous HOST array [ncomp][nz][ny][nx] (pinned or pageable)
@@ -960,16 +972,21 @@ static int sim_step_hydro_grav(ctu_sim_t* s, double dt, double dt_est[2], int n_
     return 0;
 }
 
-// construct_ctu_hydro_source + its clean_state + post_timestep's clean_state, with both dt estimates
-int ctu_sim_step_hydro(ctu_sim_t* s, double dt, double dt_est[2], int n_bad[2]) {
-    if (!s) return CTU_ERR_BAD_ARG;
+// construct_ctu_hydro_source + n_clean x clean_state (its own, Castro_ctu_hydro.cpp:1444, and -- on the last subcycle of a coarse
+// step -- post_timestep's, Castro.cpp:2043-2050), with the dt estimate after each
+static int sim_step_hydro_n(ctu_sim_t* s, double dt, int n_clean, double dt_est[2], int n_bad[2]) {
     if (s->par.do_grav) return sim_step_hydro_grav(s, dt, dt_est, n_bad);
     ctu_fab_t sb = s->fab(s->cur), sn = s->fab(1 - s->cur);
     int rc = ctu_hydro_advance(s->ws, &s->par, &s->geom, s->vbx.lo, s->vbx.hi, &sb, nullptr, nullptr, &sn, nullptr, nullptr, dt,
-                               2 | CTU_ADV_SNEW_FROM_SBORDER, dt_est, nullptr, n_bad, s->st);
+                               n_clean | CTU_ADV_SNEW_FROM_SBORDER, dt_est, nullptr, n_bad, s->st);
     if (rc < 0) return rc;
     if (rc == 0) { s->cur = 1 - s->cur; s->step++; }
     return rc;
+}
+
+int ctu_sim_step_hydro(ctu_sim_t* s, double dt, double dt_est[2], int n_bad[2]) {
+    if (!s) return CTU_ERR_BAD_ARG;
+    return sim_step_hydro_n(s, dt, 2, dt_est, n_bad);
 }
 
 
@@ -1178,25 +1195,65 @@ int ctu::sim_advance_impl(ctu_sim* s, SimHooks* hooks, int nsteps, double stop_t
         if (stop_time >= 0.0) { if ((time + dt_0) > (stop_time - eps)) dt_0 = stop_time - time; }
         dt = dt_0;
     }
-    for (; n < nsteps; ++n) {
+    bool stop = false;
+    for (; n < nsteps && !stop; ++n) {
         if (stop_time >= 0.0 && time >= stop_time) break;
-        // Castro::subcycle_advance_ctu (Castro_advance_ctu.cpp:301-303): the hydro sees the rounded time difference
-        const double dt_sub = (time + dt) - time;
-        double est[2] = {1.e300, 1.e300};
-        int nb[2];
-        // a box that fails keeps taking part in the collectives of the step, so that no peer is left waiting
-        int rc = ctu_sim_step_pre(s);
-        if (hooks) { const int r = hooks->exchange(s); if (!rc) rc = r; }
-        if (!rc) rc = ctu_sim_step_fill(s);
-        if (!rc) rc = ctu_sim_step_hydro(s, dt_sub, est, nb);
-        { const int r = reduce_step(hooks, rc, est); if (r) return r; }
-        if (rc < 0) return rc;
-        if (rc > 0) { status |= rc; break; }
+        // Castro::subcycle_advance_ctu (Castro_advance_ctu.cpp:246-528): the coarse step [time, time + dt] is covered by subcycles --
+        // one, unless an advance fails (invalid density / X, post-advance dt validity check) and castro.use_retry asks for a retry of
+        // that subcycle from its old state with dt_subcycle * retry_subcycle_factor (retry_advance_ctu, :147-241).  The hydro always
+        // sees the rounded time difference "(time + dt) - subcycle_time" (:301-303).
+        // The ping-pong buffers make the retry free of copies: a failed advance has only written the OTHER buffer.
+        double subcycle_time = time, dt_subcycle = dt, est[2] = {1.e300, 1.e300};
+        const double eps_sub = 1.0e-14;
+        int sub_iteration = 0;
+        bool prepared = false;       // the current old state is already cleaned and its ghost zones filled (a retry reuses it)
+        while (subcycle_time < (1.0 - eps_sub) * (time + dt)) {
+            if (subcycle_time + dt_subcycle > (1.0 - p.dt_cutoff) * (time + dt)) dt_subcycle = (time + dt) - subcycle_time;
+            const int nrem = (int)std::round(((time + dt) - subcycle_time) / dt_subcycle);
+            if (dt_subcycle <= p.dt_cutoff * time || nrem > p.max_subcycles) { status |= CTU_STATUS_SUBCYCLE; stop = true; break; }
+            const double dt_sub = dt_subcycle;
+            const bool last = !(subcycle_time + dt_sub < (1.0 - eps_sub) * (time + dt));
+            int nb[2];
+            // a box that fails keeps taking part in the collectives of the step, so that no peer is left waiting
+            int rc = 0;
+            if (!prepared) {
+                // first subcycle: clean_state(S_old) of initialize_advance + clean_state(Sborder) (two passes in one);
+                // later subcycles: only initialize_do_advance's clean_state(Sborder) on the previous subcycle's S_new
+                ctu_fab_t f = s->fab(s->cur);
+                s->launches += 1;
+                rc = ctu_clean_state(&s->par, s->vbx.lo, s->vbx.hi, &f, sub_iteration == 0 ? 2 : 1, s->st);
+                if (hooks) { const int r = hooks->exchange(s); if (!rc) rc = r; }
+                if (!rc) rc = ctu_sim_step_fill(s);
+                prepared = true;
+            }
+            if (!rc) rc = sim_step_hydro_n(s, dt_sub, last ? 2 : 1, est, nb);
+            { const int r = reduce_step(hooks, rc, est); if (r) return r; }
+            if (rc < 0) return rc;
+            // finalize_do_advance (Castro_advance.cpp:274-309): post-advance dt validity check on the cleaned S_new
+            if (rc == 0 && p.check_dt_after_advance && p.change_max * est_time_step(p, est[0]) < dt_sub) {
+                if (p.use_retry && !p.do_grav) { s->cur = 1 - s->cur; s->step--; }      // take the rejected state back: retry from the old one
+                rc = CTU_STATUS_DT_POST;
+            }
+            if (rc > 0) {
+                if (!p.use_retry || p.do_grav || (rc & ~(CTU_STATUS_INVALID_DENSITY | CTU_STATUS_INVALID_X | CTU_STATUS_DT_POST))) {
+                    // no retry ("Advance was unsuccessful": the reference aborts): report the status; NaNs are never retried
+                    status |= rc;
+                    if (rc == CTU_STATUS_DT_POST) { if (dt_hist) dt_hist[n] = dt; time += dt; ++n; }
+                    stop = true;
+                    break;
+                }
+                dt_subcycle = std::min(dt_sub, dt_subcycle) * p.retry_subcycle_factor;
+                s->retries++;
+                continue;
+            }
+            subcycle_time += dt_sub;
+            sub_iteration += 1;
+            prepared = false;
+        }
+        if (stop) break;
+        s->last_subcycles = sub_iteration;
         if (dt_hist) dt_hist[n] = dt;
         time += dt;
-        if (p.check_dt_after_advance) {   // finalize_do_advance (Castro_advance.cpp:274-309)
-            if (p.change_max * est_time_step(p, est[0]) < dt_sub) { status |= CTU_STATUS_DT_POST; ++n; break; }
-        }
         // computeNewDt (Castro.cpp:1751-1945)
         double dt_min = est_time_step(p, est[1]);
         if (p.fixed_dt <= 0.0) dt_min = std::min(dt_min, p.change_max * dt);

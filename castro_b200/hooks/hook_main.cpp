@@ -17,6 +17,7 @@
 #include "castro_ctu.h"
 
 extern "C" __attribute__((visibility("default"))) int ctu_hook_num_state(void) { return NUM_STATE; }
+extern "C" __attribute__((visibility("default"))) size_t ctu_hook_sizeof_params(void) { return sizeof(ctu_params_t); }
 
 extern "C" __attribute__((visibility("default"))) int ctu_hook_init(const char* prob_params, const ctu_params_t* par, const ctu_geom_t* g, const int lo[3], const int hi[3],
                              double* host_state, const int slo[3], const int shi[3])

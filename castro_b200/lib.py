@@ -32,6 +32,12 @@ def lib():
                            "`make -C castro_b200/csrc` (no fallback path exists)" % SO_PATH)
         L = C.CDLL(SO_PATH)
         L.ctu_version.restype = C.c_char_p
+        L.ctu_abi_sizeof_params.restype = C.c_size_t
+        L.ctu_abi_sizeof_geom.restype = C.c_size_t
+        if L.ctu_abi_sizeof_params() != C.sizeof(abi.Params) or L.ctu_abi_sizeof_geom() != C.sizeof(abi.Geom):
+            raise CtuError("castro_b200/abi.py and %s disagree on the layout of ctu_params_t / ctu_geom_t: rebuild the library" % SO_PATH)
+        L.ctu_sim_last_subcycles.argtypes = [C.c_void_p]
+        L.ctu_sim_retries.argtypes = [C.c_void_p]
         L.ctu_workspace_bytes.restype = C.c_size_t
         L.ctu_sim_workspace.restype = C.c_void_p
         L.ctu_workspace_create.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
@@ -391,6 +397,14 @@ class Sim:
     @property
     def last_slabs(self):
         return lib().ctu_workspace_last_slabs(lib().ctu_sim_workspace(self.h))
+
+    @property
+    def last_subcycles(self):
+        return lib().ctu_sim_last_subcycles(self.h)
+
+    @property
+    def retries(self):
+        return lib().ctu_sim_retries(self.h)
 
 
 class Dist:

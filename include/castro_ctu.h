@@ -51,6 +51,7 @@ extern "C" {
 #define CTU_STATUS_NAN              4   /* check_for_nan      Castro.cpp:4510-4532 */
 #define CTU_STATUS_DT_PRE           8   /* "pre-advance timestep validity check failed"  Castro_advance.cpp:244 */
 #define CTU_STATUS_DT_POST         16   /* "post-advance timestep validity check failed" Castro_advance.cpp:302 */
+#define CTU_STATUS_SUBCYCLE        32   /* "subcycled timesteps too short" / "too many subcycles"  Castro_advance_ctu.cpp:306-330 */
 
 /* amrex::Array4<Real>-compatible view */
 typedef struct ctu_fab_t {
@@ -96,6 +97,10 @@ typedef struct ctu_params_t {
     /* timestep control, _cpp_parameters:300-379 */
     double cfl, init_shrink, change_max, max_dt, fixed_dt, initial_dt;
     int check_dt_before_advance, check_dt_after_advance;
+    /* castro.use_retry / retry_subcycle_factor / max_subcycles / dt_cutoff (Castro_advance_ctu.cpp:147-241, 246-528): a failed advance
+     * (invalid density / X, post-advance dt check) is retried in subcycles of dt * retry_subcycle_factor */
+    int use_retry, max_subcycles;
+    double retry_subcycle_factor, dt_cutoff;
     /* eos.* (external/Microphysics/EOS/gamma_law/_parameters) */
     int eos_kind;                  /* 0 = gamma_law */
     double eos_gamma;
@@ -130,6 +135,10 @@ typedef struct ctu_workspace ctu_workspace_t;
 /* ---- library / parameters ------------------------------------------------------------------ */
 const char* ctu_version(void);
 int  ctu_device_count(void);                               /* 0 if no usable CUDA device */
+/* sizeof(ctu_params_t) / sizeof(ctu_geom_t) as the LIBRARY was compiled: a caller built against another revision of this header
+ * must refuse to run (integration/Castro_ctu_hydro.cpp and the problem-hook libraries check it) */
+size_t ctu_abi_sizeof_params(void);
+size_t ctu_abi_sizeof_geom(void);
 void ctu_params_defaults(ctu_params_t* p);                 /* _cpp_parameters defaults, gammalaw.net */
 /* Castro::variableSetUp small_* / eos_init logic, Source/driver/Castro_setup.cpp:226-285 */
 int  ctu_params_finalize(ctu_params_t* p);
@@ -234,6 +243,8 @@ void ctu_sim_destroy(ctu_sim_t* sim);
 int  ctu_sim_state(ctu_sim_t* sim, ctu_fab_t* out);        /* view of the current (ghosted) state */
 ctu_workspace_t* ctu_sim_workspace(ctu_sim_t* sim);
 int  ctu_sim_launches(const ctu_sim_t* sim);               /* kernels launched so far by this sim (all phases) */
+int  ctu_sim_last_subcycles(const ctu_sim_t* sim);         /* subcycles the last coarse step took (1 unless an advance was retried) */
+int  ctu_sim_retries(const ctu_sim_t* sim);                /* advances rejected and retried so far (Castro::retry_advance_ctu) */
 /* valid zones <-> contiguous HOST array [ncomp][nz][ny][nx] (i fastest); synchronous */
 int  ctu_sim_download(ctu_sim_t* sim, double* host);
 int  ctu_sim_upload(ctu_sim_t* sim, const double* host);

@@ -80,6 +80,10 @@ ctu_params_t make_params ()
     p.initial_dt = castro::initial_dt;
     p.check_dt_before_advance = castro::check_dt_before_advance;
     p.check_dt_after_advance = castro::check_dt_after_advance;
+    p.use_retry = castro::use_retry;
+    p.max_subcycles = castro::max_subcycles;
+    p.retry_subcycle_factor = castro::retry_subcycle_factor;
+    p.dt_cutoff = castro::dt_cutoff;
     p.eos_kind = 0;                              // gamma_law (the EOS this executable was built with is checked below)
     p.eos_gamma = eos_rp::eos_gamma;
     p.eos_assume_neutral = eos_rp::eos_assume_neutral;
@@ -135,6 +139,10 @@ Castro::construct_ctu_hydro_source (Real time, Real dt)
     }
     if (geom.Coord() != 0) {
         amrex::Abort("construct_ctu_hydro_source [libcastro_ctu]: Cartesian geometry only");
+    }
+
+    if (ctu_abi_sizeof_params() != sizeof(ctu_params_t) || ctu_abi_sizeof_geom() != sizeof(ctu_geom_t)) {
+        amrex::Abort("construct_ctu_hydro_source [libcastro_ctu]: this executable was compiled against another revision of castro_ctu.h");
     }
 
     static ctu_workspace_t* ws = nullptr;      // scratch arena of the library, kept across steps (one host thread per rank drives the GPU)

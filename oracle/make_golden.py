@@ -65,6 +65,10 @@ CASES = {
     # several non-default options at once (their interactions)
     "sedov16_combo": (16, 40, [40], ["castro.riemann_solver=1", "castro.ppm_type=0", "castro.hybrid_riemann=1",
                                      "castro.limit_fluxes_on_small_dens=1", "castro.small_dens=0.3", "castro.transverse_use_eos=1"]),
+    # castro.use_retry (default on): with init_shrink = 1 and a tight change_max the first advance fails its post-advance dt validity
+    # check and is redone as two subcycles of dt / 2 (Castro::retry_advance_ctu / subcycle_advance_ctu)
+    "sedov16_hllc_retry": (16, 8, [1, 8], ["castro.riemann_solver=2", "castro.init_shrink=1.0", "castro.change_max=1.01"]),
+    "sedov16_cgf_retry": (16, 8, [1, 8], ["castro.riemann_solver=0", "castro.init_shrink=1.0", "castro.change_max=1.003"]),
     "sedov16_hllc_limit": (16, 60, [60], ["castro.riemann_solver=2", "castro.limit_fluxes_on_small_dens=1", "castro.small_dens=0.3"]),
 }
 

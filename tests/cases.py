@@ -49,6 +49,8 @@ CASES = {
     "sedov16_combo": dict(n_cell=(16, 16, 16), solver=1, par=dict(ppm_type=0, hybrid_riemann=1, limit_fluxes_on_small_dens=1, small_dens=0.3,
                                                                    transverse_use_eos=1)),
     "sedov16_hllc_limit": dict(n_cell=(16, 16, 16), solver=2, par=dict(limit_fluxes_on_small_dens=1, small_dens=0.3)),
+    "sedov16_hllc_retry": dict(n_cell=(16, 16, 16), solver=2, par=dict(init_shrink=1.0, change_max=1.01)),
+    "sedov16_cgf_retry": dict(n_cell=(16, 16, 16), solver=0, par=dict(init_shrink=1.0, change_max=1.003)),
 }
 
 

@@ -583,6 +583,33 @@ def test_plotfile_reader_and_grid_diag_vs_reference(tmp_path):
     sim.close()
 
 
+@pytest.mark.parametrize("name", ["sedov16_hllc_retry", "sedov16_cgf_retry"])
+def test_retry_subcycling_matches_reference(name):
+    """castro.use_retry (Castro::retry_advance_ctu / subcycle_advance_ctu): the first advance fails the post-advance dt validity check
+    and is redone as two subcycles of dt / 2 from the untouched old state; states and times must match the reference's, and the
+    same run without use_retry must stop with CTU_STATUS_DT_POST like the reference aborts"""
+    _torch()
+    from castro_b200 import lib
+    par, geom, prob, g, snaps = load_case(name)
+    lib.params_finalize(par)
+    sim = lib.Sim(par, geom, (0, 0, 0), (15, 15, 15))
+    sim.init_problem("Sedov", prob)
+    rc, t, dt, hist = sim.advance(1)
+    assert rc == 0 and sim.retries >= 1 and sim.last_subcycles == 2
+    assert_bitwise(sim.download(), g["U1"], name + " step 1 (two subcycles)")
+    rc, t, dt, hist2 = sim.advance(7, time=t, dt=dt)
+    assert rc == 0
+    assert_bitwise(sim.download(), g["U8"], name + " step 8")
+    np.testing.assert_allclose(np.cumsum(np.concatenate([[0.0], hist, hist2])), g["times"][:9], rtol=1e-14, atol=0)
+    sim.close()
+    par.use_retry = 0
+    sim = lib.Sim(par, geom, (0, 0, 0), (15, 15, 15))
+    sim.init_problem("Sedov", prob)
+    rc, t, dt, hist = sim.advance(3)
+    assert rc == 16 and len(hist) == 1 and sim.retries == 0
+    sim.close()
+
+
 def test_host_streaming_mixed_boundaries():
     """ctu_sim_step_host promises the bits of upload + pre + fill + hydro + download.  Periodic x/y with a physical boundary in z
     (reflecting wall below, outflow above) is the case where a z-ghost zone is filled from an x/y-ghost zone of the boundary plane:
