@@ -109,6 +109,8 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
     P.UFS = UFA + par->nadv;
     P.QFS_off = par->nadv;
     P.gamc_const = (par->eos_kind == 0);
+    P.eos_kind = par->eos_kind;
+    if (par->eos_kind == 1 && helm_device_table(par, &P.helm) != 0) std::memset(&P.helm, 0, sizeof(P.helm));
     P.difmag = par->difmag;
     P.small_dens = par->small_dens; P.small_temp = par->small_temp;
     P.small_pres = par->small_pres; P.small_ener = par->small_ener;
@@ -148,7 +150,11 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (p->riemann_solver < 0 || p->riemann_solver > 2) return CTU_ERR_UNSUPPORTED;
     if (p->riemann_solver == 1 && (p->riemann_shock_maxiter < 6 || p->riemann_shock_maxiter > 40)) return CTU_ERR_BAD_ARG;   // HISTORY_SIZE
     if (p->ppm_temp_fix != 0 && p->ppm_temp_fix != 2) return CTU_ERR_UNSUPPORTED;   // 1 and 3 only exist in the MOL integrator
-    if (p->eos_kind != 0) return CTU_ERR_UNSUPPORTED;                           // helmholtz: SURVEY §8(f) rank 2
+    if (p->eos_kind != 0 && p->eos_kind != 1) return CTU_ERR_UNSUPPORTED;
+    if (p->eos_kind == 1 && !helm_loaded()) return CTU_ERR_UNSUPPORTED;          // Helmholtz EOS: ctu_eos_helm_load(<helm_table.dat>) first
+    // with the Helmholtz EOS: the PPM / PLM path with the three Riemann solvers; the options that call the EOS on edge states and the
+    // constant-gravity driver are instantiated for the gamma law only
+    if (p->eos_kind == 1 && (p->transverse_use_eos || p->transverse_reset_rhoe || p->ppm_temp_fix || p->do_grav)) return CTU_ERR_UNSUPPORTED;
     if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
     return 0;
 }
@@ -498,10 +504,14 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
 
         {   LaunchBox lb = make_lb(qbx);
             tm.begin(0);
-            k_ctoprim<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, qs, lb); ++launches;
+            if (P.eos_kind == 1) k_ctoprim<1><<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, qs, lb);
+            else k_ctoprim<0><<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, qs, lb);
+            ++launches;
             if (r->have_src) {   // src_to_prim on grow(slab, 3) (Castro_ctu_hydro.cpp:282); timed with ctoprim
                 const LaunchBox ls = make_lb(sbx);
-                k_src_to_prim<<<nblocks(ls.n), TPB, 0, st>>>(P, Sb, qs, r->osrc, r->scorr, r->P_predictor, srcq, ls, dt, ws->d_counters + 5); ++launches;
+                if (P.eos_kind == 1) k_src_to_prim<1><<<nblocks(ls.n), TPB, 0, st>>>(P, Sb, qs, r->osrc, r->scorr, r->P_predictor, srcq, ls, dt, ws->d_counters + 5);
+                else k_src_to_prim<0><<<nblocks(ls.n), TPB, 0, st>>>(P, Sb, qs, r->osrc, r->scorr, r->P_predictor, srcq, ls, dt, ws->d_counters + 5);
+                ++launches;
             }
             tm.end(r->have_src ? 2 : 1); }
         {   LaunchBox lb = make_lb(obx);
@@ -551,28 +561,28 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
             LaunchBox lb;
             tm.begin(3);
             lb = make_lb(grow(nb[0], 0, 1, 1));
-            k_riemann1<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd); ++launches; tm.end(1);
+            if (P.eos_kind == 1) k_riemann1<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd); else k_riemann1<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd); ++launches; tm.end(1);
             tm.begin(4);
             lb = make_lb(grow(nb[1], 0, 0, 1));   // F^{y|x}
-            k_trans_riemann<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], F2[1][0], lb, cdtd[0], fd);
+            if (P.eos_kind == 1) k_trans_riemann<1, 0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], F2[1][0], lb, cdtd[0], fd); else k_trans_riemann<1, 0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], F2[1][0], lb, cdtd[0], fd);
             lb = make_lb(grow(nb[2], 0, 1, 0));   // F^{z|x}
-            k_trans_riemann<2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[0], F2[2][0], lb, cdtd[0], fd); launches += 2; tm.end(2);
+            if (P.eos_kind == 1) k_trans_riemann<2, 0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[0], F2[2][0], lb, cdtd[0], fd); else k_trans_riemann<2, 0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[0], F2[2][0], lb, cdtd[0], fd); launches += 2; tm.end(2);
             tm.begin(3);
             lb = make_lb(grow(nb[1], 1, 0, 1));
-            k_riemann1<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd); ++launches; tm.end(1);
+            if (P.eos_kind == 1) k_riemann1<1, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd); else k_riemann1<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd); ++launches; tm.end(1);
             tm.begin(4);
             lb = make_lb(grow(nb[0], 0, 0, 1));   // F^{x|y}
-            k_trans_riemann<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], F2[0][1], lb, cdtd[1], fd);
+            if (P.eos_kind == 1) k_trans_riemann<0, 1, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], F2[0][1], lb, cdtd[1], fd); else k_trans_riemann<0, 1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], F2[0][1], lb, cdtd[1], fd);
             lb = make_lb(grow(nb[2], 1, 0, 0));   // F^{z|y}
-            k_trans_riemann<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1], fd); launches += 2; tm.end(2);
+            if (P.eos_kind == 1) k_trans_riemann<2, 1, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1], fd); else k_trans_riemann<2, 1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[1], F2[2][1], lb, cdtd[1], fd); launches += 2; tm.end(2);
             tm.begin(3);
             lb = make_lb(grow(nb[2], 1, 1, 0));
-            k_riemann1<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb, fd); ++launches; tm.end(1);
+            if (P.eos_kind == 1) k_riemann1<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb, fd); else k_riemann1<2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F1[2], lb, fd); ++launches; tm.end(1);
             tm.begin(4);
             lb = make_lb(grow(nb[0], 0, 1, 0));   // F^{x|z}
-            k_trans_riemann<0, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[2], F2[0][2], lb, cdtd[2], fd);
+            if (P.eos_kind == 1) k_trans_riemann<0, 2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[2], F2[0][2], lb, cdtd[2], fd); else k_trans_riemann<0, 2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[2], F2[0][2], lb, cdtd[2], fd);
             lb = make_lb(grow(nb[1], 1, 0, 0));   // F^{y|z}
-            k_trans_riemann<1, 2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[2], F2[1][2], lb, cdtd[2], fd); launches += 2; tm.end(2);
+            if (P.eos_kind == 1) k_trans_riemann<1, 2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[2], F2[1][2], lb, cdtd[2], fd); else k_trans_riemann<1, 2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[2], F2[1][2], lb, cdtd[2], fd); launches += 2; tm.end(2);
         }
         // final fluxes overwrite the (now dead) first-pass flux storage
         if (use_tma) {
@@ -584,11 +594,11 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
         {   LaunchBox lb;
             tm.begin(5);
             lb = make_lb(nb[0]);
-            k_final<0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F2[1][2], F2[2][1], fd, Sb, F1[0], lb, hdtd[1], hdtd[2], dt);
+            if (P.eos_kind == 1) k_final<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F2[1][2], F2[2][1], fd, Sb, F1[0], lb, hdtd[1], hdtd[2], dt); else k_final<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F2[1][2], F2[2][1], fd, Sb, F1[0], lb, hdtd[1], hdtd[2], dt);
             lb = make_lb(nb[1]);
-            k_final<1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F2[0][2], F2[2][0], fd, Sb, F1[1], lb, hdtd[0], hdtd[2], dt);
+            if (P.eos_kind == 1) k_final<1, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F2[0][2], F2[2][0], fd, Sb, F1[1], lb, hdtd[0], hdtd[2], dt); else k_final<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F2[0][2], F2[2][0], fd, Sb, F1[1], lb, hdtd[0], hdtd[2], dt);
             lb = make_lb(nb[2]);
-            k_final<2><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F2[0][1], F2[1][0], fd, Sb, F1[2], lb, hdtd[0], hdtd[1], dt); launches += 3; tm.end(3); }
+            if (P.eos_kind == 1) k_final<2, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F2[0][1], F2[1][0], fd, Sb, F1[2], lb, hdtd[0], hdtd[1], dt); else k_final<2, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[2], ta.qp[2], qs, F2[0][1], F2[1][0], fd, Sb, F1[2], lb, hdtd[0], hdtd[1], dt); launches += 3; tm.end(3); }
         {   UpdateArgs ua;
             for (int d = 0; d < 3; ++d) ua.F[d] = F1[d];
             ua.dtmin = ws->d_dtmin; ua.counters = ws->d_counters;
@@ -599,7 +609,8 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
                 rc = launch_update(P, np, F1, ibx, Sb, from_sb ? Sb : Sn, Sn, ua, tb, dt, st);
                 if (rc) return rc;
             } else {
-                k_update<<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, from_sb ? Sb : Sn, Sn, ua, lb, dt);
+                if (P.eos_kind == 1) k_update<1><<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, from_sb ? Sb : Sn, Sn, ua, lb, dt);
+                else k_update<0><<<nblocks(lb.n), TPB, 0, st>>>(P, Sb, from_sb ? Sb : Sn, Sn, ua, lb, dt);
             }
             ++launches; tm.end(1); }
         for (int d = 0; d < 3; ++d) {
@@ -629,7 +640,9 @@ int hydro_end(HydroRun* r, double dt_est[2], int dt_loc[3], int n_bad[2]) {
     struct Guard { HydroRun* r; ~Guard() { delete r; } } guard{r};
     if (dt_est && dt_loc) {
         LaunchBox lb = make_lb(vbx);
-        k_estdt_loc<<<nblocks(lb.n), TPB, 0, st>>>(r->P, r->Sn, lb, ws->d_dtmin + 1, ws->d_dtmin + 2); ++r->launches;
+        if (r->P.eos_kind == 1) k_estdt_loc<1><<<nblocks(lb.n), TPB, 0, st>>>(r->P, r->Sn, lb, ws->d_dtmin + 1, ws->d_dtmin + 2);
+        else k_estdt_loc<0><<<nblocks(lb.n), TPB, 0, st>>>(r->P, r->Sn, lb, ws->d_dtmin + 1, ws->d_dtmin + 2);
+        ++r->launches;
     }
     ws->kernel_launches += r->launches;
     CUDA_TRY(cudaGetLastError());
@@ -742,8 +755,13 @@ int ctu_estdt(const ctu_params_t* par, const ctu_geom_t* geom, const int lo[3], 
     CUDA_TRY(cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, st));
     const A4 a = make_a4(*S);
     LaunchBox lb = make_lb(bx);
-    k_estdt<<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, d);
-    if (ijk) k_estdt_loc<<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, d, d + 1);
+    if (P.eos_kind == 1) {
+        k_estdt<1><<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, d);
+        if (ijk) k_estdt_loc<1><<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, d, d + 1);
+    } else {
+        k_estdt<0><<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, d);
+        if (ijk) k_estdt_loc<0><<<nblocks(lb.n), TPB, 0, st>>>(P, a, lb, d, d + 1);
+    }
     unsigned long long h[2];
     CUDA_TRY(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -794,10 +812,12 @@ int ctu_clean_state(const ctu_params_t* par, const int lo[3], const int hi[3], c
         Box3 pb = bx;
         pb.hi[0] = bx.lo[0] + (bx.hi[0] - bx.lo[0] + 1) / 2 - 1;
         LaunchBox lb = make_lb(pb);
-        k_clean2<<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(P, a, lb, npass, nullptr);
+        if (P.eos_kind == 1) k_clean2<1><<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(P, a, lb, npass, nullptr);
+        else k_clean2<0><<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(P, a, lb, npass, nullptr);
     } else {
         LaunchBox lb = make_lb(bx);
-        k_clean<<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(P, a, lb, npass, nullptr);
+        if (P.eos_kind == 1) k_clean<1><<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(P, a, lb, npass, nullptr);
+        else k_clean<0><<<nblocks(lb.n), TPB, 0, (cudaStream_t)stream>>>(P, a, lb, npass, nullptr);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -7,6 +7,10 @@ int device_ok();
 DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom);
 int check_supported(const ctu_params_t* p, const ctu_geom_t* g);
 bool fab_covers(const ctu_fab_t* f, const Box3& b);
+// Helmholtz EOS table (ctu_eos.cu)
+bool helm_loaded();
+bool helm_host_table(const ctu_params_t* par, helm::Table* out);
+int helm_device_table(const ctu_params_t* par, helm::Table* out);
 
 // one advance of one box enqueued slab by slab (ctu_api.cu); hydro_end synchronises the stream and frees the run
 struct HydroRun;

@@ -52,6 +52,7 @@ __device__ __forceinline__ bool thread_zone(const LaunchBox& lb, int& i, int& j,
 // ctoprim: hydro::conservative_to_primitive (advection_util.H:98-235) + rho_inv passives
 // (Castro_ctu_hydro.cpp:226-230, reconstruction.H:50-83)
 // ------------------------------------------------------------------------------------------------
+template <int EK = 0>
 static __global__ void __launch_bounds__(TPB) k_ctoprim(const DevPar P, const A4 U, const A4 qs, const LaunchBox lb) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
@@ -66,14 +67,14 @@ static __global__ void __launch_bounds__(TPB) k_ctoprim(const DevPar P, const A4
     else e = U.at(ou, UEINT) * rhoinv;
     Eos s;
     s.T = U.at(ou, UTEMP); s.rho = rho; s.e = e;
-    s.mu = eos_mu(P, [&](int n) { return U.at(ou, P.UFS + n) * rhoinv; });
-    eos_re<false>(P, s);
+    s.mu = eos_mu<EK>(P, [&](int n) { return U.at(ou, P.UFS + n) * rhoinv; });
+    eos_re<false, true, EK>(P, s);
     qs.at(oq, QS_RHO) = rho;
     qs.at(oq, QS_U) = u; qs.at(oq, QS_V) = v; qs.at(oq, QS_W) = w;
     qs.at(oq, QS_P) = s.p;
     qs.at(oq, QS_RE) = s.e * rho;
     qs.at(oq, QS_C) = s.cs;
-    qs.at(oq, QS_GAMC) = P.gamma;
+    qs.at(oq, QS_GAMC) = s.gam1;
     for (int ip = 0; ip < P.npassive; ++ip) qs.at(oq, QS_X + ip) = U.at(ou, UFA + ip) * rhoinv;
 }
 
@@ -157,6 +158,7 @@ static __global__ void __launch_bounds__(TPB) k_flat_div(const DevPar P, const A
 constexpr int NSRCQ = 6;
 
 // one thread = one zone of grow(slab, 3)
+template <int EK = 0>
 static __global__ void __launch_bounds__(TPB) k_src_to_prim(const DevPar P, const A4 U, const A4 qs, const A4 osrc, const A4 scorr,
                                                      const int predictor, const A4 srcq, const LaunchBox lb, const double dt, int* __restrict__ src_mask) {
     int i, j, k;
@@ -177,8 +179,8 @@ static __global__ void __launch_bounds__(TPB) k_src_to_prim(const DevPar P, cons
     const double qre = qs.at(oq, QS_RE);
     Eos s;
     s.T = U.at(ou, UTEMP); s.rho = rho; s.e = qre * rhoinv;
-    s.mu = eos_mu(P, [&](int n) { return U.at(ou, P.UFS + n) * rhoinv; });
-    eos_re<true>(P, s);
+    s.mu = eos_mu<EK>(P, [&](int n) { return U.at(ou, P.UFS + n) * rhoinv; });
+    eos_re<true, true, EK>(P, s);
     const double s_rho = srcU[URHO];
     srcq.at(os, QS_RHO) = s_rho;
     srcq.at(os, QS_U) = (srcU[UMX] - qs.at(oq, QS_U) * s_rho) * rhoinv;
@@ -709,7 +711,7 @@ static __global__ void __launch_bounds__(TPB) k_trace_plm(const DevPar P, const 
 // Riemann driver shared by the three flux kernels: Castro::cmpflx_plus_godunov (riemann.cpp:15-200)
 //   XM(ip)/XP(ip): passive ip (mass fraction etc.) of the minus/plus state
 // ------------------------------------------------------------------------------------------------
-template <int DIR, class XM, class XP>
+template <int DIR, int EK = 0, class XM, class XP>
 __device__ __forceinline__ void solve_face(const DevPar& P, double* qm, double* qp, const A4& qs, int i, int j, int k,
                                            XM xm, XP xp, double* F, double& ugd, double& pgd, PassiveUpwind& pu, const A4& fd) {
     pu.hll = 0;
@@ -737,9 +739,9 @@ __device__ __forceinline__ void solve_face(const DevPar& P, double* qm, double* 
     auto xlf = [&](int n) { return xm(P.QFS_off + n); };
     auto xrf = [&](int n) { return xp(P.QFS_off + n); };
     if (P.riemann_solver == 0) {
-        riemann_cgf<MathExact, DIR, decltype(xlf), decltype(xrf), 0>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, xlf, xrf, F, ugd, pgd, pu);
+        riemann_cgf<MathExact, DIR, decltype(xlf), decltype(xrf), 0, EK>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, xlf, xrf, F, ugd, pgd, pu);
     } else if (P.riemann_solver == 1) {
-        riemann_cgf<MathExact, DIR, decltype(xlf), decltype(xrf), 1>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, xlf, xrf, F, ugd, pgd, pu);
+        riemann_cgf<MathExact, DIR, decltype(xlf), decltype(xrf), 1, EK>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, xlf, xrf, F, ugd, pgd, pu);
     } else {
         riemann_hllc<MathExact, DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, F, ugd, pgd, pu);
     }
@@ -761,7 +763,7 @@ __device__ __forceinline__ void load6(const A4& a, long off, double* q) {
 }
 
 // first-pass fluxes (Castro_ctu_hydro.cpp:674,745,817)
-template <int DIR>
+template <int DIR, int EK = 0>
 static __global__ void __launch_bounds__(TPB) k_riemann1(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Fo, const LaunchBox lb,
                                                   const A4 fd) {
     int i, j, k;
@@ -771,7 +773,7 @@ static __global__ void __launch_bounds__(TPB) k_riemann1(const DevPar P, const A
     PassiveUpwind pu;
     load6(qm, o, ql);
     load6(qp, o, qr);
-    solve_face<DIR>(P, ql, qr, qs, i, j, k, [&](int ip) { return qm.at(o, IS_X + ip); }, [&](int ip) { return qp.at(o, IS_X + ip); },
+    solve_face<DIR, EK>(P, ql, qr, qs, i, j, k, [&](int ip) { return qm.at(o, IS_X + ip); }, [&](int ip) { return qp.at(o, IS_X + ip); },
                     F, ugd, pgd, pu, fd);
     if (P.ppm_temp_fix == 2 && P.riemann_solver != 2) {      // the re-synced states replace the traced ones for the later stages
         qm.at(o, IS_P) = ql[IS_P]; qm.at(o, IS_RE) = ql[IS_RE];
@@ -803,7 +805,7 @@ __device__ __forceinline__ bool trans_reset(const DevPar& P, double rho, double 
 // trans_single (both states) fused with the Riemann solve on the corrected states.
 //   N = face direction, T = transverse direction whose first-pass flux Ft corrects the states.
 //   reference: trans_single(...) + cmpflx_plus_godunov(...), Castro_ctu_hydro.cpp:699-880 and :895-1080
-template <int N, int T>
+template <int N, int T, int EK = 0>
 static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Ft, const A4 Fo,
                                                        const LaunchBox lb, const double cdtdx, const A4 fd) {
     int i, j, k;
@@ -861,7 +863,7 @@ static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, co
     }
     double F[6], ugd, pgd;
     PassiveUpwind pu;
-    solve_face<N>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu, fd);
+    solve_face<N, EK>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu, fd);
     const long of = Fo.idx(i, j, k);
 #pragma unroll
     for (int n = 0; n < 6; ++n) Fo.at(of, n) = F[n];
@@ -873,7 +875,7 @@ static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, co
 // trans_final (both states) + final Riemann solve + flux cleaning:
 //   Castro_ctu_hydro.cpp:925-961 / 1004-1042 / 1085-1123, then :1131-1172 (zero T flux, apply_av, normalize_species_fluxes)
 //   F1 = F^{T1|T2}, F2 = F^{T2|T1};  c1 = dt/(2 dx_T1), c2 = dt/(2 dx_T2)
-template <int N>
+template <int N, int EK = 0>
 static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 F1, const A4 F2,
                                                const A4 fd, const A4 U, const A4 Fo, const LaunchBox lb, const double c1, const double c2,
                                                const double dt) {
@@ -944,7 +946,7 @@ static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 q
     }
     double F[6], ugd, pgd;
     PassiveUpwind pu;
-    solve_face<N>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu, fd);
+    solve_face<N, EK>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu, fd);
 
     // apply_av (advection_util.cpp:354-419): div1 = difmag * min(0, <div u> over the 4 nodes of the face)
     const long od = fd.idx(i, j, k);
@@ -1013,13 +1015,14 @@ static __global__ void __launch_bounds__(TPB) k_final(const DevPar P, const A4 q
 //     -> reset_internal_energy (:3742-3808) -> EOS temperature (:4044-4070)
 // u[0..6] = URHO..UTEMP ; passives live in S at offset o.  Returns number of invalid mass fractions (normalize_species).
 // ------------------------------------------------------------------------------------------------
+template <int EK = 0>
 __device__ __forceinline__ int clean_zone(const DevPar& P, double* __restrict__ u, const A4& S, long o) {
     int nfail = 0;
     if (u[URHO] < P.small_dens) {
         for (int ip = 0; ip < P.npassive; ++ip) S.at(o, UFA + ip) *= (P.small_dens / u[URHO]);
         Eos s; s.rho = P.small_dens; s.T = P.small_temp;
-        s.mu = eos_mu(P, [&](int n) { return S.at(o, P.UFS + n) / P.small_dens; });
-        eos_rt<false>(P, s);
+        s.mu = eos_mu<EK>(P, [&](int n) { return S.at(o, P.UFS + n) / P.small_dens; });
+        eos_rt<false, false, EK>(P, s);
         u[URHO] = s.rho;
         u[UTEMP] = s.T;
         u[UMX] = 0.0; u[UMY] = 0.0; u[UMZ] = 0.0;
@@ -1043,12 +1046,12 @@ __device__ __forceinline__ int clean_zone(const DevPar& P, double* __restrict__ 
         const double fac = rho / rhoX_sum;
         for (int n = 0; n < P.nspec; ++n) S.at(o, P.UFS + n) *= fac;
     }
-    const double mu = eos_mu(P, [&](int n) { return S.at(o, P.UFS + n) * rhoInv; });
+    const Comp mu = eos_mu<EK>(P, [&](int n) { return S.at(o, P.UFS + n) * rhoInv; });
     {   // reset_internal_energy
         const double Up = u[UMX] * rhoInv, Vp = u[UMY] * rhoInv, Wp = u[UMZ] * rhoInv;
         const double ke = 0.5 * (Up * Up + Vp * Vp + Wp * Wp);
         Eos s; s.rho = rho; s.T = P.small_temp; s.mu = mu;
-        eos_rt<false>(P, s);
+        eos_rt<false, false, EK>(P, s);
         const double small_e = s.e;
         u[UEINT] = amax(u[UEINT], rho * small_e);
         u[UEDEN] = amax(u[UEDEN], rho * (small_e + ke) + 0.0);
@@ -1057,18 +1060,19 @@ __device__ __forceinline__ int clean_zone(const DevPar& P, double* __restrict__ 
     }
     {   // computeTemp
         Eos s; s.rho = rho; s.T = u[UTEMP]; s.e = u[UEINT] * rhoInv; s.mu = mu;
-        eos_re<false>(P, s);
+        eos_re<false, false, EK>(P, s);
         u[UTEMP] = s.T;
     }
     return nfail;
 }
 
 // estdt<hydro> for one zone (timestep.H:84-139)
+template <int EK = 0>
 __device__ __forceinline__ double estdt_zone(const DevPar& P, const double* __restrict__ u, const A4& S, long o) {
     const double rhoInv = 1.0 / u[URHO];
     Eos s; s.rho = u[URHO]; s.T = u[UTEMP]; s.e = u[UEINT] * rhoInv;
-    s.mu = eos_mu(P, [&](int n) { return S.at(o, P.UFS + n) * rhoInv; });
-    eos_re<false>(P, s);
+    s.mu = eos_mu<EK>(P, [&](int n) { return S.at(o, P.UFS + n) * rhoInv; });
+    eos_re<false, true, EK>(P, s);
     const double ux = u[UMX] * rhoInv, uy = u[UMY] * rhoInv, uz = u[UMZ] * rhoInv;
     const double c = s.cs;
     const double dt1 = P.dx[0] / (c + fabs(ux));
@@ -1116,6 +1120,7 @@ struct UpdateArgs {
 // consup_hydro (Castro_ctu.cpp:10-83) + check_for_negative_density (Castro.cpp:3311-3402) + n_clean x clean_state + estdt
 //   Sin: where the pre-update state is read from -- S_new itself (reference semantics: S_new was pre-loaded with
 //   Sborder, Castro_sources.cpp:627) or Sborder directly (saves the copy pass for pure hydro)
+template <int EK = 0>
 static __global__ void __launch_bounds__(TPB) k_update(const DevPar P, const A4 Sb, const A4 Sin, const A4 Sn, const UpdateArgs a, const LaunchBox lb,
                                                 const double dt) {
     int i, j, k;
@@ -1162,11 +1167,11 @@ static __global__ void __launch_bounds__(TPB) k_update(const DevPar P, const A4 
             }
         }
         for (int c = 0; c < a.n_clean; ++c) {
-            const int nf = clean_zone(P, u, Sn, on);
+            const int nf = clean_zone<EK>(P, u, Sn, on);
             if (nf) atomicAdd(&a.counters[2], nf);
-            if (c == 0 && a.want_dt) dt0 = estdt_zone(P, u, Sn, on);
+            if (c == 0 && a.want_dt) dt0 = estdt_zone<EK>(P, u, Sn, on);
         }
-        if (a.want_dt) dt1 = (a.n_clean <= 1) ? ((a.n_clean == 1) ? dt0 : estdt_zone(P, u, Sn, on)) : estdt_zone(P, u, Sn, on);
+        if (a.want_dt) dt1 = (a.n_clean <= 1) ? ((a.n_clean == 1) ? dt0 : estdt_zone<EK>(P, u, Sn, on)) : estdt_zone<EK>(P, u, Sn, on);
         if (a.n_clean == 0) dt0 = dt1;
         bool nan = false;
 #pragma unroll
@@ -1199,6 +1204,7 @@ static __global__ void __launch_bounds__(TPB) k_store_flux(const DevPar P, const
 // ------------------------------------------------------------------------------------------------
 // stand-alone state kernels
 // ------------------------------------------------------------------------------------------------
+template <int EK = 0>
 static __global__ void __launch_bounds__(TPB) k_clean(const DevPar P, const A4 S, const LaunchBox lb, const int npass, int* counters) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
@@ -1207,7 +1213,7 @@ static __global__ void __launch_bounds__(TPB) k_clean(const DevPar P, const A4 S
 #pragma unroll
     for (int n = 0; n < 7; ++n) u[n] = S.at(o, n);
     int nf = 0;
-    for (int c = 0; c < npass; ++c) nf += clean_zone(P, u, S, o);
+    for (int c = 0; c < npass; ++c) nf += clean_zone<EK>(P, u, S, o);
 #pragma unroll
     for (int n = 0; n < 7; ++n) S.at(o, n) = u[n];
     if (nf && counters) atomicAdd(&counters[2], nf);
@@ -1216,6 +1222,7 @@ static __global__ void __launch_bounds__(TPB) k_clean(const DevPar P, const A4 S
 // the same with 128-bit accesses: one thread owns the zone pair (i, i+1) of a row and moves the seven thermodynamic components as
 // double2.  Requires an even row length, even strides, an even x offset of the box in its array and a 16-byte aligned base
 // (clean_pair_ok); anything else takes the scalar kernel.
+template <int EK = 0>
 static __global__ void __launch_bounds__(TPB) k_clean2(const DevPar P, const A4 S, const LaunchBox lb, const int npass, int* counters) {
     // lb.nx counts zone PAIRS here
     int ip2, j, k;
@@ -1229,7 +1236,7 @@ static __global__ void __launch_bounds__(TPB) k_clean2(const DevPar P, const A4 
         ua[n] = v.x; ub[n] = v.y;
     }
     int nf = 0;
-    for (int c = 0; c < npass; ++c) { nf += clean_zone(P, ua, S, o); nf += clean_zone(P, ub, S, o + 1); }
+    for (int c = 0; c < npass; ++c) { nf += clean_zone<EK>(P, ua, S, o); nf += clean_zone<EK>(P, ub, S, o + 1); }
 #pragma unroll
     for (int n = 0; n < 7; ++n) *reinterpret_cast<double2*>(&S.at(o, n)) = make_double2(ua[n], ub[n]);
     if (nf && counters) atomicAdd(&counters[2], nf);
@@ -1240,6 +1247,7 @@ inline bool clean_pair_ok(const A4& S, const Box3& bx) {
            ((reinterpret_cast<uintptr_t>(S.p) & 15) == 0);
 }
 
+template <int EK = 0>
 static __global__ void __launch_bounds__(TPB) k_estdt(const DevPar P, const A4 S, const LaunchBox lb, unsigned long long* dtmin) {
     int i, j, k;
     const bool active = thread_zone(lb, i, j, k);
@@ -1249,12 +1257,13 @@ static __global__ void __launch_bounds__(TPB) k_estdt(const DevPar P, const A4 S
         double u[7];
 #pragma unroll
         for (int n = 0; n < 7; ++n) u[n] = S.at(o, n);
-        d = estdt_zone(P, u, S, o);
+        d = estdt_zone<EK>(P, u, S, o);
     }
     block_min_atomic(d, dtmin);
 }
 
 // first zone (smallest linear index) whose dt equals the reduced minimum -> location (diagnostic, Castro.cpp:1652-1662)
+template <int EK = 0>
 static __global__ void __launch_bounds__(TPB) k_estdt_loc(const DevPar P, const A4 S, const LaunchBox lb, const unsigned long long* dtmin,
                                                    unsigned long long* loc) {
     int i, j, k;
@@ -1263,7 +1272,7 @@ static __global__ void __launch_bounds__(TPB) k_estdt_loc(const DevPar P, const 
     double u[7];
 #pragma unroll
     for (int n = 0; n < 7; ++n) u[n] = S.at(o, n);
-    const double d = estdt_zone(P, u, S, o);
+    const double d = estdt_zone<EK>(P, u, S, o);
     if ((unsigned long long)__double_as_longlong(d) == *dtmin) atomicMin(loc, (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x));
 }
 

@@ -56,12 +56,29 @@ struct HostEos {
         pres = rho * T * K_B / (m * M_U);
         e = pres / (p->eos_gamma - 1.0) * rhoinv;
     }
+    // Helmholtz EOS (eos_kind = 1): the host copy of ctu_helm.cuh on the loaded table; composition as EOS/eos_composition.H
+    bool helm_eval(int input, double& rho, double& T, double& pres, double& e, const double* xn) const {
+        helm::Table tb;
+        if (!helm_host_table(p, &tb)) return false;
+        helm::State s;
+        std::memset(&s, 0, sizeof(s));
+        s.rho = rho; s.T = T; s.p = pres; s.e = e;
+        double ye = 0.0, abar = 0.0;
+        for (int n = 0; n < p->nspec; ++n) { ye += xn[n] * p->zion[n] * (1.0 / p->aion[n]); abar += xn[n] * (1.0 / p->aion[n]); }
+        abar = 1.0 / abar;
+        s.abar = abar; s.y_e = ye; s.mu_e = 1.0 / ye; s.zbar = abar * ye;
+        helm::eos<true>(tb, input, s);
+        rho = s.rho; T = s.T; pres = s.p; e = s.e;
+        return true;
+    }
     void rt(double rho, double T, const double* xn, double& pres, double& e) const {   // eos_input_rt
+        if (p->eos_kind == 1) { helm_eval(helm::IN_RT, rho, T, pres, e, xn); return; }
         rho = hmin(1.e200, hmax(mindens(), rho));
         T = hmin(1.e200, hmax(mintemp(), T));
         from_rt(rho, T, mu(xn), pres, e);
     }
     void rp(double rho, double pin, const double* xn, double& T, double& e) const {     // eos_input_rp (actual_eos.H:116)
+        if (p->eos_kind == 1) { T = 100000.0; double pr = pin; helm_eval(helm::IN_RP, rho, T, pr, e, xn); return; }   // initial guess of the problem set-ups
         rho = hmin(1.e200, hmax(mindens(), rho));
         const double m = mu(xn);
         T = pin * m * M_U / (K_B * rho);
@@ -447,6 +464,7 @@ int hook_init(const std::string& path, const char* prob_params, const ctu_params
 }
 
 // Castro::initData tail (Castro.cpp:1186-1413): computeTemp -> enforce_consistent_e (:3215-3265) -> clean_state
+template <int EK>
 __global__ void __launch_bounds__(TPB) k_init_tail(const DevPar P, const A4 S, const LaunchBox lb) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
@@ -456,26 +474,26 @@ __global__ void __launch_bounds__(TPB) k_init_tail(const DevPar P, const A4 S, c
     for (int n = 0; n < 7; ++n) u[n] = S.at(o, n);
     const double rho = u[URHO];
     const double rhoInv = 1.0 / rho;
-    const double mu = eos_mu(P, [&](int n) { return S.at(o, P.UFS + n) * rhoInv; });
+    const Comp mu = eos_mu<EK>(P, [&](int n) { return S.at(o, P.UFS + n) * rhoInv; });
     {   // computeTemp = reset_internal_energy + T
         const double Up = u[UMX] * rhoInv, Vp = u[UMY] * rhoInv, Wp = u[UMZ] * rhoInv;
         const double ke = 0.5 * (Up * Up + Vp * Vp + Wp * Wp);
         Eos s; s.rho = rho; s.T = P.small_temp; s.mu = mu;
-        eos_rt<false>(P, s);
+        eos_rt<false, false, EK>(P, s);
         const double small_e = s.e;
         u[UEINT] = amax(u[UEINT], rho * small_e);
         u[UEDEN] = amax(u[UEDEN], rho * (small_e + ke) + 0.0);
         const double rho_eint = u[UEDEN] - rho * ke - 0.0;
         if (rho_eint > P.dual_energy_eta2 * u[UEDEN]) u[UEINT] = rho_eint;
         Eos t; t.rho = rho; t.T = u[UTEMP]; t.e = u[UEINT] * rhoInv; t.mu = mu;
-        eos_re<false>(P, t);
+        eos_re<false, false, EK>(P, t);
         u[UTEMP] = t.T;
     }
     {   // enforce_consistent_e
         const double uu = u[UMX] * rhoInv, vv = u[UMY] * rhoInv, ww = u[UMZ] * rhoInv;
         u[UEDEN] = u[UEINT] + 0.5 * rho * (uu * uu + vv * vv + ww * ww);
     }
-    clean_zone(P, u, S, o);
+    clean_zone<EK>(P, u, S, o);
 #pragma unroll
     for (int n = 0; n < 7; ++n) S.at(o, n) = u[n];
 }
@@ -667,6 +685,11 @@ int ctu_params_finalize(ctu_params_t* p) {
     if (p->small_temp < 0.0) p->small_temp = 1.e-100;
     if (p->small_pres < 0.0) p->small_pres = 1.e-100;
     if (p->small_ener < 0.0) p->small_ener = 1.e-100;
+    if (p->eos_kind == 1) {     // eos_init of the Helmholtz EOS: the table's lower limits (10^3 K, 10^-12 g/cc)
+        if (!helm_loaded()) return CTU_ERR_UNSUPPORTED;
+        p->small_temp = hmax(p->small_temp, std::pow(10.0, helm::TLO));
+        p->small_dens = hmax(p->small_dens, std::pow(10.0, helm::DLO));
+    }
     p->small_temp = hmax(p->small_temp, 1.e-200);
     p->small_dens = hmax(p->small_dens, 1.e-200);
     HostEos eos{p};
@@ -700,7 +723,8 @@ int ctu_problem_init(const char* problem, const char* prob_params, const ctu_par
     else if (name == "RT") rc = rt_init(par, geom, kv, P, a, lb, st);
     else return CTU_ERR_BAD_ARG;
     if (rc) return rc;
-    k_init_tail<<<nblk(lb.n), TPB, 0, st>>>(P, a, lb);
+    if (P.eos_kind == 1) k_init_tail<1><<<nblk(lb.n), TPB, 0, st>>>(P, a, lb);
+    else k_init_tail<0><<<nblk(lb.n), TPB, 0, st>>>(P, a, lb);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "../../include/castro_ctu.h"
+#include "ctu_helm.cuh"
 
 namespace ctu {
 
@@ -82,6 +83,8 @@ struct DevPar {
     int nspec, naux, nadv, npassive, nstate;
     int UFS, QFS_off;            // first species in U / offset of first species among the passives
     int gamc_const;              // gamma-law EOS: Gamma_1 is the same number in every zone
+    int eos_kind;                // 0 gamma law, 1 Helmholtz (table below)
+    helm::Table helm;            // device pointers of the Helmholtz table (eos_kind = 1; ctu_eos.cu)
     double difmag;
     double small_dens, small_temp, small_pres, small_ener;
     double dual_energy_eta1, dual_energy_eta2;

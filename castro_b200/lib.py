@@ -95,6 +95,8 @@ def lib():
         L.ctu_sim_read_plotfile.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ctu_sim_diag.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
         L.ctu_write_grid_diag.argtypes = [C.c_char_p, C.c_int, C.c_double, C.POINTER(C.c_double)]
+        L.ctu_eos_helm_load.argtypes = [C.c_char_p]
+        L.ctu_eos_helm_eval.argtypes = [C.POINTER(abi.Params), C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.ctu_selftest_mathfast.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
         L.ctu_problem_init.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3,
                                        C.POINTER(abi.Fab), C.c_void_p]
@@ -471,3 +473,16 @@ class Dist:
         st = C.c_int(0)
         check(lib().ctu_dist_step_host(self.h, host_in.ctypes.data, host_out.ctypes.data, dt, est, C.byref(st)), "ctu_dist_step_host")
         return st.value, (est[0], est[1])
+
+
+def helm_load(path):
+    """Helmholtz EOS table (helm_table.dat of Microphysics); must precede params_finalize with eos_kind = 1"""
+    check(lib().ctu_eos_helm_load(str(path).encode()), "ctu_eos_helm_load")
+
+
+def helm_eval(par, input, abar, ye, states, where=0):
+    """states: ndarray [n, 4] = rho, T, e, p -> ndarray [n, 8] = rho, T, e, p, cs, gam1, dpde, dpdr_e (host or device copy of the EOS)"""
+    a = np.ascontiguousarray(states, dtype=np.float64)
+    out = np.empty((a.shape[0], 8))
+    check(lib().ctu_eos_helm_eval(C.byref(par), input, abar, ye, a.shape[0], a.ctypes.data, out.ctypes.data, where), "ctu_eos_helm_eval")
+    return out

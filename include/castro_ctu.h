@@ -323,6 +323,15 @@ int  ctu_dist_step_host(ctu_dist_t* dist, const double* host_in, double* host_ou
 int  ctu_dist_halo_plan(const int dims[3], int rank, const int domlo[3], const int domhi[3], const int periodic[3], int max_msgs,
                         int* out, int* recv_order);
 
+/* ---- Helmholtz ("stellar") EOS, ctu_params_t.eos_kind = 1 (Microphysics EOS/helmholtz/actual_eos.H:154-1296) -------------------
+ * ctu_eos_helm_load reads helm_table.dat (the file Microphysics ships and Castro reads from the run directory,
+ * actual_eos.H:1298-1473) once per process; it must precede ctu_params_finalize / any compute call with eos_kind = 1 (they return
+ * CTU_ERR_UNSUPPORTED otherwise).  ctu_eos_helm_eval evaluates n states with the host (where = 0) or the device (where = 1) copy of
+ * the EOS: input 0 (rho, T), 1 (rho, p), 2 (rho, e), 3 (T, p); in[4 n] = rho, T, e, p; out[8 n] = rho, T, e, p, cs, gam1, dpde, dpdr_e. */
+int  ctu_eos_helm_load(const char* helm_table_path);
+int  ctu_eos_helm_loaded(void);
+int  ctu_eos_helm_eval(const ctu_params_t* par, int input, double abar, double ye, int n, const double* in, double* out, int where);
+
 /* Self-test of the branch-free FP64 division / reciprocal / square-root sequences the flux-stage kernels compute with (they
  * restate the fast path of nvcc's own IEEE operators; a kernel replays a tile with the language operators whenever a sequence
  * flags an operand).  Draws `iters` random operand pairs per thread (131072 threads) with binary exponents uniform in

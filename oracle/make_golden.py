@@ -106,10 +106,12 @@ RT_CASES = {
 }
 
 
-def run_case(name, n_cell, max_step, snaps, extra, exe=EXE, inputs=INPUTS, ncomp=None):
+def run_case(name, n_cell, max_step, snaps, extra, exe=EXE, inputs=INPUTS, ncomp=None, link=None):
     if isinstance(n_cell, int):
         n_cell = (n_cell,) * 3
     wd = tempfile.mkdtemp(prefix="golden_")
+    if link:
+        os.symlink(link, os.path.join(wd, os.path.basename(link)))
     try:
         args = [exe, inputs, "amr.max_level=0", "amr.n_cell=%d %d %d" % n_cell, "amr.max_grid_size=64",
                 "amr.blocking_factor=8", "max_step=%d" % max_step, "stop_time=1.e9", "amr.plot_int=1",
@@ -154,6 +156,20 @@ SOD_CASES = {
 }
 
 
+# Sod_stellar: the shock tube with the Helmholtz EOS and the 3-species ignition network (Exec/hydro_tests/Sod_stellar/inputs-test1-helm*:
+# rho 1e7 | 1e6 g/cc, T 1e8 | 1e6 K, Colella & Glaz solver as shipped; also CGF and HLLC), SURVEY §8(f) rank 2.  The executable reads
+# helm_table.dat from its run directory.
+SODS_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_sodstellar.ex")
+SODS_DIR = "/root/reference/Exec/hydro_tests/Sod_stellar"
+HELM_TABLE = os.path.join(ROOT, "oracle", "_ref", "helm_table.dat")
+SODS_CASES = {
+    "sodstellar_x_cg": ("inputs-test1-helm", (32, 8, 8), 20, [0, 20], ["geometry.prob_hi=1.e6 2.5e5 2.5e5"]),
+    "sodstellar_x_cgf": ("inputs-test1-helm", (32, 8, 8), 20, [0, 20], ["geometry.prob_hi=1.e6 2.5e5 2.5e5", "castro.riemann_solver=0"]),
+    "sodstellar_y_hllc": ("inputs-test1-helm-y", (8, 32, 8), 20, [0, 20], ["geometry.prob_hi=2.5e5 1.e6 2.5e5", "castro.riemann_solver=2"]),
+    "sodstellar_z_cgf": ("inputs-test1-helm-z", (8, 8, 32), 20, [0, 20], ["geometry.prob_hi=2.5e5 2.5e5 1.e6", "castro.riemann_solver=0"]),
+}
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     for name, (n, ms, snaps, extra) in CASES.items():
@@ -172,6 +188,11 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case(name, n, ms, snaps, extra, exe=RT_EXE, inputs=RT_INPUTS, ncomp=8)
+    for name, (inp, n, ms, snaps, extra) in SODS_CASES.items():
+        if only and name not in only:
+            continue
+        run_case(name, n, ms, snaps, extra + ["amr.check_int=-1", "castro.sum_interval=-1"], exe=SODS_EXE, inputs=os.path.join(SODS_DIR, inp),
+                 link=HELM_TABLE)
     for name, (inp, n, ms, snaps, extra) in SOD_CASES.items():
         if only and name not in only:
             continue

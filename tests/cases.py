@@ -152,3 +152,32 @@ def load_sod_case(name):
     prob = dict(p_l=1.0, u_l=0.0, rho_l=1.0, p_r=0.1, u_r=0.0, rho_r=0.125, idir=c["idir"], frac=0.5)
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
     return par, geom, prob, g, snaps
+
+
+SODSTELLAR_CASES = {
+    "sodstellar_x_cg": dict(solver=1, idir=1, lo_bc=(2, 3, 3)),
+    "sodstellar_x_cgf": dict(solver=0, idir=1, lo_bc=(2, 3, 3)),
+    "sodstellar_y_hllc": dict(solver=2, idir=2, lo_bc=(4, 2, 4)),
+    "sodstellar_z_cgf": dict(solver=0, idir=3, lo_bc=(4, 4, 2)),
+}
+IGNITION_NET = ((12.0, 6.0), (16.0, 8.0), (24.0, 12.0))      # networks/general_null/ignition.net: C12 O16 Mg24
+HELM_TABLE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "helm_table.dat")
+
+
+def load_sodstellar_case(name):
+    """Exec/hydro_tests/Sod_stellar/inputs-test1-helm{,-y,-z}: the shock tube with the Helmholtz EOS (eos_kind = 1) and the ignition
+    network, cfl 0.8, init_shrink 0.1, change_max 1.1; goldens from the reference's Sod_stellar executable (SODS_CASES)."""
+    c = SODSTELLAR_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    par = abi.default_params()
+    par.riemann_solver = c["solver"]
+    par.cfl, par.init_shrink, par.change_max = 0.8, 0.1, 1.1
+    par.eos_kind = 1
+    par.nspec = 3
+    for m, (a, z) in enumerate(IGNITION_NET):
+        par.aion[m], par.zion[m] = a, z
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), lo_bc=c["lo_bc"], hi_bc=c["lo_bc"])
+    prob = dict(T_l=1.e8, u_l=0.0, rho_l=1.0e7, T_r=1.e6, u_r=0.0, rho_r=1.e6, use_Tinit=1, idir=c["idir"], frac=0.5)
+    snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
+    return par, geom, prob, g, snaps
