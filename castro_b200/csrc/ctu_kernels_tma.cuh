@@ -39,7 +39,10 @@ constexpr int TX = 32, TY = CTU_TY, TZ = CTU_TZ, TTHR = TX * TY * TZ;      // fl
 constexpr int UTY = 4, UTZ = 2, UTTHR = TX * UTY * UTZ;                        // update kernel: 32x4x2 zones, 3 CTAs per SM
 // resident CTAs per SM the flux-stage kernels are compiled for: every further passive scalar adds ~6 KB of flux tiles per CTA
 // (4 CTAs fit with one passive, 3 with up to four, 2 with five)
-template <int NP> struct TmaMinB { static constexpr int value = (NP == 1) ? CTU_TMA_MINB : (NP <= 4) ? 3 : 2; };
+#ifndef CTU_TMA_MINB_NP2
+#define CTU_TMA_MINB_NP2 3
+#endif
+template <int NP> struct TmaMinB { static constexpr int value = (NP == 1) ? CTU_TMA_MINB : (NP <= 4) ? CTU_TMA_MINB_NP2 : 2; };
 constexpr int ceven(int n) { return (n + 1) & ~1; }
 constexpr size_t al128(size_t b) { return (b + 127) & ~(size_t)127; }
 
