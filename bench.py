@@ -544,7 +544,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the run of the reference's own CUDA build (reference_gpu)")
-    ap.add_argument("--ref-gpu-n", type=int, default=256, help="edge of the box the reference's CUDA build is timed on")
+    ap.add_argument("--ref-gpu-n", type=int, default=512, help="edge of the box the reference's CUDA build is timed on")
     ap.add_argument("--no-checks", action="store_true", help="skip parity_check (N = 1) / decomp_check (N > 1)")
     ap.add_argument("--problem", default="sedov", choices=["sedov", "kh", "rt"],
                     help="developer option: kh = Kelvin-Helmholtz as shipped (advected scalar + species, periodic), rt = Rayleigh-Taylor with "

@@ -145,6 +145,9 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (!p) return CTU_ERR_BAD_ARG;
     if (p->nspec < 1 || p->nspec > CTU_MAX_SPEC || p->naux < 0 || p->nadv < 0 || p->nspec + p->naux + p->nadv > 3 * CTU_MAX_SPEC)
         return CTU_ERR_BAD_ARG;
+    // parameters that never went through ctu_params_finalize (ctu_params_defaults / ctu_parse_inputs leave the floors at -1e200, the
+    // reference's "unset" marker) would run with negative floors: refuse them
+    if (!(p->small_dens > 0.0) || !(p->small_temp > 0.0) || !(p->small_pres > 0.0) || !(p->small_ener > 0.0)) return CTU_ERR_BAD_ARG;
     if (p->ppm_type != 0 && p->ppm_type != 1) return CTU_ERR_UNSUPPORTED;
     if (p->ppm_type == 0 && (p->plm_iorder < 1 || p->plm_iorder > 2 || p->plm_limiter < 1 || p->plm_limiter > 2)) return CTU_ERR_BAD_ARG;
     if (p->riemann_solver < 0 || p->riemann_solver > 2) return CTU_ERR_UNSUPPORTED;

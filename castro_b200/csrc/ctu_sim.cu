@@ -798,6 +798,23 @@ int ctu_parse_inputs(const char* path, const char* overrides, ctu_params_t* par,
     gd("castro.pslope_cutoff_density", par->pslope_cutoff_density);
     gi("castro.plm_iorder", par->plm_iorder); gi("castro.plm_limiter", par->plm_limiter);
     gi("castro.do_grav", par->do_grav); gi("castro.grav_source_type", par->grav_source_type); gd("gravity.const_grav", par->const_grav);
+    // keys that switch the reference onto a path this library does not implement: refuse the inputs file rather than run another scheme
+    {
+        struct Bad { const char* key; double ok; };
+        static const Bad bad[] = {{"castro.time_integration_method", 0}, {"castro.do_sponge", 0}, {"castro.use_reconstructed_gamma1", 0},
+                                  {"castro.hybrid_hydro", 0}, {"amr.max_level", 0}, {"castro.do_react", 0}, {"castro.do_rotation", 0},
+                                  {"castro.do_radiation", 0}, {"castro.diffuse_temp", 0}, {"castro.add_ext_src", 0},
+                                  {"castro.allow_non_unit_aspect_zones", 0}, {"castro.do_scf_initial_model", 0}};
+        for (const Bad& b : bad) {
+            double v = b.ok;
+            gd(b.key, v);
+            if (v != b.ok) {
+                std::fprintf(stderr, "[castro_ctu] inputs: %s = %g is outside the supported path\n", b.key, v);
+                return CTU_ERR_UNSUPPORTED;
+            }
+        }
+        if (has("castro.speed_limit")) { double v = 0.0; gd("castro.speed_limit", v); if (v != 0.0) return CTU_ERR_UNSUPPORTED; }
+    }
     int nc[3] = {32, 32, 32};
     gi3("amr.n_cell", nc);
     double plo[3] = {0, 0, 0}, phi[3] = {1, 1, 1};

@@ -97,3 +97,15 @@ def test_parse_inputs_all_hydro_options():
     assert (p.transverse_use_eos, p.transverse_reset_rhoe, p.source_term_predictor, p.grav_source_type) == (1, 1, 1, 2)
     assert (p.first_order_hydro, p.use_flattening, p.ppm_do_limiting) == (1, 0, 0)
     assert p.shock_detection_threshold == 0.5 and p.pslope_cutoff_density == 1.e-3 and p.const_grav == -9.8 and p.difmag == 0.2
+
+
+def test_parse_inputs_refuses_keys_that_leave_the_supported_path():
+    """keys that switch the reference onto another path (AMR levels, SDC integrators, sponge, reactions, ...) must not be
+    ignored silently"""
+    from castro_b200 import lib
+    inputs = os.path.join(ROOT, "bench_inputs", "inputs.sedov3d")
+    lib.parse_inputs(inputs, "castro.cfl=0.4")
+    for bad in ("amr.max_level=1", "castro.time_integration_method=3", "castro.do_sponge=1", "castro.hybrid_hydro=1", "castro.do_react=1",
+                "castro.use_reconstructed_gamma1=1", "castro.speed_limit=1.e9"):
+        with pytest.raises(lib.CtuError):
+            lib.parse_inputs(inputs, bad)
