@@ -25,7 +25,7 @@ class Fab(C.Structure):
 
 class Geom(C.Structure):
     _fields_ = [("domlo", Int3), ("domhi", Int3), ("dx", Dbl3), ("problo", Dbl3), ("probhi", Dbl3),
-                ("coord", C.c_int), ("periodic", Int3), ("lo_bc", Int3), ("hi_bc", Int3)]
+                ("coord", C.c_int), ("periodic", Int3), ("lo_bc", Int3), ("hi_bc", Int3), ("dim", C.c_int)]
 
 
 class Params(C.Structure):
@@ -101,8 +101,10 @@ def default_params():
     return p
 
 
-def make_geom(n_cell, problo=(0, 0, 0), probhi=(1, 1, 1), periodic=(0, 0, 0), lo_bc=(2, 2, 2), hi_bc=(2, 2, 2)):
+def make_geom(n_cell, problo=(0, 0, 0), probhi=(1, 1, 1), periodic=(0, 0, 0), lo_bc=(2, 2, 2), hi_bc=(2, 2, 2), dim=3):
+    """dim = 1: the 1-D Cartesian path (n_cell = (nx, 1, 1); y and z carry one zone and no ghost zones)"""
     g = Geom()
+    g.dim = dim
     for d in range(3):
         g.domlo[d] = 0
         g.domhi[d] = n_cell[d] - 1

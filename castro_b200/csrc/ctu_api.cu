@@ -110,6 +110,7 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
     P.QFS_off = par->nadv;
     P.gamc_const = (par->eos_kind == 0);
     P.eos_kind = par->eos_kind;
+    P.dim = (geom && geom->dim == 1) ? 1 : 3;
     if (par->eos_kind == 1 && helm_device_table(par, &P.helm) != 0) std::memset(&P.helm, 0, sizeof(P.helm));
     P.difmag = par->difmag;
     P.small_dens = par->small_dens; P.small_temp = par->small_temp;
@@ -159,6 +160,15 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     // constant-gravity driver are instantiated for the gamma law only
     if (p->eos_kind == 1 && (p->transverse_use_eos || p->transverse_reset_rhoe || p->ppm_temp_fix || p->do_grav)) return CTU_ERR_UNSUPPORTED;
     if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
+    if (g && g->dim != 0 && g->dim != 1 && g->dim != 3) return CTU_ERR_UNSUPPORTED;       // 2-D: not built
+    if (g && g->dim == 1) {
+        // the 1-D Cartesian path (Castro_ctu_hydro.cpp:464-481): one zone in y and z; HLLC is refused in 1-D by the reference itself
+        // (Castro.cpp:410-413); options that need transverse or source machinery are not instantiated for it
+        if (g->domlo[1] != g->domhi[1] || g->domlo[2] != g->domhi[2]) return CTU_ERR_BAD_ARG;
+        if (p->riemann_solver == 2 || p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->do_grav || p->use_pslope ||
+            p->ppm_well_balanced || p->ppm_temp_fix || p->eos_kind != 0)
+            return CTU_ERR_UNSUPPORTED;
+    }
     return 0;
 }
 
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(128) k_selftest_mathfast(const int elo, const 
 
 bool tma_ok(const DevPar& P) {
     static const bool disabled = (std::getenv("CTU_NO_TMA") != nullptr);
-    if (disabled || !P.gamc_const) return false;
+    if (disabled || !P.gamc_const || P.dim != 3) return false;
     if (P.npassive < 1 || P.npassive > CTU_TMA_MAX_NP) return false;
     if (P.ppm_temp_fix) return false;        // EOS re-sync of the interface states before each solve: register-staged family
     if (P.use_pslope || P.ppm_well_balanced) return false;   // hydrostatic-pressure-aware reconstruction: register-staged family
@@ -360,6 +370,8 @@ int ctu_workspace_stage_times(ctu_workspace_t* w, double ms[CTU_NSTAGE], int lau
     return 0;
 }
 
+static int ws_reserve(ctu_workspace* w, size_t bytes, cudaStream_t st);
+namespace ctu { int ws_reserve_bytes(ctu_workspace* w, size_t bytes, cudaStream_t st) { return ws_reserve(w, bytes, st); } }
 static int ws_reserve(ctu_workspace* w, size_t bytes, cudaStream_t st) {
     if (bytes <= w->arena_bytes) return 0;
     if (w->arena) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(w->arena)); w->arena = nullptr; w->arena_bytes = 0; }
@@ -413,7 +425,7 @@ HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     r->P_predictor = par->source_term_predictor;
     r->np = P.npassive;
     r->vbx = make_box(valid_lo, valid_hi);
-    if (!r->vbx.ok() || Sborder->ncomp < P.nstate || S_new->ncomp < P.nstate || !fab_covers(Sborder, grow(r->vbx, CTU_NGROW)) ||
+    if (!r->vbx.ok() || Sborder->ncomp < P.nstate || S_new->ncomp < P.nstate || !fab_covers(Sborder, growd(r->vbx, CTU_NGROW, P.dim)) ||
         !fab_covers(S_new, r->vbx)) {
         delete r; *rc_out = CTU_ERR_BAD_ARG; return nullptr;
     }
@@ -635,6 +647,63 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
     return 0;
 }
 
+// The 1-D body (AMREX_SPACEDIM == 1, Castro_ctu_hydro.cpp:464-481): ctoprim -> flattening + div u along x -> trace in x -> ONE
+// Riemann solve per face (its flux is the final flux) -> artificial viscosity + species-flux normalisation -> conservative
+// update with the fused epilogue.  Register-staged kernels; a 1-D box is a few hundred zones.
+int hydro_box_1d(HydroRun* r) {
+    ctu_workspace* ws = r->ws;
+    const DevPar& P = r->P;
+    const int np = r->np, NQS = QS_X + np, NIS = IS_X + np, NFX = FX_X + np;
+    cudaStream_t st = r->st;
+    const Box3 tb = r->vbx;
+    const Box3 qbx = grow(tb, 4, 0, 0), obx = grow(tb, 1, 0, 0);
+    Box3 ibx = obx; ibx.hi[0] += 1;
+    const size_t need = ((size_t)qbx.npts() * NQS + (size_t)ibx.npts() * (2 + 2 * NIS + NFX)) * sizeof(double);
+    int rc = ws_reserve_bytes(ws, need, st);
+    if (rc) return rc;
+    double* p = ws->arena;
+    const A4 qs = make_a4(p, qbx); p += qbx.npts() * NQS;
+    const A4 fd = make_a4(p, ibx); p += ibx.npts() * 2;
+    TraceArgs ta;
+    std::memset(&ta, 0, sizeof(ta));
+    ta.qm[0] = make_a4(p, ibx); p += ibx.npts() * NIS;
+    ta.qp[0] = make_a4(p, ibx); p += ibx.npts() * NIS;
+    for (int d = 0; d < 3; ++d) { ta.vlo[d] = tb.lo[d]; ta.vhi[d] = tb.hi[d]; }
+    const A4 F0 = make_a4(p, ibx); p += ibx.npts() * NFX;
+    A4 none;
+    std::memset(&none, 0, sizeof(none));
+    LaunchBox lb = make_lb(qbx);
+    k_ctoprim<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
+    lb = make_lb(obx);
+    k_flat_div_1d<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb);
+    // the node-centred div u is needed on the faces lo .. hi+1: one more than obx holds on the high side is not (obx = lo-1 .. hi+1)
+    if (P.ppm_type == 0) k_trace_plm<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none);
+    else k_trace<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none, ws->d_counters + 5);
+    Box3 xbx = tb; xbx.hi[0] += 1;
+    lb = make_lb(xbx);
+    k_riemann1<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F0, lb, fd);
+    k_av_1d<<<nblocks(lb.n), TPB, 0, st>>>(P, fd, r->Sb, F0, lb);
+    UpdateArgs ua;
+    std::memset(&ua, 0, sizeof(ua));
+    for (int d = 0; d < 3; ++d) ua.F[d] = F0;          // only F[0] is read in 1-D
+    ua.dtmin = ws->d_dtmin; ua.counters = ws->d_counters;
+    ua.n_clean = r->n_clean; ua.want_dt = r->want_dt;
+    lb = make_lb(tb);
+    k_update<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, r->from_sb ? r->Sb : r->Sn, r->Sn, ua, lb, r->dt);
+    r->launches += 7;
+    if (r->flux && r->flux[0]) {
+        if (!fab_covers(r->flux[0], xbx) || r->flux[0]->ncomp < P.nstate) return CTU_ERR_BAD_ARG;
+        // scale_flux in 1-D: dt * F * area with area = 1; k_store_flux multiplies by dx_y dx_z, so the 1-D call passes unit widths
+        DevPar P1 = P; P1.dx[1] = 1.0; P1.dx[2] = 1.0;
+        A4 mo; std::memset(&mo, 0, sizeof(mo));
+        if (r->mass_flux && r->mass_flux[0]) { if (!fab_covers(r->mass_flux[0], xbx)) return CTU_ERR_BAD_ARG; mo = make_a4(*r->mass_flux[0]); }
+        lb = make_lb(xbx);
+        k_store_flux<0><<<nblocks(lb.n), TPB, 0, st>>>(P1, F0, make_a4(*r->flux[0]), mo, lb, r->dt);
+        ++r->launches;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : CTU_ERR_CUDA;
+}
+
 // read the reductions back (synchronises the stream), fold the stage timers, free the run
 int hydro_end(HydroRun* r, double dt_est[2], int dt_loc[3], int n_bad[2]) {
     ctu_workspace* ws = r->ws;
@@ -694,7 +763,7 @@ int fill_boundary_planes(const ctu_params_t* par, const ctu_geom_t* geom, const 
     }
     const DevPar P = make_devpar(par, geom);
     const Box3 vbx = make_box(valid_lo, valid_hi);
-    Box3 gbx = grow(vbx, ng);
+    Box3 gbx = growd(vbx, ng, P.dim);
     if (!fab_covers(S, gbx)) return CTU_ERR_BAD_ARG;
     gbx.lo[2] = std::max(gbx.lo[2], zlo); gbx.hi[2] = std::min(gbx.hi[2], zhi);
     if (!gbx.ok()) return 0;
@@ -719,6 +788,12 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     HydroRun* r = hydro_begin(ws, par, geom, valid_lo, valid_hi, Sborder, S_new, flux, mass_flux, dt, flags, dt_est != nullptr,
                               (cudaStream_t)stream, &rc, old_src, src_corr);
     if (!r) return rc;
+    if (r->P.dim == 1) {
+        rc = hydro_box_1d(r);
+        if (rc) { delete r; return rc; }
+        hydro_set_slab_info(r, 1, 1);
+        return hydro_end(r, dt_est, dt_loc, n_bad);
+    }
     const long nzv = valid_hi[2] - valid_lo[2] + 1;
     long KS = hydro_max_slab_planes(r);
     if (KS < 1) { delete r; return CTU_ERR_NOMEM; }

@@ -151,6 +151,51 @@ static __global__ void __launch_bounds__(TPB) k_flat_div(const DevPar P, const A
     }
 }
 
+// 1-D (AMREX_SPACEDIM == 1): flattening along x only (flatten.H:141-150), div(i) = (u_i - u_{i-1}) / dx (advection_util.cpp:228-231)
+static __global__ void __launch_bounds__(TPB) k_flat_div_1d(const DevPar P, const A4 qs, const A4 fd, const LaunchBox lb) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long oq = qs.idx(i, j, k), of = fd.idx(i, j, k);
+    const double* __restrict__ pp = qs.p + oq + QS_P * qs.sn;
+    const double* __restrict__ uu = qs.p + oq + QS_U * qs.sn;
+    double flatn = 1.0;
+    if (P.first_order_hydro) flatn = 0.0;
+    else if (P.use_flattening) flatn = flatten_dir([&](int s) { return pp[s]; }, [&](int s) { return uu[s]; });
+    fd.at(of, 0) = flatn;
+    const double dxinv = 1.0 / P.dx[0];
+    fd.at(of, 1) = (uu[0] - uu[-1]) * dxinv;
+}
+
+// 1-D: the final x flux IS the first-pass flux; what k_final does after its Riemann solve is applied here in place:
+// apply_av (advection_util.cpp:354-419 with dg1 = dg2 = 0: the four-term average runs over one node) and normalize_species_fluxes
+static __global__ void __launch_bounds__(TPB) k_av_1d(const DevPar P, const A4 fd, const A4 U, const A4 F, const LaunchBox lb) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long of = F.idx(i, j, k), od = fd.idx(i, j, k), ou = U.idx(i, j, k);
+    const double d = fd.at(od, 1);
+    double div1 = 0.25 * (d + d + d + d);
+    div1 = P.difmag * smin(0.0, div1);
+    const double dL = P.dx[0];
+    double F0 = 0.0;
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+        const double div_var = div1 * (U.at(ou, n) - U.at(ou - 1, n));
+        const double f = F.at(of, n) + dL * div_var;
+        F.at(of, n) = f;
+        if (n == 0) F0 = f;
+    }
+    double sum = 0.0;
+    for (int ip = 0; ip < P.npassive; ++ip) {
+        const double div_var = div1 * (U.at(ou, UFA + ip) - U.at(ou - 1, UFA + ip));
+        const double f = F.at(of, FX_X + ip) + dL * div_var;
+        F.at(of, FX_X + ip) = f;
+        if (ip >= P.QFS_off && ip < P.QFS_off + P.nspec) sum += f;
+    }
+    double fac = 1.0;
+    if (fabs(sum) > 2.220446049250313e-16 * fabs(F0)) fac = F0 / sum;
+    for (int ip = P.QFS_off; ip < P.QFS_off + P.nspec; ++ip) F.at(of, FX_X + ip) = F.at(of, FX_X + ip) * fac;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Source terms in the tracing: hydro::src_to_prim (advection_util.H:16-79) and the traced primitive sources of
 // trace_ppm (trace_ppm.cpp:309-440).  srcq scratch layout: rho u v w p (rho e)  (reference src_q minus the unused QTEMP slot).
@@ -1076,8 +1121,8 @@ __device__ __forceinline__ double estdt_zone(const DevPar& P, const double* __re
     const double ux = u[UMX] * rhoInv, uy = u[UMY] * rhoInv, uz = u[UMZ] * rhoInv;
     const double c = s.cs;
     const double dt1 = P.dx[0] / (c + fabs(ux));
-    const double dt2 = P.dx[1] / (c + fabs(uy));
-    const double dt3 = P.dx[2] / (c + fabs(uz));
+    const double dt2 = (P.dim == 1) ? dt1 : P.dx[1] / (c + fabs(uy));       // timestep.H:113-130: dt2 = dt3 = dt1 in 1-D
+    const double dt3 = (P.dim == 1) ? dt1 : P.dx[2] / (c + fabs(uz));
     return amin(amin(dt1, dt2), dt3);
 }
 
@@ -1136,12 +1181,23 @@ static __global__ void __launch_bounds__(TPB) k_update(const DevPar P, const A4 
         const long f0p = f0 + 1, f1p = f1 + F1.sj, f2p = f2 + F2.sk;
         double u[7];
         const double rho_old = Sb.at(ob, URHO);
+        if (P.dim == 1) {   // consup_hydro with AMREX_SPACEDIM == 1: volume = dx, area = 1 (Castro_util.H:205-213, 295-303); only F0 exists
+            const double vi = 1.0 / P.dx[0], a = 1.0;
+#pragma unroll
+            for (int n = 0; n < 6; ++n) u[n] = Sin.at(oi, n) + dt * (F0.at(f0, n) * a - F0.at(f0p, n) * a) * vi;
+            double pdu = (F0.at(f0p, FX_PG) + F0.at(f0, FX_PG)) * (F0.at(f0p, FX_UG) * a - F0.at(f0, FX_UG) * a);
+            pdu = 0.5 * pdu * vi;
+            u[UEINT] = u[UEINT] - dt * pdu;
+            for (int ip = 0; ip < P.npassive; ++ip) {
+                const int n = FX_X + ip;
+                Sn.at(on, UFA + ip) = Sin.at(oi, UFA + ip) + dt * (F0.at(f0, n) * a - F0.at(f0p, n) * a) * vi;
+            }
+        } else {
 #pragma unroll
         for (int n = 0; n < 6; ++n) {
             u[n] = Sin.at(oi, n) + dt * (F0.at(f0, n) * a0 - F0.at(f0p, n) * a0 + F1.at(f1, n) * a1 - F1.at(f1p, n) * a1 +
                                         F2.at(f2, n) * a2 - F2.at(f2p, n) * a2) * volinv;
         }
-        u[UTEMP] = Sin.at(oi, UTEMP);   // the T flux is identically zero (Castro_ctu_hydro.cpp:1141)
         {
             double pdu = (F0.at(f0p, FX_PG) + F0.at(f0, FX_PG)) * (F0.at(f0p, FX_UG) * a0 - F0.at(f0, FX_UG) * a0);
             pdu += (F1.at(f1p, FX_PG) + F1.at(f1, FX_PG)) * (F1.at(f1p, FX_UG) * a1 - F1.at(f1, FX_UG) * a1);
@@ -1154,6 +1210,8 @@ static __global__ void __launch_bounds__(TPB) k_update(const DevPar P, const A4 
             Sn.at(on, UFA + ip) = Sin.at(oi, UFA + ip) + dt * (F0.at(f0, n) * a0 - F0.at(f0p, n) * a0 + F1.at(f1, n) * a1 - F1.at(f1p, n) * a1 +
                                                               F2.at(f2, n) * a2 - F2.at(f2p, n) * a2) * volinv;
         }
+        }
+        u[UTEMP] = Sin.at(oi, UTEMP);   // the T flux is identically zero (Castro_ctu_hydro.cpp:1141)
         // check_for_negative_density
         {
             const double rho = u[URHO];

@@ -41,6 +41,8 @@ inline Box3 grow(Box3 b, int gx, int gy, int gz) {
     return b;
 }
 inline Box3 grow(Box3 b, int g) { return grow(b, g, g, g); }
+// grow in the dimensions a run of `dim` dimensions has
+inline Box3 growd(Box3 b, int g, int dim) { return dim == 1 ? grow(b, g, 0, 0) : grow(b, g, g, g); }
 inline Box3 intersect(Box3 a, const Box3& b) {
     for (int d = 0; d < 3; ++d) { a.lo[d] = a.lo[d] > b.lo[d] ? a.lo[d] : b.lo[d]; a.hi[d] = a.hi[d] < b.hi[d] ? a.hi[d] : b.hi[d]; }
     return a;
@@ -84,6 +86,7 @@ struct DevPar {
     int UFS, QFS_off;            // first species in U / offset of first species among the passives
     int gamc_const;              // gamma-law EOS: Gamma_1 is the same number in every zone
     int eos_kind;                // 0 gamma law, 1 Helmholtz (table below)
+    int dim;                     // AMREX_SPACEDIM of the run: 3, or 1 (one zone, no ghost zones in y and z)
     helm::Table helm;            // device pointers of the Helmholtz table (eos_kind = 1; ctu_eos.cu)
     double difmag;
     double small_dens, small_temp, small_pres, small_ener;

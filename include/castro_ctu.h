@@ -69,6 +69,8 @@ typedef struct ctu_geom_t {
     int coord;            /* 0 = Cartesian (only value supported in 3-D) */
     int periodic[3];
     int lo_bc[3], hi_bc[3];   /* 0 interior, 1 inflow, 2 outflow, 3 symmetry, 4 slipwall, 5 noslipwall */
+    int dim;              /* AMREX_SPACEDIM of the run: 3 (or 0 = 3), or 1 -- the 1-D Cartesian path of Castro_ctu_hydro.cpp:464-481 (one
+                           * zone in y and z, no ghost zones there; BASELINE config[0], Sod 1-D) */
 } ctu_geom_t;
 
 /* castro.* (Source/driver/_cpp_parameters), eos.* and network table values read by the hot path */

@@ -58,6 +58,8 @@ if [ "$what" = all ] || [ "$what" = kh ];     then build KH Castro3d_kh DIM=3; f
 if [ "$what" = kh4 ]; then build KH Castro3d_kh4 DIM=3 NETWORK_INPUTS=triple_alpha_plus_o.net; fi
 # Sod_stellar: the shock tube with the Helmholtz (stellar) EOS and the 3-species ignition network; golden generator
 if [ "$what" = sodstellar ]; then build Sod_stellar Castro3d_sodstellar DIM=3 USE_MHD=FALSE; fi
+# the literal BASELINE config[0]: Sod in ONE dimension (DIM=1), golden generator for the 1-D path
+if [ "$what" = sod1d ]; then build Sod Castro1d_sod DIM=1; fi
 if [ "$what" = all ] || [ "$what" = sod ];    then build Sod Castro3d_sod DIM=3; fi
 if [ "$what" = all ] || [ "$what" = rt ]; then
   if [ ! -d "$W/Castro3d_rt" ]; then cp -r "$REF/Exec/hydro_tests/RT" "$W/Castro3d_rt"; fi

@@ -170,6 +170,46 @@ SODS_CASES = {
 }
 
 
+# BASELINE config[0] literally: the Sod shock tube in ONE dimension (DIM=1 build of the reference), 128 zones in two boxes of 64, PPM + CGF,
+# run to stop_time = 0.2 (inputs-sod-x), plus the two harder tubes of the same directory (test2: double rarefaction, test3: strong shock)
+SOD1D_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro1d_sod.ex")
+SOD1D_CASES = {
+    "sod1d_cgf": ("inputs-sod-x", 128, 81, [0, 40, 81], ["castro.riemann_solver=0"]),
+    "sod1d_cg": ("inputs-sod-x", 128, 40, [0, 40], ["castro.riemann_solver=1"]),
+    "sod1d_test2_cgf": ("inputs-test2-x", 128, 40, [0, 40], ["castro.riemann_solver=0"]),
+    # test3 (strong shock: p 1000 | 0.01) set through overrides of inputs-sod-x (inputs-test3-x names a refinement indicator the 1-D build lacks)
+    "sod1d_test3_plm": ("inputs-sod-x", 128, 40, [0, 40], ["castro.riemann_solver=0", "castro.ppm_type=0", "problem.p_l=1000.0", "problem.p_r=0.01",
+                                                           "problem.rho_l=1.0", "problem.rho_r=1.0"]),
+}
+
+
+def run_case_1d(name, inp, nx, max_step, snaps, extra):
+    wd = tempfile.mkdtemp(prefix="golden_")
+    try:
+        args = [SOD1D_EXE, os.path.join(SOD_DIR, inp), "amr.max_level=0", "amr.n_cell=%d" % nx, "amr.max_grid_size=64", "amr.blocking_factor=8",
+                "max_step=%d" % max_step, "amr.plot_int=1", "amr.check_int=-1", "amr.derive_plot_vars=NONE", "castro.sum_interval=-1",
+                "amr.plot_file=plt", "castro.v=0", "amr.v=0"] + extra
+        out = subprocess.run(args, cwd=wd, capture_output=True, text=True)
+        if out.returncode != 0:
+            print(out.stdout[-3000:], out.stderr[-3000:])
+            raise RuntimeError(name)
+        nsteps = max(int(d[3:]) for d in os.listdir(wd) if d.startswith("plt") and d[3:].isdigit())
+        times, states = [], {}
+        for s in range(nsteps + 1):
+            pf = os.path.join(wd, "plt%05d" % s)
+            h = read_header(pf)
+            times.append(h["time"])
+            if s in snaps or s == nsteps:
+                h, U = read_plotfile(pf)
+                states["U%d" % s] = U
+        meta = dict(n_cell=np.array((nx, 1, 1)), times=np.array(times), names=np.array(h["names"]), problo=np.array(h["problo"]),
+                    probhi=np.array(h["probhi"]), overrides=np.array(extra), inputs=np.array(inp))
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **meta, **states)
+        print(name, "ok: steps", nsteps, "t_end", times[-1])
+    finally:
+        shutil.rmtree(wd)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     for name, (n, ms, snaps, extra) in CASES.items():
@@ -188,6 +228,10 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case(name, n, ms, snaps, extra, exe=RT_EXE, inputs=RT_INPUTS, ncomp=8)
+    for name, (inp, nx, ms, snaps, extra) in SOD1D_CASES.items():
+        if only and name not in only:
+            continue
+        run_case_1d(name, inp, nx, ms, snaps, extra)
     for name, (inp, n, ms, snaps, extra) in SODS_CASES.items():
         if only and name not in only:
             continue

@@ -181,3 +181,29 @@ def load_sodstellar_case(name):
     prob = dict(T_l=1.e8, u_l=0.0, rho_l=1.0e7, T_r=1.e6, u_r=0.0, rho_r=1.e6, use_Tinit=1, idir=c["idir"], frac=0.5)
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
     return par, geom, prob, g, snaps
+
+
+SOD1D_CASES = {
+    "sod1d_cgf": dict(solver=0, cfl=0.9, prob=dict(p_l=1.0, u_l=0.0, rho_l=1.0, p_r=0.1, u_r=0.0, rho_r=0.125)),
+    "sod1d_cg": dict(solver=1, cfl=0.9, prob=dict(p_l=1.0, u_l=0.0, rho_l=1.0, p_r=0.1, u_r=0.0, rho_r=0.125)),
+    "sod1d_test2_cgf": dict(solver=0, cfl=0.8, prob=dict(p_l=0.4, u_l=-2.0, rho_l=1.0, p_r=0.4, u_r=2.0, rho_r=1.0)),
+    "sod1d_test3_plm": dict(solver=0, cfl=0.9, par=dict(ppm_type=0), prob=dict(p_l=1000.0, u_l=0.0, rho_l=1.0, p_r=0.01, u_r=0.0, rho_r=1.0)),
+}
+
+
+def load_sod1d_case(name):
+    """BASELINE config[0]: Exec/hydro_tests/Sod in ONE dimension (reference built with DIM=1), 128 zones, gamma = 1.4, outflow ends;
+    goldens from oracle/_ref/Castro1d_sod.ex (oracle/make_golden.py SOD1D_CASES).  The states are [ncomp, 1, 1, nx]."""
+    c = SOD1D_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    par = abi.default_params()
+    par.riemann_solver = c["solver"]
+    par.cfl, par.init_shrink, par.change_max = c["cfl"], 0.1, 1.05
+    par.eos_gamma, par.eos_assume_neutral = 1.4, 1
+    for k, v in c.get("par", {}).items():
+        setattr(par, k, v)
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    geom = abi.make_geom(n_cell, probhi=(1.0, 1.0, 1.0), lo_bc=(2, 2, 2), hi_bc=(2, 2, 2), dim=1)
+    prob = dict(c["prob"], idir=1, frac=0.5)
+    snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
+    return par, geom, prob, g, snaps

@@ -21,9 +21,16 @@ def read_header(pf):
     problo = [float(x) for x in next(it).split()]
     probhi = [float(x) for x in next(it).split()]
     next(it)  # ref ratios
-    dom = re.findall(r"\((-?\d+),(-?\d+),(-?\d+)\)", next(it))
-    domlo = [int(x) for x in dom[0]]
-    domhi = [int(x) for x in dom[1]]
+    dline = next(it)
+    if dim == 3:
+        dom = re.findall(r"\((-?\d+),(-?\d+),(-?\d+)\)", dline)
+        domlo = [int(x) for x in dom[0]]
+        domhi = [int(x) for x in dom[1]]
+    else:       # 1-D: ((lo) (hi) (0))
+        dom = re.findall(r"\((-?\d+)\)", dline)
+        domlo = [int(dom[0]), 0, 0]
+        domhi = [int(dom[1]), 0, 0]
+        problo, probhi = problo + [0.0, 0.0], probhi + [0.0, 0.0]
     steps = int(next(it).split()[0])
     dx = [float(x) for x in next(it).split()]
     return dict(version=version, ncomp=ncomp, names=names, dim=dim, time=time, finest=finest, problo=problo,
@@ -32,11 +39,14 @@ def read_header(pf):
 
 def read_plotfile(pf):
     h = read_header(pf)
-    assert h["finest"] == 0 and h["dim"] == 3
+    assert h["finest"] == 0 and h["dim"] in (1, 3)
     lev = os.path.join(pf, "Level_0")
     with open(os.path.join(lev, "Cell_H")) as f:
         txt = f.read()
-    boxes = re.findall(r"\(\((-?\d+),(-?\d+),(-?\d+)\) \((-?\d+),(-?\d+),(-?\d+)\) \(0,0,0\)\)", txt)
+    if h["dim"] == 3:
+        boxes = re.findall(r"\(\((-?\d+),(-?\d+),(-?\d+)\) \((-?\d+),(-?\d+),(-?\d+)\) \(0,0,0\)\)", txt)
+    else:
+        boxes = [(a, "0", "0", b, "0", "0") for a, b in re.findall(r"\(\((-?\d+)\) \((-?\d+)\) \(0\)\)", txt)]
     fods = re.findall(r"FabOnDisk: (\S+) (\d+)", txt)
     assert len(boxes) == len(fods)
     nx = [h["domhi"][d] - h["domlo"][d] + 1 for d in range(3)]

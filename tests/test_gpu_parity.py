@@ -682,6 +682,32 @@ def test_helmholtz_eos_device_matches_host_and_reference_values():
             assert np.max(err) < 1e-7, "Newton mode %d: the converged T does not reproduce the input: %g" % (mode, np.max(err))
 
 
+@pytest.mark.parametrize("name", ["sod1d_cgf", "sod1d_cg", "sod1d_test2_cgf", "sod1d_test3_plm"])
+def test_sod_one_dimensional_matches_reference(name):
+    """BASELINE config[0] literally: Sod in ONE dimension (geom.dim = 1; the reference built with DIM=1).  Problem hook vs the
+    reference's initial plotfile, then the full time loop (sod1d_cgf: to stop_time = 0.2, 81 steps) vs the reference's states and
+    times, bit for bit; HLLC is refused in 1-D like the reference refuses it (Castro.cpp:410-413)."""
+    _torch()
+    from castro_b200 import lib
+    from cases import load_sod1d_case
+    par, geom, prob, g, snaps = load_sod1d_case(name)
+    lib.params_finalize(par)
+    nx = int(g["n_cell"][0])
+    sim = lib.Sim(par, geom, (0, 0, 0), (nx - 1, 0, 0))
+    sim.init_problem("Sod", prob)
+    assert_bitwise(sim.download(), g["U0"], name + " initial data")
+    n = snaps[-1]
+    stop = 0.2 if name == "sod1d_cgf" else -1.0
+    rc, t, dt, hist = sim.advance(n, stop_time=stop)
+    assert rc == 0 and len(hist) == n
+    assert_bitwise(sim.download(), g["U%d" % n], "%s step %d" % (name, n))
+    np.testing.assert_allclose(np.cumsum(np.concatenate([[0.0], hist])), g["times"][:n + 1], rtol=1e-14, atol=0)
+    sim.close()
+    par.riemann_solver = 2
+    with pytest.raises(lib.CtuError):
+        lib.Sim(par, geom, (0, 0, 0), (nx - 1, 0, 0))
+
+
 def test_host_streaming_mixed_boundaries():
     """ctu_sim_step_host promises the bits of upload + pre + fill + hydro + download.  Periodic x/y with a physical boundary in z
     (reflecting wall below, outflow above) is the case where a z-ghost zone is filled from an x/y-ghost zone of the boundary plane:

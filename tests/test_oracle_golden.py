@@ -97,3 +97,27 @@ def test_oracle_sod_shock_tube_matches_golden(name):
         nbad = int((got[m] != ref[m]).sum())
         assert nbad == 0, "%s comp %d: %d zones differ, max abs %g" % (name, m, nbad, np.abs(got[m] - ref[m]).max())
     np.testing.assert_allclose(np.cumsum(np.concatenate([[0.0], hist])), g["times"][:n + 1], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("name", ["sod1d_cgf", "sod1d_cg", "sod1d_test2_cgf", "sod1d_test3_plm"])
+def test_oracle_sod_1d_matches_golden(name):
+    """BASELINE config[0] literally -- Sod in ONE dimension (the reference built with DIM=1; Castro_ctu_hydro.cpp:464-481: trace in x,
+    one Riemann solve per face, no transverse terms): the oracle's 1-D path, started from the reference's initial plotfile, against
+    the reference's states (sod1d_cgf runs to stop_time = 0.2 in 81 steps) and times, bit for bit"""
+    import oracle_lib as O
+    from cases import load_sod1d_case
+    par, geom, prob, g, snaps = load_sod1d_case(name)
+    O.params_finalize(par)
+    U0 = g["U0"]
+    ng = 4
+    nx = U0.shape[3]
+    U = np.zeros((U0.shape[0], 1 + 2 * ng, 1 + 2 * ng, nx + 2 * ng))
+    U[:, ng, ng, ng:-ng] = U0[:, 0, 0, :]
+    n = snaps[-1]
+    stop = 0.2 if name == "sod1d_cgf" else -1.0
+    st, t, dt, hist = O.run(par, geom, U, n, stop_time=stop)
+    assert st == 0 and len(hist) == n
+    assert np.array_equal(U[:, ng, ng, ng:-ng], g["U%d" % n][:, 0, 0, :])
+    np.testing.assert_allclose(np.cumsum(np.concatenate([[0.0], hist])), g["times"][:n + 1], rtol=1e-14, atol=0)
+    if name == "sod1d_cgf":
+        assert t == 0.2
