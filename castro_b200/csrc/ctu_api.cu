@@ -262,6 +262,7 @@ bool tma_ok(const DevPar& P) {
     if (P.riemann_solver == 1 && P.npassive > CTU_TMA_CG_MAX_NP) return false;   // Colella & Glaz: tile kernels instantiated for 1-2 passives
     if (P.limit_fluxes_on_small_dens) return false;     // ditto the density-floor flux limiter
     if (P.hybrid_riemann) return false;      // the HLL blend lives in the register-staged family only (keeps the tile kernels lean)
+    if (P.transverse_reset_rhoe) return false;   // reads F(rho e) in the transverse updates, which the tile kernels neither store nor stage
     return tma::encode_fn() != nullptr;
 }
 

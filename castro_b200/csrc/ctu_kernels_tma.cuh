@@ -12,6 +12,7 @@
 //                     normalisation                                                          [a16 + a12 + a18]
 //   k_update_tma      consup_hydro + check_for_negative_density + clean_state + estdt        [a19, a22, a20]
 #pragma once
+#include <cstdlib>
 #include "ctu_kernels.cuh"
 #include "ctu_tma.cuh"
 
@@ -68,22 +69,43 @@ __device__ unsigned long long ctu_phase_ticks[4][3];
 struct TileGrid {
     int lo0, lo1, lo2, hi0, hi1, hi2;   // launch box
     int ntx, nty, ntz;
+    int zg;                             // tile planes per z-group of the launch order (tile_order)
 };
+// CTU_ZGROUP=<n> (environment, developer A/B runs) overrides the default number of tile planes per z-group; 1 = plain x-y-z order
+inline int zgroup() {
+    static int zg = 0;
+    if (!zg) { const char* e = std::getenv("CTU_ZGROUP"); zg = e ? std::atoi(e) : 8; if (zg < 1) zg = 1; }
+    return zg;
+}
 template <int TYv, int TZv>
 inline TileGrid make_tg_t(const Box3& b) {
     TileGrid t;
     t.lo0 = b.lo[0]; t.lo1 = b.lo[1]; t.lo2 = b.lo[2]; t.hi0 = b.hi[0]; t.hi1 = b.hi[1]; t.hi2 = b.hi[2];
     t.ntx = (b.hi[0] - b.lo[0] + TX) / TX; t.nty = (b.hi[1] - b.lo[1] + TYv) / TYv; t.ntz = (b.hi[2] - b.lo[2] + TZv) / TZv;
+    t.zg = zgroup();
     return t;
 }
 inline TileGrid make_tg(const Box3& b) { return make_tg_t<TY, TZ>(b); }
 inline unsigned tg_blocks(const TileGrid& t) { return (unsigned)t.ntx * (unsigned)t.nty * (unsigned)t.ntz; }
 
 struct TileCtx { int i0, j0, k0, tx, ty, tz, i, j, k; };
+// Launch order of the tiles of a box: x fastest, then zg consecutive tile planes in z, then y, then the groups of planes.
+// Tiles that are neighbours in z (they share their z-halo planes: a third of every tile that has a z halo) are then
+// ntx blocks apart instead of ntx * nty, i.e. resident in the same wave, and the halo is read from L2 instead of HBM; the y halos
+// (ntx * zg blocks apart) stay inside the wave too.  Only the first plane of every group misses.
+__device__ __forceinline__ void tile_order(const int bt, const int ntx, const int nty, const int ntz, const int zg, int& bx, int& by, int& bz) {
+    bx = bt % ntx;
+    const int r = bt / ntx;
+    const int per = nty * zg, g = r / per, rem = r - g * per;
+    const int zc = min(zg, ntz - g * zg);       // the last group may be thinner
+    by = rem / zc;
+    bz = g * zg + (rem - by * zc);
+}
 template <int TYv, int TZv>
 __device__ __forceinline__ TileCtx tile_ctx_t(const TileGrid& tg, const int bt) {
     TileCtx c;
-    const int bx = bt % tg.ntx, r = bt / tg.ntx, by = r % tg.nty, bz = r / tg.nty;
+    int bx, by, bz;
+    tile_order(bt, tg.ntx, tg.nty, tg.ntz, tg.zg, bx, by, bz);
     c.i0 = tg.lo0 + bx * TX; c.j0 = tg.lo1 + by * TYv; c.k0 = tg.lo2 + bz * TZv;
     c.tx = threadIdx.x & (TX - 1); c.ty = (threadIdx.x / TX) % TYv; c.tz = threadIdx.x / (TX * TYv);
     c.i = c.i0 + c.tx; c.j = c.j0 + c.ty; c.k = c.k0 + c.tz;
@@ -133,6 +155,24 @@ using NodeTile = STile<EXT, TY + (N != 1), TZ + (N != 2)>;
 template <int N>
 using OwnFluxTile = STile<EXT, UTY + (N == 1), UTZ + (N == 2)>;     // update kernel's tile
 
+// The flux tiles of the transverse stages are staged WITHOUT the F(rho e) component (FX_EINT): the transverse updates read it only
+// under castro.transverse_reset_rhoe (that option runs the register-staged family, see tma_ok), so the first- and second-pass
+// kernels do not store it either: 1/9 of the bytes of F^T and F^{N|T} never travel.  Two TMA boxes per array, components
+// [0, FX_EINT) and [FX_UG, NFX), land in two dense sub-tiles; operator() takes the component index of the global layout.
+template <class T, int NFXv>
+struct SplitFluxTile {
+    static constexpr int NA = FX_EINT, NB = NFXv - FX_UG;
+    static constexpr size_t B_A = al128((size_t)NA * T::ZONES * 8), B_B = (size_t)NB * T::ZONES * 8, BYTES = B_A + B_B;
+    static constexpr unsigned TX = (unsigned)((NA + NB) * T::ZONES * 8);
+    const double* __restrict__ a;
+    const double* __restrict__ b;
+    __device__ __forceinline__ explicit SplitFluxTile(const unsigned char* base)
+        : a(reinterpret_cast<const double*>(base)), b(reinterpret_cast<const double*>(base + B_A)) {}
+    __device__ __forceinline__ double operator()(int off, int n) const {
+        return n < FX_EINT ? a[n * T::ZONES + off] : b[(n - FX_UG) * T::ZONES + off];
+    }
+};
+
 template <int NP>
 __device__ __forceinline__ bool is_species(const DevPar& P, int ip) { return ip >= P.QFS_off && ip < P.QFS_off + P.nspec; }
 
@@ -177,7 +217,8 @@ __device__ __forceinline__ void trans_single_side(const DevPar& P, const FT& sF,
                                                   double* qo, double* xo) {
     double fl[6], fr[6], dX[NP];
 #pragma unroll
-    for (int n = 0; n < 6; ++n) { fl[n] = sF(oz, n); fr[n] = sF(oz + ST, n); }
+    for (int n = 0; n < FX_EINT; ++n) { fl[n] = sF(oz, n); fr[n] = sF(oz + ST, n); }
+    fl[FX_EINT] = fr[FX_EINT] = 0.0;      // not staged (SplitFluxTile)
     const double ugm = sF(oz, FX_UG), ugp = sF(oz + ST, FX_UG), pgm = sF(oz, FX_PG), pgp = sF(oz + ST, FX_PG);
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) dX[ip] = cdt * (sF(oz + ST, FX_X + ip) - sF(oz, FX_X + ip));
@@ -203,7 +244,8 @@ __device__ __forceinline__ void trans_final_side(const DevPar& P, const F1T& sF1
                                                  const double* x, double c1, double c2, double* qo, double* xo) {
     double f1l[6], f1r[6], f2l[6], f2r[6];
 #pragma unroll
-    for (int n = 0; n < 6; ++n) { f1l[n] = sF1(o1, n); f1r[n] = sF1(o1 + S1, n); f2l[n] = sF2(o2, n); f2r[n] = sF2(o2 + S2, n); }
+    for (int n = 0; n < FX_EINT; ++n) { f1l[n] = sF1(o1, n); f1r[n] = sF1(o1 + S1, n); f2l[n] = sF2(o2, n); f2r[n] = sF2(o2 + S2, n); }
+    f1l[FX_EINT] = f1r[FX_EINT] = f2l[FX_EINT] = f2r[FX_EINT] = 0.0;      // not staged (SplitFluxTile)
     const double rho = q[IS_RHO];
     const double rrnew = rho - c1 * (f1r[0] - f1l[0]) - c2 * (f2r[0] - f2l[0]);
     bool reset = (P.transverse_reset_density && rrnew < 0.0);
@@ -231,12 +273,13 @@ struct Trans2Smem {
     using F1T = FluxTile<N, T1>;
     using F2T = FluxTile<N, T2>;
     using CT = ZoneTile<N>;
-    static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = (size_t)NFX * F1T::ZONES * 8, B_F2 = (size_t)NFX * F2T::ZONES * 8,
-                            B_C = (size_t)CT::ZONES * 8;
+    using S1 = SplitFluxTile<F1T, NFX>;
+    using S2 = SplitFluxTile<F2T, NFX>;
+    static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = S1::BYTES, B_F2 = S2::BYTES, B_C = (size_t)CT::ZONES * 8;
     static constexpr size_t B_QS = CTU_Q_LDG ? 0 : B_Q;    // shared-memory bytes of one interface-state tile
     static constexpr size_t O_QM = 0, O_QP = al128(O_QM + B_QS), O_F1 = al128(O_QP + B_QS), O_F2 = al128(O_F1 + B_F1),
                             O_C = al128(O_F2 + B_F2), O_BAR = al128(O_C + B_C), TOTAL = O_BAR + 128;
-    static constexpr unsigned TX_BYTES = (unsigned)(2 * B_QS + B_F1 + B_F2 + B_C);
+    static constexpr unsigned TX_BYTES = (unsigned)(2 * B_QS + S1::TX + S2::TX + B_C);
 };
 
 struct Trans2Args {
@@ -255,8 +298,8 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
     using L = Trans2Smem<N, NP>;
     constexpr int T1 = L::T1, T2 = L::T2;
     if (!in1 && !in2) return;
-    const typename L::F1T sF1{reinterpret_cast<const double*>(smem + L::O_F1)};
-    const typename L::F2T sF2{reinterpret_cast<const double*>(smem + L::O_F2)};
+    const typename L::S1 sF1(smem + L::O_F1);
+    const typename L::S2 sF2(smem + L::O_F2);
     const typename L::CT sC{reinterpret_cast<const double*>(smem + L::O_C)};
     double ql[6], qr[6], xl[NP], xr[NP];
 #if !CTU_Q_LDG
@@ -279,12 +322,12 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
         constexpr int sN = L::F1T::stride(N), sT = L::F1T::stride(T1);
         const int oz = L::F1T::off(c.tx + pg, c.ty, c.tz);
         double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
-        trans_single_side<M, NP, typename L::F1T, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
-        trans_single_side<M, NP, typename L::F1T, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
+        trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
+        trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
         solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
         const long o = a.Fo1.idx(c.i, c.j, c.k);
 #pragma unroll
-        for (int n = 0; n < 6; ++n) a.Fo1.at(o, n) = F[n];
+        for (int n = 0; n < FX_EINT; ++n) a.Fo1.at(o, n) = F[n];      // F(rho e) is not stored (SplitFluxTile)
         a.Fo1.at(o, FX_UG) = ugd;
         a.Fo1.at(o, FX_PG) = pgd;
 #pragma unroll
@@ -294,12 +337,12 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
         constexpr int sN = L::F2T::stride(N), sT = L::F2T::stride(T2);
         const int oz = L::F2T::off(c.tx + pg, c.ty, c.tz);
         double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
-        trans_single_side<M, NP, typename L::F2T, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
-        trans_single_side<M, NP, typename L::F2T, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
+        trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
+        trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
         solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
         const long o = a.Fo2.idx(c.i, c.j, c.k);
 #pragma unroll
-        for (int n = 0; n < 6; ++n) a.Fo2.at(o, n) = F[n];
+        for (int n = 0; n < FX_EINT; ++n) a.Fo2.at(o, n) = F[n];      // F(rho e) is not stored (SplitFluxTile)
         a.Fo2.at(o, FX_UG) = ugd;
         a.Fo2.at(o, FX_PG) = pgd;
 #pragma unroll
@@ -310,7 +353,8 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
 template <int N, int NP, int RS = 0>
 static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
 k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
-             const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
+             const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f1b, const __grid_constant__ CUtensorMap m_f2,
+             const __grid_constant__ CUtensorMap m_f2b, const __grid_constant__ CUtensorMap m_c,
              const Trans2Args a, const TileGrid tg) {
     using L = Trans2Smem<N, NP>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -331,7 +375,9 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
         tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
 #endif
         tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_F1 + L::S1::B_A, &m_f1b, bar, gi - pg, fj - (N == 1), fk - (N == 2), FX_UG);
         tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_F2 + L::S2::B_A, &m_f2b, bar, gi - pg, fj - (N == 1), fk - (N == 2), FX_UG);
         tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
     }
     const bool in1 = a.b1.contains(c.i, c.j, c.k), in2 = a.b2.contains(c.i, c.j, c.k);
@@ -379,18 +425,19 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
 template <int N, int NP>
 static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
 k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
-                 const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
+                 const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f1b, const __grid_constant__ CUtensorMap m_f2,
+             const __grid_constant__ CUtensorMap m_f2b, const __grid_constant__ CUtensorMap m_c,
                  const Trans2Args a, const TileGrid tg, const int ntiles) {
     using L = Trans2Smem<N, NP>;
     using M = MathFastW;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar1 = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
     uint64_t* bar2 = bar1 + 1;
-    const typename L::F1T sF1{reinterpret_cast<const double*>(smem + L::O_F1)};
-    const typename L::F2T sF2{reinterpret_cast<const double*>(smem + L::O_F2)};
+    const typename L::S1 sF1(smem + L::O_F1);
+    const typename L::S2 sF2(smem + L::O_F2);
     const typename L::CT sC{reinterpret_cast<const double*>(smem + L::O_C)};
     const FaceTile sQM{reinterpret_cast<const double*>(smem + L::O_QM)}, sQP{reinterpret_cast<const double*>(smem + L::O_QP)};
-    constexpr unsigned TX1 = (unsigned)(2 * L::B_Q + L::B_F1 + L::B_C), TX2 = (unsigned)L::B_F2;
+    constexpr unsigned TX1 = (unsigned)(2 * L::B_Q + L::S1::TX + L::B_C), TX2 = (unsigned)L::S2::TX;
     auto issue1 = [&](const int t) {      // q-, q+, F^{T1}, c of tile t
         const TileCtx n = tile_ctx(tg, t);
         const int fi = n.i0 - a.ilo[0], fj = n.j0 - a.ilo[1], fk = n.k0 - a.ilo[2], pf = fi & 1;
@@ -400,6 +447,7 @@ k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const
         tma::load_4d(smem + L::O_QM, &m_qm, bar1, fi - pf, fj, fk, 0);
         tma::load_4d(smem + L::O_QP, &m_qp, bar1, fi - pf, fj, fk, 0);
         tma::load_4d(smem + L::O_F1, &m_f1, bar1, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_F1 + L::S1::B_A, &m_f1b, bar1, gi - pg, fj - (N == 1), fk - (N == 2), FX_UG);
         tma::load_4d(smem + L::O_C, &m_c, bar1, qi - pq, n.j0 - (N == 1) - a.qlo[1], n.k0 - (N == 2) - a.qlo[2], QS_C);
     };
     auto issue2 = [&](const int t) {      // F^{T2} of tile t
@@ -408,6 +456,7 @@ k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const
         const int gi = fi - (N == 0), pg = gi & 1;
         tma::mbar_arrive_expect_tx(bar2, TX2);
         tma::load_4d(smem + L::O_F2, &m_f2, bar2, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_F2 + L::S2::B_A, &m_f2b, bar2, gi - pg, fj - (N == 1), fk - (N == 2), FX_UG);
     };
     // tiles are handed out dynamically (one global counter per launch): SMs do not run at the same speed (two dies, far L2 partitions,
     // replays), and a static stride would make every launch wait for its slowest CTA.  A CTA always knows its current and its next
@@ -445,8 +494,8 @@ k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const
         if (in1) {
             constexpr int sN = L::F1T::stride(N), sT = L::F1T::stride(L::T1);
             const int oz = L::F1T::off(c.tx + pg, c.ty, c.tz);
-            trans_single_side<M, NP, typename L::F1T, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
-            trans_single_side<M, NP, typename L::F1T, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
+            trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
+            trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
         }
         __syncthreads();                                  // group 1 is in registers everywhere: its buffers take the next tile
         if (threadIdx.x == 0) {
@@ -458,7 +507,7 @@ k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const
             solve_face_r<M, N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
             const long o = a.Fo1.idx(c.i, c.j, c.k);
 #pragma unroll
-            for (int n = 0; n < 6; ++n) a.Fo1.at(o, n) = F[n];
+            for (int n = 0; n < FX_EINT; ++n) a.Fo1.at(o, n) = F[n];
             a.Fo1.at(o, FX_UG) = ugd;
             a.Fo1.at(o, FX_PG) = pgd;
 #pragma unroll
@@ -468,8 +517,8 @@ k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const
         if (in2) {
             constexpr int sN = L::F2T::stride(N), sT = L::F2T::stride(L::T2);
             const int oz = L::F2T::off(c.tx + pg, c.ty, c.tz);
-            trans_single_side<M, NP, typename L::F2T, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
-            trans_single_side<M, NP, typename L::F2T, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
+            trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
+            trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
         }
         __syncthreads();
         if (threadIdx.x == 0 && tn < ntiles) issue2(tn);
@@ -479,7 +528,7 @@ k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const
             solve_face_r<M, N, NP>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
             const long o = a.Fo2.idx(c.i, c.j, c.k);
 #pragma unroll
-            for (int n = 0; n < 6; ++n) a.Fo2.at(o, n) = F[n];
+            for (int n = 0; n < FX_EINT; ++n) a.Fo2.at(o, n) = F[n];
             a.Fo2.at(o, FX_UG) = ugd;
             a.Fo2.at(o, FX_PG) = pgd;
 #pragma unroll
@@ -499,7 +548,8 @@ k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const
 template <int N, int NP>
 static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
 k_trans2_replay(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
-                const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
+                const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f1b, const __grid_constant__ CUtensorMap m_f2,
+             const __grid_constant__ CUtensorMap m_f2b, const __grid_constant__ CUtensorMap m_c,
                 const Trans2Args a, const TileGrid tg) {
     using L = Trans2Smem<N, NP>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -519,7 +569,9 @@ k_trans2_replay(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const 
             tma::load_4d(smem + L::O_QM, &m_qm, bar, fi - pf, fj, fk, 0);
             tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
             tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+            tma::load_4d(smem + L::O_F1 + L::S1::B_A, &m_f1b, bar, gi - pg, fj - (N == 1), fk - (N == 2), FX_UG);
             tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+            tma::load_4d(smem + L::O_F2 + L::S2::B_A, &m_f2b, bar, gi - pg, fj - (N == 1), fk - (N == 2), FX_UG);
             tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
         }
         const bool in1 = a.b1.contains(c.i, c.j, c.k), in2 = a.b2.contains(c.i, c.j, c.k);
@@ -540,12 +592,14 @@ struct FinalSmem {
     using F2T = FluxTile<N, T2>;
     using CT = ZoneTile<N>;
     using DT = NodeTile<N>;
-    static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = (size_t)NFX * F1T::ZONES * 8, B_F2 = (size_t)NFX * F2T::ZONES * 8,
+    using S1 = SplitFluxTile<F1T, NFX>;
+    using S2 = SplitFluxTile<F2T, NFX>;
+    static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = S1::BYTES, B_F2 = S2::BYTES,
                             B_C = (size_t)CT::ZONES * 8, B_D = (size_t)DT::ZONES * 8;
     static constexpr size_t B_QS = CTU_Q_LDG ? 0 : B_Q;
     static constexpr size_t O_QM = 0, O_QP = al128(O_QM + B_QS), O_F1 = al128(O_QP + B_QS), O_F2 = al128(O_F1 + B_F1),
                             O_C = al128(O_F2 + B_F2), O_D = al128(O_C + B_C), O_BAR = al128(O_D + B_D), TOTAL = O_BAR + 128;
-    static constexpr unsigned TX_BYTES = (unsigned)(2 * B_QS + B_F1 + B_F2 + B_C + B_D);
+    static constexpr unsigned TX_BYTES = (unsigned)(2 * B_QS + S1::TX + S2::TX + B_C + B_D);
 };
 
 struct FinalArgs {
@@ -563,8 +617,8 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
     using L = FinalSmem<N, NP>;
     constexpr int T1 = L::T1, T2 = L::T2;
     if (!active) return;
-    const typename L::F1T sF1{reinterpret_cast<const double*>(smem + L::O_F1)};
-    const typename L::F2T sF2{reinterpret_cast<const double*>(smem + L::O_F2)};
+    const typename L::S1 sF1(smem + L::O_F1);
+    const typename L::S2 sF2(smem + L::O_F2);
     const typename L::CT sC{reinterpret_cast<const double*>(smem + L::O_C)};
     const typename L::DT sD{reinterpret_cast<const double*>(smem + L::O_D)};
     double ql[6], qr[6], xl[NP], xr[NP];
@@ -587,8 +641,8 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
     constexpr int s1N = L::F1T::stride(N), s1T = L::F1T::stride(T1), s2N = L::F2T::stride(N), s2T = L::F2T::stride(T2);
     const int o1 = L::F1T::off(c.tx + pg, c.ty, c.tz), o2 = L::F2T::off(c.tx + pg, c.ty, c.tz);
     double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
-    trans_final_side<M, NP, typename L::F1T, s1T, typename L::F2T, s2T>(P, sF1, o1, sF2, o2, ql, xl, a.c1, a.c2, qlo, xlo);
-    trans_final_side<M, NP, typename L::F1T, s1T, typename L::F2T, s2T>(P, sF1, o1 + s1N, sF2, o2 + s2N, qr, xr, a.c1, a.c2, qro, xro);
+    trans_final_side<M, NP, typename L::S1, s1T, typename L::S2, s2T>(P, sF1, o1, sF2, o2, ql, xl, a.c1, a.c2, qlo, xlo);
+    trans_final_side<M, NP, typename L::S1, s1T, typename L::S2, s2T>(P, sF1, o1 + s1N, sF2, o2 + s2N, qr, xr, a.c1, a.c2, qro, xro);
     solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
 
     // apply_av (advection_util.cpp:354-419): div1 = difmag * min(0, <div u> over the 4 nodes of the face)
@@ -623,7 +677,8 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
 template <int N, int NP, int RS = 0>
 static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
 k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
-            const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f2, const __grid_constant__ CUtensorMap m_c,
+            const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f1b, const __grid_constant__ CUtensorMap m_f2,
+             const __grid_constant__ CUtensorMap m_f2b, const __grid_constant__ CUtensorMap m_c,
             const __grid_constant__ CUtensorMap m_d, const FinalArgs a, const TileGrid tg) {
     using L = FinalSmem<N, NP>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -643,7 +698,9 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
         tma::load_4d(smem + L::O_QP, &m_qp, bar, fi - pf, fj, fk, 0);
 #endif
         tma::load_4d(smem + L::O_F1, &m_f1, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_F1 + L::S1::B_A, &m_f1b, bar, gi - pg, fj - (N == 1), fk - (N == 2), FX_UG);
         tma::load_4d(smem + L::O_F2, &m_f2, bar, gi - pg, fj - (N == 1), fk - (N == 2), 0);
+        tma::load_4d(smem + L::O_F2 + L::S2::B_A, &m_f2b, bar, gi - pg, fj - (N == 1), fk - (N == 2), FX_UG);
         tma::load_4d(smem + L::O_C, &m_c, bar, qi - pq, c.j0 - (N == 1) - a.qlo[1], c.k0 - (N == 2) - a.qlo[2], QS_C);
         tma::load_4d(smem + L::O_D, &m_d, bar, fi - pf, fj, fk, 1);
     }
@@ -863,7 +920,7 @@ struct TraceRiemannArgs {
     Box3 obx;             // zones to trace: grow(slab, 1)
     int vlo, vhi;         // valid range of the slab along D
     int qlo[3];           // low corner of the qs allocation box
-    int ntx, nty, ntz;
+    int ntx, nty, ntz, zg;
     double dtdL;          // dt / dx_D
     A4 srcq;              // primitive source terms on grow(slab, 3) (SRC instances only)
     double hdt;           // dt / 2
@@ -1107,7 +1164,7 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
     solve_face_r<M, D, NP, RS>(P, ql, qr, xl, xr, cl, cr, idx, F, ugd, pgd, FX);
     const long of = a.Fo.idx(i, j, k);
 #pragma unroll
-    for (int n = 0; n < 6; ++n) a.Fo.at(of, n) = F[n];
+    for (int n = 0; n < FX_EINT; ++n) a.Fo.at(of, n) = F[n];      // F(rho e) is not stored (SplitFluxTile)
     a.Fo.at(of, FX_UG) = ugd;
     a.Fo.at(of, FX_PG) = pgd;
 #pragma unroll
@@ -1124,7 +1181,8 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     CTU_PT_BEGIN
     // tile and thread coordinates
     const int bt = blockIdx.x;
-    const int bx = bt % a.ntx, r = bt / a.ntx, by = r % a.nty, bz = r / a.nty;
+    int bx, by, bz;
+    tile_order(bt, a.ntx, a.nty, a.ntz, a.zg, bx, by, bz);
     const int i0 = a.obx.lo[0] + bx * TT::SX, j0 = a.obx.lo[1] + by * TT::SY, k0 = a.obx.lo[2] + bz * TT::SZ;
     TraceCtx c;
     c.tx = threadIdx.x % TT::NX; c.ty = (threadIdx.x / TT::NX) % TT::NY; c.tz = threadIdx.x / (TT::NX * TT::NY);

@@ -53,8 +53,10 @@ int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3
     if (!attr) { int rc = set_smem(k_trans2_tma<N, NP, RS>, L::TOTAL); if (rc) return rc; attr = true; }
     CTU_MAP(m_qm, ta.qm[N], ibx, L::NIS, FaceTile, L::NIS)
     CTU_MAP(m_qp, ta.qp[N], ibx, L::NIS, FaceTile, L::NIS)
-    CTU_MAP(m_f1, F1[T1], ibx, L::NFX, L::F1T, L::NFX)
-    CTU_MAP(m_f2, F1[T2], ibx, L::NFX, L::F2T, L::NFX)
+    CTU_MAP(m_f1, F1[T1], ibx, L::NFX, L::F1T, L::S1::NA)         // components [0, FX_EINT) and [FX_UG, NFX): see SplitFluxTile
+    CTU_MAP(m_f1b, F1[T1], ibx, L::NFX, L::F1T, L::S1::NB)
+    CTU_MAP(m_f2, F1[T2], ibx, L::NFX, L::F2T, L::S2::NA)
+    CTU_MAP(m_f2b, F1[T2], ibx, L::NFX, L::F2T, L::S2::NB)
     CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
     Trans2Args a;
     a.qm = ta.qm[N]; a.qp = ta.qp[N];
@@ -76,11 +78,11 @@ int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3
         const unsigned ntiles = tg_blocks(tg);
         const unsigned grid = std::min<unsigned>(ntiles, (unsigned)num_sms() * TmaMinB<NP>::value);
         if (cudaMemsetAsync(P.replay_list, 0, sizeof(int), st) != cudaSuccess || cudaMemsetAsync(P.replay_list + 2, 0, sizeof(int), st) != cudaSuccess) return CTU_ERR_CUDA;   // list length and tile counter; the overflow flag [1] is sticky
-        k_trans2_persist<N, NP><<<grid, TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg, (int)ntiles);
-        k_trans2_replay<N, NP><<<REPLAY_GRID, TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg);
+        k_trans2_persist<N, NP><<<grid, TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f1b, m_f2, m_f2b, m_c, a, tg, (int)ntiles);
+        k_trans2_replay<N, NP><<<REPLAY_GRID, TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f1b, m_f2, m_f2b, m_c, a, tg);
         return 0;
     }
-    k_trans2_tma<N, NP, RS><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, a, tg);
+    k_trans2_tma<N, NP, RS><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f1b, m_f2, m_f2b, m_c, a, tg);
     return 0;
 }
 
@@ -118,6 +120,7 @@ int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, con
     a.ntx = (D == 0) ? (n[0] - 1 + TT::SX - 1) / TT::SX : (n[0] + TT::SX - 1) / TT::SX;
     a.nty = (D == 1) ? (n[1] - 1 + TT::SY - 1) / TT::SY : (n[1] + TT::SY - 1) / TT::SY;
     a.ntz = (D == 2) ? (n[2] - 1 + TT::SZ - 1) / TT::SZ : (n[2] + TT::SZ - 1) / TT::SZ;
+    a.zg = zgroup();
     a.dtdL = dt / P.dx[D];
     a.srcq = srcq; a.hdt = 0.5 * dt; a.src_mask = src_mask;
     k_trace_riemann_tma<D, NP, SRC, RS><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
@@ -148,8 +151,10 @@ int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3&
     if (!attr) { int rc = set_smem(k_final_tma<N, NP, RS>, L::TOTAL); if (rc) return rc; attr = true; }
     CTU_MAP(m_qm, ta.qm[N], ibx, L::NIS, FaceTile, L::NIS)
     CTU_MAP(m_qp, ta.qp[N], ibx, L::NIS, FaceTile, L::NIS)
-    CTU_MAP(m_f1, F2[T1][T2], ibx, L::NFX, L::F1T, L::NFX)
-    CTU_MAP(m_f2, F2[T2][T1], ibx, L::NFX, L::F2T, L::NFX)
+    CTU_MAP(m_f1, F2[T1][T2], ibx, L::NFX, L::F1T, L::S1::NA)
+    CTU_MAP(m_f1b, F2[T1][T2], ibx, L::NFX, L::F1T, L::S1::NB)
+    CTU_MAP(m_f2, F2[T2][T1], ibx, L::NFX, L::F2T, L::S2::NA)
+    CTU_MAP(m_f2b, F2[T2][T1], ibx, L::NFX, L::F2T, L::S2::NB)
     CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
     CTU_MAP(m_d, fd, ibx, 2, L::DT, 1)
     FinalArgs a;
@@ -158,7 +163,7 @@ int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3&
     for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
     a.c1 = hdtd[T1]; a.c2 = hdtd[T2];
     const TileGrid tg = make_tg(nb[N]);
-    k_final_tma<N, NP, RS><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f2, m_c, m_d, a, tg);
+    k_final_tma<N, NP, RS><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f1b, m_f2, m_f2b, m_c, m_d, a, tg);
     return 0;
 }
 template <int NP>
