@@ -161,6 +161,11 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (p->eos_kind == 1 && (p->transverse_use_eos || p->transverse_reset_rhoe || p->ppm_temp_fix || p->do_grav)) return CTU_ERR_UNSUPPORTED;
     if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
     if (g && g->dim != 0 && g->dim != 1 && g->dim != 3) return CTU_ERR_UNSUPPORTED;       // 2-D: not built
+    if (g) {      // "external boundaries meeting at a corner not supported" (Castro_bc_fill_nd.cpp:64-98): inflow faces in two directions
+        int ndir_inflow = 0;
+        for (int d = 0; d < 3; ++d) if (!g->periodic[d] && (g->lo_bc[d] == 1 || g->hi_bc[d] == 1)) ++ndir_inflow;
+        if (ndir_inflow > 1) return CTU_ERR_UNSUPPORTED;
+    }
     if (g && g->dim == 1) {
         // the 1-D Cartesian path (Castro_ctu_hydro.cpp:464-481): one zone in y and z; HLLC is refused in 1-D by the reference itself
         // (Castro.cpp:410-413); options that need transverse or source machinery are not instantiated for it
@@ -757,11 +762,9 @@ int fill_boundary_planes(const ctu_params_t* par, const ctu_geom_t* geom, const 
                          int ng, int zlo, int zhi, cudaStream_t st) {
     if (!par || !geom || !S) return CTU_ERR_BAD_ARG;
     if (!device_ok()) return CTU_ERR_NO_DEVICE;
-    for (int d = 0; d < 3; ++d) {
-        if (geom->periodic[d]) continue;
-        const int bcs[2] = {geom->lo_bc[d], geom->hi_bc[d]};
-        for (int b : bcs) if (b == 1) return CTU_ERR_UNSUPPORTED;   // inflow (ext_dir) needs a problem-specific fill
-    }
+    // An inflow boundary (code 1, ext_dir) is filled like an outflow one here, exactly as the reference's generic fill does before it
+    // calls the problem's problem_bc_fill (Castro_bc_fill_nd.cpp:24-37); the problem-specific values are the caller's (the reference's
+    // own FillPatch when this library sits behind Castro; the "hook:<lib>" boundary hook of the ctu_sim driver).
     const DevPar P = make_devpar(par, geom);
     const Box3 vbx = make_box(valid_lo, valid_hi);
     Box3 gbx = growd(vbx, ng, P.dim);

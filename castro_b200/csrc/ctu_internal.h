@@ -53,6 +53,16 @@ struct ctu_sim {
     size_t stage_doubles = 0;
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_upfree[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr}, ev_dnfree[2] = {nullptr, nullptr};
     bool upfree_rec[2] = {false, false}, dnfree_rec[2] = {false, false};
+    // problem_bc_fill of a "hook:<lib>" problem (ctu_sim_init_problem keeps the library loaded when it exports one): run on the host on
+    // the out-of-domain ghost slabs after the generic fill of every (sub)step, at the time of the old state (fill_time)
+    void* bc_lib = nullptr;
+    int (*bc_fill)(double, const ctu_geom_t*, const int*, const int*, double*, const int*, const int*) = nullptr;
+    double fill_time = 0.0;
+    double* bc_host = nullptr;          // pinned staging: slab before the hook, slab after it
+    double* bc_dev = nullptr;
+    unsigned char* bc_mask_host = nullptr;
+    unsigned char* bc_mask_dev = nullptr;
+    size_t bc_cap = 0;                  // capacity in doubles of one slab copy
     ctu_fab_t fab(int which) const {
         ctu_fab_t f;
         f.p = buf[which];

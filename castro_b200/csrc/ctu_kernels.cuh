@@ -1363,7 +1363,7 @@ static __global__ void __launch_bounds__(TPB) k_fill(const DevPar P, const A4 S,
             if (outside && !P.periodic[d]) {
                 const bool lo_side = g < P.domlo[d];
                 const int bc = lo_side ? P.lo_bc[d] : P.hi_bc[d];
-                if (bc == 2) src[d] = lo_side ? P.domlo[d] : P.domhi[d];
+                if (bc == 2 || bc == 1) src[d] = lo_side ? P.domlo[d] : P.domhi[d];     // outflow; inflow = foextrap + the caller's problem_bc_fill
                 else if (bc >= 3 && bc <= 5) { src[d] = lo_side ? 2 * P.domlo[d] - g - 1 : 2 * P.domhi[d] - g + 1; flip[d] = true; }
                 else return;
                 any = true;

@@ -896,6 +896,11 @@ void ctu_sim_destroy(ctu_sim_t* s) {
     if (s->d_dt2) cudaFree(s->d_dt2);
     for (int d = 0; d < 3; ++d) if (s->mflux[d]) cudaFree(s->mflux[d]);
     if (s->ws) ctu_workspace_destroy(s->ws);
+    if (s->bc_host) cudaFreeHost(s->bc_host);
+    if (s->bc_dev) cudaFree(s->bc_dev);
+    if (s->bc_mask_host) cudaFreeHost(s->bc_mask_host);
+    if (s->bc_mask_dev) cudaFree(s->bc_mask_dev);
+    if (s->bc_lib) dlclose(s->bc_lib);
     delete s;
 }
 
@@ -933,9 +938,31 @@ int ctu_sim_download(ctu_sim_t* s, double* host) { return sim_xfer(s, host, true
 int ctu_sim_upload(ctu_sim_t* s, const double* host) { return sim_xfer(s, const_cast<double*>(host), false); }
 
 int ctu_sim_init_problem(ctu_sim_t* s, const char* problem, const char* prob_params) {
-    if (!s) return CTU_ERR_BAD_ARG;
+    if (!s || !problem) return CTU_ERR_BAD_ARG;
     ctu_fab_t f = s->fab(s->cur);
-    return ctu_problem_init(problem, prob_params, &s->par, &s->geom, s->vbx.lo, s->vbx.hi, &f, s->st);
+    // a hook library stays loaded for the life of the sim when it carries the problem's problem_bc_fill: the hook reads the problem
+    // parameters, EOS constants and geometry that ctu_hook_init leaves in the library's statics
+    void* lib = nullptr;
+    if (std::strncmp(problem, "hook:", 5) == 0) lib = dlopen(problem + 5, RTLD_NOW | RTLD_LOCAL);
+    const int rc = ctu_problem_init(problem, prob_params, &s->par, &s->geom, s->vbx.lo, s->vbx.hi, &f, s->st);
+    if (s->bc_lib) { dlclose(s->bc_lib); s->bc_lib = nullptr; s->bc_fill = nullptr; }
+    if (lib) {
+        typedef int (*HasFn)(void);
+        HasFn has = (HasFn)dlsym(lib, "ctu_hook_has_bc_fill");
+        if (!rc && has && has()) {
+            s->bc_lib = lib;
+            s->bc_fill = (int (*)(double, const ctu_geom_t*, const int*, const int*, double*, const int*, const int*))dlsym(lib, "ctu_hook_bc_fill");
+        } else {
+            dlclose(lib);
+        }
+    }
+    return rc;
+}
+
+int ctu_sim_set_time(ctu_sim_t* s, double time) {
+    if (!s) return CTU_ERR_BAD_ARG;
+    s->fill_time = time;
+    return 0;
 }
 
 // The reference cleans the state twice before the hydro: clean_state(S_old) on the valid zones (Castro::initialize_advance,
@@ -954,11 +981,98 @@ int ctu_sim_step_pre(ctu_sim_t* s) {
 }
 
 // Castro::initialize_do_advance: FillPatch (local part: periodic self-wrap + physical boundaries)
+}  // extern "C"
+
+namespace {
+// clean_state on the zones of a box that a mask selects (the ghost zones a problem_bc_fill hook has rewritten)
+template <int EK>
+static __global__ void __launch_bounds__(TPB) k_clean_masked(const DevPar P, const A4 S, const LaunchBox lb, const unsigned char* __restrict__ mask) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    if (!mask[blockIdx.x * blockDim.x + threadIdx.x]) return;
+    const long o = S.idx(i, j, k);
+    double u[7];
+#pragma unroll
+    for (int n = 0; n < 7; ++n) u[n] = S.at(o, n);
+    clean_zone<EK>(P, u, S, o);
+#pragma unroll
+    for (int n = 0; n < 7; ++n) S.at(o, n) = u[n];
+}
+
+// The problem's boundary hook (Source/problems/Castro_bc_fill_nd.cpp:103-122: problem_bc_fill after the generic fill, in which an
+// inflow boundary has been filled like an outflow one).  The reference calls it for every zone of the fill box; here it is given the
+// ghost zones outside the domain across every non-periodic boundary this box touches (disjoint slabs: x sides over the full y-z
+// extent, y sides over the in-domain x range, z sides over the in-domain x-y range), on the host, like the initial-data hook: host
+// libm is what makes the result bit-identical to the reference's CPU executable.  Zones the hook changed then see the one clean_state
+// pass that the reference's clean_state(Sborder, NUM_GROW) gives them (Castro_advance.cpp:170).
+int sim_bc_hook(ctu_sim_t* s) {
+    const ctu_geom_t& g = s->geom;
+    ctu_fab_t f = s->fab(s->cur);
+    const DevPar P = make_devpar(&s->par, &s->geom);
+    const A4 a = make_a4(f);
+    for (int d = 0; d < 3; ++d) {
+        if (g.periodic[d]) continue;
+        for (int side = 0; side < 2; ++side) {
+            Box3 b = s->gbx;
+            for (int e = 0; e < d; ++e) if (!g.periodic[e]) { b.lo[e] = std::max(b.lo[e], g.domlo[e]); b.hi[e] = std::min(b.hi[e], g.domhi[e]); }
+            if (side == 0) b.hi[d] = std::min(b.hi[d], g.domlo[d] - 1); else b.lo[d] = std::max(b.lo[d], g.domhi[d] + 1);
+            if (!b.ok()) continue;
+            const size_t nz = (size_t)b.npts(), n = nz * s->nstate;
+            if (n > s->bc_cap) {
+                if (s->bc_host) cudaFreeHost(s->bc_host);
+                if (s->bc_dev) cudaFree(s->bc_dev);
+                if (s->bc_mask_host) cudaFreeHost(s->bc_mask_host);
+                if (s->bc_mask_dev) cudaFree(s->bc_mask_dev);
+                s->bc_host = nullptr; s->bc_dev = nullptr; s->bc_mask_host = nullptr; s->bc_mask_dev = nullptr; s->bc_cap = 0;
+                CUDA_TRY(cudaMallocHost(&s->bc_host, 2 * n * sizeof(double)));
+                CUDA_TRY(cudaMalloc(&s->bc_dev, n * sizeof(double)));
+                CUDA_TRY(cudaMallocHost(&s->bc_mask_host, nz));
+                CUDA_TRY(cudaMalloc(&s->bc_mask_dev, nz));
+                s->bc_cap = n;
+            }
+            double* before = s->bc_host;
+            double* after = s->bc_host + n;
+            int rc = ctu_halo_pack(&f, b.lo, b.hi, s->bc_dev, s->st);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(before, s->bc_dev, n * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+            CUDA_TRY(cudaStreamSynchronize(s->st));
+            std::memcpy(after, before, n * sizeof(double));
+            rc = s->bc_fill(s->fill_time, &s->geom, b.lo, b.hi, after, b.lo, b.hi);
+            if (rc) return rc;
+            bool any = false;
+            for (size_t z = 0; z < nz; ++z) {
+                bool ch = false;
+                for (int c = 0; c < s->nstate && !ch; ++c) ch = std::memcmp(&before[c * nz + z], &after[c * nz + z], sizeof(double)) != 0;
+                s->bc_mask_host[z] = ch ? 1 : 0;
+                any |= ch;
+            }
+            if (!any) continue;
+            CUDA_TRY(cudaMemcpyAsync(s->bc_dev, after, n * sizeof(double), cudaMemcpyHostToDevice, s->st));
+            CUDA_TRY(cudaMemcpyAsync(s->bc_mask_dev, s->bc_mask_host, nz, cudaMemcpyHostToDevice, s->st));
+            rc = ctu_halo_unpack(&f, b.lo, b.hi, s->bc_dev, s->st);
+            if (rc) return rc;
+            const LaunchBox lb = make_lb(b);
+            if (P.eos_kind == 1) k_clean_masked<1><<<nblk(lb.n), TPB, 0, s->st>>>(P, a, lb, s->bc_mask_dev);
+            else k_clean_masked<0><<<nblk(lb.n), TPB, 0, s->st>>>(P, a, lb, s->bc_mask_dev);
+            s->launches += 3;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(s->st));       // the staging buffers are reused by the next slab
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
 int ctu_sim_step_fill(ctu_sim_t* s) {
     if (!s) return CTU_ERR_BAD_ARG;
     ctu_fab_t f = s->fab(s->cur);
     s->launches += 2;
-    return ctu_fill_boundary(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &f, CTU_NGROW, s->st);
+    int rc = ctu_fill_boundary(&s->par, &s->geom, s->vbx.lo, s->vbx.hi, &f, CTU_NGROW, s->st);
+    if (!rc && s->bc_fill) rc = sim_bc_hook(s);
+    return rc;
 }
 
 // the same step with gravitational source terms around the hydro (Castro::do_advance_ctu, Castro_advance_ctu.cpp:60-130):
@@ -1097,6 +1211,7 @@ static int host_upload_planes(ctu_sim_t* s, const double* host, int b, int k0, i
 }  // extern "C"
 
 int ctu::sim_step_host_impl(ctu_sim* s, SimHooks* hooks, const double* host_in, double* host_out, double dt, double dt_est[2], int n_bad[2]) {
+    if (s && s->bc_fill) return CTU_ERR_UNSUPPORTED;      // the boundary hook runs on whole ghost slabs of the resident state (ctu_sim_step_fill)
     if (!s || !host_in || !host_out) return CTU_ERR_BAD_ARG;
     if (!hooks)      // a single box must be the whole domain; with hooks the other boxes' zones arrive through the exchanges
         for (int d = 0; d < 3; ++d)
@@ -1264,6 +1379,7 @@ int ctu::sim_advance_impl(ctu_sim* s, SimHooks* hooks, int nsteps, double stop_t
                 s->launches += 1;
                 rc = ctu_clean_state(&s->par, s->vbx.lo, s->vbx.hi, &f, sub_iteration == 0 ? 2 : 1, s->st);
                 if (hooks) { const int r = hooks->exchange(s); if (!rc) rc = r; }
+                s->fill_time = subcycle_time;           // FillPatch at the old time of the (sub)step (Castro_advance.cpp:167)
                 if (!rc) rc = ctu_sim_step_fill(s);
                 prepared = true;
             }

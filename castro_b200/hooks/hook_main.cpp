@@ -13,11 +13,24 @@
 #include <problem_initialize.H>
 #include <problem_initialize_state_data.H>
 #include "prob_parameters_set.H"
+// the problem's boundary hook, if it has one (Source/problems/Castro_bc_fill_nd.cpp:5,122 calls it for every zone of the fill box)
+#if defined(__has_include)
+#if __has_include(<problem_bc_fill.H>)
+#include "Castro_util.H"
+#include <problem_bc_fill.H>
+#define CTU_HOOK_HAS_BC_FILL 1
+#endif
+#endif
 
 #include "castro_ctu.h"
 
 extern "C" __attribute__((visibility("default"))) int ctu_hook_num_state(void) { return NUM_STATE; }
 extern "C" __attribute__((visibility("default"))) size_t ctu_hook_sizeof_params(void) { return sizeof(ctu_params_t); }
+#ifdef CTU_HOOK_HAS_BC_FILL
+extern "C" __attribute__((visibility("default"))) int ctu_hook_has_bc_fill(void) { return 1; }
+#else
+extern "C" __attribute__((visibility("default"))) int ctu_hook_has_bc_fill(void) { return 0; }
+#endif
 
 extern "C" __attribute__((visibility("default"))) int ctu_hook_init(const char* prob_params, const ctu_params_t* par, const ctu_geom_t* g, const int lo[3], const int hi[3],
                              double* host_state, const int slo[3], const int shi[3])
@@ -72,4 +85,45 @@ extern "C" __attribute__((visibility("default"))) int ctu_hook_init(const char* 
             for (int i = lo[0]; i <= hi[0]; ++i)
                 problem_initialize_state_data(i, j, k, state, geomdata);
     return 0;
+}
+
+// ctu_hook_bc_fill: problem_bc_fill(i, j, k, state, time, bcs, geomdata) for every zone of [lo, hi] of a host copy of the ghosted state
+// (call site in the reference: ca_statefill, Source/problems/Castro_bc_fill_nd.cpp:103-122, after the generic fill in which inflow
+// boundaries are filled like outflow ones).  Returns CTU_ERR_UNSUPPORTED when the problem directory has no problem_bc_fill.H.
+// Must follow a ctu_hook_init of the same library (problem parameters, EOS constants, geometry).
+extern "C" __attribute__((visibility("default"))) int ctu_hook_bc_fill(double time, const ctu_geom_t* g, const int lo[3], const int hi[3],
+                                                                       double* host_state, const int slo[3], const int shi[3])
+{
+#ifdef CTU_HOOK_HAS_BC_FILL
+    if (!g || !host_state) return CTU_ERR_BAD_ARG;
+    Array4<Real> state;
+    state.p = host_state;
+    state.lox = slo[0]; state.loy = slo[1]; state.loz = slo[2];
+    state.jstride = shi[0] - slo[0] + 1;
+    state.kstride = state.jstride * (long)(shi[1] - slo[1] + 1);
+    state.nstride = state.kstride * (long)(shi[2] - slo[2] + 1);
+    state.ncomp = NUM_STATE;
+    // BCRec of every state component (Castro_setup.cpp:36-61: physical code -> mathematical type; momenta are odd across symmetry planes)
+    static const int scalar_bc[6] = {BCType::int_dir, BCType::ext_dir, BCType::foextrap, BCType::reflect_even, BCType::reflect_even, BCType::reflect_even};
+    static const int norm_vel_bc[6] = {BCType::int_dir, BCType::ext_dir, BCType::foextrap, BCType::reflect_odd, BCType::reflect_odd, BCType::reflect_odd};
+    static const int tang_vel_bc[6] = {BCType::int_dir, BCType::ext_dir, BCType::foextrap, BCType::reflect_even, BCType::reflect_even, BCType::reflect_even};
+    Array1D<BCRec, 0, NUM_STATE - 1> bcs;
+    for (int n = 0; n < NUM_STATE; ++n) {
+        for (int d = 0; d < 3; ++d) {
+            const int* tab = (n >= UMX && n <= UMZ) ? ((n - UMX == d) ? norm_vel_bc : tang_vel_bc) : scalar_bc;
+            bcs(n).bc[d] = tab[g->lo_bc[d]];
+            bcs(n).bc[3 + d] = tab[g->hi_bc[d]];
+        }
+    }
+    const GeometryData geomdata = amrex::ctu_hook_default_geometry();
+#pragma omp parallel for collapse(2)
+    for (int k = lo[2]; k <= hi[2]; ++k)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int i = lo[0]; i <= hi[0]; ++i)
+                problem_bc_fill(i, j, k, state, time, bcs, geomdata);
+    return 0;
+#else
+    (void)time; (void)g; (void)lo; (void)hi; (void)host_state; (void)slo; (void)shi;
+    return CTU_ERR_UNSUPPORTED;
+#endif
 }

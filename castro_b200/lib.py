@@ -61,6 +61,7 @@ def lib():
         L.ctu_sim_download.argtypes = [C.c_void_p, C.c_void_p]
         L.ctu_sim_upload.argtypes = [C.c_void_p, C.c_void_p]
         L.ctu_sim_init_problem.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.ctu_sim_set_time.argtypes = [C.c_void_p, C.c_double]
         L.ctu_sim_write_plotfile.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_int]
         L.ctu_sim_step_hydro.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ctu_sim_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]

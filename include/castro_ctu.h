@@ -251,6 +251,12 @@ int  ctu_sim_retries(const ctu_sim_t* sim);                /* advances rejected 
 int  ctu_sim_download(ctu_sim_t* sim, double* host);
 int  ctu_sim_upload(ctu_sim_t* sim, const double* host);
 int  ctu_sim_init_problem(ctu_sim_t* sim, const char* problem, const char* prob_params);
+/* Boundary hook.  When `problem` is "hook:<lib>" and the reference's problem directory has a problem_bc_fill.H, the library stays
+ * loaded and the step's ghost fill ends like the reference's ca_statefill (Source/problems/Castro_bc_fill_nd.cpp:103-122): generic
+ * fill (an inflow face, bc code 1, is filled like an outflow face, :24-37), then problem_bc_fill on the ghost zones outside the
+ * domain at the old time of the (sub)step, then clean_state on the zones it changed.  ctu_sim_advance keeps that time itself; a
+ * caller that drives the three phases below sets it with ctu_sim_set_time before ctu_sim_step_fill. */
+int  ctu_sim_set_time(ctu_sim_t* sim, double time);
 /* One step in three phases, so that a multi-rank caller can put its halo exchange and allreduce between them:
  *   pre  : clean_state(S_old) [Castro::initialize_advance, Castro_advance.cpp:487] AND the clean_state(Sborder) of
  *          initialize_do_advance (Castro_advance.cpp:170) on the valid zones, in one pass (clean_state is pointwise and

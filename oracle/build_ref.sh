@@ -21,6 +21,7 @@
 #                                        The reference's RT initial-data header does not compile with DIM=3 (an unqualified `L_x`,
 #                                        problem_initialize_state_data.H:50); the recipe qualifies that one identifier in the SCRATCH COPY of
 #                                        the problem directory.  No file of the hot path (Source/hydro, Source/driver, Source/gravity) is touched.
+#   oracle/_ref/Castro3d_noh.ex          (`noh`) Noh implosion problem, serial (golden generator for problem_bc_fill / inflow boundaries)
 #   oracle/_ref/fcompare.ex              AMReX plotfile comparator (DIM=3)
 #   oracle/_ref/Castro3d_sedov_cuda.ex   (`gpu`)  the UNMODIFIED reference built with its own GPU back end (USE_CUDA=TRUE CUDA_ARCH=100):
 #                                        Castro's stock unfused ParallelFor pipeline on the same B200 -- the "reference_gpu" baseline
@@ -61,6 +62,8 @@ if [ "$what" = sodstellar ]; then build Sod_stellar Castro3d_sodstellar DIM=3 US
 # the literal BASELINE config[0]: Sod in ONE dimension (DIM=1), golden generator for the 1-D path
 if [ "$what" = sod1d ]; then build Sod Castro1d_sod DIM=1; fi
 if [ "$what" = all ] || [ "$what" = sod ];    then build Sod Castro3d_sod DIM=3; fi
+# Noh implosion: the one hydro test whose outer ghost zones come from problem_bc_fill (time-dependent inflow); golden generator for the bc hook
+if [ "$what" = noh ]; then build Noh Castro3d_noh DIM=3; fi
 if [ "$what" = all ] || [ "$what" = rt ]; then
   if [ ! -d "$W/Castro3d_rt" ]; then cp -r "$REF/Exec/hydro_tests/RT" "$W/Castro3d_rt"; fi
   sed -i 's/0.5e0_rt \* L_x/0.5e0_rt * problem::L_x/' "$W/Castro3d_rt/problem_initialize_state_data.H"

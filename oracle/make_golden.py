@@ -183,6 +183,17 @@ SOD1D_CASES = {
 }
 
 
+# Noh implosion (Exec/hydro_tests/Noh/inputs_3d: symmetry planes at the low faces, CGF): the outer ghost zones are set by the problem's
+# problem_bc_fill (time-dependent analytic inflow) after the generic fill -- as shipped over outflow faces, and over inflow (ext_dir) faces
+NOH_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_noh.ex")
+NOH_INPUTS = "/root/reference/Exec/hydro_tests/Noh/inputs_3d"
+NOH_CASES = {
+    "noh16_cgf": (16, 30, [0, 1, 30], ["amr.plot_per=-1", "amr.check_per=-1"]),
+    "noh16_hllc_inflow": ((16, 24, 8), 30, [0, 30], ["amr.plot_per=-1", "amr.check_per=-1", "castro.riemann_solver=2", "castro.hi_bc=1 2 2",
+                                                    "geometry.prob_hi=1.0 1.5 0.5"]),
+}
+
+
 def run_case_1d(name, inp, nx, max_step, snaps, extra):
     wd = tempfile.mkdtemp(prefix="golden_")
     try:
@@ -228,6 +239,10 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case(name, n, ms, snaps, extra, exe=RT_EXE, inputs=RT_INPUTS, ncomp=8)
+    for name, (n, ms, snaps, extra) in NOH_CASES.items():
+        if only and name not in only:
+            continue
+        run_case(name, n, ms, snaps, extra, exe=NOH_EXE, inputs=NOH_INPUTS)
     for name, (inp, nx, ms, snaps, extra) in SOD1D_CASES.items():
         if only and name not in only:
             continue

@@ -207,3 +207,26 @@ def load_sod1d_case(name):
     prob = dict(c["prob"], idir=1, frac=0.5)
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
     return par, geom, prob, g, snaps
+
+
+NOH_CASES = {
+    "noh16_cgf": dict(solver=0, hi_bc=(2, 2, 2)),                 # as shipped: outflow faces, overwritten by problem_bc_fill
+    "noh16_hllc_inflow": dict(solver=2, hi_bc=(1, 2, 2)),         # an inflow (ext_dir) face: filled like outflow, then problem_bc_fill
+}
+
+
+def load_noh_case(name):
+    """Exec/hydro_tests/Noh/inputs_3d: uniform gas imploding at |v| = 1 onto the origin, symmetry planes at the low faces, gamma = 5/3,
+    cfl 0.5, init_shrink 0.1, change_max 1.1; the outer ghost zones hold the analytic inflow at the current time (problem_bc_fill.H).
+    Goldens from the reference's Noh executable (oracle/make_golden.py NOH_CASES); the problem runs through the hook library only."""
+    c = NOH_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    par = abi.default_params()
+    par.riemann_solver = c["solver"]
+    par.cfl, par.init_shrink, par.change_max = 0.5, 0.1, 1.1
+    par.small_dens, par.small_temp = 1.0e-6, 1.0e-16
+    par.eos_gamma, par.eos_assume_neutral = 1.6666666666666666666666666, 0
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), lo_bc=(3, 3, 3), hi_bc=c["hi_bc"])
+    snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
+    return par, geom, {}, g, snaps

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from castro_b200 import abi
-from cases import GOLDEN, load_case, load_kh_case, load_sod_case
+from cases import GOLDEN, NOH_CASES, load_case, load_kh_case, load_noh_case, load_sod_case
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOOKS = os.path.join(ROOT, "castro_b200", "hooks")
@@ -100,3 +100,73 @@ def test_problem_init_through_hook_on_gpu(hook, builtin, golden, kind):
     assert np.array_equal(Ua, Ub)
     a.close()
     b.close()
+
+
+# ---- the boundary hook: Exec/hydro_tests/Noh (initial data AND outer ghost zones come from the reference's unmodified headers) --------
+HOOK_ARGS = [C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.Geom), abi.Int3, abi.Int3, C.c_void_p, abi.Int3, abi.Int3]
+BC_ARGS = [C.c_double, C.POINTER(abi.Geom), abi.Int3, abi.Int3, C.c_void_p, abi.Int3, abi.Int3]
+
+
+@pytest.mark.parametrize("name", sorted(NOH_CASES))
+def test_oracle_with_reference_bc_hook_matches_noh_golden(name):
+    """CPU: the oracle's time loop with problem_bc_fill (the reference's header behind ctu_hook_bc_fill) after every ghost fill lands
+    bit for bit on the reference executable's Noh run, dt history included"""
+    import oracle_lib as O
+    par, geom, prob, g, snaps = load_noh_case(name)
+    O.params_finalize(par)
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    L = C.CDLL(hook_path("noh"))
+    assert L.ctu_hook_has_bc_fill() == 1
+    assert C.CDLL(hook_path("sedov")).ctu_hook_has_bc_fill() == 0
+    L.ctu_hook_init.argtypes = HOOK_ARGS
+    U0 = np.full((par.num_state, n_cell[2], n_cell[1], n_cell[0]), np.nan)
+    lo, hi = abi.Int3(0, 0, 0), abi.Int3(*[n - 1 for n in n_cell])
+    assert L.ctu_hook_init(b"", C.byref(par), C.byref(geom), lo, hi, U0.ctypes.data, lo, hi) == 0
+    f = O.fab(U0, (0, 0, 0))
+    O.lib().orc_init_tail(C.byref(par), C.byref(geom), lo, hi, C.byref(f))
+    assert np.array_equal(U0, g["U0"])
+    ng = 4
+    U = np.zeros((U0.shape[0],) + tuple(n + 2 * ng for n in U0.shape[1:]))
+    U[:, ng:-ng, ng:-ng, ng:-ng] = U0
+    O.lib().orc_set_bc_hook(C.cast(L.ctu_hook_bc_fill, C.c_void_p))
+    try:
+        t, dt, step, times = 0.0, -1.0, 0, [0.0]
+        for s in snaps[1:]:
+            st, t, dt, hist = O.run(par, geom, U, s - step, time=t, dt=dt)
+            assert st == 0
+            times += list(times[-1] + np.cumsum(hist))
+            step = s
+            assert np.array_equal(U[:, ng:-ng, ng:-ng, ng:-ng], g["U%d" % s]), "%s step %d" % (name, s)
+    finally:
+        O.lib().orc_set_bc_hook(None)
+    np.testing.assert_allclose(np.array(times), g["times"][:len(times)], rtol=1e-14, atol=0)
+    # without the hook the run is a different one (the test above is not vacuous)
+    V = np.zeros_like(U)
+    V[:, ng:-ng, ng:-ng, ng:-ng] = U0
+    O.run(par, geom, V, snaps[-1])
+    assert not np.array_equal(V[:, ng:-ng, ng:-ng, ng:-ng], g["U%d" % snaps[-1]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(NOH_CASES))
+def test_noh_with_bc_hook_on_gpu(name):
+    """ctu_sim_init_problem("hook:<noh>") keeps the library's problem_bc_fill; ctu_sim_advance must then reproduce the reference's
+    Noh run bit for bit (inflow face = outflow fill + hook; hook-written ghost zones cleaned once)"""
+    import torch
+    assert torch.cuda.is_available()
+    from castro_b200 import lib
+    par, geom, prob, g, snaps = load_noh_case(name)
+    lib.params_finalize(par)
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    sim = lib.Sim(par, geom, (0, 0, 0), tuple(n - 1 for n in n_cell))
+    sim.init_problem("hook:" + hook_path("noh"), prob)
+    assert np.array_equal(sim.download(), g["U0"])
+    t, dt, step, times = 0.0, -1.0, 0, [0.0]
+    for s in snaps[1:]:
+        st, t, dt, hist = sim.advance(s - step, time=t, dt=dt)
+        assert st == 0
+        times += list(times[-1] + np.cumsum(hist))
+        step = s
+        assert np.array_equal(sim.download(), g["U%d" % s]), "%s step %d" % (name, s)
+    np.testing.assert_allclose(np.array(times), g["times"][:len(times)], rtol=1e-14, atol=0)
+    sim.close()

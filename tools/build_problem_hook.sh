@@ -9,7 +9,8 @@ here="$(cd "$(dirname "$0")/.." && pwd)"
 hooks="$here/castro_b200/hooks"
 gen="/tmp/ctu_hook_gen_$name"; mkdir -p "$gen"
 common="$(cd "$dir/../../.." && pwd)/Source/problems/_prob_params"
-tables=("$dir/_prob_params"); [ -f "$common" ] && tables+=("$common")
+tables=(); [ -f "$dir/_prob_params" ] && tables+=("$dir/_prob_params")      # a problem without parameters of its own (Noh) has none
+[ -f "$common" ] && tables+=("$common")
 python "$hooks/gen_prob_params.py" "$gen" "${tables[@]}"
 # -ffp-contract=off, no fast-math: the reference's CPU build contains no FMA (generic x86-64), and the initial data must match it bit for bit
 g++ -O2 -std=c++17 -fPIC -shared -fopenmp -fno-gnu-unique -fvisibility=hidden -ffp-contract=off -DAMREX_SPACEDIM=3 -DCTU_HOOK_NUMSPEC=$nspec -DCTU_HOOK_NUMADV=$nadv -DCTU_HOOK_NUMAUX=$naux \
