@@ -320,6 +320,9 @@ def gpu_arm(args):
         par.do_grav, par.grav_source_type, par.const_grav = 1, 4, -1.0
         geom_kw = dict(periodic=(1, 1, 0), lo_bc=(0, 0, 4), hi_bc=(0, 0, 4))
         prob = dict(frac=0.5, rho_1=1.0, rho_2=2.0, p0_base=5.0)
+    for kv in args.par:          # developer option: any castro.* field of ctu_params_t, e.g. --par ppm_type=0 --par use_pslope=1
+        k, v = kv.split("=", 1)
+        setattr(par, k, type(getattr(par, k))(float(v)))
     lib.params_finalize(par)
     # weak scaling: dx = 1/n whatever the process grid; strong scaling: the unit cube
     geom = abi.make_geom(n_cell, probhi=(1.0, 1.0, 1.0) if strong else tuple(float(d) for d in dims), **geom_kw)
@@ -549,6 +552,7 @@ def main():
     ap.add_argument("--problem", default="sedov", choices=["sedov", "kh", "rt"],
                     help="developer option: kh = Kelvin-Helmholtz as shipped (advected scalar + species, periodic), rt = Rayleigh-Taylor with "
                          "constant gravity (cube of n^3 zones); the benchmark configuration is sedov")
+    ap.add_argument("--par", action="append", default=[], help="developer option: override a ctu_params_t field (name=value), repeatable")
     ap.add_argument("--nspec", type=int, default=1, help="developer option: species in the network (default 1 = gammalaw.net, the benchmark)")
     ap.add_argument("--profile-mode", action="store_true", help="allow warmup < 3 (ncu runs only; never a bench value)")
     args = ap.parse_args()

@@ -37,6 +37,7 @@ struct ctu_workspace {
     int last_slab_planes = 0;
     long replays_total = 0;                  // tiles replayed with the exact operators since creation (diagnostic)
     int last_num_slabs = 0;
+    int last_tile_staged = 0;        // the last advance ran the tile-staged (TMA) kernel family
     int kernel_launches = 0;
     // optional per-stage device timing (CUDA events on the launching stream)
     bool profiling = false;
@@ -262,8 +263,8 @@ bool tma_ok(const DevPar& P) {
     if (disabled || !P.gamc_const || P.dim != 3) return false;
     if (P.npassive < 1 || P.npassive > CTU_TMA_MAX_NP) return false;
     if (P.ppm_temp_fix) return false;        // EOS re-sync of the interface states before each solve: register-staged family
-    if (P.use_pslope || P.ppm_well_balanced) return false;   // hydrostatic-pressure-aware reconstruction: register-staged family
-    if (P.ppm_type == 0) return false;       // piecewise-linear reconstruction: register-staged family
+    // piecewise-linear and hydrostatic-pressure-aware reconstructions: their own instantiations of the trace kernel (ctu_rec.cu)
+    if (trace_rec(P) && (P.npassive > CTU_TMA_REC_MAX_NP || P.riemann_solver == 1)) return false;
     if (P.riemann_solver == 1 && P.npassive > CTU_TMA_CG_MAX_NP) return false;   // Colella & Glaz: tile kernels instantiated for 1-2 passives
     if (P.limit_fluxes_on_small_dens) return false;     // ditto the density-floor flux limiter
     if (P.hybrid_riemann) return false;      // the HLL blend lives in the register-staged family only (keeps the tile kernels lean)
@@ -357,6 +358,7 @@ void ctu_workspace_destroy(ctu_workspace_t* w) {
 
 size_t ctu_workspace_bytes(const ctu_workspace_t* w) { return w ? w->arena_bytes : 0; }
 int ctu_workspace_last_slabs(const ctu_workspace_t* w) { return w ? w->last_num_slabs : 0; }
+int ctu_workspace_last_tile_staged(const ctu_workspace_t* w) { return w ? w->last_tile_staged : 0; }
 long ctu_workspace_replays(const ctu_workspace_t* w) { return w ? w->replays_total : 0; }
 int ctu_workspace_launches(const ctu_workspace_t* w) { return w ? w->kernel_launches : 0; }
 
@@ -458,6 +460,7 @@ HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     r->plane_q = (size_t)(nxg + 8 + r->qpad) * (nyg + 8) * (r->NQS + (r->have_src ? NSRCQ : 0)) * sizeof(double);
     r->plane_i = (size_t)(nxg + 3 + r->ipad) * (nyg + 4) * (size_t)((P.hybrid_riemann ? 3 : 2) + 6 * r->NIS + 9 * r->NFX) * sizeof(double);
     r->use_tma = tma_ok(P);
+    ws->last_tile_staged = r->use_tma ? 1 : 0;
     const double* dx = geom->dx;
     for (int d = 0; d < 3; ++d) { r->hdtd[d] = 0.5 * dt / dx[d]; r->cdtd[d] = dt / dx[d] / 3.0; }
     r->Sb = make_a4(*Sborder); r->Sn = make_a4(*S_new);

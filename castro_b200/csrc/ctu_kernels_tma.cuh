@@ -931,11 +931,16 @@ struct TraceRiemannArgs {
 // ctu_kernels.cuh with the primitive stencil in shared memory and the results left in registers.
 //   base: &tile(zone, comp 0);  sn: component stride;  st: stride along DIR.   op/om: plus state on the low face, minus
 //   state on the high face (rho u v w p rhoe), xp/xm the passives.
-template <class M, int DIR, int NP, bool SRC>
+//   REC = 2: the hydrostatic-pressure-aware reconstructions (castro.use_pslope / castro.ppm_well_balanced; ppm_reconstruct_pslope,
+//   ppm.H:171-244 + trace_ppm.cpp:248-267,490): sb = &srcq(zone, comp 0) with strides ssn / sst (nullptr without sources).
+template <class M, int DIR, int NP, bool SRC, int REC = 0>
 __device__ __forceinline__ void trace_core(const DevPar& P, const double* __restrict__ base, const int sn, const int st, const double flat,
                                            const double dtdL, double* __restrict__ op, double* __restrict__ om, double* __restrict__ xp,
-                                           double* __restrict__ xm, const SrcAdd& sa) {
+                                           double* __restrict__ xm, const SrcAdd& sa, const double* __restrict__ sb = nullptr,
+                                           const long ssn = 0, const long sst = 0) {
 #define SA(x) (SRC ? sa.x : 0.0)
+// velocity-source terms: fac * hdt * I_src with fac = 0 in hydrostatic zones of the well-balanced method (trace_ppm.cpp:490)
+#define SAU(x) (SRC ? ((REC == 2 && wb_hse) ? 0.0 * sa.x : sa.x) : 0.0)
     constexpr int QUN = QS_U + DIR;
     constexpr int QUT = QS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
     constexpr int QUTT = QS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
@@ -963,7 +968,43 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
     pb.integ(un - cc, dtdL, Ip_un0, Im_un0);
     pb.integ(un + cc, dtdL, Ip_un2, Im_un2);
     double Ip_p0, Im_p0, Ip_p1, Im_p1, Ip_p2, Im_p2;
-    CTU_RECON(QS_P);
+    double p_m_hse = 0.0, p_p_hse = 0.0;      // HSE pressure on the interfaces (castro.ppm_well_balanced)
+    bool wb_hse = false;
+    if (REC == 2 && (P.use_pslope || P.ppm_well_balanced)) {
+        // limit the pressure with the hydrostatic part removed; g is the primitive source of the normal velocity (zero without sources)
+        const double* __restrict__ a = base + QS_P * sn;
+        const double* __restrict__ r = base + QS_RHO * sn;
+        const double dL = P.dx[DIR];
+        double src[5], pz[5], rz[5];
+#pragma unroll
+        for (int m = -2; m <= 2; ++m) {
+            src[m + 2] = (SRC && sb) ? sb[QUN * ssn + m * sst] : 0.0;
+            pz[m + 2] = a[m * st];
+            rz[m + 2] = r[m * st];
+        }
+        const double p0_hse = pz[2];
+        const double pp1_hse = p0_hse + 0.25 * dL * (rz[2] + rz[3]) * (src[2] + src[3]);
+        const double pp2_hse = pp1_hse + 0.25 * dL * (rz[3] + rz[4]) * (src[3] + src[4]);
+        const double pm1_hse = p0_hse - 0.25 * dL * (rz[2] + rz[1]) * (src[2] + src[1]);
+        const double pm2_hse = pm1_hse - 0.25 * dL * (rz[1] + rz[0]) * (src[1] + src[0]);
+        const double pph = p0_hse + 0.5 * dL * rz[2] * src[2];
+        const double pmh = p0_hse - 0.5 * dL * rz[2] * src[2];
+        const bool ptest = p0_hse < 0.0 || pp1_hse < 0.0 || pp2_hse < 0.0 || pm1_hse < 0.0 || pm2_hse < 0.0 || pph < 0.0 || pmh < 0.0;
+        const bool do_hse = !ptest && rz[2] >= P.pslope_cutoff_density;
+        if (do_hse) ppm_reconstruct(P, pz[0] - pm2_hse, pz[1] - pm1_hse, pz[2] - p0_hse, pz[3] - pp1_hse, pz[4] - pp2_hse, flat, sm, sp);
+        else ppm_reconstruct(P, pz[0], pz[1], pz[2], pz[3], pz[4], flat, sm, sp);
+        if (do_hse && !P.ppm_well_balanced) { sp += pph; sm += pmh; }
+        if (do_hse && P.ppm_well_balanced) {
+            pb.set(sm, sp, 0.0);
+            p_m_hse = pz[2] - 0.5 * dL * rz[2] * src[2];
+            p_p_hse = pz[2] + 0.5 * dL * rz[2] * src[2];
+            wb_hse = true;
+        } else {
+            pb.set(sm, sp, pz[2]);
+        }
+    } else {
+        CTU_RECON(QS_P);
+    }
     pb.integ(un - cc, dtdL, Ip_p0, Im_p0);
     pb.integ(un, dtdL, Ip_p1, Im_p1);
     pb.integ(un + cc, dtdL, Ip_p2, Im_p2);
@@ -992,23 +1033,23 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
     const double small_re = P.small_dens * P.small_ener;
     {   // plus state on the low face (trace_ppm.cpp:494-581)
         double rho_ref = Im_rho0 + SA(m_rho0);
-        double un_ref = Im_un0 + SA(m_un0);
+        double un_ref = Im_un0 + SAU(m_un0);
         double p_ref = Im_p0 + SA(m_p0);
         double rhoe_g_ref = Im_re0 + SA(m_re0);
         double gam_g_ref = Im_gc0;
         rho_ref = smax(rho_ref, P.small_dens);
         double rho_ref_inv = M::rcp(rho_ref);
         p_ref = smax(p_ref, P.small_pres);
-        double csq_ref = gam_g_ref * (0.0 + p_ref) * rho_ref_inv;
+        double csq_ref = gam_g_ref * (p_m_hse + p_ref) * rho_ref_inv;
         double cc_ref = M::sqrt(csq_ref);
         double cc_ref_inv = M::rcp(cc_ref);
-        double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
-        double d_um = un_ref - Im_un0 - SA(m_un0);
+        double h_g_ref = ((p_m_hse + p_ref) + rhoe_g_ref) * rho_ref_inv;
+        double d_um = un_ref - Im_un0 - SAU(m_un0);
         double dptotm = p_ref - Im_p0 - SA(m_p0);
         double drho = rho_ref - Im_rho1 - SA(m_rho1);
         double dptot = p_ref - Im_p1 - SA(m_p1);
         double drhoe_g = rhoe_g_ref - Im_re1 - SA(m_re1);
-        double d_up = un_ref - Im_un2 - SA(m_un2);
+        double d_up = un_ref - Im_un2 - SAU(m_un2);
         double dptotp = p_ref - Im_p2 - SA(m_p2);
         double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
         double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
@@ -1021,29 +1062,29 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
         op[IS_RHO] = smax(P.small_dens, rho_ref + alphap + alpham + alpha0r);
         op[IUN] = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
         op[IS_RE] = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
-        op[IS_P] = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
+        op[IS_P] = smax(P.small_pres, p_m_hse + p_ref + (alphap + alpham) * csq_ref);
         op[IUT] = Im_ut + SA(m_ut);
         op[IUTT] = Im_utt + SA(m_utt);
     }
     {   // minus state on the high face (trace_ppm.cpp:583-675)
         double rho_ref = Ip_rho2 + SA(p_rho2);
-        double un_ref = Ip_un2 + SA(p_un2);
+        double un_ref = Ip_un2 + SAU(p_un2);
         double p_ref = Ip_p2 + SA(p_p2);
         double rhoe_g_ref = Ip_re2 + SA(p_re2);
         double gam_g_ref = Ip_gc2;
         rho_ref = smax(rho_ref, P.small_dens);
         double rho_ref_inv = M::rcp(rho_ref);
         p_ref = smax(p_ref, P.small_pres);
-        double csq_ref = gam_g_ref * (0.0 + p_ref) * rho_ref_inv;
+        double csq_ref = gam_g_ref * (p_p_hse + p_ref) * rho_ref_inv;
         double cc_ref = M::sqrt(csq_ref);
         double cc_ref_inv = M::rcp(cc_ref);
-        double h_g_ref = ((0.0 + p_ref) + rhoe_g_ref) * rho_ref_inv;
-        double d_um = un_ref - Ip_un0 - SA(p_un0);
+        double h_g_ref = ((p_p_hse + p_ref) + rhoe_g_ref) * rho_ref_inv;
+        double d_um = un_ref - Ip_un0 - SAU(p_un0);
         double dptotm = p_ref - Ip_p0 - SA(p_p0);
         double drho = rho_ref - Ip_rho1 - SA(p_rho1);
         double dptot = p_ref - Ip_p1 - SA(p_p1);
         double drhoe_g = rhoe_g_ref - Ip_re1 - SA(p_re1);
-        double d_up = un_ref - Ip_un2 - SA(p_un2);
+        double d_up = un_ref - Ip_un2 - SAU(p_un2);
         double dptotp = p_ref - Ip_p2 - SA(p_p2);
         double alpham = 0.5 * (dptotm * rho_ref_inv * cc_ref_inv - d_um) * rho_ref * cc_ref_inv;
         double alphap = 0.5 * (dptotp * rho_ref_inv * cc_ref_inv + d_up) * rho_ref * cc_ref_inv;
@@ -1056,17 +1097,156 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
         om[IS_RHO] = smax(P.small_dens, rho_ref + alphap + alpham + alpha0r);
         om[IUN] = un_ref + (alphap - alpham) * cc_ref * rho_ref_inv;
         om[IS_RE] = smax(small_re, rhoe_g_ref + (alphap + alpham) * h_g_ref + alpha0e_g);
-        om[IS_P] = smax(P.small_pres, 0.0 + p_ref + (alphap + alpham) * csq_ref);
+        om[IS_P] = smax(P.small_pres, p_p_hse + p_ref + (alphap + alpham) * csq_ref);
         om[IUT] = Ip_ut + SA(p_ut);
         om[IUTT] = Ip_utt + SA(p_utt);
     }
 #undef SA
+#undef SAU
+}
+
+// Castro::trace_plm for one zone and direction (trace_plm.cpp:17-393; uslope / pslope of slope.H): the arithmetic of k_trace_plm in
+// ctu_kernels.cuh with the primitive stencil in shared memory and the results left in registers (REC = 1 of the tile kernel).
+//   lo_t / hi_t: the zone touches a symmetry boundary on its low / high side (reflecting slopes of the normal velocity);
+//   sb = &srcq(zone, comp 0), strides ssn / sst (SRC only): half-step sources and the g of pslope;  dt: the full step.
+template <class M, int DIR, int NP, bool SRC>
+__device__ __forceinline__ void trace_core_plm(const DevPar& P, const double* __restrict__ base, const int sn, const int st, const double flat,
+                                               const double dtdL, const double dt, const bool lo_t, const bool hi_t,
+                                               const double* __restrict__ sb, const long ssn, const long sst, double* __restrict__ op,
+                                               double* __restrict__ om, double* __restrict__ xp, double* __restrict__ xm) {
+    constexpr int QUN = QS_U + DIR;
+    constexpr int QUT = QS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
+    constexpr int QUTT = QS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
+    constexpr int IUN = IS_U + DIR;
+    constexpr int IUT = IS_U + ((DIR == 0) ? 1 : (DIR == 1) ? 2 : 0);
+    constexpr int IUTT = IS_U + ((DIR == 0) ? 2 : (DIR == 1) ? 0 : 1);
+    const double cc = base[QS_C * sn];
+    const double csq = cc * cc;
+    const double rho = base[QS_RHO * sn];
+    const double un = base[QUN * sn], ut = base[QUT * sn], utt = base[QUTT * sn];
+    const double p = base[QS_P * sn];
+    const double rhoe = base[QS_RE * sn];
+    const double enth = M::div(rhoe + p, rho * csq);
+    auto slope = [&](int comp, bool vtest) {
+        const double* __restrict__ a = base + comp * sn;
+        return plm_uslope(P, a[-2 * st], a[-st], a[0], a[st], a[2 * st], flat, lo_t && vtest, hi_t && vtest);
+    };
+    const double dq_rho = slope(QS_RHO, false), dq_un = slope(QUN, true), dq_ut = slope(QUT, false), dq_utt = slope(QUTT, false);
+    double dq_p = slope(QS_P, false);
+    const double dq_re = slope(QS_RE, false);
+    if (P.use_pslope == 1 && P.plm_iorder != 1 && rho >= P.pslope_cutoff_density) {   // pslope (slope.H:120-245), trace_plm.cpp:177-190
+        const double* __restrict__ a = base + QS_P * sn;
+        const double* __restrict__ r = base + QS_RHO * sn;
+        const double dL = P.dx[DIR];
+        double src[5];
+#pragma unroll
+        for (int m = -2; m <= 2; ++m) src[m + 2] = SRC ? sb[QUN * ssn + m * sst] : 0.0;
+        const double p0_hse = a[0];
+        const double pp1_hse = p0_hse + 0.25 * dL * (r[0] + r[st]) * (src[2] + src[3]);
+        const double pp2_hse = pp1_hse + 0.25 * dL * (r[st] + r[2 * st]) * (src[3] + src[4]);
+        const double pm1_hse = p0_hse - 0.25 * dL * (r[0] + r[-st]) * (src[2] + src[1]);
+        const double pm2_hse = pm1_hse - 0.25 * dL * (r[-st] + r[-2 * st]) * (src[1] + src[0]);
+        const double p0 = 0.0;
+        double pp1 = a[st] - pp1_hse, pp2 = a[2 * st] - pp2_hse, pm1 = a[-st] - pm1_hse, pm2 = a[-2 * st] - pm2_hse;
+        if (lo_t) { pm1 = 0.0; pm2 = 0.0; }
+        if (hi_t) { pp1 = 0.0; pp2 = 0.0; }
+        const double dlftp1 = pp1 - p0, drgtp1 = pp2 - pp1;
+        double dcen = 0.5 * (dlftp1 + drgtp1);
+        double dsgn = copysign(1.0, dcen);
+        double dlim = dlftp1 * drgtp1 >= 0.0 ? 2.0 * smin(fabs(dlftp1), fabs(drgtp1)) : 0.0;
+        const double dfp1 = dsgn * smin(dlim, fabs(dcen));
+        const double dlftm1 = pm1 - pm2, drgtm1 = p0 - pm1;
+        dcen = 0.5 * (dlftm1 + drgtm1);
+        dsgn = copysign(1.0, dcen);
+        dlim = dlftm1 * drgtm1 >= 0.0 ? 2.0 * smin(fabs(dlftm1), fabs(drgtm1)) : 0.0;
+        const double dfm1 = dsgn * smin(dlim, fabs(dcen));
+        const double dlft = drgtm1, drgt = dlftp1;
+        dcen = 0.5 * (dlft + drgt);
+        dsgn = copysign(1.0, dcen);
+        dlim = dlft * drgt >= 0.0 ? 2.0 * smin(fabs(dlft), fabs(drgt)) : 0.0;
+        const double dp1 = (4.0 / 3.0) * dcen - (1.0 / 6.0) * (dfp1 + dfm1);
+        dq_p = flat * dsgn * smin(dlim, fabs(dp1));
+        dq_p += r[0] * src[2] * dL;
+    } else if (P.use_pslope == 1 && P.plm_iorder == 1) {
+        dq_p = 0.0;
+    }
+    const double dqp_rc = M::div(dq_p, rho * cc), rho_c = M::div(rho, cc);
+    const double alpham = 0.5 * (dqp_rc - dq_un) * rho_c;
+    const double alphap = 0.5 * (dqp_rc + dq_un) * rho_c;
+    const double alpha0r = dq_rho - M::div(dq_p, csq);
+    const double alpha0e = dq_re - dq_p * enth;
+    const double e0 = un - cc, e1 = un, e2 = un + cc;
+    // half-step source terms (zero without sources: the additions are kept because they turn -0.0 into +0.0 like the reference)
+    double s_rho = 0.0, s_un = 0.0, s_ut = 0.0, s_utt = 0.0, s_p = 0.0, s_re = 0.0;
+    if (SRC) {
+        s_rho = sb[QS_RHO * ssn]; s_un = sb[QUN * ssn]; s_ut = sb[QUT * ssn]; s_utt = sb[QUTT * ssn];
+        s_p = sb[QS_P * ssn]; s_re = sb[QS_RE * ssn];
+    }
+    {   // right state on face i (trace_plm.cpp:209-248)
+        const double ref_fac = 0.5 * (1.0 + dtdL * smin(e0, 0.0));
+        const double rho_ref = rho - ref_fac * dq_rho, un_ref = un - ref_fac * dq_un, ut_ref = ut - ref_fac * dq_ut;
+        const double utt_ref = utt - ref_fac * dq_utt, p_ref = p - ref_fac * dq_p, rhoe_ref = rhoe - ref_fac * dq_re;
+        const double trace_fac0 = 0.0;
+        const double trace_fac1 = 0.25 * dtdL * (e0 - e1) * (1.0 - copysign(1.0, e1));
+        const double trace_fac2 = 0.25 * dtdL * (e0 - e2) * (1.0 - copysign(1.0, e2));
+        const double apright = trace_fac2 * alphap, amright = trace_fac0 * alpham;
+        const double azrright = trace_fac1 * alpha0r, azeright = trace_fac1 * alpha0e;
+        const double azut1rght = trace_fac1 * dq_ut, azutt1rght = trace_fac1 * dq_utt;
+        double o_rho = smax(P.small_dens, rho_ref + apright + amright + azrright);
+        double o_un = un_ref + M::div((apright - amright) * cc, rho);
+        double o_ut = ut_ref + azut1rght;
+        double o_utt = utt_ref + azutt1rght;
+        double o_p = smax(P.small_pres, p_ref + (apright + amright) * csq);
+        double o_re = rhoe_ref + (apright + amright) * enth * csq + azeright;
+        o_rho += 0.5 * dt * s_rho;
+        o_rho = smax(P.small_dens, o_rho);
+        o_un += 0.5 * dt * s_un;
+        o_ut += 0.5 * dt * s_ut;
+        o_utt += 0.5 * dt * s_utt;
+        o_re += 0.5 * dt * s_re;
+        o_p += 0.5 * dt * s_p;
+        op[IS_RHO] = o_rho; op[IUN] = o_un; op[IUT] = o_ut; op[IUTT] = o_utt; op[IS_P] = o_p; op[IS_RE] = o_re;
+    }
+    {   // left state on face i+1 (trace_plm.cpp:252-320)
+        const double ref_fac = 0.5 * (1.0 - dtdL * smax(e2, 0.0));
+        const double rho_ref = rho + ref_fac * dq_rho, un_ref = un + ref_fac * dq_un, ut_ref = ut + ref_fac * dq_ut;
+        const double utt_ref = utt + ref_fac * dq_utt, p_ref = p + ref_fac * dq_p, rhoe_ref = rhoe + ref_fac * dq_re;
+        const double trace_fac0 = 0.25 * dtdL * (e2 - e0) * (1.0 + copysign(1.0, e0));
+        const double trace_fac1 = 0.25 * dtdL * (e2 - e1) * (1.0 + copysign(1.0, e1));
+        const double trace_fac2 = 0.0;
+        const double apleft = trace_fac2 * alphap, amleft = trace_fac0 * alpham;
+        const double azrleft = trace_fac1 * alpha0r, azeleft = trace_fac1 * alpha0e;
+        const double azut1left = trace_fac1 * dq_ut, azutt1left = trace_fac1 * dq_utt;
+        double o_rho = smax(P.small_dens, rho_ref + apleft + amleft + azrleft);
+        double o_un = un_ref + M::div((apleft - amleft) * cc, rho);
+        double o_ut = ut_ref + azut1left;
+        double o_utt = utt_ref + azutt1left;
+        double o_p = smax(P.small_pres, p_ref + (apleft + amleft) * csq);
+        double o_re = rhoe_ref + (apleft + amleft) * enth * csq + azeleft;
+        o_rho = smax(P.small_dens, o_rho + 0.5 * dt * s_rho);
+        o_un += 0.5 * dt * s_un;
+        o_ut += 0.5 * dt * s_ut;
+        o_utt += 0.5 * dt * s_utt;
+        o_re += 0.5 * dt * s_re;
+        o_p += 0.5 * dt * s_p;
+        om[IS_RHO] = o_rho; om[IUN] = o_un; om[IUT] = o_ut; om[IUTT] = o_utt; om[IS_P] = o_p; om[IS_RE] = o_re;
+    }
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) {   // trace_plm.cpp:361-389
+        const double* __restrict__ a = base + (QS_X + ip) * sn;
+        const double s0 = a[0];
+        const double dX = plm_uslope(P, a[-2 * st], a[-st], s0, a[st], a[2 * st], flat, false, false);
+        const double spzero_p = un >= 0.0 ? -1.0 : un * dtdL;
+        xp[ip] = s0 + 0.5 * (-1.0 - spzero_p) * dX;
+        const double spzero_m = un >= 0.0 ? un * dtdL : 1.0;
+        xm[ip] = s0 + 0.5 * (1.0 - spzero_m) * dX;
+    }
 }
 
 // trace + first-pass Riemann solve of one zone of the tile on the staged primitives (M = MathFast: speculative pass, MathExact: replay)
 struct TraceCtx { int i, j, k, tx, ty, tz, dloc, btile, pq; bool active; };
 
-template <class M, int D, int NP, bool SRC, int RS = 0>
+template <class M, int D, int NP, bool SRC, int RS = 0, int REC = 0>
 __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceRiemannArgs& a, unsigned char* smem, const TraceCtx& c,
                                                    const double flat) {
     using L = TraceSmem<D, NP>;
@@ -1082,13 +1262,17 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
     if (active) {
         const int oq = QT::off(tx + pq + (D == 0 ? 2 : 0), ty + (D == 1 ? 2 : 0), tz + (D == 2 ? 2 : 0));
         const double* sq0 = reinterpret_cast<const double*>(smem + L::O_Q) + oq;
-        SrcAdd sa;
-        if (SRC) {   // traced source terms (trace_ppm.cpp:309-440): the primitive sources come straight from HBM / L2
-            const long sst = (D == 0) ? 1 : (D == 1) ? a.srcq.sj : a.srcq.sk;
-            trace_sources<D>(P, a.srcq.p + a.srcq.idx(i, j, k), a.srcq.sn, sst, flat, sq0[(QS_U + D) * QT::ZONES], sq0[QS_C * QT::ZONES],
-                             a.dtdL, a.hdt, sa, *a.src_mask);
+        const long sst = (D == 0) ? 1 : (D == 1) ? a.srcq.sj : a.srcq.sk;
+        const double* sb = SRC ? a.srcq.p + a.srcq.idx(i, j, k) : nullptr;      // the primitive sources come straight from HBM / L2
+        if constexpr (REC == 1) {   // piecewise-linear reconstruction (castro.ppm_type = 0)
+            trace_core_plm<M, D, NP, SRC>(P, sq0, QT::ZONES, QT::stride(D), flat, a.dtdL, 2.0 * a.hdt, sym_lo && idx == P.domlo[D],
+                                          sym_hi && idx == P.domhi[D], sb, a.srcq.sn, sst, qp_own, qm_nxt, xp_own, xm_nxt);
+        } else {
+            SrcAdd sa;
+            if (SRC)     // traced source terms (trace_ppm.cpp:309-440)
+                trace_sources<D>(P, sb, a.srcq.sn, sst, flat, sq0[(QS_U + D) * QT::ZONES], sq0[QS_C * QT::ZONES], a.dtdL, a.hdt, sa, *a.src_mask);
+            trace_core<M, D, NP, SRC, REC>(P, sq0, QT::ZONES, QT::stride(D), flat, a.dtdL, qp_own, qm_nxt, xp_own, xm_nxt, sa, sb, a.srcq.sn, sst);
         }
-        trace_core<M, D, NP, SRC>(P, sq0, QT::ZONES, QT::stride(D), flat, a.dtdL, qp_own, qm_nxt, xp_own, xm_nxt, sa);
         // hand the minus state to the thread that owns the high face
 #pragma unroll
         for (int n = 0; n < 6; ++n) sEx[n * L::NTHR + threadIdx.x] = qm_nxt[n];
@@ -1171,7 +1355,7 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
     for (int ip = 0; ip < NP; ++ip) a.Fo.at(of, FX_X + ip) = FX[ip];
 }
 
-template <int D, int NP, bool SRC, int RS = 0>
+template <int D, int NP, bool SRC, int RS = 0, int REC = 0>
 static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, CTU_TRACE_MINB)
 k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, const TraceRiemannArgs a) {
     using L = TraceSmem<D, NP>;
@@ -1206,11 +1390,11 @@ k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, con
     CTU_PT_LOADED
     // speculative pass with the branch-free division / sqrt sequences; exact replay of the tile if any thread met an operand
     // outside their range (see MathFast in ctu_physics.cuh)
-    trace_riemann_body<MathFast, D, NP, SRC, RS>(P, a, smem, c, flat);
+    trace_riemann_body<MathFast, D, NP, SRC, RS, REC>(P, a, smem, c, flat);
     __syncthreads();
     if (ctu_div_unsafe[0]) {
         if (threadIdx.x == 0 && P.replays) atomicAdd(P.replays, 1);
-        trace_riemann_body<MathExact, D, NP, SRC, RS>(P, a, smem, c, flat);
+        trace_riemann_body<MathExact, D, NP, SRC, RS, REC>(P, a, smem, c, flat);
     }
     CTU_PT_END(0)
 }

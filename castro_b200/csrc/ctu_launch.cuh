@@ -102,13 +102,21 @@ int launch_trans2_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const B
     if (!rc) rc = launch_trans2<2, NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
     return rc;
 }
-template <int D, int NP, bool SRC, int RS = 0>
+// Reconstructions other than plain PPM (REC = 1: piecewise linear, castro.ppm_type = 0; REC = 2: PPM with castro.use_pslope /
+// castro.ppm_well_balanced) only change the trace kernel; they are instantiated for CGF / HLLC and up to CTU_TMA_REC_MAX_NP passive
+// scalars, in their own translation unit (ctu_rec.cu).
+#ifndef CTU_TMA_REC_MAX_NP
+#define CTU_TMA_REC_MAX_NP 2
+#endif
+inline int trace_rec(const DevPar& P) { return P.ppm_type == 0 ? 1 : (P.use_pslope || P.ppm_well_balanced) ? 2 : 0; }
+
+template <int D, int NP, bool SRC, int RS = 0, int REC = 0>
 int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1, const Box3& tb,
                          double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
     using L = TraceSmem<D, NP>;
     using TT = TrTile<D>;
     static bool attr = false;
-    if (!attr) { int rc = set_smem(k_trace_riemann_tma<D, NP, SRC, RS>, L::TOTAL); if (rc) return rc; attr = true; }
+    if (!attr) { int rc = set_smem(k_trace_riemann_tma<D, NP, SRC, RS, REC>, L::TOTAL); if (rc) return rc; attr = true; }
     CTU_MAP(m_q, qs, qbx_a, L::NQC, L::QT, L::NQC)
     TraceRiemannArgs a;
     a.fd = fd; a.qm = ta.qm[D]; a.qp = ta.qp[D]; a.Fo = F1[D];
@@ -123,12 +131,45 @@ int launch_trace_riemann(const DevPar& P, const TraceArgs& ta, const A4& qs, con
     a.zg = zgroup();
     a.dtdL = dt / P.dx[D];
     a.srcq = srcq; a.hdt = 0.5 * dt; a.src_mask = src_mask;
-    k_trace_riemann_tma<D, NP, SRC, RS><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
+    k_trace_riemann_tma<D, NP, SRC, RS, REC><<<(unsigned)a.ntx * a.nty * a.ntz, L::NTHR, L::TOTAL, st>>>(P, m_q, a);
     return 0;
 }
 template <int NP, bool SRC>
+int launch_trace_riemann_rec_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
+                                const Box3& tb, double dt, const A4& srcq, const int* src_mask, cudaStream_t st, int rec) {
+    int rc;
+    if (rec == 1) {
+        rc = launch_trace_riemann<0, NP, SRC, 0, 1>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+        if (!rc) rc = launch_trace_riemann<1, NP, SRC, 0, 1>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+        if (!rc) rc = launch_trace_riemann<2, NP, SRC, 0, 1>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    } else {
+        rc = launch_trace_riemann<0, NP, SRC, 0, 2>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+        if (!rc) rc = launch_trace_riemann<1, NP, SRC, 0, 2>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+        if (!rc) rc = launch_trace_riemann<2, NP, SRC, 0, 2>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    }
+    return rc;
+}
+#define CTU_INSTANTIATE_REC(KW, N)                                                                                                      \
+    KW template int ctu::launch_trace_riemann_rec_np<N, true>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&, \
+                                                              const ctu::A4&, const ctu::A4*, const ctu::Box3&, double, const ctu::A4&,  \
+                                                              const int*, cudaStream_t, int);                                           \
+    KW template int ctu::launch_trace_riemann_rec_np<N, false>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&, \
+                                                               const ctu::A4&, const ctu::A4*, const ctu::Box3&, double, const ctu::A4&, \
+                                                               const int*, cudaStream_t, int);
+}  // namespace ctu
+#ifndef CTU_REC_TU      // every translation unit but ctu_rec.cu only declares them
+CTU_INSTANTIATE_REC(extern, 1)
+CTU_INSTANTIATE_REC(extern, 2)
+#endif
+namespace ctu {
+
+template <int NP, bool SRC>
 int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
                             const Box3& tb, double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
+    if (const int rec = trace_rec(P)) {
+        if constexpr (NP <= CTU_TMA_REC_MAX_NP) return launch_trace_riemann_rec_np<NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st, rec);
+        else return CTU_ERR_UNSUPPORTED;
+    }
     if constexpr (NP <= CTU_TMA_CG_MAX_NP) {
         if (P.riemann_solver == 1) {
             int rc = launch_trace_riemann<0, NP, SRC, 1>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);

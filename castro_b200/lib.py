@@ -44,6 +44,7 @@ def lib():
         L.ctu_workspace_destroy.argtypes = [C.c_void_p]
         L.ctu_workspace_bytes.argtypes = [C.c_void_p]
         L.ctu_workspace_last_slabs.argtypes = [C.c_void_p]
+        L.ctu_workspace_last_tile_staged.argtypes = [C.c_void_p]
         L.ctu_workspace_launches.argtypes = [C.c_void_p]
         L.ctu_workspace_replays.argtypes = [C.c_void_p]
         L.ctu_workspace_replays.restype = C.c_long
@@ -400,6 +401,11 @@ class Sim:
     @property
     def last_slabs(self):
         return lib().ctu_workspace_last_slabs(lib().ctu_sim_workspace(self.h))
+
+    @property
+    def tile_staged(self):
+        """True if the last advance ran the tile-staged (TMA) kernel family"""
+        return bool(lib().ctu_workspace_last_tile_staged(lib().ctu_sim_workspace(self.h)))
 
     @property
     def last_subcycles(self):

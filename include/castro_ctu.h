@@ -188,6 +188,9 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
 /* diagnostics of the last advance: number of z-slabs used, kernels launched since creation */
 int ctu_workspace_last_slabs(const ctu_workspace_t* ws);
 int ctu_workspace_launches(const ctu_workspace_t* ws);
+/* 1 if the last advance ran the tile-staged (TMA) kernels, 0 if the register-staged family took it (options / passive counts the
+ * tile kernels are not instantiated for; CTU_NO_TMA=1) */
+int ctu_workspace_last_tile_staged(const ctu_workspace_t* ws);
 /* diagnostic: number of tiles (CTAs) of the flux-stage kernels that were recomputed with the IEEE division / sqrt operators
  * because an operand fell outside the range of the branch-free sequences (see MathFast, castro_b200/csrc/ctu_physics.cuh) */
 long ctu_workspace_replays(const ctu_workspace_t* ws);

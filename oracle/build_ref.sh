@@ -22,6 +22,7 @@
 #                                        problem_initialize_state_data.H:50); the recipe qualifies that one identifier in the SCRATCH COPY of
 #                                        the problem directory.  No file of the hot path (Source/hydro, Source/driver, Source/gravity) is touched.
 #   oracle/_ref/Castro3d_noh.ex          (`noh`) Noh implosion problem, serial (golden generator for problem_bc_fill / inflow boundaries)
+#   oracle/_ref/Castro2d_sedov.ex, Castro2d_kh.ex   (`sedov2d`, `kh2d`) DIM=2 builds, golden generators for the 2-D Cartesian path
 #   oracle/_ref/fcompare.ex              AMReX plotfile comparator (DIM=3)
 #   oracle/_ref/Castro3d_sedov_cuda.ex   (`gpu`)  the UNMODIFIED reference built with its own GPU back end (USE_CUDA=TRUE CUDA_ARCH=100):
 #                                        Castro's stock unfused ParallelFor pipeline on the same B200 -- the "reference_gpu" baseline
@@ -61,6 +62,9 @@ if [ "$what" = kh4 ]; then build KH Castro3d_kh4 DIM=3 NETWORK_INPUTS=triple_alp
 if [ "$what" = sodstellar ]; then build Sod_stellar Castro3d_sodstellar DIM=3 USE_MHD=FALSE; fi
 # the literal BASELINE config[0]: Sod in ONE dimension (DIM=1), golden generator for the 1-D path
 if [ "$what" = sod1d ]; then build Sod Castro1d_sod DIM=1; fi
+# 2-D Cartesian path (AMREX_SPACEDIM == 2): Sedov (cylindrical blast in Cartesian coordinates, inputs.2d.cyl_in_cartcoords) and KH (inputs.2d)
+if [ "$what" = sedov2d ]; then build Sedov Castro2d_sedov DIM=2; fi
+if [ "$what" = kh2d ]; then build KH Castro2d_kh DIM=2; fi
 if [ "$what" = all ] || [ "$what" = sod ];    then build Sod Castro3d_sod DIM=3; fi
 # Noh implosion: the one hydro test whose outer ghost zones come from problem_bc_fill (time-dependent inflow); golden generator for the bc hook
 if [ "$what" = noh ]; then build Noh Castro3d_noh DIM=3; fi

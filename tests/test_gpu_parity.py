@@ -190,7 +190,7 @@ def test_register_staged_kernels_match_golden():
         "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
         "from cases import load_case\n"
         "from castro_b200 import lib\n"
-        "for name in ('sedov16_hllc', 'sedov_24x16x8_cgf', 'sedov16_hllc_eos', 'sedov16_hllc_hybrid', 'sedov_24x16x8_cg', 'sedov16_hllc_limit', 'sedov16_plm_hllc', 'sedov16_cgf_tempfix'):\n"
+        "for name in ('sedov16_hllc', 'sedov_24x16x8_cgf', 'sedov16_hllc_eos', 'sedov16_hllc_hybrid', 'sedov_24x16x8_cg', 'sedov16_hllc_limit', 'sedov16_plm_hllc', 'sedov16_plm_cgf_lim1', 'sedov16_cgf_rhoe', 'sedov16_cgf_tempfix'):\n"
         "    par, geom, prob, g, snaps = load_case(name)\n"
         "    lib.params_finalize(par)\n"
         "    n = tuple(int(x) for x in g['n_cell'])\n"
@@ -203,6 +203,38 @@ def test_register_staged_kernels_match_golden():
     env = dict(os.environ, CTU_NO_TMA="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_kernel_family_selection():
+    """Which option sets run the tile-staged (TMA) kernels: the defaults, Colella & Glaz, piecewise-linear reconstruction and the
+    hydrostatic-pressure-aware reconstructions (their own instantiations of the trace kernel); hybrid Riemann, the flux limiter,
+    ppm_temp_fix and transverse_reset_rhoe stay on the register-staged family.  Each case also lands bit for bit on its golden."""
+    _torch()
+    from castro_b200 import lib
+    from cases import load_rt_case
+    expect = {"sedov16_hllc": True, "sedov16_cg": True, "sedov16_plm_hllc": True, "sedov16_plm_cgf_lim1": True, "sedov16_hllc_eos": False,
+              "sedov16_hllc_hybrid": False, "sedov16_hllc_limit": False, "sedov16_cgf_tempfix": False, "sedov16_combo": False}
+    for name, tile in expect.items():
+        par, geom, prob, g, snaps = load_case(name)
+        lib.params_finalize(par)
+        n = tuple(int(x) for x in g["n_cell"])
+        sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in n))
+        sim.init_problem("Sedov", prob)
+        rc, t, dt, hist = sim.advance(snaps[-1])
+        assert rc == 0
+        assert sim.tile_staged == tile, name
+        assert_bitwise(sim.download(), g["U%d" % snaps[-1]], name)
+        sim.close()
+    for name in ("rt16_pslope", "rt16_wellbal", "rt16_plm_pslope"):      # with traced / half-step gravity sources
+        par, geom, g, snaps = load_rt_case(name)
+        lib.params_finalize(par)
+        n = tuple(int(x) for x in g["n_cell"])
+        sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in n))
+        sim.init_problem("RT", dict(frac=0.5, rho_1=1.0, rho_2=2.0, p0_base=5.0))
+        rc, t, dt, hist = sim.advance(snaps[-1])
+        assert rc == 0 and sim.tile_staged, name
+        assert_bitwise(sim.download(), g["U%d" % snaps[-1]][:par.num_state], name)
+        sim.close()
 
 
 def test_persistent_trans2_variant_matches_golden():
