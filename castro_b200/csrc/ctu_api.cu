@@ -111,7 +111,7 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
     P.QFS_off = par->nadv;
     P.gamc_const = (par->eos_kind == 0);
     P.eos_kind = par->eos_kind;
-    P.dim = (geom && geom->dim == 1) ? 1 : 3;
+    P.dim = (geom && geom->dim == 1) ? 1 : (geom && geom->dim == 2) ? 2 : 3;
     if (par->eos_kind == 1 && helm_device_table(par, &P.helm) != 0) std::memset(&P.helm, 0, sizeof(P.helm));
     P.difmag = par->difmag;
     P.small_dens = par->small_dens; P.small_temp = par->small_temp;
@@ -161,7 +161,16 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     // constant-gravity driver are instantiated for the gamma law only
     if (p->eos_kind == 1 && (p->transverse_use_eos || p->transverse_reset_rhoe || p->ppm_temp_fix || p->do_grav)) return CTU_ERR_UNSUPPORTED;
     if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
-    if (g && g->dim != 0 && g->dim != 1 && g->dim != 3) return CTU_ERR_UNSUPPORTED;       // 2-D: not built
+    if (g && g->dim != 0 && g->dim != 1 && g->dim != 2 && g->dim != 3) return CTU_ERR_BAD_ARG;
+    if (g && g->dim == 2) {
+        // the 2-D Cartesian path (Castro_ctu_hydro.cpp:530-650): one zone in z; PPM / PLM, the three Riemann solvers, any passives, the
+        // edge-state thermodynamics options.  Not instantiated for it: sources / gravity, hybrid Riemann, the flux limiter, the
+        // hydrostatic reconstructions, ppm_temp_fix, the Helmholtz EOS
+        if (g->domlo[2] != g->domhi[2]) return CTU_ERR_BAD_ARG;
+        if (p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->do_grav || p->use_pslope || p->ppm_well_balanced || p->ppm_temp_fix ||
+            p->eos_kind != 0)
+            return CTU_ERR_UNSUPPORTED;
+    }
     if (g) {      // "external boundaries meeting at a corner not supported" (Castro_bc_fill_nd.cpp:64-98): inflow faces in two directions
         int ndir_inflow = 0;
         for (int d = 0; d < 3; ++d) if (!g->periodic[d] && (g->lo_bc[d] == 1 || g->hi_bc[d] == 1)) ++ndir_inflow;
@@ -713,6 +722,86 @@ int hydro_box_1d(HydroRun* r) {
     return cudaGetLastError() == cudaSuccess ? 0 : CTU_ERR_CUDA;
 }
 
+// The 2-D Cartesian body (AMREX_SPACEDIM == 2, Castro_ctu_hydro.cpp:530-650): ctoprim -> flattening + div u -> trace in x and y -> first-pass
+// fluxes F^x on grow(xbx,(0,1)) and F^y on grow(ybx,(1,0)) -> per direction: ONE transverse correction (trans_single with the full half
+// step, area / volume form) fused with the final Riemann solve and the flux cleaning -> conservative update with the fused epilogue.
+// Register-staged kernels (a 2-D box is at most a few million zones; the 3-D tile kernels are not instantiated for it).
+int hydro_box_2d(HydroRun* r) {
+    ctu_workspace* ws = r->ws;
+    const DevPar& P = r->P;
+    const int np = r->np, NQS = QS_X + np, NIS = IS_X + np, NFX = FX_X + np;
+    cudaStream_t st = r->st;
+    const Box3 tb = r->vbx;
+    if (r->have_src) return CTU_ERR_UNSUPPORTED;
+    const Box3 qbx = grow(tb, 4, 4, 0), obx = grow(tb, 1, 1, 0);
+    Box3 ibx = obx; ibx.hi[0] += 1; ibx.hi[1] += 1;
+    const size_t ni = ibx.npts();
+    const size_t need = ((size_t)qbx.npts() * NQS + ni * (2 + 4 * NIS + 4 * NFX)) * sizeof(double);
+    int rc = ws_reserve_bytes(ws, need, st);
+    if (rc) return rc;
+    double* p = ws->arena;
+    const A4 qs = make_a4(p, qbx); p += qbx.npts() * NQS;
+    const A4 fd = make_a4(p, ibx); p += ni * 2;
+    TraceArgs ta;
+    std::memset(&ta, 0, sizeof(ta));
+    for (int d = 0; d < 2; ++d) {
+        ta.qm[d] = make_a4(p, ibx); p += ni * NIS;
+        ta.qp[d] = make_a4(p, ibx); p += ni * NIS;
+    }
+    for (int d = 0; d < 3; ++d) { ta.vlo[d] = tb.lo[d]; ta.vhi[d] = tb.hi[d]; }
+    A4 F1[2], F[2];
+    for (int d = 0; d < 2; ++d) { F1[d] = make_a4(p, ibx); p += ni * NFX; }
+    for (int d = 0; d < 2; ++d) { F[d] = make_a4(p, ibx); p += ni * NFX; }
+    A4 none;
+    std::memset(&none, 0, sizeof(none));
+    LaunchBox lb = make_lb(qbx);
+    k_ctoprim<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
+    lb = make_lb(obx);
+    k_flat_div_2d<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb);
+    if (P.ppm_type == 0) {
+        k_trace_plm<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none);
+        k_trace_plm<1, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none);
+    } else {
+        k_trace<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none, ws->d_counters + 5);
+        k_trace<1, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none, ws->d_counters + 5);
+    }
+    Box3 xbx = tb; xbx.hi[0] += 1;
+    Box3 ybx = tb; ybx.hi[1] += 1;
+    lb = make_lb(grow(xbx, 0, 1, 0));
+    k_riemann1<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd);
+    lb = make_lb(grow(ybx, 1, 0, 0));
+    k_riemann1<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd);
+    const double hdt = 0.5 * r->dt;
+    lb = make_lb(xbx);
+    k_trans_final_2d<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], fd, r->Sb, F[0], lb, hdt);
+    lb = make_lb(ybx);
+    k_trans_final_2d<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], fd, r->Sb, F[1], lb, hdt);
+    UpdateArgs ua;
+    std::memset(&ua, 0, sizeof(ua));
+    ua.F[0] = F[0]; ua.F[1] = F[1]; ua.F[2] = F[1];          // only F[0] and F[1] are read in 2-D
+    ua.dtmin = ws->d_dtmin; ua.counters = ws->d_counters;
+    ua.n_clean = r->n_clean; ua.want_dt = r->want_dt;
+    lb = make_lb(tb);
+    k_update<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, r->from_sb ? r->Sb : r->Sn, r->Sn, ua, lb, r->dt);
+    r->launches += 9;
+    for (int d = 0; d < 2; ++d) {
+        const bool want_f = r->flux && r->flux[d], want_m = r->mass_flux && r->mass_flux[d];
+        if (!want_f && !want_m) continue;
+        const Box3 fb = d == 0 ? xbx : ybx;
+        A4 fo, mo;
+        std::memset(&fo, 0, sizeof(fo)); std::memset(&mo, 0, sizeof(mo));
+        if (want_f) { if (!fab_covers(r->flux[d], fb) || r->flux[d]->ncomp < P.nstate) return CTU_ERR_BAD_ARG; fo = make_a4(*r->flux[d]); }
+        if (want_m) { if (!fab_covers(r->mass_flux[d], fb)) return CTU_ERR_BAD_ARG; mo = make_a4(*r->mass_flux[d]); }
+        // scale_flux in 2-D: dt * F * area with area_x = dy, area_y = dx; k_store_flux multiplies by the two other widths: dx_z = 1
+        DevPar P2 = P; P2.dx[2] = 1.0;
+        lb = make_lb(fb);
+        if (d == 0) k_store_flux<0><<<nblocks(lb.n), TPB, 0, st>>>(P2, F[0], fo, mo, lb, r->dt);
+        else k_store_flux<1><<<nblocks(lb.n), TPB, 0, st>>>(P2, F[1], fo, mo, lb, r->dt);
+        ++r->launches;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : CTU_ERR_CUDA;
+}
+
 // read the reductions back (synchronises the stream), fold the stage timers, free the run
 int hydro_end(HydroRun* r, double dt_est[2], int dt_loc[3], int n_bad[2]) {
     ctu_workspace* ws = r->ws;
@@ -795,8 +884,8 @@ int ctu_hydro_advance(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     HydroRun* r = hydro_begin(ws, par, geom, valid_lo, valid_hi, Sborder, S_new, flux, mass_flux, dt, flags, dt_est != nullptr,
                               (cudaStream_t)stream, &rc, old_src, src_corr);
     if (!r) return rc;
-    if (r->P.dim == 1) {
-        rc = hydro_box_1d(r);
+    if (r->P.dim == 1 || r->P.dim == 2) {
+        rc = r->P.dim == 1 ? hydro_box_1d(r) : hydro_box_2d(r);
         if (rc) { delete r; return rc; }
         hydro_set_slab_info(r, 1, 1);
         return hydro_end(r, dt_est, dt_loc, n_bad);

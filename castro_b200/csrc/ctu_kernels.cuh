@@ -196,6 +196,28 @@ static __global__ void __launch_bounds__(TPB) k_av_1d(const DevPar P, const A4 f
     for (int ip = P.QFS_off; ip < P.QFS_off + P.nspec; ++ip) F.at(of, FX_X + ip) = F.at(of, FX_X + ip) * fac;
 }
 
+// 2-D Cartesian (AMREX_SPACEDIM == 2): flattening along x and y (flatten.H:141-150), node-centred div u of advection_util.cpp:257-266
+static __global__ void __launch_bounds__(TPB) k_flat_div_2d(const DevPar P, const A4 qs, const A4 fd, const LaunchBox lb) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long oq = qs.idx(i, j, k), of = fd.idx(i, j, k);
+    const long sj = qs.sj;
+    const double* __restrict__ pp = qs.p + oq + QS_P * qs.sn;
+    const double* __restrict__ qu = qs.p + oq + QS_U * qs.sn;
+    const double* __restrict__ qv = qs.p + oq + QS_V * qs.sn;
+    double flatn = 1.0;
+    if (P.first_order_hydro) flatn = 0.0;
+    else if (P.use_flattening) {
+        flatn = flatten_dir([&](int s) { return pp[s]; }, [&](int s) { return qu[s]; });
+        flatn = smin(flatn, flatten_dir([&](int s) { return pp[s * sj]; }, [&](int s) { return qv[s * sj]; }));
+    }
+    fd.at(of, 0) = flatn;
+    const double dxinv = 1.0 / P.dx[0], dyinv = 1.0 / P.dx[1];
+    const double ux = 0.5 * (qu[0] - qu[-1] + qu[-sj] - qu[-1 - sj]) * dxinv;
+    const double vy = 0.5 * (qv[0] - qv[-sj] + qv[-1] - qv[-1 - sj]) * dyinv;
+    fd.at(of, 1) = ux + vy;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Source terms in the tracing: hydro::src_to_prim (advection_util.H:16-79) and the traced primitive sources of
 // trace_ppm (trace_ppm.cpp:309-440).  srcq scratch layout: rho u v w p (rho e)  (reference src_q minus the unused QTEMP slot).
@@ -917,6 +939,142 @@ static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, co
     for (int ip = 0; ip < P.npassive; ++ip) Fo.at(of, FX_X + ip) = passive_flux(P, pu, xm(ip), xp(ip));
 }
 
+// ------------------------------------------------------------------------------------------------
+// 2-D Cartesian (AMREX_SPACEDIM == 2, Castro_ctu_hydro.cpp:530-650): ONE transverse correction per direction, written by the reference
+// with face areas and the zone volume, hdt * (A F_r - A F_l) / V (trans.cpp:162-171,247-253,306-318,422-430,466-470), then the FINAL
+// Riemann solve and the flux cleaning (zero T flux, apply_av with dg2 = 0, normalize_species_fluxes).  N = face direction, T = 1 - N.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void trans_single_hydro_2d(const DevPar& P, const double* __restrict__ q, double* __restrict__ qo,
+                                                      const double* __restrict__ fl, const double* __restrict__ fr, double ugm, double ugp,
+                                                      double pgm, double pgp, double gamc, double hdt, double area, double volinv,
+                                                      double rrnew, bool reset) {
+    double dup = area * pgp * ugp - area * pgm * ugm;
+    double du = area * ugp - area * ugm;
+    double pav = 0.5 * (pgp + pgm);
+    double rrn = q[IS_RHO];
+    double run = rrn * q[IS_U];
+    double rvn = rrn * q[IS_V];
+    double rwn = rrn * q[IS_W];
+    double ekenn = 0.5 * rrn * (q[IS_U] * q[IS_U] + q[IS_V] * q[IS_V] + q[IS_W] * q[IS_W]);
+    double ren = q[IS_RE] + ekenn;
+    double rrnewn = rrnew;
+    double runewn = run - hdt * (area * fr[1] - area * fl[1]) * volinv;
+    double rvnewn = rvn - hdt * (area * fr[2] - area * fl[2]) * volinv;
+    double rwnewn = rwn - hdt * (area * fr[3] - area * fl[3]) * volinv;
+    double renewn = ren - hdt * (area * fr[4] - area * fl[4]) * volinv;
+    if (reset) { rrnewn = rrn; runewn = run; rvnewn = rvn; rwnewn = rwn; renewn = ren; }
+    qo[IS_RHO] = rrnewn;
+    const double rhoinv = 1.0 / rrnewn;
+    qo[IS_U] = runewn * rhoinv;
+    qo[IS_V] = rvnewn * rhoinv;
+    qo[IS_W] = rwnewn * rhoinv;
+    double rhoekenn = 0.5 * (runewn * runewn + rvnewn * rvnewn + rwnewn * rwnewn) * rhoinv;
+    double reo = renewn - rhoekenn;
+    if (!reset) {
+        if (P.transverse_reset_rhoe == 1 && reo <= 0.0) reo = q[IS_RE] - hdt * (area * fr[5] - area * fl[5] + pav * du) * volinv;
+        if (reo <= 0.0) reo = q[IS_RE];
+        double pnewn = q[IS_P] - hdt * (dup + pav * du * (gamc - 1.0)) * volinv;
+        qo[IS_P] = amax(pnewn, P.small_pres);
+        qo[IS_RE] = reo;
+    } else {
+        qo[IS_P] = q[IS_P];
+        qo[IS_RE] = q[IS_RE];
+    }
+}
+
+template <int N, int EK = 0>
+static __global__ void __launch_bounds__(TPB) k_trans_final_2d(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Ft, const A4 fd,
+                                                        const A4 U, const A4 Fo, const LaunchBox lb, const double hdt) {
+    constexpr int T = 1 - N;
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const double area = P.dx[1 - T];                  // faces normal to T: dx of the other direction
+    const double vol = P.dx[0] * P.dx[1];
+    const double volinv = 1.0 / vol;
+    const long o = qm.idx(i, j, k);
+    const long sN_f = (N == 0) ? 1 : Ft.sj, sT_f = (T == 0) ? 1 : Ft.sj;
+    const long sN_q = (N == 0) ? 1 : qs.sj;
+    const long ofp = Ft.idx(i, j, k), ofm = ofp - sN_f;
+    const long oqp = qs.idx(i, j, k), oqm = oqp - sN_q;
+    double qlo[6], qro[6];
+    bool reset_m, reset_p;
+    double rrnew_m, rrnew_p;
+    {   // minus state: zone (face - e_N)
+        double q[6], fl[6], fr[6];
+        load6(qm, o, q);
+        load6(Ft, ofm, fl);
+        load6(Ft, ofm + sT_f, fr);
+        rrnew_m = q[IS_RHO] - hdt * (area * fr[0] - area * fl[0]) * volinv;
+        reset_m = trans_reset(P, q[IS_RHO], rrnew_m, [&](int ip) { return qm.at(o, IS_X + ip); },
+                              [&](int ip, double c0) { return c0 - hdt * (area * Ft.at(ofm + sT_f, FX_X + ip) - area * Ft.at(ofm, FX_X + ip)) * volinv; });
+        const double gamc = P.gamc_const ? P.gamma : qs.at(oqm, QS_GAMC);
+        trans_single_hydro_2d(P, q, qlo, fl, fr, Ft.at(ofm, FX_UG), Ft.at(ofm + sT_f, FX_UG), Ft.at(ofm, FX_PG), Ft.at(ofm + sT_f, FX_PG),
+                              gamc, hdt, area, volinv, rrnew_m, reset_m);
+    }
+    {   // plus state: zone (face)
+        double q[6], fl[6], fr[6];
+        load6(qp, o, q);
+        load6(Ft, ofp, fl);
+        load6(Ft, ofp + sT_f, fr);
+        rrnew_p = q[IS_RHO] - hdt * (area * fr[0] - area * fl[0]) * volinv;
+        reset_p = trans_reset(P, q[IS_RHO], rrnew_p, [&](int ip) { return qp.at(o, IS_X + ip); },
+                              [&](int ip, double c0) { return c0 - hdt * (area * Ft.at(ofp + sT_f, FX_X + ip) - area * Ft.at(ofp, FX_X + ip)) * volinv; });
+        const double gamc = P.gamc_const ? P.gamma : qs.at(oqp, QS_GAMC);
+        trans_single_hydro_2d(P, q, qro, fl, fr, Ft.at(ofp, FX_UG), Ft.at(ofp + sT_f, FX_UG), Ft.at(ofp, FX_PG), Ft.at(ofp + sT_f, FX_PG),
+                              gamc, hdt, area, volinv, rrnew_p, reset_p);
+    }
+    const double rho_m = qm.at(o, IS_RHO), rho_p = qp.at(o, IS_RHO);
+    auto xm = [&](int ip) {
+        const double X = qm.at(o, IS_X + ip);
+        if (reset_m) return X;
+        return (rho_m * X - hdt * (area * Ft.at(ofm + sT_f, FX_X + ip) - area * Ft.at(ofm, FX_X + ip)) * volinv) / rrnew_m;
+    };
+    auto xp = [&](int ip) {
+        const double X = qp.at(o, IS_X + ip);
+        if (reset_p) return X;
+        return (rho_p * X - hdt * (area * Ft.at(ofp + sT_f, FX_X + ip) - area * Ft.at(ofp, FX_X + ip)) * volinv) / rrnew_p;
+    };
+    if (P.transverse_use_eos || P.transverse_reset_rhoe) {
+        edge_thermo_post<false>(P, qlo, eos_mu(P, [&](int n) { return xm(P.QFS_off + n); }), reset_m);
+        edge_thermo_post<false>(P, qro, eos_mu(P, [&](int n) { return xp(P.QFS_off + n); }), reset_p);
+    }
+    double F[6], ugd, pgd;
+    PassiveUpwind pu;
+    solve_face<N, EK>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu, fd);
+    // apply_av (advection_util.cpp:354-419) with dg1 = 1, dg2 = 0: the four-term average visits two nodes twice
+    const double* __restrict__ dv = fd.p + fd.idx(i, j, k) + fd.sn;
+    double div1;
+    if (N == 0) div1 = 0.25 * (dv[0] + dv[fd.sj] + dv[0] + dv[fd.sj]);
+    else div1 = 0.25 * (dv[0] + dv[1] + dv[0] + dv[1]);
+    div1 = P.difmag * smin(0.0, div1);
+    const double dL = P.dx[N];
+    const long ou = U.idx(i, j, k);
+    const long oum = ou - ((N == 0) ? 1 : U.sj);
+    const long of = Fo.idx(i, j, k);
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+        const double div_var = div1 * (U.at(ou, n) - U.at(oum, n));
+        F[n] += dL * div_var;
+        Fo.at(of, n) = F[n];
+    }
+    Fo.at(of, FX_UG) = ugd;
+    Fo.at(of, FX_PG) = pgd;
+    double sum = 0.0;
+    for (int ip = 0; ip < P.npassive; ++ip) {
+        double f = passive_flux(P, pu, xm(ip), xp(ip));
+        const double div_var = div1 * (U.at(ou, UFA + ip) - U.at(oum, UFA + ip));
+        f += dL * div_var;
+        Fo.at(of, FX_X + ip) = f;
+        if (ip >= P.QFS_off && ip < P.QFS_off + P.nspec) sum += f;
+    }
+    double fac = 1.0;
+    if (fabs(sum) > 2.220446049250313e-16 * fabs(F[0])) fac = F[0] / sum;
+    for (int n = 0; n < P.nspec; ++n) {
+        const int ip = P.QFS_off + n;
+        Fo.at(of, FX_X + ip) = Fo.at(of, FX_X + ip) * fac;
+    }
+}
+
 // trans_final (both states) + final Riemann solve + flux cleaning:
 //   Castro_ctu_hydro.cpp:925-961 / 1004-1042 / 1085-1123, then :1131-1172 (zero T flux, apply_av, normalize_species_fluxes)
 //   F1 = F^{T1|T2}, F2 = F^{T2|T1};  c1 = dt/(2 dx_T1), c2 = dt/(2 dx_T2)
@@ -1122,7 +1280,7 @@ __device__ __forceinline__ double estdt_zone(const DevPar& P, const double* __re
     const double c = s.cs;
     const double dt1 = P.dx[0] / (c + fabs(ux));
     const double dt2 = (P.dim == 1) ? dt1 : P.dx[1] / (c + fabs(uy));       // timestep.H:113-130: dt2 = dt3 = dt1 in 1-D
-    const double dt3 = (P.dim == 1) ? dt1 : P.dx[2] / (c + fabs(uz));
+    const double dt3 = (P.dim <= 2) ? dt1 : P.dx[2] / (c + fabs(uz));
     return amin(amin(dt1, dt2), dt3);
 }
 
@@ -1191,6 +1349,19 @@ static __global__ void __launch_bounds__(TPB) k_update(const DevPar P, const A4 
             for (int ip = 0; ip < P.npassive; ++ip) {
                 const int n = FX_X + ip;
                 Sn.at(on, UFA + ip) = Sin.at(oi, UFA + ip) + dt * (F0.at(f0, n) * a - F0.at(f0p, n) * a) * vi;
+            }
+        } else if (P.dim == 2) {   // AMREX_SPACEDIM == 2, Cartesian: volume = dx dy, area_x = dy, area_y = dx (Castro_util.H:236-248,324-342)
+            const double b0 = P.dx[1], b1 = P.dx[0], vi = 1.0 / (P.dx[0] * P.dx[1]);
+#pragma unroll
+            for (int n = 0; n < 6; ++n)
+                u[n] = Sin.at(oi, n) + dt * (F0.at(f0, n) * b0 - F0.at(f0p, n) * b0 + F1.at(f1, n) * b1 - F1.at(f1p, n) * b1) * vi;
+            double pdu = (F0.at(f0p, FX_PG) + F0.at(f0, FX_PG)) * (F0.at(f0p, FX_UG) * b0 - F0.at(f0, FX_UG) * b0);
+            pdu += (F1.at(f1p, FX_PG) + F1.at(f1, FX_PG)) * (F1.at(f1p, FX_UG) * b1 - F1.at(f1, FX_UG) * b1);
+            pdu = 0.5 * pdu * vi;
+            u[UEINT] = u[UEINT] - dt * pdu;
+            for (int ip = 0; ip < P.npassive; ++ip) {
+                const int n = FX_X + ip;
+                Sn.at(on, UFA + ip) = Sin.at(oi, UFA + ip) + dt * (F0.at(f0, n) * b0 - F0.at(f0p, n) * b0 + F1.at(f1, n) * b1 - F1.at(f1p, n) * b1) * vi;
             }
         } else {
 #pragma unroll

@@ -853,7 +853,7 @@ int ctu_sim_create(ctu_sim_t** out, const ctu_params_t* par, const ctu_geom_t* g
     ctu_sim* s = new ctu_sim();
     s->par = *par; s->geom = *geom;
     s->vbx = make_box(lo, hi);
-    s->gbx = growd(s->vbx, CTU_NGROW, geom->dim == 1 ? 1 : 3);
+    s->gbx = growd(s->vbx, CTU_NGROW, geom->dim == 1 ? 1 : geom->dim == 2 ? 2 : 3);
     s->nstate = ctu_num_state(par);
     s->st = (cudaStream_t)stream;
     const size_t bytes = (size_t)s->gbx.npts() * s->nstate * sizeof(double);
@@ -1216,7 +1216,7 @@ int ctu::sim_step_host_impl(ctu_sim* s, SimHooks* hooks, const double* host_in, 
     if (!hooks)      // a single box must be the whole domain; with hooks the other boxes' zones arrive through the exchanges
         for (int d = 0; d < 3; ++d)
             if (s->vbx.lo[d] != s->geom.domlo[d] || s->vbx.hi[d] != s->geom.domhi[d]) return CTU_ERR_UNSUPPORTED;
-    if (s->par.do_grav || s->geom.dim == 1) return CTU_ERR_UNSUPPORTED;     // the streamed step covers pure hydro in 3-D only
+    if (s->par.do_grav || s->geom.dim == 1 || s->geom.dim == 2) return CTU_ERR_UNSUPPORTED;     // the streamed step covers pure hydro in 3-D only
     const int nz = s->vbx.hi[2] - s->vbx.lo[2] + 1;
     const int zlo = s->vbx.lo[2], zhi = s->vbx.hi[2];
     ctu_fab_t sb = s->fab(s->cur), sn = s->fab(1 - s->cur);

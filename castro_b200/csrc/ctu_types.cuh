@@ -42,7 +42,7 @@ inline Box3 grow(Box3 b, int gx, int gy, int gz) {
 }
 inline Box3 grow(Box3 b, int g) { return grow(b, g, g, g); }
 // grow in the dimensions a run of `dim` dimensions has
-inline Box3 growd(Box3 b, int g, int dim) { return dim == 1 ? grow(b, g, 0, 0) : grow(b, g, g, g); }
+inline Box3 growd(Box3 b, int g, int dim) { return dim == 1 ? grow(b, g, 0, 0) : dim == 2 ? grow(b, g, g, 0) : grow(b, g, g, g); }
 inline Box3 intersect(Box3 a, const Box3& b) {
     for (int d = 0; d < 3; ++d) { a.lo[d] = a.lo[d] > b.lo[d] ? a.lo[d] : b.lo[d]; a.hi[d] = a.hi[d] < b.hi[d] ? a.hi[d] : b.hi[d]; }
     return a;

@@ -169,7 +169,8 @@ def tensor_fab(t, lo):
 
 
 def prob_string(d):
-    return " ".join("%s=%r" % (k, v) for k, v in d.items())
+    # arrays (problem.center = 0.5 0.5 0.0) are written v1,v2,v3
+    return " ".join("%s=%s" % (k, ",".join(repr(x) for x in v) if isinstance(v, (tuple, list)) else repr(v)) for k, v in d.items())
 
 
 class Workspace:

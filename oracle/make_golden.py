@@ -194,6 +194,53 @@ NOH_CASES = {
 }
 
 
+# the 2-D Cartesian path (DIM=2 builds of the reference): the cylindrical Sedov blast in Cartesian coordinates
+# (Exec/hydro_tests/Sedov/inputs.2d.cyl_in_cartcoords: outflow, CGF as shipped; also HLLC, CG, PLM, a non-square box, periodic) and
+# Kelvin-Helmholtz (Exec/hydro_tests/KH/inputs.2d: periodic, two passives)
+SEDOV2D_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro2d_sedov.ex")
+SEDOV2D_INPUTS = "/root/reference/Exec/hydro_tests/Sedov/inputs.2d.cyl_in_cartcoords"
+KH2D_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro2d_kh.ex")
+KH2D_INPUTS = "/root/reference/Exec/hydro_tests/KH/inputs.2d"
+CASES_2D = {
+    "sedov2d_cgf": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 40, [0, 1, 40], ["castro.riemann_solver=0"]),
+    "sedov2d_hllc": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 40, [0, 40], ["castro.riemann_solver=2"]),
+    "sedov2d_cg_24x16": (SEDOV2D_EXE, SEDOV2D_INPUTS, (24, 16), 30, [0, 30], ["castro.riemann_solver=1", "geometry.prob_hi=1.5 1.0"]),
+    "sedov2d_plm_hllc": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 30, [0, 30], ["castro.riemann_solver=2", "castro.ppm_type=0"]),
+    "sedov2d_hllc_eos": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 30, [0, 30], ["castro.riemann_solver=2", "castro.transverse_use_eos=1",
+                                                                           "castro.transverse_reset_rhoe=1"]),
+    "sedov2d_symm_cgf": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 60, [0, 60], ["castro.riemann_solver=0", "castro.lo_bc=3 3", "castro.hi_bc=4 2",
+                                                                           "geometry.prob_hi=0.5 0.5"]),
+    "kh2d_cgf": (KH2D_EXE, KH2D_INPUTS, (32, 32), 20, [0, 20], ["castro.riemann_solver=0"]),
+    "kh2d_hllc": (KH2D_EXE, KH2D_INPUTS, (32, 16), 20, [0, 20], ["castro.riemann_solver=2", "problem.bulk_velocity=0.3", "geometry.prob_hi=1.0 0.5"]),
+}
+
+
+def run_case_2d(name, exe, inputs, n_cell, max_step, snaps, extra):
+    wd = tempfile.mkdtemp(prefix="golden_")
+    try:
+        args = [exe, inputs, "amr.max_level=0", "amr.n_cell=%d %d" % n_cell, "amr.max_grid_size=16", "amr.blocking_factor=8",
+                "max_step=%d" % max_step, "stop_time=1.e9", "amr.plot_int=1", "amr.plot_per=-1", "amr.check_int=-1", "amr.check_per=-1",
+                "amr.derive_plot_vars=NONE", "castro.sum_interval=-1", "amr.plot_file=plt", "castro.v=0", "amr.v=0"] + extra
+        out = subprocess.run(args, cwd=wd, capture_output=True, text=True)
+        if out.returncode != 0:
+            print(out.stdout[-3000:], out.stderr[-3000:])
+            raise RuntimeError(name)
+        times, states = [], {}
+        for s in range(max_step + 1):
+            pf = os.path.join(wd, "plt%05d" % s)
+            h = read_header(pf)
+            times.append(h["time"])
+            if s in snaps:
+                h, U = read_plotfile(pf)
+                states["U%d" % s] = U
+        meta = dict(n_cell=np.array(n_cell + (1,)), times=np.array(times), names=np.array(h["names"]), problo=np.array(h["problo"]),
+                    probhi=np.array(h["probhi"]), overrides=np.array(extra), inputs=np.array(os.path.basename(inputs)))
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **meta, **states)
+        print(name, "ok: steps", max_step, "t_end", times[-1])
+    finally:
+        shutil.rmtree(wd)
+
+
 def run_case_1d(name, inp, nx, max_step, snaps, extra):
     wd = tempfile.mkdtemp(prefix="golden_")
     try:
@@ -243,6 +290,10 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case(name, n, ms, snaps, extra, exe=NOH_EXE, inputs=NOH_INPUTS)
+    for name, (exe, inp, n, ms, snaps, extra) in CASES_2D.items():
+        if only and name not in only:
+            continue
+        run_case_2d(name, exe, inp, n, ms, snaps, extra)
     for name, (inp, nx, ms, snaps, extra) in SOD1D_CASES.items():
         if only and name not in only:
             continue

@@ -230,3 +230,42 @@ def load_noh_case(name):
     geom = abi.make_geom(n_cell, probhi=tuple(float(x) for x in g["probhi"]), lo_bc=(3, 3, 3), hi_bc=c["hi_bc"])
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
     return par, geom, {}, g, snaps
+
+
+# the 2-D Cartesian path (geom.dim = 2; the reference built with DIM=2): Exec/hydro_tests/Sedov/inputs.2d.cyl_in_cartcoords and
+# Exec/hydro_tests/KH/inputs.2d; goldens from oracle/make_golden.py CASES_2D
+CASES_2D = {
+    "sedov2d_cgf": dict(kind="sedov", solver=0),
+    "sedov2d_hllc": dict(kind="sedov", solver=2),
+    "sedov2d_cg_24x16": dict(kind="sedov", solver=1),
+    "sedov2d_plm_hllc": dict(kind="sedov", solver=2, par=dict(ppm_type=0)),
+    "sedov2d_hllc_eos": dict(kind="sedov", solver=2, par=dict(transverse_use_eos=1, transverse_reset_rhoe=1)),
+    "sedov2d_symm_cgf": dict(kind="sedov", solver=0, lo_bc=(3, 3, 2), hi_bc=(4, 2, 2)),
+    "kh2d_cgf": dict(kind="kh", solver=0, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0, center=(0.5, 0.5, 0.0))),
+    "kh2d_hllc": dict(kind="kh", solver=2, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.3, center=(0.5, 0.5, 0.0))),
+}
+
+
+def load_2d_case(name):
+    c = CASES_2D[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    par = abi.default_params()
+    par.riemann_solver = c["solver"]
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    probhi = (float(g["probhi"][0]), float(g["probhi"][1]), 1.0)
+    if c["kind"] == "sedov":
+        par.cfl, par.init_shrink, par.change_max = 0.5, 0.01, 1.1
+        par.eos_gamma, par.eos_assume_neutral = 1.4, 1
+        geom = abi.make_geom(n_cell, probhi=probhi, lo_bc=c.get("lo_bc", (2, 2, 2)), hi_bc=c.get("hi_bc", (2, 2, 2)), dim=2)
+        prob = dict(r_init=0.01, p_ambient=1.e-6, exp_energy=1.0, dens_ambient=1.0, nsub=10)
+    else:
+        par.cfl, par.init_shrink, par.change_max = 0.5, 0.1, 1.1
+        par.small_temp, par.small_dens = 1.e-9, 1.e-4
+        par.eos_assume_neutral = 1
+        par.nadv, par.nspec = 1, 1
+        geom = abi.make_geom(n_cell, probhi=probhi, periodic=(1, 1, 0), lo_bc=(0, 0, 2), hi_bc=(0, 0, 2), dim=2)
+        prob = c["prob"]
+    for k, v in c.get("par", {}).items():
+        setattr(par, k, v)
+    snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
+    return par, geom, prob, g, snaps

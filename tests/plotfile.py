@@ -26,6 +26,11 @@ def read_header(pf):
         dom = re.findall(r"\((-?\d+),(-?\d+),(-?\d+)\)", dline)
         domlo = [int(x) for x in dom[0]]
         domhi = [int(x) for x in dom[1]]
+    elif dim == 2:      # ((lox,loy) (hix,hiy) (0,0))
+        dom = re.findall(r"\((-?\d+),(-?\d+)\)", dline)
+        domlo = [int(dom[0][0]), int(dom[0][1]), 0]
+        domhi = [int(dom[1][0]), int(dom[1][1]), 0]
+        problo, probhi = problo + [0.0], probhi + [0.0]
     else:       # 1-D: ((lo) (hi) (0))
         dom = re.findall(r"\((-?\d+)\)", dline)
         domlo = [int(dom[0]), 0, 0]
@@ -39,12 +44,14 @@ def read_header(pf):
 
 def read_plotfile(pf):
     h = read_header(pf)
-    assert h["finest"] == 0 and h["dim"] in (1, 3)
+    assert h["finest"] == 0 and h["dim"] in (1, 2, 3)
     lev = os.path.join(pf, "Level_0")
     with open(os.path.join(lev, "Cell_H")) as f:
         txt = f.read()
     if h["dim"] == 3:
         boxes = re.findall(r"\(\((-?\d+),(-?\d+),(-?\d+)\) \((-?\d+),(-?\d+),(-?\d+)\) \(0,0,0\)\)", txt)
+    elif h["dim"] == 2:
+        boxes = [(a, b, "0", c, d, "0") for a, b, c, d in re.findall(r"\(\((-?\d+),(-?\d+)\) \((-?\d+),(-?\d+)\) \(0,0\)\)", txt)]
     else:
         boxes = [(a, "0", "0", b, "0", "0") for a, b in re.findall(r"\(\((-?\d+)\) \((-?\d+)\) \(0\)\)", txt)]
     fods = re.findall(r"FabOnDisk: (\S+) (\d+)", txt)

@@ -983,3 +983,52 @@ def test_exact_replay_path_is_exercised():
     for m in (0, 1, 2, 3, 4, 5, 7):
         assert np.array_equal(U0[m], U1[m]), "a uniform state at rest must stay exactly as it is (comp %d)" % m
     sim.close()
+
+
+from cases import CASES_2D
+
+
+@pytest.mark.parametrize("name", sorted(CASES_2D))
+def test_two_dimensional_matches_reference(name):
+    """The 2-D Cartesian path (geom.dim = 2; the reference built with DIM=2): the reference's unmodified problem headers compiled for
+    AMREX_SPACEDIM = 2 give the initial plotfile, then the full time loop against the reference's states and times, bit for bit
+    (Sedov cylindrical blast in Cartesian coordinates: CGF / HLLC / Colella & Glaz, PLM, EOS edge states, symmetry + wall + outflow
+    boundaries, a non-square box; Kelvin-Helmholtz: periodic, two passives)."""
+    _torch()
+    import os
+    from castro_b200 import lib
+    from cases import load_2d_case
+    par, geom, prob, g, snaps = load_2d_case(name)
+    lib.params_finalize(par)
+    nx, ny = int(g["n_cell"][0]), int(g["n_cell"][1])
+    sim = lib.Sim(par, geom, (0, 0, 0), (nx - 1, ny - 1, 0))
+    hook = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "castro_b200", "hooks",
+                        "libctu_hook_%s.so" % ("sedov2d" if name.startswith("sedov") else "kh2d"))
+    if os.path.exists(hook):
+        sim.init_problem("hook:" + hook, prob)
+        assert_bitwise(sim.download(), g["U0"], name + " initial data")
+    else:
+        sim.upload(g["U0"])
+    t, dt, step, times = 0.0, -1.0, 0, [0.0]
+    for s in snaps[1:]:
+        rc, t, dt, hist = sim.advance(s - step, time=t, dt=dt)
+        assert rc == 0 and len(hist) == s - step
+        times += list(times[-1] + np.cumsum(hist))
+        step = s
+        assert_bitwise(sim.download(), g["U%d" % s], "%s step %d" % (name, s))
+    np.testing.assert_allclose(np.array(times), g["times"][:len(times)], rtol=1e-14, atol=0)
+    assert not sim.tile_staged
+    sim.close()
+
+
+def test_two_dimensional_unsupported_options_are_refused():
+    _torch()
+    from castro_b200 import lib
+    from cases import load_2d_case
+    par, geom, prob, g, snaps = load_2d_case("sedov2d_cgf")
+    for k in ("hybrid_riemann", "limit_fluxes_on_small_dens", "use_pslope", "do_grav"):
+        par, geom, prob, g, snaps = load_2d_case("sedov2d_cgf")
+        setattr(par, k, 1)
+        lib.params_finalize(par)
+        with pytest.raises(lib.CtuError):
+            lib.Sim(par, geom, (0, 0, 0), (31, 31, 0))

@@ -121,3 +121,30 @@ def test_oracle_sod_1d_matches_golden(name):
     np.testing.assert_allclose(np.cumsum(np.concatenate([[0.0], hist])), g["times"][:n + 1], rtol=1e-14, atol=0)
     if name == "sod1d_cgf":
         assert t == 0.2
+
+
+from cases import CASES_2D
+
+
+@pytest.mark.parametrize("name", sorted(CASES_2D))
+def test_oracle_two_dimensional_matches_golden(name):
+    """The 2-D Cartesian path (the reference built with DIM=2; Castro_ctu_hydro.cpp:530-650: one transverse correction per direction in
+    the area / volume form of trans.cpp, 2-D div u, two-node artificial viscosity average, dx dy volumes): the oracle, started from the
+    reference's initial plotfile, against the reference's states and times, bit for bit"""
+    import oracle_lib as O
+    from cases import load_2d_case
+    par, geom, prob, g, snaps = load_2d_case(name)
+    O.params_finalize(par)
+    U0 = g["U0"]
+    ng = 4
+    ny, nx = U0.shape[2], U0.shape[3]
+    U = np.zeros((U0.shape[0], 1 + 2 * ng, ny + 2 * ng, nx + 2 * ng))
+    U[:, ng, ng:-ng, ng:-ng] = U0[:, 0]
+    t, dt, step, times = 0.0, -1.0, 0, [0.0]
+    for s in snaps[1:]:
+        st, t, dt, hist = O.run(par, geom, U, s - step, time=t, dt=dt)
+        assert st == 0 and len(hist) == s - step
+        times += list(times[-1] + np.cumsum(hist))
+        step = s
+        assert np.array_equal(U[:, ng, ng:-ng, ng:-ng], g["U%d" % s][:, 0]), "%s step %d" % (name, s)
+    np.testing.assert_allclose(np.array(times), g["times"][:len(times)], rtol=1e-14, atol=0)

@@ -24,7 +24,8 @@ def hook_path(name):
 
 
 def prob_string(d):
-    return " ".join("%s=%r" % (k, v) for k, v in d.items())
+    # arrays (problem.center = 0.5 0.5 0.0) are written v1,v2,v3
+    return " ".join("%s=%s" % (k, ",".join(repr(x) for x in v) if isinstance(v, (tuple, list)) else repr(v)) for k, v in d.items())
 
 
 # (hook library, problem name of the built-in kernels, golden with the reference's initial plotfile, loader)
@@ -170,3 +171,25 @@ def test_noh_with_bc_hook_on_gpu(name):
         assert np.array_equal(sim.download(), g["U%d" % s]), "%s step %d" % (name, s)
     np.testing.assert_allclose(np.array(times), g["times"][:len(times)], rtol=1e-14, atol=0)
     sim.close()
+
+
+# ---- the same problem headers compiled for AMREX_SPACEDIM = 2 (libctu_hook_sedov2d / kh2d) ---------------------------------------------
+HOOK_CASES_2D = [("sedov2d", "sedov2d_cgf"), ("sedov2d", "sedov2d_cg_24x16"), ("sedov2d", "sedov2d_symm_cgf"), ("kh2d", "kh2d_cgf"),
+                 ("kh2d", "kh2d_hllc")]
+
+
+@pytest.mark.parametrize("hook,golden", HOOK_CASES_2D)
+def test_reference_hook_reproduces_reference_initial_plotfile_2d(hook, golden):
+    import oracle_lib as O
+    from cases import load_2d_case
+    par, geom, prob, g, snaps = load_2d_case(golden)
+    O.params_finalize(par)
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    L = C.CDLL(hook_path(hook))
+    U = np.full((par.num_state, 1, n_cell[1], n_cell[0]), np.nan)
+    lo, hi = abi.Int3(0, 0, 0), abi.Int3(n_cell[0] - 1, n_cell[1] - 1, 0)
+    L.ctu_hook_init.argtypes = HOOK_ARGS
+    assert L.ctu_hook_init(prob_string(prob).encode(), C.byref(par), C.byref(geom), lo, hi, U.ctypes.data, lo, hi) == 0
+    f = O.fab(U, (0, 0, 0))
+    O.lib().orc_init_tail(C.byref(par), C.byref(geom), lo, hi, C.byref(f))
+    assert np.array_equal(U, g["U0"]), "hook %s vs the reference's plt00000 of %s" % (hook, golden)
