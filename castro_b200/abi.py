@@ -101,7 +101,7 @@ def default_params():
     return p
 
 
-def make_geom(n_cell, problo=(0, 0, 0), probhi=(1, 1, 1), periodic=(0, 0, 0), lo_bc=(2, 2, 2), hi_bc=(2, 2, 2), dim=3):
+def make_geom(n_cell, problo=(0, 0, 0), probhi=(1, 1, 1), periodic=(0, 0, 0), lo_bc=(2, 2, 2), hi_bc=(2, 2, 2), dim=3, coord=0):
     """dim = 1: the 1-D Cartesian path (n_cell = (nx, 1, 1); y and z carry one zone and no ghost zones)"""
     g = Geom()
     g.dim = dim
@@ -115,5 +115,5 @@ def make_geom(n_cell, problo=(0, 0, 0), probhi=(1, 1, 1), periodic=(0, 0, 0), lo
         g.periodic[d] = periodic[d]
         g.lo_bc[d] = lo_bc[d]
         g.hi_bc[d] = hi_bc[d]
-    g.coord = 0
+    g.coord = coord          # geometry.coord_sys: 0 Cartesian, 1 cylindrical / 2 spherical radial coordinate (1-D runs)
     return g

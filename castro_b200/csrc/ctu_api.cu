@@ -132,7 +132,9 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
         P.aion_inv[n] = (n < par->nspec) ? 1.0 / par->aion[n] : 0.0;
         P.zion[n] = (n < par->nspec) ? par->zion[n] : 0.0;
     }
+    P.coord = 0; P.problo0 = 0.0;
     if (geom) {
+        if (geom->dim == 1) { P.coord = geom->coord; P.problo0 = geom->problo[0]; }
         for (int d = 0; d < 3; ++d) {
             P.dx[d] = geom->dx[d];
             P.domlo[d] = geom->domlo[d]; P.domhi[d] = geom->domhi[d];
@@ -160,7 +162,8 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     // with the Helmholtz EOS: the PPM / PLM path with the three Riemann solvers; the options that call the EOS on edge states and the
     // constant-gravity driver are instantiated for the gamma law only
     if (p->eos_kind == 1 && (p->transverse_use_eos || p->transverse_reset_rhoe || p->ppm_temp_fix || p->do_grav)) return CTU_ERR_UNSUPPORTED;
-    if (g && g->coord != 0) return CTU_ERR_UNSUPPORTED;
+    // curvilinear coordinates: the radial coordinate of a cylinder (1) or a sphere (2) in ONE dimension; 2-D R-Z / R-theta are not built
+    if (g && g->coord != 0 && !(g->dim == 1 && (g->coord == 1 || g->coord == 2))) return CTU_ERR_UNSUPPORTED;
     if (g && g->dim != 0 && g->dim != 1 && g->dim != 2 && g->dim != 3) return CTU_ERR_BAD_ARG;
     if (g && g->dim == 2) {
         // the 2-D Cartesian path (Castro_ctu_hydro.cpp:530-650): one zone in z; PPM / PLM, the three Riemann solvers, any passives, the
@@ -676,7 +679,8 @@ int hydro_box_1d(HydroRun* r) {
     const Box3 tb = r->vbx;
     const Box3 qbx = grow(tb, 4, 0, 0), obx = grow(tb, 1, 0, 0);
     Box3 ibx = obx; ibx.hi[0] += 1;
-    const size_t need = ((size_t)qbx.npts() * NQS + (size_t)ibx.npts() * (2 + 2 * NIS + NFX)) * sizeof(double);
+    const Box3 sbx = grow(tb, 3, 0, 0);
+    const size_t need = ((size_t)qbx.npts() * NQS + (size_t)ibx.npts() * (2 + 2 * NIS + NFX) + (size_t)sbx.npts() * NSRCQ) * sizeof(double);
     int rc = ws_reserve_bytes(ws, need, st);
     if (rc) return rc;
     double* p = ws->arena;
@@ -695,8 +699,16 @@ int hydro_box_1d(HydroRun* r) {
     lb = make_lb(obx);
     k_flat_div_1d<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb);
     // the node-centred div u is needed on the faces lo .. hi+1: one more than obx holds on the high side is not (obx = lo-1 .. hi+1)
-    if (P.ppm_type == 0) k_trace_plm<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none);
-    else k_trace<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none, ws->d_counters + 5);
+    if (P.ppm_type == 0) k_trace_plm<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none);      // adds its own geometry terms
+    else if (P.coord != 0) {
+        // curvilinear radial coordinate: the geometric source terms are traced like any primitive source (trace_ppm.cpp:320-405)
+        const A4 gsrc = make_a4(p, sbx); p += sbx.npts() * NSRCQ;
+        CUDA_TRY(cudaMemsetAsync(ws->d_counters + 5, 0, sizeof(int), st));
+        const LaunchBox ls = make_lb(sbx);
+        k_geom_src_1d<<<nblocks(ls.n), TPB, 0, st>>>(P, qs, gsrc, ls, ws->d_counters + 5);
+        k_trace<0, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, gsrc, ws->d_counters + 5);
+        ++r->launches;
+    } else k_trace<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none, ws->d_counters + 5);
     Box3 xbx = tb; xbx.hi[0] += 1;
     lb = make_lb(xbx);
     k_riemann1<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F0, lb, fd);

@@ -151,7 +151,31 @@ static __global__ void __launch_bounds__(TPB) k_flat_div(const DevPar P, const A
     }
 }
 
-// 1-D (AMREX_SPACEDIM == 1): flattening along x only (flatten.H:141-150), div(i) = (u_i - u_{i-1}) / dx (advection_util.cpp:228-231)
+constexpr int NSRCQ = 6;      // primitive source components kept: rho u v w p (rho e)
+
+// 1-D curvilinear geometry (radial coordinate of a cylinder, P.coord 1, or of a sphere, 2): dLogArea of AMReX (amrex_setdloga,
+// AMReX_COORDSYS_1D_C.H:97-127), face area and zone volume of Castro_util.H:183-235,296-320 (identical to AMReX's amrex_setarea)
+constexpr double CTU_PI = 3.141592653589793238462643383279502884;
+__host__ __device__ __forceinline__ double dloga_1d(const DevPar& P, int i) {
+    if (P.coord == 0) return 0.0;
+    const double rc = P.problo0 + P.dx[0] * (i + 0.5);
+    return (P.coord == 1) ? 1.0 / rc : 2.0 / rc;
+}
+__host__ __device__ __forceinline__ double area_1d(const DevPar& P, int i) {
+    if (P.coord == 0) return 1.0;
+    const double r = P.problo0 + static_cast<double>(i) * P.dx[0];
+    return (P.coord == 1) ? fabs(2.0 * CTU_PI * r) : fabs(4.0 * CTU_PI * r * r);
+}
+__host__ __device__ __forceinline__ double volume_1d(const DevPar& P, int i) {
+    if (P.coord == 0) return P.dx[0];
+    const double rl = P.problo0 + static_cast<double>(i) * P.dx[0];
+    const double rr = rl + P.dx[0];
+    if (P.coord == 1) return fabs(CTU_PI * P.dx[0] * (rr + rl));
+    return fabs((4.0 / 3.0) * CTU_PI * P.dx[0] * (rl * rl + rl * rr + rr * rr));
+}
+
+// 1-D (AMREX_SPACEDIM == 1): flattening along x only (flatten.H:141-150); div u of advection_util.cpp:228-255: (u_i - u_{i-1}) / dx in
+// Cartesian coordinates, (r_r^a u_i - r_l^a u_{i-1}) / (dx r_c^a) with a = 1 (cylindrical) or 2 (spherical), 0 at the node i = 0
 static __global__ void __launch_bounds__(TPB) k_flat_div_1d(const DevPar P, const A4 qs, const A4 fd, const LaunchBox lb) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
@@ -163,7 +187,37 @@ static __global__ void __launch_bounds__(TPB) k_flat_div_1d(const DevPar P, cons
     else if (P.use_flattening) flatn = flatten_dir([&](int s) { return pp[s]; }, [&](int s) { return uu[s]; });
     fd.at(of, 0) = flatn;
     const double dxinv = 1.0 / P.dx[0];
-    fd.at(of, 1) = (uu[0] - uu[-1]) * dxinv;
+    if (P.coord == 0) fd.at(of, 1) = (uu[0] - uu[-1]) * dxinv;
+    else if (i == 0) fd.at(of, 1) = 0.0;
+    else {
+        const double rl = (i - 0.5) * P.dx[0] + P.problo0;
+        const double rr = (i + 0.5) * P.dx[0] + P.problo0;
+        const double rc = (i) * P.dx[0] + P.problo0;
+        if (P.coord == 1) fd.at(of, 1) = (rr * uu[0] - rl * uu[-1]) * dxinv / rc;
+        else fd.at(of, 1) = (rr * rr * uu[0] - rl * rl * uu[-1]) * dxinv / (rc * rc);
+    }
+}
+
+// 1-D curvilinear: the geometric source terms of the primitive system, -alpha rho u / r, -alpha Gamma1 p u / r, -alpha (rho e + p) u / r
+// with alpha / r = dloga (reconstruction.H:84-210), as a primitive-source array for the source tracing of k_trace ("0.0 +": the
+// reference adds them to the stencil of a zero src_q); sets the non-zero-component mask like k_src_to_prim
+static __global__ void __launch_bounds__(TPB) k_geom_src_1d(const DevPar P, const A4 qs, const A4 srcq, const LaunchBox lb, int* __restrict__ src_mask) {
+    int i, j, k;
+    if (!thread_zone(lb, i, j, k)) return;
+    const long oq = qs.idx(i, j, k), os = srcq.idx(i, j, k);
+    const double dlg = dloga_1d(P, i);
+    const double rho = qs.at(oq, QS_RHO), u = qs.at(oq, QS_U), p = qs.at(oq, QS_P), re = qs.at(oq, QS_RE);
+    const double gamc = P.gamc_const ? P.gamma : qs.at(oq, QS_GAMC);
+    const double s_rho = 0.0 + -dlg * rho * u;
+    const double s_p = 0.0 + -dlg * p * gamc * u;
+    const double s_re = 0.0 + -dlg * (re + p) * u;
+    for (int n = 0; n < NSRCQ; ++n) srcq.at(os, n) = 0.0;
+    srcq.at(os, QS_RHO) = s_rho; srcq.at(os, QS_P) = s_p; srcq.at(os, QS_RE) = s_re;
+    int m = 0;
+    if (fabs(s_rho) > 0.0) m |= 1 << QS_RHO;
+    if (fabs(s_p) > 0.0) m |= 1 << QS_P;
+    if (fabs(s_re) > 0.0) m |= 1 << QS_RE;
+    if (m) atomicOr(src_mask, m);
 }
 
 // 1-D: the final x flux IS the first-pass flux; what k_final does after its Riemann solve is applied here in place:
@@ -172,6 +226,9 @@ static __global__ void __launch_bounds__(TPB) k_av_1d(const DevPar P, const A4 f
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
     const long of = F.idx(i, j, k), od = fd.idx(i, j, k), ou = U.idx(i, j, k);
+    // curvilinear radial coordinate: the momentum flux carries no pressure (mom_flux_has_p, Castro_util.H:62-96; compute_flux_q,
+    // riemann_solvers.H:52-58): F(rho u) = F(rho) * u_gdnv, the very product the solve formed before it added p
+    if (P.coord != 0) F.at(of, FX_MX) = F.at(of, FX_RHO) * F.at(of, FX_UG);
     const double d = fd.at(od, 1);
     double div1 = 0.25 * (d + d + d + d);
     div1 = P.difmag * smin(0.0, div1);
@@ -222,7 +279,6 @@ static __global__ void __launch_bounds__(TPB) k_flat_div_2d(const DevPar P, cons
 // Source terms in the tracing: hydro::src_to_prim (advection_util.H:16-79) and the traced primitive sources of
 // trace_ppm (trace_ppm.cpp:309-440).  srcq scratch layout: rho u v w p (rho e)  (reference src_q minus the unused QTEMP slot).
 // ------------------------------------------------------------------------------------------------
-constexpr int NSRCQ = 6;
 
 // one thread = one zone of grow(slab, 3)
 template <int EK = 0>
@@ -753,6 +809,29 @@ static __global__ void __launch_bounds__(TPB) k_trace_plm(const DevPar P, const 
         if (refl_hi) {
             qp.at(om, IS_RHO) = o_rho; qp.at(om, IUN) = -o_un; qp.at(om, IUT) = o_ut; qp.at(om, IUTT) = o_utt;
             qp.at(om, IS_P) = o_p; qp.at(om, IS_RE) = o_re;
+        }
+    }
+    if (DIR == 0 && P.dim == 1 && P.coord != 0) {      // geometry source terms of the x states (trace_plm.cpp:321-357)
+        const double dlg = dloga_1d(P, i);
+        if (dlg != 0.0) {
+            const double courn = dtdL * (cc + fabs(un));
+            const double eta = (1.0 - courn) / (cc * dt * fabs(dlg));
+            const double dlogatmp = smin(eta, 1.0) * dlg;
+            const double sourcr = -0.5 * dt * rho * dlogatmp * un;
+            const double sourcp = sourcr * csq;
+            const double source = sourcp * enth;
+            if (idx <= ta.vhi[DIR]) {
+                qm.at(om, IS_RHO) = amax(qm.at(om, IS_RHO) + sourcr, P.small_dens);
+                qm.at(om, IS_P) += sourcp;
+                qm.at(om, IS_RE) += source;
+                if (refl_hi) { qp.at(om, IS_RHO) = qm.at(om, IS_RHO); qp.at(om, IS_P) = qm.at(om, IS_P); qp.at(om, IS_RE) = qm.at(om, IS_RE); }
+            }
+            if (idx >= ta.vlo[DIR]) {
+                qp.at(op, IS_RHO) = amax(qp.at(op, IS_RHO) + sourcr, P.small_dens);
+                qp.at(op, IS_P) += sourcp;
+                qp.at(op, IS_RE) += source;
+                if (refl_lo) { qm.at(op, IS_RHO) = qp.at(op, IS_RHO); qm.at(op, IS_P) = qp.at(op, IS_P); qm.at(op, IS_RE) = qp.at(op, IS_RE); }
+            }
         }
     }
     for (int ip = 0; ip < P.npassive; ++ip) {   // trace_plm.cpp:361-389
@@ -1340,15 +1419,18 @@ static __global__ void __launch_bounds__(TPB) k_update(const DevPar P, const A4 
         double u[7];
         const double rho_old = Sb.at(ob, URHO);
         if (P.dim == 1) {   // consup_hydro with AMREX_SPACEDIM == 1: volume = dx, area = 1 (Castro_util.H:205-213, 295-303); only F0 exists
-            const double vi = 1.0 / P.dx[0], a = 1.0;
+            // curvilinear radial coordinate (P.coord 1, 2): r-dependent face areas and volume, and the grad p term of the radial momentum,
+            // whose flux carries no pressure (Castro_ctu.cpp:66-70)
+            const double vi = 1.0 / volume_1d(P, i), al = area_1d(P, i), ar = area_1d(P, i + 1);
 #pragma unroll
-            for (int n = 0; n < 6; ++n) u[n] = Sin.at(oi, n) + dt * (F0.at(f0, n) * a - F0.at(f0p, n) * a) * vi;
-            double pdu = (F0.at(f0p, FX_PG) + F0.at(f0, FX_PG)) * (F0.at(f0p, FX_UG) * a - F0.at(f0, FX_UG) * a);
+            for (int n = 0; n < 6; ++n) u[n] = Sin.at(oi, n) + dt * (F0.at(f0, n) * al - F0.at(f0p, n) * ar) * vi;
+            double pdu = (F0.at(f0p, FX_PG) + F0.at(f0, FX_PG)) * (F0.at(f0p, FX_UG) * ar - F0.at(f0, FX_UG) * al);
             pdu = 0.5 * pdu * vi;
             u[UEINT] = u[UEINT] - dt * pdu;
+            if (P.coord != 0) u[UMX] += -dt * (F0.at(f0p, FX_PG) - F0.at(f0, FX_PG)) / P.dx[0];
             for (int ip = 0; ip < P.npassive; ++ip) {
                 const int n = FX_X + ip;
-                Sn.at(on, UFA + ip) = Sin.at(oi, UFA + ip) + dt * (F0.at(f0, n) * a - F0.at(f0p, n) * a) * vi;
+                Sn.at(on, UFA + ip) = Sin.at(oi, UFA + ip) + dt * (F0.at(f0, n) * al - F0.at(f0p, n) * ar) * vi;
             }
         } else if (P.dim == 2) {   // AMREX_SPACEDIM == 2, Cartesian: volume = dx dy, area_x = dy, area_y = dx (Castro_util.H:236-248,324-342)
             const double b0 = P.dx[1], b1 = P.dx[0], vi = 1.0 / (P.dx[0] * P.dx[1]);
@@ -1418,7 +1500,8 @@ template <int DIR>
 static __global__ void __launch_bounds__(TPB) k_store_flux(const DevPar P, const A4 F, const A4 fo, const A4 mo, const LaunchBox lb, const double dt) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
-    const double area = (DIR == 0) ? P.dx[1] * P.dx[2] : (DIR == 1) ? P.dx[0] * P.dx[2] : P.dx[0] * P.dx[1];
+    double area = (DIR == 0) ? P.dx[1] * P.dx[2] : (DIR == 1) ? P.dx[0] * P.dx[2] : P.dx[0] * P.dx[1];
+    if (DIR == 0 && P.dim == 1 && P.coord != 0) area = area_1d(P, i);      // the face area of a radial coordinate (amrex_setarea)
     const long of = F.idx(i, j, k);
     if (fo.p) {
         const long oo = fo.idx(i, j, k);

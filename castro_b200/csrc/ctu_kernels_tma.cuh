@@ -21,6 +21,16 @@ namespace ctu {
 #ifndef CTU_TRACE_MINB
 #define CTU_TRACE_MINB 3
 #endif
+// resident CTAs per SM of the trace kernels that carry traced source terms (SRC instances: 24 more live doubles per thread)
+// (measured, RT at 512^3: 2 CTAs / SM at 112 registers instead of 3 at 72-80 with ~1 KB of spills -- k_trace 89.9 -> 72.1 ms/step with 4
+// species, 60.2 -> 57.3 with one)
+#ifndef CTU_TRACE_MINB_SRC
+#define CTU_TRACE_MINB_SRC 2
+#endif
+// ... and of the source-free instances with three or more passive scalars (developer switch)
+#ifndef CTU_TRACE_MINB_NP3
+#define CTU_TRACE_MINB_NP3 CTU_TRACE_MINB
+#endif
 #ifndef CTU_TMA_MINB
 #define CTU_TMA_MINB 4
 #endif
@@ -44,6 +54,12 @@ constexpr int UTY = 4, UTZ = 2, UTTHR = TX * UTY * UTZ;                        /
 #define CTU_TMA_MINB_NP2 3
 #endif
 template <int NP> struct TmaMinB { static constexpr int value = (NP == 1) ? CTU_TMA_MINB : (NP <= 4) ? CTU_TMA_MINB_NP2 : 2; };
+// k_trans2_tma with an x or y normal and one passive stages 43 KB per CTA: a fifth CTA fits the SM's shared memory (developer switch;
+// the z-normal tiles and k_final_tma stage more)
+#ifndef CTU_TMA_MINB_T2XY
+#define CTU_TMA_MINB_T2XY CTU_TMA_MINB
+#endif
+template <int N, int NP> struct Trans2MinB { static constexpr int value = (NP == 1 && N != 2) ? CTU_TMA_MINB_T2XY : TmaMinB<NP>::value; };
 constexpr int ceven(int n) { return (n + 1) & ~1; }
 constexpr size_t al128(size_t b) { return (b + 127) & ~(size_t)127; }
 
@@ -351,7 +367,7 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
 }
 
 template <int N, int NP, int RS = 0>
-static __global__ void __launch_bounds__(TTHR, TmaMinB<NP>::value)
+static __global__ void __launch_bounds__(TTHR, (RS == 0 ? Trans2MinB<N, NP>::value : TmaMinB<NP>::value))
 k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __grid_constant__ CUtensorMap m_qp,
              const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f1b, const __grid_constant__ CUtensorMap m_f2,
              const __grid_constant__ CUtensorMap m_f2b, const __grid_constant__ CUtensorMap m_c,
@@ -1356,7 +1372,7 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
 }
 
 template <int D, int NP, bool SRC, int RS = 0, int REC = 0>
-static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, CTU_TRACE_MINB)
+static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, SRC ? CTU_TRACE_MINB_SRC : (NP >= 3 ? CTU_TRACE_MINB_NP3 : CTU_TRACE_MINB))
 k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, const TraceRiemannArgs a) {
     using L = TraceSmem<D, NP>;
     using TT = TrTile<D>;

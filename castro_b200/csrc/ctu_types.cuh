@@ -98,6 +98,8 @@ struct DevPar {
     double aion_inv[CTU_MAX_SPEC], zion[CTU_MAX_SPEC];
     // geometry
     double dx[3];
+    int coord;                   // geometry.coord_sys of a 1-D run: 0 Cartesian, 1 cylindrical, 2 spherical radial coordinate
+    double problo0;              // geometry.prob_lo[0] (radius of the inner edge of zone 0)
     int domlo[3], domhi[3];
     int lo_bc[3], hi_bc[3], periodic[3];
     // diagnostics: number of CTAs that replayed their tile with the exact division / sqrt operators (nullptr = do not count)

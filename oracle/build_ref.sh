@@ -63,6 +63,7 @@ if [ "$what" = sodstellar ]; then build Sod_stellar Castro3d_sodstellar DIM=3 US
 # the literal BASELINE config[0]: Sod in ONE dimension (DIM=1), golden generator for the 1-D path
 if [ "$what" = sod1d ]; then build Sod Castro1d_sod DIM=1; fi
 # 2-D Cartesian path (AMREX_SPACEDIM == 2): Sedov (cylindrical blast in Cartesian coordinates, inputs.2d.cyl_in_cartcoords) and KH (inputs.2d)
+if [ "$what" = sedov1d ]; then build Sedov Castro1d_sedov DIM=1; fi      # 1-D spherical / cylindrical Sedov (inputs.1d.sph, inputs.1d.cyl): the non-Cartesian 1-D terms
 if [ "$what" = sedov2d ]; then build Sedov Castro2d_sedov DIM=2; fi
 if [ "$what" = kh2d ]; then build KH Castro2d_kh DIM=2; fi
 if [ "$what" = all ] || [ "$what" = sod ];    then build Sod Castro3d_sod DIM=3; fi

@@ -241,10 +241,24 @@ def run_case_2d(name, exe, inputs, n_cell, max_step, snaps, extra):
         shutil.rmtree(wd)
 
 
-def run_case_1d(name, inp, nx, max_step, snaps, extra):
+# 1-D curvilinear coordinates (the reference's DIM=1 Sedov executable): the spherical blast of Exec/hydro_tests/Sedov/inputs.1d.sph and the
+# cylindrical one of inputs.1d.cyl -- geometric source terms in the tracing, r-dependent face areas / volumes, the radial momentum
+# flux without pressure + grad p, the curvilinear div u; symmetry at r = 0, outflow outside
+SEDOV1D_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro1d_sedov.ex")
+SEDOV_DIR = "/root/reference/Exec/hydro_tests/Sedov"
+SEDOV1D_CASES = {
+    "sedov1d_sph_cgf": ("inputs.1d.sph", 64, 120, [0, 1, 60, 120], ["castro.riemann_solver=0"]),
+    "sedov1d_sph_cg": ("inputs.1d.sph", 64, 80, [0, 80], ["castro.riemann_solver=1"]),
+    "sedov1d_sph_plm": ("inputs.1d.sph", 64, 80, [0, 80], ["castro.riemann_solver=0", "castro.ppm_type=0"]),
+    "sedov1d_cyl_cgf": ("inputs.1d.cyl", 64, 120, [0, 120], ["castro.riemann_solver=0"]),
+    "sedov1d_cyl_plm": ("inputs.1d.cyl", 64, 80, [0, 80], ["castro.riemann_solver=0", "castro.ppm_type=0"]),
+}
+
+
+def run_case_1d(name, inp, nx, max_step, snaps, extra, exe=None, inp_dir=None):
     wd = tempfile.mkdtemp(prefix="golden_")
     try:
-        args = [SOD1D_EXE, os.path.join(SOD_DIR, inp), "amr.max_level=0", "amr.n_cell=%d" % nx, "amr.max_grid_size=64", "amr.blocking_factor=8",
+        args = [exe or SOD1D_EXE, os.path.join(inp_dir or SOD_DIR, inp), "amr.max_level=0", "amr.n_cell=%d" % nx, "amr.max_grid_size=32", "amr.blocking_factor=8",
                 "max_step=%d" % max_step, "amr.plot_int=1", "amr.check_int=-1", "amr.derive_plot_vars=NONE", "castro.sum_interval=-1",
                 "amr.plot_file=plt", "castro.v=0", "amr.v=0"] + extra
         out = subprocess.run(args, cwd=wd, capture_output=True, text=True)
@@ -298,6 +312,10 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case_1d(name, inp, nx, ms, snaps, extra)
+    for name, (inp, nx, ms, snaps, extra) in SEDOV1D_CASES.items():
+        if only and name not in only:
+            continue
+        run_case_1d(name, inp, nx, ms, snaps, extra + ["stop_time=1.e9"], exe=SEDOV1D_EXE, inp_dir=SEDOV_DIR)
     for name, (inp, n, ms, snaps, extra) in SODS_CASES.items():
         if only and name not in only:
             continue

@@ -269,3 +269,29 @@ def load_2d_case(name):
         setattr(par, k, v)
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
     return par, geom, prob, g, snaps
+
+
+# 1-D curvilinear coordinates (geom.dim = 1, geom.coord = 2 spherical / 1 cylindrical): Exec/hydro_tests/Sedov/inputs.1d.sph / .cyl
+SEDOV1D_CASES = {
+    "sedov1d_sph_cgf": dict(solver=0, coord=2), "sedov1d_sph_cg": dict(solver=1, coord=2),
+    "sedov1d_sph_plm": dict(solver=0, coord=2, par=dict(ppm_type=0)),
+    "sedov1d_cyl_cgf": dict(solver=0, coord=1), "sedov1d_cyl_plm": dict(solver=0, coord=1, par=dict(ppm_type=0)),
+}
+
+
+def load_sedov1d_case(name):
+    """The radial Sedov blast in one dimension (the reference built with DIM=1): symmetry at r = 0, outflow outside, gamma = 1.4,
+    cfl 0.5, init_shrink 0.01, change_max 1.1; goldens from oracle/_ref/Castro1d_sedov.ex (oracle/make_golden.py SEDOV1D_CASES)."""
+    c = SEDOV1D_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    par = abi.default_params()
+    par.riemann_solver = c["solver"]
+    par.cfl, par.init_shrink, par.change_max = 0.5, 0.01, 1.1
+    par.eos_gamma, par.eos_assume_neutral = 1.4, 1
+    for k, v in c.get("par", {}).items():
+        setattr(par, k, v)
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    geom = abi.make_geom(n_cell, probhi=(float(g["probhi"][0]), 1.0, 1.0), lo_bc=(3, 2, 2), hi_bc=(2, 2, 2), dim=1, coord=c["coord"])
+    prob = dict(r_init=0.01, p_ambient=1.e-5 if c["coord"] == 2 else 1.e-6, exp_energy=1.0, dens_ambient=1.0, nsub=10)      # inputs.1d.sph / .cyl
+    snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
+    return par, geom, prob, g, snaps

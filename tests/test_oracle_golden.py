@@ -148,3 +148,30 @@ def test_oracle_two_dimensional_matches_golden(name):
         step = s
         assert np.array_equal(U[:, ng, ng:-ng, ng:-ng], g["U%d" % s][:, 0]), "%s step %d" % (name, s)
     np.testing.assert_allclose(np.array(times), g["times"][:len(times)], rtol=1e-14, atol=0)
+
+
+from cases import SEDOV1D_CASES
+
+
+@pytest.mark.parametrize("name", sorted(SEDOV1D_CASES))
+def test_oracle_one_dimensional_curvilinear_matches_golden(name):
+    """1-D spherical / cylindrical coordinates (geometry.coord_sys 2 / 1): geometric source terms in the PPM / PLM tracing, r-dependent
+    areas and volumes in consup_hydro, the radial momentum flux without pressure + the grad p term, the curvilinear div u -- the
+    oracle, started from the reference's initial plotfile, against the reference's states and times, bit for bit"""
+    import oracle_lib as O
+    from cases import load_sedov1d_case
+    par, geom, prob, g, snaps = load_sedov1d_case(name)
+    O.params_finalize(par)
+    U0 = g["U0"]
+    ng = 4
+    nx = U0.shape[3]
+    U = np.zeros((U0.shape[0], 1 + 2 * ng, 1 + 2 * ng, nx + 2 * ng))
+    U[:, ng, ng, ng:-ng] = U0[:, 0, 0, :]
+    t, dt, step, times = 0.0, -1.0, 0, [0.0]
+    for s in snaps[1:]:
+        st, t, dt, hist = O.run(par, geom, U, s - step, time=t, dt=dt)
+        assert st == 0 and len(hist) == s - step
+        times += list(times[-1] + np.cumsum(hist))
+        step = s
+        assert np.array_equal(U[:, ng, ng, ng:-ng], g["U%d" % s][:, 0, 0, :]), "%s step %d" % (name, s)
+    np.testing.assert_allclose(np.array(times), g["times"][:len(times)], rtol=1e-14, atol=0)

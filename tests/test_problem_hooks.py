@@ -193,3 +193,21 @@ def test_reference_hook_reproduces_reference_initial_plotfile_2d(hook, golden):
     f = O.fab(U, (0, 0, 0))
     O.lib().orc_init_tail(C.byref(par), C.byref(geom), lo, hi, C.byref(f))
     assert np.array_equal(U, g["U0"]), "hook %s vs the reference's plt00000 of %s" % (hook, golden)
+
+
+@pytest.mark.parametrize("golden", ["sedov1d_sph_cgf", "sedov1d_cyl_cgf"])
+def test_reference_hook_reproduces_reference_initial_plotfile_1d_curvilinear(golden):
+    """the Sedov headers compiled for AMREX_SPACEDIM = 1 in spherical / cylindrical coordinates (volume-weighted sub-zone sampling)"""
+    import oracle_lib as O
+    from cases import load_sedov1d_case
+    par, geom, prob, g, snaps = load_sedov1d_case(golden)
+    O.params_finalize(par)
+    nx = int(g["n_cell"][0])
+    L = C.CDLL(hook_path("sedov1d"))
+    U = np.full((par.num_state, 1, 1, nx), np.nan)
+    lo, hi = abi.Int3(0, 0, 0), abi.Int3(nx - 1, 0, 0)
+    L.ctu_hook_init.argtypes = HOOK_ARGS
+    assert L.ctu_hook_init(prob_string(prob).encode(), C.byref(par), C.byref(geom), lo, hi, U.ctypes.data, lo, hi) == 0
+    f = O.fab(U, (0, 0, 0))
+    O.lib().orc_init_tail(C.byref(par), C.byref(geom), lo, hi, C.byref(f))
+    assert np.array_equal(U, g["U0"]), "hook vs the reference's plt00000 of %s" % golden
