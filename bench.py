@@ -157,7 +157,8 @@ def workload_config(args, world, cpu_sample=None):
     return {"workload": w,
             "zones_per_gpu": (args.global_n ** 3 // world) if getattr(args, "scaling", "weak") == "strong" else args.n ** 3, "num_state": 7 + getattr(args, "nspec", 1) + (1 if getattr(args, "problem", "sedov") == "kh" else 0),
             "problem": getattr(args, "problem", "sedov"), "proc_grid": list(dims),
-            "l2": "inputs larger than L2 (state %.1f GB per GPU); no explicit flush" % (8 * 8 * (args.n + 8) ** 3 / 1e9)}
+            "l2": "inputs larger than L2 (state %.1f GB per GPU); no explicit flush" % (
+                8 * (7 + getattr(args, "nspec", 1) + (1 if getattr(args, "problem", "sedov") == "kh" else 0)) * (args.n + 8) ** 3 / 1e9)}
 
 
 # ---- clocks -------------------------------------------------------------------------------------------------------

@@ -134,7 +134,7 @@ DevPar make_devpar(const ctu_params_t* par, const ctu_geom_t* geom) {
     }
     P.coord = 0; P.problo0 = 0.0;
     if (geom) {
-        if (geom->dim == 1) { P.coord = geom->coord; P.problo0 = geom->problo[0]; }
+        if (geom->dim == 1 || geom->dim == 2) { P.coord = geom->coord; P.problo0 = geom->problo[0]; }
         for (int d = 0; d < 3; ++d) {
             P.dx[d] = geom->dx[d];
             P.domlo[d] = geom->domlo[d]; P.domhi[d] = geom->domhi[d];
@@ -162,8 +162,8 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     // with the Helmholtz EOS: the PPM / PLM path with the three Riemann solvers; the options that call the EOS on edge states and the
     // constant-gravity driver are instantiated for the gamma law only
     if (p->eos_kind == 1 && (p->transverse_use_eos || p->transverse_reset_rhoe || p->ppm_temp_fix || p->do_grav)) return CTU_ERR_UNSUPPORTED;
-    // curvilinear coordinates: the radial coordinate of a cylinder (1) or a sphere (2) in ONE dimension; 2-D R-Z / R-theta are not built
-    if (g && g->coord != 0 && !(g->dim == 1 && (g->coord == 1 || g->coord == 2))) return CTU_ERR_UNSUPPORTED;
+    // curvilinear coordinates: the radial coordinate of a cylinder (1) or a sphere (2) in ONE dimension, cylindrical R-Z in two; R-theta is not built
+    if (g && g->coord != 0 && !(g->dim == 1 && (g->coord == 1 || g->coord == 2)) && !(g->dim == 2 && g->coord == 1)) return CTU_ERR_UNSUPPORTED;
     if (g && g->dim != 0 && g->dim != 1 && g->dim != 2 && g->dim != 3) return CTU_ERR_BAD_ARG;
     if (g && g->dim == 2) {
         // the 2-D Cartesian path (Castro_ctu_hydro.cpp:530-650): one zone in z; PPM / PLM, the three Riemann solvers, any passives, the
@@ -748,7 +748,8 @@ int hydro_box_2d(HydroRun* r) {
     const Box3 qbx = grow(tb, 4, 4, 0), obx = grow(tb, 1, 1, 0);
     Box3 ibx = obx; ibx.hi[0] += 1; ibx.hi[1] += 1;
     const size_t ni = ibx.npts();
-    const size_t need = ((size_t)qbx.npts() * NQS + ni * (2 + 4 * NIS + 4 * NFX)) * sizeof(double);
+    const Box3 sbx = grow(tb, 3, 3, 0);
+    const size_t need = ((size_t)qbx.npts() * NQS + ni * (2 + 4 * NIS + 4 * NFX) + (size_t)sbx.npts() * NSRCQ) * sizeof(double);
     int rc = ws_reserve_bytes(ws, need, st);
     if (rc) return rc;
     double* p = ws->arena;
@@ -770,22 +771,32 @@ int hydro_box_2d(HydroRun* r) {
     k_ctoprim<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
     lb = make_lb(obx);
     k_flat_div_2d<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb);
+    const bool rz = P.coord != 0;       // cylindrical R-Z: geometric sources in the radial tracing, pressure-free radial momentum flux
     if (P.ppm_type == 0) {
-        k_trace_plm<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none);
+        k_trace_plm<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none);      // adds its own geometry terms
         k_trace_plm<1, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none);
     } else {
-        k_trace<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none, ws->d_counters + 5);
+        if (rz) {
+            const A4 gsrc = make_a4(p, sbx); p += sbx.npts() * NSRCQ;
+            CUDA_TRY(cudaMemsetAsync(ws->d_counters + 5, 0, sizeof(int), st));
+            const LaunchBox ls = make_lb(sbx);
+            k_geom_src_1d<<<nblocks(ls.n), TPB, 0, st>>>(P, qs, gsrc, ls, ws->d_counters + 5);
+            k_trace<0, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, gsrc, ws->d_counters + 5);
+            ++r->launches;
+        } else k_trace<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none, ws->d_counters + 5);
         k_trace<1, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none, ws->d_counters + 5);
     }
     Box3 xbx = tb; xbx.hi[0] += 1;
     Box3 ybx = tb; ybx.hi[1] += 1;
     lb = make_lb(grow(xbx, 0, 1, 0));
-    k_riemann1<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd);
+    if (rz) k_riemann1<0, 0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd);
+    else k_riemann1<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd);
     lb = make_lb(grow(ybx, 1, 0, 0));
     k_riemann1<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd);
     const double hdt = 0.5 * r->dt;
     lb = make_lb(xbx);
-    k_trans_final_2d<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], fd, r->Sb, F[0], lb, hdt);
+    if (rz) k_trans_final_2d<0, 0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], fd, r->Sb, F[0], lb, hdt);
+    else k_trans_final_2d<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], fd, r->Sb, F[0], lb, hdt);
     lb = make_lb(ybx);
     k_trans_final_2d<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], fd, r->Sb, F[1], lb, hdt);
     UpdateArgs ua;

@@ -72,13 +72,17 @@ __global__ void __launch_bounds__(TPB) k_diag(const DevPar P, const A4 S, const 
     }
 }
 
-bool parse_box(const std::string& s, size_t& pos, int lo[3], int hi[3]) {
-    // "((lo0,lo1,lo2) (hi0,hi1,hi2) (0,0,0))"
+bool parse_box(const std::string& s, size_t& pos, int lo[3], int hi[3], int dim = 3) {
+    // "((lo0,lo1,lo2) (hi0,hi1,hi2) (0,0,0))" in 3-D, "((lo0,lo1) (hi0,hi1) (0,0))" in 2-D, "((lo0) (hi0) (0))" in 1-D
     const size_t a = s.find("((", pos);
     if (a == std::string::npos) return false;
     int t[3];
-    if (std::sscanf(s.c_str() + a, "((%d,%d,%d) (%d,%d,%d) (%d,%d,%d))", &lo[0], &lo[1], &lo[2], &hi[0], &hi[1], &hi[2], &t[0], &t[1], &t[2]) != 9)
-        return false;
+    for (int d = 0; d < 3; ++d) { lo[d] = 0; hi[d] = 0; }
+    bool ok;
+    if (dim == 3) ok = std::sscanf(s.c_str() + a, "((%d,%d,%d) (%d,%d,%d) (%d,%d,%d))", &lo[0], &lo[1], &lo[2], &hi[0], &hi[1], &hi[2], &t[0], &t[1], &t[2]) == 9;
+    else if (dim == 2) ok = std::sscanf(s.c_str() + a, "((%d,%d) (%d,%d) (%d,%d))", &lo[0], &lo[1], &hi[0], &hi[1], &t[0], &t[1]) == 6;
+    else ok = std::sscanf(s.c_str() + a, "((%d) (%d) (%d))", &lo[0], &hi[0], &t[0]) == 3;
+    if (!ok) return false;
     pos = s.find("))", a) + 2;
     return true;
 }
@@ -169,7 +173,8 @@ int ctu_sim_read_plotfile(ctu_sim_t* s, const char* dir, double* time, int* step
     int dim = 0, finest = 0;
     double t = 0.0;
     hf >> dim >> t >> finest;
-    if (dim != 3 || finest != 0) return CTU_ERR_UNSUPPORTED;
+    const int sdim = s->geom.dim == 1 ? 1 : s->geom.dim == 2 ? 2 : 3;
+    if (dim != sdim || finest != 0) return CTU_ERR_UNSUPPORTED;      // a plotfile of another dimensionality (or with refined levels)
     std::getline(hf, line);
     std::getline(hf, line);                       // prob_lo
     std::getline(hf, line);                       // prob_hi
@@ -192,7 +197,7 @@ int ctu_sim_read_plotfile(ctu_sim_t* s, const char* dir, double* time, int* step
     while (true) {
         Box3 b;
         size_t p2 = pos;
-        if (!parse_box(txt, p2, b.lo, b.hi) || p2 > end_boxes) break;
+        if (!parse_box(txt, p2, b.lo, b.hi, dim) || p2 > end_boxes) break;
         boxes.push_back(b);
         pos = p2;
     }

@@ -174,6 +174,34 @@ __host__ __device__ __forceinline__ double volume_1d(const DevPar& P, int i) {
     return fabs((4.0 / 3.0) * CTU_PI * P.dx[0] * (rl * rl + rl * rr + rr * rr));
 }
 
+// 2-D geometry (Cartesian or R-Z, P.coord 1).  Two sets, because the reference uses two: the area / volume MultiFabs of AMReX
+// (amrex_setarea / amrex_setvol, AMReX_COORDSYS_2D_C.H:12-140) in the transverse corrections and in scale_flux, and the functions of
+// Castro_util.H (:236-248, :324-347) in consup_hydro; in R-Z they associate their products differently.
+__host__ __device__ __forceinline__ double amrex_area_2d(const DevPar& P, int i, int dir) {
+    if (P.coord == 0) return (dir == 0) ? P.dx[1] : P.dx[0];
+    if (dir == 0) { const double ri = P.problo0 + P.dx[0] * (i); return fabs((2.0 * CTU_PI) * ri * P.dx[1]); }
+    const double rc = P.problo0 + P.dx[0] * (i + 0.5);
+    return fabs(P.dx[0] * (2.0 * CTU_PI) * rc);
+}
+__host__ __device__ __forceinline__ double amrex_vol_2d(const DevPar& P, int i) {
+    if (P.coord == 0) return P.dx[0] * P.dx[1];
+    const double ri = P.problo0 + P.dx[0] * (i);
+    const double ro = ri + P.dx[0];
+    return fabs(CTU_PI * P.dx[1] * P.dx[0] * (ro + ri));
+}
+__host__ __device__ __forceinline__ double castro_area_2d(const DevPar& P, int i, int dir) {
+    if (P.coord == 0) return (dir == 0) ? P.dx[1] : P.dx[0];
+    if (dir == 0) { const double r = P.problo0 + static_cast<double>(i) * P.dx[0]; return fabs(2.0 * CTU_PI * r * P.dx[1]); }
+    const double r = P.problo0 + (static_cast<double>(i) + 0.5) * P.dx[0];
+    return fabs(2.0 * CTU_PI * r * P.dx[0]);
+}
+__host__ __device__ __forceinline__ double castro_vol_2d(const DevPar& P, int i) {
+    if (P.coord == 0) return P.dx[0] * P.dx[1];
+    const double r_l = P.problo0 + static_cast<double>(i) * P.dx[0];
+    const double r_r = P.problo0 + static_cast<double>(i + 1) * P.dx[0];
+    return fabs(CTU_PI * (r_l + r_r) * P.dx[0] * P.dx[1]);
+}
+
 // 1-D (AMREX_SPACEDIM == 1): flattening along x only (flatten.H:141-150); div u of advection_util.cpp:228-255: (u_i - u_{i-1}) / dx in
 // Cartesian coordinates, (r_r^a u_i - r_l^a u_{i-1}) / (dx r_c^a) with a = 1 (cylindrical) or 2 (spherical), 0 at the node i = 0
 static __global__ void __launch_bounds__(TPB) k_flat_div_1d(const DevPar P, const A4 qs, const A4 fd, const LaunchBox lb) {
@@ -270,8 +298,23 @@ static __global__ void __launch_bounds__(TPB) k_flat_div_2d(const DevPar P, cons
     }
     fd.at(of, 0) = flatn;
     const double dxinv = 1.0 / P.dx[0], dyinv = 1.0 / P.dx[1];
-    const double ux = 0.5 * (qu[0] - qu[-1] + qu[-sj] - qu[-1 - sj]) * dxinv;
-    const double vy = 0.5 * (qv[0] - qv[-sj] + qv[-1] - qv[-1 - sj]) * dyinv;
+    double ux = 0.0, vy = 0.0;
+    if (P.coord == 0) {
+        ux = 0.5 * (qu[0] - qu[-1] + qu[-sj] - qu[-1 - sj]) * dxinv;
+        vy = 0.5 * (qv[0] - qv[-sj] + qv[-1] - qv[-1 - sj]) * dyinv;
+    } else {      // cylindrical R-Z (advection_util.cpp:268-290)
+        if (i != 0) {
+            const double rl = (i - 0.5) * P.dx[0] + P.problo0;
+            const double rr = (i + 0.5) * P.dx[0] + P.problo0;
+            const double rc = (i) * P.dx[0] + P.problo0;
+            const double ul = 0.5 * (qu[-1] + qu[-1 - sj]);
+            const double ur = 0.5 * (qu[0] + qu[-sj]);
+            ux = (rr * ur - rl * ul) * dxinv / rc;
+        }
+        const double vb = 0.5 * (qv[-sj] + qv[-1 - sj]);
+        const double vt = 0.5 * (qv[0] + qv[-1]);
+        vy = (vt - vb) * dyinv;
+    }
     fd.at(of, 1) = ux + vy;
 }
 
@@ -811,7 +854,7 @@ static __global__ void __launch_bounds__(TPB) k_trace_plm(const DevPar P, const 
             qp.at(om, IS_P) = o_p; qp.at(om, IS_RE) = o_re;
         }
     }
-    if (DIR == 0 && P.dim == 1 && P.coord != 0) {      // geometry source terms of the x states (trace_plm.cpp:321-357)
+    if (DIR == 0 && P.dim <= 2 && P.coord != 0) {      // geometry source terms of the x states (trace_plm.cpp:321-357; dloga_y = 0 in R-Z)
         const double dlg = dloga_1d(P, i);
         if (dlg != 0.0) {
             const double courn = dtdL * (cc + fabs(un));
@@ -857,7 +900,7 @@ static __global__ void __launch_bounds__(TPB) k_trace_plm(const DevPar P, const 
 // Riemann driver shared by the three flux kernels: Castro::cmpflx_plus_godunov (riemann.cpp:15-200)
 //   XM(ip)/XP(ip): passive ip (mass fraction etc.) of the minus/plus state
 // ------------------------------------------------------------------------------------------------
-template <int DIR, int EK = 0, class XM, class XP>
+template <int DIR, int EK = 0, bool MP = true, class XM, class XP>
 __device__ __forceinline__ void solve_face(const DevPar& P, double* qm, double* qp, const A4& qs, int i, int j, int k,
                                            XM xm, XP xp, double* F, double& ugd, double& pgd, PassiveUpwind& pu, const A4& fd) {
     pu.hll = 0;
@@ -885,11 +928,11 @@ __device__ __forceinline__ void solve_face(const DevPar& P, double* qm, double* 
     auto xlf = [&](int n) { return xm(P.QFS_off + n); };
     auto xrf = [&](int n) { return xp(P.QFS_off + n); };
     if (P.riemann_solver == 0) {
-        riemann_cgf<MathExact, DIR, decltype(xlf), decltype(xrf), 0, EK>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, xlf, xrf, F, ugd, pgd, pu);
+        riemann_cgf<MathExact, DIR, decltype(xlf), decltype(xrf), 0, EK, MP>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, xlf, xrf, F, ugd, pgd, pu);
     } else if (P.riemann_solver == 1) {
-        riemann_cgf<MathExact, DIR, decltype(xlf), decltype(xrf), 1, EK>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, xlf, xrf, F, ugd, pgd, pu);
+        riemann_cgf<MathExact, DIR, decltype(xlf), decltype(xrf), 1, EK, MP>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, xlf, xrf, F, ugd, pgd, pu);
     } else {
-        riemann_hllc<MathExact, DIR>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, F, ugd, pgd, pu);
+        riemann_hllc<MathExact, DIR, MP>(P, qm, qp, gamcl, gamcr, cl, cr, bnd_fac, F, ugd, pgd, pu);
     }
     if (P.hybrid_riemann) {      // HLL flux next to a detected shock (riemann.cpp:144-197)
         const long of = fd.idx(i, j, k);
@@ -909,7 +952,7 @@ __device__ __forceinline__ void load6(const A4& a, long off, double* q) {
 }
 
 // first-pass fluxes (Castro_ctu_hydro.cpp:674,745,817)
-template <int DIR, int EK = 0>
+template <int DIR, int EK = 0, bool MP = true>
 static __global__ void __launch_bounds__(TPB) k_riemann1(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Fo, const LaunchBox lb,
                                                   const A4 fd) {
     int i, j, k;
@@ -919,8 +962,8 @@ static __global__ void __launch_bounds__(TPB) k_riemann1(const DevPar P, const A
     PassiveUpwind pu;
     load6(qm, o, ql);
     load6(qp, o, qr);
-    solve_face<DIR, EK>(P, ql, qr, qs, i, j, k, [&](int ip) { return qm.at(o, IS_X + ip); }, [&](int ip) { return qp.at(o, IS_X + ip); },
-                    F, ugd, pgd, pu, fd);
+    solve_face<DIR, EK, MP>(P, ql, qr, qs, i, j, k, [&](int ip) { return qm.at(o, IS_X + ip); }, [&](int ip) { return qp.at(o, IS_X + ip); },
+                        F, ugd, pgd, pu, fd);
     if (P.ppm_temp_fix == 2 && P.riemann_solver != 2) {      // the re-synced states replace the traced ones for the later stages
         qm.at(o, IS_P) = ql[IS_P]; qm.at(o, IS_RE) = ql[IS_RE];
         qp.at(o, IS_P) = qr[IS_P]; qp.at(o, IS_RE) = qr[IS_RE];
@@ -1023,12 +1066,14 @@ static __global__ void __launch_bounds__(TPB) k_trans_riemann(const DevPar P, co
 // with face areas and the zone volume, hdt * (A F_r - A F_l) / V (trans.cpp:162-171,247-253,306-318,422-430,466-470), then the FINAL
 // Riemann solve and the flux cleaning (zero T flux, apply_av with dg2 = 0, normalize_species_fluxes).  N = face direction, T = 1 - N.
 // ------------------------------------------------------------------------------------------------
+// al / ar: area of the low / high transverse face; pcorr = hdt / dx_T when the transverse direction is the radial one of a curvilinear
+// run (its momentum flux carries no pressure, so the pressure difference is added here: trans.cpp:308-310), else 0
 __device__ __forceinline__ void trans_single_hydro_2d(const DevPar& P, const double* __restrict__ q, double* __restrict__ qo,
                                                       const double* __restrict__ fl, const double* __restrict__ fr, double ugm, double ugp,
-                                                      double pgm, double pgp, double gamc, double hdt, double area, double volinv,
-                                                      double rrnew, bool reset) {
-    double dup = area * pgp * ugp - area * pgm * ugm;
-    double du = area * ugp - area * ugm;
+                                                      double pgm, double pgp, double gamc, double hdt, double al, double ar, double volinv,
+                                                      double rrnew, bool reset, bool radial_t, double cdtdx) {
+    double dup = ar * pgp * ugp - al * pgm * ugm;
+    double du = ar * ugp - al * ugm;
     double pav = 0.5 * (pgp + pgm);
     double rrn = q[IS_RHO];
     double run = rrn * q[IS_U];
@@ -1037,10 +1082,11 @@ __device__ __forceinline__ void trans_single_hydro_2d(const DevPar& P, const dou
     double ekenn = 0.5 * rrn * (q[IS_U] * q[IS_U] + q[IS_V] * q[IS_V] + q[IS_W] * q[IS_W]);
     double ren = q[IS_RE] + ekenn;
     double rrnewn = rrnew;
-    double runewn = run - hdt * (area * fr[1] - area * fl[1]) * volinv;
-    double rvnewn = rvn - hdt * (area * fr[2] - area * fl[2]) * volinv;
-    double rwnewn = rwn - hdt * (area * fr[3] - area * fl[3]) * volinv;
-    double renewn = ren - hdt * (area * fr[4] - area * fl[4]) * volinv;
+    double runewn = run - hdt * (ar * fr[1] - al * fl[1]) * volinv;
+    if (radial_t) runewn = runewn - cdtdx * (pgp - pgm);
+    double rvnewn = rvn - hdt * (ar * fr[2] - al * fl[2]) * volinv;
+    double rwnewn = rwn - hdt * (ar * fr[3] - al * fl[3]) * volinv;
+    double renewn = ren - hdt * (ar * fr[4] - al * fl[4]) * volinv;
     if (reset) { rrnewn = rrn; runewn = run; rvnewn = rvn; rwnewn = rwn; renewn = ren; }
     qo[IS_RHO] = rrnewn;
     const double rhoinv = 1.0 / rrnewn;
@@ -1050,7 +1096,7 @@ __device__ __forceinline__ void trans_single_hydro_2d(const DevPar& P, const dou
     double rhoekenn = 0.5 * (runewn * runewn + rvnewn * rvnewn + rwnewn * rwnewn) * rhoinv;
     double reo = renewn - rhoekenn;
     if (!reset) {
-        if (P.transverse_reset_rhoe == 1 && reo <= 0.0) reo = q[IS_RE] - hdt * (area * fr[5] - area * fl[5] + pav * du) * volinv;
+        if (P.transverse_reset_rhoe == 1 && reo <= 0.0) reo = q[IS_RE] - hdt * (ar * fr[5] - al * fl[5] + pav * du) * volinv;
         if (reo <= 0.0) reo = q[IS_RE];
         double pnewn = q[IS_P] - hdt * (dup + pav * du * (gamc - 1.0)) * volinv;
         qo[IS_P] = amax(pnewn, P.small_pres);
@@ -1061,15 +1107,18 @@ __device__ __forceinline__ void trans_single_hydro_2d(const DevPar& P, const dou
     }
 }
 
-template <int N, int EK = 0>
+template <int N, int EK = 0, bool MP = true>
 static __global__ void __launch_bounds__(TPB) k_trans_final_2d(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Ft, const A4 fd,
                                                         const A4 U, const A4 Fo, const LaunchBox lb, const double hdt) {
     constexpr int T = 1 - N;
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
-    const double area = P.dx[1 - T];                  // faces normal to T: dx of the other direction
-    const double vol = P.dx[0] * P.dx[1];
-    const double volinv = 1.0 / vol;
+    // zone on the minus side of the face: (i, j) - e_N; its transverse faces: low (il) and high (il + e_T).  AMReX's areas / volume
+    const int im = i - (N == 0 ? 1 : 0);
+    const double al_m = amrex_area_2d(P, im, T), ar_m = amrex_area_2d(P, im + (T == 0 ? 1 : 0), T), vinv_m = 1.0 / amrex_vol_2d(P, im);
+    const double al_p = amrex_area_2d(P, i, T), ar_p = amrex_area_2d(P, i + (T == 0 ? 1 : 0), T), vinv_p = 1.0 / amrex_vol_2d(P, i);
+    const bool radial_t = (T == 0 && P.coord != 0);
+    const double cdtdx = hdt / P.dx[T];
     const long o = qm.idx(i, j, k);
     const long sN_f = (N == 0) ? 1 : Ft.sj, sT_f = (T == 0) ? 1 : Ft.sj;
     const long sN_q = (N == 0) ? 1 : qs.sj;
@@ -1083,35 +1132,35 @@ static __global__ void __launch_bounds__(TPB) k_trans_final_2d(const DevPar P, c
         load6(qm, o, q);
         load6(Ft, ofm, fl);
         load6(Ft, ofm + sT_f, fr);
-        rrnew_m = q[IS_RHO] - hdt * (area * fr[0] - area * fl[0]) * volinv;
+        rrnew_m = q[IS_RHO] - hdt * (ar_m * fr[0] - al_m * fl[0]) * vinv_m;
         reset_m = trans_reset(P, q[IS_RHO], rrnew_m, [&](int ip) { return qm.at(o, IS_X + ip); },
-                              [&](int ip, double c0) { return c0 - hdt * (area * Ft.at(ofm + sT_f, FX_X + ip) - area * Ft.at(ofm, FX_X + ip)) * volinv; });
+                              [&](int ip, double c0) { return c0 - hdt * (ar_m * Ft.at(ofm + sT_f, FX_X + ip) - al_m * Ft.at(ofm, FX_X + ip)) * vinv_m; });
         const double gamc = P.gamc_const ? P.gamma : qs.at(oqm, QS_GAMC);
         trans_single_hydro_2d(P, q, qlo, fl, fr, Ft.at(ofm, FX_UG), Ft.at(ofm + sT_f, FX_UG), Ft.at(ofm, FX_PG), Ft.at(ofm + sT_f, FX_PG),
-                              gamc, hdt, area, volinv, rrnew_m, reset_m);
+                              gamc, hdt, al_m, ar_m, vinv_m, rrnew_m, reset_m, radial_t, cdtdx);
     }
     {   // plus state: zone (face)
         double q[6], fl[6], fr[6];
         load6(qp, o, q);
         load6(Ft, ofp, fl);
         load6(Ft, ofp + sT_f, fr);
-        rrnew_p = q[IS_RHO] - hdt * (area * fr[0] - area * fl[0]) * volinv;
+        rrnew_p = q[IS_RHO] - hdt * (ar_p * fr[0] - al_p * fl[0]) * vinv_p;
         reset_p = trans_reset(P, q[IS_RHO], rrnew_p, [&](int ip) { return qp.at(o, IS_X + ip); },
-                              [&](int ip, double c0) { return c0 - hdt * (area * Ft.at(ofp + sT_f, FX_X + ip) - area * Ft.at(ofp, FX_X + ip)) * volinv; });
+                              [&](int ip, double c0) { return c0 - hdt * (ar_p * Ft.at(ofp + sT_f, FX_X + ip) - al_p * Ft.at(ofp, FX_X + ip)) * vinv_p; });
         const double gamc = P.gamc_const ? P.gamma : qs.at(oqp, QS_GAMC);
         trans_single_hydro_2d(P, q, qro, fl, fr, Ft.at(ofp, FX_UG), Ft.at(ofp + sT_f, FX_UG), Ft.at(ofp, FX_PG), Ft.at(ofp + sT_f, FX_PG),
-                              gamc, hdt, area, volinv, rrnew_p, reset_p);
+                              gamc, hdt, al_p, ar_p, vinv_p, rrnew_p, reset_p, radial_t, cdtdx);
     }
     const double rho_m = qm.at(o, IS_RHO), rho_p = qp.at(o, IS_RHO);
     auto xm = [&](int ip) {
         const double X = qm.at(o, IS_X + ip);
         if (reset_m) return X;
-        return (rho_m * X - hdt * (area * Ft.at(ofm + sT_f, FX_X + ip) - area * Ft.at(ofm, FX_X + ip)) * volinv) / rrnew_m;
+        return (rho_m * X - hdt * (ar_m * Ft.at(ofm + sT_f, FX_X + ip) - al_m * Ft.at(ofm, FX_X + ip)) * vinv_m) / rrnew_m;
     };
     auto xp = [&](int ip) {
         const double X = qp.at(o, IS_X + ip);
         if (reset_p) return X;
-        return (rho_p * X - hdt * (area * Ft.at(ofp + sT_f, FX_X + ip) - area * Ft.at(ofp, FX_X + ip)) * volinv) / rrnew_p;
+        return (rho_p * X - hdt * (ar_p * Ft.at(ofp + sT_f, FX_X + ip) - al_p * Ft.at(ofp, FX_X + ip)) * vinv_p) / rrnew_p;
     };
     if (P.transverse_use_eos || P.transverse_reset_rhoe) {
         edge_thermo_post<false>(P, qlo, eos_mu(P, [&](int n) { return xm(P.QFS_off + n); }), reset_m);
@@ -1119,7 +1168,7 @@ static __global__ void __launch_bounds__(TPB) k_trans_final_2d(const DevPar P, c
     }
     double F[6], ugd, pgd;
     PassiveUpwind pu;
-    solve_face<N, EK>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu, fd);
+    solve_face<N, EK, MP>(P, qlo, qro, qs, i, j, k, xm, xp, F, ugd, pgd, pu, fd);
     // apply_av (advection_util.cpp:354-419) with dg1 = 1, dg2 = 0: the four-term average visits two nodes twice
     const double* __restrict__ dv = fd.p + fd.idx(i, j, k) + fd.sn;
     double div1;
@@ -1433,17 +1482,20 @@ static __global__ void __launch_bounds__(TPB) k_update(const DevPar P, const A4 
                 Sn.at(on, UFA + ip) = Sin.at(oi, UFA + ip) + dt * (F0.at(f0, n) * al - F0.at(f0p, n) * ar) * vi;
             }
         } else if (P.dim == 2) {   // AMREX_SPACEDIM == 2, Cartesian: volume = dx dy, area_x = dy, area_y = dx (Castro_util.H:236-248,324-342)
-            const double b0 = P.dx[1], b1 = P.dx[0], vi = 1.0 / (P.dx[0] * P.dx[1]);
+            // R-Z (P.coord 1): r-dependent areas / volume, and the grad p term of the radial momentum (Castro_ctu.cpp:66-70)
+            const double b0l = castro_area_2d(P, i, 0), b0r = castro_area_2d(P, i + 1, 0), b1 = castro_area_2d(P, i, 1);
+            const double vi = 1.0 / castro_vol_2d(P, i);
 #pragma unroll
             for (int n = 0; n < 6; ++n)
-                u[n] = Sin.at(oi, n) + dt * (F0.at(f0, n) * b0 - F0.at(f0p, n) * b0 + F1.at(f1, n) * b1 - F1.at(f1p, n) * b1) * vi;
-            double pdu = (F0.at(f0p, FX_PG) + F0.at(f0, FX_PG)) * (F0.at(f0p, FX_UG) * b0 - F0.at(f0, FX_UG) * b0);
+                u[n] = Sin.at(oi, n) + dt * (F0.at(f0, n) * b0l - F0.at(f0p, n) * b0r + F1.at(f1, n) * b1 - F1.at(f1p, n) * b1) * vi;
+            double pdu = (F0.at(f0p, FX_PG) + F0.at(f0, FX_PG)) * (F0.at(f0p, FX_UG) * b0r - F0.at(f0, FX_UG) * b0l);
             pdu += (F1.at(f1p, FX_PG) + F1.at(f1, FX_PG)) * (F1.at(f1p, FX_UG) * b1 - F1.at(f1, FX_UG) * b1);
             pdu = 0.5 * pdu * vi;
             u[UEINT] = u[UEINT] - dt * pdu;
+            if (P.coord != 0) u[UMX] += -dt * (F0.at(f0p, FX_PG) - F0.at(f0, FX_PG)) / P.dx[0];
             for (int ip = 0; ip < P.npassive; ++ip) {
                 const int n = FX_X + ip;
-                Sn.at(on, UFA + ip) = Sin.at(oi, UFA + ip) + dt * (F0.at(f0, n) * b0 - F0.at(f0p, n) * b0 + F1.at(f1, n) * b1 - F1.at(f1p, n) * b1) * vi;
+                Sn.at(on, UFA + ip) = Sin.at(oi, UFA + ip) + dt * (F0.at(f0, n) * b0l - F0.at(f0p, n) * b0r + F1.at(f1, n) * b1 - F1.at(f1p, n) * b1) * vi;
             }
         } else {
 #pragma unroll
@@ -1502,6 +1554,7 @@ static __global__ void __launch_bounds__(TPB) k_store_flux(const DevPar P, const
     if (!thread_zone(lb, i, j, k)) return;
     double area = (DIR == 0) ? P.dx[1] * P.dx[2] : (DIR == 1) ? P.dx[0] * P.dx[2] : P.dx[0] * P.dx[1];
     if (DIR == 0 && P.dim == 1 && P.coord != 0) area = area_1d(P, i);      // the face area of a radial coordinate (amrex_setarea)
+    if (DIR <= 1 && P.dim == 2 && P.coord != 0) area = amrex_area_2d(P, i, DIR);
     const long of = F.idx(i, j, k);
     if (fo.p) {
         const long oo = fo.idx(i, j, k);

@@ -27,9 +27,10 @@ namespace ctu {
 #ifndef CTU_TRACE_MINB_SRC
 #define CTU_TRACE_MINB_SRC 2
 #endif
-// ... and of the source-free instances with three or more passive scalars (developer switch)
+// ... and of the source-free instances with three or more passive scalars or the Colella & Glaz iteration (measured at 512^3 with all
+// trace kernels at 2 CTAs / SM: one passive 40.0 -> 44.5 ms, two 47.0 -> 50.9, five 65.3 -> 62.6, Colella & Glaz 153.4 -> 144.2)
 #ifndef CTU_TRACE_MINB_NP3
-#define CTU_TRACE_MINB_NP3 CTU_TRACE_MINB
+#define CTU_TRACE_MINB_NP3 2
 #endif
 #ifndef CTU_TMA_MINB
 #define CTU_TMA_MINB 4
@@ -1372,7 +1373,7 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
 }
 
 template <int D, int NP, bool SRC, int RS = 0, int REC = 0>
-static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, SRC ? CTU_TRACE_MINB_SRC : (NP >= 3 ? CTU_TRACE_MINB_NP3 : CTU_TRACE_MINB))
+static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, SRC ? CTU_TRACE_MINB_SRC : ((NP >= 3 || RS == 1) ? CTU_TRACE_MINB_NP3 : CTU_TRACE_MINB))
 k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, const TraceRiemannArgs a) {
     using L = TraceSmem<D, NP>;
     using TT = TrTile<D>;

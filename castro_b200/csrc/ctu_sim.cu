@@ -1451,8 +1451,11 @@ int ctu_sim_write_plotfile(ctu_sim_t* s, const char* dir, double time, int step)
     for (int i = 0; i < s->par.naux; ++i) names.push_back("rho_aux" + std::to_string(i));
     const ctu_geom_t& g = s->geom;
     char buf[256];
+    const int dim = g.dim == 1 ? 1 : g.dim == 2 ? 2 : 3;      // AMREX_SPACEDIM of the run: boxes, prob_lo / hi and dx carry that many entries
     auto box_str = [&](const Box3& b) {
-        std::snprintf(buf, sizeof(buf), "((%d,%d,%d) (%d,%d,%d) (0,0,0))", b.lo[0], b.lo[1], b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
+        if (dim == 3) std::snprintf(buf, sizeof(buf), "((%d,%d,%d) (%d,%d,%d) (0,0,0))", b.lo[0], b.lo[1], b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
+        else if (dim == 2) std::snprintf(buf, sizeof(buf), "((%d,%d) (%d,%d) (0,0))", b.lo[0], b.lo[1], b.hi[0], b.hi[1]);
+        else std::snprintf(buf, sizeof(buf), "((%d) (%d) (0))", b.lo[0], b.hi[0]);
         return std::string(buf);
     };
     auto num = [&](double v) { std::snprintf(buf, sizeof(buf), "%.15g", v); return std::string(buf); };   // the reference writes its header with 15 significant digits
@@ -1460,15 +1463,18 @@ int ctu_sim_write_plotfile(ctu_sim_t* s, const char* dir, double time, int step)
         if (!f) return CTU_ERR_IO;
         f << "HyperCLaw-V1.1\n" << nc << "\n";
         for (auto& n : names) f << n << "\n";
-        f << "3\n" << num(time) << "\n0\n";
-        f << num(g.problo[0]) << " " << num(g.problo[1]) << " " << num(g.problo[2]) << " \n";
-        f << num(g.probhi[0]) << " " << num(g.probhi[1]) << " " << num(g.probhi[2]) << " \n\n";
+        f << dim << "\n" << num(time) << "\n0\n";
+        for (int d = 0; d < dim; ++d) f << num(g.problo[d]) << " ";
+        f << "\n";
+        for (int d = 0; d < dim; ++d) f << num(g.probhi[d]) << " ";
+        f << "\n\n";
         Box3 dom; for (int d = 0; d < 3; ++d) { dom.lo[d] = g.domlo[d]; dom.hi[d] = g.domhi[d]; }
         f << box_str(dom) << " \n" << step << " \n";
-        f << num(g.dx[0]) << " " << num(g.dx[1]) << " " << num(g.dx[2]) << " \n";
+        for (int d = 0; d < dim; ++d) f << num(g.dx[d]) << " ";
+        f << "\n";
         f << g.coord << "\n0\n";
         f << "0 1 " << num(time) << "\n" << step << "\n";
-        for (int d = 0; d < 3; ++d)
+        for (int d = 0; d < dim; ++d)
             f << num(g.problo[d] + (s->vbx.lo[d] - g.domlo[d]) * g.dx[d]) << " " << num(g.problo[d] + (s->vbx.hi[d] + 1 - g.domlo[d]) * g.dx[d]) << "\n";
         f << "Level_0/Cell\n";
         if (!f) return CTU_ERR_IO; }

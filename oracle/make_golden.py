@@ -201,6 +201,7 @@ SEDOV2D_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro2d_sedov.ex")
 SEDOV2D_INPUTS = "/root/reference/Exec/hydro_tests/Sedov/inputs.2d.cyl_in_cartcoords"
 KH2D_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro2d_kh.ex")
 KH2D_INPUTS = "/root/reference/Exec/hydro_tests/KH/inputs.2d"
+SEDOV_DIR_ = "/root/reference/Exec/hydro_tests/Sedov"
 CASES_2D = {
     "sedov2d_cgf": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 40, [0, 1, 40], ["castro.riemann_solver=0"]),
     "sedov2d_hllc": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 40, [0, 40], ["castro.riemann_solver=2"]),
@@ -210,6 +211,11 @@ CASES_2D = {
                                                                            "castro.transverse_reset_rhoe=1"]),
     "sedov2d_symm_cgf": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 60, [0, 60], ["castro.riemann_solver=0", "castro.lo_bc=3 3", "castro.hi_bc=4 2",
                                                                            "geometry.prob_hi=0.5 0.5"]),
+    # cylindrical R-Z coordinates (inputs.2d.sph_in_cylcoords: the spherical blast on the axis, symmetry at r = 0 and z = 0)
+    "sedov2d_rz_cgf": (SEDOV2D_EXE, SEDOV_DIR_ + "/inputs.2d.sph_in_cylcoords", (32, 32), 80, [0, 1, 80], ["castro.riemann_solver=0"]),
+    "sedov2d_rz_hllc": (SEDOV2D_EXE, SEDOV_DIR_ + "/inputs.2d.sph_in_cylcoords", (32, 32), 60, [0, 60], ["castro.riemann_solver=2"]),
+    "sedov2d_rz_plm_24x32": (SEDOV2D_EXE, SEDOV_DIR_ + "/inputs.2d.sph_in_cylcoords", (24, 32), 60, [0, 60], ["castro.riemann_solver=0", "castro.ppm_type=0",
+                                                                                                    "geometry.prob_hi=0.375 0.5"]),
     "kh2d_cgf": (KH2D_EXE, KH2D_INPUTS, (32, 32), 20, [0, 20], ["castro.riemann_solver=0"]),
     "kh2d_hllc": (KH2D_EXE, KH2D_INPUTS, (32, 16), 20, [0, 20], ["castro.riemann_solver=2", "problem.bulk_velocity=0.3", "geometry.prob_hi=1.0 0.5"]),
 }

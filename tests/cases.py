@@ -241,6 +241,9 @@ CASES_2D = {
     "sedov2d_plm_hllc": dict(kind="sedov", solver=2, par=dict(ppm_type=0)),
     "sedov2d_hllc_eos": dict(kind="sedov", solver=2, par=dict(transverse_use_eos=1, transverse_reset_rhoe=1)),
     "sedov2d_symm_cgf": dict(kind="sedov", solver=0, lo_bc=(3, 3, 2), hi_bc=(4, 2, 2)),
+    "sedov2d_rz_cgf": dict(kind="sedov", solver=0, coord=1, lo_bc=(3, 3, 2), hi_bc=(2, 2, 2)),
+    "sedov2d_rz_hllc": dict(kind="sedov", solver=2, coord=1, lo_bc=(3, 3, 2), hi_bc=(2, 2, 2)),
+    "sedov2d_rz_plm_24x32": dict(kind="sedov", solver=0, coord=1, lo_bc=(3, 3, 2), hi_bc=(2, 2, 2), par=dict(ppm_type=0)),
     "kh2d_cgf": dict(kind="kh", solver=0, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0, center=(0.5, 0.5, 0.0))),
     "kh2d_hllc": dict(kind="kh", solver=2, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.3, center=(0.5, 0.5, 0.0))),
 }
@@ -256,8 +259,9 @@ def load_2d_case(name):
     if c["kind"] == "sedov":
         par.cfl, par.init_shrink, par.change_max = 0.5, 0.01, 1.1
         par.eos_gamma, par.eos_assume_neutral = 1.4, 1
-        geom = abi.make_geom(n_cell, probhi=probhi, lo_bc=c.get("lo_bc", (2, 2, 2)), hi_bc=c.get("hi_bc", (2, 2, 2)), dim=2)
-        prob = dict(r_init=0.01, p_ambient=1.e-6, exp_energy=1.0, dens_ambient=1.0, nsub=10)
+        geom = abi.make_geom(n_cell, probhi=probhi, lo_bc=c.get("lo_bc", (2, 2, 2)), hi_bc=c.get("hi_bc", (2, 2, 2)), dim=2, coord=c.get("coord", 0))
+        # inputs.2d.cyl_in_cartcoords: p_ambient 1e-6; inputs.2d.sph_in_cylcoords (R-Z): 1e-5
+        prob = dict(r_init=0.01, p_ambient=1.e-5 if c.get("coord", 0) else 1.e-6, exp_energy=1.0, dens_ambient=1.0, nsub=10)
     else:
         par.cfl, par.init_shrink, par.change_max = 0.5, 0.1, 1.1
         par.small_temp, par.small_dens = 1.e-9, 1.e-4

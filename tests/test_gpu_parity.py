@@ -1071,3 +1071,31 @@ def test_one_dimensional_curvilinear_matches_reference(name):
     g3 = abi.make_geom((16, 16, 16), coord=1)
     with pytest.raises(lib.CtuError):
         lib.Sim(par, g3, (0, 0, 0), (15, 15, 15))
+
+
+@pytest.mark.parametrize("name", ["sedov2d_cg_24x16", "sedov1d_sph_cgf"])
+def test_plotfile_io_in_one_and_two_dimensions(name, tmp_path):
+    """ctu_sim_write_plotfile / ctu_sim_read_plotfile follow the run's dimensionality (boxes, prob_lo / hi and dx with AMREX_SPACEDIM
+    entries, coord_sys in the Header): the file parses with the reader that parsed the reference's own 1-D / 2-D plotfiles when the
+    goldens were made, and reads back bit for bit"""
+    _torch()
+    from castro_b200 import lib
+    from plotfile import read_plotfile
+    from cases import load_2d_case, load_sedov1d_case
+    par, geom, prob, g, snaps = load_2d_case(name) if "2d" in name else load_sedov1d_case(name)
+    lib.params_finalize(par)
+    hi = (int(g["n_cell"][0]) - 1, int(g["n_cell"][1]) - 1, 0)
+    sim = lib.Sim(par, geom, (0, 0, 0), hi)
+    sim.upload(g["U0"])
+    rc, t, dt, hist = sim.advance(5)
+    assert rc == 0
+    pf = tmp_path / "plt00005"
+    sim.write_plotfile(pf, t, 5)
+    h, U = read_plotfile(str(pf))
+    assert h["dim"] == geom.dim and h["step"] == 5 and h["time"] == pytest.approx(t, rel=1e-14)
+    assert np.array_equal(U, sim.download())
+    other = lib.Sim(par, geom, (0, 0, 0), hi)
+    t2, st2 = other.read_plotfile(pf)
+    assert st2 == 5 and np.array_equal(other.download(), sim.download())
+    sim.close()
+    other.close()
