@@ -167,12 +167,12 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (g && g->dim != 0 && g->dim != 1 && g->dim != 2 && g->dim != 3) return CTU_ERR_BAD_ARG;
     if (g && g->dim == 2) {
         // the 2-D Cartesian path (Castro_ctu_hydro.cpp:530-650): one zone in z; PPM / PLM, the three Riemann solvers, any passives, the
-        // edge-state thermodynamics options.  Not instantiated for it: sources / gravity, hybrid Riemann, the flux limiter, the
+        // edge-state thermodynamics options, source terms (constant gravity along y).  Not instantiated for it: hybrid Riemann, the flux limiter, the
         // hydrostatic reconstructions, ppm_temp_fix, the Helmholtz EOS
         if (g->domlo[2] != g->domhi[2]) return CTU_ERR_BAD_ARG;
-        if (p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->do_grav || p->use_pslope || p->ppm_well_balanced || p->ppm_temp_fix ||
-            p->eos_kind != 0)
+        if (p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->use_pslope || p->ppm_well_balanced || p->ppm_temp_fix || p->eos_kind != 0)
             return CTU_ERR_UNSUPPORTED;
+        if (p->do_grav && g->coord != 0) return CTU_ERR_UNSUPPORTED;      // constant gravity (along y) in Cartesian 2-D runs only
     }
     if (g) {      // "external boundaries meeting at a corner not supported" (Castro_bc_fill_nd.cpp:64-98): inflow faces in two directions
         int ndir_inflow = 0;
@@ -452,8 +452,8 @@ HydroRun* hydro_begin(ctu_workspace_t* ws, const ctu_params_t* par, const ctu_ge
     // source terms: NSRC = 7 components on grow(valid, NUM_GROW_SRC); src_corr only together with old_src
     std::memset(&r->osrc, 0, sizeof(A4)); std::memset(&r->scorr, 0, sizeof(A4));
     r->have_src = old_src != nullptr;
-    if ((src_corr && !old_src) || (old_src && (old_src->ncomp < 7 || !fab_covers(old_src, grow(r->vbx, CTU_NGROW_SRC)))) ||
-        (src_corr && (src_corr->ncomp < 7 || !fab_covers(src_corr, grow(r->vbx, CTU_NGROW_SRC))))) {
+    if ((src_corr && !old_src) || (old_src && (old_src->ncomp < 7 || !fab_covers(old_src, growd(r->vbx, CTU_NGROW_SRC, P.dim)))) ||
+        (src_corr && (src_corr->ncomp < 7 || !fab_covers(src_corr, growd(r->vbx, CTU_NGROW_SRC, P.dim))))) {
         delete r; *rc_out = CTU_ERR_BAD_ARG; return nullptr;
     }
     if (old_src) r->osrc = make_a4(*old_src);
@@ -744,7 +744,7 @@ int hydro_box_2d(HydroRun* r) {
     const int np = r->np, NQS = QS_X + np, NIS = IS_X + np, NFX = FX_X + np;
     cudaStream_t st = r->st;
     const Box3 tb = r->vbx;
-    if (r->have_src) return CTU_ERR_UNSUPPORTED;
+    if (r->have_src && P.coord != 0) return CTU_ERR_UNSUPPORTED;
     const Box3 qbx = grow(tb, 4, 4, 0), obx = grow(tb, 1, 1, 0);
     Box3 ibx = obx; ibx.hi[0] += 1; ibx.hi[1] += 1;
     const size_t ni = ibx.npts();
@@ -772,7 +772,19 @@ int hydro_box_2d(HydroRun* r) {
     lb = make_lb(obx);
     k_flat_div_2d<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb);
     const bool rz = P.coord != 0;       // cylindrical R-Z: geometric sources in the radial tracing, pressure-free radial momentum flux
-    if (P.ppm_type == 0) {
+    if (r->have_src) {                  // source terms (src_to_prim on grow(box, 3), then traced by PPM / added by PLM in both directions)
+        const A4 srcq = make_a4(p, sbx); p += sbx.npts() * NSRCQ;
+        const LaunchBox ls = make_lb(sbx);
+        k_src_to_prim<0><<<nblocks(ls.n), TPB, 0, st>>>(P, r->Sb, qs, r->osrc, r->scorr, r->P_predictor, srcq, ls, r->dt, ws->d_counters + 5);
+        if (P.ppm_type == 0) {
+            k_trace_plm<0, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, srcq);
+            k_trace_plm<1, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, srcq);
+        } else {
+            k_trace<0, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, srcq, ws->d_counters + 5);
+            k_trace<1, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, srcq, ws->d_counters + 5);
+        }
+        ++r->launches;
+    } else if (P.ppm_type == 0) {
         k_trace_plm<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none);      // adds its own geometry terms
         k_trace_plm<1, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none);
     } else {

@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(TPB) k_init_tail(const DevPar P, const A4 S, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Constant gravity (gravity.gravity_type = "ConstantGrav": g = const_grav along z in 3-D), SURVEY §8(f) rank 1.
+// Constant gravity (gravity.gravity_type = "ConstantGrav": g = const_grav along z in 3-D, along y in 2-D), SURVEY §8(f) rank 1.
 //   k_grav_old: Castro::construct_old_gravity_source (Source/gravity/Castro_gravity.cpp:300-428) on every zone of
 //               grow(valid, NUM_GROW_SRC) that lies inside the domain or is a periodic image (Sborder already holds the right
 //               state there, so no separate FillPatch of the source is needed for those zones; physical boundaries are filled
@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(TPB) k_grav_old(const DevPar P, const A4 Sb, c
     for (int d = 0; d < 3; ++d)
         if (!P.periodic[d] && (idx[d] < P.domlo[d] || idx[d] > P.domhi[d])) return;
     const long ob = Sb.idx(i, j, k);
-    const double grav[3] = {0.0, 0.0, const_grav};
+    double grav[3] = {0.0, 0.0, 0.0};
+    grav[P.dim - 1] = const_grav;          // ConstantGrav points along the last coordinate direction of the run
     double src[7] = {0, 0, 0, 0, 0, 0, 0};
     double snew[3];
     const double rho = Sb.at(ob, URHO);
@@ -567,8 +568,12 @@ __global__ void __launch_bounds__(TPB) k_grav_new(const DevPar P, const A4 Sb, c
     double dt0 = DT_HUGE, dt1 = DT_HUGE;
     if (active) {
         const long ob = Sb.idx(i, j, k), on = Sn.idx(i, j, k);
-        const double vol = P.dx[0] * P.dx[1] * P.dx[2];
-        const double gold[3] = {0.0, 0.0, a.const_grav}, gnew[3] = {0.0, 0.0, a.const_grav};
+        // volume MultiFab of AMReX; the reference zeroes the widths of the directions the run does not have (Castro_gravity.cpp:471-477)
+        const bool two_d = (P.dim == 2);
+        const double vol = two_d ? P.dx[0] * P.dx[1] : P.dx[0] * P.dx[1] * P.dx[2];
+        const double dx2 = two_d ? 0.0 : P.dx[2];
+        double gold[3] = {0.0, 0.0, 0.0}, gnew[3] = {0.0, 0.0, 0.0};
+        gold[P.dim - 1] = a.const_grav; gnew[P.dim - 1] = a.const_grav;
         double src[7] = {0, 0, 0, 0, 0, 0, 0};
         double u[7];
 #pragma unroll
@@ -618,7 +623,7 @@ __global__ void __launch_bounds__(TPB) k_grav_new(const DevPar P, const A4 Sb, c
             const A4& m0 = a.mflux[0]; const A4& m1 = a.mflux[1]; const A4& m2 = a.mflux[2];
             SrEcorr += hdtInv * (m0(i, j, k, 0) * gxl * P.dx[0] + m0(i + 1, j, k, 0) * gxr * P.dx[0] +
                                  m1(i, j, k, 0) * gyl * P.dx[1] + m1(i, j + 1, k, 0) * gyr * P.dx[1] +
-                                 m2(i, j, k, 0) * gzl * P.dx[2] + m2(i, j, k + 1, 0) * gzr * P.dx[2]) / vol;
+                                 (two_d ? 0.0 : m2(i, j, k, 0)) * gzl * dx2 + (two_d ? 0.0 : m2(i, j, k + 1, 0)) * gzr * dx2) / vol;
         }
         src[UEDEN] = SrEcorr;
 #pragma unroll
@@ -865,7 +870,7 @@ int ctu_sim_create(ctu_sim_t** out, const ctu_params_t* par, const ctu_geom_t* g
     if (rc) { ctu_sim_destroy(s); return rc; }
     if (par->do_grav) {
         if (par->grav_source_type < 1 || par->grav_source_type > 4) { ctu_sim_destroy(s); return CTU_ERR_UNSUPPORTED; }
-        const Box3 sbx = grow(s->vbx, CTU_NGROW_SRC);
+        const Box3 sbx = growd(s->vbx, CTU_NGROW_SRC, geom->dim == 2 ? 2 : 3);
         bool ok = cudaMalloc(&s->osrc, (size_t)sbx.npts() * 7 * sizeof(double)) == cudaSuccess &&
                   cudaMalloc(&s->d_dt2, 2 * sizeof(unsigned long long)) == cudaSuccess;
         for (int d = 0; d < 3 && ok; ++d) {
@@ -1085,7 +1090,7 @@ static int sim_step_hydro_grav(ctu_sim_t* s, double dt, double dt_est[2], int n_
     const DevPar P = make_devpar(&s->par, &s->geom);
     ctu_fab_t sb = s->fab(s->cur), sn = s->fab(1 - s->cur);
     const A4 Sb = make_a4(sb), Sn = make_a4(sn);
-    const Box3 sbx = grow(s->vbx, CTU_NGROW_SRC);
+    const Box3 sbx = growd(s->vbx, CTU_NGROW_SRC, P.dim);
     ctu_fab_t fo;
     fo.p = s->osrc; fo.ncomp = 7;
     for (int d = 0; d < 3; ++d) { fo.lo[d] = sbx.lo[d]; fo.hi[d] = sbx.hi[d]; }
@@ -1102,7 +1107,7 @@ static int sim_step_hydro_grav(ctu_sim_t* s, double dt, double dt_est[2], int n_
     GravNewArgs ga;
     std::memset(&ga, 0, sizeof(ga));
     if (par.grav_source_type == 4) {
-        for (int d = 0; d < 3; ++d) {
+        for (int d = 0; d < P.dim; ++d) {
             mf[d].p = s->mflux[d]; mf[d].ncomp = 1;
             for (int e = 0; e < 3; ++e) { mf[d].lo[e] = s->vbx.lo[e]; mf[d].hi[e] = s->vbx.hi[e] + (e == d ? 1 : 0); }
             mfp[d] = &mf[d];

@@ -66,6 +66,7 @@ if [ "$what" = sod1d ]; then build Sod Castro1d_sod DIM=1; fi
 if [ "$what" = sedov1d ]; then build Sedov Castro1d_sedov DIM=1; fi      # 1-D spherical / cylindrical Sedov (inputs.1d.sph, inputs.1d.cyl): the non-Cartesian 1-D terms
 if [ "$what" = sedov2d ]; then build Sedov Castro2d_sedov DIM=2; fi
 if [ "$what" = kh2d ]; then build KH Castro2d_kh DIM=2; fi
+if [ "$what" = rt2d ]; then build RT Castro2d_rt DIM=2; fi      # Rayleigh-Taylor as shipped (inputs_2d): constant gravity along y
 if [ "$what" = all ] || [ "$what" = sod ];    then build Sod Castro3d_sod DIM=3; fi
 # Noh implosion: the one hydro test whose outer ghost zones come from problem_bc_fill (time-dependent inflow); golden generator for the bc hook
 if [ "$what" = noh ]; then build Noh Castro3d_noh DIM=3; fi

@@ -244,6 +244,8 @@ CASES_2D = {
     "sedov2d_rz_cgf": dict(kind="sedov", solver=0, coord=1, lo_bc=(3, 3, 2), hi_bc=(2, 2, 2)),
     "sedov2d_rz_hllc": dict(kind="sedov", solver=2, coord=1, lo_bc=(3, 3, 2), hi_bc=(2, 2, 2)),
     "sedov2d_rz_plm_24x32": dict(kind="sedov", solver=0, coord=1, lo_bc=(3, 3, 2), hi_bc=(2, 2, 2), par=dict(ppm_type=0)),
+    "rt2d_cgf": dict(kind="rt", solver=0, gst=4), "rt2d_hllc_gst2": dict(kind="rt", solver=2, gst=2),
+    "rt2d_plm_gst3": dict(kind="rt", solver=0, gst=3, par=dict(ppm_type=0)),
     "kh2d_cgf": dict(kind="kh", solver=0, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0, center=(0.5, 0.5, 0.0))),
     "kh2d_hllc": dict(kind="kh", solver=2, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.3, center=(0.5, 0.5, 0.0))),
 }
@@ -262,6 +264,12 @@ def load_2d_case(name):
         geom = abi.make_geom(n_cell, probhi=probhi, lo_bc=c.get("lo_bc", (2, 2, 2)), hi_bc=c.get("hi_bc", (2, 2, 2)), dim=2, coord=c.get("coord", 0))
         # inputs.2d.cyl_in_cartcoords: p_ambient 1e-6; inputs.2d.sph_in_cylcoords (R-Z): 1e-5
         prob = dict(r_init=0.01, p_ambient=1.e-5 if c.get("coord", 0) else 1.e-6, exp_energy=1.0, dens_ambient=1.0, nsub=10)
+    elif c["kind"] == "rt":      # Exec/hydro_tests/RT/inputs_2d: periodic x, slip walls in y, const_grav = -1 along y, gamma = 5/3
+        par.cfl, par.init_shrink, par.change_max = 0.9, 0.3, 1.1
+        par.eos_assume_neutral = 1
+        par.do_grav, par.grav_source_type, par.const_grav = 1, c["gst"], -1.0
+        geom = abi.make_geom(n_cell, probhi=probhi, periodic=(1, 0, 0), lo_bc=(0, 4, 2), hi_bc=(0, 4, 2), dim=2)
+        prob = dict(frac=0.5, rho_1=1.0, rho_2=2.0, p0_base=5.0)
     else:
         par.cfl, par.init_shrink, par.change_max = 0.5, 0.1, 1.1
         par.small_temp, par.small_dens = 1.e-9, 1.e-4

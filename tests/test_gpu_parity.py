@@ -1003,7 +1003,7 @@ def test_two_dimensional_matches_reference(name):
     nx, ny = int(g["n_cell"][0]), int(g["n_cell"][1])
     sim = lib.Sim(par, geom, (0, 0, 0), (nx - 1, ny - 1, 0))
     hook = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "castro_b200", "hooks",
-                        "libctu_hook_%s.so" % ("sedov2d" if name.startswith("sedov") else "kh2d"))
+                        "libctu_hook_%s.so" % ("sedov2d" if name.startswith("sedov") else "rt2d" if name.startswith("rt") else "kh2d"))
     if os.path.exists(hook):
         sim.init_problem("hook:" + hook, prob)
         assert_bitwise(sim.download(), g["U0"], name + " initial data")
@@ -1026,7 +1026,7 @@ def test_two_dimensional_unsupported_options_are_refused():
     from castro_b200 import lib
     from cases import load_2d_case
     par, geom, prob, g, snaps = load_2d_case("sedov2d_cgf")
-    for k in ("hybrid_riemann", "limit_fluxes_on_small_dens", "use_pslope", "do_grav"):
+    for k in ("hybrid_riemann", "limit_fluxes_on_small_dens", "use_pslope", "ppm_temp_fix"):
         par, geom, prob, g, snaps = load_2d_case("sedov2d_cgf")
         setattr(par, k, 1)
         lib.params_finalize(par)

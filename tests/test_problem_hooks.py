@@ -175,7 +175,7 @@ def test_noh_with_bc_hook_on_gpu(name):
 
 # ---- the same problem headers compiled for AMREX_SPACEDIM = 2 (libctu_hook_sedov2d / kh2d) ---------------------------------------------
 HOOK_CASES_2D = [("sedov2d", "sedov2d_cgf"), ("sedov2d", "sedov2d_cg_24x16"), ("sedov2d", "sedov2d_symm_cgf"), ("sedov2d", "sedov2d_rz_cgf"), ("kh2d", "kh2d_cgf"),
-                 ("kh2d", "kh2d_hllc")]
+                 ("kh2d", "kh2d_hllc"), ("rt2d", "rt2d_cgf")]
 
 
 @pytest.mark.parametrize("hook,golden", HOOK_CASES_2D)
