@@ -820,8 +820,13 @@ int ctu_parse_inputs(const char* path, const char* overrides, ctu_params_t* par,
         }
         if (has("castro.speed_limit")) { double v = 0.0; gd("castro.speed_limit", v); if (v != 0.0) return CTU_ERR_UNSUPPORTED; }
     }
+    // the number of entries of amr.n_cell is the dimensionality of the run (the reference fixes it at build time: AMREX_SPACEDIM);
+    // directions the run does not have carry one zone of unit width
     int nc[3] = {32, 32, 32};
+    const int dim = has("amr.n_cell") ? std::min<int>(3, std::max<int>(1, (int)tab["amr.n_cell"].size())) : 3;
+    for (int d = dim; d < 3; ++d) nc[d] = 1;
     gi3("amr.n_cell", nc);
+    geom->dim = dim;
     double plo[3] = {0, 0, 0}, phi[3] = {1, 1, 1};
     gd3("geometry.prob_lo", plo); gd3("geometry.prob_hi", phi);
     int per[3] = {0, 0, 0}, lobc[3] = {0, 0, 0}, hibc[3] = {0, 0, 0}, coord = 0;
@@ -840,7 +845,9 @@ int ctu_parse_inputs(const char* path, const char* overrides, ctu_params_t* par,
         std::string s;
         for (auto& k : order) {
             if (k.rfind("problem.", 0) != 0 || tab[k].empty()) continue;
-            s += k.substr(8) + "=" + tab[k][0] + "\n";
+            std::string v = tab[k][0];
+            for (size_t m = 1; m < tab[k].size(); ++m) v += "," + tab[k][m];      // arrays (problem.center = 0.5 0.5 0.0): v1,v2,v3
+            s += k.substr(8) + "=" + v + "\n";
         }
         if (s.size() + 1 > prob_len) return CTU_ERR_NOMEM;
         std::memcpy(prob_out, s.c_str(), s.size() + 1);

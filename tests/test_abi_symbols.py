@@ -109,3 +109,24 @@ def test_parse_inputs_refuses_keys_that_leave_the_supported_path():
                 "castro.use_reconstructed_gamma1=1", "castro.speed_limit=1.e9"):
         with pytest.raises(lib.CtuError):
             lib.parse_inputs(inputs, bad)
+
+
+def test_parse_inputs_dimensionality_and_coordinates(tmp_path):
+    """the number of entries of amr.n_cell gives the dimensionality of the run (the reference fixes AMREX_SPACEDIM at build time);
+    geometry.coord_sys and array-valued problem parameters come through (files laid out like Exec/hydro_tests/Sedov/inputs.2d.sph_in_cylcoords,
+    inputs.1d.sph and KH/inputs.2d)"""
+    from castro_b200 import lib
+    f = tmp_path / "inputs.2d"
+    f.write_text("max_step = 7\ngeometry.is_periodic = 0 0\ngeometry.coord_sys = 1\ngeometry.prob_lo = 0 0\ngeometry.prob_hi = 0.5 0.25\n"
+                 "amr.n_cell = 16 8\ncastro.lo_bc = 3 3\ncastro.hi_bc = 2 2\ncastro.cfl = 0.5\namr.max_level = 0\n"
+                 "problem.center = 0.5 0.5 0.0\nproblem.r_init = 0.01\n")
+    p, g, nc, ms, stop, prob = lib.parse_inputs(str(f))
+    assert g.dim == 2 and g.coord == 1 and nc == (16, 8, 1) and ms == 7
+    assert list(g.lo_bc)[:2] == [3, 3] and g.dx[0] == 0.5 / 16 and g.dx[1] == 0.25 / 8 and g.domhi[2] == 0
+    assert "center=0.5,0.5,0.0" in prob and "r_init=0.01" in prob
+    f1 = tmp_path / "inputs.1d"
+    f1.write_text("geometry.coord_sys = 2\ngeometry.prob_lo = 0\ngeometry.prob_hi = 1\namr.n_cell = 32\ncastro.lo_bc = 3\ncastro.hi_bc = 2\n")
+    p, g, nc, ms, stop, prob = lib.parse_inputs(str(f1))
+    assert g.dim == 1 and g.coord == 2 and nc == (32, 1, 1) and g.dx[0] == 1.0 / 32
+    p, g, nc, ms, stop, prob = lib.parse_inputs(os.path.join(ROOT, "bench_inputs", "inputs.sedov3d"))
+    assert g.dim == 3 and g.coord == 0
