@@ -167,11 +167,10 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (g && g->dim != 0 && g->dim != 1 && g->dim != 2 && g->dim != 3) return CTU_ERR_BAD_ARG;
     if (g && g->dim == 2) {
         // the 2-D Cartesian path (Castro_ctu_hydro.cpp:530-650): one zone in z; PPM / PLM, the three Riemann solvers, any passives, the
-        // edge-state thermodynamics options, source terms (constant gravity along y).  Not instantiated for it: hybrid Riemann, the flux limiter, the
-        // hydrostatic reconstructions, ppm_temp_fix, the Helmholtz EOS
+        // edge-state thermodynamics options, source terms (constant gravity along y), the hydrostatic reconstructions.  Not instantiated for it: hybrid Riemann, the flux
+        // limiter, ppm_temp_fix, the Helmholtz EOS
         if (g->domlo[2] != g->domhi[2]) return CTU_ERR_BAD_ARG;
-        if (p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->use_pslope || p->ppm_well_balanced || p->ppm_temp_fix || p->eos_kind != 0)
-            return CTU_ERR_UNSUPPORTED;
+        if (p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->ppm_temp_fix || p->eos_kind != 0) return CTU_ERR_UNSUPPORTED;
         if (p->do_grav && g->coord != 0) return CTU_ERR_UNSUPPORTED;      // constant gravity (along y) in Cartesian 2-D runs only
     }
     if (g) {      // "external boundaries meeting at a corner not supported" (Castro_bc_fill_nd.cpp:64-98): inflow faces in two directions

@@ -321,7 +321,9 @@ int ctu_dist_create(ctu_dist_t** out, const ctu_params_t* par, const ctu_geom_t*
                     const char id[128], size_t workspace_bytes, void* stream) {
     if (!out || !par || !geom || !dims || rank < 0 || rank >= world || dims[0] * dims[1] * dims[2] != world) return CTU_ERR_BAD_ARG;
     if (!device_ok()) return CTU_ERR_NO_DEVICE;
-    if ((geom->dim == 1 || geom->dim == 2) && world > 1) return CTU_ERR_UNSUPPORTED;       // 1-D / 2-D boxes are not decomposed
+    if (geom->dim == 1 && world > 1) return CTU_ERR_UNSUPPORTED;       // 1-D boxes are not decomposed
+    // a 2-D run is decomposed in x and y only; with one box and no periodicity in z the halo plan has no message with d_z != 0
+    if (geom->dim == 2 && world > 1 && (dims[2] != 1 || geom->periodic[2])) return CTU_ERR_BAD_ARG;
     int c[3], lo[3], hi[3];
     rank_coords(rank, dims, c);
     if (!box_of(c, dims, geom->domlo, geom->domhi, lo, hi)) return CTU_ERR_BAD_ARG;

@@ -222,6 +222,10 @@ CASES_2D = {
     "rt2d_cgf": (RT2D_EXE, RT2D_INPUTS, (16, 32), 40, [0, 40], ["castro.riemann_solver=0"]),
     "rt2d_hllc_gst2": (RT2D_EXE, RT2D_INPUTS, (16, 32), 40, [0, 40], ["castro.riemann_solver=2", "castro.grav_source_type=2"]),
     "rt2d_plm_gst3": (RT2D_EXE, RT2D_INPUTS, (16, 32), 40, [0, 40], ["castro.riemann_solver=0", "castro.ppm_type=0", "castro.grav_source_type=3"]),
+    # hydrostatic-pressure-aware reconstructions under gravity in 2-D (PPM pslope, well-balanced PPM, PLM pslope)
+    "rt2d_pslope": (RT2D_EXE, RT2D_INPUTS, (16, 32), 40, [0, 40], ["castro.riemann_solver=0", "castro.use_pslope=1"]),
+    "rt2d_wellbal": (RT2D_EXE, RT2D_INPUTS, (16, 32), 40, [0, 40], ["castro.riemann_solver=2", "castro.ppm_well_balanced=1"]),
+    "rt2d_plm_pslope": (RT2D_EXE, RT2D_INPUTS, (16, 32), 40, [0, 40], ["castro.riemann_solver=0", "castro.ppm_type=0", "castro.use_pslope=1"]),
     "kh2d_cgf": (KH2D_EXE, KH2D_INPUTS, (32, 32), 20, [0, 20], ["castro.riemann_solver=0"]),
     "kh2d_hllc": (KH2D_EXE, KH2D_INPUTS, (32, 16), 20, [0, 20], ["castro.riemann_solver=2", "problem.bulk_velocity=0.3", "geometry.prob_hi=1.0 0.5"]),
 }

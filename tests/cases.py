@@ -246,6 +246,8 @@ CASES_2D = {
     "sedov2d_rz_plm_24x32": dict(kind="sedov", solver=0, coord=1, lo_bc=(3, 3, 2), hi_bc=(2, 2, 2), par=dict(ppm_type=0)),
     "rt2d_cgf": dict(kind="rt", solver=0, gst=4), "rt2d_hllc_gst2": dict(kind="rt", solver=2, gst=2),
     "rt2d_plm_gst3": dict(kind="rt", solver=0, gst=3, par=dict(ppm_type=0)),
+    "rt2d_pslope": dict(kind="rt", solver=0, gst=4, par=dict(use_pslope=1)), "rt2d_wellbal": dict(kind="rt", solver=2, gst=4, par=dict(ppm_well_balanced=1)),
+    "rt2d_plm_pslope": dict(kind="rt", solver=0, gst=4, par=dict(ppm_type=0, use_pslope=1)),
     "kh2d_cgf": dict(kind="kh", solver=0, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.0, center=(0.5, 0.5, 0.0))),
     "kh2d_hllc": dict(kind="kh", solver=2, prob=dict(problem=3, rho1=1.0, rho2=2.0, pressure=2.5, bulk_velocity=0.3, center=(0.5, 0.5, 0.0))),
 }

@@ -12,9 +12,10 @@ NG = 4
 class OracleBoxEngine:
     def __init__(self, par, geom, lo, hi):
         self.par, self.geom, self.lo, self.hi = par, geom, tuple(lo), tuple(hi)
-        self.glo = tuple(l - NG for l in lo)
-        self.ghi = tuple(h + NG for h in hi)
-        shp = tuple(hi[d] - lo[d] + 1 + 2 * NG for d in (2, 1, 0))
+        ngd = (NG, NG, 0 if geom.dim == 2 else NG)          # a 2-D run has no ghost zones in z
+        self.glo = tuple(l - g for l, g in zip(lo, ngd))
+        self.ghi = tuple(h + g for h, g in zip(hi, ngd))
+        shp = tuple(hi[d] - lo[d] + 1 + 2 * ngd[d] for d in (2, 1, 0))
         self.U = np.zeros((par.num_state,) + shp)
         self.launches = 0
 
@@ -22,6 +23,11 @@ class OracleBoxEngine:
         return tuple(slice(lo[d] - self.glo[d], hi[d] - self.glo[d] + 1) for d in (2, 1, 0))
 
     def init_problem(self, problem, prob):
+        if problem == "upload":          # prob["U0"]: the whole domain's initial state [ncomp, nz, ny, nx] (a reference plotfile)
+            kz, jy, ix = self._sl(self.lo, self.hi)
+            U0 = prob["U0"]
+            self.U[:, kz, jy, ix] = U0[:, self.lo[2]:self.hi[2] + 1, self.lo[1]:self.hi[1] + 1, self.lo[0]:self.hi[0] + 1]
+            return
         assert problem == "Sedov"
         n_cell = tuple(self.geom.domhi[d] - self.geom.domlo[d] + 1 for d in range(3))
         self.U = O.sedov_init(self.par, self.geom, n_cell, lo=self.lo, hi=self.hi, **prob)
@@ -42,7 +48,7 @@ class OracleBoxEngine:
         O.clean_state(self.par, self.U, self.glo, self.lo, self.hi)
 
     def step_fill(self):
-        O.fill_boundary(self.par, self.geom, self.U, self.lo, self.hi)
+        O.fill_boundary(self.par, self.geom, self.U, self.lo, self.hi, lo_arr=self.glo)
         O.clean_state(self.par, self.U, self.glo, self.glo, self.ghi)
 
     def step_hydro(self, dt):

@@ -96,8 +96,8 @@ def clean_state(par, U, lo_arr, lo, hi, npass=1):
     lib().orc_clean_state(C.byref(par), abi.Int3(*lo), abi.Int3(*hi), C.byref(f), C.c_int(npass))
 
 
-def fill_boundary(par, geom, U, vlo, vhi, ng=abi.CTU_NGROW):
-    f = fab(U, tuple(l - ng for l in vlo))
+def fill_boundary(par, geom, U, vlo, vhi, ng=abi.CTU_NGROW, lo_arr=None):
+    f = fab(U, lo_arr if lo_arr is not None else tuple(l - ng for l in vlo))
     lib().orc_fill_boundary(C.byref(par), C.byref(geom), abi.Int3(*vlo), abi.Int3(*vhi), C.byref(f), C.c_int(ng))
 
 

@@ -33,11 +33,18 @@ def _worker(rank, world, port, name, nsteps, dims, out):
         import oracle_lib as O
         from oracle_engine import OracleBoxEngine
         from castro_b200.dist import DistSim
-        par, geom, prob, g, snaps = load_case(name)
+        if "2d" in name:          # 2-D runs start from the reference's own initial plotfile
+            from cases import load_2d_case
+            par, geom, prob, g, snaps = load_2d_case(name)
+        else:
+            par, geom, prob, g, snaps = load_case(name)
         O.params_finalize(par)
         n_cell = tuple(int(x) for x in g["n_cell"])
         sim = DistSim(par, geom, n_cell, OracleBoxEngine, comm=dist, rank=rank, world=world, dims=dims)
-        sim.init_problem("Sedov", prob)
+        if "2d" in name:
+            sim.init_problem("upload", dict(U0=g["U0"]))
+        else:
+            sim.init_problem("Sedov", prob)
         status, hist = sim.advance(nsteps)
         assert status == 0
         mine = torch.from_numpy(sim.engine.download())
@@ -58,12 +65,18 @@ def _worker(rank, world, port, name, nsteps, dims, out):
     ("sedov16_hllc", 5, 2, (2, 1, 1)),
     ("sedov16_periodic_hllc", 10, 2, (1, 2, 1)),     # both y-neighbours are the same peer: message-order check
     ("sedov16_cgf", 5, 4, (2, 1, 2)),
+    # 2-D runs decomposed in x, in y and in both (kh2d: periodic, every box is its own neighbour's neighbour twice)
+    ("sedov2d_hllc", 40, 2, (2, 1, 1)), ("kh2d_cgf", 20, 2, (1, 2, 1)), ("kh2d_hllc", 20, 4, (2, 2, 1)), ("sedov2d_rz_cgf", 80, 2, (1, 2, 1)),
 ])
 def test_multibox_matches_reference_golden(tmp_path, name, nsteps, world, dims):
     out = str(tmp_path / "out.npz")
     mp.spawn(_worker, args=(world, _free_port(), name, nsteps, dims, out), nprocs=world, join=True)
     r = np.load(out)
-    par, geom, prob, g, snaps = load_case(name)
+    if "2d" in name:
+        from cases import load_2d_case
+        par, geom, prob, g, snaps = load_2d_case(name)
+    else:
+        par, geom, prob, g, snaps = load_case(name)
     ref = g["U%d" % nsteps]
     assert np.array_equal(r["U"], ref), "multi-box run differs from the reference golden state"
     np.testing.assert_allclose(r["times"], g["times"][:nsteps + 1], rtol=1e-14, atol=0)

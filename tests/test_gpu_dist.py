@@ -84,6 +84,10 @@ def _worker_cpp(rank, world, port, kind, name, nsteps, dims, out, streamed):
             from cases import load_rt_case
             par, geom, g, snaps = load_rt_case(name)
             prob = None
+        elif kind == "2d":
+            from cases import load_2d_case
+            par, geom, prob, g, snaps = load_2d_case(name)
+            prob = None
         else:
             par, geom, prob, g, snaps = load_case(name)
         lib.params_finalize(par)
@@ -158,6 +162,17 @@ def test_two_gpus_cpp_dist_gravity(tmp_path, name, dims):
     par, geom, g, snaps = load_rt_case(name)
     n = snaps[-1]
     r = _spawn2(tmp_path, "rt", name, n, dims, False)
+    assert np.array_equal(r["U"], g["U%d" % n])
+    np.testing.assert_allclose(r["times"], g["times"][:n + 1], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("name,dims", [("sedov2d_hllc", (2, 1, 1)), ("kh2d_cgf", (1, 2, 1)), ("rt2d_cgf", (1, 2, 1)), ("sedov2d_rz_cgf", (2, 1, 1))])
+def test_two_gpus_cpp_dist_two_dimensional(tmp_path, name, dims):
+    """2-D runs (Cartesian, periodic, with gravity, R-Z) on two boxes through the C++ driver against the single-run goldens, bit for bit"""
+    from cases import load_2d_case
+    par, geom, prob, g, snaps = load_2d_case(name)
+    n = snaps[-1]
+    r = _spawn2(tmp_path, "2d", name, n, dims, False)
     assert np.array_equal(r["U"], g["U%d" % n])
     np.testing.assert_allclose(r["times"], g["times"][:n + 1], rtol=1e-14, atol=0)
 

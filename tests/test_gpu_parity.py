@@ -1026,7 +1026,7 @@ def test_two_dimensional_unsupported_options_are_refused():
     from castro_b200 import lib
     from cases import load_2d_case
     par, geom, prob, g, snaps = load_2d_case("sedov2d_cgf")
-    for k in ("hybrid_riemann", "limit_fluxes_on_small_dens", "use_pslope", "ppm_temp_fix"):
+    for k in ("hybrid_riemann", "limit_fluxes_on_small_dens", "ppm_temp_fix"):
         par, geom, prob, g, snaps = load_2d_case("sedov2d_cgf")
         setattr(par, k, 1)
         lib.params_finalize(par)
