@@ -41,6 +41,9 @@ namespace ctu {
 #ifndef CTU_Q_LDG
 #define CTU_Q_LDG 0
 #endif
+#ifndef CTU_TRANS2_DUAL
+#define CTU_TRANS2_DUAL 0
+#endif
 #ifndef CTU_TY
 #define CTU_TY 2
 #endif
@@ -335,6 +338,30 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
     const int oc = L::CT::off(c.tx + pq, c.ty, c.tz);
     const double cl = sC(oc, 0), cr = sC(oc + L::CT::stride(N), 0);
     const int idx = (N == 0) ? c.i : (N == 1) ? c.j : c.k;
+#if CTU_TRANS2_DUAL
+    // developer switch: interior faces (both transverse corrections wanted) run the two independent state updates + Riemann solves in ONE
+    // straight-line region, so that the instruction scheduler can interleave their dependent division / sqrt chains
+    if (in1 && in2) {
+        constexpr int sN1 = L::F1T::stride(N), sT1 = L::F1T::stride(T1), sN2 = L::F2T::stride(N), sT2 = L::F2T::stride(T2);
+        const int oz1 = L::F1T::off(c.tx + pg, c.ty, c.tz), oz2 = L::F2T::off(c.tx + pg, c.ty, c.tz);
+        double qlo1[6], qro1[6], xlo1[NP], xro1[NP], qlo2[6], qro2[6], xlo2[NP], xro2[NP];
+        trans_single_side<M, NP, typename L::S1, sT1>(P, sF1, oz1, ql, xl, a.cdt1, qlo1, xlo1);
+        trans_single_side<M, NP, typename L::S2, sT2>(P, sF2, oz2, ql, xl, a.cdt2, qlo2, xlo2);
+        trans_single_side<M, NP, typename L::S1, sT1>(P, sF1, oz1 + sN1, qr, xr, a.cdt1, qro1, xro1);
+        trans_single_side<M, NP, typename L::S2, sT2>(P, sF2, oz2 + sN2, qr, xr, a.cdt2, qro2, xro2);
+        double Fa[6], FXa[NP], uga, pga, Fb[6], FXb[NP], ugb, pgb;
+        solve_face_r<M, N, NP, RS>(P, qlo1, qro1, xlo1, xro1, cl, cr, idx, Fa, uga, pga, FXa);
+        solve_face_r<M, N, NP, RS>(P, qlo2, qro2, xlo2, xro2, cl, cr, idx, Fb, ugb, pgb, FXb);
+        const long o1 = a.Fo1.idx(c.i, c.j, c.k), o2 = a.Fo2.idx(c.i, c.j, c.k);
+#pragma unroll
+        for (int n = 0; n < FX_EINT; ++n) { a.Fo1.at(o1, n) = Fa[n]; a.Fo2.at(o2, n) = Fb[n]; }
+        a.Fo1.at(o1, FX_UG) = uga; a.Fo1.at(o1, FX_PG) = pga;
+        a.Fo2.at(o2, FX_UG) = ugb; a.Fo2.at(o2, FX_PG) = pgb;
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip) { a.Fo1.at(o1, FX_X + ip) = FXa[ip]; a.Fo2.at(o2, FX_X + ip) = FXb[ip]; }
+        return;
+    }
+#endif
     if (in1) {
         constexpr int sN = L::F1T::stride(N), sT = L::F1T::stride(T1);
         const int oz = L::F1T::off(c.tx + pg, c.ty, c.tz);
