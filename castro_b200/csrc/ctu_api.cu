@@ -167,10 +167,11 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (g && g->dim != 0 && g->dim != 1 && g->dim != 2 && g->dim != 3) return CTU_ERR_BAD_ARG;
     if (g && g->dim == 2) {
         // the 2-D Cartesian path (Castro_ctu_hydro.cpp:530-650): one zone in z; PPM / PLM, the three Riemann solvers, any passives, the
-        // edge-state thermodynamics options, source terms (constant gravity along y), the hydrostatic reconstructions.  Not instantiated for it: hybrid Riemann, the flux
-        // limiter, ppm_temp_fix, the Helmholtz EOS
+        // edge-state thermodynamics options, source terms (constant gravity along y), the hydrostatic reconstructions, hybrid Riemann and the flux limiter (Cartesian), the Helmholtz EOS.
+        // Not instantiated for it: ppm_temp_fix
         if (g->domlo[2] != g->domhi[2]) return CTU_ERR_BAD_ARG;
-        if (p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->ppm_temp_fix || p->eos_kind != 0) return CTU_ERR_UNSUPPORTED;
+        if (p->ppm_temp_fix) return CTU_ERR_UNSUPPORTED;
+        if ((p->hybrid_riemann || p->limit_fluxes_on_small_dens) && g->coord != 0) return CTU_ERR_UNSUPPORTED;      // Cartesian 2-D runs only
         if (p->do_grav && g->coord != 0) return CTU_ERR_UNSUPPORTED;      // constant gravity (along y) in Cartesian 2-D runs only
     }
     if (g) {      // "external boundaries meeting at a corner not supported" (Castro_bc_fill_nd.cpp:64-98): inflow faces in two directions
@@ -183,7 +184,7 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
         // (Castro.cpp:410-413); options that need transverse or source machinery are not instantiated for it
         if (g->domlo[1] != g->domhi[1] || g->domlo[2] != g->domhi[2]) return CTU_ERR_BAD_ARG;
         if (p->riemann_solver == 2 || p->hybrid_riemann || p->limit_fluxes_on_small_dens || p->do_grav || p->use_pslope ||
-            p->ppm_well_balanced || p->ppm_temp_fix || p->eos_kind != 0)
+            p->ppm_well_balanced || p->ppm_temp_fix)
             return CTU_ERR_UNSUPPORTED;
     }
     return 0;
@@ -694,7 +695,9 @@ int hydro_box_1d(HydroRun* r) {
     A4 none;
     std::memset(&none, 0, sizeof(none));
     LaunchBox lb = make_lb(qbx);
-    k_ctoprim<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
+    const bool helm = P.eos_kind == 1;       // the Helmholtz EOS: EK = 1 instances of the kernels that call the EOS
+    if (helm) k_ctoprim<1><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
+    else k_ctoprim<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
     lb = make_lb(obx);
     k_flat_div_1d<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb);
     // the node-centred div u is needed on the faces lo .. hi+1: one more than obx holds on the high side is not (obx = lo-1 .. hi+1)
@@ -710,7 +713,8 @@ int hydro_box_1d(HydroRun* r) {
     } else k_trace<0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, none, ws->d_counters + 5);
     Box3 xbx = tb; xbx.hi[0] += 1;
     lb = make_lb(xbx);
-    k_riemann1<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F0, lb, fd);
+    if (helm) k_riemann1<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F0, lb, fd);
+    else k_riemann1<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F0, lb, fd);
     k_av_1d<<<nblocks(lb.n), TPB, 0, st>>>(P, fd, r->Sb, F0, lb);
     UpdateArgs ua;
     std::memset(&ua, 0, sizeof(ua));
@@ -718,7 +722,8 @@ int hydro_box_1d(HydroRun* r) {
     ua.dtmin = ws->d_dtmin; ua.counters = ws->d_counters;
     ua.n_clean = r->n_clean; ua.want_dt = r->want_dt;
     lb = make_lb(tb);
-    k_update<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, r->from_sb ? r->Sb : r->Sn, r->Sn, ua, lb, r->dt);
+    if (helm) k_update<1><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, r->from_sb ? r->Sb : r->Sn, r->Sn, ua, lb, r->dt);
+    else k_update<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, r->from_sb ? r->Sb : r->Sn, r->Sn, ua, lb, r->dt);
     r->launches += 7;
     if (r->flux && r->flux[0]) {
         if (!fab_covers(r->flux[0], xbx) || r->flux[0]->ncomp < P.nstate) return CTU_ERR_BAD_ARG;
@@ -748,12 +753,13 @@ int hydro_box_2d(HydroRun* r) {
     Box3 ibx = obx; ibx.hi[0] += 1; ibx.hi[1] += 1;
     const size_t ni = ibx.npts();
     const Box3 sbx = grow(tb, 3, 3, 0);
-    const size_t need = ((size_t)qbx.npts() * NQS + ni * (2 + 4 * NIS + 4 * NFX) + (size_t)sbx.npts() * NSRCQ) * sizeof(double);
+    const int NFD = P.hybrid_riemann ? 3 : 2;      // flattening, div u [, shock flag]
+    const size_t need = ((size_t)qbx.npts() * NQS + ni * (NFD + 4 * NIS + 4 * NFX) + (size_t)sbx.npts() * NSRCQ) * sizeof(double);
     int rc = ws_reserve_bytes(ws, need, st);
     if (rc) return rc;
     double* p = ws->arena;
     const A4 qs = make_a4(p, qbx); p += qbx.npts() * NQS;
-    const A4 fd = make_a4(p, ibx); p += ni * 2;
+    const A4 fd = make_a4(p, ibx); p += ni * NFD;
     TraceArgs ta;
     std::memset(&ta, 0, sizeof(ta));
     for (int d = 0; d < 2; ++d) {
@@ -767,9 +773,13 @@ int hydro_box_2d(HydroRun* r) {
     A4 none;
     std::memset(&none, 0, sizeof(none));
     LaunchBox lb = make_lb(qbx);
-    k_ctoprim<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
+    const bool helm = P.eos_kind == 1;       // the Helmholtz EOS: EK = 1 instances of the kernels that call the EOS (Cartesian runs)
+    if (helm && (P.coord != 0 || r->have_src)) return CTU_ERR_UNSUPPORTED;
+    if (helm) k_ctoprim<1><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
+    else k_ctoprim<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
     lb = make_lb(obx);
-    k_flat_div_2d<<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb);
+    if (P.hybrid_riemann) k_flat_div_2d<true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb, r->osrc);
+    else k_flat_div_2d<false><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, lb, r->osrc);
     const bool rz = P.coord != 0;       // cylindrical R-Z: geometric sources in the radial tracing, pressure-free radial momentum flux
     if (r->have_src) {                  // source terms (src_to_prim on grow(box, 3), then traced by PPM / added by PLM in both directions)
         const A4 srcq = make_a4(p, sbx); p += sbx.npts() * NSRCQ;
@@ -801,22 +811,27 @@ int hydro_box_2d(HydroRun* r) {
     Box3 ybx = tb; ybx.hi[1] += 1;
     lb = make_lb(grow(xbx, 0, 1, 0));
     if (rz) k_riemann1<0, 0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd);
+    else if (helm) k_riemann1<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd);
     else k_riemann1<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[0], lb, fd);
     lb = make_lb(grow(ybx, 1, 0, 0));
-    k_riemann1<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd);
+    if (helm) k_riemann1<1, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd);
+    else k_riemann1<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[1], lb, fd);
     const double hdt = 0.5 * r->dt;
     lb = make_lb(xbx);
-    if (rz) k_trans_final_2d<0, 0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], fd, r->Sb, F[0], lb, hdt);
-    else k_trans_final_2d<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], fd, r->Sb, F[0], lb, hdt);
+    if (rz) k_trans_final_2d<0, 0, false><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], fd, r->Sb, F[0], lb, hdt, r->dt);
+    else if (helm) k_trans_final_2d<0, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], fd, r->Sb, F[0], lb, hdt, r->dt);
+    else k_trans_final_2d<0, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[0], ta.qp[0], qs, F1[1], fd, r->Sb, F[0], lb, hdt, r->dt);
     lb = make_lb(ybx);
-    k_trans_final_2d<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], fd, r->Sb, F[1], lb, hdt);
+    if (helm) k_trans_final_2d<1, 1><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], fd, r->Sb, F[1], lb, hdt, r->dt);
+    else k_trans_final_2d<1, 0><<<nblocks(lb.n), TPB, 0, st>>>(P, ta.qm[1], ta.qp[1], qs, F1[0], fd, r->Sb, F[1], lb, hdt, r->dt);
     UpdateArgs ua;
     std::memset(&ua, 0, sizeof(ua));
     ua.F[0] = F[0]; ua.F[1] = F[1]; ua.F[2] = F[1];          // only F[0] and F[1] are read in 2-D
     ua.dtmin = ws->d_dtmin; ua.counters = ws->d_counters;
     ua.n_clean = r->n_clean; ua.want_dt = r->want_dt;
     lb = make_lb(tb);
-    k_update<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, r->from_sb ? r->Sb : r->Sn, r->Sn, ua, lb, r->dt);
+    if (helm) k_update<1><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, r->from_sb ? r->Sb : r->Sn, r->Sn, ua, lb, r->dt);
+    else k_update<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, r->from_sb ? r->Sb : r->Sn, r->Sn, ua, lb, r->dt);
     r->launches += 9;
     for (int d = 0; d < 2; ++d) {
         const bool want_f = r->flux && r->flux[d], want_m = r->mass_flux && r->mass_flux[d];

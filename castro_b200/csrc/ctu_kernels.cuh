@@ -282,7 +282,8 @@ static __global__ void __launch_bounds__(TPB) k_av_1d(const DevPar P, const A4 f
 }
 
 // 2-D Cartesian (AMREX_SPACEDIM == 2): flattening along x and y (flatten.H:141-150), node-centred div u of advection_util.cpp:257-266
-static __global__ void __launch_bounds__(TPB) k_flat_div_2d(const DevPar P, const A4 qs, const A4 fd, const LaunchBox lb) {
+template <bool HYB = false>
+static __global__ void __launch_bounds__(TPB) k_flat_div_2d(const DevPar P, const A4 qs, const A4 fd, const LaunchBox lb, const A4 usrc) {
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
     const long oq = qs.idx(i, j, k), of = fd.idx(i, j, k);
@@ -316,6 +317,36 @@ static __global__ void __launch_bounds__(TPB) k_flat_div_2d(const DevPar P, cons
         vy = (vt - vb) * dyinv;
     }
     fd.at(of, 1) = ux + vy;
+    // Castro::shock in 2-D Cartesian coordinates (advection_util.cpp:61-200 without the z terms; hybrid Riemann solver only)
+    if (HYB) {
+        const double* __restrict__ qw = qs.p + oq + QS_W * qs.sn;
+        double div_u = 0.0;
+        div_u += 0.5 * (qu[1] - qu[-1]) * dxinv;
+        div_u += 0.5 * (qv[sj] - qv[-sj]) * dyinv;
+        double dP_x = 0.5 * (pp[1] - pp[-1]);
+        double dP_y = 0.5 * (pp[sj] - pp[-sj]);
+        const double dP_z = 0.0;
+        if (P.shock_detection_include_sources == 1) {
+            double sx = 0.0, sy = 0.0;     // the conserved old-time momentum sources (zero without source terms)
+            if (usrc.p) {
+                const long os = usrc.idx(i, j, k);
+                const double* __restrict__ mx = usrc.p + os + UMX * usrc.sn;
+                const double* __restrict__ my = usrc.p + os + UMY * usrc.sn;
+                sx = mx[1] + 2.0 * mx[0] + mx[-1];
+                sy = my[usrc.sj] + 2.0 * my[0] + my[-usrc.sj];
+            } else {
+                sx = 0.0 + 2.0 * 0.0 + 0.0; sy = sx;
+            }
+            dP_x += -0.25 * P.dx[0] * sx;
+            dP_y += -0.25 * P.dx[1] * sy;
+        }
+        const double u0 = qu[0], v0 = qv[0], w0 = qw[0];
+        const double vel = sqrt(u0 * u0 + v0 * v0 + w0 * w0);
+        double g = 0.0;
+        if (vel != 0.0) g = fabs(dP_x * u0 + dP_y * v0 + dP_z * w0) / vel;
+        g /= pp[0];
+        fd.at(of, 2) = (g > P.shock_detection_threshold && div_u < 0.0) ? 1.0 : 0.0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1109,7 +1140,7 @@ __device__ __forceinline__ void trans_single_hydro_2d(const DevPar& P, const dou
 
 template <int N, int EK = 0, bool MP = true>
 static __global__ void __launch_bounds__(TPB) k_trans_final_2d(const DevPar P, const A4 qm, const A4 qp, const A4 qs, const A4 Ft, const A4 fd,
-                                                        const A4 U, const A4 Fo, const LaunchBox lb, const double hdt) {
+                                                        const A4 U, const A4 Fo, const LaunchBox lb, const double hdt, const double dt) {
     constexpr int T = 1 - N;
     int i, j, k;
     if (!thread_zone(lb, i, j, k)) return;
@@ -1183,6 +1214,27 @@ static __global__ void __launch_bounds__(TPB) k_trans_final_2d(const DevPar P, c
     for (int n = 0; n < 6; ++n) {
         const double div_var = div1 * (U.at(ou, n) - U.at(oum, n));
         F[n] += dL * div_var;
+    }
+    // limit_hydro_fluxes_on_small_dens in 2-D (advection_util.cpp:543-645: volume dx dy, face area, 2 * AMREX_SPACEDIM = 4 faces)
+    double lf = 1.0;
+    bool limited = false;
+    if (P.limit_fluxes_on_small_dens == 1) {
+        const double density_floor = P.small_dens * 1.1;
+        const double vol = P.dx[0] * P.dx[1];
+        const double area = (N == 0) ? P.dx[1] : P.dx[0];
+        const double rhoR = U.at(ou, URHO), rhoL = U.at(oum, URHO);
+        double flux_coef = 1.0 / vol;
+        flux_coef *= dt * area;
+        const double drho = flux_coef * F[0];
+        if (rhoR >= density_floor && fabs(drho) > 0.0 && rhoR + 2 * 2 * drho < density_floor) {
+            lf = fabs((density_floor - rhoR) / (2 * 2 * drho)); limited = true;
+        } else if (rhoL >= density_floor && fabs(drho) > 0.0 && rhoL - 2 * 2 * drho < density_floor) {
+            lf = fabs((density_floor - rhoL) / (2 * 2 * drho)); limited = true;
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+        if (limited) F[n] = F[n] * lf;
         Fo.at(of, n) = F[n];
     }
     Fo.at(of, FX_UG) = ugd;
@@ -1192,6 +1244,7 @@ static __global__ void __launch_bounds__(TPB) k_trans_final_2d(const DevPar P, c
         double f = passive_flux(P, pu, xm(ip), xp(ip));
         const double div_var = div1 * (U.at(ou, UFA + ip) - U.at(oum, UFA + ip));
         f += dL * div_var;
+        if (limited) f = f * lf;
         Fo.at(of, FX_X + ip) = f;
         if (ip >= P.QFS_off && ip < P.QFS_off + P.nspec) sum += f;
     }

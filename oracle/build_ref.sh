@@ -60,6 +60,9 @@ if [ "$what" = all ] || [ "$what" = kh ];     then build KH Castro3d_kh DIM=3; f
 if [ "$what" = kh4 ]; then build KH Castro3d_kh4 DIM=3 NETWORK_INPUTS=triple_alpha_plus_o.net; fi
 # Sod_stellar: the shock tube with the Helmholtz (stellar) EOS and the 3-species ignition network; golden generator
 if [ "$what" = sodstellar ]; then build Sod_stellar Castro3d_sodstellar DIM=3 USE_MHD=FALSE; fi
+# ... and in the dimensionalities the problem ships with (GNUmakefile: DIM = 2; the README runs it in 1-D): golden generators for the Helmholtz EOS in 1-D / 2-D
+if [ "$what" = sodstellar2d ]; then build Sod_stellar Castro2d_sodstellar DIM=2 USE_MHD=FALSE; fi
+if [ "$what" = sodstellar1d ]; then build Sod_stellar Castro1d_sodstellar DIM=1 USE_MHD=FALSE; fi
 # the literal BASELINE config[0]: Sod in ONE dimension (DIM=1), golden generator for the 1-D path
 if [ "$what" = sod1d ]; then build Sod Castro1d_sod DIM=1; fi
 # 2-D Cartesian path (AMREX_SPACEDIM == 2): Sedov (cylindrical blast in Cartesian coordinates, inputs.2d.cyl_in_cartcoords) and KH (inputs.2d)

@@ -211,6 +211,11 @@ CASES_2D = {
     "sedov2d_plm_hllc": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 30, [0, 30], ["castro.riemann_solver=2", "castro.ppm_type=0"]),
     "sedov2d_hllc_eos": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 30, [0, 30], ["castro.riemann_solver=2", "castro.transverse_use_eos=1",
                                                                            "castro.transverse_reset_rhoe=1"]),
+    # hybrid Riemann solver (shock detection + HLL fluxes) and the density-floor flux limiter in 2-D
+    "sedov2d_hllc_hybrid": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 60, [0, 60], ["castro.riemann_solver=2", "castro.hybrid_riemann=1"]),
+    "sedov2d_cgf_hybrid": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 60, [0, 60], ["castro.riemann_solver=0", "castro.hybrid_riemann=1"]),
+    "sedov2d_hllc_limit": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 150, [0, 150], ["castro.riemann_solver=2", "castro.limit_fluxes_on_small_dens=1",
+                                                                              "castro.small_dens=0.3"]),
     "sedov2d_symm_cgf": (SEDOV2D_EXE, SEDOV2D_INPUTS, (32, 32), 60, [0, 60], ["castro.riemann_solver=0", "castro.lo_bc=3 3", "castro.hi_bc=4 2",
                                                                            "geometry.prob_hi=0.5 0.5"]),
     # cylindrical R-Z coordinates (inputs.2d.sph_in_cylcoords: the spherical blast on the axis, symmetry at r = 0 and z = 0)
@@ -231,8 +236,10 @@ CASES_2D = {
 }
 
 
-def run_case_2d(name, exe, inputs, n_cell, max_step, snaps, extra):
+def run_case_2d(name, exe, inputs, n_cell, max_step, snaps, extra, link=None):
     wd = tempfile.mkdtemp(prefix="golden_")
+    if link:
+        os.symlink(link, os.path.join(wd, os.path.basename(link)))
     try:
         args = [exe, inputs, "amr.max_level=0", "amr.n_cell=%d %d" % n_cell, "amr.max_grid_size=16", "amr.blocking_factor=8",
                 "max_step=%d" % max_step, "stop_time=1.e9", "amr.plot_int=1", "amr.plot_per=-1", "amr.check_int=-1", "amr.check_per=-1",
@@ -271,8 +278,10 @@ SEDOV1D_CASES = {
 }
 
 
-def run_case_1d(name, inp, nx, max_step, snaps, extra, exe=None, inp_dir=None):
+def run_case_1d(name, inp, nx, max_step, snaps, extra, exe=None, inp_dir=None, link=None):
     wd = tempfile.mkdtemp(prefix="golden_")
+    if link:
+        os.symlink(link, os.path.join(wd, os.path.basename(link)))
     try:
         args = [exe or SOD1D_EXE, os.path.join(inp_dir or SOD_DIR, inp), "amr.max_level=0", "amr.n_cell=%d" % nx, "amr.max_grid_size=32", "amr.blocking_factor=8",
                 "max_step=%d" % max_step, "amr.plot_int=1", "amr.check_int=-1", "amr.derive_plot_vars=NONE", "castro.sum_interval=-1",
@@ -296,6 +305,18 @@ def run_case_1d(name, inp, nx, max_step, snaps, extra, exe=None, inp_dir=None):
         print(name, "ok: steps", nsteps, "t_end", times[-1])
     finally:
         shutil.rmtree(wd)
+
+
+# the Helmholtz-EOS shock tube in the dimensionalities the problem ships with (Exec/hydro_tests/Sod_stellar: DIM = 2 in its GNUmakefile,
+# 1-D in its README): inputs-test1-helm (Colella & Glaz as shipped; CGF)
+SODS2D_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro2d_sodstellar.ex")
+SODS1D_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro1d_sodstellar.ex")
+SODS_LOWD = {
+    "sodstellar2d_cg": (2, (32, 8), 20, [0, 20], ["geometry.prob_hi=1.e6 2.5e5"]),
+    "sodstellar2d_hllc": (2, (32, 8), 20, [0, 20], ["geometry.prob_hi=1.e6 2.5e5", "castro.riemann_solver=2"]),
+    "sodstellar1d_cg": (1, 64, 20, [0, 20], []),
+    "sodstellar1d_cgf_plm": (1, 64, 20, [0, 20], ["castro.riemann_solver=0", "castro.ppm_type=0"]),
+}
 
 
 if __name__ == "__main__":
@@ -332,6 +353,13 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case_1d(name, inp, nx, ms, snaps, extra + ["stop_time=1.e9"], exe=SEDOV1D_EXE, inp_dir=SEDOV_DIR)
+    for name, (dim, n, ms, snaps, extra) in SODS_LOWD.items():
+        if only and name not in only:
+            continue
+        if dim == 2:
+            run_case_2d(name, SODS2D_EXE, os.path.join(SODS_DIR, "inputs-test1-helm"), n, ms, snaps, extra, link=HELM_TABLE)
+        else:
+            run_case_1d(name, "inputs-test1-helm", n, ms, snaps, extra + ["stop_time=1.e9"], exe=SODS1D_EXE, inp_dir=SODS_DIR, link=HELM_TABLE)
     for name, (inp, n, ms, snaps, extra) in SODS_CASES.items():
         if only and name not in only:
             continue

@@ -241,6 +241,9 @@ CASES_2D = {
     "sedov2d_plm_hllc": dict(kind="sedov", solver=2, par=dict(ppm_type=0)),
     "sedov2d_hllc_eos": dict(kind="sedov", solver=2, par=dict(transverse_use_eos=1, transverse_reset_rhoe=1)),
     "sedov2d_symm_cgf": dict(kind="sedov", solver=0, lo_bc=(3, 3, 2), hi_bc=(4, 2, 2)),
+    "sedov2d_hllc_hybrid": dict(kind="sedov", solver=2, par=dict(hybrid_riemann=1)),
+    "sedov2d_cgf_hybrid": dict(kind="sedov", solver=0, par=dict(hybrid_riemann=1)),
+    "sedov2d_hllc_limit": dict(kind="sedov", solver=2, par=dict(limit_fluxes_on_small_dens=1, small_dens=0.3)),
     "sedov2d_rz_cgf": dict(kind="sedov", solver=0, coord=1, lo_bc=(3, 3, 2), hi_bc=(2, 2, 2)),
     "sedov2d_rz_hllc": dict(kind="sedov", solver=2, coord=1, lo_bc=(3, 3, 2), hi_bc=(2, 2, 2)),
     "sedov2d_rz_plm_24x32": dict(kind="sedov", solver=0, coord=1, lo_bc=(3, 3, 2), hi_bc=(2, 2, 2), par=dict(ppm_type=0)),
@@ -307,5 +310,32 @@ def load_sedov1d_case(name):
     n_cell = tuple(int(x) for x in g["n_cell"])
     geom = abi.make_geom(n_cell, probhi=(float(g["probhi"][0]), 1.0, 1.0), lo_bc=(3, 2, 2), hi_bc=(2, 2, 2), dim=1, coord=c["coord"])
     prob = dict(r_init=0.01, p_ambient=1.e-5 if c["coord"] == 2 else 1.e-6, exp_energy=1.0, dens_ambient=1.0, nsub=10)      # inputs.1d.sph / .cyl
+    snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
+    return par, geom, prob, g, snaps
+
+
+# the Helmholtz-EOS shock tube in 2-D (the problem's GNUmakefile default) and 1-D: Exec/hydro_tests/Sod_stellar/inputs-test1-helm
+SODSTELLAR_LOWD = {
+    "sodstellar2d_cg": dict(dim=2, solver=1), "sodstellar2d_hllc": dict(dim=2, solver=2),
+    "sodstellar1d_cg": dict(dim=1, solver=1), "sodstellar1d_cgf_plm": dict(dim=1, solver=0, par=dict(ppm_type=0)),
+}
+
+
+def load_sodstellar_lowd_case(name):
+    c = SODSTELLAR_LOWD[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    par = abi.default_params()
+    par.riemann_solver = c["solver"]
+    par.cfl, par.init_shrink, par.change_max = 0.8, 0.1, 1.1
+    par.eos_kind = 1
+    par.nspec = 3
+    for m, (a, z) in enumerate(IGNITION_NET):
+        par.aion[m], par.zion[m] = a, z
+    for k, v in c.get("par", {}).items():
+        setattr(par, k, v)
+    n_cell = tuple(int(x) for x in g["n_cell"])
+    probhi = (float(g["probhi"][0]), float(g["probhi"][1]) if c["dim"] == 2 else 1.0, 1.0)
+    geom = abi.make_geom(n_cell, probhi=probhi, lo_bc=(2, 3, 3), hi_bc=(2, 3, 3), dim=c["dim"])
+    prob = dict(T_l=1.e8, u_l=0.0, rho_l=1.0e7, T_r=1.e6, u_r=0.0, rho_r=1.e6, use_Tinit=1, idir=1, frac=0.5)
     snaps = sorted(int(k[1:]) for k in g.files if k.startswith("U") and k[1:].isdigit())
     return par, geom, prob, g, snaps
