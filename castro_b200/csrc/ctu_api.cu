@@ -278,8 +278,9 @@ bool tma_ok(const DevPar& P) {
     // piecewise-linear and hydrostatic-pressure-aware reconstructions: their own instantiations of the trace kernel (ctu_rec.cu)
     if (trace_rec(P) && (P.npassive > CTU_TMA_REC_MAX_NP || P.riemann_solver == 1)) return false;
     if (P.riemann_solver == 1 && P.npassive > CTU_TMA_CG_MAX_NP) return false;   // Colella & Glaz: tile kernels instantiated for 1-2 passives
-    if (P.limit_fluxes_on_small_dens) return false;     // ditto the density-floor flux limiter
-    if (P.hybrid_riemann) return false;      // the HLL blend lives in the register-staged family only (keeps the tile kernels lean)
+    // hybrid Riemann solver / density-floor flux limiter: the "extended" instantiations of the tile kernels (ctu_ext.cu), which the default
+    // ones stay free of (the HLL branch alone was measured to cost them 5 %)
+    if (ext_on(P) && (P.npassive > CTU_TMA_EXT_MAX_NP || P.riemann_solver == 1 || trace_rec(P))) return false;
     if (P.transverse_reset_rhoe) return false;   // reads F(rho e) in the transverse updates, which the tile kernels neither store nor stage
     return tma::encode_fn() != nullptr;
 }
@@ -534,6 +535,7 @@ int hydro_slab(HydroRun* r, int klo, int khi, bool last_slab) {
             ta.qp[d] = make_a4(p, ibx); p += ni * NIS;
             ta.vlo[d] = tb.lo[d]; ta.vhi[d] = tb.hi[d];
         }
+        ta.fd = fd; ta.dt = dt;
         A4 F1[3], F2[3][3];
         for (int d = 0; d < 3; ++d) { F1[d] = make_a4(p, ibx); p += ni * NFX; }
         for (int n = 0; n < 3; ++n) for (int t = 0; t < 3; ++t) if (n != t) { F2[n][t] = make_a4(p, ibx); p += ni * NFX; }

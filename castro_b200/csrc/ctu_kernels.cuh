@@ -655,6 +655,8 @@ __device__ __forceinline__ void trace_dir(const DevPar& P, const A4& qs, long oq
 struct TraceArgs {
     A4 qm[3], qp[3];
     int vlo[3], vhi[3];
+    A4 fd;          // flattening / div u / shock flag of the slab and the time step: what the "extended" tile instances (RS = 2) read
+    double dt;
 };
 
 // one thread = one zone of obx, one direction per launch (blockIdx.y)

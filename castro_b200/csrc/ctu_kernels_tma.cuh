@@ -200,9 +200,13 @@ __device__ __forceinline__ bool is_species(const DevPar& P, int ip) { return ip 
 // RS = 0: castro.riemann_solver 0 (CGF) or 2 (HLLC), chosen at run time; RS = 1: the iterative Colella & Glaz solver
 // (castro.riemann_solver = 1) -- its own instantiation of every tile kernel, because the out-of-line iteration inside the default
 // kernels was measured to wreck their register allocation (141 -> 261 ms/step).
+// RS = 2: the "extended" instantiation -- the default solvers plus the options whose code the default kernels do not carry (measured:
+// the HLL branch alone costs them 5 %): castro.hybrid_riemann (HLL flux on faces next to a detected shock, riemann.cpp:144-197;
+// `shocked` = shk(zone left of the face) + shk(zone right of it) >= 1) and, in k_final_tma, castro.limit_fluxes_on_small_dens.
 template <class M, int DIR, int NP, int RS = 0>
 __device__ __forceinline__ void solve_face_r(const DevPar& P, const double* ql, const double* qr, const double* xl, const double* xr,
-                                             double cl, double cr, int idx, double* F, double& ugd, double& pgd, double* FX) {
+                                             double cl, double cr, int idx, double* F, double& ugd, double& pgd, double* FX,
+                                             const bool shocked = false) {
     const bool sp_lo = P.lo_bc[DIR] >= 3 && P.lo_bc[DIR] <= 5, sp_hi = P.hi_bc[DIR] >= 3 && P.hi_bc[DIR] <= 5;
     double bnd_fac = 1.0;
     if ((idx == P.domlo[DIR] && sp_lo) || (idx == P.domhi[DIR] + 1 && sp_hi)) bnd_fac = 0.0;
@@ -229,6 +233,24 @@ __device__ __forceinline__ void solve_face_r(const DevPar& P, const double* ql, 
 #pragma unroll
         for (int ip = 0; ip < NP; ++ip) FX[ip] = passive_flux_hllc(pu, xl[ip], xr[ip]);
     }
+    if (RS == 2) {
+        if (P.hybrid_riemann && shocked) {
+            pu.hll = 0;
+            hll_flux<M, DIR>(ql, qr, cl, cr, F, pu);
+            if (pu.hll) {
+#pragma unroll
+                for (int ip = 0; ip < NP; ++ip) FX[ip] = passive_flux_hll(pu, xl[ip], xr[ip]);
+            }
+        }
+    }
+}
+// shock flags of the two zones adjacent to the DIR-face (i, j, k): fd component 2 (k_flat_div<true>), read straight from L1 / L2
+template <int DIR>
+__device__ __forceinline__ bool face_shocked(const DevPar& P, const A4& fd, int i, int j, int k) {
+    if (!P.hybrid_riemann) return false;
+    const long of = fd.idx(i, j, k);
+    const long ofm = of - ((DIR == 0) ? 1 : (DIR == 1) ? fd.sj : fd.sk);
+    return static_cast<int>(fd.at(ofm, 2) + fd.at(of, 2)) >= 1;
 }
 
 // actual_trans_single for one state (trans.cpp:67-498): zone at tile offset oz of the T-flux tile sF
@@ -308,6 +330,7 @@ struct Trans2Args {
     Box3 b1, b2;          // their boxes
     int ilo[3], qlo[3];   // low corners of the interface-array box and of the qs box (TMA coordinates are relative to them)
     double cdt1, cdt2;
+    A4 fd;                // flattening / div u / shock flag (RS = 2 instances read the shock flag)
 };
 
 // the arithmetic of one face of the tile, on the staged operands (M = MathFast: speculative pass, MathExact: replay)
@@ -350,8 +373,9 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
         trans_single_side<M, NP, typename L::S1, sT1>(P, sF1, oz1 + sN1, qr, xr, a.cdt1, qro1, xro1);
         trans_single_side<M, NP, typename L::S2, sT2>(P, sF2, oz2 + sN2, qr, xr, a.cdt2, qro2, xro2);
         double Fa[6], FXa[NP], uga, pga, Fb[6], FXb[NP], ugb, pgb;
-        solve_face_r<M, N, NP, RS>(P, qlo1, qro1, xlo1, xro1, cl, cr, idx, Fa, uga, pga, FXa);
-        solve_face_r<M, N, NP, RS>(P, qlo2, qro2, xlo2, xro2, cl, cr, idx, Fb, ugb, pgb, FXb);
+        const bool shk2 = (RS == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false;
+        solve_face_r<M, N, NP, RS>(P, qlo1, qro1, xlo1, xro1, cl, cr, idx, Fa, uga, pga, FXa, shk2);
+        solve_face_r<M, N, NP, RS>(P, qlo2, qro2, xlo2, xro2, cl, cr, idx, Fb, ugb, pgb, FXb, shk2);
         const long o1 = a.Fo1.idx(c.i, c.j, c.k), o2 = a.Fo2.idx(c.i, c.j, c.k);
 #pragma unroll
         for (int n = 0; n < FX_EINT; ++n) { a.Fo1.at(o1, n) = Fa[n]; a.Fo2.at(o2, n) = Fb[n]; }
@@ -368,7 +392,7 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
         double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
         trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
         trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
-        solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+        solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX, (RS == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false);
         const long o = a.Fo1.idx(c.i, c.j, c.k);
 #pragma unroll
         for (int n = 0; n < FX_EINT; ++n) a.Fo1.at(o, n) = F[n];      // F(rho e) is not stored (SplitFluxTile)
@@ -383,7 +407,7 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
         double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
         trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
         trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
-        solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+        solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX, (RS == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false);
         const long o = a.Fo2.idx(c.i, c.j, c.k);
 #pragma unroll
         for (int n = 0; n < FX_EINT; ++n) a.Fo2.at(o, n) = F[n];      // F(rho e) is not stored (SplitFluxTile)
@@ -652,6 +676,8 @@ struct FinalArgs {
     A4 Fo;                // output: final flux on N-faces
     int ilo[3], qlo[3];
     double c1, c2;        // dt/(2 dx_T1), dt/(2 dx_T2)
+    A4 fd;                // shock flag (RS = 2 instances)
+    double dt;            // flux limiter (RS = 2 instances)
 };
 
 template <class M, int N, int NP, int RS = 0>
@@ -687,7 +713,7 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
     double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
     trans_final_side<M, NP, typename L::S1, s1T, typename L::S2, s2T>(P, sF1, o1, sF2, o2, ql, xl, a.c1, a.c2, qlo, xlo);
     trans_final_side<M, NP, typename L::S1, s1T, typename L::S2, s2T>(P, sF1, o1 + s1N, sF2, o2 + s2N, qr, xr, a.c1, a.c2, qro, xro);
-    solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX);
+    solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX, (RS == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false);
 
     // apply_av (advection_util.cpp:354-419): div1 = difmag * min(0, <div u> over the 4 nodes of the face)
     const int od = L::DT::off(c.tx + pf, c.ty, c.tz);
@@ -700,6 +726,32 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
     for (int n = 0; n < 6; ++n) {
         const double div_var = div1 * dU[n];
         F[n] += dL * div_var;
+    }
+    // limit_hydro_fluxes_on_small_dens (advection_util.cpp:543-645; RS = 2 instances): scale every flux of the face so that neither
+    // neighbour can be drained below 1.1 * small_dens even if all six of its faces evacuate it
+    double lf = 1.0;
+    bool limited = false;
+    if (RS == 2) {
+        if (P.limit_fluxes_on_small_dens == 1) {
+            const double density_floor = P.small_dens * 1.1;
+            const double vol = P.dx[0] * P.dx[1] * P.dx[2];
+            const double area = (N == 0) ? P.dx[1] * P.dx[2] : (N == 1) ? P.dx[0] * P.dx[2] : P.dx[0] * P.dx[1];
+            const long ou = a.U.idx(c.i, c.j, c.k);
+            const long oum = ou - ((N == 0) ? 1 : (N == 1) ? a.U.sj : a.U.sk);
+            const double rhoR = a.U.at(ou, URHO), rhoL = a.U.at(oum, URHO);
+            double flux_coef = 1.0 / vol;
+            flux_coef *= a.dt * area;
+            const double drho = flux_coef * F[0];
+            if (rhoR >= density_floor && fabs(drho) > 0.0 && rhoR + 2 * 3 * drho < density_floor) {
+                lf = fabs((density_floor - rhoR) / (2 * 3 * drho)); limited = true;
+            } else if (rhoL >= density_floor && fabs(drho) > 0.0 && rhoL - 2 * 3 * drho < density_floor) {
+                lf = fabs((density_floor - rhoL) / (2 * 3 * drho)); limited = true;
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+        if (RS == 2 && limited) F[n] = F[n] * lf;
         a.Fo.at(o, n) = F[n];
     }
     a.Fo.at(o, FX_UG) = ugd;
@@ -710,6 +762,7 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
     for (int ip = 0; ip < NP; ++ip) {
         const double div_var = div1 * dUX[ip];
         FX[ip] += dL * div_var;
+        if (RS == 2 && limited) FX[ip] = FX[ip] * lf;
         if (is_species<NP>(P, ip)) sum += FX[ip];
     }
     double fac = 1.0;
@@ -1389,7 +1442,7 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
     const int oq = QT::off(tx + pq + (D == 0 ? 2 : 0), ty + (D == 1 ? 2 : 0), tz + (D == 2 ? 2 : 0));
     const double cr = sq[QS_C * QT::ZONES + oq], cl = sq[QS_C * QT::ZONES + oq - QT::stride(D)];
     double F[6], FX[NP], ugd, pgd;
-    solve_face_r<M, D, NP, RS>(P, ql, qr, xl, xr, cl, cr, idx, F, ugd, pgd, FX);
+    solve_face_r<M, D, NP, RS>(P, ql, qr, xl, xr, cl, cr, idx, F, ugd, pgd, FX, (RS == 2) ? face_shocked<D>(P, a.fd, i, j, k) : false);
     const long of = a.Fo.idx(i, j, k);
 #pragma unroll
     for (int n = 0; n < FX_EINT; ++n) a.Fo.at(of, n) = F[n];      // F(rho e) is not stored (SplitFluxTile)

@@ -67,6 +67,7 @@ int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3
     a.b2 = grow(nb[N], g2[0], g2[1], g2[2]);
     for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
     a.cdt1 = cdtd[T1]; a.cdt2 = cdtd[T2];
+    a.fd = ta.fd;
     const TileGrid tg = make_tg(grow(nb[N], gu[0], gu[1], gu[2]));
     if (RS == 0 && persist_on() && !CTU_Q_LDG && P.replay_list) {
         static bool attr2 = false;
@@ -86,9 +87,28 @@ int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3
     return 0;
 }
 
+// "Extended" instantiations (RS = 2: castro.hybrid_riemann, castro.limit_fluxes_on_small_dens) exist for CGF / HLLC, plain PPM and up to
+// CTU_TMA_EXT_MAX_NP passive scalars, in their own translation unit (ctu_ext.cu)
+#ifndef CTU_TMA_EXT_MAX_NP
+#define CTU_TMA_EXT_MAX_NP 2
+#endif
+inline bool ext_on(const DevPar& P) { return P.hybrid_riemann || P.limit_fluxes_on_small_dens; }
+template <int NP>
+int launch_trans2_ext_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
+                         const Box3* nb, const double* cdtd, cudaStream_t st) {
+    int rc = launch_trans2<0, NP, 2>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    if (!rc) rc = launch_trans2<1, NP, 2>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    if (!rc) rc = launch_trans2<2, NP, 2>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    return rc;
+}
+
 template <int NP>
 int launch_trans2_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
                      const Box3* nb, const double* cdtd, cudaStream_t st) {
+    if (ext_on(P)) {
+        if constexpr (NP <= CTU_TMA_EXT_MAX_NP) return launch_trans2_ext_np<NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+        else return CTU_ERR_UNSUPPORTED;
+    }
     if constexpr (NP <= CTU_TMA_CG_MAX_NP) {
         if (P.riemann_solver == 1) {
             int rc = launch_trans2<0, NP, 1>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
@@ -164,8 +184,21 @@ CTU_INSTANTIATE_REC(extern, 2)
 namespace ctu {
 
 template <int NP, bool SRC>
+int launch_trace_riemann_ext_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
+                                const Box3& tb, double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
+    int rc = launch_trace_riemann<0, NP, SRC, 2>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    if (!rc) rc = launch_trace_riemann<1, NP, SRC, 2>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    if (!rc) rc = launch_trace_riemann<2, NP, SRC, 2>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    return rc;
+}
+
+template <int NP, bool SRC>
 int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
                             const Box3& tb, double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
+    if (ext_on(P)) {
+        if constexpr (NP <= CTU_TMA_EXT_MAX_NP) return launch_trace_riemann_ext_np<NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+        else return CTU_ERR_UNSUPPORTED;
+    }
     if (const int rec = trace_rec(P)) {
         if constexpr (NP <= CTU_TMA_REC_MAX_NP) return launch_trace_riemann_rec_np<NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st, rec);
         else return CTU_ERR_UNSUPPORTED;
@@ -203,13 +236,27 @@ int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3&
     a.U = Sb; a.Fo = F1[N];
     for (int d = 0; d < 3; ++d) { a.ilo[d] = ibx.lo[d]; a.qlo[d] = qbx_a.lo[d]; }
     a.c1 = hdtd[T1]; a.c2 = hdtd[T2];
+    a.fd = ta.fd; a.dt = ta.dt;
     const TileGrid tg = make_tg(nb[N]);
     k_final_tma<N, NP, RS><<<tg_blocks(tg), TTHR, L::TOTAL, st>>>(P, m_qm, m_qp, m_f1, m_f1b, m_f2, m_f2b, m_c, m_d, a, tg);
     return 0;
 }
 template <int NP>
+int launch_final_ext_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
+                        const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
+    int rc = launch_final<0, NP, 2>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    if (!rc) rc = launch_final<1, NP, 2>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    if (!rc) rc = launch_final<2, NP, 2>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    return rc;
+}
+
+template <int NP>
 int launch_final_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
                     const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
+    if (ext_on(P)) {
+        if constexpr (NP <= CTU_TMA_EXT_MAX_NP) return launch_final_ext_np<NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+        else return CTU_ERR_UNSUPPORTED;
+    }
     if constexpr (NP <= CTU_TMA_CG_MAX_NP) {
         if (P.riemann_solver == 1) {
             int rc = launch_final<0, NP, 1>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
@@ -255,3 +302,22 @@ int launch_update_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb
                                             const ctu::Box3*, const double*, cudaStream_t);                                            \
     KW template int ctu::launch_update_np<N>(const ctu::DevPar&, const ctu::A4*, const ctu::Box3&, const ctu::A4&, const ctu::A4&,      \
                                              const ctu::A4&, const ctu::UpdateArgs&, const ctu::Box3&, double, cudaStream_t);
+
+// explicit instantiation of the "extended" launchers (definition in ctu_ext.cu, declaration everywhere else)
+#define CTU_INSTANTIATE_EXT(KW, N)                                                                                                     \
+    KW template int ctu::launch_trans2_ext_np<N>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&,           \
+                                                 const ctu::Box3&, const ctu::A4*, ctu::A4 (*)[3], const ctu::Box3*, const double*,     \
+                                                 cudaStream_t);                                                                        \
+    KW template int ctu::launch_trace_riemann_ext_np<N, true>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&,                \
+                                                              const ctu::Box3&, const ctu::A4&, const ctu::A4*, const ctu::Box3&,       \
+                                                              double, const ctu::A4&, const int*, cudaStream_t);                       \
+    KW template int ctu::launch_trace_riemann_ext_np<N, false>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&,               \
+                                                               const ctu::Box3&, const ctu::A4&, const ctu::A4*, const ctu::Box3&,      \
+                                                               double, const ctu::A4&, const int*, cudaStream_t);                      \
+    KW template int ctu::launch_final_ext_np<N>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&,            \
+                                                const ctu::Box3&, const ctu::A4&, const ctu::A4&, const ctu::A4*, ctu::A4 (*)[3],       \
+                                                const ctu::Box3*, const double*, cudaStream_t);
+#ifndef CTU_EXT_TU
+CTU_INSTANTIATE_EXT(extern, 1)
+CTU_INSTANTIATE_EXT(extern, 2)
+#endif

@@ -206,14 +206,16 @@ def test_register_staged_kernels_match_golden():
 
 
 def test_kernel_family_selection():
-    """Which option sets run the tile-staged (TMA) kernels: the defaults, Colella & Glaz, piecewise-linear reconstruction and the
-    hydrostatic-pressure-aware reconstructions (their own instantiations of the trace kernel); hybrid Riemann, the flux limiter,
-    ppm_temp_fix and transverse_reset_rhoe stay on the register-staged family.  Each case also lands bit for bit on its golden."""
+    """Which option sets run the tile-staged (TMA) kernels: the defaults, Colella & Glaz, piecewise-linear reconstruction, the
+    hydrostatic-pressure-aware reconstructions (their own instantiations of the trace kernel), the hybrid Riemann solver and the flux
+    limiter ("extended" instantiations); ppm_temp_fix, transverse_reset_rhoe and combinations of several of these stay on the
+    register-staged family.  Each case also lands bit for bit on its golden."""
     _torch()
     from castro_b200 import lib
     from cases import load_rt_case
     expect = {"sedov16_hllc": True, "sedov16_cg": True, "sedov16_plm_hllc": True, "sedov16_plm_cgf_lim1": True, "sedov16_hllc_eos": False,
-              "sedov16_hllc_hybrid": False, "sedov16_hllc_limit": False, "sedov16_cgf_tempfix": False, "sedov16_combo": False}
+              "sedov16_hllc_hybrid": True, "sedov16_cgf_hybrid": True, "sedov16_hllc_limit": True, "sedov16_cgf_tempfix": False,
+              "sedov16_combo": False}
     for name, tile in expect.items():
         par, geom, prob, g, snaps = load_case(name)
         lib.params_finalize(par)
@@ -527,6 +529,32 @@ def test_plotfile_vs_reference_with_fcompare(solver, n_cell, nsteps, wsb, tmp_pa
     assert rc == 0 and len(hist) == nsteps
     if wsb:
         assert sim.last_slabs > 1, "meant to exercise the multi-slab path"
+    my_pf = str(tmp_path / "b200_plt")
+    sim.write_plotfile(my_pf, t, nsteps)
+    sim.close()
+    _fcompare_exact(fcmp, ref_pf, my_pf)
+
+
+@pytest.mark.parametrize("solver,n_cell,nsteps,opts", [
+    (2, (64, 64, 64), 30, "castro.hybrid_riemann=1"),
+    (0, (72, 40, 32), 30, "castro.hybrid_riemann=1 castro.limit_fluxes_on_small_dens=1 castro.small_dens=0.3"),
+    (2, (72, 40, 32), 12, "castro.ppm_type=0"),
+    (1, (64, 64, 64), 12, "")])
+def test_option_instances_of_the_tile_kernels_with_fcompare(solver, n_cell, nsteps, opts, tmp_path):
+    """the acceptance procedure above for the non-default instantiations of the tile-staged kernels at a size where their tiles have
+    neighbours, seams and odd origins: hybrid Riemann solver, hybrid + flux limiter, piecewise-linear reconstruction, Colella & Glaz"""
+    _torch()
+    from castro_b200 import lib
+    hi = "geometry.prob_hi=%r %r %r" % tuple(float(n) / min(n_cell) for n in n_cell)
+    extra = [hi] + opts.split()
+    ref_pf, fcmp, inputs = _run_reference_plotfile(tmp_path, n_cell, solver, nsteps, extra=extra)
+    over = "amr.n_cell=%d %d %d castro.riemann_solver=%d " % (n_cell + (solver,)) + hi + " " + opts
+    par, geom, nc, max_step, stop_time, prob = lib.parse_inputs(inputs, over)
+    lib.params_finalize(par)
+    sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in nc))
+    sim.init_problem("Sedov", {k: (int(v) if k == "nsub" else float(v)) for k, v in (kv.split("=") for kv in prob.split())})
+    rc, t, dt, hist = sim.advance(nsteps)
+    assert rc == 0 and len(hist) == nsteps and sim.tile_staged
     my_pf = str(tmp_path / "b200_plt")
     sim.write_plotfile(my_pf, t, nsteps)
     sim.close()
