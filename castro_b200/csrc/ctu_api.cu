@@ -159,9 +159,9 @@ int check_supported(const ctu_params_t* p, const ctu_geom_t* g) {
     if (p->ppm_temp_fix != 0 && p->ppm_temp_fix != 2) return CTU_ERR_UNSUPPORTED;   // 1 and 3 only exist in the MOL integrator
     if (p->eos_kind != 0 && p->eos_kind != 1) return CTU_ERR_UNSUPPORTED;
     if (p->eos_kind == 1 && !helm_loaded()) return CTU_ERR_UNSUPPORTED;          // Helmholtz EOS: ctu_eos_helm_load(<helm_table.dat>) first
-    // with the Helmholtz EOS: the PPM / PLM path with the three Riemann solvers; the options that call the EOS on edge states and the
-    // constant-gravity driver are instantiated for the gamma law only
-    if (p->eos_kind == 1 && (p->transverse_use_eos || p->transverse_reset_rhoe || p->ppm_temp_fix || p->do_grav)) return CTU_ERR_UNSUPPORTED;
+    // with the Helmholtz EOS: the PPM / PLM path with the three Riemann solvers and traced sources (constant gravity); the options that
+    // call the EOS on edge states are instantiated for the gamma law only
+    if (p->eos_kind == 1 && (p->transverse_use_eos || p->transverse_reset_rhoe || p->ppm_temp_fix)) return CTU_ERR_UNSUPPORTED;
     // curvilinear coordinates: the radial coordinate of a cylinder (1) or a sphere (2) in ONE dimension, cylindrical R-Z in two; R-theta is not built
     if (g && g->coord != 0 && !(g->dim == 1 && (g->coord == 1 || g->coord == 2)) && !(g->dim == 2 && g->coord == 1)) return CTU_ERR_UNSUPPORTED;
     if (g && g->dim != 0 && g->dim != 1 && g->dim != 2 && g->dim != 3) return CTU_ERR_BAD_ARG;
@@ -776,7 +776,7 @@ int hydro_box_2d(HydroRun* r) {
     std::memset(&none, 0, sizeof(none));
     LaunchBox lb = make_lb(qbx);
     const bool helm = P.eos_kind == 1;       // the Helmholtz EOS: EK = 1 instances of the kernels that call the EOS (Cartesian runs)
-    if (helm && (P.coord != 0 || r->have_src)) return CTU_ERR_UNSUPPORTED;
+    if (helm && P.coord != 0) return CTU_ERR_UNSUPPORTED;
     if (helm) k_ctoprim<1><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
     else k_ctoprim<0><<<nblocks(lb.n), TPB, 0, st>>>(P, r->Sb, qs, lb);
     lb = make_lb(obx);
@@ -786,7 +786,8 @@ int hydro_box_2d(HydroRun* r) {
     if (r->have_src) {                  // source terms (src_to_prim on grow(box, 3), then traced by PPM / added by PLM in both directions)
         const A4 srcq = make_a4(p, sbx); p += sbx.npts() * NSRCQ;
         const LaunchBox ls = make_lb(sbx);
-        k_src_to_prim<0><<<nblocks(ls.n), TPB, 0, st>>>(P, r->Sb, qs, r->osrc, r->scorr, r->P_predictor, srcq, ls, r->dt, ws->d_counters + 5);
+        if (helm) k_src_to_prim<1><<<nblocks(ls.n), TPB, 0, st>>>(P, r->Sb, qs, r->osrc, r->scorr, r->P_predictor, srcq, ls, r->dt, ws->d_counters + 5);
+        else k_src_to_prim<0><<<nblocks(ls.n), TPB, 0, st>>>(P, r->Sb, qs, r->osrc, r->scorr, r->P_predictor, srcq, ls, r->dt, ws->d_counters + 5);
         if (P.ppm_type == 0) {
             k_trace_plm<0, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, srcq);
             k_trace_plm<1, true><<<nblocks(lb.n), TPB, 0, st>>>(P, qs, fd, ta, lb, r->dt, srcq);

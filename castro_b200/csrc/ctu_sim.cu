@@ -508,6 +508,7 @@ __global__ void __launch_bounds__(TPB) k_init_tail(const DevPar P, const A4 S, c
 //   k_grav_new: Castro::construct_new_gravity_source (Castro_gravity.cpp:430-690) + S_new += dt*source + clean_state
 //               (do_new_sources, Castro_sources.cpp:204-260) + post_timestep's clean_state, with both dt estimates.
 // ------------------------------------------------------------------------------------------------
+template <int EK>
 __global__ void __launch_bounds__(TPB) k_grav_old(const DevPar P, const A4 Sb, const A4 Sn, const A4 osrc, const LaunchBox lb, const Box3 vbx,
                                                   const double const_grav, const int gst, const double dt) {
     int i, j, k;
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(TPB) k_grav_old(const DevPar P, const A4 Sb, c
 #pragma unroll
     for (int n = 0; n < 7; ++n) u[n] = Sb.at(ob, n) + dt * src[n];
     for (int ip = 0; ip < P.npassive; ++ip) Sn.at(on, UFA + ip) = Sb.at(ob, UFA + ip);
-    clean_zone(P, u, Sn, on);
+    clean_zone<EK>(P, u, Sn, on);
 #pragma unroll
     for (int n = 0; n < 7; ++n) Sn.at(on, n) = u[n];
 }
@@ -562,6 +563,7 @@ struct GravNewArgs {
     int gst;
 };
 
+template <int EK>
 __global__ void __launch_bounds__(TPB) k_grav_new(const DevPar P, const A4 Sb, const A4 Sn, const GravNewArgs a, const LaunchBox lb, const double dt) {
     int i, j, k;
     const bool active = thread_zone(lb, i, j, k);
@@ -628,10 +630,10 @@ __global__ void __launch_bounds__(TPB) k_grav_new(const DevPar P, const A4 Sb, c
         src[UEDEN] = SrEcorr;
 #pragma unroll
         for (int n = 0; n < 7; ++n) u[n] += dt * (0.0 + src[n]);
-        clean_zone(P, u, Sn, on);
-        dt0 = estdt_zone(P, u, Sn, on);
-        clean_zone(P, u, Sn, on);
-        dt1 = estdt_zone(P, u, Sn, on);
+        clean_zone<EK>(P, u, Sn, on);
+        dt0 = estdt_zone<EK>(P, u, Sn, on);
+        clean_zone<EK>(P, u, Sn, on);
+        dt1 = estdt_zone<EK>(P, u, Sn, on);
 #pragma unroll
         for (int n = 0; n < 7; ++n) Sn.at(on, n) = u[n];
     }
@@ -1103,7 +1105,8 @@ static int sim_step_hydro_grav(ctu_sim_t* s, double dt, double dt_est[2], int n_
     for (int d = 0; d < 3; ++d) { fo.lo[d] = sbx.lo[d]; fo.hi[d] = sbx.hi[d]; }
     const A4 osrc = make_a4(fo);
     {   LaunchBox lb = make_lb(sbx);
-        k_grav_old<<<nblk(lb.n), TPB, 0, s->st>>>(P, Sb, Sn, osrc, lb, s->vbx, par.const_grav, par.grav_source_type, dt);
+        if (P.eos_kind == 1) k_grav_old<1><<<nblk(lb.n), TPB, 0, s->st>>>(P, Sb, Sn, osrc, lb, s->vbx, par.const_grav, par.grav_source_type, dt);
+        else k_grav_old<0><<<nblk(lb.n), TPB, 0, s->st>>>(P, Sb, Sn, osrc, lb, s->vbx, par.const_grav, par.grav_source_type, dt);
         DevPar P7 = P;
         P7.nstate = 7;          // the source has NSRC components and the state's boundary types (Castro_setup.cpp: Source_Type)
         k_fill<1><<<nblk(lb.n), TPB, 0, s->st>>>(P7, osrc, lb, s->vbx);
@@ -1128,7 +1131,8 @@ static int sim_step_hydro_grav(ctu_sim_t* s, double dt, double dt_est[2], int n_
     CUDA_TRY(cudaMemcpyAsync(s->d_dt2, init, sizeof(init), cudaMemcpyHostToDevice, s->st));
     ga.dtmin = s->d_dt2; ga.const_grav = par.const_grav; ga.gst = par.grav_source_type;
     {   LaunchBox lb = make_lb(s->vbx);
-        k_grav_new<<<nblk(lb.n), TPB, 0, s->st>>>(P, Sb, Sn, ga, lb, dt);
+        if (P.eos_kind == 1) k_grav_new<1><<<nblk(lb.n), TPB, 0, s->st>>>(P, Sb, Sn, ga, lb, dt);
+        else k_grav_new<0><<<nblk(lb.n), TPB, 0, s->st>>>(P, Sb, Sn, ga, lb, dt);
         s->launches += 1;
         CUDA_TRY(cudaGetLastError()); }
     unsigned long long h[2];

@@ -63,6 +63,10 @@ if [ "$what" = sodstellar ]; then build Sod_stellar Castro3d_sodstellar DIM=3 US
 # ... and in the dimensionalities the problem ships with (GNUmakefile: DIM = 2; the README runs it in 1-D): golden generators for the Helmholtz EOS in 1-D / 2-D
 if [ "$what" = sodstellar2d ]; then build Sod_stellar Castro2d_sodstellar DIM=2 USE_MHD=FALSE; fi
 if [ "$what" = sodstellar1d ]; then build Sod_stellar Castro1d_sodstellar DIM=1 USE_MHD=FALSE; fi
+# ... and with the gravity module compiled in (USE_GRAV=TRUE, gravity.gravity_type = ConstantGrav): golden generator for the Helmholtz EOS
+# together with the constant-gravity source terms and the source predictor (the literal combination of BASELINE config[4])
+if [ "$what" = sodstellar_grav ]; then build Sod_stellar Castro3d_sodstellar_grav DIM=3 USE_MHD=FALSE USE_GRAV=TRUE; fi
+if [ "$what" = sodstellar2d_grav ]; then build Sod_stellar Castro2d_sodstellar_grav DIM=2 USE_MHD=FALSE USE_GRAV=TRUE; fi
 # the literal BASELINE config[0]: Sod in ONE dimension (DIM=1), golden generator for the 1-D path
 if [ "$what" = sod1d ]; then build Sod Castro1d_sod DIM=1; fi
 # 2-D Cartesian path (AMREX_SPACEDIM == 2): Sedov (cylindrical blast in Cartesian coordinates, inputs.2d.cyl_in_cartcoords) and KH (inputs.2d)

@@ -169,6 +169,16 @@ SODS_CASES = {
     "sodstellar_z_cgf": ("inputs-test1-helm-z", (8, 8, 32), 20, [0, 20], ["geometry.prob_hi=2.5e5 2.5e5 1.e6", "castro.riemann_solver=0"]),
 }
 
+# ... and with constant gravity (reference built with USE_GRAV=TRUE: `build_ref.sh sodstellar_grav`): the Helmholtz EOS together with
+# the gravity source terms traced through PPM -- g = -1e10 cm/s^2 along z (rho g L ~ 10 % of the pressure), along the tube and across it
+SODS_GRAV_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro3d_sodstellar_grav.ex")
+_GRAV = ["castro.do_grav=1", "gravity.gravity_type=ConstantGrav", "gravity.const_grav=-1.e10"]
+SODS_GRAV_CASES = {
+    "sodstellar_z_grav_cgf": ("inputs-test1-helm-z", (8, 8, 32), 20, [0, 20], ["geometry.prob_hi=2.5e5 2.5e5 1.e6", "castro.riemann_solver=0"] + _GRAV),
+    "sodstellar_x_grav_hllc_gst2": ("inputs-test1-helm", (32, 8, 8), 12, [0, 12], ["geometry.prob_hi=1.e6 2.5e5 2.5e5", "castro.riemann_solver=2",
+                                                                                 "castro.grav_source_type=2"] + _GRAV),
+}
+
 
 # BASELINE config[0] literally: the Sod shock tube in ONE dimension (DIM=1 build of the reference), 128 zones in two boxes of 64, PPM + CGF,
 # run to stop_time = 0.2 (inputs-sod-x), plus the two harder tubes of the same directory (test2: double rarefaction, test3: strong shock)
@@ -255,7 +265,7 @@ def run_case_2d(name, exe, inputs, n_cell, max_step, snaps, extra, link=None):
             times.append(h["time"])
             if s in snaps:
                 h, U = read_plotfile(pf)
-                states["U%d" % s] = np.ascontiguousarray(U[:8]) if "rt2d" in name else U      # gravity builds append phiGrav, grav_*
+                states["U%d" % s] = np.ascontiguousarray(U[:8]) if "rt2d" in name else (np.ascontiguousarray(U[:10]) if "2d_grav" in name else U)   # gravity builds append phiGrav, grav_*
         meta = dict(n_cell=np.array(n_cell + (1,)), times=np.array(times), names=np.array(h["names"]), problo=np.array(h["problo"]),
                     probhi=np.array(h["probhi"]), overrides=np.array(extra), inputs=np.array(os.path.basename(inputs)))
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **meta, **states)
@@ -314,6 +324,9 @@ SODS1D_EXE = os.path.join(ROOT, "oracle", "_ref", "Castro1d_sodstellar.ex")
 SODS_LOWD = {
     "sodstellar2d_cg": (2, (32, 8), 20, [0, 20], ["geometry.prob_hi=1.e6 2.5e5"]),
     "sodstellar2d_hllc": (2, (32, 8), 20, [0, 20], ["geometry.prob_hi=1.e6 2.5e5", "castro.riemann_solver=2"]),
+    # the 2-D tube with constant gravity along y, across the tube (reference built with USE_GRAV=TRUE: `build_ref.sh sodstellar2d_grav`)
+    "sodstellar2d_grav_cgf": (2, (32, 8), 12, [0, 12], ["geometry.prob_hi=1.e6 2.5e5", "castro.riemann_solver=0", "castro.do_grav=1",
+                                                        "gravity.gravity_type=ConstantGrav", "gravity.const_grav=-1.e10"]),
     "sodstellar1d_cg": (1, 64, 20, [0, 20], []),
     "sodstellar1d_cgf_plm": (1, 64, 20, [0, 20], ["castro.riemann_solver=0", "castro.ppm_type=0"]),
 }
@@ -357,7 +370,8 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         if dim == 2:
-            run_case_2d(name, SODS2D_EXE, os.path.join(SODS_DIR, "inputs-test1-helm"), n, ms, snaps, extra, link=HELM_TABLE)
+            run_case_2d(name, SODS2D_EXE.replace(".ex", "_grav.ex") if "grav" in name else SODS2D_EXE, os.path.join(SODS_DIR, "inputs-test1-helm"),
+                        n, ms, snaps, extra, link=HELM_TABLE)
         else:
             run_case_1d(name, "inputs-test1-helm", n, ms, snaps, extra + ["stop_time=1.e9"], exe=SODS1D_EXE, inp_dir=SODS_DIR, link=HELM_TABLE)
     for name, (inp, n, ms, snaps, extra) in SODS_CASES.items():
@@ -365,6 +379,11 @@ if __name__ == "__main__":
             continue
         run_case(name, n, ms, snaps, extra + ["amr.check_int=-1", "castro.sum_interval=-1"], exe=SODS_EXE, inputs=os.path.join(SODS_DIR, inp),
                  link=HELM_TABLE)
+    for name, (inp, n, ms, snaps, extra) in SODS_GRAV_CASES.items():
+        if only and name not in only:
+            continue
+        run_case(name, n, ms, snaps, extra + ["amr.check_int=-1", "castro.sum_interval=-1"], exe=SODS_GRAV_EXE, inputs=os.path.join(SODS_DIR, inp),
+                 ncomp=10, link=HELM_TABLE)
     for name, (inp, n, ms, snaps, extra) in SOD_CASES.items():
         if only and name not in only:
             continue

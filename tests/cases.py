@@ -159,6 +159,9 @@ SODSTELLAR_CASES = {
     "sodstellar_x_cgf": dict(solver=0, idir=1, lo_bc=(2, 3, 3)),
     "sodstellar_y_hllc": dict(solver=2, idir=2, lo_bc=(4, 2, 4)),
     "sodstellar_z_cgf": dict(solver=0, idir=3, lo_bc=(4, 4, 2)),
+    # with constant gravity along z (reference built with USE_GRAV=TRUE): Helmholtz EOS + traced gravity sources, along the tube and across it
+    "sodstellar_z_grav_cgf": dict(solver=0, idir=3, lo_bc=(4, 4, 2), par=dict(do_grav=1, const_grav=-1.e10)),
+    "sodstellar_x_grav_hllc_gst2": dict(solver=2, idir=1, lo_bc=(2, 3, 3), par=dict(do_grav=1, const_grav=-1.e10, grav_source_type=2)),
 }
 IGNITION_NET = ((12.0, 6.0), (16.0, 8.0), (24.0, 12.0))      # networks/general_null/ignition.net: C12 O16 Mg24
 HELM_TABLE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "helm_table.dat")
@@ -174,6 +177,8 @@ def load_sodstellar_case(name):
     par.cfl, par.init_shrink, par.change_max = 0.8, 0.1, 1.1
     par.eos_kind = 1
     par.nspec = 3
+    for k, v in c.get("par", {}).items():
+        setattr(par, k, v)
     for m, (a, z) in enumerate(IGNITION_NET):
         par.aion[m], par.zion[m] = a, z
     n_cell = tuple(int(x) for x in g["n_cell"])
@@ -317,6 +322,7 @@ def load_sedov1d_case(name):
 # the Helmholtz-EOS shock tube in 2-D (the problem's GNUmakefile default) and 1-D: Exec/hydro_tests/Sod_stellar/inputs-test1-helm
 SODSTELLAR_LOWD = {
     "sodstellar2d_cg": dict(dim=2, solver=1), "sodstellar2d_hllc": dict(dim=2, solver=2),
+    "sodstellar2d_grav_cgf": dict(dim=2, solver=0, par=dict(do_grav=1, const_grav=-1.e10)),      # + constant gravity along y (USE_GRAV=TRUE build)
     "sodstellar1d_cg": dict(dim=1, solver=1), "sodstellar1d_cgf_plm": dict(dim=1, solver=0, par=dict(ppm_type=0)),
 }
 
