@@ -277,7 +277,7 @@ bool tma_ok(const DevPar& P) {
     if (P.ppm_temp_fix) return false;        // EOS re-sync of the interface states before each solve: register-staged family
     // piecewise-linear and hydrostatic-pressure-aware reconstructions: their own instantiations of the trace kernel (ctu_rec.cu)
     if (trace_rec(P) && (P.npassive > CTU_TMA_REC_MAX_NP || P.riemann_solver == 1)) return false;
-    if (P.riemann_solver == 1 && P.npassive > CTU_TMA_CG_MAX_NP) return false;   // Colella & Glaz: tile kernels instantiated for 1-2 passives
+    if (P.riemann_solver == 1 && P.npassive > CTU_TMA_CG_MAX_NP) return false;   // Colella & Glaz: its own instantiations of the tile kernels
     // hybrid Riemann solver / density-floor flux limiter: the "extended" instantiations of the tile kernels (ctu_ext.cu), which the default
     // ones stay free of (the HLL branch alone was measured to cost them 5 %)
     if (ext_on(P) && (P.npassive > CTU_TMA_EXT_MAX_NP || P.riemann_solver == 1 || trace_rec(P))) return false;

@@ -42,7 +42,7 @@ int set_smem(K kernel, size_t bytes) {
 
 // Colella & Glaz instantiations (RS = 1) exist for up to CTU_TMA_CG_MAX_NP passive scalars
 #ifndef CTU_TMA_CG_MAX_NP
-#define CTU_TMA_CG_MAX_NP 2
+#define CTU_TMA_CG_MAX_NP 5
 #endif
 template <int N, int NP, int RS = 0>
 int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
@@ -88,9 +88,9 @@ int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3
 }
 
 // "Extended" instantiations (RS = 2: castro.hybrid_riemann, castro.limit_fluxes_on_small_dens) exist for CGF / HLLC, plain PPM and up to
-// CTU_TMA_EXT_MAX_NP passive scalars, in their own translation unit (ctu_ext.cu)
+// CTU_TMA_EXT_MAX_NP passive scalars, in their own translation units (ctu_ext.cu: 1 and 2 passives; ctu_ext3 / 4 / 5.cu)
 #ifndef CTU_TMA_EXT_MAX_NP
-#define CTU_TMA_EXT_MAX_NP 2
+#define CTU_TMA_EXT_MAX_NP 5
 #endif
 inline bool ext_on(const DevPar& P) { return P.hybrid_riemann || P.limit_fluxes_on_small_dens; }
 template <int NP>
@@ -124,9 +124,9 @@ int launch_trans2_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const B
 }
 // Reconstructions other than plain PPM (REC = 1: piecewise linear, castro.ppm_type = 0; REC = 2: PPM with castro.use_pslope /
 // castro.ppm_well_balanced) only change the trace kernel; they are instantiated for CGF / HLLC and up to CTU_TMA_REC_MAX_NP passive
-// scalars, in their own translation unit (ctu_rec.cu).
+// scalars, in their own translation units (ctu_rec.cu: 1 and 2 passives; ctu_rec3 / 4 / 5.cu).
 #ifndef CTU_TMA_REC_MAX_NP
-#define CTU_TMA_REC_MAX_NP 2
+#define CTU_TMA_REC_MAX_NP 5
 #endif
 inline int trace_rec(const DevPar& P) { return P.ppm_type == 0 ? 1 : (P.use_pslope || P.ppm_well_balanced) ? 2 : 0; }
 
@@ -180,6 +180,9 @@ int launch_trace_riemann_rec_np(const DevPar& P, const TraceArgs& ta, const A4& 
 #ifndef CTU_REC_TU      // every translation unit but ctu_rec.cu only declares them
 CTU_INSTANTIATE_REC(extern, 1)
 CTU_INSTANTIATE_REC(extern, 2)
+CTU_INSTANTIATE_REC(extern, 3)
+CTU_INSTANTIATE_REC(extern, 4)
+CTU_INSTANTIATE_REC(extern, 5)
 #endif
 namespace ctu {
 
@@ -320,4 +323,7 @@ int launch_update_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb
 #ifndef CTU_EXT_TU
 CTU_INSTANTIATE_EXT(extern, 1)
 CTU_INSTANTIATE_EXT(extern, 2)
+CTU_INSTANTIATE_EXT(extern, 3)
+CTU_INSTANTIATE_EXT(extern, 4)
+CTU_INSTANTIATE_EXT(extern, 5)
 #endif

@@ -198,6 +198,11 @@ class Workspace:
         return lib().ctu_workspace_last_slabs(self.h)
 
     @property
+    def tile_staged(self):
+        """True when the last ctu_hydro_advance on this workspace ran the tile-staged (TMA) kernels"""
+        return bool(lib().ctu_workspace_last_tile_staged(self.h))
+
+    @property
     def launches(self):
         return lib().ctu_workspace_launches(self.h)
 

@@ -327,10 +327,17 @@ def test_kh_two_passives_matches_reference_golden(name):
     sim.close()
 
 
-@pytest.mark.parametrize("nadv,nspec,solver", [(1, 1, 2), (1, 1, 0), (0, 2, 2), (0, 3, 2), (1, 3, 0), (0, 4, 2), (1, 4, 0), (2, 4, 2)])
-def test_passives_vs_oracle(nadv, nspec, solver):
+@pytest.mark.parametrize("nadv,nspec,solver,opt", [(1, 1, 2, ""), (1, 1, 0, ""), (0, 2, 2, ""), (0, 3, 2, ""), (1, 3, 0, ""), (0, 4, 2, ""),
+                                                   (1, 4, 0, ""), (2, 4, 2, ""), (0, 3, 2, "ext"), (1, 3, 0, "ext"), (1, 4, 2, "ext"),
+                                                   (2, 4, 0, "ext"), (0, 3, 1, "cg"), (1, 4, 1, "cg"), (0, 3, 2, "plm"), (0, 4, 0, "plm"),
+                                                   (1, 4, 2, "plm"), (1, 2, 0, "pslope"), (1, 4, 2, "pslope")])
+def test_passives_vs_oracle(nadv, nspec, solver, opt):
     """evolved 3-D Sedov state with non-trivial advected scalars / several species: one ctu_hydro_advance vs the oracle.
-    Up to five passives run the tile-staged kernels (NP = 2, 3, 4, 5 here), (2,4) = six passives the register-staged ones."""
+    Up to five passives run the tile-staged kernels (NP = 2, 3, 4, 5 here), (2,4) = six passives the register-staged ones.
+    opt = "ext": with the hybrid Riemann solver and the density-floor flux limiter (the "extended" tile instances; small_dens is raised
+    into the range of the data so that the limiter acts); "cg": the Colella & Glaz solver; "plm": piecewise-linear reconstruction;
+    "pslope": the hydrostatic-pressure-aware PPM (without gravity: the same numbers through the other trace instance) -- the tile
+    instances of each option for 3, 4 and 5 passives."""
     torch = _torch()
     import oracle_lib as O
     from castro_b200 import lib, abi
@@ -340,6 +347,14 @@ def test_passives_vs_oracle(nadv, nspec, solver):
     for n in range(nspec):
         par.aion[n] = 1.0 + 3.0 * n
         par.zion[n] = 1.0 + n
+    if opt == "ext":
+        par.hybrid_riemann, par.limit_fluxes_on_small_dens, par.small_dens = 1, 1, 0.3
+    elif opt == "cg":
+        par.riemann_solver = 1
+    elif opt == "plm":
+        par.ppm_type = 0
+    elif opt == "pslope":
+        par.use_pslope = 1
     O.params_finalize(par)
     n_cell = (20, 12, 10)
     geom = abi.make_geom(n_cell, probhi=(1.25, 0.75, 0.625))
@@ -373,7 +388,8 @@ def test_passives_vs_oracle(nadv, nspec, solver):
     rc, est, loc, nbad = lib.hydro_advance(ws, par, geom, (0, 0, 0), hi, dSb, glo, dSn, (0, 0, 0), dt, n_clean=1)
     torch.cuda.synchronize()
     assert rc == st_ref and nbad == nbad_ref
-    assert_bitwise(dSn.cpu().numpy(), Sn_ref, "S_new nadv=%d nspec=%d" % (nadv, nspec))
+    assert ws.tile_staged == (nadv + nspec <= 5)
+    assert_bitwise(dSn.cpu().numpy(), Sn_ref, "S_new nadv=%d nspec=%d %s" % (nadv, nspec, opt))
     assert est[1] == dt_ref
 
 
