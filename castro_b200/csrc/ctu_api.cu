@@ -272,8 +272,11 @@ __global__ void __launch_bounds__(128) k_selftest_mathfast(const int elo, const 
 
 bool tma_ok(const DevPar& P) {
     static const bool disabled = (std::getenv("CTU_NO_TMA") != nullptr);
-    if (disabled || !P.gamc_const || P.dim != 3) return false;
+    if (disabled || P.dim != 3) return false;
     if (P.npassive < 1 || P.npassive > CTU_TMA_MAX_NP) return false;
+    // Helmholtz EOS (Gamma_1 varies from zone to zone): its own instantiations of the tile kernels (ctu_helm1 .. 5.cu), plain PPM with the
+    // three Riemann solvers
+    if (!P.gamc_const && (P.npassive > CTU_TMA_HELM_MAX_NP || trace_rec(P) || ext_on(P))) return false;
     if (P.ppm_temp_fix) return false;        // EOS re-sync of the interface states before each solve: register-staged family
     // piecewise-linear and hydrostatic-pressure-aware reconstructions: their own instantiations of the trace kernel (ctu_rec.cu)
     if (trace_rec(P) && (P.npassive > CTU_TMA_REC_MAX_NP || P.riemann_solver == 1)) return false;

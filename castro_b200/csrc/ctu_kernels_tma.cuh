@@ -203,10 +203,16 @@ __device__ __forceinline__ bool is_species(const DevPar& P, int ip) { return ip 
 // RS = 2: the "extended" instantiation -- the default solvers plus the options whose code the default kernels do not carry (measured:
 // the HLL branch alone costs them 5 %): castro.hybrid_riemann (HLL flux on faces next to a detected shock, riemann.cpp:144-197;
 // `shocked` = shk(zone left of the face) + shk(zone right of it) >= 1) and, in k_final_tma, castro.limit_fluxes_on_small_dens.
+// Bit 2 of RS is the EOS kind of the instance (EK: RS = 4 the default solvers, RS = 5 Colella & Glaz, both with the Helmholtz EOS):
+// Gamma_1 of the two zones next to the face comes from the staged tiles (gcl, gcr) instead of P.gamma.
+__host__ __device__ constexpr int rs_kind(int RS) { return RS & 3; }
+__host__ __device__ constexpr int rs_ek(int RS) { return RS >> 2; }
 template <class M, int DIR, int NP, int RS = 0>
 __device__ __forceinline__ void solve_face_r(const DevPar& P, const double* ql, const double* qr, const double* xl, const double* xr,
                                              double cl, double cr, int idx, double* F, double& ugd, double& pgd, double* FX,
-                                             const bool shocked = false) {
+                                             const bool shocked = false, const double gcl_t = 0.0, const double gcr_t = 0.0) {
+    constexpr int EK = rs_ek(RS);
+    const double gcl = EK ? gcl_t : P.gamma, gcr = EK ? gcr_t : P.gamma;
     const bool sp_lo = P.lo_bc[DIR] >= 3 && P.lo_bc[DIR] <= 5, sp_hi = P.hi_bc[DIR] >= 3 && P.hi_bc[DIR] <= 5;
     double bnd_fac = 1.0;
     if ((idx == P.domlo[DIR] && sp_lo) || (idx == P.domhi[DIR] + 1 && sp_hi)) bnd_fac = 0.0;
@@ -217,23 +223,24 @@ __device__ __forceinline__ void solve_face_r(const DevPar& P, const double* ql, 
         for (int ip = 0; ip < NP; ++ip) if (ip == P.QFS_off + n) r = x[ip];
         return r;
     };
-    if (RS == 1) {
+    if (rs_kind(RS) == 1) {
         auto fl = [&](int n) { return sel(xl, n); };
         auto fr = [&](int n) { return sel(xr, n); };
-        riemann_cgf<M, DIR, decltype(fl), decltype(fr), 1>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, fl, fr, F, ugd, pgd, pu);
+        riemann_cgf<M, DIR, decltype(fl), decltype(fr), 1, EK>(P, ql, qr, gcl, gcr, cl, cr, bnd_fac, fl, fr, F, ugd, pgd, pu);
 #pragma unroll
         for (int ip = 0; ip < NP; ++ip) FX[ip] = passive_flux_cgf(pu, xl[ip], xr[ip]);
     } else if (P.riemann_solver == 0) {
-        riemann_cgf<M, DIR>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, [&](int n) { return sel(xl, n); }, [&](int n) { return sel(xr, n); },
-                         F, ugd, pgd, pu);
+        auto fl = [&](int n) { return sel(xl, n); };
+        auto fr = [&](int n) { return sel(xr, n); };
+        riemann_cgf<M, DIR, decltype(fl), decltype(fr), 0, EK>(P, ql, qr, gcl, gcr, cl, cr, bnd_fac, fl, fr, F, ugd, pgd, pu);
 #pragma unroll
         for (int ip = 0; ip < NP; ++ip) FX[ip] = passive_flux_cgf(pu, xl[ip], xr[ip]);
     } else {
-        riemann_hllc<M, DIR>(P, ql, qr, P.gamma, P.gamma, cl, cr, bnd_fac, F, ugd, pgd, pu);
+        riemann_hllc<M, DIR>(P, ql, qr, gcl, gcr, cl, cr, bnd_fac, F, ugd, pgd, pu);
 #pragma unroll
         for (int ip = 0; ip < NP; ++ip) FX[ip] = passive_flux_hllc(pu, xl[ip], xr[ip]);
     }
-    if (RS == 2) {
+    if (rs_kind(RS) == 2) {
         if (P.hybrid_riemann && shocked) {
             pu.hll = 0;
             hll_flux<M, DIR>(ql, qr, cl, cr, F, pu);
@@ -256,7 +263,7 @@ __device__ __forceinline__ bool face_shocked(const DevPar& P, const A4& fd, int 
 // actual_trans_single for one state (trans.cpp:67-498): zone at tile offset oz of the T-flux tile sF
 template <class M, int NP, class FT, int ST>
 __device__ __forceinline__ void trans_single_side(const DevPar& P, const FT& sF, int oz, const double* q, const double* x, double cdt,
-                                                  double* qo, double* xo) {
+                                                  double* qo, double* xo, const double gamc) {
     double fl[6], fr[6], dX[NP];
 #pragma unroll
     for (int n = 0; n < FX_EINT; ++n) { fl[n] = sF(oz, n); fr[n] = sF(oz + ST, n); }
@@ -273,7 +280,7 @@ __device__ __forceinline__ void trans_single_side(const DevPar& P, const FT& sF,
         xn[ip] = M::div(rho * x[ip] - dX[ip], rrnew);
         if (is_species<NP>(P, ip) && (xn[ip] > 1.0 + P.abundance_failure_tolerance || xn[ip] < -P.abundance_failure_tolerance)) reset = true;
     }
-    trans_single_hydro<M>(P, q, qo, fl, fr, ugm, ugp, pgm, pgp, P.gamma, cdt, rrnew, reset);
+    trans_single_hydro<M>(P, q, qo, fl, fr, ugm, ugp, pgm, pgp, gamc, cdt, rrnew, reset);
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) xo[ip] = reset ? x[ip] : xn[ip];
     if (P.transverse_use_eos || P.transverse_reset_rhoe)      // non-default edge-state thermodynamics (a17)
@@ -283,7 +290,7 @@ __device__ __forceinline__ void trans_single_side(const DevPar& P, const FT& sF,
 // actual_trans_final for one state (trans.cpp:559-968)
 template <class M, int NP, class F1T, int S1, class F2T, int S2>
 __device__ __forceinline__ void trans_final_side(const DevPar& P, const F1T& sF1, int o1, const F2T& sF2, int o2, const double* q,
-                                                 const double* x, double c1, double c2, double* qo, double* xo) {
+                                                 const double* x, double c1, double c2, double* qo, double* xo, const double gamc) {
     double f1l[6], f1r[6], f2l[6], f2r[6];
 #pragma unroll
     for (int n = 0; n < FX_EINT; ++n) { f1l[n] = sF1(o1, n); f1r[n] = sF1(o1 + S1, n); f2l[n] = sF2(o2, n); f2r[n] = sF2(o2 + S2, n); }
@@ -298,7 +305,7 @@ __device__ __forceinline__ void trans_final_side(const DevPar& P, const F1T& sF1
         if (is_species<NP>(P, ip) && (xn[ip] > 1.0 + P.abundance_failure_tolerance || xn[ip] < -P.abundance_failure_tolerance)) reset = true;
     }
     trans_final_hydro<M>(P, q, qo, f1l, f1r, f2l, f2r, sF1(o1, FX_UG), sF1(o1 + S1, FX_UG), sF1(o1, FX_PG), sF1(o1 + S1, FX_PG),
-                      sF2(o2, FX_UG), sF2(o2 + S2, FX_UG), sF2(o2, FX_PG), sF2(o2 + S2, FX_PG), P.gamma, c1, c2, rrnew, reset);
+                      sF2(o2, FX_UG), sF2(o2 + S2, FX_UG), sF2(o2, FX_PG), sF2(o2 + S2, FX_PG), gamc, c1, c2, rrnew, reset);
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) xo[ip] = reset ? x[ip] : xn[ip];
     if (P.transverse_use_eos || P.transverse_reset_rhoe)
@@ -308,7 +315,7 @@ __device__ __forceinline__ void trans_final_side(const DevPar& P, const F1T& sF1
 // ------------------------------------------------------------------------------------------------
 // k_trans2_tma
 // ------------------------------------------------------------------------------------------------
-template <int N, int NP>
+template <int N, int NP, int EK = 0>
 struct Trans2Smem {
     static constexpr int T1 = (N == 0) ? 1 : 0, T2 = (N == 2) ? 1 : 2;
     static constexpr int NIS = IS_X + NP, NFX = FX_X + NP;
@@ -317,7 +324,8 @@ struct Trans2Smem {
     using CT = ZoneTile<N>;
     using S1 = SplitFluxTile<F1T, NFX>;
     using S2 = SplitFluxTile<F2T, NFX>;
-    static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = S1::BYTES, B_F2 = S2::BYTES, B_C = (size_t)CT::ZONES * 8;
+    static constexpr int NC = 1 + EK;                      // staged qs components: c (QS_C) and, with the Helmholtz EOS, Gamma_1 (QS_GAMC = QS_C + 1)
+    static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = S1::BYTES, B_F2 = S2::BYTES, B_C = (size_t)NC * CT::ZONES * 8;
     static constexpr size_t B_QS = CTU_Q_LDG ? 0 : B_Q;    // shared-memory bytes of one interface-state tile
     static constexpr size_t O_QM = 0, O_QP = al128(O_QM + B_QS), O_F1 = al128(O_QP + B_QS), O_F2 = al128(O_F1 + B_F1),
                             O_C = al128(O_F2 + B_F2), O_BAR = al128(O_C + B_C), TOTAL = O_BAR + 128;
@@ -338,7 +346,8 @@ template <class M, int N, int NP, int RS = 0>
 __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a, const unsigned char* smem, const TileCtx& c, const bool in1,
                                             const bool in2, const int pf, const int pg, const int pq, const double* gql, const double* gqr,
                                             const double* gxl, const double* gxr) {
-    using L = Trans2Smem<N, NP>;
+    constexpr int EK = rs_ek(RS);
+    using L = Trans2Smem<N, NP, EK>;
     constexpr int T1 = L::T1, T2 = L::T2;
     if (!in1 && !in2) return;
     const typename L::S1 sF1(smem + L::O_F1);
@@ -360,6 +369,7 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
 #endif
     const int oc = L::CT::off(c.tx + pq, c.ty, c.tz);
     const double cl = sC(oc, 0), cr = sC(oc + L::CT::stride(N), 0);
+    const double gl = EK ? sC(oc, EK) : P.gamma, gr = EK ? sC(oc + L::CT::stride(N), EK) : P.gamma;      // Gamma_1 of the zones left / right of the face
     const int idx = (N == 0) ? c.i : (N == 1) ? c.j : c.k;
 #if CTU_TRANS2_DUAL
     // developer switch: interior faces (both transverse corrections wanted) run the two independent state updates + Riemann solves in ONE
@@ -368,14 +378,14 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
         constexpr int sN1 = L::F1T::stride(N), sT1 = L::F1T::stride(T1), sN2 = L::F2T::stride(N), sT2 = L::F2T::stride(T2);
         const int oz1 = L::F1T::off(c.tx + pg, c.ty, c.tz), oz2 = L::F2T::off(c.tx + pg, c.ty, c.tz);
         double qlo1[6], qro1[6], xlo1[NP], xro1[NP], qlo2[6], qro2[6], xlo2[NP], xro2[NP];
-        trans_single_side<M, NP, typename L::S1, sT1>(P, sF1, oz1, ql, xl, a.cdt1, qlo1, xlo1);
-        trans_single_side<M, NP, typename L::S2, sT2>(P, sF2, oz2, ql, xl, a.cdt2, qlo2, xlo2);
-        trans_single_side<M, NP, typename L::S1, sT1>(P, sF1, oz1 + sN1, qr, xr, a.cdt1, qro1, xro1);
-        trans_single_side<M, NP, typename L::S2, sT2>(P, sF2, oz2 + sN2, qr, xr, a.cdt2, qro2, xro2);
+        trans_single_side<M, NP, typename L::S1, sT1>(P, sF1, oz1, ql, xl, a.cdt1, qlo1, xlo1, gl);
+        trans_single_side<M, NP, typename L::S2, sT2>(P, sF2, oz2, ql, xl, a.cdt2, qlo2, xlo2, gl);
+        trans_single_side<M, NP, typename L::S1, sT1>(P, sF1, oz1 + sN1, qr, xr, a.cdt1, qro1, xro1, gr);
+        trans_single_side<M, NP, typename L::S2, sT2>(P, sF2, oz2 + sN2, qr, xr, a.cdt2, qro2, xro2, gr);
         double Fa[6], FXa[NP], uga, pga, Fb[6], FXb[NP], ugb, pgb;
-        const bool shk2 = (RS == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false;
-        solve_face_r<M, N, NP, RS>(P, qlo1, qro1, xlo1, xro1, cl, cr, idx, Fa, uga, pga, FXa, shk2);
-        solve_face_r<M, N, NP, RS>(P, qlo2, qro2, xlo2, xro2, cl, cr, idx, Fb, ugb, pgb, FXb, shk2);
+        const bool shk2 = (rs_kind(RS) == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false;
+        solve_face_r<M, N, NP, RS>(P, qlo1, qro1, xlo1, xro1, cl, cr, idx, Fa, uga, pga, FXa, shk2, gl, gr);
+        solve_face_r<M, N, NP, RS>(P, qlo2, qro2, xlo2, xro2, cl, cr, idx, Fb, ugb, pgb, FXb, shk2, gl, gr);
         const long o1 = a.Fo1.idx(c.i, c.j, c.k), o2 = a.Fo2.idx(c.i, c.j, c.k);
 #pragma unroll
         for (int n = 0; n < FX_EINT; ++n) { a.Fo1.at(o1, n) = Fa[n]; a.Fo2.at(o2, n) = Fb[n]; }
@@ -390,9 +400,9 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
         constexpr int sN = L::F1T::stride(N), sT = L::F1T::stride(T1);
         const int oz = L::F1T::off(c.tx + pg, c.ty, c.tz);
         double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
-        trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
-        trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
-        solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX, (RS == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false);
+        trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo, gl);
+        trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro, gr);
+        solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX, (rs_kind(RS) == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false, gl, gr);
         const long o = a.Fo1.idx(c.i, c.j, c.k);
 #pragma unroll
         for (int n = 0; n < FX_EINT; ++n) a.Fo1.at(o, n) = F[n];      // F(rho e) is not stored (SplitFluxTile)
@@ -405,9 +415,9 @@ __device__ __forceinline__ void trans2_body(const DevPar& P, const Trans2Args& a
         constexpr int sN = L::F2T::stride(N), sT = L::F2T::stride(T2);
         const int oz = L::F2T::off(c.tx + pg, c.ty, c.tz);
         double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
-        trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
-        trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
-        solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX, (RS == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false);
+        trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo, gl);
+        trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro, gr);
+        solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX, (rs_kind(RS) == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false, gl, gr);
         const long o = a.Fo2.idx(c.i, c.j, c.k);
 #pragma unroll
         for (int n = 0; n < FX_EINT; ++n) a.Fo2.at(o, n) = F[n];      // F(rho e) is not stored (SplitFluxTile)
@@ -424,7 +434,7 @@ k_trans2_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __g
              const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f1b, const __grid_constant__ CUtensorMap m_f2,
              const __grid_constant__ CUtensorMap m_f2b, const __grid_constant__ CUtensorMap m_c,
              const Trans2Args a, const TileGrid tg) {
-    using L = Trans2Smem<N, NP>;
+    using L = Trans2Smem<N, NP, rs_ek(RS)>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
     CTU_PT_BEGIN
@@ -562,8 +572,8 @@ k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const
         if (in1) {
             constexpr int sN = L::F1T::stride(N), sT = L::F1T::stride(L::T1);
             const int oz = L::F1T::off(c.tx + pg, c.ty, c.tz);
-            trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo);
-            trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro);
+            trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz, ql, xl, a.cdt1, qlo, xlo, P.gamma);
+            trans_single_side<M, NP, typename L::S1, sT>(P, sF1, oz + sN, qr, xr, a.cdt1, qro, xro, P.gamma);
         }
         __syncthreads();                                  // group 1 is in registers everywhere: its buffers take the next tile
         if (threadIdx.x == 0) {
@@ -585,8 +595,8 @@ k_trans2_persist(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const
         if (in2) {
             constexpr int sN = L::F2T::stride(N), sT = L::F2T::stride(L::T2);
             const int oz = L::F2T::off(c.tx + pg, c.ty, c.tz);
-            trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo);
-            trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro);
+            trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz, ql, xl, a.cdt2, qlo, xlo, P.gamma);
+            trans_single_side<M, NP, typename L::S2, sT>(P, sF2, oz + sN, qr, xr, a.cdt2, qro, xro, P.gamma);
         }
         __syncthreads();
         if (threadIdx.x == 0 && tn < ntiles) issue2(tn);
@@ -652,7 +662,7 @@ k_trans2_replay(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const 
 // ------------------------------------------------------------------------------------------------
 // k_final_tma
 // ------------------------------------------------------------------------------------------------
-template <int N, int NP>
+template <int N, int NP, int EK = 0>
 struct FinalSmem {
     static constexpr int T1 = (N == 0) ? 1 : 0, T2 = (N == 2) ? 1 : 2;
     static constexpr int NIS = IS_X + NP, NFX = FX_X + NP;
@@ -663,7 +673,7 @@ struct FinalSmem {
     using S1 = SplitFluxTile<F1T, NFX>;
     using S2 = SplitFluxTile<F2T, NFX>;
     static constexpr size_t B_Q = (size_t)NIS * FaceTile::ZONES * 8, B_F1 = S1::BYTES, B_F2 = S2::BYTES,
-                            B_C = (size_t)CT::ZONES * 8, B_D = (size_t)DT::ZONES * 8;
+                            B_C = (size_t)(1 + EK) * CT::ZONES * 8, B_D = (size_t)DT::ZONES * 8;
     static constexpr size_t B_QS = CTU_Q_LDG ? 0 : B_Q;
     static constexpr size_t O_QM = 0, O_QP = al128(O_QM + B_QS), O_F1 = al128(O_QP + B_QS), O_F2 = al128(O_F1 + B_F1),
                             O_C = al128(O_F2 + B_F2), O_D = al128(O_C + B_C), O_BAR = al128(O_D + B_D), TOTAL = O_BAR + 128;
@@ -684,7 +694,8 @@ template <class M, int N, int NP, int RS = 0>
 __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, const unsigned char* smem, const TileCtx& c, const bool active,
                                            const int pf, const int pg, const int pq, const double* dU, const double* dUX, const double* gql,
                                            const double* gqr, const double* gxl, const double* gxr) {
-    using L = FinalSmem<N, NP>;
+    constexpr int EK = rs_ek(RS);
+    using L = FinalSmem<N, NP, EK>;
     constexpr int T1 = L::T1, T2 = L::T2;
     if (!active) return;
     const typename L::S1 sF1(smem + L::O_F1);
@@ -707,13 +718,14 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
 #endif
     const int oc = L::CT::off(c.tx + pq, c.ty, c.tz);
     const double cl = sC(oc, 0), cr = sC(oc + L::CT::stride(N), 0);
+    const double gl = EK ? sC(oc, EK) : P.gamma, gr = EK ? sC(oc + L::CT::stride(N), EK) : P.gamma;      // Gamma_1 of the zones left / right of the face
     const int idx = (N == 0) ? c.i : (N == 1) ? c.j : c.k;
     constexpr int s1N = L::F1T::stride(N), s1T = L::F1T::stride(T1), s2N = L::F2T::stride(N), s2T = L::F2T::stride(T2);
     const int o1 = L::F1T::off(c.tx + pg, c.ty, c.tz), o2 = L::F2T::off(c.tx + pg, c.ty, c.tz);
     double qlo[6], qro[6], xlo[NP], xro[NP], F[6], FX[NP], ugd, pgd;
-    trans_final_side<M, NP, typename L::S1, s1T, typename L::S2, s2T>(P, sF1, o1, sF2, o2, ql, xl, a.c1, a.c2, qlo, xlo);
-    trans_final_side<M, NP, typename L::S1, s1T, typename L::S2, s2T>(P, sF1, o1 + s1N, sF2, o2 + s2N, qr, xr, a.c1, a.c2, qro, xro);
-    solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX, (RS == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false);
+    trans_final_side<M, NP, typename L::S1, s1T, typename L::S2, s2T>(P, sF1, o1, sF2, o2, ql, xl, a.c1, a.c2, qlo, xlo, gl);
+    trans_final_side<M, NP, typename L::S1, s1T, typename L::S2, s2T>(P, sF1, o1 + s1N, sF2, o2 + s2N, qr, xr, a.c1, a.c2, qro, xro, gr);
+    solve_face_r<M, N, NP, RS>(P, qlo, qro, xlo, xro, cl, cr, idx, F, ugd, pgd, FX, (rs_kind(RS) == 2) ? face_shocked<N>(P, a.fd, c.i, c.j, c.k) : false, gl, gr);
 
     // apply_av (advection_util.cpp:354-419): div1 = difmag * min(0, <div u> over the 4 nodes of the face)
     const int od = L::DT::off(c.tx + pf, c.ty, c.tz);
@@ -731,7 +743,7 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
     // neighbour can be drained below 1.1 * small_dens even if all six of its faces evacuate it
     double lf = 1.0;
     bool limited = false;
-    if (RS == 2) {
+    if (rs_kind(RS) == 2) {
         if (P.limit_fluxes_on_small_dens == 1) {
             const double density_floor = P.small_dens * 1.1;
             const double vol = P.dx[0] * P.dx[1] * P.dx[2];
@@ -751,7 +763,7 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
     }
 #pragma unroll
     for (int n = 0; n < 6; ++n) {
-        if (RS == 2 && limited) F[n] = F[n] * lf;
+        if (rs_kind(RS) == 2 && limited) F[n] = F[n] * lf;
         a.Fo.at(o, n) = F[n];
     }
     a.Fo.at(o, FX_UG) = ugd;
@@ -762,7 +774,7 @@ __device__ __forceinline__ void final_body(const DevPar& P, const FinalArgs& a, 
     for (int ip = 0; ip < NP; ++ip) {
         const double div_var = div1 * dUX[ip];
         FX[ip] += dL * div_var;
-        if (RS == 2 && limited) FX[ip] = FX[ip] * lf;
+        if (rs_kind(RS) == 2 && limited) FX[ip] = FX[ip] * lf;
         if (is_species<NP>(P, ip)) sum += FX[ip];
     }
     double fac = 1.0;
@@ -777,7 +789,7 @@ k_final_tma(const DevPar P, const __grid_constant__ CUtensorMap m_qm, const __gr
             const __grid_constant__ CUtensorMap m_f1, const __grid_constant__ CUtensorMap m_f1b, const __grid_constant__ CUtensorMap m_f2,
              const __grid_constant__ CUtensorMap m_f2b, const __grid_constant__ CUtensorMap m_c,
             const __grid_constant__ CUtensorMap m_d, const FinalArgs a, const TileGrid tg) {
-    using L = FinalSmem<N, NP>;
+    using L = FinalSmem<N, NP, rs_ek(RS)>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
     CTU_PT_BEGIN
@@ -888,8 +900,8 @@ struct UpdateSmem {
     static constexpr unsigned TX_BYTES = (unsigned)(B_0 + B_1 + B_2);
 };
 
-template <int NP>
-static __global__ void __launch_bounds__(UTTHR, 3)
+template <int NP, int EK = 0>
+static __global__ void __launch_bounds__(UTTHR, EK ? 2 : 3)
 k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __grid_constant__ CUtensorMap m_f1,
              const __grid_constant__ CUtensorMap m_f2, const A4 Sb, const A4 Sin, const A4 Sn, const UpdateArgs a, const int ilo0,
              const int ilo1, const int ilo2, const TileGrid tg, const double dt) {
@@ -960,11 +972,11 @@ k_update_tma(const DevPar P, const __grid_constant__ CUtensorMap m_f0, const __g
             }
         }
         for (int cc = 0; cc < a.n_clean; ++cc) {
-            const int nf = clean_zone(P, u, Sn, on);
+            const int nf = clean_zone<EK>(P, u, Sn, on);
             if (nf) atomicAdd(&a.counters[2], nf);
-            if (cc == 0 && a.want_dt) dt0 = estdt_zone(P, u, Sn, on);
+            if (cc == 0 && a.want_dt) dt0 = estdt_zone<EK>(P, u, Sn, on);
         }
-        if (a.want_dt) dt1 = (a.n_clean == 1) ? dt0 : estdt_zone(P, u, Sn, on);
+        if (a.want_dt) dt1 = (a.n_clean == 1) ? dt0 : estdt_zone<EK>(P, u, Sn, on);
         if (a.n_clean == 0) dt0 = dt1;
         bool nan = false;
 #pragma unroll
@@ -1030,7 +1042,8 @@ struct TraceRiemannArgs {
 //   state on the high face (rho u v w p rhoe), xp/xm the passives.
 //   REC = 2: the hydrostatic-pressure-aware reconstructions (castro.use_pslope / castro.ppm_well_balanced; ppm_reconstruct_pslope,
 //   ppm.H:171-244 + trace_ppm.cpp:248-267,490): sb = &srcq(zone, comp 0) with strides ssn / sst (nullptr without sources).
-template <class M, int DIR, int NP, bool SRC, int REC = 0>
+//   EK = 1 (Helmholtz EOS): Gamma_1 varies from zone to zone and is reconstructed and traced like the reference does (trace_ppm.cpp:221-232).
+template <class M, int DIR, int NP, bool SRC, int REC = 0, int EK = 0>
 __device__ __forceinline__ void trace_core(const DevPar& P, const double* __restrict__ base, const int sn, const int st, const double flat,
                                            const double dtdL, double* __restrict__ op, double* __restrict__ om, double* __restrict__ xp,
                                            double* __restrict__ xm, const SrcAdd& sa, const double* __restrict__ sb = nullptr,
@@ -1116,7 +1129,12 @@ __device__ __forceinline__ void trace_core(const DevPar& P, const double* __rest
     CTU_RECON(QUTT);
     pb.integ(un, dtdL, Ip_utt, Im_utt);
     // gamma-law EOS: PPM of a spatially constant Gamma_1 returns the constant exactly (see trace_dir)
-    const double Ip_gc2 = P.gamma, Im_gc0 = P.gamma;
+    double Ip_gc2 = P.gamma, Im_gc0 = P.gamma;
+    if constexpr (EK == 1) {
+        CTU_RECON(QS_GAMC);
+        pb.integ(un - cc, dtdL, dum, Im_gc0);
+        pb.integ(un + cc, dtdL, Ip_gc2, dum);
+    }
     // passives (trace_ppm.cpp:443-485)
 #pragma unroll
     for (int ip = 0; ip < NP; ++ip) {
@@ -1368,7 +1386,7 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
             SrcAdd sa;
             if (SRC)     // traced source terms (trace_ppm.cpp:309-440)
                 trace_sources<D>(P, sb, a.srcq.sn, sst, flat, sq0[(QS_U + D) * QT::ZONES], sq0[QS_C * QT::ZONES], a.dtdL, a.hdt, sa, *a.src_mask);
-            trace_core<M, D, NP, SRC, REC>(P, sq0, QT::ZONES, QT::stride(D), flat, a.dtdL, qp_own, qm_nxt, xp_own, xm_nxt, sa, sb, a.srcq.sn, sst);
+            trace_core<M, D, NP, SRC, REC, rs_ek(RS)>(P, sq0, QT::ZONES, QT::stride(D), flat, a.dtdL, qp_own, qm_nxt, xp_own, xm_nxt, sa, sb, a.srcq.sn, sst);
         }
         // hand the minus state to the thread that owns the high face
 #pragma unroll
@@ -1441,8 +1459,9 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
     const double* sq = reinterpret_cast<const double*>(smem + L::O_Q);
     const int oq = QT::off(tx + pq + (D == 0 ? 2 : 0), ty + (D == 1 ? 2 : 0), tz + (D == 2 ? 2 : 0));
     const double cr = sq[QS_C * QT::ZONES + oq], cl = sq[QS_C * QT::ZONES + oq - QT::stride(D)];
+    const double gcr = rs_ek(RS) ? sq[QS_GAMC * QT::ZONES + oq] : 0.0, gcl = rs_ek(RS) ? sq[QS_GAMC * QT::ZONES + oq - QT::stride(D)] : 0.0;
     double F[6], FX[NP], ugd, pgd;
-    solve_face_r<M, D, NP, RS>(P, ql, qr, xl, xr, cl, cr, idx, F, ugd, pgd, FX, (RS == 2) ? face_shocked<D>(P, a.fd, i, j, k) : false);
+    solve_face_r<M, D, NP, RS>(P, ql, qr, xl, xr, cl, cr, idx, F, ugd, pgd, FX, (rs_kind(RS) == 2) ? face_shocked<D>(P, a.fd, i, j, k) : false, gcl, gcr);
     const long of = a.Fo.idx(i, j, k);
 #pragma unroll
     for (int n = 0; n < FX_EINT; ++n) a.Fo.at(of, n) = F[n];      // F(rho e) is not stored (SplitFluxTile)
@@ -1453,7 +1472,7 @@ __device__ __forceinline__ void trace_riemann_body(const DevPar& P, const TraceR
 }
 
 template <int D, int NP, bool SRC, int RS = 0, int REC = 0>
-static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, SRC ? CTU_TRACE_MINB_SRC : ((NP >= 3 || RS == 1) ? CTU_TRACE_MINB_NP3 : CTU_TRACE_MINB))
+static __global__ void __launch_bounds__(TraceSmem<D, NP>::NTHR, SRC ? CTU_TRACE_MINB_SRC : ((NP >= 3 || rs_kind(RS) == 1 || rs_ek(RS)) ? CTU_TRACE_MINB_NP3 : CTU_TRACE_MINB))
 k_trace_riemann_tma(const DevPar P, const __grid_constant__ CUtensorMap m_q, const TraceRiemannArgs a) {
     using L = TraceSmem<D, NP>;
     using TT = TrTile<D>;

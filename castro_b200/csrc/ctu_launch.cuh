@@ -47,7 +47,7 @@ int set_smem(K kernel, size_t bytes) {
 template <int N, int NP, int RS = 0>
 int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
                   const Box3* nb, const double* cdtd, cudaStream_t st) {
-    using L = Trans2Smem<N, NP>;
+    using L = Trans2Smem<N, NP, rs_ek(RS)>;
     constexpr int T1 = L::T1, T2 = L::T2;
     static bool attr = false;
     if (!attr) { int rc = set_smem(k_trans2_tma<N, NP, RS>, L::TOTAL); if (rc) return rc; attr = true; }
@@ -57,7 +57,7 @@ int launch_trans2(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3
     CTU_MAP(m_f1b, F1[T1], ibx, L::NFX, L::F1T, L::S1::NB)
     CTU_MAP(m_f2, F1[T2], ibx, L::NFX, L::F2T, L::S2::NA)
     CTU_MAP(m_f2b, F1[T2], ibx, L::NFX, L::F2T, L::S2::NB)
-    CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
+    CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, L::NC)      // c and, for the Helmholtz instances, Gamma_1
     Trans2Args a;
     a.qm = ta.qm[N]; a.qp = ta.qp[N];
     a.Fo1 = F2[N][T1]; a.Fo2 = F2[N][T2];
@@ -102,9 +102,35 @@ int launch_trans2_ext_np(const DevPar& P, const TraceArgs& ta, const A4& qs, con
     return rc;
 }
 
+// Helmholtz EOS (eos_kind = 1; Gamma_1 varies from zone to zone): instantiations RS = 4 (CGF / HLLC) and RS = 5 (Colella & Glaz) of the
+// flux-stage kernels, which stage Gamma_1 beside the sound speed, and the EK = 1 update kernel; plain PPM, up to CTU_TMA_HELM_MAX_NP
+// passive scalars, in their own translation units (ctu_helm1 .. 5.cu)
+#ifndef CTU_TMA_HELM_MAX_NP
+#define CTU_TMA_HELM_MAX_NP 5
+#endif
+template <int NP>
+int launch_trans2_helm_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
+                          const Box3* nb, const double* cdtd, cudaStream_t st) {
+    int rc;
+    if (P.riemann_solver == 1) {
+        rc = launch_trans2<0, NP, 5>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+        if (!rc) rc = launch_trans2<1, NP, 5>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+        if (!rc) rc = launch_trans2<2, NP, 5>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    } else {
+        rc = launch_trans2<0, NP, 4>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+        if (!rc) rc = launch_trans2<1, NP, 4>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+        if (!rc) rc = launch_trans2<2, NP, 4>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+    }
+    return rc;
+}
+
 template <int NP>
 int launch_trans2_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4* F1, A4 (*F2)[3],
                      const Box3* nb, const double* cdtd, cudaStream_t st) {
+    if (P.eos_kind == 1) {
+        if constexpr (NP <= CTU_TMA_HELM_MAX_NP) return launch_trans2_helm_np<NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
+        else return CTU_ERR_UNSUPPORTED;
+    }
     if (ext_on(P)) {
         if constexpr (NP <= CTU_TMA_EXT_MAX_NP) return launch_trans2_ext_np<NP>(P, ta, qs, qbx_a, ibx, F1, F2, nb, cdtd, st);
         else return CTU_ERR_UNSUPPORTED;
@@ -196,8 +222,28 @@ int launch_trace_riemann_ext_np(const DevPar& P, const TraceArgs& ta, const A4& 
 }
 
 template <int NP, bool SRC>
+int launch_trace_riemann_helm_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
+                                 const Box3& tb, double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
+    int rc;
+    if (P.riemann_solver == 1) {
+        rc = launch_trace_riemann<0, NP, SRC, 5>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+        if (!rc) rc = launch_trace_riemann<1, NP, SRC, 5>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+        if (!rc) rc = launch_trace_riemann<2, NP, SRC, 5>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    } else {
+        rc = launch_trace_riemann<0, NP, SRC, 4>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+        if (!rc) rc = launch_trace_riemann<1, NP, SRC, 4>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+        if (!rc) rc = launch_trace_riemann<2, NP, SRC, 4>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+    }
+    return rc;
+}
+
+template <int NP, bool SRC>
 int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const A4& fd, const A4* F1,
                             const Box3& tb, double dt, const A4& srcq, const int* src_mask, cudaStream_t st) {
+    if (P.eos_kind == 1) {
+        if constexpr (NP <= CTU_TMA_HELM_MAX_NP) return launch_trace_riemann_helm_np<NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
+        else return CTU_ERR_UNSUPPORTED;
+    }
     if (ext_on(P)) {
         if constexpr (NP <= CTU_TMA_EXT_MAX_NP) return launch_trace_riemann_ext_np<NP, SRC>(P, ta, qs, qbx_a, fd, F1, tb, dt, srcq, src_mask, st);
         else return CTU_ERR_UNSUPPORTED;
@@ -222,7 +268,7 @@ int launch_trace_riemann_np(const DevPar& P, const TraceArgs& ta, const A4& qs, 
 template <int N, int NP, int RS = 0>
 int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
                  const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
-    using L = FinalSmem<N, NP>;
+    using L = FinalSmem<N, NP, rs_ek(RS)>;
     constexpr int T1 = L::T1, T2 = L::T2;
     static bool attr = false;
     if (!attr) { int rc = set_smem(k_final_tma<N, NP, RS>, L::TOTAL); if (rc) return rc; attr = true; }
@@ -232,7 +278,7 @@ int launch_final(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3&
     CTU_MAP(m_f1b, F2[T1][T2], ibx, L::NFX, L::F1T, L::S1::NB)
     CTU_MAP(m_f2, F2[T2][T1], ibx, L::NFX, L::F2T, L::S2::NA)
     CTU_MAP(m_f2b, F2[T2][T1], ibx, L::NFX, L::F2T, L::S2::NB)
-    CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1)
+    CTU_MAP(m_c, qs, qbx_a, QS_X + NP, L::CT, 1 + rs_ek(RS))
     CTU_MAP(m_d, fd, ibx, 2, L::DT, 1)
     FinalArgs a;
     a.qm = ta.qm[N]; a.qp = ta.qp[N];
@@ -254,8 +300,28 @@ int launch_final_ext_np(const DevPar& P, const TraceArgs& ta, const A4& qs, cons
 }
 
 template <int NP>
+int launch_final_helm_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
+                         const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
+    int rc;
+    if (P.riemann_solver == 1) {
+        rc = launch_final<0, NP, 5>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+        if (!rc) rc = launch_final<1, NP, 5>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+        if (!rc) rc = launch_final<2, NP, 5>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    } else {
+        rc = launch_final<0, NP, 4>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+        if (!rc) rc = launch_final<1, NP, 4>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+        if (!rc) rc = launch_final<2, NP, 4>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+    }
+    return rc;
+}
+
+template <int NP>
 int launch_final_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Box3& qbx_a, const Box3& ibx, const A4& fd, const A4& Sb,
                     const A4* F1, A4 (*F2)[3], const Box3* nb, const double* hdtd, cudaStream_t st) {
+    if (P.eos_kind == 1) {
+        if constexpr (NP <= CTU_TMA_HELM_MAX_NP) return launch_final_helm_np<NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
+        else return CTU_ERR_UNSUPPORTED;
+    }
     if (ext_on(P)) {
         if constexpr (NP <= CTU_TMA_EXT_MAX_NP) return launch_final_ext_np<NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
         else return CTU_ERR_UNSUPPORTED;
@@ -273,18 +339,32 @@ int launch_final_np(const DevPar& P, const TraceArgs& ta, const A4& qs, const Bo
     if (!rc) rc = launch_final<2, NP>(P, ta, qs, qbx_a, ibx, fd, Sb, F1, F2, nb, hdtd, st);
     return rc;
 }
-template <int NP>
-int launch_update_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,
-                     const Box3& tb, double dt, cudaStream_t st) {
+template <int NP, int EK>
+int launch_update_impl(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,
+                       const Box3& tb, double dt, cudaStream_t st) {
     using L = UpdateSmem<NP>;
     static bool attr = false;
-    if (!attr) { int rc = set_smem(k_update_tma<NP>, L::TOTAL); if (rc) return rc; attr = true; }
+    if (!attr) { int rc = set_smem(k_update_tma<NP, EK>, L::TOTAL); if (rc) return rc; attr = true; }
     CTU_MAP(m_f0, F[0], ibx, L::NFX, L::F0T, L::NFX)
     CTU_MAP(m_f1, F[1], ibx, L::NFX, L::F1T, L::NFX)
     CTU_MAP(m_f2, F[2], ibx, L::NFX, L::F2T, L::NFX)
     const TileGrid tg = make_tg_t<UTY, UTZ>(tb);
-    k_update_tma<NP><<<tg_blocks(tg), UTTHR, L::TOTAL, st>>>(P, m_f0, m_f1, m_f2, Sb, Sin, Sn, ua, ibx.lo[0], ibx.lo[1], ibx.lo[2], tg, dt);
+    k_update_tma<NP, EK><<<tg_blocks(tg), UTTHR, L::TOTAL, st>>>(P, m_f0, m_f1, m_f2, Sb, Sin, Sn, ua, ibx.lo[0], ibx.lo[1], ibx.lo[2], tg, dt);
     return 0;
+}
+template <int NP>
+int launch_update_helm_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,
+                          const Box3& tb, double dt, cudaStream_t st) {
+    return launch_update_impl<NP, 1>(P, F, ibx, Sb, Sin, Sn, ua, tb, dt, st);
+}
+template <int NP>
+int launch_update_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb, const A4& Sin, const A4& Sn, const UpdateArgs& ua,
+                     const Box3& tb, double dt, cudaStream_t st) {
+    if (P.eos_kind == 1) {
+        if constexpr (NP <= CTU_TMA_HELM_MAX_NP) return launch_update_helm_np<NP>(P, F, ibx, Sb, Sin, Sn, ua, tb, dt, st);
+        else return CTU_ERR_UNSUPPORTED;
+    }
+    return launch_update_impl<NP, 0>(P, F, ibx, Sb, Sin, Sn, ua, tb, dt, st);
 }
 
 }  // namespace ctu
@@ -320,6 +400,30 @@ int launch_update_np(const DevPar& P, const A4* F, const Box3& ibx, const A4& Sb
     KW template int ctu::launch_final_ext_np<N>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&,            \
                                                 const ctu::Box3&, const ctu::A4&, const ctu::A4&, const ctu::A4*, ctu::A4 (*)[3],       \
                                                 const ctu::Box3*, const double*, cudaStream_t);
+// explicit instantiation of the Helmholtz-EOS launchers (definition in ctu_helmN.cu, declaration everywhere else)
+#define CTU_INSTANTIATE_HELM(KW, N)                                                                                                    \
+    KW template int ctu::launch_trans2_helm_np<N>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&,          \
+                                                  const ctu::Box3&, const ctu::A4*, ctu::A4 (*)[3], const ctu::Box3*, const double*,    \
+                                                  cudaStream_t);                                                                       \
+    KW template int ctu::launch_trace_riemann_helm_np<N, true>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&,               \
+                                                               const ctu::Box3&, const ctu::A4&, const ctu::A4*, const ctu::Box3&,      \
+                                                               double, const ctu::A4&, const int*, cudaStream_t);                      \
+    KW template int ctu::launch_trace_riemann_helm_np<N, false>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&,              \
+                                                                const ctu::Box3&, const ctu::A4&, const ctu::A4*, const ctu::Box3&,     \
+                                                                double, const ctu::A4&, const int*, cudaStream_t);                     \
+    KW template int ctu::launch_final_helm_np<N>(const ctu::DevPar&, const ctu::TraceArgs&, const ctu::A4&, const ctu::Box3&,           \
+                                                 const ctu::Box3&, const ctu::A4&, const ctu::A4&, const ctu::A4*, ctu::A4 (*)[3],      \
+                                                 const ctu::Box3*, const double*, cudaStream_t);                                       \
+    KW template int ctu::launch_update_helm_np<N>(const ctu::DevPar&, const ctu::A4*, const ctu::Box3&, const ctu::A4&,                 \
+                                                  const ctu::A4&, const ctu::A4&, const ctu::UpdateArgs&, const ctu::Box3&, double,     \
+                                                  cudaStream_t);
+#ifndef CTU_HELM_TU
+CTU_INSTANTIATE_HELM(extern, 1)
+CTU_INSTANTIATE_HELM(extern, 2)
+CTU_INSTANTIATE_HELM(extern, 3)
+CTU_INSTANTIATE_HELM(extern, 4)
+CTU_INSTANTIATE_HELM(extern, 5)
+#endif
 #ifndef CTU_EXT_TU
 CTU_INSTANTIATE_EXT(extern, 1)
 CTU_INSTANTIATE_EXT(extern, 2)

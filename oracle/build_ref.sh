@@ -47,6 +47,7 @@ build() {  # $1 = problem dir name, $2 = output name, rest = make args
   ( cd "$d" && make CASTRO_HOME="$REF" USE_MPI=FALSE "$@" -j"$J" >build.log 2>&1 ) || { tail -30 "$d/build.log"; exit 1; }
   local exe; exe=$(ls -t "$d"/Castro*.ex | head -1)
   cp "$exe" "$OUT/$out.ex"
+  case "$out" in *_cuda|*_stub) strip "$OUT/$out.ex" ;; esac      # symbol tables only (31 MB each): the gpurun snapshot is limited to 512 MiB
   echo "built $OUT/$out.ex"
 }
 

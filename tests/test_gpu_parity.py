@@ -729,6 +729,56 @@ def test_helmholtz_eos_sod_stellar_matches_reference(name):
     sim.close()
 
 
+def test_helmholtz_tile_staged_kernels_match_register_staged_bitwise(tmp_path):
+    """The Helmholtz-EOS instances of the tile-staged kernels (Gamma_1 staged beside the sound speed, reconstructed and traced; RS = 4:
+    CGF / HLLC, RS = 5: Colella & Glaz; EK = 1 update kernel) against the register-staged family (CTU_NO_TMA=1, a subprocess because the
+    switch is read once per process), which test_helmholtz_eos_sod_stellar_matches_reference pins to the reference: the same device
+    arithmetic in the same order, so the two families agree bit for bit -- with and without gravity, tube along x, y and z."""
+    import os
+    import subprocess
+    import sys
+    _torch()
+    from castro_b200 import lib
+    from cases import load_sodstellar_case, HELM_TABLE
+    if not os.path.exists(HELM_TABLE):
+        pytest.skip("oracle/_ref/helm_table.dat missing")
+    names = ["sodstellar_x_cg", "sodstellar_x_cgf", "sodstellar_y_hllc", "sodstellar_z_cgf", "sodstellar_z_grav_cgf", "sodstellar_x_grav_hllc_gst2"]
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from cases import load_sodstellar_case, HELM_TABLE\n"
+        "from castro_b200 import lib\n"
+        "lib.helm_load(HELM_TABLE)\n"
+        "out = {}\n"
+        "for name in %r:\n"
+        "    par, geom, prob, g, snaps = load_sodstellar_case(name)\n"
+        "    lib.params_finalize(par)\n"
+        "    n = tuple(int(x) for x in g['n_cell'])\n"
+        "    sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in n))\n"
+        "    sim.init_problem('Sod', prob)\n"
+        "    rc, t, dt, hist = sim.advance(snaps[-1])\n"
+        "    assert rc == 0 and not sim.tile_staged\n"
+        "    out[name] = sim.download(); out[name + '_dt'] = np.array(hist)\n"
+        "np.savez(%r, **out)\n"
+        "print('ok')\n") % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))), names,
+                            str(tmp_path / "reg.npz"))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CTU_NO_TMA="1"), capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+    reg = np.load(str(tmp_path / "reg.npz"))
+    lib.helm_load(HELM_TABLE)
+    for name in names:
+        par, geom, prob, g, snaps = load_sodstellar_case(name)
+        lib.params_finalize(par)
+        n = tuple(int(x) for x in g["n_cell"])
+        sim = lib.Sim(par, geom, (0, 0, 0), tuple(x - 1 for x in n))
+        sim.init_problem("Sod", prob)
+        rc, t, dt, hist = sim.advance(snaps[-1])
+        assert rc == 0 and sim.tile_staged, name
+        assert np.array_equal(np.array(hist), reg[name + "_dt"]), name
+        assert_bitwise(sim.download(), reg[name], name + " tile-staged vs register-staged")
+        sim.close()
+
+
 def test_helmholtz_eos_device_matches_host_and_reference_values():
     """the device copy of the Helmholtz EOS against its host copy on a sweep of (rho, T) over the table (1e-12 relative) and round
     trips through the Newton modes (rho, e) and (rho, p)"""

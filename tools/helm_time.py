@@ -57,7 +57,9 @@ def main():
     assert rc == 0
     ms = e0.elapsed_time(e1) / args.steps
     st = lib.workspace_stage_times(ws, reset=True)
-    print(json.dumps({"n": n, "eos": "gamma" if args.gamma else "helmholtz", "solver": args.solver, "grav": args.grav,
+    import hashlib
+    sha = hashlib.sha256(sim.download().tobytes()).hexdigest()[:16]
+    print(json.dumps({"n": n, "state_sha256": sha, "eos": "gamma" if args.gamma else "helmholtz", "solver": args.solver, "grav": args.grav,
                       "tile_staged": bool(sim.tile_staged), "no_tma_env": os.environ.get("CTU_NO_TMA", ""),
                       "ms_per_step": ms, "zones_per_s": n ** 3 / (ms * 1e-3),
                       "kernels_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in st.items() if v[1]}}))
