@@ -200,7 +200,9 @@ bool fab_covers(const ctu_fab_t* f, const Box3& b) {
 }  // namespace ctu
 
 
-// ---- launchers of the TMA-staged kernels (ctu_launch.cuh); NP = 3, 4, 5 are compiled in their own translation units ------
+// ---- launchers of the TMA-staged kernels (ctu_launch.cuh); every passive count is compiled in its own translation unit (ctu_npN.cu) ------
+CTU_INSTANTIATE_NP(extern, 1)
+CTU_INSTANTIATE_NP(extern, 2)
 CTU_INSTANTIATE_NP(extern, 3)
 CTU_INSTANTIATE_NP(extern, 4)
 CTU_INSTANTIATE_NP(extern, 5)

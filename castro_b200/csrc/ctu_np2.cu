@@ -1,0 +1,3 @@
+// tile-staged kernels for 2 passive scalar(s) (see ctu_launch.cuh)
+#include "ctu_launch.cuh"
+CTU_INSTANTIATE_NP(, 2)
