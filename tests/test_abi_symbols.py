@@ -130,3 +130,16 @@ def test_parse_inputs_dimensionality_and_coordinates(tmp_path):
     assert g.dim == 1 and g.coord == 2 and nc == (32, 1, 1) and g.dx[0] == 1.0 / 32
     p, g, nc, ms, stop, prob = lib.parse_inputs(os.path.join(ROOT, "bench_inputs", "inputs.sedov3d"))
     assert g.dim == 3 and g.coord == 0
+
+
+def test_every_translation_unit_is_in_the_makefile():
+    """the library is built from one translation unit per option family and passive count (ctu_np*, ctu_rec*, ctu_ext*, ctu_helm*):
+    every .cu file of castro_b200/csrc must be listed in the Makefile's SRCS (the launchers declare their instantiations `extern`, so a
+    forgotten unit would only show up as an unresolved symbol when the library is loaded)."""
+    import glob
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "castro_b200", "csrc")
+    mk = open(os.path.join(csrc, "Makefile")).read()
+    srcs = set(re.search(r"^SRCS := (.*)$", mk, re.M).group(1).split())
+    on_disk = {os.path.basename(f) for f in glob.glob(os.path.join(csrc, "*.cu"))}
+    assert on_disk == srcs, (sorted(on_disk - srcs), sorted(srcs - on_disk))
